@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Headline benchmark of the hot path: raw-signal samples/sec of the WaveNet forward pass.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): vanilla WaveNet,
+2 stacks x 10 dilations (1..512), 256 residual/skip channels, 256-way softmax, batch 32 x 16384 samples
+per GPU, bf16 forward.  Input: synthetic Gaussian pore-model signal (wavenet_speech_b200/utils/signal_gen.py),
+mu-law quantised to 256 levels and one-hot encoded, exactly what the reference feeds its WaveNet.
+
+One JSON line is printed by rank 0 (see the task contract): value = samples/s with inputs resident in HBM,
+e2e = the same through the module call with pinned HOST buffers (H2D of the input and D2H of the output inside
+the timed region), roofline = the fused residual-block kernel against the measured bf16 peak, cpu_baseline =
+the oracle (a CPU restatement of the reference's PyTorch modules) on this box's host cores.
+
+N > 1: one process per GPU (torchrun), the batch is sharded (each rank owns `batch` reads: weak scaling), no
+data-path collective exists for inference; value = all ranks' samples / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+WORKLOADS = {
+    # name: (in_dim, entry_k, dilations, C, out_dim, batch, T)
+    "wavenet_2x10_c256_b32_t16384": dict(in_dim=256, entry_k=2, dil=[1, 2, 4, 8, 16, 32, 64, 128, 256, 512] * 2,
+                                         C=256, batch=32, T=16384),
+    "wavenet_small": dict(in_dim=64, entry_k=2, dil=[1, 2, 4, 8], C=64, batch=2, T=2048),
+}
+DEFAULT_WORKLOAD = "wavenet_2x10_c256_b32_t16384"
+METRIC = "raw-signal samples/sec (WaveNet forward)"
+UNIT = "samples/s"
+
+
+def flops_per_timestep(w):
+    C, D = w["C"], w["in_dim"]
+    return 2 * w["entry_k"] * D * C + len(w["dil"]) * 16 * C * C + 4 * C * C
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_input(w, rank):
+    """(B, in_dim, T) one-hot of a mu-law quantised synthetic pore-model signal, as a pinned host bf16 tensor."""
+    from wavenet_speech_b200.utils import signal_gen as S
+    lev = S.quantized_batch(w["batch"], w["T"], num_levels=w["in_dim"], seed=1234 + rank)
+    lev = torch.from_numpy(lev)
+    x = torch.zeros((w["batch"], w["in_dim"], w["T"]), dtype=torch.bfloat16)
+    x.scatter_(1, lev.unsqueeze(1), 1.0)
+    return x.pin_memory() if torch.cuda.is_available() else x
+
+
+def build_model(w, softmax=True):
+    import wavenet_speech_b200 as W
+    torch.manual_seed(0)
+    layers = [(w["C"], w["C"], 2, d) for d in w["dil"]]
+    return W.WaveNet(w["in_dim"], w["entry_k"], layers, w["C"], softmax=softmax), layers
+
+
+def cpu_baseline(w, target_s=12.0, threads=None):
+    """Oracle (CPU restatement of the reference's PyTorch modules) on the host cores, bounded sample."""
+    from oracle import wavenet_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    net, layers = build_model(w)
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    D = w["in_dim"]
+
+    def run(B, T):
+        lev = torch.randint(0, D, (B, T))
+        x = torch.zeros(B, D, T).scatter_(1, lev.unsqueeze(1), 1.0)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            O.wavenet_forward(sd, x, layers, softmax=True)
+        return time.perf_counter() - t0
+
+    run(1, 1024)                                  # warm-up (thread pool, mkldnn primitives)
+    probe_T = 2048
+    dt = run(1, probe_T)
+    rate = probe_T / dt
+    T = int(min(w["T"], max(2048, rate * target_s / 2)))
+    B = 2 if rate * target_s >= 2 * T else 1
+    dt = min(run(B, T) for _ in range(2))
+    return {"value": B * T / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "oracle (torch CPU fp32 restatement of the reference modules), %d x %d samples, best of 2, "
+                      "%.2f s" % (B, T, dt)}
+
+
+def run_reference(args, w):
+    """--impl reference: the reference is Python/torch and cannot travel to the GPU box (and is not
+    pip-installable: it has no setup.py), so this arm times the oracle port of its CPU path."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import wavenet_oracle as O
+    threads = os.cpu_count()
+    torch.set_num_threads(threads)
+    net, layers = build_model(w)
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    D = w["in_dim"]
+    B, T = 1, min(w["T"], 4096)
+    lev = torch.randint(0, D, (B, T))
+    x = torch.zeros(B, D, T).scatter_(1, lev.unsqueeze(1), 1.0)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            O.wavenet_forward(sd, x, layers, softmax=True)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.wavenet_forward(sd, x, layers, softmax=True)
+        dt = time.perf_counter() - t0
+    val = B * T * args.steps / dt
+    sample = "oracle port, fp32, %d x %d samples per step (bounded sample of the %d x %d workload)" % (
+        B, T, w["batch"], w["T"])
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--T", type=int, default=None)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.batch:
+        w["batch"] = args.batch
+    if args.T:
+        w["T"] = args.T
+    if args.impl == "reference":
+        run_reference(args, w)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import wavenet_speech_b200 as W
+    from wavenet_speech_b200 import _lib
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    net, layers = build_model(w)
+    net = net.cuda().to(dtype).eval()
+    x_host = make_input(w, rank).to(dtype)
+    x_host = x_host.pin_memory()
+    x_dev = x_host.cuda(non_blocking=True)
+    samples = w["batch"] * w["T"]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing ----------------------------------------------------------------------
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            y = net(x_dev)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        l0 = _lib.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            y = net(x_dev)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        launches = _lib.launch_count - l0
+        clocks = sampler.stop()
+
+        # ---- end-to-end: pinned host input -> H2D -> forward -> D2H of the output ------------------------
+        e2e = None
+        if not args.no_e2e:
+            y_host = torch.empty(y.shape, dtype=y.dtype).pin_memory()
+            for _ in range(2):
+                xd = x_host.cuda(non_blocking=True)
+                y_host.copy_(net(xd), non_blocking=True)
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                xd = x_host.cuda(non_blocking=True)
+                y_host.copy_(net(xd), non_blocking=True)
+            e1.record()
+            barrier()
+            ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+            e2e = {"value": samples * world * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+                   "h2d_bytes_per_step": x_host.numel() * x_host.element_size(),
+                   "d2h_bytes_per_step": y_host.numel() * y_host.element_size(),
+                   "ms_per_step": ms_e2e / args.steps}
+
+        # ---- roofline of the dominant kernel: per-launch CUDA-event timing on the launching stream ------
+        _lib.kernel_timing(True)
+        for _ in range(2):
+            net(x_dev)
+        torch.cuda.synchronize()
+        log = _lib.kernel_timing(False)
+    per = {}
+    for name, a, b in log:
+        per.setdefault(name, []).append(a.elapsed_time(b))
+    peaks = load_peaks()
+    C = w["C"]
+    dom = "wnb200_resblock_fwd_tc" if "wnb200_resblock_fwd_tc" in per else "wnb200_taps_fwd"
+    tot = sum(sum(v) for v in per.values())
+    if dom == "wnb200_resblock_fwd_tc":
+        flops_launch = 16 * C * C * samples                        # block + bottleneck as written
+        avg_ms = float(np.mean(per[dom]))
+    else:                                                           # generic path: all contraction launches together
+        flops_launch = flops_per_timestep(w) * samples
+        avg_ms = float(sum(per[dom])) / 2.0
+    achieved = flops_launch / (avg_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
+                "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                "peak_source": peaks["source"] + " (bf16_tflops_sustained)",
+                "share_of_step": float(sum(per[dom])) / tot if tot > 0 else None,
+                "avg_launch_ms": avg_ms}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    cpu = None if args.no_cpu_baseline else cpu_baseline(w)
+    value = samples * world * args.steps / (ms * 1e-3)
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": args.workload, "batch_per_gpu": w["batch"], "T": w["T"], "channels": C,
+                   "layers": len(w["dil"]), "softmax": True, "sharding": "batch x%d" % world,
+                   "l2": "input %.0f MB and every inter-layer tensor exceed the 126 MB L2" % (
+                       x_dev.numel() * x_dev.element_size() / 1e6),
+                   "flop_per_sample": flops_per_timestep(w)},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "tflops": value * flops_per_timestep(w) / 1e12,
+    }
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

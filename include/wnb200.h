@@ -1,0 +1,128 @@
+/*
+ * wnb200.h -- C-ABI of the B200-native wavenet-speech hot path (libwnb200.so).
+ *
+ * The reference (paultsw/wavenet-speech) has no FFI layer: its hot path is a set of torch.nn
+ * modules (modules/conv_ops.py, block.py, wavenet.py, raw_ctcnet.py, classifier.py,
+ * layernorm.py, linear_conv_ops.py) that call ATen/cuDNN.  This header declares the entry points
+ * that stand where those library calls stood; each one cites the reference call site it replaces.
+ * The Python drop-in modules (wavenet_speech_b200/modules/*) are the only callers.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless it says "host"; the caller owns every buffer,
+ *     including workspaces; nothing is allocated, freed or synchronised in here;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - return 0 on success, non-zero on error; wnb200_last_error() gives the message (thread local);
+ *   - dtype: WNB200_F32 or WNB200_BF16 = storage type of activations AND weights; accumulation is
+ *     always fp32; gradients of parameters are always written as fp32;
+ *   - "NCL" = (batch, channels, time) with time contiguous (the reference's layout);
+ *     "NLC" = (batch, time, channels) with channels contiguous (the tensor-core path's layout);
+ *   - sm_100a only.  There is no CPU fallback and no other-arch fallback.
+ */
+#ifndef WNB200_H_
+#define WNB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WNB200_F32 0
+#define WNB200_BF16 1
+
+#define WNB200_EPI_NONE 0  /* y = acc + bias                                              */
+#define WNB200_EPI_LEAKY 1 /* y = LeakyReLU_0.01(acc + bias)   (wavenet.py:67-71)         */
+#define WNB200_EPI_GATE 2  /* y = tanh(acc_t + b_t) * sigmoid(acc_s + b_s) (block.py:185) */
+
+#define WNB200_MAX_SRC 4
+
+/* One (input tensor, weight slab, time offset) term of a tap-sum contraction. */
+typedef struct {
+  const void* x;        /* NCL activations [B, C, T_src] (strided)                        */
+  const void* w;        /* weight slab [rows, C] row-major, same dtype as x               */
+  int64_t batch_stride; /* elements between batch items of x                              */
+  int64_t chan_stride;  /* elements between channels of x (time stride is 1)              */
+  int32_t C;            /* channels contracted                                            */
+  int32_t T_src;        /* valid time extent of x; reads outside [0, T_src) give 0        */
+  int32_t t_off;        /* output frame t reads x[.., t + t_off]                          */
+  int32_t pre_act;      /* 1: LeakyReLU(0.01) applied to x as it is loaded, 0: none        */
+} wnb200_src_t;
+
+const char* wnb200_last_error(void);
+int wnb200_version(void);
+/* 0 if the current device is sm_100 (B200); error otherwise. */
+int wnb200_check_device(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Generic tap-sum contraction (any channel count, kernel width, dilation; fp32 FFMA math):
+ *     out[b, m, t] (+)= epi( bias[m] + sum_s sum_c w_s[m, c] * pre(x_s[b, c, t + t_off_s]) )
+ * Replaces nn.Conv1d + slice in CausalConv1d/NonCausalConv1d.forward (conv_ops.py:39-44, 74-79),
+ * the 1x1 convs and the nn.Linear residual projection with its two transposes (block.py:73-79,
+ * conv_ops.py:91-101), the skip bottlenecks (wavenet.py:100), the output stacks (wavenet.py:103)
+ * and LinearConv1d.linear (linear_conv_ops.py:39-68).
+ * EPI_GATE: weight rows/bias are packed per 64 output channels as [64 tanh rows; 64 sigmoid rows]
+ * (2*ceil(M/64)*64 rows in total); `th`/`sg` (optional, may be NULL) receive tanh(.) and
+ * sigmoid(.) for the backward pass.  `accumulate`=1 adds into `out` (running skip sum).
+ * ------------------------------------------------------------------------------------------ */
+int wnb200_taps_fwd(int dtype, int B, int T_out, int M, int nsrc, const wnb200_src_t* srcs /*host*/,
+                    const float* bias, int epilogue, int accumulate, void* out, void* th, void* sg,
+                    void* stream);
+
+/* dW[m, c] += sum_{b,t} dout[b, m, t] * pre(x[b, c, t + t_off]) ; dout is contiguous [B, M, T_out].
+ * Weight gradient of every conv / linear above (autograd of conv_ops.py:43, block.py:73-78). */
+int wnb200_taps_wgrad(int dtype, int B, int T_out, int M, const wnb200_src_t* src /*host, w unused*/,
+                      const void* dout, float* dw, void* stream);
+
+/* out[c] += sum_{b,t} a[b,c,t] * (b_or_null ? b[b,c,t] : 1)   (bias / gamma / beta gradients) */
+int wnb200_channel_reduce(int dtype, int B, int C, int T, const void* a, const void* b_or_null,
+                          float* out, void* stream);
+
+/* Gate backward (block.py:185): d_ab[b, 0:C, t] = dact*sg*(1-th^2); d_ab[b, C:2C, t] = dact*th*sg*(1-sg). */
+int wnb200_gate_bwd(int dtype, int B, int C, int T, const void* dact, const void* th, const void* sg,
+                    void* d_ab, void* stream);
+
+/* dx = dy * (ref > 0 ? 1 : 0.01)  (LeakyReLU backward; ref = input or output of the LeakyReLU). */
+int wnb200_leaky_bwd(int dtype, int64_t n, const void* dy, const void* ref, void* dx, void* stream);
+
+/* Channel (dim=1) softmax / log-softmax of an NCL tensor, without the reshape_in/reshape_out copies
+ * (wavenet.py:108-109, raw_ctcnet.py:152-153, classifier.py:119-120). */
+int wnb200_softmax_fwd(int dtype, int B, int C, int T, const void* x, void* y, int log_mode, void* stream);
+int wnb200_softmax_bwd(int dtype, int B, int C, int T, const void* y, const void* dy, void* dx,
+                       int log_mode, void* stream);
+
+/* nn.AvgPool1d(kernel=pool) (stride=pool, no padding, floor) (classifier.py:53,102). */
+int wnb200_avgpool_fwd(int dtype, int B, int C, int T, int pool, const void* x, void* y, void* stream);
+int wnb200_avgpool_bwd(int dtype, int B, int C, int T, int pool, const void* dy, void* dx, void* stream);
+
+/* LayerNorm over channels with unbiased std and eps added to the std (layernorm.py:25-28).
+ * stats: fp32 [B, T, 2] = (mean, 1/(std+eps)). */
+int wnb200_layernorm_fwd(int dtype, int B, int C, int T, const void* x, const float* gamma,
+                         const float* beta, float eps, void* y, float* stats, void* stream);
+int wnb200_layernorm_bwd(int dtype, int B, int C, int T, const void* x, const float* gamma,
+                         const float* stats, float eps, const void* dy, void* dx, void* stream);
+
+/* Fused log-softmax + NLL over channels: replaces the T-iteration Python loop of
+ * nn.CrossEntropyLoss in legacy_code/train.py:36-39.  logits NCL [B,C,T], target int64 [B,T].
+ * loss_bt[b,t] = logsumexp_c(logits) - logits[b,target,t];  lse[b,t] kept for backward.
+ * bwd: dlogits[b,c,t] = (exp(logits - lse) - [c == target]) * (*gscale) . */
+int wnb200_xent_fwd(int dtype, int B, int C, int T, const void* logits, const int64_t* target,
+                    float* loss_bt, float* lse, void* stream);
+int wnb200_xent_bwd(int dtype, int B, int C, int T, const void* logits, const int64_t* target,
+                    const float* lse, const float* gscale /*device scalar*/, void* dlogits, void* stream);
+
+/* out[0] = sum(x[0:n]) deterministically (two-stage); scratch >= 1024 floats. */
+int wnb200_sum_f32(int64_t n, const float* x, float* out, float* scratch, void* stream);
+
+/* RawCTCNet position mixing (raw_ctcnet.py:131-135): out[b,f,t] += hardtanh(w[f]*(t + t0) + bias[f]). */
+int wnb200_positions_add(int dtype, int B, int F, int T, int t0, const float* w, const float* bias,
+                         void* out, void* stream);
+
+/* Per-frame argmax over channels of NCL logits -> int64 [B,T]  (sequence_decoders.py:21-23,
+ * legacy_code/train.py:36). */
+int wnb200_argmax_channels(int dtype, int B, int C, int T, const void* x, int64_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WNB200_H_ */

@@ -1,0 +1,99 @@
+"""CPU-side checks of the drop-in boundary: state_dict compatibility with the reference (via the golden
+fixtures, which hold reference state_dicts), constructor attributes, the C-ABI export list, and the
+no-CPU-fallback rule."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import wavenet_speech_b200 as W
+from wavenet_speech_b200 import _lib
+from wavenet_speech_b200 import functional as WF
+from tests import _golden as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "wnb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(wnb200_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 15
+    lib = ctypes.CDLL(_lib.LIB_PATH) if os.path.exists(_lib.LIB_PATH) else _lib.load()
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    # and the ctypes table binds exactly the declared set
+    assert set(_lib.SIGNATURES) == declared
+
+
+def test_load_binds_and_reports_version():
+    lib = _lib.load()
+    assert lib.wnb200_version() >= 100
+
+
+def test_state_dicts_load_reference_checkpoints_strictly():
+    g = G.load("wavenet_onehot_c32")
+    m = g["meta"]
+    net = W.WaveNet(m["in_dim"], m["entry_kwidth"], m["layers"], m["out_dim"], softmax=m["softmax"])
+    net.load_state_dict(g["sd"], strict=True)
+    g = G.load("rawctcnet_positions")
+    m = g["meta"]
+    net = W.RawCTCNet(m["num_features"], m["feature_kwidth"], m["num_labels"], m["layers"], m["out_dim"],
+                      positions=True, softmax=True)
+    net.load_state_dict(g["sd"], strict=True)
+    g = G.load("classifier_pool3")
+    m = g["meta"]
+    net = W.WaveNetClassifier(m["in_dim"], m["num_labels"], m["layers"], m["out_dim"],
+                              pool_kernel_size=m["pool_kernel_size"], softmax=False)
+    net.load_state_dict(g["sd"], strict=True)
+    g = G.load("block_noncausal_k3_d3")
+    blk = W.ResidualBlock(8, 8, 3, 3, causal=False)
+    blk.load_state_dict(g["sd"], strict=True)
+    g = G.load("layernorm_c6")
+    W.LayerNorm(6).load_state_dict(g["sd"], strict=True)
+    g = G.load("linearconv_k3_d2")
+    W.LinearConv1d(4, 6, 3, dilation=2).load_state_dict(g["sd"], strict=True)
+    g = G.load("multiplicative_unit")
+    W.MultiplicativeUnit(6, 3, dilation=2).load_state_dict(g["sd"], strict=True)
+
+
+def test_attributes_match_reference_semantics():
+    c = W.CausalConv1d(4, 6, 5, dilation=3)
+    assert c.padding == 12 and c.receptive_field == 13          # conv_ops.py:28,37
+    n = W.NonCausalConv1d(4, 6, 2, dilation=3)
+    assert n.padding == 2                                        # autopad(2,3) = ceil(3/2)
+    assert W.autopad(3, 2) == 2 and W.autopad(2, 16) == 8 and W.autopad(2, 1) == 1
+    b = W.ResidualBlock(4, 5, 2, 2, causal=False)
+    assert b.receptive_field == 3 and b.causal is False and b.conditioning is False
+    w = W.WaveNet(11, 2, [(11, 11, 2, d) for d in (1, 2, 4)], 11)
+    assert (w.in_dim, w.out_dim, w.num_layers, w.softmax) == (11, 11, 3, True)
+    lc = W.LinearConv1d(4, 6, 3, dilation=2)
+    assert lc.receptive_field == 5 and lc._ker_ixs == [0, 2, 4]
+    assert W.compute_new_length(15, 12, 3, 5) == 27.0
+
+
+def test_tap_offsets():
+    assert WF.tap_offsets(2, 1, False) == [-1, 0]
+    assert WF.tap_offsets(2, 3, False) == [-2, 1]
+    assert WF.tap_offsets(2, 16, False) == [-8, 8]
+    assert WF.tap_offsets(2, 512, True) == [-512, 0]
+    assert WF.tap_offsets(3, 2, False) == [-2, 0, 2]
+
+
+def test_no_cpu_fallback():
+    net = W.CausalConv1d(4, 6, 2, dilation=1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.randn(1, 4, 8))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        W.LayerNorm(4)(torch.randn(1, 4, 8))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "wavenet_speech_b200")
+    for dp, _dn, fn in os.walk(pkg):
+        for f in fn:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), os.path.join(dp, f)

@@ -1,0 +1,36 @@
+"""The synthetic-input generator follows the reference's generator statistics."""
+import numpy as np
+
+from wavenet_speech_b200.utils import signal_gen as S
+
+
+def test_kmer_index_matches_reference_formula():
+    bases = np.array([1, 2, 3, 4, 1, 4, 4], dtype=np.int64)
+    # utils/raw_signal_generator.py:91-93: sum((nts-1) * [256,64,16,4,1]) over a centred window of 5
+    want = [sum((bases[i + j] - 1) * w for j, w in enumerate([256, 64, 16, 4, 1])) for i in range(3)]
+    assert S.kmer_indices(bases).tolist() == want
+    assert S.kmer_indices(np.full(5, 4)).tolist() == [1023]
+
+
+def test_raw_signal_statistics():
+    means, stdvs = S.load_pore_model()
+    assert means.shape == (1024,) and 59 < means.min() < 60 and 118 < means.max() < 119
+    x = S.raw_batch(4, 4000, seed=1, normalize=False)
+    assert x.shape == (4, 1, 4000) and x.dtype == np.float32
+    assert 30 < x.min() and x.max() < 150
+    # mean dwell: gamma(2.46, 1/587.29) * 800 has mean 3.35; floored and clamped to >= 1 it is ~2.95
+    rng = np.random.default_rng(0)
+    reps = np.maximum((rng.gamma(S.DURATION_SHAPE, 1 / S.DURATION_RATE, size=200000) * S.SAMPLE_RATE).astype(int), 1)
+    assert 2.8 < reps.mean() < 3.1
+    xn = S.raw_batch(4, 4000, seed=1)
+    assert abs(xn.mean()) < 1e-3 and abs(xn.std() - 1) < 1e-2
+
+
+def test_mu_law_one_hot():
+    lev = S.quantized_batch(2, 500, seed=3)
+    assert lev.shape == (2, 500) and lev.min() >= 0 and lev.max() <= 255
+    oh = S.one_hot(lev)
+    assert oh.shape == (2, 256, 500) and np.all(oh.sum(1) == 1)
+    assert np.array_equal(oh.argmax(1), lev)
+    sig, labels = S.raw_signal(300, np.random.default_rng(2), with_labels=True)
+    assert sig.shape == (300,) and labels.min() >= 1 and labels.max() <= 4 and 40 < len(labels) < 200

@@ -1,0 +1,110 @@
+"""ctypes binding of libwnb200.so (the C-ABI declared in include/wnb200.h).
+
+The library is built in-tree by `wavenet_speech_b200/csrc/build.py` (nvcc, sm_100a).  There is no
+CPU fallback: if the library cannot be loaded, or a tensor is not on a CUDA device, the call raises.
+"""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libwnb200.so")
+
+c_void_p, c_int, c_int64, c_float_p = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p
+
+
+class Src(ctypes.Structure):
+    """Mirror of wnb200_src_t."""
+    _fields_ = [("x", c_void_p), ("w", c_void_p), ("batch_stride", c_int64), ("chan_stride", c_int64),
+                ("C", ctypes.c_int32), ("T_src", ctypes.c_int32), ("t_off", ctypes.c_int32),
+                ("pre_act", ctypes.c_int32)]
+
+
+# name -> argtypes (return type is int unless listed in _RESTYPES)
+SIGNATURES = {
+    "wnb200_last_error": [],
+    "wnb200_version": [],
+    "wnb200_check_device": [],
+    "wnb200_taps_fwd": [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(Src), c_void_p, c_int, c_int,
+                        c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_taps_wgrad": [c_int, c_int, c_int, c_int, ctypes.POINTER(Src), c_void_p, c_void_p, c_void_p],
+    "wnb200_channel_reduce": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_gate_bwd": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_leaky_bwd": [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_softmax_fwd": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p],
+    "wnb200_softmax_bwd": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "wnb200_avgpool_fwd": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "wnb200_avgpool_bwd": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "wnb200_layernorm_fwd": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, ctypes.c_float,
+                             c_void_p, c_void_p, c_void_p],
+    "wnb200_layernorm_bwd": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, ctypes.c_float,
+                             c_void_p, c_void_p, c_void_p],
+    "wnb200_xent_fwd": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_xent_bwd": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_sum_f32": [c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_positions_add": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_argmax_channels": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+}
+_RESTYPES = {"wnb200_last_error": ctypes.c_char_p}
+
+_lib = None
+
+
+class WnbError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (building first if the .so is absent and nvcc is available).  Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from .csrc import build as _build
+        _build.build()
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise WnbError("wavenet_speech_b200: cannot load %s (%s); the CUDA library is required, there is "
+                       "no CPU fallback" % (LIB_PATH, e))
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name, None)
+        if fn is None:
+            raise WnbError("wavenet_speech_b200: %s does not export %s (stale build?)" % (LIB_PATH, name))
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, ctypes.c_int)
+    _lib = lib
+    return lib
+
+
+# kernel launches issued per C-ABI call (for bench.py's `gpu_launches` claim)
+_LAUNCHES_PER_CALL = {"wnb200_sum_f32": 2, "wnb200_last_error": 0, "wnb200_version": 0, "wnb200_check_device": 0,
+                      "wnb200_tc_pack_bytes": 0}
+launch_count = 0
+_event_log = None     # list of (name, start_event, end_event) while kernel timing is on
+
+
+def kernel_timing(enable):
+    """Turn per-call CUDA-event timing on/off (events are recorded on torch's current stream, the stream the
+    kernels are launched on).  Returns the log collected so far when turning off."""
+    global _event_log
+    log, _event_log = _event_log, ([] if enable else None)
+    return log
+
+
+def call(name, *args):
+    global launch_count
+    lib = load()
+    fn = getattr(lib, name)
+    if _event_log is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        _event_log.append((name, e0, e1))
+    else:
+        rc = fn(*args)
+    if rc != 0:
+        raise WnbError("%s failed (code %d): %s" % (name, rc, lib.wnb200_last_error().decode()))
+    launch_count += _LAUNCHES_PER_CALL.get(name, 1)
+    return rc

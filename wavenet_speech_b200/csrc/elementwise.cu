@@ -1,0 +1,404 @@
+// Bandwidth-bound kernels of the hot path (NCL layout): gate backward, LeakyReLU backward,
+// channel softmax / log-softmax (+ fused NLL), mean-pool, LayerNorm, position mixing, argmax.
+// One thread per (batch, frame) column for the channel reductions: consecutive threads read
+// consecutive frames, so every global access is coalesced and no transposing copies
+// (reshape_in / reshape_out, reference conv_ops.py:91-101) are ever materialised.
+#include "common.cuh"
+
+namespace wnb {
+
+// ---------------------------------------------------------------- gate backward (block.py:185)
+template <typename T>
+__global__ void gate_bwd_kernel(int B, int C, int Tn, const T* dact, const T* th, const T* sg, T* dab) {
+  const long long n = (long long)B * C * Tn;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / ((long long)C * Tn);
+    const long long r = i - b * (long long)C * Tn;
+    const float g = to_f32<T>(dact[i]), t = to_f32<T>(th[i]), s = to_f32<T>(sg[i]);
+    const long long o = b * 2ll * C * Tn + r;
+    dab[o] = from_f32<T>(g * s * (1.f - t * t));
+    dab[o + (long long)C * Tn] = from_f32<T>(g * t * s * (1.f - s));
+  }
+}
+
+template <typename T>
+__global__ void leaky_bwd_kernel(long long n, const T* dy, const T* ref, T* dx) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float g = to_f32<T>(dy[i]);
+    dx[i] = from_f32<T>(to_f32<T>(ref[i]) > 0.f ? g : 0.01f * g);
+  }
+}
+
+// ---------------------------------------------------------------- channel softmax
+template <typename T>
+__global__ void softmax_fwd_kernel(int B, int C, int Tn, const T* x, T* y, int log_mode) {
+  const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (col >= (long long)B * Tn) return;
+  const long long b = col / Tn, t = col - b * Tn;
+  const T* xp = x + b * (long long)C * Tn + t;
+  T* yp = y + b * (long long)C * Tn + t;
+  float m = -INFINITY, s = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float v = to_f32<T>(xp[(long long)c * Tn]);
+    if (v > m) { s = s * expf(m - v); m = v; }
+    s += expf(v - m);
+  }
+  const float lse = m + logf(s);
+  const float inv = 1.f / s;
+  for (int c = 0; c < C; ++c) {
+    const float v = to_f32<T>(xp[(long long)c * Tn]);
+    yp[(long long)c * Tn] = from_f32<T>(log_mode ? (v - lse) : expf(v - m) * inv);
+  }
+}
+
+template <typename T>
+__global__ void softmax_bwd_kernel(int B, int C, int Tn, const T* y, const T* dy, T* dx, int log_mode) {
+  const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (col >= (long long)B * Tn) return;
+  const long long b = col / Tn, t = col - b * Tn;
+  const long long base = b * (long long)C * Tn + t;
+  float dot = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float g = to_f32<T>(dy[base + (long long)c * Tn]);
+    dot += log_mode ? g : g * to_f32<T>(y[base + (long long)c * Tn]);
+  }
+  for (int c = 0; c < C; ++c) {
+    const float g = to_f32<T>(dy[base + (long long)c * Tn]);
+    const float yy = to_f32<T>(y[base + (long long)c * Tn]);
+    dx[base + (long long)c * Tn] = from_f32<T>(log_mode ? (g - expf(yy) * dot) : yy * (g - dot));
+  }
+}
+
+// ---------------------------------------------------------------- fused log-softmax + NLL
+template <typename T>
+__global__ void xent_fwd_kernel(int B, int C, int Tn, const T* x, const long long* target, float* loss_bt,
+                                float* lse_out) {
+  const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (col >= (long long)B * Tn) return;
+  const long long b = col / Tn, t = col - b * Tn;
+  const T* xp = x + b * (long long)C * Tn + t;
+  float m = -INFINITY, s = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float v = to_f32<T>(xp[(long long)c * Tn]);
+    if (v > m) { s = s * expf(m - v); m = v; }
+    s += expf(v - m);
+  }
+  const float lse = m + logf(s);
+  long long tg = target[col];
+  tg = tg < 0 ? 0 : (tg >= C ? C - 1 : tg);
+  loss_bt[col] = lse - to_f32<T>(xp[tg * Tn]);
+  lse_out[col] = lse;
+}
+
+template <typename T>
+__global__ void xent_bwd_kernel(int B, int C, int Tn, const T* x, const long long* target, const float* lse,
+                                const float* gscale, T* dx) {
+  const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (col >= (long long)B * Tn) return;
+  const long long b = col / Tn, t = col - b * Tn;
+  const long long base = b * (long long)C * Tn + t;
+  const float g = *gscale, l = lse[col];
+  const long long tg = target[col];
+  for (int c = 0; c < C; ++c) {
+    const float pr = expf(to_f32<T>(x[base + (long long)c * Tn]) - l);
+    dx[base + (long long)c * Tn] = from_f32<T>((pr - (c == tg ? 1.f : 0.f)) * g);
+  }
+}
+
+__global__ void sum_stage_kernel(long long n, const float* x, float* partial) {
+  float s = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    s += x[i];
+  __shared__ float red[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  }
+}
+
+// ---------------------------------------------------------------- mean pool (classifier.py:53,102)
+template <typename T>
+__global__ void avgpool_fwd_kernel(long long rows, int Tn, int To, int pool, const T* x, T* y) {
+  const long long n = rows * To;
+  const float inv = 1.f / (float)pool;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / To;
+    const int to = (int)(i - r * To);
+    const T* xp = x + r * Tn + (long long)to * pool;
+    float s = 0.f;
+    for (int j = 0; j < pool; ++j) s += to_f32<T>(xp[j]);
+    y[i] = from_f32<T>(s * inv);
+  }
+}
+
+template <typename T>
+__global__ void avgpool_bwd_kernel(long long rows, int Tn, int To, int pool, const T* dy, T* dx) {
+  const long long n = rows * Tn;
+  const float inv = 1.f / (float)pool;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / Tn;
+    const int t = (int)(i - r * Tn);
+    const int to = t / pool;
+    dx[i] = from_f32<T>(to < To ? to_f32<T>(dy[r * To + to]) * inv : 0.f);
+  }
+}
+
+// ---------------------------------------------------------------- LayerNorm (layernorm.py:25-28)
+template <typename T>
+__global__ void layernorm_fwd_kernel(int B, int C, int Tn, const T* x, const float* gamma, const float* beta,
+                                     float eps, T* y, float* stats) {
+  const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (col >= (long long)B * Tn) return;
+  const long long b = col / Tn, t = col - b * Tn;
+  const long long base = b * (long long)C * Tn + t;
+  float mean = 0.f;
+  for (int c = 0; c < C; ++c) mean += to_f32<T>(x[base + (long long)c * Tn]);
+  mean /= (float)C;
+  float var = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float d = to_f32<T>(x[base + (long long)c * Tn]) - mean;
+    var += d * d;
+  }
+  const float sd = sqrtf(var / (float)(C - 1));   // unbiased, as torch.std
+  const float r = 1.f / (sd + eps);
+  for (int c = 0; c < C; ++c) {
+    const float d = to_f32<T>(x[base + (long long)c * Tn]) - mean;
+    y[base + (long long)c * Tn] = from_f32<T>(gamma[c] * d * r + beta[c]);
+  }
+  if (stats) { stats[col * 2] = mean; stats[col * 2 + 1] = r; }
+}
+
+template <typename T>
+__global__ void layernorm_bwd_kernel(int B, int C, int Tn, const T* x, const float* gamma, const float* stats,
+                                     float eps, const T* dy, T* dx) {
+  const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (col >= (long long)B * Tn) return;
+  const long long b = col / Tn, t = col - b * Tn;
+  const long long base = b * (long long)C * Tn + t;
+  const float mean = stats[col * 2], r = stats[col * 2 + 1];
+  const float sd = 1.f / r - eps;
+  // y = gamma * xc * r + beta,  r = 1/(sd+eps),  sd = sqrt(sum xc^2 / (C-1))
+  float s1 = 0.f, s2 = 0.f;   // sum(g), sum(g * xc)
+  for (int c = 0; c < C; ++c) {
+    const float g = to_f32<T>(dy[base + (long long)c * Tn]) * gamma[c];
+    const float xc = to_f32<T>(x[base + (long long)c * Tn]) - mean;
+    s1 += g; s2 += g * xc;
+  }
+  // d sd = -r^2 * s2 ; d xc_i (via sd) = dsd * xc_i / ((C-1) sd)
+  const float k = (sd > 0.f) ? (-r * r * s2 / ((float)(C - 1) * sd)) : 0.f;
+  // dx_i = dxc_i - mean_j(dxc_j); sum_j xc_j = 0 so mean_j(dxc_j) = r * s1 / C
+  const float mu = r * s1 / (float)C;
+  for (int c = 0; c < C; ++c) {
+    const float g = to_f32<T>(dy[base + (long long)c * Tn]) * gamma[c];
+    const float xc = to_f32<T>(x[base + (long long)c * Tn]) - mean;
+    dx[base + (long long)c * Tn] = from_f32<T>(g * r + k * xc - mu);
+  }
+}
+
+// ---------------------------------------------------------------- positions (raw_ctcnet.py:131-135)
+template <typename T>
+__global__ void positions_add_kernel(int B, int F, int Tn, int t0, const float* w, const float* bias, T* out) {
+  const long long n = (long long)B * F * Tn;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % Tn);
+    const int f = (int)((i / Tn) % F);
+    float v = w[f] * (float)(t + t0) + bias[f];
+    v = fminf(1.f, fmaxf(-1.f, v));
+    out[i] = from_f32<T>(to_f32<T>(out[i]) + v);
+  }
+}
+
+template <typename T>
+__global__ void argmax_kernel(int B, int C, int Tn, const T* x, long long* out) {
+  const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (col >= (long long)B * Tn) return;
+  const long long b = col / Tn, t = col - b * Tn;
+  const T* xp = x + b * (long long)C * Tn + t;
+  float m = to_f32<T>(xp[0]);
+  int arg = 0;
+  for (int c = 1; c < C; ++c) {
+    const float v = to_f32<T>(xp[(long long)c * Tn]);
+    if (v > m) { m = v; arg = c; }
+  }
+  out[col] = arg;
+}
+
+static inline int grid_for(long long n, int block = 256) {
+  long long g = (n + block - 1) / block;
+  const long long cap = 148ll * 32;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace wnb
+
+using namespace wnb;
+typedef __nv_bfloat16 bf16;
+
+#define DISPATCH(dtype, NAME, ...)                                             \
+  do {                                                                         \
+    if ((dtype) == WNB200_F32) { using T = float; __VA_ARGS__; }               \
+    else if ((dtype) == WNB200_BF16) { using T = bf16; __VA_ARGS__; }          \
+    else { set_error(NAME ": bad dtype %d", (int)(dtype)); return 1; }         \
+  } while (0)
+
+extern "C" int wnb200_gate_bwd(int dtype, int B, int C, int T_, const void* dact, const void* th, const void* sg,
+                               void* d_ab, void* stream) {
+  WNB_CHECK_ARG(dact && th && sg && d_ab, "gate_bwd: null pointer");
+  const long long n = (long long)B * C * T_;
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(dtype, "gate_bwd", (gate_bwd_kernel<T><<<grid_for(n), 256, 0, st>>>(B, C, T_, (const T*)dact,
+                                                                              (const T*)th, (const T*)sg, (T*)d_ab)));
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_leaky_bwd(int dtype, int64_t n, const void* dy, const void* ref, void* dx, void* stream) {
+  WNB_CHECK_ARG(dy && ref && dx, "leaky_bwd: null pointer");
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(dtype, "leaky_bwd", (leaky_bwd_kernel<T><<<grid_for(n), 256, 0, st>>>(n, (const T*)dy, (const T*)ref, (T*)dx)));
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_softmax_fwd(int dtype, int B, int C, int T_, const void* x, void* y, int log_mode,
+                                  void* stream) {
+  WNB_CHECK_ARG(x && y && C >= 1, "softmax_fwd: bad args");
+  const long long cols = (long long)B * T_;
+  if (cols == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(dtype, "softmax_fwd", (softmax_fwd_kernel<T><<<(unsigned)ceil_div64(cols, 128), 128, 0, st>>>(
+                                      B, C, T_, (const T*)x, (T*)y, log_mode)));
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_softmax_bwd(int dtype, int B, int C, int T_, const void* y, const void* dy, void* dx,
+                                  int log_mode, void* stream) {
+  WNB_CHECK_ARG(y && dy && dx, "softmax_bwd: null pointer");
+  const long long cols = (long long)B * T_;
+  if (cols == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(dtype, "softmax_bwd", (softmax_bwd_kernel<T><<<(unsigned)ceil_div64(cols, 128), 128, 0, st>>>(
+                                      B, C, T_, (const T*)y, (const T*)dy, (T*)dx, log_mode)));
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_xent_fwd(int dtype, int B, int C, int T_, const void* logits, const int64_t* target,
+                               float* loss_bt, float* lse, void* stream) {
+  WNB_CHECK_ARG(logits && target && loss_bt && lse, "xent_fwd: null pointer");
+  const long long cols = (long long)B * T_;
+  if (cols == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(dtype, "xent_fwd", (xent_fwd_kernel<T><<<(unsigned)ceil_div64(cols, 128), 128, 0, st>>>(
+                                   B, C, T_, (const T*)logits, (const long long*)target, loss_bt, lse)));
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_xent_bwd(int dtype, int B, int C, int T_, const void* logits, const int64_t* target,
+                               const float* lse, const float* gscale, void* dlogits, void* stream) {
+  WNB_CHECK_ARG(logits && target && lse && gscale && dlogits, "xent_bwd: null pointer");
+  const long long cols = (long long)B * T_;
+  if (cols == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(dtype, "xent_bwd", (xent_bwd_kernel<T><<<(unsigned)ceil_div64(cols, 128), 128, 0, st>>>(
+                                   B, C, T_, (const T*)logits, (const long long*)target, lse, gscale, (T*)dlogits)));
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_sum_f32(int64_t n, const float* x, float* out, float* scratch, void* stream) {
+  WNB_CHECK_ARG(x && out && scratch, "sum_f32: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int g = grid_for(n, 256);
+  if (g > 1024) g = 1024;
+  sum_stage_kernel<<<g, 256, 0, st>>>(n, x, scratch);
+  sum_stage_kernel<<<1, 256, 0, st>>>(g, scratch, out);
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_avgpool_fwd(int dtype, int B, int C, int T_, int pool, const void* x, void* y, void* stream) {
+  WNB_CHECK_ARG(x && y && pool >= 1, "avgpool_fwd: bad args");
+  const int To = T_ / pool;
+  const long long n = (long long)B * C * To;
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(dtype, "avgpool_fwd", (avgpool_fwd_kernel<T><<<grid_for(n), 256, 0, st>>>((long long)B * C, T_, To, pool,
+                                                                                    (const T*)x, (T*)y)));
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_avgpool_bwd(int dtype, int B, int C, int T_, int pool, const void* dy, void* dx, void* stream) {
+  WNB_CHECK_ARG(dy && dx && pool >= 1, "avgpool_bwd: bad args");
+  const int To = T_ / pool;
+  const long long n = (long long)B * C * T_;
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(dtype, "avgpool_bwd", (avgpool_bwd_kernel<T><<<grid_for(n), 256, 0, st>>>((long long)B * C, T_, To, pool,
+                                                                                    (const T*)dy, (T*)dx)));
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_layernorm_fwd(int dtype, int B, int C, int T_, const void* x, const float* gamma,
+                                    const float* beta, float eps, void* y, float* stats, void* stream) {
+  WNB_CHECK_ARG(x && y && gamma && beta && C >= 2, "layernorm_fwd: bad args");
+  const long long cols = (long long)B * T_;
+  if (cols == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(dtype, "layernorm_fwd", (layernorm_fwd_kernel<T><<<(unsigned)ceil_div64(cols, 128), 128, 0, st>>>(
+                                        B, C, T_, (const T*)x, gamma, beta, eps, (T*)y, stats)));
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_layernorm_bwd(int dtype, int B, int C, int T_, const void* x, const float* gamma,
+                                    const float* stats, float eps, const void* dy, void* dx, void* stream) {
+  WNB_CHECK_ARG(x && gamma && stats && dy && dx, "layernorm_bwd: null pointer");
+  const long long cols = (long long)B * T_;
+  if (cols == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(dtype, "layernorm_bwd", (layernorm_bwd_kernel<T><<<(unsigned)ceil_div64(cols, 128), 128, 0, st>>>(
+                                        B, C, T_, (const T*)x, gamma, stats, eps, (const T*)dy, (T*)dx)));
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_positions_add(int dtype, int B, int F, int T_, int t0, const float* w, const float* bias,
+                                    void* out, void* stream) {
+  WNB_CHECK_ARG(w && bias && out, "positions_add: null pointer");
+  const long long n = (long long)B * F * T_;
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(dtype, "positions_add", (positions_add_kernel<T><<<grid_for(n), 256, 0, st>>>(B, F, T_, t0, w, bias, (T*)out)));
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_argmax_channels(int dtype, int B, int C, int T_, const void* x, int64_t* out, void* stream) {
+  WNB_CHECK_ARG(x && out && C >= 1, "argmax_channels: bad args");
+  const long long cols = (long long)B * T_;
+  if (cols == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(dtype, "argmax_channels", (argmax_kernel<T><<<(unsigned)ceil_div64(cols, 128), 128, 0, st>>>(
+                                          B, C, T_, (const T*)x, (long long*)out)));
+  WNB_LAUNCH_OK();
+  return 0;
+}

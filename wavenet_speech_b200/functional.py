@@ -1,0 +1,385 @@
+"""Autograd-aware functional layer over the C-ABI kernels (generic NCL path).
+
+Each torch.autograd.Function below runs its forward AND backward in libwnb200 kernels; torch is
+used for buffer allocation and for the tiny parameter re-layouts (weight slabs per tap).
+Offsets follow the reference exactly: see `tap_offsets`.
+"""
+import torch
+
+from . import ops
+from .ops import EPI_GATE, EPI_LEAKY, EPI_NONE, Term
+
+
+# --------------------------------------------------------------------------- offsets
+def autopad(k, d):
+    """Same rule as the reference's autopad (modules/conv_ops.py:104-116): ceil((k-1)*d / 2)."""
+    total = (k - 1) * d
+    return (total + 1) // 2
+
+
+def tap_offsets(k, d, causal):
+    """Frame offset read by tap j.  Causal (conv_ops.py:28,44): j*d-(k-1)*d.  Non-causal
+    (conv_ops.py:62,79): j*d-autopad(k,d)."""
+    pad = (k - 1) * d if causal else autopad(k, d)
+    return [j * d - pad for j in range(k)]
+
+
+# --------------------------------------------------------------------------- weight re-layouts
+def _slabs(w, dtype):
+    """[M, C, k] (or [M, C]) -> [k, M, C] contiguous in the compute dtype."""
+    if w.dim() == 2:
+        w = w.unsqueeze(2)
+    return w.detach().to(dtype).permute(2, 0, 1).contiguous()
+
+
+def _slabs_t(w, dtype):
+    """[M, C, k] -> [k, C, M] contiguous (transposed slabs for the data gradient)."""
+    if w.dim() == 2:
+        w = w.unsqueeze(2)
+    return w.detach().to(dtype).permute(2, 1, 0).contiguous()
+
+
+def _pack_gate(wt, ws, bt, bs, dtype):
+    """Interleave tanh / sigmoid filters per 64 output channels: rows [128i, 128i+64) = tanh
+    channels 64i.., rows [128i+64, 128i+128) = sigmoid channels 64i.. (see wnb200.h, EPI_GATE)."""
+    M, C, k = wt.shape
+    Mp = (M + 63) // 64 * 64
+    nb = Mp // 64
+
+    def padw(w):
+        w = w.detach().to(dtype)
+        if Mp != M:
+            w = torch.cat([w, w.new_zeros(Mp - M, C, k)], 0)
+        return w.view(nb, 64, C, k)
+
+    def padb(b):
+        b = b.detach().float() if b is not None else torch.zeros(M, device=wt.device)
+        if Mp != M:
+            b = torch.cat([b, b.new_zeros(Mp - M)], 0)
+        return b.view(nb, 64)
+
+    wg = torch.stack([padw(wt), padw(ws)], 1).reshape(2 * Mp, C, k).permute(2, 0, 1).contiguous()
+    bg = torch.stack([padb(bt), padb(bs)], 1).reshape(2 * Mp).contiguous()
+    return wg, bg
+
+
+def _f32(b):
+    return None if b is None else b.detach().float().contiguous()
+
+
+# --------------------------------------------------------------------------- generic conv
+class _TapsConv(torch.autograd.Function):
+    """out = epi(bias + sum_i sum_j w_i[:,:,j] @ pre_i(x_i[.., t + off_ij]))."""
+
+    @staticmethod
+    def forward(ctx, cfg, bias, *tensors):
+        n = len(tensors) // 2
+        xs = [ops.time_major(t) for t in tensors[:n]]
+        ws = tensors[n:]
+        dtype = xs[0].dtype
+        M = ws[0].shape[0]
+        T_out = cfg["T_out"] if cfg.get("T_out") is not None else xs[0].shape[2]
+        terms = []
+        for i in range(n):
+            slabs = _slabs(ws[i], dtype)
+            for j, off in enumerate(cfg["offsets"][i]):
+                terms.append(Term(xs[i], slabs[j], off, cfg["pre_acts"][i]))
+        out = ops.taps_fwd(terms, _f32(bias), M, T_out, cfg["epilogue"])
+        ctx.cfg = cfg
+        ctx.n = n
+        ctx.has_bias = bias is not None
+        ctx.bias_dtype = bias.dtype if bias is not None else None
+        ctx.save_for_backward(out if cfg["epilogue"] == EPI_LEAKY else None, *xs, *ws)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        cfg, n = ctx.cfg, ctx.n
+        saved = ctx.saved_tensors
+        out, xs, ws = saved[0], saved[1:1 + n], saved[1 + n:]
+        if dout is None:
+            return (None, None) + (None,) * (2 * n)
+        dout = dout.contiguous()
+        if cfg["epilogue"] == EPI_LEAKY:
+            dout = ops.leaky_bwd(dout, out)
+        dtype = dout.dtype
+        M, T_out = dout.shape[1], dout.shape[2]
+        gx, gw = [], []
+        for i in range(n):
+            x, w = xs[i], ws[i]
+            offs = cfg["offsets"][i]
+            if ctx.needs_input_grad[2 + i]:
+                wt = _slabs_t(w, dtype)
+                terms = [Term(dout, wt[j], -off) for j, off in enumerate(offs)]
+                dx = ops.taps_fwd(terms, None, x.shape[1], x.shape[2])
+                if cfg["pre_acts"][i]:
+                    dx = ops.leaky_bwd(dx, x)
+                gx.append(dx)
+            else:
+                gx.append(None)
+            if ctx.needs_input_grad[2 + n + i]:
+                k = len(offs)
+                dw = torch.zeros((k, M, x.shape[1]), dtype=torch.float32, device=dout.device)
+                for j, off in enumerate(offs):
+                    ops.taps_wgrad(x, off, cfg["pre_acts"][i], dout, dw[j])
+                dw = dw.permute(1, 2, 0)
+                if w.dim() == 2:
+                    dw = dw[:, :, 0]
+                gw.append(dw.to(w.dtype))
+            else:
+                gw.append(None)
+        gb = None
+        if ctx.has_bias and ctx.needs_input_grad[1]:
+            gb = ops.channel_reduce(dout).to(ctx.bias_dtype)
+        return (None, gb) + tuple(gx) + tuple(gw)
+
+
+def multi_conv(terms, bias, epilogue=EPI_NONE, T_out=None):
+    """terms: list of (x, weight[M,C,k] or [M,C], offsets(list of k ints), pre_act)."""
+    cfg = {"offsets": [list(t[2]) for t in terms], "pre_acts": [int(t[3]) for t in terms],
+           "epilogue": epilogue, "T_out": T_out}
+    xs = [t[0] for t in terms]
+    ws = [t[1] for t in terms]
+    return _TapsConv.apply(cfg, bias, *xs, *ws)
+
+
+def conv_taps(x, weight, bias, offsets, pre_act=0, epilogue=EPI_NONE, T_out=None):
+    return multi_conv([(x, weight, offsets, pre_act)], bias, epilogue, T_out)
+
+
+# --------------------------------------------------------------------------- residual block
+class _ResBlock(torch.autograd.Function):
+    """ResidualBlock.forward (reference modules/block.py:54-82) in three launches:
+    gate = tanh(conv_t x) * sigmoid(conv_s x);  res = Wres gate + Wproj x + b;  skip = Wskip gate + b."""
+
+    @staticmethod
+    def forward(ctx, offsets, x, wt, bt, ws, bs, wres, bres, wskip, bskip, wproj, bproj):
+        x = ops.time_major(x)
+        dtype = x.dtype
+        M, C, k = wt.shape
+        if k > ops.MAX_SRC:
+            raise NotImplementedError("gated conv with kernel width > %d" % ops.MAX_SRC)
+        T = x.shape[2]
+        wg, bg = _pack_gate(wt, ws, bt, bs, dtype)
+        need_bwd = any(ctx.needs_input_grad)
+        gterms = [Term(x, wg[j], offsets[j]) for j in range(k)]
+        if need_bwd:
+            act, th, sg = ops.taps_fwd(gterms, bg, M, T, EPI_GATE, want_gate_parts=True)
+        else:
+            act, th, sg = ops.taps_fwd(gterms, bg, M, T, EPI_GATE), None, None
+        wres2, wproj2, wskip2 = _slabs(wres, dtype)[0], _slabs(wproj, dtype)[0], _slabs(wskip, dtype)[0]
+        b_res = _f32(bres) + _f32(bproj)
+        res = ops.taps_fwd([Term(act, wres2), Term(x, wproj2)], b_res, M, T)
+        skip = ops.taps_fwd([Term(act, wskip2)], _f32(bskip), M, T)
+        ctx.offsets = list(offsets)
+        ctx.save_for_backward(x, act, th, sg, wt, ws, wres, wskip, wproj)
+        ctx.set_materialize_grads(False)
+        ctx.bias_dtypes = (bt.dtype, bs.dtype, bres.dtype, bskip.dtype, bproj.dtype)
+        return res, skip
+
+    @staticmethod
+    def backward(ctx, dres, dskip):
+        x, act, th, sg, wt, ws, wres, wskip, wproj = ctx.saved_tensors
+        offs = ctx.offsets
+        nothing = (None,) * 12
+        if dres is None and dskip is None:
+            return nothing
+        dtype = x.dtype
+        M, C, k = wt.shape
+        B, _, T = x.shape
+        dev = x.device
+        if dres is not None:
+            dres = dres.contiguous()
+        if dskip is not None:
+            dskip = dskip.contiguous()
+        # d(gate)
+        terms = []
+        if dres is not None:
+            terms.append(Term(dres, _slabs_t(wres, dtype)[0]))
+        if dskip is not None:
+            terms.append(Term(dskip, _slabs_t(wskip, dtype)[0]))
+        dact = ops.taps_fwd(terms, None, M, T)
+        dab = ops.gate_bwd(dact, th, sg)                        # [B, 2M, T] = (d tanh-pre ; d sigmoid-pre)
+        # d(x)
+        wab_t = torch.cat([_slabs_t(wt, dtype), _slabs_t(ws, dtype)], 2)   # [k, C, 2M]
+        terms = [Term(dab, wab_t[j].contiguous(), -offs[j]) for j in range(k)]
+        if dres is not None:
+            terms.append(Term(dres, _slabs_t(wproj, dtype)[0]))
+        dx = ops.taps_fwd(terms, None, C, T) if ctx.needs_input_grad[1] else None
+        # parameter gradients (fp32 accumulation)
+        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+        dwab = z(k, 2 * M, C)
+        for j in range(k):
+            ops.taps_wgrad(x, offs[j], 0, dab, dwab[j])
+        dwt = dwab[:, :M].permute(1, 2, 0).to(wt.dtype)
+        dws = dwab[:, M:].permute(1, 2, 0).to(ws.dtype)
+        dbab = ops.channel_reduce(dab)
+        bd = ctx.bias_dtypes
+        dbt, dbs = dbab[:M].to(bd[0]), dbab[M:].to(bd[1])
+        dwres = dwproj = dbres = dbproj = dwskip = dbskip = None
+        if dres is not None:
+            dwres = ops.taps_wgrad(act, 0, 0, dres, z(M, M)).view(wres.shape).to(wres.dtype)
+            dwproj = ops.taps_wgrad(x, 0, 0, dres, z(M, C)).view(wproj.shape).to(wproj.dtype)
+            db = ops.channel_reduce(dres)
+            dbres, dbproj = db.to(bd[2]), db.to(bd[4])
+        if dskip is not None:
+            dwskip = ops.taps_wgrad(act, 0, 0, dskip, z(M, M)).view(wskip.shape).to(wskip.dtype)
+            dbskip = ops.channel_reduce(dskip).to(bd[3])
+        return (None, dx, dwt, dbt, dws, dbs, dwres, dbres, dwskip, dbskip, dwproj, dbproj)
+
+
+def residual_block(x, p, offsets):
+    """p: object with conv_tanh / conv_sigmoid / conv1x1_residual / conv1x1_skip / residual_proj."""
+    return _ResBlock.apply(list(offsets), x,
+                           p.conv_tanh.conv1d.weight, p.conv_tanh.conv1d.bias,
+                           p.conv_sigmoid.conv1d.weight, p.conv_sigmoid.conv1d.bias,
+                           p.conv1x1_residual.weight, p.conv1x1_residual.bias,
+                           p.conv1x1_skip.weight, p.conv1x1_skip.bias,
+                           p.residual_proj.weight, p.residual_proj.bias)
+
+
+class _SkipAccum(torch.autograd.Function):
+    """skips += Wbn skip + bbn, in place (reference wavenet.py:100 allocates a new tensor per layer)."""
+
+    @staticmethod
+    def forward(ctx, skips, skip, w, b):
+        skip = ops.time_major(skip)
+        dtype = skip.dtype
+        M = w.shape[0]
+        ops.taps_fwd([Term(skip, _slabs(w, dtype)[0])], _f32(b), M, skip.shape[2], EPI_NONE, out=skips,
+                     accumulate=True)
+        ctx.mark_dirty(skips)
+        ctx.save_for_backward(skip, w)
+        ctx.bias_dtype = b.dtype
+        return skips
+
+    @staticmethod
+    def backward(ctx, dout):
+        skip, w = ctx.saved_tensors
+        dout = dout.contiguous()
+        dtype = dout.dtype
+        M, C = w.shape[0], w.shape[1]
+        dskip = ops.taps_fwd([Term(dout, _slabs_t(w, dtype)[0])], None, C, skip.shape[2])
+        dw = ops.taps_wgrad(skip, 0, 0, dout, torch.zeros((M, C), dtype=torch.float32, device=dout.device))
+        db = ops.channel_reduce(dout).to(ctx.bias_dtype)
+        return dout, dskip, dw.view(w.shape).to(w.dtype), db
+
+
+def skip_accumulate(skips, skip, w, b):
+    """First call (skips is None) starts the running sum; later calls accumulate in place."""
+    if skips is None:
+        return conv_taps(skip, w, b, [0])
+    return _SkipAccum.apply(skips, skip, w, b)
+
+
+def output_stack(x, w1, b1, w3, b3):
+    """LeakyReLU -> 1x1 -> LeakyReLU -> 1x1 (reference wavenet.py:67-71): two launches, the
+    activations ride on the load of the first and the epilogue of the first."""
+    h = conv_taps(x, w1, b1, [0], pre_act=1, epilogue=EPI_LEAKY)
+    return conv_taps(h, w3, b3, [0])
+
+
+# --------------------------------------------------------------------------- softmax / pool / LN / loss
+class _ChannelSoftmax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, log_mode):
+        y = ops.softmax_fwd(x, log_mode)
+        ctx.log_mode = log_mode
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return ops.softmax_bwd(y, dy, ctx.log_mode), None
+
+
+def channel_softmax(x, log=False):
+    return _ChannelSoftmax.apply(x, bool(log))
+
+
+class _AvgPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pool):
+        ctx.T, ctx.pool = x.shape[2], pool
+        return ops.avgpool_fwd(x, pool)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.avgpool_bwd(dy, ctx.T, ctx.pool), None
+
+
+def avg_pool(x, pool):
+    return _AvgPool.apply(x, int(pool))
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        x = x.contiguous()
+        g = gamma.detach().float().reshape(-1).contiguous()
+        b = beta.detach().float().reshape(-1).contiguous()
+        y, stats = ops.layernorm_fwd(x, g, b, eps)
+        ctx.eps = eps
+        ctx.save_for_backward(x, g, stats, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g, stats, gamma = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = ops.layernorm_bwd(x, g, stats, ctx.eps, dy)
+        # y_hat = (x - mean) * r  recovered from the affine output is avoided: recompute via dx-free path
+        B, C, T = x.shape
+        mean = stats[:, :, 0].unsqueeze(1)
+        r = stats[:, :, 1].unsqueeze(1)
+        yhat = ((x.float() - mean) * r).to(x.dtype)      # plumbing for the (tiny-model) decoder-side LN only
+        dgamma = ops.channel_reduce(dy, yhat).view(gamma.shape).to(gamma.dtype)
+        dbeta = ops.channel_reduce(dy).view(gamma.shape).to(gamma.dtype)
+        return dx, dgamma, dbeta, None
+
+
+def layer_norm(x, gamma, beta, eps=1e-6):
+    return _LayerNorm.apply(x, gamma, beta, float(eps))
+
+
+class _XentSum(torch.autograd.Function):
+    """sum_{b,t} -log softmax(logits[b,:,t])[target[b,t]] in one pass (legacy_code/train.py:36-39
+    loops over t in Python and launches T-1 CrossEntropyLoss ops)."""
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        logits = logits.contiguous()
+        loss_bt, lse = ops.xent_fwd(logits, target)
+        ctx.save_for_backward(logits, target, lse)
+        return ops.sum_f32(loss_bt)
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, target, lse = ctx.saved_tensors
+        gs = g.detach().float().reshape(1).contiguous()
+        return ops.xent_bwd(logits, target, lse, gs), None
+
+
+def cross_entropy_sum(logits, target):
+    return _XentSum.apply(logits, target)
+
+
+class _Positions(torch.autograd.Function):
+    """out + hardtanh(w * t + b) (reference raw_ctcnet.py:131-135).  Parameter gradients of the
+    position layer are not propagated (the reference never trains with positions=True)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, t0):
+        out = x.contiguous().clone()
+        ops.positions_add_(out, w.detach().float().reshape(-1).contiguous(),
+                           b.detach().float().reshape(-1).contiguous(), t0)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None, None, None
+
+
+def positions_mix(x, w, b, t0=0):
+    return _Positions.apply(x, w, b, int(t0))

@@ -1,0 +1,148 @@
+"""Residual / gated blocks (reference: modules/block.py)."""
+import torch
+import torch.nn as nn
+
+from .. import functional as WF
+from ..ops import EPI_NONE
+from .conv_ops import CausalConv1d, NonCausalConv1d
+from .layernorm import LayerNorm
+
+
+class GatedActivationUnit(nn.Module):
+    """tanh(x) * sigmoid(y) (reference block.py:177-188).  Stand-alone use goes through a zero-weight-free
+    elementwise path: the gate is normally fused into the block's contraction epilogue."""
+
+    def forward(self, x, y):
+        return _GateOnly.apply(x, y)
+
+    def __repr__(self):
+        return self.__class__.__name__ + ' ()'
+
+
+class _GateOnly(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        # identity "contraction" is wasteful; this op only exists for API completeness
+        th, sg = torch.tanh(a), torch.sigmoid(b)
+        ctx.save_for_backward(th, sg)
+        return th * sg
+
+    @staticmethod
+    def backward(ctx, g):
+        th, sg = ctx.saved_tensors
+        from .. import ops
+        dab = ops.gate_bwd(g, th, sg)
+        c = g.shape[1]
+        return dab[:, :c], dab[:, c:]
+
+
+class ResidualBlock(nn.Module):
+    """Two dilated convs -> tanh*sigmoid gate -> 1x1 residual (+ a learned Linear projection of the block
+    input, not an identity) and 1x1 skip (reference block.py:15-82).  forward returns (residual, skip)."""
+
+    def __init__(self, in_channels, out_channels, kernel_width, dilation, causal=True, conditioning=None):
+        super(ResidualBlock, self).__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_width = kernel_width
+        self.dilation = dilation
+        self.causal = causal
+        self.conditioning = conditioning is not None      # accepted and ignored, as in the reference
+        conv_cls = CausalConv1d if causal else NonCausalConv1d
+        # construction order fixes the RNG stream -> same default init as the reference under a seed
+        self.conv_tanh = conv_cls(in_channels, out_channels, kernel_width, dilation=dilation)
+        self.conv_sigmoid = conv_cls(in_channels, out_channels, kernel_width, dilation=dilation)
+        self.conv1x1_residual = nn.Conv1d(out_channels, out_channels, kernel_size=1)
+        self.conv1x1_skip = nn.Conv1d(out_channels, out_channels, kernel_size=1)
+        self.gated_activation = GatedActivationUnit()
+        self.residual_proj = nn.Linear(in_channels, out_channels)
+        self.receptive_field = self.conv_tanh.receptive_field
+
+    @property
+    def offsets(self):
+        return self.conv_tanh.offsets
+
+    def forward(self, seq):
+        return WF.residual_block(seq, self, self.offsets)
+
+
+class MultiplicativeUnit(nn.Module):
+    """g1 * tanh(g2*h + g3*tanh(u)) with four causal convs (reference block.py:192-225)."""
+
+    def __init__(self, ndim, k, dilation=1):
+        super(MultiplicativeUnit, self).__init__()
+        self.ndim = ndim
+        self.gate1 = CausalConv1d(ndim, ndim, kernel_width=k, dilation=dilation)
+        self.gate2 = CausalConv1d(ndim, ndim, kernel_width=k, dilation=dilation)
+        self.gate3 = CausalConv1d(ndim, ndim, kernel_width=k, dilation=dilation)
+        self.update = CausalConv1d(ndim, ndim, kernel_width=k, dilation=dilation)
+        self.init()
+        self.receptive_field = max(self.gate1.receptive_field, self.gate2.receptive_field,
+                                   self.gate3.receptive_field, self.update.receptive_field)
+
+    def forward(self, h):
+        # secondary (decoder-side) block: convs run in libwnb200, the pointwise glue is torch
+        g1 = torch.sigmoid(self.gate1(h))
+        g2 = torch.sigmoid(self.gate2(h))
+        g3 = torch.sigmoid(self.gate3(h))
+        u = torch.tanh(self.update(h))
+        return g1 * torch.tanh(g2 * h + g3 * u)
+
+    def init(self):
+        for p in self.parameters():
+            if p.dim() >= 2:
+                nn.init.kaiming_normal_(p)
+            if p.dim() == 1:
+                p.data.zero_().add_(0.001 * torch.randn(p.size()))
+
+
+class _ByteNetBlock(nn.Module):
+    def forward(self, seq):
+        return seq + self.stack(seq)
+
+    def init(self):
+        for p in self.parameters():
+            if p.dim() >= 2:
+                nn.init.kaiming_normal_(p)
+            if p.dim() == 1:
+                p.data.zero_().add_(0.001 * torch.randn(p.size()))
+
+
+class _Conv1x1(nn.Conv1d):
+    """nn.Conv1d(k=1) parameter container whose forward is the libwnb200 contraction."""
+
+    def forward(self, x):
+        return WF.conv_taps(x, self.weight, self.bias, [0])
+
+
+class _ReLU(nn.Module):
+    def forward(self, x):
+        return torch.relu(x)
+
+
+class ResidualMUBlock(_ByteNetBlock):
+    """ByteNet residual multiplicative block (reference block.py:86-126)."""
+
+    def __init__(self, nchannels, k_width, dilation=1):
+        super(ResidualMUBlock, self).__init__()
+        self.nchannels, self.k_width, self.dilation = nchannels, k_width, dilation
+        half = int(nchannels / 2)
+        self.stack = nn.Sequential(
+            LayerNorm(nchannels), _ReLU(), _Conv1x1(nchannels, half, 1), LayerNorm(half, dim=1), _ReLU(),
+            MultiplicativeUnit(half, k_width, dilation=dilation), MultiplicativeUnit(half, 1, dilation=1),
+            _Conv1x1(half, nchannels, 1))
+        self.receptive_field = self.stack[5].receptive_field
+
+
+class ResidualReLUBlock(_ByteNetBlock):
+    """ByteNet residual ReLU block (reference block.py:130-173)."""
+
+    def __init__(self, nchannels, k_width, dilation=1):
+        super(ResidualReLUBlock, self).__init__()
+        self.nchannels, self.k_width, self.dilation = nchannels, k_width, dilation
+        half = int(nchannels / 2)
+        self.stack = nn.Sequential(
+            LayerNorm(nchannels), _ReLU(), _Conv1x1(nchannels, half, 1), LayerNorm(half), _ReLU(),
+            CausalConv1d(half, half, kernel_width=k_width, dilation=dilation), LayerNorm(half), _ReLU(),
+            _Conv1x1(half, nchannels, 1))
+        self.receptive_field = self.stack[5].receptive_field

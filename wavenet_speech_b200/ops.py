@@ -1,0 +1,251 @@
+"""Tensor-level wrappers over the C-ABI (no autograd here; see functional.py).
+
+Every function takes CUDA tensors, allocates outputs with torch (device memory plumbing only) and
+enqueues the kernels on torch's current stream.  A CPU tensor raises: there is no CPU path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+EPI_NONE, EPI_LEAKY, EPI_GATE = 0, 1, 2
+MAX_SRC = 4
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def _dt(t):
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError("wavenet_speech_b200 supports float32 and bfloat16 tensors, got %s" % t.dtype)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("wavenet_speech_b200 runs on CUDA (sm_100a) only; got a %s tensor. "
+                               "There is no CPU fallback." % t.device)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+_checked = {}
+
+
+def check_device():
+    dev = torch.cuda.current_device()
+    if dev not in _checked:
+        _lib.call("wnb200_check_device")
+        _checked[dev] = True
+
+
+def time_major(x):
+    """Make the time stride 1 (the only layout requirement of the NCL kernels)."""
+    return x if x.stride(2) == 1 and x.dim() == 3 else x.contiguous()
+
+
+class Term(object):
+    """One (x, weight-slab, offset) term.  x: [B, C, T_src] with stride(2)==1; w: [rows, C] contiguous."""
+    __slots__ = ("x", "w", "t_off", "pre_act")
+
+    def __init__(self, x, w, t_off=0, pre_act=0):
+        self.x, self.w, self.t_off, self.pre_act = x, w, int(t_off), int(pre_act)
+
+
+def _fill(src, term):
+    x = term.x
+    src.x = x.data_ptr()
+    src.w = 0 if term.w is None else term.w.data_ptr()
+    src.batch_stride = x.stride(0)
+    src.chan_stride = x.stride(1)
+    src.C = x.shape[1]
+    src.T_src = x.shape[2]
+    src.t_off = term.t_off
+    src.pre_act = term.pre_act
+
+
+def taps_fwd(terms, bias, M, T_out, epilogue=EPI_NONE, out=None, accumulate=False, want_gate_parts=False):
+    """out[b,m,t] (+)= epi(bias[m] + sum_terms w @ pre(x[.., t+off])).  Returns out (and th, sg)."""
+    x0 = terms[0].x
+    _need_cuda(x0)
+    check_device()
+    B = x0.shape[0]
+    dt = _dt(x0)
+    for tm in terms:
+        assert tm.x.dtype == x0.dtype and tm.w.dtype == x0.dtype, "mixed dtypes in taps_fwd"
+        assert tm.x.stride(2) == 1 and tm.w.is_contiguous()
+        assert tm.w.shape[1] == tm.x.shape[1]
+    if out is None:
+        out = torch.empty((B, M, T_out), dtype=x0.dtype, device=x0.device)
+        assert not accumulate
+    th = sg = None
+    if want_gate_parts:
+        th = torch.empty_like(out)
+        sg = torch.empty_like(out)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous()
+    # more than MAX_SRC terms: chain launches through the accumulate path (epilogue applied last)
+    chunks = [terms[i:i + MAX_SRC] for i in range(0, len(terms), MAX_SRC)]
+    if len(chunks) > 1:
+        assert epilogue == EPI_NONE, "more than %d terms only supported without epilogue" % MAX_SRC
+    for ci, chunk in enumerate(chunks):
+        arr = (_lib.Src * len(chunk))()
+        for i, tm in enumerate(chunk):
+            _fill(arr[i], tm)
+        _lib.call("wnb200_taps_fwd", dt, B, T_out, M, len(chunk), arr, _p(bias if ci == 0 else None),
+                  epilogue, 1 if (accumulate or ci > 0) else 0, _p(out), _p(th), _p(sg), _stream())
+    if want_gate_parts:
+        return out, th, sg
+    return out
+
+
+def taps_wgrad(x, t_off, pre_act, dout, dw):
+    """dw[m,c] += sum_{b,t} dout[b,m,t] * pre(x[b,c,t+t_off]); dw fp32 [M, C]."""
+    _need_cuda(x, dout, dw)
+    assert dout.is_contiguous() and dw.dtype == torch.float32 and dw.is_contiguous()
+    assert x.stride(2) == 1 and x.dtype == dout.dtype
+    B, M, T_out = dout.shape
+    src = _lib.Src()
+    _fill(src, Term(x, None, t_off, pre_act))
+    _lib.call("wnb200_taps_wgrad", _dt(x), B, T_out, M, ctypes.byref(src), _p(dout), _p(dw), _stream())
+    return dw
+
+
+def channel_reduce(a, b=None, out=None):
+    _need_cuda(a)
+    a = a.contiguous()
+    B, C, T = a.shape
+    if out is None:
+        out = torch.zeros(C, dtype=torch.float32, device=a.device)
+    if b is not None:
+        b = b.contiguous()
+    _lib.call("wnb200_channel_reduce", _dt(a), B, C, T, _p(a), _p(b), _p(out), _stream())
+    return out
+
+
+def gate_bwd(dact, th, sg):
+    _need_cuda(dact)
+    dact = dact.contiguous()
+    B, C, T = dact.shape
+    dab = torch.empty((B, 2 * C, T), dtype=dact.dtype, device=dact.device)
+    _lib.call("wnb200_gate_bwd", _dt(dact), B, C, T, _p(dact), _p(th), _p(sg), _p(dab), _stream())
+    return dab
+
+
+def leaky_bwd(dy, ref):
+    _need_cuda(dy, ref)
+    dy = dy.contiguous()
+    ref = ref.contiguous()
+    dx = torch.empty_like(dy)
+    _lib.call("wnb200_leaky_bwd", _dt(dy), dy.numel(), _p(dy), _p(ref), _p(dx), _stream())
+    return dx
+
+
+def softmax_fwd(x, log_mode=False):
+    _need_cuda(x)
+    check_device()
+    x = x.contiguous()
+    B, C, T = x.shape
+    y = torch.empty_like(x)
+    _lib.call("wnb200_softmax_fwd", _dt(x), B, C, T, _p(x), _p(y), int(log_mode), _stream())
+    return y
+
+
+def softmax_bwd(y, dy, log_mode=False):
+    dy = dy.contiguous()
+    B, C, T = y.shape
+    dx = torch.empty_like(y)
+    _lib.call("wnb200_softmax_bwd", _dt(y), B, C, T, _p(y), _p(dy), _p(dx), int(log_mode), _stream())
+    return dx
+
+
+def avgpool_fwd(x, pool):
+    _need_cuda(x)
+    check_device()
+    x = x.contiguous()
+    B, C, T = x.shape
+    y = torch.empty((B, C, T // pool), dtype=x.dtype, device=x.device)
+    _lib.call("wnb200_avgpool_fwd", _dt(x), B, C, T, pool, _p(x), _p(y), _stream())
+    return y
+
+
+def avgpool_bwd(dy, T, pool):
+    dy = dy.contiguous()
+    B, C, _ = dy.shape
+    dx = torch.empty((B, C, T), dtype=dy.dtype, device=dy.device)
+    _lib.call("wnb200_avgpool_bwd", _dt(dy), B, C, T, pool, _p(dy), _p(dx), _stream())
+    return dx
+
+
+def layernorm_fwd(x, gamma, beta, eps):
+    _need_cuda(x)
+    check_device()
+    x = x.contiguous()
+    B, C, T = x.shape
+    y = torch.empty_like(x)
+    stats = torch.empty((B, T, 2), dtype=torch.float32, device=x.device)
+    _lib.call("wnb200_layernorm_fwd", _dt(x), B, C, T, _p(x), _p(gamma), _p(beta), float(eps), _p(y), _p(stats),
+              _stream())
+    return y, stats
+
+
+def layernorm_bwd(x, gamma, stats, eps, dy):
+    dy = dy.contiguous()
+    B, C, T = x.shape
+    dx = torch.empty_like(x)
+    _lib.call("wnb200_layernorm_bwd", _dt(x), B, C, T, _p(x), _p(gamma), _p(stats), float(eps), _p(dy), _p(dx),
+              _stream())
+    return dx
+
+
+def xent_fwd(logits, target):
+    _need_cuda(logits, target)
+    check_device()
+    logits = logits.contiguous()
+    target = target.contiguous()
+    assert target.dtype == torch.int64
+    B, C, T = logits.shape
+    loss_bt = torch.empty((B, T), dtype=torch.float32, device=logits.device)
+    lse = torch.empty((B, T), dtype=torch.float32, device=logits.device)
+    _lib.call("wnb200_xent_fwd", _dt(logits), B, C, T, _p(logits), _p(target), _p(loss_bt), _p(lse), _stream())
+    return loss_bt, lse
+
+
+def xent_bwd(logits, target, lse, gscale):
+    B, C, T = logits.shape
+    d = torch.empty_like(logits)
+    _lib.call("wnb200_xent_bwd", _dt(logits), B, C, T, _p(logits), _p(target), _p(lse), _p(gscale), _p(d),
+              _stream())
+    return d
+
+
+def sum_f32(x):
+    _need_cuda(x)
+    x = x.contiguous()
+    out = torch.empty((), dtype=torch.float32, device=x.device)
+    scratch = torch.empty(1024, dtype=torch.float32, device=x.device)
+    _lib.call("wnb200_sum_f32", x.numel(), _p(x), _p(out), _p(scratch), _stream())
+    return out
+
+
+def positions_add_(out, w, bias, t0=0):
+    B, F, T = out.shape
+    _lib.call("wnb200_positions_add", _dt(out), B, F, T, int(t0), _p(w), _p(bias), _p(out), _stream())
+    return out
+
+
+def argmax_channels(x):
+    _need_cuda(x)
+    check_device()
+    x = x.contiguous()
+    B, C, T = x.shape
+    out = torch.empty((B, T), dtype=torch.int64, device=x.device)
+    _lib.call("wnb200_argmax_channels", _dt(x), B, C, T, _p(x), _p(out), _stream())
+    return out

@@ -1,0 +1,106 @@
+"""Synthetic Gaussian pore-model signal: the benchmark / test input of the hot path.
+
+Restates, vectorised in numpy, what the reference's on-line generators do (paths relative to the reference):
+  * k-mer index of a centred 5-base window, sum((nt-1) * [256,64,16,4,1]), edges dropped
+    (utils/raw_signal_generator.py:91-93,107-108);
+  * samples per k-mer ~ max(1, int(Gamma(shape=2.461964, scale=1/587.2858) * 800))
+    (raw_signal_generator.py:77-78,189-203);
+  * picoamp samples ~ N(means[k], stdvs[k]) from the r9.4 450bps 5-mer template table
+    (raw_signal_generator.py:110-118), shipped here as pore_model_r94_5mer.npy (2 x 1024 float32);
+  * bases ~ U{1..4} (utils/gaussian_kmer_model.py:281) in place of the reference-genome HDF5 the reference
+    reads, which is not distributed with it;
+  * mu-law 256-level quantisation and one-hot encoding (utils/pore_model.py:58-62,78-96).
+Host-side input preparation only -- not part of the timed path."""
+import os
+
+import numpy as np
+
+_TABLE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "pore_model_r94_5mer.npy")
+DURATION_SHAPE, DURATION_RATE, SAMPLE_RATE = 2.461964, 587.2858, 800.0
+_KMER_W = np.array([256, 64, 16, 4, 1], dtype=np.int64)
+
+
+def load_pore_model():
+    t = np.load(_TABLE)
+    return t[0], t[1]
+
+
+def kmer_indices(bases):
+    """bases: int array of values 1..4, length L -> k-mer ids for the L-4 fully covered windows."""
+    b = np.asarray(bases, dtype=np.int64) - 1
+    win = np.lib.stride_tricks.sliding_window_view(b, 5)
+    return win @ _KMER_W
+
+
+def raw_signal(T, rng, with_labels=False):
+    """One read of exactly T picoamp samples (float32).  Optionally also returns the bases (labels 1..4)
+    whose k-mers were (at least partly) emitted."""
+    means, stdvs = load_pore_model()
+    nb = int(T / 2.5) + 64
+    while True:
+        bases = rng.integers(1, 5, size=nb)
+        kmers = kmer_indices(bases)
+        reps = (rng.gamma(DURATION_SHAPE, 1.0 / DURATION_RATE, size=kmers.shape) * SAMPLE_RATE).astype(np.int64)
+        reps = np.maximum(reps, 1)
+        if int(reps.sum()) >= T:
+            break
+        nb *= 2
+    seq = np.repeat(kmers, reps)[:T]
+    sig = rng.normal(means[seq], stdvs[seq]).astype(np.float32)
+    if not with_labels:
+        return sig
+    n_used = int(np.searchsorted(np.cumsum(reps), T, side="left")) + 1
+    return sig, bases[2:2 + n_used].astype(np.int64)
+
+
+def raw_batch(B, T, seed=1234, normalize=True, with_labels=False):
+    """(B, 1, T) float32 raw signal; normalised over the batch the way the reference's callers do with
+    BatchNorm1d(1) (legacy_code/run_raw_ctc.py:38,58)."""
+    rng = np.random.default_rng(seed)
+    sigs, labels = [], []
+    for _ in range(B):
+        r = raw_signal(T, rng, with_labels=with_labels)
+        if with_labels:
+            sigs.append(r[0])
+            labels.append(r[1])
+        else:
+            sigs.append(r)
+    x = np.stack(sigs, 0)[:, None, :]
+    if normalize:
+        x = (x - x.mean()) / (x.std() + 1e-5)
+    x = x.astype(np.float32)
+    return (x, labels) if with_labels else x
+
+
+def mu_law_levels(sig, num_levels=256):
+    """utils/pore_model.py:58-62,78-86: normalise by (max-min), mu-law compand with mu=num_levels, digitize on
+    linspace(-1,1,num_levels).  Returns integer levels clipped into [0, num_levels-1]."""
+    sig = np.asarray(sig, dtype=np.float64)
+    norm = (sig - sig.mean()) / (sig.max() - sig.min())
+    mu = float(num_levels)
+    mapped = np.sign(norm) * np.log1p(mu * np.abs(norm)) / np.log1p(mu)
+    lev = np.digitize(mapped, np.linspace(-1.0, 1.0, num=num_levels))
+    return np.clip(lev, 0, num_levels - 1).astype(np.int64)
+
+
+def quantized_batch(B, T, num_levels=256, seed=1234, with_labels=False):
+    """(B, T) int64 levels of B synthetic reads (one-hot encode with `one_hot`)."""
+    rng = np.random.default_rng(seed)
+    levs, labels = [], []
+    for _ in range(B):
+        r = raw_signal(T, rng, with_labels=with_labels)
+        if with_labels:
+            levs.append(mu_law_levels(r[0], num_levels))
+            labels.append(r[1])
+        else:
+            levs.append(mu_law_levels(r, num_levels))
+    levs = np.stack(levs, 0)
+    return (levs, labels) if with_labels else levs
+
+
+def one_hot(levels, num_levels=256, dtype=np.float32):
+    """(B, T) levels -> (B, num_levels, T) one-hot (utils/pore_model.py:88-96)."""
+    B, T = levels.shape
+    out = np.zeros((B, num_levels, T), dtype=dtype)
+    out[np.arange(B)[:, None], levels, np.arange(T)[None, :]] = 1
+    return out
