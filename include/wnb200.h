@@ -122,6 +122,60 @@ int wnb200_positions_add(int dtype, int B, int F, int T, int t0, const float* w,
  * legacy_code/train.py:36). */
 int wnb200_argmax_channels(int dtype, int B, int C, int T, const void* x, int64_t* out, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Tensor-core path (bf16 storage, fp32 accumulation in TMEM, tcgen05.mma + TMA), NLC layout.
+ * One launch evaluates, per 128-frame tile, a chain of up to two channel contractions with the
+ * intermediate kept in shared memory (never written to HBM):
+ *   stage 1: acc1 = sum_j W1[:, j*C:(j+1)*C] x[t + t_off[j]]          (dilated taps, zero padded)
+ *   epi 1  : GATE  act = tanh(acc1[0:C]+b1[0:C]) * sigmoid(acc1[C:2C]+b1[C:2C])   (block.py:66-70,185)
+ *            LEAKY act = LeakyReLU(acc1+b1)    LINEAR act = acc1+b1
+ *   stage 2: acc2 = W2[:, 0:C] act (+ W2[0:C, C:2C] x[t] into rows 0:C when use_x2)
+ *   epi 2  : RESBLOCK res = acc2[0:C]+b2[0:C] -> y_nlc (bf16);  skips (+)= acc2[C:2C]+b2[C:2C] (fp32)
+ *            HEAD     (softmax over) acc2[0:n_out]+b2 -> out_ncl                  (wavenet.py:103-109)
+ * With n2 == 0 the call is a single contraction whose epilogue writes y_nlc [B,T,n1].
+ * A whole ResidualBlock + skip bottleneck (block.py:54-82, wavenet.py:100) is one call:
+ *   W1 = [Wtanh ; Wsigmoid] (rows) with tap-major columns, W2 = [[Wres, Wproj], [Wbn*Wskip, 0]],
+ *   b2 = [bres+bproj ; Wbn*bskip+bbn]  (the skip->bottleneck product is exact: nothing non-linear sits
+ *   between conv1x1_skip and the bottleneck).
+ * ------------------------------------------------------------------------------------------ */
+#define WNB200_TC_GATE 0
+#define WNB200_TC_LEAKY 1
+#define WNB200_TC_LINEAR 2
+#define WNB200_TC_EPI2_RESBLOCK 1
+#define WNB200_TC_EPI2_HEAD 2
+
+typedef struct {
+  int32_t B, T, C;        /* C = contracted channels = width of act; 64, 128 or 256              */
+  int32_t ntaps;          /* 1..3                                                               */
+  int32_t t_off[3];
+  int32_t epi1;           /* WNB200_TC_GATE / LEAKY / LINEAR                                     */
+  int32_t n1;             /* rows of w1: 2C for GATE, else C when a stage 2 follows, else <= 2C  */
+  int32_t n2;             /* rows of w2 (multiple of 16; 0 = no second stage)                    */
+  int32_t use_x2;
+  int32_t epi2;           /* WNB200_TC_EPI2_*                                                    */
+  int32_t skips_init;     /* 1: skips = ..., 0: skips += ...                                     */
+  int32_t out_f32;        /* HEAD output type: 1 fp32, 0 bf16                                    */
+  int32_t n_out;          /* HEAD: valid output channels (<= n2)                                 */
+  int32_t softmax;        /* HEAD: 1 = channel softmax, 0 = logits                               */
+  const void* x;          /* NLC bf16 [B,T,C]                                                    */
+  const void* w1;         /* bf16 [n1][ntaps*C]                                                  */
+  const float* bias1;     /* [n1]                                                                */
+  const void* w2;         /* bf16 [n2][C or 2C]                                                  */
+  const float* bias2;     /* [n2]                                                                */
+  void* y_nlc;            /* bf16 NLC: res (RESBLOCK; may be NULL = not needed) or stage-1 output */
+  float* skips;           /* fp32 NLC [B,T,C] running skip sum (RESBLOCK)                        */
+  void* skips_act;        /* optional bf16 NLC: LeakyReLU(skips) for the head (may be NULL)      */
+  void* out_ncl;          /* HEAD output, NCL [B, n_out, T]                                      */
+} wnb200_chain_t;
+
+int wnb200_chain_fwd_tc(const wnb200_chain_t* args /*host*/, void* stream);
+
+/* NCL (fp32/bf16) -> NLC bf16, and NLC (fp32/bf16) -> NCL (fp32/bf16): layout change at the module
+ * boundary only (the reference's reshape_in/reshape_out, conv_ops.py:91-101, ran once per block). */
+int wnb200_ncl_to_nlc_bf16(int dtype, int B, int C, int T, const void* x, void* y, void* stream);
+int wnb200_nlc_to_ncl(int out_dtype, int src_is_f32, int B, int C, int T, const void* x, void* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,3 +4,4 @@ from . import functional, ops  # noqa: F401
 from .modules import *  # noqa: F401,F403
 
 __version__ = "0.1.0"
+from . import _lib, fastpath  # noqa: F401,E402

@@ -19,6 +19,17 @@ class Src(ctypes.Structure):
                 ("pre_act", ctypes.c_int32)]
 
 
+class Chain(ctypes.Structure):
+    """Mirror of wnb200_chain_t."""
+    _fields_ = [("B", ctypes.c_int32), ("T", ctypes.c_int32), ("C", ctypes.c_int32), ("ntaps", ctypes.c_int32),
+                ("t_off", ctypes.c_int32 * 3), ("epi1", ctypes.c_int32), ("n1", ctypes.c_int32),
+                ("n2", ctypes.c_int32), ("use_x2", ctypes.c_int32), ("epi2", ctypes.c_int32),
+                ("skips_init", ctypes.c_int32), ("out_f32", ctypes.c_int32), ("n_out", ctypes.c_int32),
+                ("softmax", ctypes.c_int32), ("x", c_void_p), ("w1", c_void_p), ("bias1", c_void_p),
+                ("w2", c_void_p), ("bias2", c_void_p), ("y_nlc", c_void_p), ("skips", c_void_p),
+                ("skips_act", c_void_p), ("out_ncl", c_void_p)]
+
+
 # name -> argtypes (return type is int unless listed in _RESTYPES)
 SIGNATURES = {
     "wnb200_last_error": [],
@@ -43,6 +54,9 @@ SIGNATURES = {
     "wnb200_sum_f32": [c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_positions_add": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_argmax_channels": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "wnb200_chain_fwd_tc": [ctypes.POINTER(Chain), c_void_p],
+    "wnb200_ncl_to_nlc_bf16": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "wnb200_nlc_to_ncl": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
 }
 _RESTYPES = {"wnb200_last_error": ctypes.c_char_p}
 

@@ -11,7 +11,7 @@ LIB = os.path.join(PKG, "libwnb200.so")
 STAMP = os.path.join(PKG, ".libwnb200.stamp")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--shared",
-         "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-lcuda"]
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 
 def _sources():

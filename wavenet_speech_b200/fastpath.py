@@ -1,6 +1,189 @@
-"""Dispatch to the tensor-core (tcgen05, NLC, bf16) pipeline when a forward call is eligible.
-Returns None when it is not, and the caller continues on the generic NCL path."""
+"""Tensor-core (tcgen05 / TMA, bf16, NLC) inference pipeline behind the drop-in modules.
+
+A forward call is routed here when it is eligible: bf16 input, no autograd graph requested, every block
+`C -> C` with C in {64, 128, 256} and kernel width <= 3.  Anything else continues on the generic NCL path
+(`functional.py`), which is also the training path.  Weights are re-laid-out once per parameter version into
+the K-major bf16 matrices the kernels stream by TMA (see wnb200.h, wnb200_chain_t):
+
+  residual block l :  W1 = [Wtanh ; Wsigmoid] with tap-major columns          [2C, k*C]
+                      W2 = [[Wres, Wproj], [Wbn_l @ Wskip, 0]]                 [2C, 2C]
+                      b2 = [bres + bproj ; Wbn_l @ bskip + bbn_l]
+  The skip -> bottleneck product is exact (reference wavenet.py:100 applies the bottleneck straight to
+  conv1x1_skip's output) and saves one of the block's five contractions.
+"""
+import ctypes
+
+import torch
+
+from . import _lib, ops
+
+TC_GATE, TC_LEAKY, TC_LINEAR = 0, 1, 2
+EPI2_RESBLOCK, EPI2_HEAD = 1, 2
+_OK_C = (64, 128, 256)
+
+
+def _pad16(n):
+    return (n + 15) // 16 * 16
+
+
+def _bf16(t):
+    return t.detach().to(torch.bfloat16).contiguous()
+
+
+def _taps_matrix(w):
+    """conv weight [M, C, k] -> [M, k*C] with tap-major columns."""
+    M, C, k = w.shape
+    return w.detach().float().permute(0, 2, 1).reshape(M, k * C)
+
+
+def pack_block(block, bottleneck):
+    """-> dict(w1, b1, w2, b2, offsets) for one ResidualBlock + its skip bottleneck."""
+    C = block.out_channels
+    wt, ws = block.conv_tanh.conv1d, block.conv_sigmoid.conv1d
+    w1 = torch.cat([_taps_matrix(wt.weight), _taps_matrix(ws.weight)], 0)
+    b1 = torch.cat([wt.bias.detach().float(), ws.bias.detach().float()], 0)
+    wres = block.conv1x1_residual.weight.detach().float()[:, :, 0]
+    wskip = block.conv1x1_skip.weight.detach().float()[:, :, 0]
+    wproj = block.residual_proj.weight.detach().float()
+    wbn = bottleneck.weight.detach().float()[:, :, 0]
+    fold = wbn @ wskip
+    w2 = torch.cat([torch.cat([wres, wproj], 1), torch.cat([fold, torch.zeros_like(fold)], 1)], 0)
+    b2 = torch.cat([block.conv1x1_residual.bias.detach().float() + block.residual_proj.bias.detach().float(),
+                    wbn @ block.conv1x1_skip.bias.detach().float() + bottleneck.bias.detach().float()], 0)
+    return {"w1": _bf16(w1), "b1": b1.contiguous(), "w2": _bf16(w2), "b2": b2.contiguous(),
+            "offsets": list(block.offsets), "C": C}
+
+
+def pack_head(head, C):
+    """LeakyReLU -> 1x1 -> LeakyReLU -> 1x1: the first LeakyReLU is applied by the producer of the skip sum."""
+    w1 = head[1].weight.detach().float()[:, :, 0]
+    w3 = head[3].weight.detach().float()[:, :, 0]
+    n_out = w3.shape[0]
+    n2 = _pad16(n_out)
+    w2 = torch.zeros(n2, C, device=w3.device)
+    w2[:n_out] = w3
+    b2 = torch.zeros(n2, device=w3.device)
+    b2[:n_out] = head[3].bias.detach().float()
+    return {"w1": _bf16(w1), "b1": head[1].bias.detach().float().contiguous(), "w2": _bf16(w2), "b2": b2,
+            "n_out": n_out, "n2": n2}
+
+
+def _version_key(module):
+    return tuple((p.data_ptr(), p._version) for p in module.parameters())
+
+
+def _cached(module, name, build):
+    key = _version_key(module)
+    cache = module.__dict__.setdefault("_wnb_pack_cache", {})
+    hit = cache.get(name)
+    if hit is None or hit[0] != key:
+        hit = (key, build())
+        cache[name] = hit
+    return hit[1]
+
+
+def chain(x_nlc, C, offsets, epi1, w1, b1, n1, n2=0, use_x2=0, epi2=0, w2=None, b2=None, y_nlc=None, skips=None,
+          skips_init=0, skips_act=None, out_ncl=None, n_out=0, softmax=0):
+    a = _lib.Chain()
+    B, T, _ = x_nlc.shape
+    a.B, a.T, a.C = B, T, C
+    a.ntaps = len(offsets)
+    for j, o in enumerate(offsets):
+        a.t_off[j] = int(o)
+    a.epi1, a.n1, a.n2, a.use_x2, a.epi2 = epi1, n1, n2, use_x2, epi2
+    a.skips_init, a.n_out, a.softmax = skips_init, n_out, softmax
+    a.out_f32 = 1 if (out_ncl is not None and out_ncl.dtype == torch.float32) else 0
+    p = lambda t: 0 if t is None else t.data_ptr()
+    a.x, a.w1, a.bias1, a.w2, a.bias2 = p(x_nlc), p(w1), p(b1), p(w2), p(b2)
+    a.y_nlc, a.skips, a.skips_act, a.out_ncl = p(y_nlc), p(skips), p(skips_act), p(out_ncl)
+    _lib.call("wnb200_chain_fwd_tc", ctypes.byref(a), ops._stream())
+
+
+def ncl_to_nlc_bf16(x):
+    x = x.contiguous()
+    B, C, T = x.shape
+    y = torch.empty((B, T, C), dtype=torch.bfloat16, device=x.device)
+    _lib.call("wnb200_ncl_to_nlc_bf16", ops._dt(x), B, C, T, ops._p(x), ops._p(y), ops._stream())
+    return y
+
+
+def nlc_to_ncl(x, out_dtype):
+    B, T, C = x.shape
+    y = torch.empty((B, C, T), dtype=out_dtype, device=x.device)
+    _lib.call("wnb200_nlc_to_ncl", ops._DT[out_dtype], 1 if x.dtype == torch.float32 else 0, B, C, T, ops._p(x),
+              ops._p(y), ops._stream())
+    return y
+
+
+def _no_graph(module, x):
+    return not (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters())))
+
+
+def _stack_ok(C, layers):
+    return C in _OK_C and all(ci == C and co == C and k <= 3 for (ci, co, k, _d) in layers)
+
+
+def run_blocks(h, blocks, bottlenecks, packs, skips, first_init, want_act):
+    """Residual stack on NLC bf16 activations: one fused launch per layer.  Returns (h, skips_act)."""
+    B, T, C = h.shape
+    buf = [h, torch.empty_like(h)]
+    skips_act = torch.empty_like(h) if want_act else None
+    n = len(packs)
+    for l, pk in enumerate(packs):
+        last = l == n - 1
+        chain(buf[0], C, pk["offsets"], TC_GATE, pk["w1"], pk["b1"], 2 * C, n2=2 * C, use_x2=1,
+              epi2=EPI2_RESBLOCK, w2=pk["w2"], b2=pk["b2"], y_nlc=None if last else buf[1], skips=skips,
+              skips_init=1 if (first_init and l == 0) else 0, skips_act=skips_act if last else None)
+        if not last:
+            buf = [buf[1], buf[0]]
+    return buf[0], skips_act
 
 
 def try_wavenet_forward(model, signal):
-    return None
+    """WaveNet.forward (reference wavenet.py:88-111) on the tensor-core path, or None if not eligible."""
+    if signal.dtype != torch.bfloat16 or not signal.is_cuda or signal.dim() != 3:
+        return None
+    C = model.layers[0][0]
+    if not (_no_graph(model, signal) and model.in_dim == C and model.out_dim == C and _stack_ok(C, model.layers)
+            and model.entry_kwidth <= 3 and signal.shape[0] > 0 and signal.shape[2] > 0):
+        return None
+    ops.check_device()
+
+    def build():
+        ec = model.entry_conv1d
+        return {"entry": {"w1": _bf16(_taps_matrix(ec.conv1d.weight)), "b1": ec.conv1d.bias.detach().float().contiguous(),
+                          "offsets": list(ec.offsets)},
+                "blocks": [pack_block(b, n) for b, n in zip(model.convolutions, model.bottlenecks)],
+                "head": pack_head(model.output_stack, C)}
+
+    pk = _cached(model, "wavenet", build)
+    B, _, T = signal.shape
+    x = ncl_to_nlc_bf16(signal)
+    h = torch.empty_like(x)
+    chain(x, C, pk["entry"]["offsets"], TC_LINEAR, pk["entry"]["w1"], pk["entry"]["b1"], C, y_nlc=h)
+    skips = torch.empty((B, T, C), dtype=torch.float32, device=signal.device)
+    _, skips_act = run_blocks(h, model.convolutions, model.bottlenecks, pk["blocks"], skips, True, True)
+    hd = pk["head"]
+    out = torch.empty((B, hd["n_out"], T), dtype=signal.dtype, device=signal.device)
+    chain(skips_act, C, [0], TC_LEAKY, hd["w1"], hd["b1"], C, n2=hd["n2"], epi2=EPI2_HEAD, w2=hd["w2"], b2=hd["b2"],
+          out_ncl=out, n_out=hd["n_out"], softmax=1 if model.softmax else 0)
+    return out
+
+
+def smoke_check(reference_forward):
+    """Tiny eligible WaveNet on the tensor-core path vs `reference_forward(state_dict, x, layers, softmax)`
+    evaluated by the caller's checker on bf16-rounded weights (used by __graft_entry__.smoke())."""
+    from .modules.wavenet import WaveNet
+    torch.manual_seed(1)
+    layers = [(64, 64, 2, d) for d in (1, 2, 4)]
+    net = WaveNet(64, 2, layers, 64, softmax=True)
+    sd = {k: v.detach().bfloat16().float() for k, v in net.state_dict().items()}
+    lev = torch.randint(0, 64, (2, 300))
+    x = torch.zeros(2, 64, 300).scatter_(1, lev.unsqueeze(1), 1.0)
+    ref = reference_forward(sd, x, layers, True)
+    with torch.no_grad():
+        y = try_wavenet_forward(net.cuda().bfloat16(), x.cuda().bfloat16())
+    assert y is not None, "tensor-core path refused an eligible shape"
+    err = float((y.float().cpu() - ref).abs().max() / ref.abs().max())
+    assert err < 2e-2, "tensor-core path mismatch vs the checker: %g" % err
+    return "tensor-core path rel err %.2e" % err
