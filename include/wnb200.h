@@ -167,9 +167,37 @@ typedef struct {
   float* skips;           /* fp32 NLC [B,T,C] running skip sum (RESBLOCK)                        */
   void* skips_act;        /* optional bf16 NLC: LeakyReLU(skips) for the head (may be NULL)      */
   void* out_ncl;          /* HEAD output, NCL [B, n_out, T]                                      */
+  void* dbg;              /* optional int64[8*16] device buffer: per-phase clock64 stamps of CTA 0 */
 } wnb200_chain_t;
 
 int wnb200_chain_fwd_tc(const wnb200_chain_t* args /*host*/, void* stream);
+
+
+/* Fused ResidualBlock + skip bottleneck, pipelined variant for C = 128 / 256 (resblock_tc.cu): TMEM is
+ * split in two regions so the gate / output epilogues overlap the next contraction, res is written with
+ * TMA stores and the skip sum is accumulated in HBM with TMA reduce-add (the SM never reads it).
+ *   w1   bf16 [2C][ntaps*C]: rows = [tanh 0:C/2 ; sigmoid 0:C/2 ; tanh C/2:C ; sigmoid C/2:C], tap-major columns
+ *   b1   fp32 [2C] in the same row order
+ *   w2   bf16 [2C][2C] = [[Wres, Wproj], [Wbn*Wskip, 0]];   b2 fp32 [2C] = [bres+bproj ; Wbn*bskip+bbn]
+ *   res  bf16 NLC [B,T,C] or NULL (last layer: not needed);  skips fp32 NLC [B,T,C]. */
+typedef struct {
+  int32_t B, T, C, ntaps;
+  int32_t t_off[3];
+  int32_t skips_init;     /* 1: skips = contribution, 0: skips += contribution */
+  const void* x;          /* NLC bf16 [B,T,C] */
+  const void* w1;
+  const float* bias1;
+  const void* w2;
+  const float* bias2;
+  void* res;
+  float* skips;
+  void* dbg;              /* optional int64[8*16] timeline buffer */
+} wnb200_resblock_t;
+int wnb200_resblock_fwd_tc(const wnb200_resblock_t* args /*host*/, void* stream);
+
+/* y = bf16(LeakyReLU_0.01(x)), n a multiple of 4: turns the fp32 skip sum into the head's input
+ * (first LeakyReLU of output_stack, wavenet.py:67). */
+int wnb200_leaky_to_bf16(int64_t n, const float* x, void* y, void* stream);
 
 /* NCL (fp32/bf16) -> NLC bf16, and NLC (fp32/bf16) -> NCL (fp32/bf16): layout change at the module
  * boundary only (the reference's reshape_in/reshape_out, conv_ops.py:91-101, ran once per block). */

@@ -83,6 +83,19 @@ def test_fused_block(C, k, d, causal, T, B):
     FP.chain(xn, C, pk["offsets"], FP.TC_GATE, pk["w1"], pk["b1"], 2 * C, n2=2 * C, use_x2=1,
              epi2=FP.EPI2_RESBLOCK, w2=pk["w2"], b2=pk["b2"], y_nlc=None, skips=skips2, skips_init=1)
     assert rel(skips2.permute(0, 2, 1), contrib_ref) <= BF16_TOL
+    if C in (128, 256):
+        # pipelined kernel (TMA store / reduce-add outputs)
+        res3 = torch.empty_like(xn)
+        skips3 = prev.clone()
+        FP.resblock(xn, pk, res3, skips3, False)
+        torch.cuda.synchronize()
+        assert rel(res3.float().permute(0, 2, 1), res_ref) <= BF16_TOL, ("res v2", rel(res3.float().permute(0, 2, 1), res_ref))
+        assert rel((skips3 - prev).permute(0, 2, 1), contrib_ref) <= BF16_TOL
+        skips4 = torch.full_like(prev, 1e9)
+        FP.resblock(xn, pk, None, skips4, True)
+        assert rel(skips4.permute(0, 2, 1), contrib_ref) <= BF16_TOL
+        # the two kernels agree closely with each other
+        assert rel(res3.float(), res.float().cpu()) <= 1e-2
 
 
 @pytest.mark.parametrize("C,nl,T,B,softmax", [(64, 4, 300, 2, True), (128, 5, 1000, 2, False),
@@ -100,7 +113,7 @@ def test_wavenet_tc(C, nl, T, B, softmax):
         before = W._lib.launch_count
         y = net(x.cuda().bfloat16())
         assert y.dtype == torch.bfloat16 and tuple(y.shape) == tuple(ref.shape)
-    assert W._lib.launch_count - before == nl + 3          # transpose + entry + nl blocks + head
+    assert W._lib.launch_count - before == nl + 3 + (1 if C in (128, 256) else 0)   # transpose, entry, blocks, [leaky], head
     e = rel(y, ref)
     assert e <= BF16_TOL, e
     if not softmax:

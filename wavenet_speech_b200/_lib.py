@@ -27,7 +27,15 @@ class Chain(ctypes.Structure):
                 ("skips_init", ctypes.c_int32), ("out_f32", ctypes.c_int32), ("n_out", ctypes.c_int32),
                 ("softmax", ctypes.c_int32), ("x", c_void_p), ("w1", c_void_p), ("bias1", c_void_p),
                 ("w2", c_void_p), ("bias2", c_void_p), ("y_nlc", c_void_p), ("skips", c_void_p),
-                ("skips_act", c_void_p), ("out_ncl", c_void_p)]
+                ("skips_act", c_void_p), ("out_ncl", c_void_p), ("dbg", c_void_p)]
+
+
+class ResBlock(ctypes.Structure):
+    """Mirror of wnb200_resblock_t."""
+    _fields_ = [("B", ctypes.c_int32), ("T", ctypes.c_int32), ("C", ctypes.c_int32), ("ntaps", ctypes.c_int32),
+                ("t_off", ctypes.c_int32 * 3), ("skips_init", ctypes.c_int32), ("x", c_void_p), ("w1", c_void_p),
+                ("bias1", c_void_p), ("w2", c_void_p), ("bias2", c_void_p), ("res", c_void_p), ("skips", c_void_p),
+                ("dbg", c_void_p)]
 
 
 # name -> argtypes (return type is int unless listed in _RESTYPES)
@@ -55,6 +63,8 @@ SIGNATURES = {
     "wnb200_positions_add": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_argmax_channels": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "wnb200_chain_fwd_tc": [ctypes.POINTER(Chain), c_void_p],
+    "wnb200_resblock_fwd_tc": [ctypes.POINTER(ResBlock), c_void_p],
+    "wnb200_leaky_to_bf16": [c_int64, c_void_p, c_void_p, c_void_p],
     "wnb200_ncl_to_nlc_bf16": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "wnb200_nlc_to_ncl": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
 }
@@ -95,6 +105,7 @@ _LAUNCHES_PER_CALL = {"wnb200_sum_f32": 2, "wnb200_last_error": 0, "wnb200_versi
                       "wnb200_tc_pack_bytes": 0}
 launch_count = 0
 _event_log = None     # list of (name, start_event, end_event) while kernel timing is on
+current_tag = None    # optional label (e.g. "resblock") attached to timed calls by the caller
 
 
 def kernel_timing(enable):
@@ -115,7 +126,7 @@ def call(name, *args):
         e0.record()
         rc = fn(*args)
         e1.record()
-        _event_log.append((name, e0, e1))
+        _event_log.append((name if current_tag is None else name + ":" + current_tag, e0, e1))
     else:
         rc = fn(*args)
     if rc != 0:

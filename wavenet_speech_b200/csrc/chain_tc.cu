@@ -23,6 +23,8 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 
+#define WNB_STAMP(slot) do { if (p.dbg && blockIdx.x == 0 && it < 8) p.dbg[it * 16 + (slot)] = clock64(); } while (0)
+
 namespace wnb {
 using namespace tc;
 typedef __nv_bfloat16 bf16;
@@ -44,6 +46,7 @@ struct ChainDev {
   bf16* skips_act;   // optional: LeakyReLU(skips) as bf16 NLC (input of the head)
   void* out_ncl;     // HEAD output, NCL
   int out_f32, n_out, softmax;
+  long long* dbg;   // optional timeline buffer (block 0): [iter][16] clock64 stamps
 };
 
 constexpr int TILE_M = 128;
@@ -185,6 +188,7 @@ chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
           mbar_wait(tmem_empty, (uint32_t)((it - 1) & 1));
           tc_fence_after();
         }
+        WNB_STAMP(0);
         for (int kb = 0; kb < p.ntaps * K::KB; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -194,9 +198,11 @@ chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
           advance();
         }
         umma_commit(g1_full);
+        WNB_STAMP(1);
         if (has2) {
           mbar_wait(act_ready, (uint32_t)(it & 1));
           tc_fence_after();
+          WNB_STAMP(2);
           for (int kb = 0; kb < K::KB; ++kb) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
@@ -216,6 +222,7 @@ chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
             }
           }
           umma_commit(g2_full);
+          WNB_STAMP(3);
         }
       }
     }
@@ -234,6 +241,7 @@ chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
 
       mbar_wait(g1_full, (uint32_t)(it & 1));
       tc_fence_after();
+      if (threadIdx.x == 64) WNB_STAMP(4);
       if (has2) {
         // ---- epilogue 1: -> act (bf16, swizzled K-major blocks in smem) ----
         for (int c0 = 0; c0 < C; c0 += 16) {
@@ -264,9 +272,11 @@ chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
         fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
         tc_fence_before();
         mbar_arrive(act_ready);
+        if (threadIdx.x == 64) WNB_STAMP(5);
 
         mbar_wait(g2_full, (uint32_t)(it & 1));
         tc_fence_after();
+        if (threadIdx.x == 64) WNB_STAMP(6);
         if (p.epi2 == EPI2_RESBLOCK) {
           if (p.y_nlc) {
             for (int c0 = 0; c0 < C; c0 += 16) {
@@ -374,6 +384,7 @@ chain_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ 
       }
       tc_fence_before();
       mbar_arrive(tmem_empty);
+      if (threadIdx.x == 64) WNB_STAMP(7);
     }
   }
 
@@ -480,6 +491,7 @@ extern "C" int wnb200_chain_fwd_tc(const wnb200_chain_t* a, void* stream) {
   p.bias1 = a->bias1; p.bias2 = a->bias2;
   p.y_nlc = (bf16*)a->y_nlc; p.skips = a->skips; p.skips_init = a->skips_init; p.skips_act = (bf16*)a->skips_act;
   p.out_ncl = a->out_ncl; p.out_f32 = a->out_f32; p.n_out = a->n_out; p.softmax = a->softmax;
+  p.dbg = (long long*)a->dbg;
   if (a->n2 > 0) {
     WNB_CHECK_ARG(a->epi2 == EPI2_RESBLOCK || a->epi2 == EPI2_HEAD, "chain_fwd_tc: bad epi2");
     if (a->epi2 == EPI2_RESBLOCK)

@@ -1,0 +1,500 @@
+// Fused residual block + skip bottleneck, tensor-core path v2 (C = 128 or 256, NLC bf16).
+//
+// One persistent CTA per SM walks 128-frame tiles.  TMEM (2C fp32 columns) is split into two regions A|B of C
+// columns so that the epilogue of one region overlaps the MMAs into the other:
+//
+//   MMA order per tile                       TMEM     epilogue (8 warps, overlapped)
+//   G1a  x taps  * W1[half 0]  (N = C)   ->   A       E1a: gate channels [0, C/2)   -> act blocks (smem)
+//   G1b  x taps  * W1[half 1]  (N = C)   ->   B       E1b: gate channels [C/2, C)   -> act blocks (smem)
+//   G2r  x(t)*Wproj + act*Wres (N = C)   ->   A       E2a: res  + bias -> bf16 -> smem -> TMA store
+//   G2s  act * (Wbn*Wskip)     (N = C)   ->   B       E2b: skip + bias -> fp32 -> smem -> TMA reduce-add
+//
+// W1 rows are packed per half as [tanh C/2 ; sigmoid C/2] so a thread finds the two pre-activations of one
+// channel in the same TMEM lane.  The skip sum is accumulated in HBM by cp.reduce.async.bulk (L2 does the add):
+// the SM never reads the running sum.  Weight and activation blocks stream through a ring of (16 KB + C*128 B)
+// stages filled by TMA; out-of-range frames are zero-filled by TMA (= the reference's conv padding).
+//
+// Roles: warp 0 TMA producer, warp 1 TMEM alloc + MMA issue, warps 2..9 epilogue (lane quarter = warp % 4,
+// column half = (warp - 2) / 4).
+// Reference semantics: modules/block.py:54-82 (ResidualBlock.forward) + modules/wavenet.py:100 (bottleneck add).
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace wnb {
+using namespace tc;
+typedef __nv_bfloat16 bf16;
+
+struct ResDev {
+  int B, T, tiles_per_seq, num_tiles;
+  int ntaps, t_off[3];
+  const float* bias1;   // [2C] packed like W1 rows
+  const float* bias2;   // [2C] = [res ; skip]
+  int write_res, skips_init;
+  long long* dbg;
+};
+
+constexpr int RB_THREADS = 320;
+constexpr int RB_EPI_THREADS = 256;
+constexpr int RB_TILE = 128;
+constexpr int RB_ABYTES = RB_TILE * 128;
+
+template <int C>
+struct RCfg {
+  static constexpr int KB = C / 64;
+  static constexpr int BBYTES = C * 128;                       // [C rows x 64] bf16
+  static constexpr int STAGE = RB_ABYTES + BBYTES;
+  static constexpr int ACT = KB * RB_ABYTES;
+  static constexpr int STAGING = RB_ABYTES;                    // 16 KB output staging
+  static constexpr int NSTAGE = (C == 256) ? 3 : 5;
+  static constexpr int SMEM = NSTAGE * STAGE + ACT + STAGING + 1024 + 256;
+};
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// one 64-channel K block (4 UMMA K-steps), N = C columns
+template <int C>
+__device__ __forceinline__ void mma_kblock(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, bool first) {
+  constexpr uint32_t idesc = make_idesc_bf16(RB_TILE, C);
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4)
+    umma_bf16(tmem_d, make_smem_desc_sw128(a_addr + k4 * 32), make_smem_desc_sw128(b_addr + k4 * 32), idesc,
+              (first && k4 == 0) ? 0u : 1u);
+}
+
+#define RB_STAMP(slot) do { if (p.dbg && blockIdx.x == 0 && it < 8) p.dbg[it * 16 + (slot)] = clock64(); } while (0)
+
+template <int C>
+__global__ void __launch_bounds__(RB_THREADS, 1)
+resblock_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
+                const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_res,
+                const __grid_constant__ CUtensorMap map_skips, const ResDev p) {
+  using K = RCfg<C>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t act_base = smem_base + K::NSTAGE * K::STAGE;
+  const uint32_t stg_base = act_base + K::ACT;
+  const uint32_t bar_base = stg_base + K::STAGING;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (K::NSTAGE + s); };
+  const uint32_t bb = bar_base + 8u * (2 * K::NSTAGE);
+  const uint32_t accA_full = bb, accB_full = bb + 8, e1a_done = bb + 16, e1b_done = bb + 24, e2a_done = bb + 32,
+                 e2b_done = bb + 40, tmem_slot = bb + 48;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&map_x);
+    prefetch_tensormap(&map_w1);
+    prefetch_tensormap(&map_w2);
+    prefetch_tensormap(&map_res);
+    prefetch_tensormap(&map_skips);
+    for (int s = 0; s < K::NSTAGE; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accA_full, 1);
+    mbar_init(accB_full, 1);
+    mbar_init(e1a_done, RB_EPI_THREADS);
+    mbar_init(e1b_done, RB_EPI_THREADS);
+    mbar_init(e2a_done, RB_EPI_THREADS);
+    mbar_init(e2b_done, RB_EPI_THREADS);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 2 * C);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  const uint32_t tmemA = tmem_base, tmemB = tmem_base + C;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto next = [&]() {
+        if (++stage == K::NSTAGE) { stage = 0; phase ^= 1; }
+      };
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int b = tile / p.tiles_per_seq;
+        const int t0 = (tile - b * p.tiles_per_seq) * RB_TILE;
+        // G1a, G1b: x taps + W1 half
+        for (int half = 0; half < 2; ++half) {
+          for (int kb = 0; kb < p.ntaps * K::KB; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            const uint32_t sa = smem_base + stage * K::STAGE;
+            mbar_expect_tx(full_bar(stage), K::STAGE);
+            const int tap = kb / K::KB, cb = kb - tap * K::KB;
+            tma_load_3d(sa, &map_x, full_bar(stage), cb * 64, t0 + p.t_off[tap], b);
+            tma_load_2d(sa + RB_ABYTES, &map_w1, full_bar(stage), kb * 64, half * C);
+            next();
+          }
+        }
+        // G2r, x(t) part: x block + Wproj block
+        for (int kb = 0; kb < K::KB; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * K::STAGE;
+          mbar_expect_tx(full_bar(stage), K::STAGE);
+          tma_load_3d(sa, &map_x, full_bar(stage), kb * 64, t0, b);
+          tma_load_2d(sa + RB_ABYTES, &map_w2, full_bar(stage), C + kb * 64, 0);
+          next();
+        }
+        // G2r act part (Wres) then G2s (folded skip weights): weights only
+        for (int part = 0; part < 2; ++part) {
+          for (int kb = 0; kb < K::KB; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            const uint32_t sa = smem_base + stage * K::STAGE;
+            mbar_expect_tx(full_bar(stage), K::BBYTES);
+            tma_load_2d(sa + RB_ABYTES, &map_w2, full_bar(stage), kb * 64, part * C);
+            next();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto next = [&]() {
+        if (++stage == K::NSTAGE) { stage = 0; phase ^= 1; }
+      };
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t prev = (uint32_t)((it - 1) & 1), cur = (uint32_t)(it & 1);
+        RB_STAMP(0);
+        for (int half = 0; half < 2; ++half) {
+          if (it > 0) {
+            mbar_wait(half == 0 ? e2a_done : e2b_done, prev);   // region drained by the previous tile's epilogue 2
+            tc_fence_after();
+          }
+          for (int kb = 0; kb < p.ntaps * K::KB; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * K::STAGE;
+            mma_kblock<C>(half == 0 ? tmemA : tmemB, sa, sa + RB_ABYTES, kb == 0);
+            umma_commit(empty_bar(stage));
+            next();
+          }
+          umma_commit(half == 0 ? accA_full : accB_full);
+          RB_STAMP(1 + half);
+        }
+        // G2r: x(t) * Wproj into region A (needs E1a to have drained A)
+        mbar_wait(e1a_done, cur);
+        tc_fence_after();
+        RB_STAMP(3);
+        for (int kb = 0; kb < K::KB; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * K::STAGE;
+          mma_kblock<C>(tmemA, sa, sa + RB_ABYTES, kb == 0);
+          umma_commit(empty_bar(stage));
+          next();
+        }
+        // G2r: act * Wres (act blocks of half 0 are ready; half 1 after E1b)
+        for (int kb = 0; kb < K::KB; ++kb) {
+          if (kb == K::KB / 2) {
+            mbar_wait(e1b_done, cur);
+            tc_fence_after();
+            RB_STAMP(4);
+          }
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * K::STAGE;
+          mma_kblock<C>(tmemA, act_base + kb * RB_ABYTES, sa + RB_ABYTES, false);
+          umma_commit(empty_bar(stage));
+          next();
+        }
+        umma_commit(accA_full);
+        RB_STAMP(5);
+        // G2s: act * (Wbn Wskip) into region B (drained by E1b, waited above)
+        for (int kb = 0; kb < K::KB; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * K::STAGE;
+          mma_kblock<C>(tmemB, act_base + kb * RB_ABYTES, sa + RB_ABYTES, kb == 0);
+          umma_commit(empty_bar(stage));
+          next();
+        }
+        umma_commit(accB_full);
+        RB_STAMP(6);
+      }
+    }
+  } else {
+    // ================================ epilogue warps ================================
+    const int q = warp & 3;
+    const int h = (warp - 2) >> 2;                 // column half handled by this warp
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const bool issuer = (threadIdx.x == 64);
+    uint8_t* stg_row = smem_gen + (stg_base - smem_base) + row * 128;
+    const int sw = row & 7;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int b = tile / p.tiles_per_seq;
+      const int t0 = (tile - b * p.tiles_per_seq) * RB_TILE;
+
+      // ---------------- E1a / E1b: gate -> act (bf16, swizzled K-major blocks) ----------------
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(half == 0 ? accA_full : accB_full, 0u);
+        tc_fence_after();
+        if (issuer) RB_STAMP(8 + half);
+        const uint32_t treg = (half == 0 ? tmemA : tmemB) + lane_off;
+#pragma unroll 1
+        for (int cc = 0; cc < C / 4; cc += 16) {
+          const int col = h * (C / 4) + cc;        // channel inside the half; tanh col = col, sigmoid col = C/2+col
+          float a[16], g[16];
+          tmem_ld16(treg + col, a);
+          tmem_ld16(treg + C / 2 + col, g);
+          const float4* bt = reinterpret_cast<const float4*>(p.bias1 + half * C + col);
+          const float4* bs = reinterpret_cast<const float4*>(p.bias1 + half * C + C / 2 + col);
+          float bta[16], bsa[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 u = __ldg(bt + j), v = __ldg(bs + j);
+            bta[4 * j] = u.x; bta[4 * j + 1] = u.y; bta[4 * j + 2] = u.z; bta[4 * j + 3] = u.w;
+            bsa[4 * j] = v.x; bsa[4 * j + 1] = v.y; bsa[4 * j + 2] = v.z; bsa[4 * j + 3] = v.w;
+          }
+          tmem_wait_ld();
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const float v0 = tanh_approx(a[i] + bta[i]) * sigmoid_approx(g[i] + bsa[i]);
+            const float v1 = tanh_approx(a[i + 1] + bta[i + 1]) * sigmoid_approx(g[i + 1] + bsa[i + 1]);
+            pk[i >> 1] = pack_bf16x2(v0, v1);
+          }
+          const int ch = half * (C / 2) + col;     // global channel of a[0]
+          const int kb = ch >> 6, ci = (ch & 63) >> 3;
+          uint8_t* blk = smem_gen + (act_base - smem_base) + kb * RB_ABYTES + row * 128;
+          *reinterpret_cast<uint4*>(blk + ((ci ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(blk + (((ci + 1) ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(half == 0 ? e1a_done : e1b_done);
+      }
+
+      // ---------------- E2a: res = acc + bias -> bf16 -> staging -> TMA store ----------------
+      mbar_wait(accA_full, 1u);
+      tc_fence_after();
+      if (issuer) RB_STAMP(10);
+      if (p.write_res) {
+#pragma unroll 1
+        for (int c = 0; c < C / 64; ++c) {
+          const int col = c * 64 + h * 32;
+          float a[32];
+          tmem_ld16(tmemA + lane_off + col, a);
+          tmem_ld16(tmemA + lane_off + col + 16, a + 16);
+          const float4* bp = reinterpret_cast<const float4*>(p.bias2 + col);
+          float bv[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 u = __ldg(bp + j);
+            bv[4 * j] = u.x; bv[4 * j + 1] = u.y; bv[4 * j + 2] = u.z; bv[4 * j + 3] = u.w;
+          }
+          tmem_wait_ld();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) pk[i >> 1] = pack_bf16x2(a[i] + bv[i], a[i + 1] + bv[i + 1]);
+          if (issuer) bulk_wait_read0();            // previous TMA op has finished reading the staging buffer
+          epi_bar();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(stg_row + (((4 * h + j) ^ sw) << 4)) =
+                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          fence_proxy_async_smem();
+          epi_bar();
+          if (issuer) {
+            tma_store_3d(&map_res, stg_base, c * 64, t0, b);
+            bulk_commit();
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(e2a_done);
+
+      // ---------------- E2b: skips (+)= acc + bias (fp32) -> staging -> TMA reduce-add ----------------
+      mbar_wait(accB_full, 1u);
+      tc_fence_after();
+      if (issuer) RB_STAMP(11);
+#pragma unroll 1
+      for (int c = 0; c < C / 32; ++c) {
+        const int col = c * 32 + h * 16;
+        float a[16];
+        tmem_ld16(tmemB + lane_off + col, a);
+        const float4* bp = reinterpret_cast<const float4*>(p.bias2 + C + col);
+        float bv[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 u = __ldg(bp + j);
+          bv[4 * j] = u.x; bv[4 * j + 1] = u.y; bv[4 * j + 2] = u.z; bv[4 * j + 3] = u.w;
+        }
+        tmem_wait_ld();
+        if (issuer) bulk_wait_read0();
+        epi_bar();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(stg_row + (((4 * h + j) ^ sw) << 4)) =
+              make_float4(a[4 * j] + bv[4 * j], a[4 * j + 1] + bv[4 * j + 1], a[4 * j + 2] + bv[4 * j + 2],
+                          a[4 * j + 3] + bv[4 * j + 3]);
+        fence_proxy_async_smem();
+        epi_bar();
+        if (issuer) {
+          if (p.skips_init) tma_store_3d(&map_skips, stg_base, c * 32, t0, b);
+          else tma_reduce_add_3d(&map_skips, stg_base, c * 32, t0, b);
+          bulk_commit();
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(e2b_done);
+      if (issuer) RB_STAMP(12);
+    }
+    if (issuer) bulk_wait0();      // all output traffic issued by this CTA has completed
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * C);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn rb_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static int rb_map_2d(CUtensorMap* m, const void* ptr, int rows, int cols, int boxrows) {
+  EncodeTiledFn enc = rb_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return 5; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)boxrows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(2d) failed: %d", (int)r); return 5; }
+  return 0;
+}
+
+// NLC tensor [B][T][C] of `esize`-byte elements -> boxes [1][128 frames][128 bytes], 128B swizzle
+static int rb_map_nlc(CUtensorMap* m, const void* ptr, int B, int T, int C, int esize) {
+  EncodeTiledFn enc = rb_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return 5; }
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)C * esize, (cuuint64_t)T * C * esize};
+  cuuint32_t box[3] = {(cuuint32_t)(128 / esize), RB_TILE, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                   const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(nlc esize %d) failed: %d", esize, (int)r); return 5; }
+  return 0;
+}
+
+template <int C>
+static int launch_resblock(const CUtensorMap& mx, const CUtensorMap& mw1, const CUtensorMap& mw2,
+                           const CUtensorMap& mres, const CUtensorMap& msk, const ResDev& p, cudaStream_t st) {
+  using K = RCfg<C>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    WNB_CUDA_OK(cudaFuncSetAttribute(resblock_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  resblock_kernel<C><<<grid, RB_THREADS, K::SMEM, st>>>(mx, mw1, mw2, mres, msk, p);
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+__global__ void leaky_to_bf16_kernel(long long n4, const float4* x, uint2* y) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    uint2 o;
+    o.x = pack_bf16x2(leaky(v.x), leaky(v.y));
+    o.y = pack_bf16x2(leaky(v.z), leaky(v.w));
+    y[i] = o;
+  }
+}
+
+}  // namespace wnb
+
+using namespace wnb;
+
+extern "C" int wnb200_resblock_fwd_tc(const wnb200_resblock_t* a, void* stream) {
+  WNB_CHECK_ARG(a != nullptr, "resblock_fwd_tc: null argument");
+  const int C = a->C;
+  WNB_CHECK_ARG(C == 128 || C == 256, "resblock_fwd_tc: C=%d not in {128,256}", C);
+  WNB_CHECK_ARG(a->ntaps >= 1 && a->ntaps <= 3, "resblock_fwd_tc: ntaps=%d not in 1..3", a->ntaps);
+  if (a->B == 0 || a->T == 0) return 0;
+  WNB_CHECK_ARG(a->x && a->w1 && a->w2 && a->bias1 && a->bias2 && a->skips, "resblock_fwd_tc: null pointer");
+  ResDev p;
+  memset(&p, 0, sizeof(p));
+  p.B = a->B; p.T = a->T;
+  p.tiles_per_seq = ceil_div(a->T, RB_TILE);
+  p.num_tiles = p.tiles_per_seq * a->B;
+  p.ntaps = a->ntaps;
+  for (int j = 0; j < 3; ++j) p.t_off[j] = a->t_off[j];
+  p.bias1 = a->bias1; p.bias2 = a->bias2;
+  p.write_res = a->res != nullptr; p.skips_init = a->skips_init;
+  p.dbg = (long long*)a->dbg;
+  CUtensorMap mx, mw1, mw2, mres, msk;
+  int rc;
+  if ((rc = rb_map_nlc(&mx, a->x, a->B, a->T, C, 2))) return rc;
+  if ((rc = rb_map_2d(&mw1, a->w1, 2 * C, a->ntaps * C, C))) return rc;
+  if ((rc = rb_map_2d(&mw2, a->w2, 2 * C, 2 * C, C))) return rc;
+  if ((rc = rb_map_nlc(&mres, a->res ? a->res : a->x, a->B, a->T, C, 2))) return rc;
+  if ((rc = rb_map_nlc(&msk, a->skips, a->B, a->T, C, 4))) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return C == 256 ? launch_resblock<256>(mx, mw1, mw2, mres, msk, p, st)
+                  : launch_resblock<128>(mx, mw1, mw2, mres, msk, p, st);
+}
+
+extern "C" int wnb200_leaky_to_bf16(int64_t n, const float* x, void* y, void* stream) {
+  WNB_CHECK_ARG(n % 4 == 0, "leaky_to_bf16: n must be a multiple of 4");
+  if (n == 0) return 0;
+  WNB_CHECK_ARG(x && y, "leaky_to_bf16: null pointer");
+  const long long n4 = n / 4;
+  long long g = (n4 + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  leaky_to_bf16_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(n4, (const float4*)x, (uint2*)y);
+  WNB_LAUNCH_OK();
+  return 0;
+}

@@ -339,9 +339,9 @@ extern "C" int wnb200_taps_fwd(int dtype, int B, int T_out, int M, int nsrc, con
   WNB_CHECK_ARG(dtype == WNB200_F32 || dtype == WNB200_BF16, "taps_fwd: bad dtype %d", dtype);
   WNB_CHECK_ARG(nsrc >= 1 && nsrc <= WNB200_MAX_SRC, "taps_fwd: nsrc %d out of range", nsrc);
   WNB_CHECK_ARG(B >= 0 && T_out >= 0 && M >= 1, "taps_fwd: bad shape B=%d T=%d M=%d", B, T_out, M);
+  if (B == 0 || T_out == 0) return 0;
   WNB_CHECK_ARG(out != nullptr && srcs != nullptr, "taps_fwd: null pointer");
   WNB_CHECK_ARG(B <= 65535, "taps_fwd: batch %d > 65535", B);
-  if (B == 0 || T_out == 0) return 0;
   TapsParams p;
   p.B = B; p.T_out = T_out; p.M = M; p.nsrc = nsrc;
   p.rows = (epilogue == WNB200_EPI_GATE) ? 2 * ceil_div(M, 64) * 64 : M;
@@ -357,8 +357,8 @@ extern "C" int wnb200_taps_fwd(int dtype, int B, int T_out, int M, int nsrc, con
 extern "C" int wnb200_taps_wgrad(int dtype, int B, int T_out, int M, const wnb200_src_t* src, const void* dout,
                                  float* dw, void* stream) {
   WNB_CHECK_ARG(dtype == WNB200_F32 || dtype == WNB200_BF16, "taps_wgrad: bad dtype %d", dtype);
-  WNB_CHECK_ARG(src && src->x && dout && dw, "taps_wgrad: null pointer");
   if (B == 0 || T_out == 0) return 0;
+  WNB_CHECK_ARG(src && src->x && dout && dw, "taps_wgrad: null pointer");
   WgradParams p;
   p.B = B; p.T_out = T_out; p.M = M; p.nchunk = ceil_div(T_out, WG_CHUNK);
   fill_src(p.src, *src);
@@ -375,8 +375,8 @@ extern "C" int wnb200_taps_wgrad(int dtype, int B, int T_out, int M, const wnb20
 extern "C" int wnb200_channel_reduce(int dtype, int B, int C, int T, const void* a, const void* b_or_null,
                                      float* out, void* stream) {
   WNB_CHECK_ARG(dtype == WNB200_F32 || dtype == WNB200_BF16, "channel_reduce: bad dtype %d", dtype);
-  WNB_CHECK_ARG(a && out, "channel_reduce: null pointer");
   if (B == 0 || T == 0 || C == 0) return 0;
+  WNB_CHECK_ARG(a && out, "channel_reduce: null pointer");
   WNB_CHECK_ARG(B <= 65535, "channel_reduce: batch too large");
   dim3 grid(C, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -50,8 +50,16 @@ def pack_block(block, bottleneck):
     w2 = torch.cat([torch.cat([wres, wproj], 1), torch.cat([fold, torch.zeros_like(fold)], 1)], 0)
     b2 = torch.cat([block.conv1x1_residual.bias.detach().float() + block.residual_proj.bias.detach().float(),
                     wbn @ block.conv1x1_skip.bias.detach().float() + bottleneck.bias.detach().float()], 0)
-    return {"w1": _bf16(w1), "b1": b1.contiguous(), "w2": _bf16(w2), "b2": b2.contiguous(),
-            "offsets": list(block.offsets), "C": C}
+    pk = {"w1": _bf16(w1), "b1": b1.contiguous(), "w2": _bf16(w2), "b2": b2.contiguous(),
+          "offsets": list(block.offsets), "C": C}
+    if C in (128, 256):
+        # pipelined kernel: rows per half = [tanh C/2 ; sigmoid C/2]
+        hc = C // 2
+        order = torch.cat([torch.arange(0, hc), torch.arange(C, C + hc), torch.arange(hc, C),
+                           torch.arange(C + hc, 2 * C)]).to(w1.device)
+        pk["w1h"] = _bf16(w1[order])
+        pk["b1h"] = b1[order].contiguous()
+    return pk
 
 
 def pack_head(head, C):
@@ -83,7 +91,8 @@ def _cached(module, name, build):
 
 
 def chain(x_nlc, C, offsets, epi1, w1, b1, n1, n2=0, use_x2=0, epi2=0, w2=None, b2=None, y_nlc=None, skips=None,
-          skips_init=0, skips_act=None, out_ncl=None, n_out=0, softmax=0):
+          skips_init=0, skips_act=None, out_ncl=None, n_out=0, softmax=0, dbg=None):
+    _lib.current_tag = "resblock" if epi2 == EPI2_RESBLOCK else ("head" if epi2 == EPI2_HEAD else "dense")
     a = _lib.Chain()
     B, T, _ = x_nlc.shape
     a.B, a.T, a.C = B, T, C
@@ -96,7 +105,35 @@ def chain(x_nlc, C, offsets, epi1, w1, b1, n1, n2=0, use_x2=0, epi2=0, w2=None, 
     p = lambda t: 0 if t is None else t.data_ptr()
     a.x, a.w1, a.bias1, a.w2, a.bias2 = p(x_nlc), p(w1), p(b1), p(w2), p(b2)
     a.y_nlc, a.skips, a.skips_act, a.out_ncl = p(y_nlc), p(skips), p(skips_act), p(out_ncl)
-    _lib.call("wnb200_chain_fwd_tc", ctypes.byref(a), ops._stream())
+    a.dbg = p(dbg)
+    try:
+        _lib.call("wnb200_chain_fwd_tc", ctypes.byref(a), ops._stream())
+    finally:
+        _lib.current_tag = None
+
+
+def resblock(x_nlc, pk, res, skips, skips_init, dbg=None):
+    """Pipelined fused block (C = 128 / 256)."""
+    a = _lib.ResBlock()
+    B, T, C = x_nlc.shape
+    a.B, a.T, a.C, a.ntaps = B, T, C, len(pk["offsets"])
+    for j, o in enumerate(pk["offsets"]):
+        a.t_off[j] = int(o)
+    a.skips_init = int(skips_init)
+    p = lambda t: 0 if t is None else t.data_ptr()
+    a.x, a.w1, a.bias1, a.w2, a.bias2 = p(x_nlc), p(pk["w1h"]), p(pk["b1h"]), p(pk["w2"]), p(pk["b2"])
+    a.res, a.skips, a.dbg = p(res), p(skips), p(dbg)
+    _lib.current_tag = "resblock"
+    try:
+        _lib.call("wnb200_resblock_fwd_tc", ctypes.byref(a), ops._stream())
+    finally:
+        _lib.current_tag = None
+
+
+def leaky_to_bf16(x):
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.call("wnb200_leaky_to_bf16", x.numel(), ops._p(x), ops._p(y), ops._stream())
+    return y
 
 
 def ncl_to_nlc_bf16(x):
@@ -127,8 +164,15 @@ def run_blocks(h, blocks, bottlenecks, packs, skips, first_init, want_act):
     """Residual stack on NLC bf16 activations: one fused launch per layer.  Returns (h, skips_act)."""
     B, T, C = h.shape
     buf = [h, torch.empty_like(h)]
-    skips_act = torch.empty_like(h) if want_act else None
     n = len(packs)
+    if C in (128, 256):
+        for l, pk in enumerate(packs):
+            last = l == n - 1
+            resblock(buf[0], pk, None if last else buf[1], skips, first_init and l == 0)
+            if not last:
+                buf = [buf[1], buf[0]]
+        return buf[0], (leaky_to_bf16(skips) if want_act else None)
+    skips_act = torch.empty_like(h) if want_act else None
     for l, pk in enumerate(packs):
         last = l == n - 1
         chain(buf[0], C, pk["offsets"], TC_GATE, pk["w1"], pk["b1"], 2 * C, n2=2 * C, use_x2=1,
