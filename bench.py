@@ -293,9 +293,10 @@ def main():
         per.setdefault(name, []).append(a.elapsed_time(b))
     peaks = load_peaks()
     C = w["C"]
-    dom = "wnb200_chain_fwd_tc:resblock" if "wnb200_chain_fwd_tc:resblock" in per else "wnb200_taps_fwd"
+    tagged = [k for k in per if k.endswith(":resblock")]
+    dom = tagged[0] if tagged else "wnb200_taps_fwd"
     tot = sum(sum(v) for v in per.values())
-    if dom == "wnb200_chain_fwd_tc:resblock":
+    if tagged:
         flops_launch = 16 * C * C * samples                        # block + bottleneck as written
         avg_ms = float(np.mean(per[dom]))
     else:                                                           # generic path: all contraction launches together

@@ -184,6 +184,7 @@ typedef struct {
   int32_t B, T, C, ntaps;
   int32_t t_off[3];
   int32_t skips_init;     /* 1: skips = contribution, 0: skips += contribution */
+  int32_t variant;        /* 0 = default (CTA-pair kernel, cta_group::2), 1 = single-CTA kernel */
   const void* x;          /* NLC bf16 [B,T,C] */
   const void* w1;
   const float* bias1;

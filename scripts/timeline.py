@@ -9,6 +9,7 @@ from wavenet_speech_b200 import fastpath as FP
 C, B, T = 256, 32, 16384
 d = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 v2 = len(sys.argv) > 2
+variant = int(sys.argv[2][1:]) - 1 if v2 else 0   # "v2" -> single-CTA (1), "v3" -> CTA pair (2)
 torch.manual_seed(0)
 blk = W.ResidualBlock(C, C, 2, d, causal=True)
 bn = torch.nn.Conv1d(C, C, 1)
@@ -22,7 +23,7 @@ for i in range(4):
     if i == 3:
         ev[0].record()
     if v2:
-        FP.resblock(x, pk, res, skips, False, dbg=dbg)
+        FP.resblock(x, pk, res, skips, False, dbg=dbg, variant=variant)
     else:
         FP.chain(x, C, pk["offsets"], FP.TC_GATE, pk["w1"], pk["b1"], 2 * C, n2=2 * C, use_x2=1,
                  epi2=FP.EPI2_RESBLOCK, w2=pk["w2"], b2=pk["b2"], y_nlc=res, skips=skips, skips_init=0, dbg=dbg)
@@ -33,10 +34,10 @@ print("kernel %.3f ms -> %.1f TFLOP/s (16*C*C flop/sample)" % (ms, 16 * C * C * 
 t = dbg.cpu().view(8, 16)
 if v2:
     names = {0: "G1start", 1: "G1a_iss", 2: "G1b_iss", 3: "e1a_seen", 4: "e1b_seen", 5: "G2r_iss", 6: "G2s_iss",
-             8: "E1a_go", 9: "E1b_go", 10: "E2a_go", 11: "E2b_go", 12: "tile_done"}
+             8: "E1a_go", 9: "E1b_go", 10: "E2a_go", 11: "E2b_go", 12: "tile_done", 13: "wfullG1a", 14: "wfullG1ab"}
 else:
     names = {0: "G1start", 1: "G1_iss", 2: "act_ready", 3: "G2_iss", 4: "g1_full", 5: "act_done", 6: "g2_full",
              7: "tile_done"}
 t0 = int(t[0, 0])
 for it in range(6):
-    print("tile", it, " ".join("%s=%d" % (n, int(t[it, i]) - t0) for i, n in sorted(names.items())))
+    print("tile", it, " ".join("%s=%d" % (n, int(t[it, i]) - (0 if n.startswith("wfull") else t0)) for i, n in sorted(names.items())))

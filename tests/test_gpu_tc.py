@@ -84,18 +84,20 @@ def test_fused_block(C, k, d, causal, T, B):
              epi2=FP.EPI2_RESBLOCK, w2=pk["w2"], b2=pk["b2"], y_nlc=None, skips=skips2, skips_init=1)
     assert rel(skips2.permute(0, 2, 1), contrib_ref) <= BF16_TOL
     if C in (128, 256):
-        # pipelined kernel (TMA store / reduce-add outputs)
-        res3 = torch.empty_like(xn)
-        skips3 = prev.clone()
-        FP.resblock(xn, pk, res3, skips3, False)
-        torch.cuda.synchronize()
-        assert rel(res3.float().permute(0, 2, 1), res_ref) <= BF16_TOL, ("res v2", rel(res3.float().permute(0, 2, 1), res_ref))
-        assert rel((skips3 - prev).permute(0, 2, 1), contrib_ref) <= BF16_TOL
-        skips4 = torch.full_like(prev, 1e9)
-        FP.resblock(xn, pk, None, skips4, True)
-        assert rel(skips4.permute(0, 2, 1), contrib_ref) <= BF16_TOL
-        # the two kernels agree closely with each other
-        assert rel(res3.float(), res.float().cpu()) <= 1e-2
+        # pipelined kernels (TMA store / reduce-add outputs): variant 1 = single CTA, 2 = CTA pair (cta_group::2)
+        for variant in (1, 2):
+            res3 = torch.empty_like(xn)
+            skips3 = prev.clone()
+            FP.resblock(xn, pk, res3, skips3, False, variant=variant)
+            torch.cuda.synchronize()
+            e = rel(res3.float().permute(0, 2, 1), res_ref)
+            assert e <= BF16_TOL, ("res variant %d" % variant, e)
+            assert rel((skips3 - prev).permute(0, 2, 1), contrib_ref) <= BF16_TOL, variant
+            skips4 = torch.full_like(prev, 1e9)
+            FP.resblock(xn, pk, None, skips4, True, variant=variant)
+            assert rel(skips4.permute(0, 2, 1), contrib_ref) <= BF16_TOL, variant
+            # the kernels agree closely with each other
+            assert rel(res3.float(), res.float().cpu()) <= 1e-2, variant
 
 
 @pytest.mark.parametrize("C,nl,T,B,softmax", [(64, 4, 300, 2, True), (128, 5, 1000, 2, False),

@@ -33,7 +33,8 @@ class Chain(ctypes.Structure):
 class ResBlock(ctypes.Structure):
     """Mirror of wnb200_resblock_t."""
     _fields_ = [("B", ctypes.c_int32), ("T", ctypes.c_int32), ("C", ctypes.c_int32), ("ntaps", ctypes.c_int32),
-                ("t_off", ctypes.c_int32 * 3), ("skips_init", ctypes.c_int32), ("x", c_void_p), ("w1", c_void_p),
+                ("t_off", ctypes.c_int32 * 3), ("skips_init", ctypes.c_int32), ("variant", ctypes.c_int32),
+                ("_pad", ctypes.c_int32), ("x", c_void_p), ("w1", c_void_p),
                 ("bias1", c_void_p), ("w2", c_void_p), ("bias2", c_void_p), ("res", c_void_p), ("skips", c_void_p),
                 ("dbg", c_void_p)]
 

@@ -381,6 +381,348 @@ resblock_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   }
 }
 
+
+// =========================================================================================================
+// CTA-pair variant (cta_group::2): two CTAs of a cluster process 256 consecutive frames.  Each CTA owns 128
+// frames (its own A tiles, act tile, TMEM lanes and outputs); every weight block is split between the two CTAs
+// (each loads C/2 of its C rows) and the leader CTA's single MMA thread issues M=256 tcgen05.mma instructions
+// that read both shared memories and write both tensor memories.  Compared with the single-CTA kernel this
+// halves the weight bytes each SM pulls from L2 (the limiter there) and shrinks a stage to 32 KB.
+// Barriers: full[s] lives in the leader (count 2 = leader's expect_tx + peer's arrive; both CTAs' TMA bytes are
+// signalled on it); empty[s] / acc*_full are per CTA and receive the multicast tcgen05.commit; the four
+// epilogue->MMA barriers live in the leader and collect 2 x 256 arrivals.
+// =========================================================================================================
+template <int C>
+struct R2Cfg {
+  static constexpr int KB = C / 64;
+  static constexpr int BHBYTES = (C / 2) * 128;                // this CTA's half of a [C x 64] weight block
+  static constexpr int STAGE = RB_ABYTES + BHBYTES;
+  static constexpr int ACT = KB * RB_ABYTES;
+  static constexpr int STAGING = 2 * RB_ABYTES;                // double-buffered output staging
+  static constexpr int NSTAGE = (C == 256) ? 4 : 6;
+  static constexpr int SMEM = NSTAGE * STAGE + ACT + STAGING + 1024 + 256;
+};
+
+template <int C>
+__device__ __forceinline__ void mma_kblock_2sm(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, bool first) {
+  constexpr uint32_t idesc = make_idesc_bf16(2 * RB_TILE, C);
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4)
+    umma_bf16_2sm(tmem_d, make_smem_desc_sw128(a_addr + k4 * 32), make_smem_desc_sw128(b_addr + k4 * 32), idesc,
+                  (first && k4 == 0) ? 0u : 1u);
+}
+
+template <int C>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RB_THREADS, 1)
+resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
+                 const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_res,
+                 const __grid_constant__ CUtensorMap map_skips, const ResDev p) {
+  using K = R2Cfg<C>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t act_base = smem_base + K::NSTAGE * K::STAGE;
+  const uint32_t stg_base = act_base + K::ACT;
+  const uint32_t bar_base = stg_base + K::STAGING;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (K::NSTAGE + s); };
+  const uint32_t bb = bar_base + 8u * (2 * K::NSTAGE);
+  const uint32_t accA_full = bb, accB_full = bb + 8, e1a_done = bb + 16, e1b_done = bb + 24, e2a_done = bb + 32,
+                 e2b_done = bb + 40, tmem_slot = bb + 48;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&map_x);
+    prefetch_tensormap(&map_w1);
+    prefetch_tensormap(&map_w2);
+    prefetch_tensormap(&map_res);
+    prefetch_tensormap(&map_skips);
+    for (int s = 0; s < K::NSTAGE; ++s) {
+      mbar_init(full_bar(s), 2);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accA_full, 1);
+    mbar_init(accB_full, 1);
+    mbar_init(e1a_done, 2 * RB_EPI_THREADS);
+    mbar_init(e1b_done, 2 * RB_EPI_THREADS);
+    mbar_init(e2a_done, 2 * RB_EPI_THREADS);
+    mbar_init(e2b_done, 2 * RB_EPI_THREADS);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_slot, 2 * C);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();          // barriers of both CTAs initialised before any remote arrive / TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  const uint32_t tmemA = tmem_base, tmemB = tmem_base + C;
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto next = [&]() {
+        if (++stage == K::NSTAGE) { stage = 0; phase ^= 1; }
+      };
+      const int wrow = (int)rank * (C / 2);       // this CTA's rows inside a [C x 64] weight block
+      auto begin_stage = [&](uint32_t bytes_per_cta) -> uint32_t {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * bytes_per_cta);
+        return mapa_shared(full_bar(stage), 0);
+      };
+      auto end_stage = [&](uint32_t lfull) {
+        if (rank != 0) mbar_arrive_cluster(lfull);
+        next();
+      };
+      for (int pt = pair; pt < p.num_tiles; pt += npairs) {
+        const int b = pt / p.tiles_per_seq;
+        const int t0 = (pt - b * p.tiles_per_seq) * (2 * RB_TILE) + (int)rank * RB_TILE;
+        for (int half = 0; half < 2; ++half) {
+          for (int kb = 0; kb < p.ntaps * K::KB; ++kb) {
+            const uint32_t sa = smem_base + stage * K::STAGE;
+            const uint32_t lfull = begin_stage(K::STAGE);
+            const int tap = kb / K::KB, cb = kb - tap * K::KB;
+            tma_load_3d_2sm(sa, &map_x, lfull, cb * 64, t0 + p.t_off[tap], b);
+            tma_load_2d_2sm(sa + RB_ABYTES, &map_w1, lfull, kb * 64, half * C + wrow);
+            end_stage(lfull);
+          }
+        }
+        for (int kb = 0; kb < K::KB; ++kb) {
+          const uint32_t sa = smem_base + stage * K::STAGE;
+          const uint32_t lfull = begin_stage(K::STAGE);
+          tma_load_3d_2sm(sa, &map_x, lfull, kb * 64, t0, b);
+          tma_load_2d_2sm(sa + RB_ABYTES, &map_w2, lfull, C + kb * 64, wrow);
+          end_stage(lfull);
+        }
+        for (int part = 0; part < 2; ++part) {
+          for (int kb = 0; kb < K::KB; ++kb) {
+            const uint32_t sa = smem_base + stage * K::STAGE;
+            const uint32_t lfull = begin_stage(K::BHBYTES);
+            tma_load_2d_2sm(sa + RB_ABYTES, &map_w2, lfull, kb * 64, part * C + wrow);
+            end_stage(lfull);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader CTA only) ================================
+    if (lane == 0 && rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto next = [&]() {
+        if (++stage == K::NSTAGE) { stage = 0; phase ^= 1; }
+      };
+      int it = 0;
+      for (int pt = pair; pt < p.num_tiles; pt += npairs, ++it) {
+        const uint32_t prev = (uint32_t)((it - 1) & 1), cur = (uint32_t)(it & 1);
+        long long wfull = 0;
+        RB_STAMP(0);
+        for (int half = 0; half < 2; ++half) {
+          if (it > 0) {
+            mbar_wait(half == 0 ? e2a_done : e2b_done, prev);
+            tc_fence_after();
+          }
+          for (int kb = 0; kb < p.ntaps * K::KB; ++kb) {
+            { const long long c0 = clock64(); mbar_wait(full_bar(stage), phase); wfull += clock64() - c0; }
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * K::STAGE;
+            mma_kblock_2sm<C>(half == 0 ? tmemA : tmemB, sa, sa + RB_ABYTES, kb == 0);
+            umma_commit_2sm(empty_bar(stage));
+            next();
+          }
+          umma_commit_2sm(half == 0 ? accA_full : accB_full);
+          RB_STAMP(1 + half);
+          if (p.dbg && blockIdx.x == 0 && it < 8) p.dbg[it * 16 + 13 + half] = wfull;
+        }
+        mbar_wait(e1a_done, cur);
+        tc_fence_after();
+        RB_STAMP(3);
+        for (int kb = 0; kb < K::KB; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * K::STAGE;
+          mma_kblock_2sm<C>(tmemA, sa, sa + RB_ABYTES, kb == 0);
+          umma_commit_2sm(empty_bar(stage));
+          next();
+        }
+        for (int kb = 0; kb < K::KB; ++kb) {
+          if (kb == K::KB / 2) {
+            mbar_wait(e1b_done, cur);
+            tc_fence_after();
+            RB_STAMP(4);
+          }
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * K::STAGE;
+          mma_kblock_2sm<C>(tmemA, act_base + kb * RB_ABYTES, sa + RB_ABYTES, false);
+          umma_commit_2sm(empty_bar(stage));
+          next();
+        }
+        umma_commit_2sm(accA_full);
+        RB_STAMP(5);
+        for (int kb = 0; kb < K::KB; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * K::STAGE;
+          mma_kblock_2sm<C>(tmemB, act_base + kb * RB_ABYTES, sa + RB_ABYTES, kb == 0);
+          umma_commit_2sm(empty_bar(stage));
+          next();
+        }
+        umma_commit_2sm(accB_full);
+        RB_STAMP(6);
+      }
+    }
+  } else {
+    // ================================ epilogue warps (both CTAs) ================================
+    const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const bool issuer = (threadIdx.x == 64);
+    const int sw = row & 7;
+    const uint32_t r_e1a = mapa_shared(e1a_done, 0), r_e1b = mapa_shared(e1b_done, 0),
+                   r_e2a = mapa_shared(e2a_done, 0), r_e2b = mapa_shared(e2b_done, 0);
+    uint32_t nchunk = 0;
+    int it = 0;
+    for (int pt = pair; pt < p.num_tiles; pt += npairs, ++it) {
+      const int b = pt / p.tiles_per_seq;
+      const int t0 = (pt - b * p.tiles_per_seq) * (2 * RB_TILE) + (int)rank * RB_TILE;
+
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(half == 0 ? accA_full : accB_full, 0u);
+        tc_fence_after();
+        if (issuer && rank == 0) RB_STAMP(8 + half);
+        const uint32_t treg = (half == 0 ? tmemA : tmemB) + lane_off;
+#pragma unroll 1
+        for (int cc = 0; cc < C / 4; cc += 16) {
+          const int col = h * (C / 4) + cc;
+          float a[16], g[16];
+          tmem_ld16(treg + col, a);
+          tmem_ld16(treg + C / 2 + col, g);
+          const float4* bt = reinterpret_cast<const float4*>(p.bias1 + half * C + col);
+          const float4* bs = reinterpret_cast<const float4*>(p.bias1 + half * C + C / 2 + col);
+          float bta[16], bsa[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 u = __ldg(bt + j), v = __ldg(bs + j);
+            bta[4 * j] = u.x; bta[4 * j + 1] = u.y; bta[4 * j + 2] = u.z; bta[4 * j + 3] = u.w;
+            bsa[4 * j] = v.x; bsa[4 * j + 1] = v.y; bsa[4 * j + 2] = v.z; bsa[4 * j + 3] = v.w;
+          }
+          tmem_wait_ld();
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const float v0 = tanh_approx(a[i] + bta[i]) * sigmoid_approx(g[i] + bsa[i]);
+            const float v1 = tanh_approx(a[i + 1] + bta[i + 1]) * sigmoid_approx(g[i + 1] + bsa[i + 1]);
+            pk[i >> 1] = pack_bf16x2(v0, v1);
+          }
+          const int ch = half * (C / 2) + col;
+          const int kb = ch >> 6, ci = (ch & 63) >> 3;
+          uint8_t* blk = smem_gen + (act_base - smem_base) + kb * RB_ABYTES + row * 128;
+          *reinterpret_cast<uint4*>(blk + ((ci ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(blk + (((ci + 1) ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive_cluster(half == 0 ? r_e1a : r_e1b);
+      }
+
+      // ---- E2a: res ----
+      mbar_wait(accA_full, 1u);
+      tc_fence_after();
+      if (issuer && rank == 0) RB_STAMP(10);
+      if (p.write_res) {
+#pragma unroll 1
+        for (int c = 0; c < C / 64; ++c, ++nchunk) {
+          const int col = c * 64 + h * 32;
+          float a[32];
+          tmem_ld16(tmemA + lane_off + col, a);
+          tmem_ld16(tmemA + lane_off + col + 16, a + 16);
+          const float4* bp = reinterpret_cast<const float4*>(p.bias2 + col);
+          float bv[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 u = __ldg(bp + j);
+            bv[4 * j] = u.x; bv[4 * j + 1] = u.y; bv[4 * j + 2] = u.z; bv[4 * j + 3] = u.w;
+          }
+          tmem_wait_ld();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) pk[i >> 1] = pack_bf16x2(a[i] + bv[i], a[i + 1] + bv[i + 1]);
+          const uint32_t boff = (nchunk & 1u) * RB_ABYTES;
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          epi_bar();
+          uint8_t* srow = smem_gen + (stg_base - smem_base) + boff + row * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(srow + (((4 * h + j) ^ sw) << 4)) =
+                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          fence_proxy_async_smem();
+          epi_bar();
+          if (issuer) {
+            tma_store_3d(&map_res, stg_base + boff, c * 64, t0, b);
+            bulk_commit();
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(r_e2a);
+
+      // ---- E2b: skips ----
+      mbar_wait(accB_full, 1u);
+      tc_fence_after();
+      if (issuer && rank == 0) RB_STAMP(11);
+#pragma unroll 1
+      for (int c = 0; c < C / 32; ++c, ++nchunk) {
+        const int col = c * 32 + h * 16;
+        float a[16];
+        tmem_ld16(tmemB + lane_off + col, a);
+        const float4* bp = reinterpret_cast<const float4*>(p.bias2 + C + col);
+        float bv[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 u = __ldg(bp + j);
+          bv[4 * j] = u.x; bv[4 * j + 1] = u.y; bv[4 * j + 2] = u.z; bv[4 * j + 3] = u.w;
+        }
+        tmem_wait_ld();
+        const uint32_t boff = (nchunk & 1u) * RB_ABYTES;
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        epi_bar();
+        uint8_t* srow = smem_gen + (stg_base - smem_base) + boff + row * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(srow + (((4 * h + j) ^ sw) << 4)) =
+              make_float4(a[4 * j] + bv[4 * j], a[4 * j + 1] + bv[4 * j + 1], a[4 * j + 2] + bv[4 * j + 2],
+                          a[4 * j + 3] + bv[4 * j + 3]);
+        fence_proxy_async_smem();
+        epi_bar();
+        if (issuer) {
+          if (p.skips_init) tma_store_3d(&map_skips, stg_base + boff, c * 32, t0, b);
+          else tma_reduce_add_3d(&map_skips, stg_base + boff, c * 32, t0, b);
+          bulk_commit();
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(r_e2b);
+      if (issuer && rank == 0) RB_STAMP(12);
+    }
+    if (issuer) bulk_wait0();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();          // the peer's shared / tensor memory must outlive the leader's last MMA
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 2 * C);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -444,6 +786,25 @@ static int launch_resblock(const CUtensorMap& mx, const CUtensorMap& mw1, const 
   return 0;
 }
 
+template <int C>
+static int launch_resblock2(const CUtensorMap& mx, const CUtensorMap& mw1, const CUtensorMap& mw2,
+                            const CUtensorMap& mres, const CUtensorMap& msk, const ResDev& p, cudaStream_t st) {
+  using K = R2Cfg<C>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    WNB_CUDA_OK(cudaFuncSetAttribute(resblock2_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int pairs = sms / 2;
+  if (p.num_tiles < pairs) pairs = p.num_tiles;
+  resblock2_kernel<C><<<2 * pairs, RB_THREADS, K::SMEM, st>>>(mx, mw1, mw2, mres, msk, p);
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
 __global__ void leaky_to_bf16_kernel(long long n4, const float4* x, uint2* y) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = x[i];
@@ -475,14 +836,22 @@ extern "C" int wnb200_resblock_fwd_tc(const wnb200_resblock_t* a, void* stream) 
   p.bias1 = a->bias1; p.bias2 = a->bias2;
   p.write_res = a->res != nullptr; p.skips_init = a->skips_init;
   p.dbg = (long long*)a->dbg;
+  const bool pair = a->variant != 1;     // 0 / 2: CTA-pair kernel (default); 1: single-CTA kernel
+  const int wbox = pair ? C / 2 : C;
   CUtensorMap mx, mw1, mw2, mres, msk;
   int rc;
   if ((rc = rb_map_nlc(&mx, a->x, a->B, a->T, C, 2))) return rc;
-  if ((rc = rb_map_2d(&mw1, a->w1, 2 * C, a->ntaps * C, C))) return rc;
-  if ((rc = rb_map_2d(&mw2, a->w2, 2 * C, 2 * C, C))) return rc;
+  if ((rc = rb_map_2d(&mw1, a->w1, 2 * C, a->ntaps * C, wbox))) return rc;
+  if ((rc = rb_map_2d(&mw2, a->w2, 2 * C, 2 * C, wbox))) return rc;
   if ((rc = rb_map_nlc(&mres, a->res ? a->res : a->x, a->B, a->T, C, 2))) return rc;
   if ((rc = rb_map_nlc(&msk, a->skips, a->B, a->T, C, 4))) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (pair) {
+    p.tiles_per_seq = ceil_div(a->T, 2 * RB_TILE);
+    p.num_tiles = p.tiles_per_seq * a->B;
+    return C == 256 ? launch_resblock2<256>(mx, mw1, mw2, mres, msk, p, st)
+                    : launch_resblock2<128>(mx, mw1, mw2, mres, msk, p, st);
+  }
   return C == 256 ? launch_resblock<256>(mx, mw1, mw2, mres, msk, p, st)
                   : launch_resblock<128>(mx, mw1, mw2, mres, msk, p, st);
 }

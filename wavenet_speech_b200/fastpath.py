@@ -112,14 +112,18 @@ def chain(x_nlc, C, offsets, epi1, w1, b1, n1, n2=0, use_x2=0, epi2=0, w2=None, 
         _lib.current_tag = None
 
 
-def resblock(x_nlc, pk, res, skips, skips_init, dbg=None):
-    """Pipelined fused block (C = 128 / 256)."""
+RESBLOCK_VARIANT = int(__import__("os").environ.get("WNB200_RESBLOCK_VARIANT", "0"))
+
+
+def resblock(x_nlc, pk, res, skips, skips_init, dbg=None, variant=None):
+    """Pipelined fused block (C = 128 / 256).  variant 0/2 = CTA-pair kernel, 1 = single-CTA kernel."""
     a = _lib.ResBlock()
     B, T, C = x_nlc.shape
     a.B, a.T, a.C, a.ntaps = B, T, C, len(pk["offsets"])
     for j, o in enumerate(pk["offsets"]):
         a.t_off[j] = int(o)
     a.skips_init = int(skips_init)
+    a.variant = RESBLOCK_VARIANT if variant is None else int(variant)
     p = lambda t: 0 if t is None else t.data_ptr()
     a.x, a.w1, a.bias1, a.w2, a.bias2 = p(x_nlc), p(pk["w1h"]), p(pk["b1h"]), p(pk["w2"]), p(pk["b2"])
     a.res, a.skips, a.dbg = p(res), p(skips), p(dbg)
