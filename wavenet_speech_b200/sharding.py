@@ -1,0 +1,121 @@
+"""Multi-GPU partitioning of the hot path (one process per GPU, torch.distributed; NCCL on GPUs, gloo in the
+CPU tests).  The reference has no distributed code at all; both schemes below are exact.
+
+* batch sharding  -- reads are independent through every op on the path.  Inference needs no collective; training
+  needs one gradient all-reduce (SUM) per step, with the batch-MEAN cross-entropy term pre-scaled by 1/world and
+  the batch-SUM CTC term left alone (legacy_code/train.py:39 vs :46).
+* time sharding   -- the networks are fixed-receptive-field stacks: a rank that owns frames [s, e) of a long read
+  needs `halo_left` / `halo_right` extra input samples from its neighbours, recomputes that fringe and keeps only
+  its own span.  Zero padding at the TRUE ends of the read is what the kernels do natively (TMA / bounds-check
+  zero fill), so the first and last rank simply get no halo on that side.
+"""
+import torch
+
+from .functional import tap_offsets
+
+
+# ----------------------------------------------------------------------------------------- batch sharding
+def shard_range(n, rank, world):
+    """Contiguous split of n items: -> (start, end) of `rank` (sizes differ by at most one)."""
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def joint_loss_for_backward(xe_local_sum_over_t, ctc_local_sum, T, T_ctc, world):
+    """Local loss whose gradient, all-reduced with SUM, equals the reference's single-process gradient of
+    xe/T + ctc/T' (legacy_code/train.py:50-54).  `xe_local_sum_over_t` is already a mean over the LOCAL batch."""
+    return xe_local_sum_over_t / (T * world) + ctc_local_sum / T_ctc
+
+
+def allreduce_gradients(params, group=None, bucket_bytes=32 << 20):
+    """Bucketed SUM all-reduce of .grad over the process group (NCCL over NVLink on GPUs).  Buckets are filled in
+    reverse parameter order -- the order backward produces them -- and each is reduced as one flat tensor."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    grads = [p.grad for p in reversed(list(params)) if p.grad is not None]
+    n_buckets, i = 0, 0
+    while i < len(grads):
+        bucket, size = [], 0
+        dt, dev = grads[i].dtype, grads[i].device
+        while i < len(grads) and grads[i].dtype == dt and (not bucket or size < bucket_bytes):
+            bucket.append(grads[i])
+            size += grads[i].numel() * grads[i].element_size()
+            i += 1
+        flat = torch.cat([g.reshape(-1) for g in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        off = 0
+        for g in bucket:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        n_buckets += 1
+    return n_buckets
+
+
+# ----------------------------------------------------------------------------------------- receptive fields
+def stack_halo(tap_lists):
+    """tap_lists: one list of frame offsets per layer -> (left, right) input frames a frame depends on."""
+    left = sum(max(0, -min(offs)) for offs in tap_lists)
+    right = sum(max(0, max(offs)) for offs in tap_lists)
+    return left, right
+
+
+def wavenet_halo(model):
+    """Config-2 WaveNet (entry k=2 + 2 x (1..512)): (2047, 0)."""
+    taps = [tap_offsets(model.entry_kwidth, 1, True)]
+    taps += [tap_offsets(k, d, True) for (_ci, _co, k, d) in model.layers]
+    return stack_halo(taps)
+
+
+def raw_ctcnet_halo(model):
+    """RawCTCNet: featuriser (reads x[t'-(fk-1) .. t']) + input block + stack.  ecoli config, fk=3: (51, 45)."""
+    fk = model.feature_kwidth
+    taps = [[j - (fk - 1) for j in range(fk)]]
+    taps.append(tap_offsets(model.input_kernel_size, model.input_dilation, model.causal))
+    taps += [tap_offsets(k, d, model.causal) for (_ci, _co, k, d) in model.layers]
+    return stack_halo(taps)
+
+
+# ----------------------------------------------------------------------------------------- time sharding
+def time_shard_plan(T, rank, world, halo_left, halo_right, align=1):
+    """-> dict(start, end, lo, hi): this rank owns input frames [start, end) and must read [lo, hi)."""
+    per = -(-T // world)
+    per = -(-per // align) * align
+    start, end = min(T, rank * per), min(T, (rank + 1) * per)
+    return {"start": start, "end": end, "lo": max(0, start - halo_left), "hi": min(T, end + halo_right)}
+
+
+def exchange_halo(x_shard, plan, rank, world, group=None):
+    """x_shard holds frames [start, end) of a (B, C, T) tensor split along time.  Fetch the missing
+    [lo, start) from the left neighbour(s) and [end, hi) from the right one(s) with point-to-point sends;
+    returns the extended tensor for frames [lo, hi).  Halos are assumed not to span more than one neighbour."""
+    import torch.distributed as dist
+    need_l, need_r = plan["start"] - plan["lo"], plan["hi"] - plan["end"]
+    B, C, _ = x_shard.shape
+    left = x_shard.new_empty((B, C, need_l))
+    right = x_shard.new_empty((B, C, need_r))
+    reqs = []
+    # what the neighbours need from me mirrors what I need from them (same halo widths everywhere)
+    if rank > 0 and need_l > 0:
+        reqs.append(dist.irecv(left, src=rank - 1, group=group))
+    if rank < world - 1 and need_r > 0:
+        reqs.append(dist.irecv(right, src=rank + 1, group=group))
+    hl, hr = plan.get("halo_left", need_l), plan.get("halo_right", need_r)
+    if rank < world - 1 and hl > 0:
+        reqs.append(dist.isend(x_shard[:, :, -hl:].contiguous(), dst=rank + 1, group=group))
+    if rank > 0 and hr > 0:
+        reqs.append(dist.isend(x_shard[:, :, :hr].contiguous(), dst=rank - 1, group=group))
+    for r in reqs:
+        r.wait()
+    return torch.cat([left, x_shard, right], 2)
+
+
+def time_sharded_forward(forward_fn, x_ext, plan, T, out_extra=0):
+    """Run `forward_fn` on the halo-extended input of one rank and keep the output frames this rank owns.
+    Output frame g of the full read corresponds to local frame g - lo.  `out_extra` = frames the network appends
+    (RawCTCNet: feature_kwidth - 1, emitted by the last rank only)."""
+    y = forward_fn(x_ext)
+    lo, start, end = plan["lo"], plan["start"], plan["end"]
+    stop = end + (out_extra if end == T else 0)
+    return y[:, :, start - lo:stop - lo]
