@@ -63,12 +63,15 @@ class ClockSampler(object):
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.window = index, None, [], None
+
+    def mark(self, t0, t1):
+        self.window = (t0, t1)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -77,7 +80,7 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -90,7 +93,11 @@ class ClockSampler(object):
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = self.lines
+        if self.window is not None:
+            inside = [l for l in lines if self.window[0] <= l[0] <= self.window[1] + 0.05]
+            lines = inside if len(inside) >= 2 else lines
+        for _ts, ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -190,7 +197,7 @@ def run_reference(args, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
@@ -244,20 +251,22 @@ def main():
         return float(t.item())
 
     # ---- device-resident timing ----------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     with torch.no_grad():
         for _ in range(args.warmup):
             y = net(x_dev)
         barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
         l0 = _lib.launch_count
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        w0 = time.time()
         e0.record()
         for _ in range(args.steps):
             y = net(x_dev)
         e1.record()
         barrier()
+        sampler.mark(w0, time.time())
         ms = max_over_ranks(e0.elapsed_time(e1))
         launches = _lib.launch_count - l0
         clocks = sampler.stop()

@@ -196,6 +196,26 @@ typedef struct {
 } wnb200_resblock_t;
 int wnb200_resblock_fwd_tc(const wnb200_resblock_t* args /*host*/, void* stream);
 
+
+/* Dense channel contraction on tensor cores (CTA pair), NLC bf16 in:
+ *   y[b,t,:] = epi(W [x[b,t+off_0,:]; x[b,t+off_1,:]; ...] + bias),   W bf16 [N][ntaps*Cin] (tap-major columns)
+ * mode 0: y = bf16 NLC [B,T,N] (N %% 64 == 0), optional LeakyReLU  -- entry conv (wavenet.py:54,93), first 1x1 of
+ *         the heads (wavenet.py:68-69), RawCTCNet feature 1x1 (raw_ctcnet.py:60-61)
+ * mode 1: y = NCL [B,n_out,T] (bf16 or fp32), optional channel softmax -- last 1x1 of the heads + softmax
+ *         (wavenet.py:70-71,103-109).  N = n_out rounded up to 16, padded rows of W / bias are zero. */
+typedef struct {
+  int32_t B, T, Cin, ntaps;
+  int32_t t_off[3];
+  int32_t N;
+  int32_t mode, leaky, n_out, softmax, out_f32;
+  int32_t _pad;
+  const void* x;
+  const void* w;
+  const float* bias;
+  void* y;
+} wnb200_dense_t;
+int wnb200_dense_fwd_tc(const wnb200_dense_t* args /*host*/, void* stream);
+
 /* y = bf16(LeakyReLU_0.01(x)), n a multiple of 4: turns the fp32 skip sum into the head's input
  * (first LeakyReLU of output_stack, wavenet.py:67). */
 int wnb200_leaky_to_bf16(int64_t n, const float* x, void* y, void* stream);

@@ -47,6 +47,49 @@ def test_single_contraction(C, k, T, B):
     assert e <= 1e-2, e
 
 
+@pytest.mark.parametrize("Cin,N,k,T,B,leaky", [(64, 64, 2, 300, 2, 0), (256, 256, 2, 257, 3, 1), (128, 192, 1, 520, 1, 1),
+                                               (256, 64, 3, 100, 2, 0)])
+def test_dense_nlc(Cin, N, k, T, B, leaky):
+    """CTA-pair dense contraction, NLC output (entry conv / first 1x1 of the head)."""
+    torch.manual_seed(Cin + N + k)
+    w = r16(torch.randn(N, Cin, k) / (Cin * k) ** 0.5)
+    bias = torch.randn(N) * 0.1
+    x = r16(torch.randn(B, Cin, T))
+    offs = [j - (k - 1) for j in range(k)]
+    ref = O.causal_conv1d(x, w, bias, 1)
+    if leaky:
+        ref = torch.nn.functional.leaky_relu(ref, 0.01)
+    y = FP.dense(FP.ncl_to_nlc_bf16(x.cuda()), offs, FP._bf16(FP._taps_matrix(w)).cuda(), bias.cuda(), N, leaky=leaky)
+    torch.cuda.synchronize()
+    assert rel(y.float().permute(0, 2, 1), ref) <= 1e-2
+
+
+@pytest.mark.parametrize("C,n_out,T,B,softmax,dt", [(256, 256, 384, 2, True, torch.bfloat16),
+                                                    (256, 256, 130, 2, False, torch.bfloat16),
+                                                    (128, 5, 200, 3, False, torch.float32),
+                                                    (64, 8, 77, 2, True, torch.float32),
+                                                    (256, 40, 257, 1, True, torch.bfloat16)])
+def test_dense_head(C, n_out, T, B, softmax, dt):
+    """CTA-pair dense contraction with the NCL / softmax epilogue (TMA-store and direct-store variants)."""
+    torch.manual_seed(C + n_out + T)
+    w = r16(torch.randn(n_out, C) / C ** 0.5)
+    bias = torch.randn(n_out) * 0.1
+    x = r16(torch.randn(B, C, T))
+    ref = torch.nn.functional.conv1d(x, w.unsqueeze(2), bias)
+    if softmax:
+        ref = torch.softmax(ref, 1)
+    n2 = (n_out + 15) // 16 * 16
+    wp = torch.zeros(n2, C)
+    wp[:n_out] = w
+    bp = torch.zeros(n2)
+    bp[:n_out] = bias
+    out = torch.empty(B, n_out, T, dtype=dt, device="cuda")
+    FP.dense(FP.ncl_to_nlc_bf16(x.cuda()), [0], FP._bf16(wp).cuda(), bp.cuda(), n2, mode=1, out=out, n_out=n_out,
+             softmax=softmax)
+    torch.cuda.synchronize()
+    assert rel(out, ref) <= 1e-2, rel(out, ref)
+
+
 @pytest.mark.parametrize("C,k,d,causal,T,B", [(64, 2, 1, True, 128, 1), (64, 2, 4, True, 300, 2),
                                               (128, 2, 2, False, 200, 2), (256, 2, 8, True, 384, 2),
                                               (256, 2, 3, False, 130, 3), (256, 3, 2, False, 260, 1),
@@ -115,7 +158,7 @@ def test_wavenet_tc(C, nl, T, B, softmax):
         before = W._lib.launch_count
         y = net(x.cuda().bfloat16())
         assert y.dtype == torch.bfloat16 and tuple(y.shape) == tuple(ref.shape)
-    assert W._lib.launch_count - before == nl + 3 + (1 if C in (128, 256) else 0)   # transpose, entry, blocks, [leaky], head
+    assert W._lib.launch_count - before == nl + 4 + (1 if C in (128, 256) else 0)   # transpose, entry, blocks, [leaky], 2 x head
     e = rel(y, ref)
     assert e <= BF16_TOL, e
     if not softmax:

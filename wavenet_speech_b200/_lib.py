@@ -39,6 +39,15 @@ class ResBlock(ctypes.Structure):
                 ("dbg", c_void_p)]
 
 
+class Dense(ctypes.Structure):
+    """Mirror of wnb200_dense_t."""
+    _fields_ = [("B", ctypes.c_int32), ("T", ctypes.c_int32), ("Cin", ctypes.c_int32), ("ntaps", ctypes.c_int32),
+                ("t_off", ctypes.c_int32 * 3), ("N", ctypes.c_int32), ("mode", ctypes.c_int32),
+                ("leaky", ctypes.c_int32), ("n_out", ctypes.c_int32), ("softmax", ctypes.c_int32),
+                ("out_f32", ctypes.c_int32), ("_pad", ctypes.c_int32), ("x", c_void_p), ("w", c_void_p),
+                ("bias", c_void_p), ("y", c_void_p)]
+
+
 # name -> argtypes (return type is int unless listed in _RESTYPES)
 SIGNATURES = {
     "wnb200_last_error": [],
@@ -65,6 +74,7 @@ SIGNATURES = {
     "wnb200_argmax_channels": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "wnb200_chain_fwd_tc": [ctypes.POINTER(Chain), c_void_p],
     "wnb200_resblock_fwd_tc": [ctypes.POINTER(ResBlock), c_void_p],
+    "wnb200_dense_fwd_tc": [ctypes.POINTER(Dense), c_void_p],
     "wnb200_leaky_to_bf16": [c_int64, c_void_p, c_void_p, c_void_p],
     "wnb200_ncl_to_nlc_bf16": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "wnb200_nlc_to_ncl": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],

@@ -558,19 +558,6 @@ __global__ void nlc_to_ncl_kernel(int C, int Tn, const TI* x, TO* y) {
 }
 }  // namespace wnb
 
-extern "C" int wnb200_ncl_to_nlc_bf16(int dtype, int B, int C, int T_, const void* x, void* y, void* stream) {
-  WNB_CHECK_ARG(x && y, "ncl_to_nlc_bf16: null pointer");
-  WNB_CHECK_ARG(dtype == WNB200_F32 || dtype == WNB200_BF16, "ncl_to_nlc_bf16: bad dtype");
-  if (B == 0 || C == 0 || T_ == 0) return 0;
-  WNB_CHECK_ARG(B <= 65535 && ceil_div(C, 32) <= 65535, "ncl_to_nlc_bf16: shape too large");
-  dim3 grid(ceil_div(T_, 32), ceil_div(C, 32), B), block(32, 8);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == WNB200_F32) ncl_to_nlc_kernel<float><<<grid, block, 0, st>>>(C, T_, (const float*)x, (bf16*)y);
-  else ncl_to_nlc_kernel<bf16><<<grid, block, 0, st>>>(C, T_, (const bf16*)x, (bf16*)y);
-  WNB_LAUNCH_OK();
-  return 0;
-}
-
 extern "C" int wnb200_nlc_to_ncl(int out_dtype, int src_is_f32, int B, int C, int T_, const void* x, void* y,
                                  void* stream) {
   WNB_CHECK_ARG(x && y, "nlc_to_ncl: null pointer");

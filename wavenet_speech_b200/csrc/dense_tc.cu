@@ -1,0 +1,382 @@
+// Dense channel contraction on tensor cores, CTA pair, NLC bf16 input:
+//     y[b, t, :] = epi( W · [x[b, t+off_0, :] ; x[b, t+off_1, :] ; ...] + bias )          N <= 256 outputs
+// Used for the WaveNet entry conv (wavenet.py:54,93), both 1x1 convs of the output heads (wavenet.py:67-71,
+// raw_ctcnet.py:84-88, classifier.py:70-74) and RawCTCNet's feature 1x1 (raw_ctcnet.py:60).
+//
+// Same machinery as resblock2_kernel (cta_group::2, weights split across the pair, TMA-fed ring, multicast commits),
+// but one accumulator per tile: TMEM holds two N-column regions that alternate between tiles, so the epilogue of
+// tile i overlaps the MMAs of tile i+1.  Epilogues:
+//   NLC : (+bias, optional LeakyReLU) -> bf16 -> swizzled staging -> TMA store into an NLC tensor
+//   HEAD: (+bias, optional channel softmax, thread-local over TMEM columns + one cross-warp combine) ->
+//         transposed staging [channel][frame] -> TMA store into the NCL output (or direct stores when the NCL
+//         row pitch is not 16-byte aligned).
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tc_host.cuh"
+
+namespace wnb {
+using namespace tc;
+typedef __nv_bfloat16 bf16;
+
+struct DenseDev {
+  int B, T, tiles_per_seq, num_tiles;
+  int ntaps, t_off[3];
+  int kb_per_tap;   // Cin / 64
+  int N;            // accumulator columns (multiple of 16, <= 256)
+  int mode;         // 0 NLC store, 1 HEAD
+  int leaky;        // NLC: LeakyReLU(0.01) after bias
+  int n_out, softmax, out_f32, tma_out;
+  const float* bias;
+  void* out;        // HEAD direct-store fallback: NCL [B, n_out, T]
+};
+
+constexpr int DN_THREADS = 320;
+constexpr int DN_ABYTES = RB_TILE * 128;
+constexpr int DN_STAGE = 2 * DN_ABYTES;        // A block + up to 128 weight rows
+constexpr int DN_NSTAGE = 5;
+constexpr int DN_STAGING = 2 * DN_ABYTES;
+constexpr int DN_SCRATCH = 2 * RB_TILE * 8;    // softmax partials (max, sum) per column half
+constexpr int DN_SMEM = DN_NSTAGE * DN_STAGE + DN_STAGING + DN_SCRATCH + 1024 + 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DN_THREADS, 1)
+dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+              const __grid_constant__ CUtensorMap map_y, const DenseDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t stg_base = smem_base + DN_NSTAGE * DN_STAGE;
+  const uint32_t scr_base = stg_base + DN_STAGING;
+  const uint32_t bar_base = scr_base + DN_SCRATCH;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (DN_NSTAGE + s); };
+  const uint32_t bb = bar_base + 8u * (2 * DN_NSTAGE);
+  auto acc_full = [&](int r) { return bb + 8u * r; };
+  auto acc_empty = [&](int r) { return bb + 16u + 8u * r; };
+  const uint32_t tmem_slot = bb + 32;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int nkb = p.ntaps * p.kb_per_tap;
+  const uint32_t bhalf_bytes = (uint32_t)(p.N / 2) * 128u;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&map_x);
+    prefetch_tensormap(&map_w);
+    prefetch_tensormap(&map_y);
+    for (int s = 0; s < DN_NSTAGE; ++s) {
+      mbar_init(full_bar(s), 2);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int r = 0; r < 2; ++r) {
+      mbar_init(acc_full(r), 1);
+      mbar_init(acc_empty(r), 2 * 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_slot, 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = pair; pt < p.num_tiles; pt += npairs) {
+        const int b = pt / p.tiles_per_seq;
+        const int t0 = (pt - b * p.tiles_per_seq) * (2 * RB_TILE) + (int)rank * RB_TILE;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * DN_STAGE;
+          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * (DN_ABYTES + bhalf_bytes));
+          const uint32_t lfull = mapa_shared(full_bar(stage), 0);
+          const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
+          tma_load_3d_2sm(sa, &map_x, lfull, cb * 64, t0 + p.t_off[tap], b);
+          tma_load_2d_2sm(sa + DN_ABYTES, &map_w, lfull, kb * 64, (int)rank * (p.N / 2));
+          if (rank != 0) mbar_arrive_cluster(lfull);
+          if (++stage == DN_NSTAGE) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t idesc = make_idesc_bf16(2 * RB_TILE, p.N);
+      int it = 0;
+      for (int pt = pair; pt < p.num_tiles; pt += npairs, ++it) {
+        const int r = it & 1, use = it >> 1;
+        if (use > 0) {
+          mbar_wait(acc_empty(r), (uint32_t)((use - 1) & 1));
+          tc_fence_after();
+        }
+        const uint32_t tacc = tmem_base + (uint32_t)r * 256u;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * DN_STAGE;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            umma_bf16_2sm(tacc, make_smem_desc_sw128(sa + k4 * 32), make_smem_desc_sw128(sa + DN_ABYTES + k4 * 32),
+                          idesc, (kb == 0 && k4 == 0) ? 0u : 1u);
+          umma_commit_2sm(empty_bar(stage));
+          if (++stage == DN_NSTAGE) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(acc_full(r));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const bool issuer = (threadIdx.x == 64);
+    const int sw = row & 7;
+    float* scratch = reinterpret_cast<float*>(smem_gen + (scr_base - smem_base));
+    uint32_t nchunk = 0;
+    int it = 0;
+    for (int pt = pair; pt < p.num_tiles; pt += npairs, ++it) {
+      const int b = pt / p.tiles_per_seq;
+      const int t0 = (pt - b * p.tiles_per_seq) * (2 * RB_TILE) + (int)rank * RB_TILE;
+      const int r = it & 1, use = it >> 1;
+      const uint32_t tacc = tmem_base + (uint32_t)r * 256u + lane_off;
+      mbar_wait(acc_full(r), (uint32_t)(use & 1));
+      tc_fence_after();
+
+      if (p.mode == 0) {
+        // -------- (+bias, LeakyReLU) -> bf16 NLC, 64 channels per TMA store --------
+        for (int c = 0; c < p.N / 64; ++c, ++nchunk) {
+          const int col = c * 64 + h * 32;
+          float a[32];
+          tmem_ld16(tacc + col, a);
+          tmem_ld16(tacc + col + 16, a + 16);
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
+          float bv[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 u = __ldg(bp + j);
+            bv[4 * j] = u.x; bv[4 * j + 1] = u.y; bv[4 * j + 2] = u.z; bv[4 * j + 3] = u.w;
+          }
+          tmem_wait_ld();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float v0 = a[i] + bv[i], v1 = a[i + 1] + bv[i + 1];
+            if (p.leaky) { v0 = leaky(v0); v1 = leaky(v1); }
+            pk[i >> 1] = pack_bf16x2(v0, v1);
+          }
+          const uint32_t boff = (nchunk & 1u) * DN_ABYTES;
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          epi_bar();
+          uint8_t* srow = smem_gen + (stg_base - smem_base) + boff + row * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(srow + (((4 * h + j) ^ sw) << 4)) =
+                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          fence_proxy_async_smem();
+          epi_bar();
+          if (issuer) {
+            tma_store_3d(&map_y, stg_base + boff, c * 64, t0, b);
+            bulk_commit();
+          }
+        }
+      } else {
+        // -------- HEAD: optional channel softmax, output NCL --------
+        float mx = 0.f, inv = 1.f;
+        if (p.softmax) {
+          float m = -INFINITY, s = 0.f;
+          const int cbeg = h * (p.N / 2);
+          const int cend = (cbeg + p.N / 2) < p.n_out ? (cbeg + p.N / 2) : p.n_out;   // this warp's valid columns
+          for (int c0 = cbeg; c0 < cend; c0 += 16) {
+            float a[16];
+            tmem_ld16(tacc + c0, a);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (c0 + i < cend) {
+                const float v = a[i] + __ldg(p.bias + c0 + i);
+                if (v > m) { s *= __expf(m - v); m = v; }
+                s += __expf(v - m);
+              }
+            }
+          }
+          scratch[(h * RB_TILE + row) * 2] = m;
+          scratch[(h * RB_TILE + row) * 2 + 1] = s;
+          epi_bar();
+          const float m2 = scratch[((h ^ 1) * RB_TILE + row) * 2], s2 = scratch[((h ^ 1) * RB_TILE + row) * 2 + 1];
+          mx = fmaxf(m, m2);
+          const float tot = (m == -INFINITY ? 0.f : s * __expf(m - mx)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mx));
+          inv = 1.f / tot;
+          epi_bar();      // scratch may be rewritten by the next tile only after everyone has read it
+        }
+        const int esize = p.out_f32 ? 4 : 2;
+        for (int c32 = 0; c32 * 32 < p.n_out; ++c32, ++nchunk) {
+          const int col = c32 * 32 + h * 16;
+          float a[16];
+          tmem_ld16(tacc + col, a);
+          tmem_wait_ld();
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = col + i;
+            float x = a[i] + ((c < p.n_out) ? __ldg(p.bias + c) : 0.f);
+            if (p.softmax) x = __expf(x - mx) * inv;
+            v[i] = x;
+          }
+          if (p.tma_out) {
+            const uint32_t boff = (nchunk & 1u) * DN_ABYTES;
+            if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            epi_bar();
+            uint8_t* sbase = smem_gen + (stg_base - smem_base) + boff;     // [32 channels][128 frames]
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              uint8_t* dst = sbase + ((h * 16 + i) * RB_TILE + row) * esize;
+              if (p.out_f32) *reinterpret_cast<float*>(dst) = v[i];
+              else *reinterpret_cast<bf16*>(dst) = __float2bfloat16_rn(v[i]);
+            }
+            fence_proxy_async_smem();
+            epi_bar();
+            if (issuer) {
+              tma_store_3d(&map_y, stg_base + boff, t0, c32 * 32, b);
+              bulk_commit();
+            }
+          } else {
+            const int t = t0 + row;
+            if (t < p.T) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int c = col + i;
+                if (c < p.n_out) {
+                  const long long o = ((long long)b * p.n_out + c) * p.T + t;
+                  if (p.out_f32) reinterpret_cast<float*>(p.out)[o] = v[i];
+                  else reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16_rn(v[i]);
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(mapa_shared(acc_empty(r), 0));
+    }
+    if (issuer) bulk_wait0();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+// NCL -> NLC bf16: 64 x 64 (channels x frames) tiles through shared memory, 16/32-byte accesses on both sides
+template <typename T>
+__global__ void __launch_bounds__(256) ncl_to_nlc_v2_kernel(int C, int Tn, const T* x, bf16* y) {
+  __shared__ __align__(16) bf16 tile[64][72];     // [frame][channel], 144-byte rows
+  const int b = blockIdx.z, c0 = blockIdx.y * 64, t0 = blockIdx.x * 64;
+  const int tid = threadIdx.x;
+  {   // load: thread -> (channel = tid % 64, 16 consecutive frames)
+    const int c = tid & 63, tq = (tid >> 6) * 16;
+    const T* src = x + ((long long)b * C + (c0 + c)) * Tn + t0 + tq;
+    bf16 v[16];
+    const bool cok = (c0 + c) < C;
+    if (cok && t0 + tq + 16 <= Tn && (Tn % 8 == 0) && sizeof(T) == 2) {
+      *reinterpret_cast<uint4*>(&v[0]) = __ldg(reinterpret_cast<const uint4*>(src));
+      *reinterpret_cast<uint4*>(&v[8]) = __ldg(reinterpret_cast<const uint4*>(src) + 1);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        v[i] = (cok && t0 + tq + i < Tn) ? __float2bfloat16_rn(to_f32<T>(src[i])) : __float2bfloat16_rn(0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) tile[tq + i][c] = v[i];
+  }
+  __syncthreads();
+  {   // store: thread -> (frame = tid / 4, 16 consecutive channels)
+    const int t = tid >> 2, cq = (tid & 3) * 16;
+    if (t0 + t < Tn) {
+      bf16* dst = y + ((long long)b * Tn + t0 + t) * C + c0 + cq;
+      if (c0 + cq + 16 <= C && (C % 8 == 0)) {
+        reinterpret_cast<uint4*>(dst)[0] = *reinterpret_cast<const uint4*>(&tile[t][cq]);
+        reinterpret_cast<uint4*>(dst)[1] = *reinterpret_cast<const uint4*>(&tile[t][cq + 8]);
+      } else {
+        for (int i = 0; i < 16; ++i)
+          if (c0 + cq + i < C) dst[i] = tile[t][cq + i];
+      }
+    }
+  }
+}
+
+}  // namespace wnb
+
+using namespace wnb;
+
+extern "C" int wnb200_dense_fwd_tc(const wnb200_dense_t* a, void* stream) {
+  WNB_CHECK_ARG(a != nullptr, "dense_fwd_tc: null argument");
+  if (a->B == 0 || a->T == 0) return 0;
+  WNB_CHECK_ARG(a->Cin >= 64 && a->Cin % 64 == 0, "dense_fwd_tc: Cin=%d must be a multiple of 64", a->Cin);
+  WNB_CHECK_ARG(a->ntaps >= 1 && a->ntaps <= 3, "dense_fwd_tc: ntaps=%d not in 1..3", a->ntaps);
+  WNB_CHECK_ARG(a->N >= 16 && a->N <= 256 && a->N % 16 == 0, "dense_fwd_tc: N=%d must be a multiple of 16 <= 256", a->N);
+  WNB_CHECK_ARG(a->x && a->w && a->bias && a->y, "dense_fwd_tc: null pointer");
+  WNB_CHECK_ARG(a->mode == 0 || a->mode == 1, "dense_fwd_tc: bad mode");
+  WNB_CHECK_ARG(a->mode != 0 || a->N % 64 == 0, "dense_fwd_tc: NLC output needs N %% 64 == 0");
+  WNB_CHECK_ARG(a->mode != 1 || (a->n_out >= 1 && a->n_out <= a->N), "dense_fwd_tc: bad n_out");
+  DenseDev p;
+  memset(&p, 0, sizeof(p));
+  p.B = a->B; p.T = a->T;
+  p.tiles_per_seq = ceil_div(a->T, 2 * RB_TILE);
+  p.num_tiles = p.tiles_per_seq * a->B;
+  p.ntaps = a->ntaps;
+  for (int j = 0; j < 3; ++j) p.t_off[j] = a->t_off[j];
+  p.kb_per_tap = a->Cin / 64;
+  p.N = a->N; p.mode = a->mode; p.leaky = a->leaky;
+  p.n_out = a->n_out; p.softmax = a->softmax; p.out_f32 = a->out_f32;
+  p.bias = a->bias; p.out = a->y;
+  const int esize = a->out_f32 ? 4 : 2;
+  p.tma_out = (a->mode == 1 && ((long long)a->T * esize) % 16 == 0) ? 1 : 0;
+  CUtensorMap mx, mw, my;
+  int rc;
+  if ((rc = rb_map_nlc(&mx, a->x, a->B, a->T, a->Cin, 2))) return rc;
+  if ((rc = rb_map_2d(&mw, a->w, a->N, a->ntaps * a->Cin, a->N / 2))) return rc;
+  if (a->mode == 0) {
+    if ((rc = rb_map_nlc(&my, a->y, a->B, a->T, a->N, 2))) return rc;
+  } else if (p.tma_out) {
+    if ((rc = rb_map_ncl(&my, a->y, a->B, a->n_out, a->T, esize, RB_TILE, a->n_out < 32 ? a->n_out : 32))) return rc;
+  } else {
+    my = mx;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    WNB_CUDA_OK(cudaFuncSetAttribute(dense2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DN_SMEM));
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int pairs = sms / 2;
+  if (p.num_tiles < pairs) pairs = p.num_tiles;
+  dense2_kernel<<<2 * pairs, DN_THREADS, DN_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(mx, mw, my, p);
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_ncl_to_nlc_bf16(int dtype, int B, int C, int T_, const void* x, void* y, void* stream) {
+  WNB_CHECK_ARG(dtype == WNB200_F32 || dtype == WNB200_BF16, "ncl_to_nlc_bf16: bad dtype");
+  if (B == 0 || C == 0 || T_ == 0) return 0;
+  WNB_CHECK_ARG(x && y, "ncl_to_nlc_bf16: null pointer");
+  WNB_CHECK_ARG(B <= 65535 && ceil_div(C, 64) <= 65535, "ncl_to_nlc_bf16: shape too large");
+  dim3 grid(ceil_div(T_, 64), ceil_div(C, 64), B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == WNB200_F32) ncl_to_nlc_v2_kernel<float><<<grid, 256, 0, st>>>(C, T_, (const float*)x, (bf16*)y);
+  else ncl_to_nlc_v2_kernel<bf16><<<grid, 256, 0, st>>>(C, T_, (const bf16*)x, (bf16*)y);
+  WNB_LAUNCH_OK();
+  return 0;
+}

@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tc_host.cuh"
 
 namespace wnb {
 using namespace tc;
@@ -37,7 +38,6 @@ struct ResDev {
 
 constexpr int RB_THREADS = 320;
 constexpr int RB_EPI_THREADS = 256;
-constexpr int RB_TILE = 128;
 constexpr int RB_ABYTES = RB_TILE * 128;
 
 template <int C>
@@ -50,23 +50,6 @@ struct RCfg {
   static constexpr int NSTAGE = (C == 256) ? 3 : 5;
   static constexpr int SMEM = NSTAGE * STAGE + ACT + STAGING + 1024 + 256;
 };
-
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(m)),
-               "r"(src), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
-  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(m)),
-               "r"(src), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // one 64-channel K block (4 UMMA K-steps), N = C columns
 template <int C>
@@ -724,50 +707,6 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn rb_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
-}
-
-static int rb_map_2d(CUtensorMap* m, const void* ptr, int rows, int cols, int boxrows) {
-  EncodeTiledFn enc = rb_encode();
-  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return 5; }
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)boxrows};
-  cuuint32_t es[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(2d) failed: %d", (int)r); return 5; }
-  return 0;
-}
-
-// NLC tensor [B][T][C] of `esize`-byte elements -> boxes [1][128 frames][128 bytes], 128B swizzle
-static int rb_map_nlc(CUtensorMap* m, const void* ptr, int B, int T, int C, int esize) {
-  EncodeTiledFn enc = rb_encode();
-  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return 5; }
-  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
-  cuuint64_t strides[2] = {(cuuint64_t)C * esize, (cuuint64_t)T * C * esize};
-  cuuint32_t box[3] = {(cuuint32_t)(128 / esize), RB_TILE, 1};
-  cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = enc(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
-                   const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(nlc esize %d) failed: %d", esize, (int)r); return 5; }
-  return 0;
-}
-
 template <int C>
 static int launch_resblock(const CUtensorMap& mx, const CUtensorMap& mw1, const CUtensorMap& mw2,
                            const CUtensorMap& mres, const CUtensorMap& msk, const ResDev& p, cudaStream_t st) {

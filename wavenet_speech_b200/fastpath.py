@@ -134,6 +134,26 @@ def resblock(x_nlc, pk, res, skips, skips_init, dbg=None, variant=None):
         _lib.current_tag = None
 
 
+def dense(x_nlc, offsets, w, bias, N, mode=0, leaky=0, out=None, n_out=0, softmax=0):
+    """CTA-pair dense contraction.  mode 0 -> NLC bf16 [B,T,N]; mode 1 -> NCL `out` [B,n_out,T]."""
+    B, T, Cin = x_nlc.shape
+    a = _lib.Dense()
+    a.B, a.T, a.Cin, a.ntaps = B, T, Cin, len(offsets)
+    for j, o in enumerate(offsets):
+        a.t_off[j] = int(o)
+    a.N, a.mode, a.leaky, a.n_out, a.softmax = N, mode, int(leaky), n_out, int(softmax)
+    if mode == 0:
+        out = torch.empty((B, T, N), dtype=torch.bfloat16, device=x_nlc.device)
+    a.out_f32 = 1 if out.dtype == torch.float32 else 0
+    a.x, a.w, a.bias, a.y = x_nlc.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr()
+    _lib.current_tag = "dense" if mode == 0 else "head"
+    try:
+        _lib.call("wnb200_dense_fwd_tc", ctypes.byref(a), ops._stream())
+    finally:
+        _lib.current_tag = None
+    return out
+
+
 def leaky_to_bf16(x):
     y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     _lib.call("wnb200_leaky_to_bf16", x.numel(), ops._p(x), ops._p(y), ops._stream())
@@ -187,6 +207,14 @@ def run_blocks(h, blocks, bottlenecks, packs, skips, first_init, want_act):
     return buf[0], skips_act
 
 
+def run_head(skips_act, hd, out_dtype, softmax):
+    """LeakyReLU -> 1x1 -> LeakyReLU -> 1x1 [-> softmax] on the LeakyReLU'd skip sum: two dense launches."""
+    B, T, C = skips_act.shape
+    h1 = dense(skips_act, [0], hd["w1"], hd["b1"], C, leaky=1)
+    out = torch.empty((B, hd["n_out"], T), dtype=out_dtype, device=skips_act.device)
+    return dense(h1, [0], hd["w2"], hd["b2"], hd["n2"], mode=1, out=out, n_out=hd["n_out"], softmax=softmax)
+
+
 def try_wavenet_forward(model, signal):
     """WaveNet.forward (reference wavenet.py:88-111) on the tensor-core path, or None if not eligible."""
     if signal.dtype != torch.bfloat16 or not signal.is_cuda or signal.dim() != 3:
@@ -207,15 +235,10 @@ def try_wavenet_forward(model, signal):
     pk = _cached(model, "wavenet", build)
     B, _, T = signal.shape
     x = ncl_to_nlc_bf16(signal)
-    h = torch.empty_like(x)
-    chain(x, C, pk["entry"]["offsets"], TC_LINEAR, pk["entry"]["w1"], pk["entry"]["b1"], C, y_nlc=h)
+    h = dense(x, pk["entry"]["offsets"], pk["entry"]["w1"], pk["entry"]["b1"], C)
     skips = torch.empty((B, T, C), dtype=torch.float32, device=signal.device)
     _, skips_act = run_blocks(h, model.convolutions, model.bottlenecks, pk["blocks"], skips, True, True)
-    hd = pk["head"]
-    out = torch.empty((B, hd["n_out"], T), dtype=signal.dtype, device=signal.device)
-    chain(skips_act, C, [0], TC_LEAKY, hd["w1"], hd["b1"], C, n2=hd["n2"], epi2=EPI2_HEAD, w2=hd["w2"], b2=hd["b2"],
-          out_ncl=out, n_out=hd["n_out"], softmax=1 if model.softmax else 0)
-    return out
+    return run_head(skips_act, pk["head"], signal.dtype, model.softmax)
 
 
 def smoke_check(reference_forward):
