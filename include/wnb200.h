@@ -216,6 +216,16 @@ typedef struct {
 } wnb200_dense_t;
 int wnb200_dense_fwd_tc(const wnb200_dense_t* args /*host*/, void* stream);
 
+
+/* RawCTCNet featuriser, first layer: Conv1d(1, F, fk, padding=fk-1) + LeakyReLU (raw_ctcnet.py:57-59) on the raw
+ * signal x [B, 1, T] -> y NLC bf16 [B, T+fk-1, F].  w fp32 [F, fk], bias fp32 [F]. */
+int wnb200_featurize_nlc(int dtype, int B, int T, int F, int fk, const void* x, const float* w, const float* bias,
+                         void* y, void* stream);
+
+/* AvgPool1d(pool) (classifier.py:53,102) fused with the NCL -> NLC bf16 layout change:
+ * x NCL [B, C, T] -> y NLC bf16 [B, floor(T/pool), C]. */
+int wnb200_avgpool_ncl_to_nlc_bf16(int dtype, int B, int C, int T, int pool, const void* x, void* y, void* stream);
+
 /* y = bf16(LeakyReLU_0.01(x)), n a multiple of 4: turns the fp32 skip sum into the head's input
  * (first LeakyReLU of output_stack, wavenet.py:67). */
 int wnb200_leaky_to_bf16(int64_t n, const float* x, void* y, void* stream);

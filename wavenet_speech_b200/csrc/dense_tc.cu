@@ -315,6 +315,74 @@ __global__ void __launch_bounds__(256) ncl_to_nlc_v2_kernel(int C, int Tn, const
   }
 }
 
+
+// RawCTCNet featuriser, first layer (raw_ctcnet.py:57-59): Conv1d(1, F, fk, padding=fk-1) + LeakyReLU on the raw
+// 1-channel signal, written as NLC bf16 [B, T+fk-1, F].  Bandwidth kernel: 4 B read, 2F B written per frame.
+// Block = 32 frames x F channels; thread = 8 consecutive channels of one frame -> 16-byte coalesced stores.
+template <typename T>
+__global__ void __launch_bounds__(256) featurize_nlc_kernel(int Tn, int F, int fk, const T* x, const float* w,
+                                                            const float* bias, bf16* y) {
+  extern __shared__ float fsm[];            // [fk][F] weights (tap-major), [F] bias, [32 + fk] signal window
+  float* ws = fsm;
+  float* bs = fsm + fk * F;
+  float* xs = bs + F;
+  const int b = blockIdx.y, t0 = blockIdx.x * 32, To = Tn + fk - 1;
+  for (int i = threadIdx.x; i < fk * F; i += blockDim.x) {
+    const int j = i / F, f = i - j * F;
+    ws[i] = w[f * fk + j];
+  }
+  for (int i = threadIdx.x; i < F; i += blockDim.x) bs[i] = bias[i];
+  for (int i = threadIdx.x; i < 32 + fk - 1; i += blockDim.x) {
+    const int t = t0 + i - (fk - 1);
+    xs[i] = (t >= 0 && t < Tn) ? to_f32<T>(x[(long long)b * Tn + t]) : 0.f;
+  }
+  __syncthreads();
+  const int groups = F / 8;
+  for (int i = threadIdx.x; i < 32 * groups; i += blockDim.x) {
+    const int tl = i / groups, f0 = (i - tl * groups) * 8;
+    const int t = t0 + tl;
+    if (t >= To) continue;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = bs[f0 + k];
+    for (int j = 0; j < fk; ++j) {
+      const float xv = xs[tl + j];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = fmaf(ws[j * F + f0 + k], xv, acc[k]);
+    }
+    uint4 o;
+    o.x = pack_bf16x2(leaky(acc[0]), leaky(acc[1]));
+    o.y = pack_bf16x2(leaky(acc[2]), leaky(acc[3]));
+    o.z = pack_bf16x2(leaky(acc[4]), leaky(acc[5]));
+    o.w = pack_bf16x2(leaky(acc[6]), leaky(acc[7]));
+    *reinterpret_cast<uint4*>(y + ((long long)b * To + t) * F + f0) = o;
+  }
+}
+
+// AvgPool1d(pool) on an NCL tensor fused with the NCL -> NLC bf16 layout change (classifier.py:53,102):
+// y[b, to, c] = mean_i x[b, c, to*pool + i].  32 x 32 (channels x pooled frames) tiles through shared memory.
+template <typename T>
+__global__ void __launch_bounds__(256) avgpool_ncl_to_nlc_kernel(int C, int Tn, int To, int pool, const T* x, bf16* y) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+  const float inv = 1.f / (float)pool;
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, to = t0 + tx;
+    float s = 0.f;
+    if (c < C && to < To) {
+      const T* src = x + ((long long)b * C + c) * Tn + (long long)to * pool;
+      for (int k = 0; k < pool; ++k) s += to_f32<T>(src[k]);
+    }
+    tile[i][tx] = s * inv;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int to = t0 + i, c = c0 + tx;
+    if (to < To && c < C) y[((long long)b * To + to) * C + c] = __float2bfloat16_rn(tile[tx][i]);
+  }
+}
+
 }  // namespace wnb
 
 using namespace wnb;
@@ -377,6 +445,43 @@ extern "C" int wnb200_ncl_to_nlc_bf16(int dtype, int B, int C, int T_, const voi
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == WNB200_F32) ncl_to_nlc_v2_kernel<float><<<grid, 256, 0, st>>>(C, T_, (const float*)x, (bf16*)y);
   else ncl_to_nlc_v2_kernel<bf16><<<grid, 256, 0, st>>>(C, T_, (const bf16*)x, (bf16*)y);
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_featurize_nlc(int dtype, int B, int T_, int F, int fk, const void* x, const float* w,
+                                    const float* bias, void* y, void* stream) {
+  WNB_CHECK_ARG(dtype == WNB200_F32 || dtype == WNB200_BF16, "featurize_nlc: bad dtype");
+  WNB_CHECK_ARG(F >= 8 && F % 8 == 0 && fk >= 1 && fk <= 64, "featurize_nlc: F=%d fk=%d unsupported", F, fk);
+  if (B == 0 || T_ == 0) return 0;
+  WNB_CHECK_ARG(x && w && bias && y, "featurize_nlc: null pointer");
+  WNB_CHECK_ARG(B <= 65535, "featurize_nlc: batch too large");
+  const int To = T_ + fk - 1;
+  const size_t smem = sizeof(float) * ((size_t)fk * F + F + 32 + fk);
+  WNB_CHECK_ARG(smem <= 48 * 1024, "featurize_nlc: fk*F too large for the weight cache");
+  dim3 grid(ceil_div(To, 32), B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == WNB200_F32)
+    featurize_nlc_kernel<float><<<grid, 256, smem, st>>>(T_, F, fk, (const float*)x, w, bias, (bf16*)y);
+  else
+    featurize_nlc_kernel<bf16><<<grid, 256, smem, st>>>(T_, F, fk, (const bf16*)x, w, bias, (bf16*)y);
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_avgpool_ncl_to_nlc_bf16(int dtype, int B, int C, int T_, int pool, const void* x, void* y,
+                                              void* stream) {
+  WNB_CHECK_ARG(dtype == WNB200_F32 || dtype == WNB200_BF16, "avgpool_ncl_to_nlc_bf16: bad dtype");
+  WNB_CHECK_ARG(pool >= 1, "avgpool_ncl_to_nlc_bf16: bad pool");
+  const int To = T_ / pool;
+  if (B == 0 || C == 0 || To == 0) return 0;
+  WNB_CHECK_ARG(x && y, "avgpool_ncl_to_nlc_bf16: null pointer");
+  dim3 grid(ceil_div(To, 32), ceil_div(C, 32), B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == WNB200_F32)
+    avgpool_ncl_to_nlc_kernel<float><<<grid, 256, 0, st>>>(C, T_, To, pool, (const float*)x, (bf16*)y);
+  else
+    avgpool_ncl_to_nlc_kernel<bf16><<<grid, 256, 0, st>>>(C, T_, To, pool, (const bf16*)x, (bf16*)y);
   WNB_LAUNCH_OK();
   return 0;
 }

@@ -241,6 +241,65 @@ def try_wavenet_forward(model, signal):
     return run_head(skips_act, pk["head"], signal.dtype, model.softmax)
 
 
+def _stack_packs(model):
+    packs = [pack_block(model.input_block, model.input_skip_bottleneck)]
+    packs += [pack_block(b, n) for b, n in zip(model.convolutions, model.bottlenecks)]
+    return packs
+
+
+def try_raw_ctcnet_forward(model, seq):
+    """RawCTCNet.forward (reference raw_ctcnet.py:117-153) on the tensor-core path, or None if not eligible."""
+    if seq.dtype != torch.bfloat16 or not seq.is_cuda or seq.dim() != 3 or seq.shape[1] != 1:
+        return None
+    C, F = model.layers[0][0], model.num_features
+    if not (_no_graph(model, seq) and F == C and model.out_dim == C and C in (128, 256) and not model.positions
+            and _stack_ok(C, model.layers) and model.input_kernel_size <= 3 and model.feature_kwidth * F <= 8192
+            and seq.shape[0] > 0 and seq.shape[2] > 0):
+        return None
+    ops.check_device()
+
+    def build():
+        f0, f2 = model.feature_layer[0], model.feature_layer[2]
+        return {"f0w": f0.weight.detach().float()[:, 0, :].contiguous(), "f0b": f0.bias.detach().float().contiguous(),
+                "f2w": _bf16(f2.weight.detach().float()[:, :, 0]), "f2b": f2.bias.detach().float().contiguous(),
+                "blocks": _stack_packs(model), "head": pack_head(model.output_block, C)}
+
+    pk = _cached(model, "raw_ctcnet", build)
+    B, _, T = seq.shape
+    fk = model.feature_kwidth
+    To = T + fk - 1
+    seq = seq.contiguous()
+    h = torch.empty((B, To, F), dtype=torch.bfloat16, device=seq.device)
+    _lib.call("wnb200_featurize_nlc", ops._dt(seq), B, T, F, fk, ops._p(seq), ops._p(pk["f0w"]), ops._p(pk["f0b"]),
+              ops._p(h), ops._stream())
+    h = dense(h, [0], pk["f2w"], pk["f2b"], F, leaky=1)
+    skips = torch.empty((B, To, C), dtype=torch.float32, device=seq.device)
+    _, skips_act = run_blocks(h, None, None, pk["blocks"], skips, True, True)
+    return run_head(skips_act, pk["head"], seq.dtype, model.softmax)
+
+
+def try_classifier_forward(model, seq):
+    """WaveNetClassifier.forward (reference classifier.py:91-120) on the tensor-core path, or None."""
+    if seq.dtype != torch.bfloat16 or not seq.is_cuda or seq.dim() != 3:
+        return None
+    C = model.layers[0][0]
+    pool = model.pool_kernel_size
+    if not (_no_graph(model, seq) and model.in_dim == C and model.out_dim == C and C in (128, 256)
+            and _stack_ok(C, model.layers) and model.input_kernel_size <= 3 and seq.shape[0] > 0
+            and seq.shape[2] // pool > 0):
+        return None
+    ops.check_device()
+    pk = _cached(model, "classifier", lambda: {"blocks": _stack_packs(model), "head": pack_head(model.output_block, C)})
+    seq = seq.contiguous()
+    B, _, T = seq.shape
+    To = T // pool
+    h = torch.empty((B, To, C), dtype=torch.bfloat16, device=seq.device)
+    _lib.call("wnb200_avgpool_ncl_to_nlc_bf16", ops._dt(seq), B, C, T, pool, ops._p(seq), ops._p(h), ops._stream())
+    skips = torch.empty((B, To, C), dtype=torch.float32, device=seq.device)
+    _, skips_act = run_blocks(h, None, None, pk["blocks"], skips, True, True)
+    return run_head(skips_act, pk["head"], seq.dtype, model.softmax)
+
+
 def smoke_check(reference_forward):
     """Tiny eligible WaveNet on the tensor-core path vs `reference_forward(state_dict, x, layers, softmax)`
     evaluated by the caller's checker on bf16-rounded weights (used by __graft_entry__.smoke())."""

@@ -47,6 +47,10 @@ class WaveNetClassifier(nn.Module):
         _stack.kaiming_weights_(self.output_block.parameters(), zero)
 
     def forward(self, seq):
+        from .. import fastpath
+        y = fastpath.try_classifier_forward(self, seq)
+        if y is not None:
+            return y
         out = WF.avg_pool(seq, self.pool_kernel_size)
         out, skip = self.input_block(out)
         skips = WF.skip_accumulate(None, skip, self.input_skip_bottleneck.weight, self.input_skip_bottleneck.bias)
