@@ -207,3 +207,18 @@ def test_classifier_tc():
         y = net.cuda().bfloat16()(x.cuda().bfloat16())
     assert tuple(y.shape) == (2, 5, 333)
     assert rel(y, ref) <= BF16_TOL, rel(y, ref)
+
+
+def test_host_pipeline_matches_direct_call():
+    """Chunked H2D / compute / D2H overlap returns exactly what the plain module call returns."""
+    from wavenet_speech_b200.pipeline import HostPipeline
+    torch.manual_seed(4)
+    C = 128
+    layers = [(C, C, 2, d) for d in (1, 2, 4)]
+    net = W.WaveNet(C, 2, layers, C, softmax=True).cuda().bfloat16()
+    x = torch.randn(7, C, 500).bfloat16().pin_memory()
+    with torch.no_grad():
+        direct = net(x.cuda()).cpu()
+    for chunks in (1, 3, 7, 16):
+        y = HostPipeline(net, chunks=chunks)(x)
+        assert torch.equal(y, direct), chunks

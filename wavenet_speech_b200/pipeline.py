@@ -1,0 +1,73 @@
+"""Host-buffer pipeline: run a drop-in module over a batch that lives in pinned HOST memory, overlapping the
+host->device copy of chunk i+1, the kernels of chunk i and the device->host copy of chunk i-1 on three CUDA
+streams.  Reads in a batch are independent through every op on the path, so splitting the batch is exact.
+
+The reference's callers do `model(signal.cuda())` followed by `.cpu()` (legacy_code/run_raw_ctc.py:57-59,
+pretrain_tnt.py:145,159): the copies and the compute are serialised on one stream.  PCIe is full duplex and the
+copy engines are independent of the SMs, so with >= 3 chunks the step costs max(copy-in, compute, copy-out)
+instead of their sum."""
+import torch
+
+
+class HostPipeline(object):
+    def __init__(self, model, chunks=4, device=None):
+        self.model = model
+        self.chunks = int(chunks)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.s_in = torch.cuda.Stream(self.device)
+        self.s_out = torch.cuda.Stream(self.device)
+        self._bufs = None
+
+    def _buffers(self, n, x_shape, x_dtype):
+        key = (n, tuple(x_shape), x_dtype)
+        if self._bufs is None or self._bufs[0] != key:
+            xs = [torch.empty(x_shape, dtype=x_dtype, device=self.device) for _ in range(min(n, 2))]
+            self._bufs = (key, xs)
+        return self._bufs[1]
+
+    def __call__(self, x_host, y_host=None):
+        """x_host: pinned CPU tensor (B, C, T).  Returns y_host (pinned CPU tensor), valid when the call returns
+        (it synchronises on the last copy-out)."""
+        y_host = self.submit(x_host, y_host)
+        self.wait()
+        return y_host
+
+    def wait(self):
+        """Block until every copy-out submitted so far has landed in host memory."""
+        self.s_out.synchronize()
+
+    @torch.no_grad()
+    def submit(self, x_host, y_host=None):
+        """Enqueue one batch without waiting for it: back-to-back submits overlap the tail of one batch (last
+        kernels, last copy-out) with the head of the next (first copy-in).  `y_host` is valid after wait()."""
+        assert not x_host.is_cuda and x_host.is_pinned(), "HostPipeline expects a pinned host tensor"
+        B = x_host.shape[0]
+        n = max(1, min(self.chunks, B))
+        bounds = [(B * i // n, B * (i + 1) // n) for i in range(n)]
+        per = max(e - s for s, e in bounds)
+        xbuf = self._buffers(n, (per,) + tuple(x_host.shape[1:]), x_host.dtype)
+        cur = torch.cuda.current_stream(self.device)
+        in_done = [torch.cuda.Event() for _ in range(n)]
+        comp_done = [torch.cuda.Event() for _ in range(n)]
+        buf_free = [None, None]
+        outs = []
+        for i, (s, e) in enumerate(bounds):
+            slot = i % len(xbuf)
+            with torch.cuda.stream(self.s_in):
+                if buf_free[slot] is not None:
+                    self.s_in.wait_event(buf_free[slot])          # kernels of chunk i-2 have consumed the slot
+                xd = xbuf[slot][:e - s]
+                xd.copy_(x_host[s:e], non_blocking=True)
+                in_done[i].record(self.s_in)
+            cur.wait_event(in_done[i])
+            y = self.model(xd)
+            comp_done[i].record(cur)
+            buf_free[slot] = comp_done[i]
+            if y_host is None:
+                y_host = torch.empty((B,) + tuple(y.shape[1:]), dtype=y.dtype).pin_memory()
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(comp_done[i])
+                y_host[s:e].copy_(y, non_blocking=True)
+                y.record_stream(self.s_out)
+            outs.append(y)
+        return y_host
