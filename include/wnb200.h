@@ -82,6 +82,9 @@ int wnb200_channel_reduce(int dtype, int B, int C, int T, const void* a, const v
 int wnb200_gate_bwd(int dtype, int B, int C, int T, const void* dact, const void* th, const void* sg,
                     void* d_ab, void* stream);
 
+/* Stand-alone gate (block.py:184-185): out = tanh(a) * sigmoid(b); th / sg (optional) keep the two factors. */
+int wnb200_gate_fwd(int dtype, int64_t n, const void* a, const void* b, void* out, void* th, void* sg, void* stream);
+
 /* dx = dy * (ref > 0 ? 1 : 0.01)  (LeakyReLU backward; ref = input or output of the LeakyReLU). */
 int wnb200_leaky_bwd(int dtype, int64_t n, const void* dy, const void* ref, void* dx, void* stream);
 
@@ -101,6 +104,10 @@ int wnb200_layernorm_fwd(int dtype, int B, int C, int T, const void* x, const fl
                          const float* beta, float eps, void* y, float* stats, void* stream);
 int wnb200_layernorm_bwd(int dtype, int B, int C, int T, const void* x, const float* gamma,
                          const float* stats, float eps, const void* dy, void* dx, void* stream);
+
+/* dgamma[c] += sum_{b,t} dy*(x-mean)*r ; dbeta[c] += sum_{b,t} dy  (stats from wnb200_layernorm_fwd). */
+int wnb200_layernorm_bwd_params(int dtype, int B, int C, int T, const void* x, const float* stats, const void* dy,
+                                float* dgamma, float* dbeta, void* stream);
 
 /* Fused log-softmax + NLL over channels: replaces the T-iteration Python loop of
  * nn.CrossEntropyLoss in legacy_code/train.py:36-39.  logits NCL [B,C,T], target int64 [B,T].

@@ -1,0 +1,119 @@
+"""Secondary measurements (BASELINE configs 1, 3, 4, 5) -- not bench.py's headline line.  One JSON line each.
+    python scripts/bench_extra.py [rawctc] [train] [longread] [example]"""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import wavenet_speech_b200 as W
+from wavenet_speech_b200 import sharding as S
+from wavenet_speech_b200.utils import signal_gen as SG
+
+which = set(sys.argv[1:]) or {"rawctc", "train", "longread", "example"}
+ECOLI = [1, 2, 4, 8, 16] * 3
+
+
+def timed(fn, steps, warmup=2):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def ecoli_net(fk=3):
+    torch.manual_seed(0)
+    return W.RawCTCNet(256, fk, 5, [(256, 256, 2, d) for d in ECOLI], 256, softmax=False)
+
+
+if "rawctc" in which:      # config 4: RawCTCNet from configs/ecoli_testrun.json, batch sweep, bf16 inference
+    net = ecoli_net().cuda().bfloat16().eval()
+    flop = 17043456
+    for B in (64, 256, 1024):
+        x = torch.from_numpy(SG.raw_batch(min(B, 64), 4000, seed=7)).repeat((B + 63) // 64, 1, 1)[:B].cuda().bfloat16()
+        with torch.no_grad():
+            ms = timed(lambda: net(x), 5)
+        sps = B * 4000 / (ms * 1e-3)
+        print(json.dumps({"config": "rawctcnet_ecoli_fk3_bf16_fwd", "batch": B, "T": 4000, "ms_per_step": ms,
+                          "samples_per_s": sps, "tflops_as_written": sps * flop / 1e12}))
+
+if "example" in which:     # config 1: RawCTCNet from configs/example.json, fp32, 8 x 4000 (generic path) + CPU oracle
+    from oracle import wavenet_oracle as O
+    torch.manual_seed(0)
+    layers = [(1, 1, 1, 1)]
+    net = W.RawCTCNet(256, 2, 8, layers, 256, softmax=False)
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    x = torch.from_numpy(SG.raw_batch(8, 4000, seed=3))
+    t0 = time.perf_counter()
+    ref = O.raw_ctcnet_forward(sd, x, layers, softmax=False)
+    cpu_s = time.perf_counter() - t0
+    net = net.cuda()
+    xg = x.cuda()
+    with torch.no_grad():
+        y = net(xg)
+        ms = timed(lambda: net(xg), 10)
+    err = float((y.cpu() - ref).abs().max() / ref.abs().max())
+    print(json.dumps({"config": "rawctcnet_example_json_fp32_fwd", "batch": 8, "T": 4000, "ms_per_step": ms,
+                      "samples_per_s": 32000 / (ms * 1e-3), "cpu_oracle_samples_per_s": 32000 / cpu_s,
+                      "cpu_threads": torch.get_num_threads(), "rel_linf_vs_oracle": err}))
+
+if "train" in which:       # config 3: WaveNet-CTC train step (legacy_code/train.py:24-61), fp32 generic kernels
+    torch.manual_seed(0)
+    dil = [1, 2, 4, 8, 16, 32, 64, 128, 256, 512] * 2
+    wn = W.WaveNet(256, 2, [(256, 256, 2, d) for d in dil], 256, softmax=False).cuda()
+    cn = W.WaveNetClassifier(256, 5, [(256, 256, 2, d) for d in ECOLI], 256, pool_kernel_size=3, softmax=False).cuda()
+    opt = torch.optim.Adam(list(wn.parameters()) + list(cn.parameters()), lr=1e-5)
+    B, T = 4, 4096
+    lev, labels = SG.quantized_batch(B, T, seed=5, with_labels=True)
+    sig = torch.from_numpy(SG.one_hot(lev)).cuda()
+    lengths = torch.tensor([min(len(l), 300) for l in labels], dtype=torch.int32)
+    seq = torch.cat([torch.from_numpy(l[:300]) for l in labels]).int().cuda()
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        pred = wn(sig[:, :, 0:-1])
+        trans = cn(pred)
+        dense = W.ops.argmax_channels(sig[:, :, 1:].contiguous())
+        xe = W.functional.cross_entropy_sum(pred, dense) / B
+        probs = trans.permute(2, 0, 1).contiguous()
+        pl = torch.full((B,), probs.shape[0], dtype=torch.int32)
+        ctc = torch.nn.functional.ctc_loss(torch.log_softmax(probs.float(), 2), seq, pl, lengths, blank=0,
+                                           reduction="sum", zero_infinity=True)
+        loss = xe / T + ctc / trans.shape[2]
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    l0 = step()
+    ms = timed(step, 3, warmup=1)
+    l1 = step()
+    print(json.dumps({"config": "wavenet_ctc_train_step_fp32_generic", "batch": B, "T": T, "ms_per_step": ms,
+                      "samples_per_s": B * T / (ms * 1e-3), "loss_first": l0, "loss_after": l1,
+                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}))
+
+if "longread" in which:    # config 5: 1M-sample read, time-sharded in 8 shards (emulated on one GPU) vs one pass
+    net = ecoli_net().cuda().bfloat16().eval()
+    T = 1000000
+    x = torch.from_numpy(SG.raw_batch(1, T, seed=11)).cuda().bfloat16()
+    with torch.no_grad():
+        full = net(x)
+        ms_full = timed(lambda: net(x), 3, warmup=1)
+        hl, hr = S.raw_ctcnet_halo(net)
+        world = 8
+        outs, ms_shards = [], []
+        for r in range(world):
+            plan = S.time_shard_plan(T, r, world, hl, hr)
+            x_ext = x[:, :, plan["lo"]:plan["hi"]].contiguous()
+            outs.append(S.time_sharded_forward(net, x_ext, plan, T, out_extra=net.feature_kwidth - 1))
+            ms_shards.append(timed(lambda: net(x_ext), 3, warmup=1))
+        y = torch.cat(outs, 2)
+    same = bool(torch.equal(y, full))
+    print(json.dumps({"config": "rawctcnet_ecoli_1M_read_time_sharded", "T": T, "shards": world, "halo": [hl, hr],
+                      "one_gpu_full_read_ms": ms_full, "one_gpu_samples_per_s": T / (ms_full * 1e-3),
+                      "per_shard_ms_max": max(ms_shards), "projected_8gpu_samples_per_s": T / (max(ms_shards) * 1e-3),
+                      "sharded_equals_full_bitwise": same,
+                      "max_abs_diff": float((y.float() - full.float()).abs().max())}))

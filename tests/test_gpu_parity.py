@@ -241,3 +241,56 @@ def test_bf16_generic_path():
         y = net.cuda().bfloat16()(x.cuda())
     assert y.dtype == torch.bfloat16
     check(y, ref, tol=2e-2, what="bf16 wavenet")
+
+
+def test_time_sharding_matches_full_read():
+    """Config 5 in miniature: a read split into 4 time shards with receptive-field halos (ranks emulated one after
+    the other on one GPU) gives the same logits as one pass, on both kernel paths."""
+    from wavenet_speech_b200 import sharding as S
+    torch.manual_seed(31)
+    # fp32 generic path, odd sizes
+    layers = [(12, 12, 2, d) for d in (1, 2, 4, 8)] + [(12, 12, 3, 3)]
+    net = W.RawCTCNet(12, 3, 5, layers, 12, softmax=False).cuda()
+    T = 997
+    x = torch.randn(2, 1, T).cuda()
+    hl, hr = S.raw_ctcnet_halo(net)
+    with torch.no_grad():
+        full = net(x)
+        outs = []
+        for r in range(4):
+            plan = S.time_shard_plan(T, r, 4, hl, hr)
+            outs.append(S.time_sharded_forward(net, x[:, :, plan["lo"]:plan["hi"]].contiguous(), plan, T,
+                                               out_extra=net.feature_kwidth - 1))
+    y = torch.cat(outs, 2)
+    assert y.shape == full.shape
+    assert G.rel_linf(y.cpu(), full.cpu()) <= 1e-6
+    # bf16 tensor-core path
+    C = 128
+    layers = [(C, C, 2, d) for d in (1, 2, 4, 8, 16)]
+    net = W.RawCTCNet(C, 3, 5, layers, C, softmax=False).cuda().bfloat16()
+    T = 5000
+    x = torch.randn(1, 1, T).cuda().bfloat16()
+    hl, hr = S.raw_ctcnet_halo(net)
+    with torch.no_grad():
+        full = net(x)
+        outs = []
+        for r in range(3):
+            plan = S.time_shard_plan(T, r, 3, hl, hr)
+            outs.append(S.time_sharded_forward(net, x[:, :, plan["lo"]:plan["hi"]].contiguous(), plan, T,
+                                               out_extra=net.feature_kwidth - 1))
+    y = torch.cat(outs, 2)
+    assert torch.equal(y, full)        # same frames, same arithmetic: bit-identical
+
+
+def test_standalone_gate():
+    torch.manual_seed(2)
+    a = torch.randn(2, 5, 33, requires_grad=True)
+    b = torch.randn(2, 5, 33, requires_grad=True)
+    ref = O.gated_activation(a, b)
+    r = torch.randn_like(ref)
+    (ref * r).sum().backward()
+    ag, bg = a.detach().cuda().requires_grad_(True), b.detach().cuda().requires_grad_(True)
+    y = W.GatedActivationUnit()(ag, bg)
+    (y * r.cuda()).sum().backward()
+    check(y, ref.detach(), what="gate")
+    assert G.rel_linf(ag.grad.cpu(), a.grad) <= 1e-5 and G.rel_linf(bg.grad.cpu(), b.grad) <= 1e-5

@@ -58,6 +58,9 @@ SIGNATURES = {
     "wnb200_taps_wgrad": [c_int, c_int, c_int, c_int, ctypes.POINTER(Src), c_void_p, c_void_p, c_void_p],
     "wnb200_channel_reduce": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_gate_bwd": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_gate_fwd": [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_layernorm_bwd_params": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p],
     "wnb200_leaky_bwd": [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_softmax_fwd": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "wnb200_softmax_bwd": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p],

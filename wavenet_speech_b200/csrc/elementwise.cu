@@ -22,6 +22,47 @@ __global__ void gate_bwd_kernel(int B, int C, int Tn, const T* dact, const T* th
   }
 }
 
+// stand-alone GatedActivationUnit.forward (block.py:184-185); inside ResidualBlock the gate is a GEMM epilogue
+template <typename T>
+__global__ void gate_fwd_kernel(long long n, const T* a, const T* b, T* out, T* th, T* sg) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float t = tanhf(to_f32<T>(a[i])), s = sigmoid_precise(to_f32<T>(b[i]));
+    out[i] = from_f32<T>(t * s);
+    if (th) th[i] = from_f32<T>(t);
+    if (sg) sg[i] = from_f32<T>(s);
+  }
+}
+
+// LayerNorm parameter gradients: dgamma[c] += sum_{b,t} dy * (x - mean) * r ; dbeta[c] += sum_{b,t} dy
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_bwd_params_kernel(int C, int Tn, const T* x, const float* stats,
+                                                                   const T* dy, float* dgamma, float* dbeta) {
+  const int c = blockIdx.x, b = blockIdx.y;
+  const long long base = ((long long)b * C + c) * Tn;
+  float sg_ = 0.f, sb_ = 0.f;
+  for (int t = threadIdx.x; t < Tn; t += blockDim.x) {
+    const float g = to_f32<T>(dy[base + t]);
+    const float mean = stats[((long long)b * Tn + t) * 2], r = stats[((long long)b * Tn + t) * 2 + 1];
+    sg_ += g * (to_f32<T>(x[base + t]) - mean) * r;
+    sb_ += g;
+  }
+  __shared__ float red[2][8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sg_ += __shfl_xor_sync(0xffffffffu, sg_, o);
+    sb_ += __shfl_xor_sync(0xffffffffu, sb_, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sg_; red[1][threadIdx.x >> 5] = sb_; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, bsum = 0.f;
+    for (int i = 0; i < 8; ++i) { a += red[0][i]; bsum += red[1][i]; }
+    atomicAdd(&dgamma[c], a);
+    atomicAdd(&dbeta[c], bsum);
+  }
+}
+
 template <typename T>
 __global__ void leaky_bwd_kernel(long long n, const T* dy, const T* ref, T* dx) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
@@ -261,6 +302,30 @@ extern "C" int wnb200_gate_bwd(int dtype, int B, int C, int T_, const void* dact
   cudaStream_t st = (cudaStream_t)stream;
   DISPATCH(dtype, "gate_bwd", (gate_bwd_kernel<T><<<grid_for(n), 256, 0, st>>>(B, C, T_, (const T*)dact,
                                                                               (const T*)th, (const T*)sg, (T*)d_ab)));
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_gate_fwd(int dtype, int64_t n, const void* a, const void* b, void* out, void* th, void* sg,
+                               void* stream) {
+  if (n == 0) return 0;
+  WNB_CHECK_ARG(a && b && out, "gate_fwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(dtype, "gate_fwd", (gate_fwd_kernel<T><<<grid_for(n), 256, 0, st>>>(n, (const T*)a, (const T*)b, (T*)out,
+                                                                              (T*)th, (T*)sg)));
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_layernorm_bwd_params(int dtype, int B, int C, int T_, const void* x, const float* stats,
+                                           const void* dy, float* dgamma, float* dbeta, void* stream) {
+  if (B == 0 || C == 0 || T_ == 0) return 0;
+  WNB_CHECK_ARG(x && stats && dy && dgamma && dbeta, "layernorm_bwd_params: null pointer");
+  WNB_CHECK_ARG(B <= 65535, "layernorm_bwd_params: batch too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(C, B);
+  DISPATCH(dtype, "layernorm_bwd_params", (layernorm_bwd_params_kernel<T><<<grid, 256, 0, st>>>(
+                                               C, T_, (const T*)x, stats, (const T*)dy, dgamma, dbeta)));
   WNB_LAUNCH_OK();
   return 0;
 }

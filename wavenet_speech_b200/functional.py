@@ -329,14 +329,8 @@ class _LayerNorm(torch.autograd.Function):
         x, g, stats, gamma = ctx.saved_tensors
         dy = dy.contiguous()
         dx = ops.layernorm_bwd(x, g, stats, ctx.eps, dy)
-        # y_hat = (x - mean) * r  recovered from the affine output is avoided: recompute via dx-free path
-        B, C, T = x.shape
-        mean = stats[:, :, 0].unsqueeze(1)
-        r = stats[:, :, 1].unsqueeze(1)
-        yhat = ((x.float() - mean) * r).to(x.dtype)      # plumbing for the (tiny-model) decoder-side LN only
-        dgamma = ops.channel_reduce(dy, yhat).view(gamma.shape).to(gamma.dtype)
-        dbeta = ops.channel_reduce(dy).view(gamma.shape).to(gamma.dtype)
-        return dx, dgamma, dbeta, None
+        dgamma, dbeta = ops.layernorm_bwd_params(x, stats, dy)
+        return dx, dgamma.view(gamma.shape).to(gamma.dtype), dbeta.view(gamma.shape).to(gamma.dtype), None
 
 
 def layer_norm(x, gamma, beta, eps=1e-6):
@@ -363,6 +357,29 @@ class _XentSum(torch.autograd.Function):
 
 def cross_entropy_sum(logits, target):
     return _XentSum.apply(logits, target)
+
+
+class _Gate(torch.autograd.Function):
+    """Stand-alone tanh(a) * sigmoid(b) (reference block.py:184-185)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        out, th, sg = ops.gate_fwd(a, b, want_parts=True)
+        ctx.save_for_backward(th, sg)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        th, sg = ctx.saved_tensors
+        shape = g.shape
+        g3 = g.contiguous().view(1, -1, 1) if g.dim() != 3 else g.contiguous()
+        dab = ops.gate_bwd(g3, th.view_as(g3), sg.view_as(g3))
+        c = g3.shape[1]
+        return dab[:, :c].reshape(shape), dab[:, c:].reshape(shape)
+
+
+def gated_activation(a, b):
+    return _Gate.apply(a, b)
 
 
 class _Positions(torch.autograd.Function):

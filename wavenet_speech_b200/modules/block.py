@@ -9,31 +9,14 @@ from .layernorm import LayerNorm
 
 
 class GatedActivationUnit(nn.Module):
-    """tanh(x) * sigmoid(y) (reference block.py:177-188).  Stand-alone use goes through a zero-weight-free
-    elementwise path: the gate is normally fused into the block's contraction epilogue."""
+    """tanh(x) * sigmoid(y) (reference block.py:177-188).  Inside ResidualBlock the gate is fused into the
+    contraction epilogue; called on its own it runs the stand-alone gate kernel."""
 
     def forward(self, x, y):
-        return _GateOnly.apply(x, y)
+        return WF.gated_activation(x, y)
 
     def __repr__(self):
         return self.__class__.__name__ + ' ()'
-
-
-class _GateOnly(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, a, b):
-        # identity "contraction" is wasteful; this op only exists for API completeness
-        th, sg = torch.tanh(a), torch.sigmoid(b)
-        ctx.save_for_backward(th, sg)
-        return th * sg
-
-    @staticmethod
-    def backward(ctx, g):
-        th, sg = ctx.saved_tensors
-        from .. import ops
-        dab = ops.gate_bwd(g, th, sg)
-        c = g.shape[1]
-        return dab[:, :c], dab[:, c:]
 
 
 class ResidualBlock(nn.Module):

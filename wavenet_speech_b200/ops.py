@@ -139,6 +139,26 @@ def gate_bwd(dact, th, sg):
     return dab
 
 
+def gate_fwd(a, b, want_parts=False):
+    _need_cuda(a, b)
+    check_device()
+    a, b = a.contiguous(), b.contiguous()
+    out = torch.empty_like(a)
+    th = torch.empty_like(a) if want_parts else None
+    sg = torch.empty_like(a) if want_parts else None
+    _lib.call("wnb200_gate_fwd", _dt(a), a.numel(), _p(a), _p(b), _p(out), _p(th), _p(sg), _stream())
+    return (out, th, sg) if want_parts else out
+
+
+def layernorm_bwd_params(x, stats, dy):
+    B, C, T = x.shape
+    dgamma = torch.zeros(C, dtype=torch.float32, device=x.device)
+    dbeta = torch.zeros(C, dtype=torch.float32, device=x.device)
+    _lib.call("wnb200_layernorm_bwd_params", _dt(x), B, C, T, _p(x), _p(stats), _p(dy.contiguous()), _p(dgamma),
+              _p(dbeta), _stream())
+    return dgamma, dbeta
+
+
 def leaky_bwd(dy, ref):
     _need_cuda(dy, ref)
     dy = dy.contiguous()
