@@ -233,6 +233,14 @@ int wnb200_featurize_nlc(int dtype, int B, int T, int F, int fk, const void* x, 
  * x NCL [B, C, T] -> y NLC bf16 [B, floor(T/pool), C]. */
 int wnb200_avgpool_ncl_to_nlc_bf16(int dtype, int B, int C, int T, int pool, const void* x, void* y, void* stream);
 
+
+/* Weight gradient on tensor cores (CTA pair, MN-major operands):
+ *   dw[m, n] += sum_{b,t} g[b, t, m0 + m] * x[b, t + off, n],   m < 256, n < N (N = 128 or 256)
+ * g NLC bf16 [B,T,Cg], x NLC bf16 [B,T,N], dw fp32 [256][N] (accumulated into; zero it first).  Frames outside
+ * [0,T) read as zero.  Weight gradient of every contraction of the residual stack on the bf16 training step. */
+int wnb200_wgrad_tc(int B, int T, int Cg, int m0, int N, int off, const void* g_nlc, const void* x_nlc, float* dw,
+                    void* stream);
+
 /* y = bf16(LeakyReLU_0.01(x)), n a multiple of 4: turns the fp32 skip sum into the head's input
  * (first LeakyReLU of output_stack, wavenet.py:67). */
 int wnb200_leaky_to_bf16(int64_t n, const float* x, void* y, void* stream);

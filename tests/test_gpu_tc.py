@@ -222,3 +222,25 @@ def test_host_pipeline_matches_direct_call():
     for chunks in (1, 3, 7, 16):
         y = HostPipeline(net, chunks=chunks)(x)
         assert torch.equal(y, direct), chunks
+
+
+@pytest.mark.parametrize("B,T,Cg,m0,N,off", [(1, 64, 256, 0, 256, 0), (2, 300, 256, 0, 256, -3), (3, 1000, 512, 256, 256, 8),
+                                             (2, 130, 256, 0, 128, 0), (4, 5000, 256, 0, 256, -512)])
+def test_wgrad_tc(B, T, Cg, m0, N, off):
+    """Time-contraction weight gradient with MN-major tensor-core operands vs an fp32 einsum."""
+    torch.manual_seed(B + T + off)
+    g = r16(torch.randn(B, T, Cg) * 0.1)
+    x = r16(torch.randn(B, T, N))
+    xs = torch.zeros_like(x)
+    if off >= 0:
+        xs[:, :T - off] = x[:, off:] if off < T else 0
+    else:
+        xs[:, -off:] = x[:, :T + off] if -off < T else 0
+    ref = torch.einsum("btm,btn->mn", g[:, :, m0:m0 + 256].double(), xs.double()).float()
+    dw = FP.wgrad(g.cuda().bfloat16(), x.cuda().bfloat16(), off=off, m0=m0)
+    torch.cuda.synchronize()
+    e = rel(dw, ref)
+    assert e <= 2e-3, e
+    # accumulates into an existing buffer
+    dw2 = FP.wgrad(g.cuda().bfloat16(), x.cuda().bfloat16(), off=off, m0=m0, dw=dw.clone())
+    assert rel(dw2, 2 * ref) <= 2e-3

@@ -80,6 +80,7 @@ SIGNATURES = {
     "wnb200_dense_fwd_tc": [ctypes.POINTER(Dense), c_void_p],
     "wnb200_featurize_nlc": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_avgpool_ncl_to_nlc_bf16": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "wnb200_wgrad_tc": [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_leaky_to_bf16": [c_int64, c_void_p, c_void_p, c_void_p],
     "wnb200_ncl_to_nlc_bf16": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "wnb200_nlc_to_ncl": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],

@@ -154,6 +154,21 @@ def dense(x_nlc, offsets, w, bias, N, mode=0, leaky=0, out=None, n_out=0, softma
     return out
 
 
+def wgrad(g_nlc, x_nlc, off=0, m0=0, dw=None):
+    """dw[m, n] += sum_{b,t} g[b,t,m0+m] * x[b,t+off,n] on tensor cores; returns dw fp32 [256, N]."""
+    B, T, Cg = g_nlc.shape
+    N = x_nlc.shape[2]
+    if dw is None:
+        dw = torch.zeros((256, N), dtype=torch.float32, device=g_nlc.device)
+    _lib.current_tag = "wgrad"
+    try:
+        _lib.call("wnb200_wgrad_tc", B, T, Cg, int(m0), N, int(off), ops._p(g_nlc), ops._p(x_nlc), ops._p(dw),
+                  ops._stream())
+    finally:
+        _lib.current_tag = None
+    return dw
+
+
 def leaky_to_bf16(x):
     y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     _lib.call("wnb200_leaky_to_bf16", x.numel(), ops._p(x), ops._p(y), ops._stream())
