@@ -200,6 +200,9 @@ typedef struct {
   void* res;
   float* skips;
   void* dbg;              /* optional int64[8*16] timeline buffer */
+  void* save_act;         /* optional (training): gate, tanh(.) and sigmoid(.) as NLC bf16 [B,T,C] each */
+  void* save_th;
+  void* save_sg;
 } wnb200_resblock_t;
 int wnb200_resblock_fwd_tc(const wnb200_resblock_t* args /*host*/, void* stream);
 
@@ -215,11 +218,13 @@ typedef struct {
   int32_t t_off[3];
   int32_t N;
   int32_t mode, leaky, n_out, softmax, out_f32;
-  int32_t _pad;
+  int32_t Cin2, ntaps2;   /* optional second source x2 (NLC bf16 [B,T,Cin2]): its taps follow x's in W's columns */
+  int32_t t_off2[3];
   const void* x;
   const void* w;
   const float* bias;
   void* y;
+  const void* x2;         /* NULL = single source */
 } wnb200_dense_t;
 int wnb200_dense_fwd_tc(const wnb200_dense_t* args /*host*/, void* stream);
 
@@ -240,6 +245,13 @@ int wnb200_avgpool_ncl_to_nlc_bf16(int dtype, int B, int C, int T, int pool, con
  * [0,T) read as zero.  Weight gradient of every contraction of the residual stack on the bf16 training step. */
 int wnb200_wgrad_tc(int B, int T, int Cg, int m0, int N, int off, const void* g_nlc, const void* x_nlc, float* dw,
                     void* stream);
+
+/* Gate backward on NLC bf16 tensors (block.py:185): dab[r, 0:C] = dact*sg*(1-th^2), dab[r, C:2C] = dact*th*sg*(1-sg)
+ * for each of `rows` = B*T frames. */
+int wnb200_gate_bwd_nlc(int64_t rows, int C, const void* dact, const void* th, const void* sg, void* dab, void* stream);
+
+/* out[c] += sum over rows of x[r, c]  (x NLC bf16 [rows, C]; bias gradients on the tensor-core training path). */
+int wnb200_colsum_nlc(int64_t rows, int C, const void* x, float* out, void* stream);
 
 /* y = bf16(LeakyReLU_0.01(x)), n a multiple of 4: turns the fp32 skip sum into the head's input
  * (first LeakyReLU of output_stack, wavenet.py:67). */

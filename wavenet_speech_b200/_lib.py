@@ -36,7 +36,7 @@ class ResBlock(ctypes.Structure):
                 ("t_off", ctypes.c_int32 * 3), ("skips_init", ctypes.c_int32), ("variant", ctypes.c_int32),
                 ("_pad", ctypes.c_int32), ("x", c_void_p), ("w1", c_void_p),
                 ("bias1", c_void_p), ("w2", c_void_p), ("bias2", c_void_p), ("res", c_void_p), ("skips", c_void_p),
-                ("dbg", c_void_p)]
+                ("dbg", c_void_p), ("save_act", c_void_p), ("save_th", c_void_p), ("save_sg", c_void_p)]
 
 
 class Dense(ctypes.Structure):
@@ -44,8 +44,9 @@ class Dense(ctypes.Structure):
     _fields_ = [("B", ctypes.c_int32), ("T", ctypes.c_int32), ("Cin", ctypes.c_int32), ("ntaps", ctypes.c_int32),
                 ("t_off", ctypes.c_int32 * 3), ("N", ctypes.c_int32), ("mode", ctypes.c_int32),
                 ("leaky", ctypes.c_int32), ("n_out", ctypes.c_int32), ("softmax", ctypes.c_int32),
-                ("out_f32", ctypes.c_int32), ("_pad", ctypes.c_int32), ("x", c_void_p), ("w", c_void_p),
-                ("bias", c_void_p), ("y", c_void_p)]
+                ("out_f32", ctypes.c_int32), ("Cin2", ctypes.c_int32), ("ntaps2", ctypes.c_int32),
+                ("t_off2", ctypes.c_int32 * 3), ("x", c_void_p), ("w", c_void_p),
+                ("bias", c_void_p), ("y", c_void_p), ("x2", c_void_p)]
 
 
 # name -> argtypes (return type is int unless listed in _RESTYPES)
@@ -81,6 +82,8 @@ SIGNATURES = {
     "wnb200_featurize_nlc": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_avgpool_ncl_to_nlc_bf16": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "wnb200_wgrad_tc": [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_gate_bwd_nlc": [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_colsum_nlc": [c_int64, c_int, c_void_p, c_void_p, c_void_p],
     "wnb200_leaky_to_bf16": [c_int64, c_void_p, c_void_p, c_void_p],
     "wnb200_ncl_to_nlc_bf16": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "wnb200_nlc_to_ncl": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],

@@ -24,6 +24,7 @@ struct DenseDev {
   int B, T, tiles_per_seq, num_tiles;
   int ntaps, t_off[3];
   int kb_per_tap;   // Cin / 64
+  int ntaps2, t_off2[3], kb_per_tap2;   // optional second source tensor (its taps follow the first one's in K)
   int N;            // accumulator columns (multiple of 16, <= 256)
   int mode;         // 0 NLC store, 1 HEAD
   int leaky;        // NLC: LeakyReLU(0.01) after bias
@@ -41,8 +42,8 @@ constexpr int DN_SCRATCH = 2 * RB_TILE * 8;    // softmax partials (max, sum) pe
 constexpr int DN_SMEM = DN_NSTAGE * DN_STAGE + DN_STAGING + DN_SCRATCH + 1024 + 256;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DN_THREADS, 1)
-dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-              const __grid_constant__ CUtensorMap map_y, const DenseDev p) {
+dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_x2,
+              const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_y, const DenseDev p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -59,11 +60,13 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int nkb = p.ntaps * p.kb_per_tap;
+  const int nkb1 = p.ntaps * p.kb_per_tap;
+  const int nkb = nkb1 + p.ntaps2 * p.kb_per_tap2;
   const uint32_t bhalf_bytes = (uint32_t)(p.N / 2) * 128u;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&map_x);
+    if (p.ntaps2 > 0) prefetch_tensormap(&map_x2);
     prefetch_tensormap(&map_w);
     prefetch_tensormap(&map_y);
     for (int s = 0; s < DN_NSTAGE; ++s) {
@@ -97,8 +100,14 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
           const uint32_t sa = smem_base + stage * DN_STAGE;
           if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * (DN_ABYTES + bhalf_bytes));
           const uint32_t lfull = mapa_shared(full_bar(stage), 0);
-          const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
-          tma_load_3d_2sm(sa, &map_x, lfull, cb * 64, t0 + p.t_off[tap], b);
+          if (kb < nkb1) {
+            const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
+            tma_load_3d_2sm(sa, &map_x, lfull, cb * 64, t0 + p.t_off[tap], b);
+          } else {
+            const int k2 = kb - nkb1;
+            const int tap = k2 / p.kb_per_tap2, cb = k2 - tap * p.kb_per_tap2;
+            tma_load_3d_2sm(sa, &map_x2, lfull, cb * 64, t0 + p.t_off2[tap], b);
+          }
           tma_load_2d_2sm(sa + DN_ABYTES, &map_w, lfull, kb * 64, (int)rank * (p.N / 2));
           if (rank != 0) mbar_arrive_cluster(lfull);
           if (++stage == DN_NSTAGE) { stage = 0; phase ^= 1; }
@@ -405,15 +414,22 @@ extern "C" int wnb200_dense_fwd_tc(const wnb200_dense_t* a, void* stream) {
   p.ntaps = a->ntaps;
   for (int j = 0; j < 3; ++j) p.t_off[j] = a->t_off[j];
   p.kb_per_tap = a->Cin / 64;
+  p.ntaps2 = a->x2 ? a->ntaps2 : 0;
+  for (int j = 0; j < 3; ++j) p.t_off2[j] = a->t_off2[j];
+  p.kb_per_tap2 = a->Cin2 / 64;
+  if (p.ntaps2 > 0)
+    WNB_CHECK_ARG(a->Cin2 >= 64 && a->Cin2 % 64 == 0 && a->ntaps2 <= 3, "dense_fwd_tc: bad second source");
   p.N = a->N; p.mode = a->mode; p.leaky = a->leaky;
   p.n_out = a->n_out; p.softmax = a->softmax; p.out_f32 = a->out_f32;
   p.bias = a->bias; p.out = a->y;
   const int esize = a->out_f32 ? 4 : 2;
   p.tma_out = (a->mode == 1 && ((long long)a->T * esize) % 16 == 0) ? 1 : 0;
-  CUtensorMap mx, mw, my;
+  CUtensorMap mx, mx2, mw, my;
   int rc;
   if ((rc = rb_map_nlc(&mx, a->x, a->B, a->T, a->Cin, 2))) return rc;
-  if ((rc = rb_map_2d(&mw, a->w, a->N, a->ntaps * a->Cin, a->N / 2))) return rc;
+  mx2 = mx;
+  if (p.ntaps2 > 0 && (rc = rb_map_nlc(&mx2, a->x2, a->B, a->T, a->Cin2, 2))) return rc;
+  if ((rc = rb_map_2d(&mw, a->w, a->N, a->ntaps * a->Cin + p.ntaps2 * a->Cin2, a->N / 2))) return rc;
   if (a->mode == 0) {
     if ((rc = rb_map_nlc(&my, a->y, a->B, a->T, a->N, 2))) return rc;
   } else if (p.tma_out) {
@@ -431,7 +447,7 @@ extern "C" int wnb200_dense_fwd_tc(const wnb200_dense_t* a, void* stream) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int pairs = sms / 2;
   if (p.num_tiles < pairs) pairs = p.num_tiles;
-  dense2_kernel<<<2 * pairs, DN_THREADS, DN_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(mx, mw, my, p);
+  dense2_kernel<<<2 * pairs, DN_THREADS, DN_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(mx, mx2, mw, my, p);
   WNB_LAUNCH_OK();
   return 0;
 }

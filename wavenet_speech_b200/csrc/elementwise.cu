@@ -276,6 +276,50 @@ __global__ void argmax_kernel(int B, int C, int Tn, const T* x, long long* out) 
   out[col] = arg;
 }
 
+// gate backward on NLC bf16: 8 channels (16 B) per thread
+__global__ void gate_bwd_nlc_kernel(long long rows, int C, const uint4* dact, const uint4* th, const uint4* sg,
+                                    uint4* dab) {
+  const int g = C / 8;
+  const long long n = rows * g;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / g;
+    const int cg = (int)(i - r * g);
+    const uint4 d4 = dact[i], t4 = th[i], s4 = sg[i];
+    const __nv_bfloat162* dp = reinterpret_cast<const __nv_bfloat162*>(&d4);
+    const __nv_bfloat162* tp = reinterpret_cast<const __nv_bfloat162*>(&t4);
+    const __nv_bfloat162* sp = reinterpret_cast<const __nv_bfloat162*>(&s4);
+    uint4 oa, ob;
+    __nv_bfloat162* ap = reinterpret_cast<__nv_bfloat162*>(&oa);
+    __nv_bfloat162* bp = reinterpret_cast<__nv_bfloat162*>(&ob);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 d = __bfloat1622float2(dp[k]), t = __bfloat1622float2(tp[k]), s_ = __bfloat1622float2(sp[k]);
+      ap[k] = __floats2bfloat162_rn(d.x * s_.x * (1.f - t.x * t.x), d.y * s_.y * (1.f - t.y * t.y));
+      bp[k] = __floats2bfloat162_rn(d.x * t.x * s_.x * (1.f - s_.x), d.y * t.y * s_.y * (1.f - s_.y));
+    }
+    dab[r * (2 * g) + cg] = oa;
+    dab[r * (2 * g) + g + cg] = ob;
+  }
+}
+
+// column sums of an NLC bf16 tensor [rows][C]: block = 32 channel-pairs x 8 row lanes
+__global__ void __launch_bounds__(256) colsum_nlc_kernel(long long rows, int C, const __nv_bfloat16* x, float* out) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  float s = 0.f;
+  if (c < C)
+    for (long long r = blockIdx.y * 8ll + ry; r < rows; r += 8ll * gridDim.y) s += __bfloat162float(x[r * C + c]);
+  __shared__ float red[8][33];
+  red[ry][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
+    atomicAdd(&out[c], t);
+  }
+}
+
 static inline int grid_for(long long n, int block = 256) {
   long long g = (n + block - 1) / block;
   const long long cap = 148ll * 32;
@@ -464,6 +508,28 @@ extern "C" int wnb200_argmax_channels(int dtype, int B, int C, int T_, const voi
   cudaStream_t st = (cudaStream_t)stream;
   DISPATCH(dtype, "argmax_channels", (argmax_kernel<T><<<(unsigned)ceil_div64(cols, 128), 128, 0, st>>>(
                                           B, C, T_, (const T*)x, (long long*)out)));
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_gate_bwd_nlc(int64_t rows, int C, const void* dact, const void* th, const void* sg, void* dab,
+                                   void* stream) {
+  WNB_CHECK_ARG(C % 8 == 0, "gate_bwd_nlc: C must be a multiple of 8");
+  if (rows == 0) return 0;
+  WNB_CHECK_ARG(dact && th && sg && dab, "gate_bwd_nlc: null pointer");
+  gate_bwd_nlc_kernel<<<grid_for(rows * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
+      rows, C, (const uint4*)dact, (const uint4*)th, (const uint4*)sg, (uint4*)dab);
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_colsum_nlc(int64_t rows, int C, const void* x, float* out, void* stream) {
+  if (rows == 0 || C == 0) return 0;
+  WNB_CHECK_ARG(x && out, "colsum_nlc: null pointer");
+  long long gy = (rows + 1023) / 1024;
+  if (gy > 592) gy = 592;
+  dim3 grid((C + 31) / 32, (unsigned)gy);
+  colsum_nlc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rows, C, (const __nv_bfloat16*)x, out);
   WNB_LAUNCH_OK();
   return 0;
 }

@@ -34,6 +34,9 @@ struct ResDev {
   const float* bias2;   // [2C] = [res ; skip]
   int write_res, skips_init;
   long long* dbg;
+  bf16* save_act;   // training: gate / tanh / sigmoid, NLC bf16 (CTA-pair kernel only)
+  bf16* save_th;
+  bf16* save_sg;
 };
 
 constexpr int RB_THREADS = 320;
@@ -598,14 +601,25 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             bsa[4 * j] = v.x; bsa[4 * j + 1] = v.y; bsa[4 * j + 2] = v.z; bsa[4 * j + 3] = v.w;
           }
           tmem_wait_ld();
-          uint32_t pk[8];
+          uint32_t pk[8], pt[8], ps[8];
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
-            const float v0 = tanh_approx(a[i] + bta[i]) * sigmoid_approx(g[i] + bsa[i]);
-            const float v1 = tanh_approx(a[i + 1] + bta[i + 1]) * sigmoid_approx(g[i + 1] + bsa[i + 1]);
-            pk[i >> 1] = pack_bf16x2(v0, v1);
+            const float t0v = tanh_approx(a[i] + bta[i]), s0v = sigmoid_approx(g[i] + bsa[i]);
+            const float t1v = tanh_approx(a[i + 1] + bta[i + 1]), s1v = sigmoid_approx(g[i + 1] + bsa[i + 1]);
+            pk[i >> 1] = pack_bf16x2(t0v * s0v, t1v * s1v);
+            pt[i >> 1] = pack_bf16x2(t0v, t1v);
+            ps[i >> 1] = pack_bf16x2(s0v, s1v);
           }
           const int ch = half * (C / 2) + col;
+          if (p.save_act && t0 + row < p.T) {          // training: keep the gate and its two factors for backward
+            const long long o = ((long long)b * p.T + t0 + row) * C + ch;
+            uint4* da = reinterpret_cast<uint4*>(p.save_act + o);
+            uint4* dt = reinterpret_cast<uint4*>(p.save_th + o);
+            uint4* ds = reinterpret_cast<uint4*>(p.save_sg + o);
+            da[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]); da[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            dt[0] = make_uint4(pt[0], pt[1], pt[2], pt[3]); dt[1] = make_uint4(pt[4], pt[5], pt[6], pt[7]);
+            ds[0] = make_uint4(ps[0], ps[1], ps[2], ps[3]); ds[1] = make_uint4(ps[4], ps[5], ps[6], ps[7]);
+          }
           const int kb = ch >> 6, ci = (ch & 63) >> 3;
           uint8_t* blk = smem_gen + (act_base - smem_base) + kb * RB_ABYTES + row * 128;
           *reinterpret_cast<uint4*>(blk + ((ci ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -775,6 +789,9 @@ extern "C" int wnb200_resblock_fwd_tc(const wnb200_resblock_t* a, void* stream) 
   p.bias1 = a->bias1; p.bias2 = a->bias2;
   p.write_res = a->res != nullptr; p.skips_init = a->skips_init;
   p.dbg = (long long*)a->dbg;
+  p.save_act = (bf16*)a->save_act; p.save_th = (bf16*)a->save_th; p.save_sg = (bf16*)a->save_sg;
+  WNB_CHECK_ARG(!a->save_act || (a->save_th && a->save_sg && a->variant != 1),
+                "resblock_fwd_tc: saving the gate factors needs all three buffers and the CTA-pair kernel");
   const bool pair = a->variant != 1;     // 0 / 2: CTA-pair kernel (default); 1: single-CTA kernel
   const int wbox = pair ? C / 2 : C;
   CUtensorMap mx, mw1, mw2, mres, msk;
