@@ -110,40 +110,54 @@ def gated_activation(a, b):
     return torch.mul(torch.tanh(a), torch.sigmoid(b))
 
 
-def residual_block(sd, prefix, x, d, causal):
+def bf16_storage(x):
+    """Round to bf16 with a straight-through gradient.  NOT part of the reference: passed as `q` to the
+    forward functions below it reproduces where a bf16 kernel pipeline STORES activations between kernels
+    (gate, residual stream, head activations), so that gradient parity tests are not dominated by LeakyReLU /
+    rounding decisions flipping between an fp32 and a bf16 evaluation.  q=None is the reference, exactly."""
+    return x + (x.detach().bfloat16().float() - x.detach())
+
+
+def _id(x):
+    return x
+
+
+def residual_block(sd, prefix, x, d, causal, q=None):
     """modules/block.py:54-82 (ResidualBlock.forward) -> (residual_out, skip_out)."""
+    q = q or _id
     conv = causal_conv1d if causal else noncausal_conv1d
     a = conv(x, sd[prefix + "conv_tanh.conv1d.weight"], sd[prefix + "conv_tanh.conv1d.bias"], d)
     b = conv(x, sd[prefix + "conv_sigmoid.conv1d.weight"], sd[prefix + "conv_sigmoid.conv1d.bias"], d)
-    act = gated_activation(a, b)
+    act = q(gated_activation(a, b))
     res1x1 = F.conv1d(act, sd[prefix + "conv1x1_residual.weight"], sd[prefix + "conv1x1_residual.bias"])
     skip = F.conv1d(act, sd[prefix + "conv1x1_skip.weight"], sd[prefix + "conv1x1_skip.bias"])
     flat, axes = reshape_in(x)
     proj = reshape_out(F.linear(flat, sd[prefix + "residual_proj.weight"], sd[prefix + "residual_proj.bias"]), axes)
-    return res1x1 + proj, skip
+    return q(res1x1 + proj), skip
 
 
-def _output_stack(sd, prefix, x):
+def _output_stack(sd, prefix, x, q=None):
     """modules/wavenet.py:67-71 / raw_ctcnet.py:84-88 / classifier.py:70-74:
     LeakyReLU(0.01) -> 1x1 -> LeakyReLU(0.01) -> 1x1."""
-    h = F.leaky_relu(x, 0.01)
+    q = q or _id
+    h = q(F.leaky_relu(q(x), 0.01))
     h = F.conv1d(h, sd[prefix + "1.weight"], sd[prefix + "1.bias"])
-    h = F.leaky_relu(h, 0.01)
+    h = q(F.leaky_relu(h, 0.01))
     return F.conv1d(h, sd[prefix + "3.weight"], sd[prefix + "3.bias"])
 
 
 # ----------------------------------------------------------------------------
 # modules/wavenet.py
 # ----------------------------------------------------------------------------
-def wavenet_forward(sd, signal, layers, softmax=True):
+def wavenet_forward(sd, signal, layers, softmax=True, q=None):
     """modules/wavenet.py:88-111 (WaveNet.forward).  `layers` = [(c_in,c_out,k,d)]."""
-    out = causal_conv1d(signal, sd["entry_conv1d.conv1d.weight"], sd["entry_conv1d.conv1d.bias"], 1)
+    out = (q or _id)(causal_conv1d(signal, sd["entry_conv1d.conv1d.weight"], sd["entry_conv1d.conv1d.bias"], 1))
     out_dim = sd["bottlenecks.0.weight"].shape[0]
     skips = signal.new_zeros(signal.shape[0], out_dim, signal.shape[2])
     for l, (_ci, _co, _k, d) in enumerate(layers):
-        out, skip = residual_block(sd, "convolutions.%d." % l, out, d, True)
+        out, skip = residual_block(sd, "convolutions.%d." % l, out, d, True, q)
         skips = skips + F.conv1d(skip, sd["bottlenecks.%d.weight" % l], sd["bottlenecks.%d.bias" % l])
-    y = _output_stack(sd, "output_stack.", skips)
+    y = _output_stack(sd, "output_stack.", skips, q)
     if not softmax:
         return y
     return channel_softmax(y)
@@ -152,16 +166,17 @@ def wavenet_forward(sd, signal, layers, softmax=True):
 # ----------------------------------------------------------------------------
 # modules/raw_ctcnet.py
 # ----------------------------------------------------------------------------
-def raw_ctcnet_forward(sd, seq, layers, input_dilation=1, positions=False, softmax=True, causal=False):
+def raw_ctcnet_forward(sd, seq, layers, input_dilation=1, positions=False, softmax=True, causal=False, q=None):
     """modules/raw_ctcnet.py:117-153 (RawCTCNet.forward).  Output length is
     T + feature_kwidth - 1: the featuriser pads by fk-1 and never truncates
     (raw_ctcnet.py:58)."""
     w0 = sd["feature_layer.0.weight"]
     fk = w0.shape[2]
     out = F.conv1d(seq, w0, sd["feature_layer.0.bias"], padding=fk - 1)
-    out = F.leaky_relu(out, 0.01)
+    q_ = q or _id
+    out = q_(F.leaky_relu(out, 0.01))
     out = F.conv1d(out, sd["feature_layer.2.weight"], sd["feature_layer.2.bias"])
-    out = F.leaky_relu(out, 0.01)
+    out = q_(F.leaky_relu(out, 0.01))
     if positions:
         # raw_ctcnet.py:131-135
         incr = torch.arange(0., out.shape[2], dtype=out.dtype)
@@ -169,12 +184,12 @@ def raw_ctcnet_forward(sd, seq, layers, input_dilation=1, positions=False, softm
         out = out + F.hardtanh(pos)
     out_dim = sd["input_skip_bottleneck.weight"].shape[0]
     skips = out.new_zeros(out.shape[0], out_dim, out.shape[2])
-    out, skip = residual_block(sd, "input_block.", out, input_dilation, causal)
+    out, skip = residual_block(sd, "input_block.", out, input_dilation, causal, q)
     skips = skips + F.conv1d(skip, sd["input_skip_bottleneck.weight"], sd["input_skip_bottleneck.bias"])
     for l, (_ci, _co, _k, d) in enumerate(layers):
-        out, skip = residual_block(sd, "convolutions.%d." % l, out, d, causal)
+        out, skip = residual_block(sd, "convolutions.%d." % l, out, d, causal, q)
         skips = skips + F.conv1d(skip, sd["bottlenecks.%d.weight" % l], sd["bottlenecks.%d.bias" % l])
-    y = _output_stack(sd, "output_block.", skips)
+    y = _output_stack(sd, "output_block.", skips, q)
     if not softmax:
         return y
     return channel_softmax(y)
@@ -183,17 +198,17 @@ def raw_ctcnet_forward(sd, seq, layers, input_dilation=1, positions=False, softm
 # ----------------------------------------------------------------------------
 # modules/classifier.py
 # ----------------------------------------------------------------------------
-def classifier_forward(sd, seq, layers, pool_kernel_size=2, input_dilation=1, softmax=True):
+def classifier_forward(sd, seq, layers, pool_kernel_size=2, input_dilation=1, softmax=True, q=None):
     """modules/classifier.py:91-120 (WaveNetClassifier.forward)."""
-    out = F.avg_pool1d(seq, kernel_size=pool_kernel_size, padding=0)   # classifier.py:53,102
+    out = (q or _id)(F.avg_pool1d(seq, kernel_size=pool_kernel_size, padding=0))   # classifier.py:53,102
     out_dim = sd["input_skip_bottleneck.weight"].shape[0]
     skips = out.new_zeros(out.shape[0], out_dim, out.shape[2])
-    out, skip = residual_block(sd, "input_block.", out, input_dilation, False)
+    out, skip = residual_block(sd, "input_block.", out, input_dilation, False, q)
     skips = skips + F.conv1d(skip, sd["input_skip_bottleneck.weight"], sd["input_skip_bottleneck.bias"])
     for l, (_ci, _co, _k, d) in enumerate(layers):
-        out, skip = residual_block(sd, "convolutions.%d." % l, out, d, False)
+        out, skip = residual_block(sd, "convolutions.%d." % l, out, d, False, q)
         skips = skips + F.conv1d(skip, sd["bottlenecks.%d.weight" % l], sd["bottlenecks.%d.bias" % l])
-    y = _output_stack(sd, "output_block.", skips)
+    y = _output_stack(sd, "output_block.", skips, q)
     if not softmax:
         return y
     return channel_softmax(y)

@@ -8,7 +8,8 @@ import wavenet_speech_b200 as W
 from wavenet_speech_b200 import sharding as S
 from wavenet_speech_b200.utils import signal_gen as SG
 
-which = set(sys.argv[1:]) or {"rawctc", "train", "longread", "example"}
+which = set(a for a in sys.argv[1:] if "=" not in a) or {"rawctc", "train", "longread", "example"}
+opts = dict(a.split("=", 1) for a in sys.argv[1:] if "=" in a)
 ECOLI = [1, 2, 4, 8, 16] * 3
 
 
@@ -94,6 +95,76 @@ if "train" in which:       # config 3: WaveNet-CTC train step (legacy_code/train
     print(json.dumps({"config": "wavenet_ctc_train_step_fp32_generic", "batch": B, "T": T, "ms_per_step": ms,
                       "samples_per_s": B * T / (ms * 1e-3), "loss_first": l0, "loss_after": l1,
                       "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}))
+
+if "train_tc" in which:    # config 3 on the tensor-core path: bf16 operands, fp32 master weights / gradients / Adam
+    from wavenet_speech_b200 import _lib
+    torch.manual_seed(0)
+    dil = [1, 2, 4, 8, 16, 32, 64, 128, 256, 512] * 2
+    wn = W.WaveNet(256, 2, [(256, 256, 2, d) for d in dil], 256, softmax=False).cuda()
+    cn = W.WaveNetClassifier(256, 5, [(256, 256, 2, d) for d in ECOLI], 256, pool_kernel_size=3, softmax=False).cuda()
+    opt = torch.optim.Adam(list(wn.parameters()) + list(cn.parameters()), lr=1e-5, fused=True)
+    B, T = int(opts.get("B", 32)), int(opts.get("T", 16384))
+    lev, labels = SG.quantized_batch(min(B, 8), T, seed=5, with_labels=True)
+    rep = (B + 7) // 8
+    sig = torch.from_numpy(SG.one_hot(lev)).repeat(rep, 1, 1)[:B].cuda().bfloat16()
+    labels = (labels * rep)[:B]
+    nlab = T // 3 // 2
+    lengths = torch.tensor([min(len(l), nlab) for l in labels], dtype=torch.int32)
+    seq = torch.cat([torch.from_numpy(l[:nlab]) for l in labels]).int().cuda()
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        pred = wn(sig[:, :, 0:-1])
+        trans = cn(pred)
+        dense = W.ops.argmax_channels(sig[:, :, 1:].contiguous())
+        xe = W.functional.cross_entropy_sum(pred, dense) / B
+        probs = trans.permute(2, 0, 1).contiguous()
+        pl = torch.full((B,), probs.shape[0], dtype=torch.int32)
+        ctc = torch.nn.functional.ctc_loss(torch.log_softmax(probs.float(), 2), seq, pl, lengths, blank=0,
+                                           reduction="sum", zero_infinity=True)
+        loss = xe / T + ctc / trans.shape[2]
+        loss.backward()
+        opt.step()
+        return loss
+
+    l0 = float(step())
+    ms = timed(step, int(opts.get("steps", 5)), warmup=2)
+    l1 = float(step())
+    _lib.kernel_timing(True)
+    step()
+    torch.cuda.synchronize()
+    agg = {}
+    for name, e0, e1 in _lib.kernel_timing(False):
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += e0.elapsed_time(e1)
+    # host/device split of one step: wall clock with a sync after each phase
+    def phase(fn):
+        torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize()
+        return r, (time.perf_counter() - t0) * 1e3
+    ph = {}
+    opt.zero_grad(set_to_none=True)
+    pred, ph["wavenet_fwd"] = phase(lambda: wn(sig[:, :, 0:-1]))
+    trans, ph["classifier_fwd"] = phase(lambda: cn(pred))
+    def xe_():
+        dense = W.ops.argmax_channels(sig[:, :, 1:].contiguous())
+        return W.functional.cross_entropy_sum(pred, dense) / B
+    xe, ph["xent"] = phase(xe_)
+    def ctc_():
+        probs = trans.permute(2, 0, 1).contiguous()
+        pl = torch.full((B,), probs.shape[0], dtype=torch.int32)
+        return torch.nn.functional.ctc_loss(torch.log_softmax(probs.float(), 2), seq, pl, lengths, blank=0,
+                                            reduction="sum", zero_infinity=True)
+    ctc, ph["ctc_fwd"] = phase(ctc_)
+    loss = xe / T + ctc / trans.shape[2]
+    _, ph["backward"] = phase(loss.backward)
+    _, ph["adam"] = phase(opt.step)
+    flop = 3 * (21495808 + 16910848 / 3)
+    print(json.dumps({"config": "wavenet_ctc_train_step_bf16_tensor_core", "batch": B, "T": T, "ms_per_step": ms,
+                      "samples_per_s": B * T / (ms * 1e-3), "tflops_as_written_3x_fwd": B * T / (ms * 1e-3) * flop / 1e12,
+                      "loss_first": l0, "loss_after": l1, "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+                      "phases_ms": {k: round(v, 2) for k, v in ph.items()},
+                      "kernels_ms": {k: [v[0], round(v[1], 3)] for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])}}))
 
 if "longread" in which:    # config 5: 1M-sample read, time-sharded in 8 shards (emulated on one GPU) vs one pass
     net = ecoli_net().cuda().bfloat16().eval()

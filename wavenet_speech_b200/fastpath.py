@@ -115,8 +115,9 @@ def chain(x_nlc, C, offsets, epi1, w1, b1, n1, n2=0, use_x2=0, epi2=0, w2=None, 
 RESBLOCK_VARIANT = int(__import__("os").environ.get("WNB200_RESBLOCK_VARIANT", "0"))
 
 
-def resblock(x_nlc, pk, res, skips, skips_init, dbg=None, variant=None):
-    """Pipelined fused block (C = 128 / 256).  variant 0/2 = CTA-pair kernel, 1 = single-CTA kernel."""
+def resblock(x_nlc, pk, res, skips, skips_init, dbg=None, variant=None, save=None):
+    """Pipelined fused block (C = 128 / 256).  variant 0/2 = CTA-pair kernel, 1 = single-CTA kernel.
+    save = (gate, th, sg) NLC bf16 buffers: training keeps the gate and its two factors for backward."""
     a = _lib.ResBlock()
     B, T, C = x_nlc.shape
     a.B, a.T, a.C, a.ntaps = B, T, C, len(pk["offsets"])
@@ -127,6 +128,8 @@ def resblock(x_nlc, pk, res, skips, skips_init, dbg=None, variant=None):
     p = lambda t: 0 if t is None else t.data_ptr()
     a.x, a.w1, a.bias1, a.w2, a.bias2 = p(x_nlc), p(pk["w1h"]), p(pk["b1h"]), p(pk["w2"]), p(pk["b2"])
     a.res, a.skips, a.dbg = p(res), p(skips), p(dbg)
+    if save is not None:
+        a.save_act, a.save_th, a.save_sg = p(save[0]), p(save[1]), p(save[2])
     _lib.current_tag = "resblock"
     try:
         _lib.call("wnb200_resblock_fwd_tc", ctypes.byref(a), ops._stream())
@@ -134,8 +137,9 @@ def resblock(x_nlc, pk, res, skips, skips_init, dbg=None, variant=None):
         _lib.current_tag = None
 
 
-def dense(x_nlc, offsets, w, bias, N, mode=0, leaky=0, out=None, n_out=0, softmax=0):
-    """CTA-pair dense contraction.  mode 0 -> NLC bf16 [B,T,N]; mode 1 -> NCL `out` [B,n_out,T]."""
+def dense(x_nlc, offsets, w, bias, N, mode=0, leaky=0, out=None, n_out=0, softmax=0, x2=None, offsets2=()):
+    """CTA-pair dense contraction.  mode 0 -> NLC bf16 [B,T,N]; mode 1 -> NCL `out` [B,n_out,T].
+    Optional second source x2 [B,T,Cin2] with its own taps: its columns follow x's in `w`."""
     B, T, Cin = x_nlc.shape
     a = _lib.Dense()
     a.B, a.T, a.Cin, a.ntaps = B, T, Cin, len(offsets)
@@ -146,6 +150,12 @@ def dense(x_nlc, offsets, w, bias, N, mode=0, leaky=0, out=None, n_out=0, softma
         out = torch.empty((B, T, N), dtype=torch.bfloat16, device=x_nlc.device)
     a.out_f32 = 1 if out.dtype == torch.float32 else 0
     a.x, a.w, a.bias, a.y = x_nlc.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr()
+    if x2 is not None:
+        assert x2.shape[:2] == x_nlc.shape[:2]
+        a.x2, a.Cin2, a.ntaps2 = x2.data_ptr(), x2.shape[2], len(offsets2)
+        for j, o in enumerate(offsets2):
+            a.t_off2[j] = int(o)
+    assert w.shape[1] == Cin * len(offsets) + (0 if x2 is None else x2.shape[2] * len(offsets2)), "dense: K mismatch"
     _lib.current_tag = "dense" if mode == 0 else "head"
     try:
         _lib.call("wnb200_dense_fwd_tc", ctypes.byref(a), ops._stream())
@@ -235,7 +245,10 @@ def try_wavenet_forward(model, signal):
     if signal.dtype != torch.bfloat16 or not signal.is_cuda or signal.dim() != 3:
         return None
     C = model.layers[0][0]
-    if not (_no_graph(model, signal) and model.in_dim == C and model.out_dim == C and _stack_ok(C, model.layers)
+    if not _no_graph(model, signal):
+        from . import training
+        return training.wavenet_forward_train(model, signal) if training.wavenet_train_eligible(model, signal) else None
+    if not (model.in_dim == C and model.out_dim == C and _stack_ok(C, model.layers)
             and model.entry_kwidth <= 3 and signal.shape[0] > 0 and signal.shape[2] > 0):
         return None
     ops.check_device()
@@ -299,7 +312,10 @@ def try_classifier_forward(model, seq):
         return None
     C = model.layers[0][0]
     pool = model.pool_kernel_size
-    if not (_no_graph(model, seq) and model.in_dim == C and model.out_dim == C and C in (128, 256)
+    if not _no_graph(model, seq):
+        from . import training
+        return training.classifier_forward_train(model, seq) if training.classifier_train_eligible(model, seq) else None
+    if not (model.in_dim == C and model.out_dim == C and C in (128, 256)
             and _stack_ok(C, model.layers) and model.input_kernel_size <= 3 and seq.shape[0] > 0
             and seq.shape[2] // pool > 0):
         return None

@@ -1,0 +1,336 @@
+"""Tensor-core training path: forward that keeps what backward needs, and the backward itself, for the
+residual stack and the networks built on it (WaveNet, WaveNetClassifier) -- the WaveNet-CTC train step of
+reference legacy_code/train.py:24-61 (BASELINE config 3).
+
+Everything is NLC bf16 between kernels, fp32 accumulation in TMEM, fp32 parameter gradients.  Per block
+(reference block.py:54-82 + the bottleneck of wavenet.py:100), with row vectors per frame:
+
+  forward   gate = th * sg,  th = tanh(Wt (*) x + bt),  sg = sigmoid(Ws (*) x + bs)      fused block kernel,
+            res  = Wres gate + Wproj x + b ;  skips += Wbn (Wskip gate + bskip) + bbn     saves gate, th, sg
+  backward  dgate = Wres^T dres + (Wbn Wskip)^T dskips                 two-source dense contraction
+            dab   = [dgate sg (1-th^2) ; dgate th sg (1-sg)]           gate-backward kernel
+            dx    = sum_j [Wt_j ; Ws_j]^T dab(t - off_j) + Wproj^T dres   two-source dense, negated tap offsets
+            dWt_j, dWs_j = dab (x) x(t + off_j);  dWres = dres (x) gate;  dWproj = dres (x) x   time-contraction
+            M = dskips (x) gate;  dWskip = Wbn^T M;  dWbn = M Wskip^T + colsum(dskips) bskip^T   (weight space)
+
+`dskips` (gradient of the running skip sum) is the same tensor for every layer.
+"""
+import torch
+
+from . import _lib, fastpath as FP, ops
+
+
+def _t(w):
+    return w.detach().float().t()
+
+
+def _zeros(n, dev):
+    return torch.zeros(n, dtype=torch.float32, device=dev)
+
+
+def pack_block_bwd(block, bottleneck):
+    """K-major bf16 matrices of the two data-gradient contractions of one block."""
+    C = block.out_channels
+    wt = block.conv_tanh.conv1d.weight.detach().float()         # [C, C, k]
+    ws = block.conv_sigmoid.conv1d.weight.detach().float()
+    k = wt.shape[2]
+    wres = block.conv1x1_residual.weight.detach().float()[:, :, 0]
+    wskip = block.conv1x1_skip.weight.detach().float()[:, :, 0]
+    wproj = block.residual_proj.weight.detach().float()
+    wbn = bottleneck.weight.detach().float()[:, :, 0]
+    fold = wbn @ wskip
+    # dgate[n] = sum_m Wres[m, n] dres[m] + sum_m fold[m, n] dskips[m]
+    wdg = torch.cat([wres.t(), fold.t()], 1)                     # [C, 2C]
+    # dx[n] = sum_j sum_m Wt[m, n, j] da[m](t - off_j) + Ws[m, n, j] ds[m](t - off_j)  +  sum_m Wproj[m, n] dres[m]
+    cols = []
+    for j in range(k):
+        cols += [wt[:, :, j].t(), ws[:, :, j].t()]
+    wdx_taps = torch.cat(cols, 1)                                # [C, k * 2C]
+    return {"wdg": FP._bf16(wdg), "wdg_skip": FP._bf16(fold.t()), "wdx": FP._bf16(torch.cat([wdx_taps, wproj.t()], 1)),
+            "wdx_taps": FP._bf16(wdx_taps), "k": k, "C": C}
+
+
+def colsum(x_nlc, out=None):
+    """fp32 column sums of an NLC bf16 tensor [B, T, C] (accumulates into `out`)."""
+    B, T, C = x_nlc.shape
+    if out is None:
+        out = _zeros(C, x_nlc.device)
+    _lib.call("wnb200_colsum_nlc", B * T, C, ops._p(x_nlc), ops._p(out), ops._stream())
+    return out
+
+
+def gate_bwd_nlc(dgate, th, sg):
+    B, T, C = dgate.shape
+    dab = torch.empty((B, T, 2 * C), dtype=torch.bfloat16, device=dgate.device)
+    _lib.call("wnb200_gate_bwd_nlc", B * T, C, ops._p(dgate), ops._p(th), ops._p(sg), ops._p(dab), ops._stream())
+    return dab
+
+
+def leaky_bwd(dy, ref):
+    """dy * (ref > 0 ? 1 : 0.01), any layout (ref = the LeakyReLU's input or output: same sign)."""
+    return ops.leaky_bwd(dy, ref)
+
+
+def wgrad_rows(g, x, off, rows, N):
+    """sum_{b,t} g[b,t,m] x[b,t+off,n] for m < rows -> fp32 [rows, N] (256 rows of dW per launch)."""
+    parts = [FP.wgrad(g, x, off=off, m0=m0)[:min(256, rows - m0)] for m0 in range(0, rows, 256)]
+    return parts[0] if len(parts) == 1 else torch.cat(parts, 0)
+
+
+class Stack(object):
+    """The blocks + bottlenecks of one network with their forward / backward weight packs."""
+
+    def __init__(self, blocks, bottlenecks):
+        self.blocks, self.necks = list(blocks), list(bottlenecks)
+        self.fwd = [FP.pack_block(b, n) for b, n in zip(self.blocks, self.necks)]
+        self.bwd = [pack_block_bwd(b, n) for b, n in zip(self.blocks, self.necks)]
+
+    def params(self):
+        """Per layer, in this order: wt, bt, ws, bs, wres, bres, wskip, bskip, wproj, bproj, wbn, bbn."""
+        out = []
+        for b, n in zip(self.blocks, self.necks):
+            out += [b.conv_tanh.conv1d.weight, b.conv_tanh.conv1d.bias, b.conv_sigmoid.conv1d.weight,
+                    b.conv_sigmoid.conv1d.bias, b.conv1x1_residual.weight, b.conv1x1_residual.bias,
+                    b.conv1x1_skip.weight, b.conv1x1_skip.bias, b.residual_proj.weight, b.residual_proj.bias,
+                    n.weight, n.bias]
+        return out
+
+
+def stack_forward(h0, stack, skips):
+    """Residual stack keeping (x, gate, th, sg) of every layer.  Returns the saved list."""
+    saved = []
+    h = h0
+    n = len(stack.fwd)
+    for l, pk in enumerate(stack.fwd):
+        last = l == n - 1
+        act, th, sg = torch.empty_like(h), torch.empty_like(h), torch.empty_like(h)
+        res = None if last else torch.empty_like(h)
+        FP.resblock(h, pk, res, skips, l == 0, save=(act, th, sg))
+        saved.append((h, act, th, sg))
+        h = res
+    return saved
+
+
+def stack_backward(stack, saved, dskips, need_dx0):
+    """-> (dh0 or None, list of per-layer parameter gradients in Stack.params() order, fp32)."""
+    B, T, C = dskips.shape
+    dev = dskips.device
+    zb = _zeros(C, dev)
+    csk = colsum(dskips)                                    # d(bottleneck bias), identical for every layer
+    L = len(saved)
+    grads = [None] * L
+    Ms = [None] * L
+    dres = None
+    for l in range(L - 1, -1, -1):
+        x, act, th, sg = saved[l]
+        pb, offs = stack.bwd[l], stack.fwd[l]["offsets"]
+        k = pb["k"]
+        if dres is None:
+            dg = FP.dense(dskips, [0], pb["wdg_skip"], zb, C)
+        else:
+            dg = FP.dense(dres, [0], pb["wdg"], zb, C, x2=dskips, offsets2=[0])
+        dab = gate_bwd_nlc(dg, th, sg)
+        del dg
+        dx = None
+        if l > 0 or need_dx0:
+            neg = [-o for o in offs]
+            if dres is None:
+                dx = FP.dense(dab, neg, pb["wdx_taps"], zb, C)
+            else:
+                dx = FP.dense(dab, neg, pb["wdx"], zb, C, x2=dres, offsets2=[0])
+        dwab = [wgrad_rows(dab, x, offs[j], 2 * C, C) for j in range(k)]            # k x [2C, C]
+        dwt = torch.stack([d[:C] for d in dwab], 2)
+        dws = torch.stack([d[C:] for d in dwab], 2)
+        dbab = colsum(dab)
+        dwres = dwproj = dbres = None
+        if dres is not None:
+            dwres = wgrad_rows(dres, act, 0, C, C).unsqueeze(2)
+            dwproj = wgrad_rows(dres, x, 0, C, C)
+            dbres = colsum(dres)
+        Ms[l] = wgrad_rows(dskips, act, 0, C, C)
+        grads[l] = [dwt, dbab[:C], dws, dbab[C:], dwres, dbres, None, None, dwproj, dbres, None, csk]
+        saved[l] = None                                     # free this layer's activations
+        dres = dx
+    # weight-space algebra of the folded skip -> bottleneck product, batched over layers
+    M = torch.stack(Ms)                                                               # [L, C, C]
+    wbn = torch.stack([n.weight.detach().float()[:, :, 0] for n in stack.necks])
+    wskip = torch.stack([b.conv1x1_skip.weight.detach().float()[:, :, 0] for b in stack.blocks])
+    bskip = torch.stack([b.conv1x1_skip.bias.detach().float() for b in stack.blocks])
+    dwskip = torch.bmm(wbn.transpose(1, 2), M)
+    dwbn = torch.bmm(M, wskip.transpose(1, 2)) + csk.view(1, C, 1) * bskip.view(L, 1, C)
+    dbskip = torch.matmul(wbn.transpose(1, 2), csk)
+    for l in range(L):
+        grads[l][6], grads[l][7], grads[l][10] = dwskip[l].unsqueeze(2), dbskip[l], dwbn[l].unsqueeze(2)
+    return dres, grads
+
+
+def head_forward(skips, hd, out_dtype, softmax):
+    """LeakyReLU -> 1x1 -> LeakyReLU -> 1x1 [-> softmax]; returns (out NCL, skips_act, h1)."""
+    B, T, C = skips.shape
+    skips_act = FP.leaky_to_bf16(skips)
+    h1 = FP.dense(skips_act, [0], hd["w1"], hd["b1"], C, leaky=1)
+    out = torch.empty((B, hd["n_out"], T), dtype=out_dtype, device=skips.device)
+    FP.dense(h1, [0], hd["w2"], hd["b2"], hd["n2"], mode=1, out=out, n_out=hd["n_out"], softmax=softmax)
+    return out, skips_act, h1
+
+
+def pack_head_bwd(head, C):
+    w1 = head[1].weight.detach().float()[:, :, 0]
+    w3 = head[3].weight.detach().float()[:, :, 0]               # [n_out, C]
+    n_out = w3.shape[0]
+    npad = (n_out + 63) // 64 * 64
+    w3t = torch.zeros(C, npad, device=w3.device)
+    w3t[:, :n_out] = w3.t()
+    return {"w3t": FP._bf16(w3t), "w1t": FP._bf16(w1.t()), "npad": npad, "n_out": n_out}
+
+
+def head_backward(dout, out, softmax, hb, skips_act, h1):
+    """dout NCL [B, n_out, T] -> (dskips NLC bf16, [dw1, db1, dw3, db3])."""
+    B, n_out, T = dout.shape
+    C = h1.shape[2]
+    dev = dout.device
+    if softmax:
+        dout = ops.softmax_bwd(out, dout.to(out.dtype))
+    if hb["npad"] != n_out:
+        pad = torch.zeros((B, hb["npad"], T), dtype=dout.dtype, device=dev)
+        pad[:, :n_out] = dout
+        dout = pad
+    dl = FP.ncl_to_nlc_bf16(dout)                                                   # [B, T, npad]
+    zb = _zeros(C, dev)
+    dh1 = leaky_bwd(FP.dense(dl, [0], hb["w3t"], zb, C), h1)
+    dw3 = wgrad_rows(dl, h1, 0, n_out, C).unsqueeze(2)
+    db3 = colsum(dl)[:n_out]
+    dskips = leaky_bwd(FP.dense(dh1, [0], hb["w1t"], zb, C), skips_act)
+    dw1 = wgrad_rows(dh1, skips_act, 0, C, C).unsqueeze(2)
+    db1 = colsum(dh1)
+    return dskips, [dw1, db1, dw3, db3]
+
+
+def _head_params(head):
+    return [head[1].weight, head[1].bias, head[3].weight, head[3].bias]
+
+
+def _cast(grads, params):
+    return tuple(None if g is None else g.reshape(p.shape).to(p.dtype) for g, p in zip(grads, params))
+
+
+# --------------------------------------------------------------------------- WaveNet
+def _wavenet_pack(model):
+    C = model.layers[0][0]
+    ec = model.entry_conv1d.conv1d
+    w = ec.weight.detach().float()                                                  # [C, in_dim, k]
+    return {"entry_w": FP._bf16(FP._taps_matrix(ec.weight)), "entry_b": ec.bias.detach().float().contiguous(),
+            "entry_wt": FP._bf16(torch.cat([w[:, :, j].t() for j in range(w.shape[2])], 1)),   # [in_dim, k*C]
+            "stack": Stack(model.convolutions, model.bottlenecks),
+            "head": FP.pack_head(model.output_stack, C), "head_bwd": pack_head_bwd(model.output_stack, C)}
+
+
+def _wavenet_params(model, pk):
+    ec = model.entry_conv1d.conv1d
+    return [ec.weight, ec.bias] + pk["stack"].params() + _head_params(model.output_stack)
+
+
+class _WaveNetTrain(torch.autograd.Function):
+    """WaveNet.forward (reference wavenet.py:88-111) with its backward, both on the tensor-core kernels."""
+
+    @staticmethod
+    def forward(ctx, model, pk, signal, *params):
+        C = model.layers[0][0]
+        B, _, T = signal.shape
+        x = FP.ncl_to_nlc_bf16(signal)
+        offs = list(model.entry_conv1d.offsets)
+        h0 = FP.dense(x, offs, pk["entry_w"], pk["entry_b"], C)
+        skips = torch.empty((B, T, C), dtype=torch.float32, device=signal.device)
+        saved = stack_forward(h0, pk["stack"], skips)
+        out, skips_act, h1 = head_forward(skips, pk["head"], signal.dtype, model.softmax)
+        del skips
+        ctx.model, ctx.pk, ctx.params = model, pk, params
+        ctx.keep = (x, offs, saved, skips_act, h1, out if model.softmax else None)
+        ctx.in_dtype = signal.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        model, pk, params = ctx.model, ctx.pk, ctx.params
+        x, offs, saved, skips_act, h1, out = ctx.keep
+        ctx.keep = None
+        dskips, ghead = head_backward(dout.contiguous(), out, model.softmax, pk["head_bwd"], skips_act, h1)
+        dh0, gl = stack_backward(pk["stack"], saved, dskips, True)
+        C, in_dim = dh0.shape[2], x.shape[2]
+        dwe = torch.stack([wgrad_rows(dh0, x, o, C, in_dim) for o in offs], 2)
+        dbe = colsum(dh0)
+        dsignal = None
+        if ctx.needs_input_grad[2]:
+            dxn = FP.dense(dh0, [-o for o in offs], pk["entry_wt"], _zeros(in_dim, dh0.device), in_dim)
+            dsignal = FP.nlc_to_ncl(dxn, ctx.in_dtype)
+        grads = [dwe, dbe] + [g for layer in gl for g in layer] + ghead
+        return (None, None, dsignal) + _cast(grads, params)
+
+
+def wavenet_train_eligible(model, signal):
+    C = model.layers[0][0]
+    return (signal.dtype == torch.bfloat16 and signal.is_cuda and signal.dim() == 3 and C in (128, 256)
+            and model.in_dim in (128, 256) and model.out_dim == C and FP._stack_ok(C, model.layers)
+            and model.entry_kwidth <= 3 and signal.shape[0] > 0 and signal.shape[2] > 0)
+
+
+def wavenet_forward_train(model, signal):
+    ops.check_device()
+    pk = FP._cached(model, "wavenet_train", lambda: _wavenet_pack(model))
+    return _WaveNetTrain.apply(model, pk, signal.contiguous(), *_wavenet_params(model, pk))
+
+
+# --------------------------------------------------------------------------- WaveNetClassifier
+def _classifier_pack(model):
+    C = model.layers[0][0]
+    return {"stack": Stack([model.input_block] + list(model.convolutions),
+                           [model.input_skip_bottleneck] + list(model.bottlenecks)),
+            "head": FP.pack_head(model.output_block, C), "head_bwd": pack_head_bwd(model.output_block, C)}
+
+
+class _ClassifierTrain(torch.autograd.Function):
+    """WaveNetClassifier.forward (reference classifier.py:91-120) with its backward on the tensor-core kernels."""
+
+    @staticmethod
+    def forward(ctx, model, pk, seq, *params):
+        C = model.layers[0][0]
+        pool = model.pool_kernel_size
+        B, _, T = seq.shape
+        To = T // pool
+        h0 = torch.empty((B, To, C), dtype=torch.bfloat16, device=seq.device)
+        _lib.call("wnb200_avgpool_ncl_to_nlc_bf16", ops._dt(seq), B, C, T, pool, ops._p(seq), ops._p(h0), ops._stream())
+        skips = torch.empty((B, To, C), dtype=torch.float32, device=seq.device)
+        saved = stack_forward(h0, pk["stack"], skips)
+        out, skips_act, h1 = head_forward(skips, pk["head"], seq.dtype, model.softmax)
+        ctx.model, ctx.pk, ctx.params = model, pk, params
+        ctx.keep = (saved, skips_act, h1, out if model.softmax else None)
+        ctx.T, ctx.in_dtype = T, seq.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        model, pk, params = ctx.model, ctx.pk, ctx.params
+        saved, skips_act, h1, out = ctx.keep
+        ctx.keep = None
+        need_dx = ctx.needs_input_grad[2]
+        dskips, ghead = head_backward(dout.contiguous(), out, model.softmax, pk["head_bwd"], skips_act, h1)
+        dh0, gl = stack_backward(pk["stack"], saved, dskips, need_dx)
+        dseq = None
+        if need_dx:
+            dseq = ops.avgpool_bwd(FP.nlc_to_ncl(dh0, ctx.in_dtype), ctx.T, model.pool_kernel_size)
+        grads = [g for layer in gl for g in layer] + ghead
+        return (None, None, dseq) + _cast(grads, params)
+
+
+def classifier_train_eligible(model, seq):
+    C = model.layers[0][0]
+    return (seq.dtype == torch.bfloat16 and seq.is_cuda and seq.dim() == 3 and C in (128, 256) and model.in_dim == C
+            and model.out_dim == C and FP._stack_ok(C, model.layers) and model.input_kernel_size <= 3
+            and seq.shape[0] > 0 and seq.shape[2] // model.pool_kernel_size > 0)
+
+
+def classifier_forward_train(model, seq):
+    ops.check_device()
+    pk = FP._cached(model, "classifier_train", lambda: _classifier_pack(model))
+    params = pk["stack"].params() + _head_params(model.output_block)
+    return _ClassifierTrain.apply(model, pk, seq.contiguous(), *params)
