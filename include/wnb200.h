@@ -253,6 +253,22 @@ int wnb200_gate_bwd_nlc(int64_t rows, int C, const void* dact, const void* th, c
 /* out[c] += sum over rows of x[r, c]  (x NLC bf16 [rows, C]; bias gradients on the tensor-core training path). */
 int wnb200_colsum_nlc(int64_t rows, int C, const void* x, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * CTC loss (replaces warpctc_pytorch.CTCLoss at legacy_code/train.py:42-46, run_raw_ctc.py:59-62, Loss.py:50-53;
+ * third party in the reference).  Activations are pre-softmax, class 0 is the blank, `act` is addressed by element
+ * strides (sb, sc, st) for (read, class, frame) so both the reference's (T,B,C) layout and the classifier's (B,C,T)
+ * output are read in place.  labels: concatenated int32 labels; label_offsets: int64[B+1] prefix sums;
+ * act_lengths: int32[B] or NULL (= T for every read).  workspace: wnb200_ctc_workspace_bytes() bytes, shared by
+ * fwd and bwd.  fwd writes nll[b] = -log p(labels_b | act_b) (+inf if no alignment exists);
+ * bwd writes grad = gscale[0] * d(sum_b nll[b]) / d act with act's strides (zero for infeasible reads). */
+size_t wnb200_ctc_workspace_bytes(int B, int L, int T, int max_label_len);
+int wnb200_ctc_fwd(int dtype, int B, int L, int T, int max_label_len, const void* act, int64_t sb, int64_t sc,
+                   int64_t st, const int32_t* labels, const int64_t* label_offsets, const int32_t* act_lengths,
+                   float* workspace, float* nll, void* stream);
+int wnb200_ctc_bwd(int dtype, int B, int L, int T, int max_label_len, const int32_t* labels,
+                   const int64_t* label_offsets, const int32_t* act_lengths, const float* workspace, const float* nll,
+                   const float* gscale, void* grad, int64_t sb, int64_t sc, int64_t st, void* stream);
+
 /* y = bf16(LeakyReLU_0.01(x)), n a multiple of 4: turns the fp32 skip sum into the head's input
  * (first LeakyReLU of output_stack, wavenet.py:67). */
 int wnb200_leaky_to_bf16(int64_t n, const float* x, void* y, void* stream);

@@ -261,13 +261,13 @@ def xe_loss_sum_over_time(pred, dense_target):
     return F.cross_entropy(pred, dense_target, reduction="sum") / B
 
 
-def ctc_loss_sum(activations_tbc, flat_labels, act_lengths, label_lengths):
+def ctc_loss_sum(activations_tbc, flat_labels, act_lengths, label_lengths, dtype=torch.float32):
     """Stand-in for warpctc_pytorch.CTCLoss as the reference calls it
     (legacy_code/train.py:42-46): pre-softmax activations (T,B,C), flattened int
     labels with 0 = blank, summed over the batch.  warp-ctc is an un-vendored,
     un-pinned third-party dependency (README.md:15-16); its published semantics
     are softmax-inside + sum reduction, reproduced here with torch's CTC."""
-    logp = F.log_softmax(activations_tbc.float(), dim=2)
+    logp = F.log_softmax(activations_tbc.to(dtype), dim=2)     # dtype=float64: the precision yardstick of the tests
     return F.ctc_loss(logp, flat_labels, act_lengths, label_lengths, blank=0, reduction="sum",
                       zero_infinity=False)
 

@@ -112,16 +112,24 @@ if "train_tc" in which:    # config 3 on the tensor-core path: bf16 operands, fp
     lengths = torch.tensor([min(len(l), nlab) for l in labels], dtype=torch.int32)
     seq = torch.cat([torch.from_numpy(l[:nlab]) for l in labels]).int().cuda()
 
+    def ctc_torch(trans):
+        probs = trans.permute(2, 0, 1).contiguous()
+        pl = torch.full((B,), probs.shape[0], dtype=torch.int32)
+        return torch.nn.functional.ctc_loss(torch.log_softmax(probs.float(), 2), seq, pl, lengths, blank=0,
+                                            reduction="sum", zero_infinity=True)
+
+    def ctc_ours(trans):                    # device CTC kernels, reads the classifier's (B, C, T) output in place
+        return W.functional.ctc_loss_sum(trans, seq, lengths, layout="bct")
+
+    ctc_fn = ctc_torch if opts.get("ctc") == "torch" else ctc_ours
+
     def step():
         opt.zero_grad(set_to_none=True)
         pred = wn(sig[:, :, 0:-1])
         trans = cn(pred)
         dense = W.ops.argmax_channels(sig[:, :, 1:].contiguous())
         xe = W.functional.cross_entropy_sum(pred, dense) / B
-        probs = trans.permute(2, 0, 1).contiguous()
-        pl = torch.full((B,), probs.shape[0], dtype=torch.int32)
-        ctc = torch.nn.functional.ctc_loss(torch.log_softmax(probs.float(), 2), seq, pl, lengths, blank=0,
-                                           reduction="sum", zero_infinity=True)
+        ctc = ctc_fn(trans)
         loss = xe / T + ctc / trans.shape[2]
         loss.backward()
         opt.step()
@@ -150,17 +158,12 @@ if "train_tc" in which:    # config 3 on the tensor-core path: bf16 operands, fp
         dense = W.ops.argmax_channels(sig[:, :, 1:].contiguous())
         return W.functional.cross_entropy_sum(pred, dense) / B
     xe, ph["xent"] = phase(xe_)
-    def ctc_():
-        probs = trans.permute(2, 0, 1).contiguous()
-        pl = torch.full((B,), probs.shape[0], dtype=torch.int32)
-        return torch.nn.functional.ctc_loss(torch.log_softmax(probs.float(), 2), seq, pl, lengths, blank=0,
-                                            reduction="sum", zero_infinity=True)
-    ctc, ph["ctc_fwd"] = phase(ctc_)
+    ctc, ph["ctc_fwd"] = phase(lambda: ctc_fn(trans))
     loss = xe / T + ctc / trans.shape[2]
     _, ph["backward"] = phase(loss.backward)
     _, ph["adam"] = phase(opt.step)
     flop = 3 * (21495808 + 16910848 / 3)
-    print(json.dumps({"config": "wavenet_ctc_train_step_bf16_tensor_core", "batch": B, "T": T, "ms_per_step": ms,
+    print(json.dumps({"config": "wavenet_ctc_train_step_bf16_tensor_core", "ctc": opts.get("ctc", "wnb200"), "batch": B, "T": T, "ms_per_step": ms,
                       "samples_per_s": B * T / (ms * 1e-3), "tflops_as_written_3x_fwd": B * T / (ms * 1e-3) * flop / 1e12,
                       "loss_first": l0, "loss_after": l1, "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
                       "phases_ms": {k: round(v, 2) for k, v in ph.items()},

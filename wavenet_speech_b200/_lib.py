@@ -84,11 +84,16 @@ SIGNATURES = {
     "wnb200_wgrad_tc": [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_gate_bwd_nlc": [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_colsum_nlc": [c_int64, c_int, c_void_p, c_void_p, c_void_p],
+    "wnb200_ctc_workspace_bytes": [c_int, c_int, c_int, c_int],
+    "wnb200_ctc_fwd": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+                       c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_ctc_bwd": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                       c_void_p, c_int64, c_int64, c_int64, c_void_p],
     "wnb200_leaky_to_bf16": [c_int64, c_void_p, c_void_p, c_void_p],
     "wnb200_ncl_to_nlc_bf16": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "wnb200_nlc_to_ncl": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
 }
-_RESTYPES = {"wnb200_last_error": ctypes.c_char_p}
+_RESTYPES = {"wnb200_last_error": ctypes.c_char_p, "wnb200_ctc_workspace_bytes": ctypes.c_size_t}
 
 _lib = None
 
@@ -122,7 +127,7 @@ def load():
 
 # kernel launches issued per C-ABI call (for bench.py's `gpu_launches` claim)
 _LAUNCHES_PER_CALL = {"wnb200_sum_f32": 2, "wnb200_last_error": 0, "wnb200_version": 0, "wnb200_check_device": 0,
-                      "wnb200_tc_pack_bytes": 0}
+                      "wnb200_tc_pack_bytes": 0, "wnb200_ctc_workspace_bytes": 0, "wnb200_ctc_fwd": 2}
 launch_count = 0
 _event_log = None     # list of (name, start_event, end_event) while kernel timing is on
 current_tag = None    # optional label (e.g. "resblock") attached to timed calls by the caller

@@ -28,16 +28,51 @@ def _digest():
     return h.hexdigest()
 
 
+def _file_digest(src, headers):
+    h = hashlib.sha256()
+    for p in [src] + headers + [__file__]:
+        with open(p, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()
+
+
 def build(force=False, verbose=False):
+    """One `nvcc -c` per .cu (in parallel, objects cached under csrc/_obj by content hash), then one link."""
+    from concurrent.futures import ThreadPoolExecutor
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
         return LIB
-    cmd = [NVCC] + FLAGS + ["-o", LIB] + _sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
-    with open(os.path.join(PKG, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if res.returncode != 0:
+    objdir = os.path.join(HERE, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    headers = sorted(glob.glob(os.path.join(HERE, "*.cuh"))) + [os.path.join(os.path.dirname(PKG), "include", "wnb200.h")]
+    cflags = [f for f in FLAGS if f != "--shared"]
+    logs = {}
+
+    def compile_one(src):
+        base = os.path.splitext(os.path.basename(src))[0]
+        obj, stamp = os.path.join(objdir, base + ".o"), os.path.join(objdir, base + ".stamp")
+        d = _file_digest(src, headers)
+        if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read().strip() == d:
+            return obj, 0
+        cmd = [NVCC] + cflags + ["-c", "-o", obj, src]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        logs[base] = " ".join(cmd) + "\n" + res.stdout + res.stderr
+        if res.returncode == 0:
+            with open(stamp, "w") as f:
+                f.write(d)
+        return obj, res.returncode
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
+        results = list(ex.map(compile_one, _sources()))
+    link = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", LIB] + [o for o, _ in results]
+    bad = [o for o, rc in results if rc != 0]
+    res = None if bad else subprocess.run(link, capture_output=True, text=True)
+    log = "".join(logs[k] for k in sorted(logs)) + ("" if res is None else " ".join(link) + "\n" + res.stdout + res.stderr)
+    prev = os.path.join(PKG, "build.log")
+    with open(prev, "a" if logs and os.path.exists(prev) and not force else "w") as f:
+        f.write(log)
+    if bad or res.returncode != 0:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed building libwnb200.so")
     if verbose:

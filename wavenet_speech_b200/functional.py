@@ -400,3 +400,68 @@ class _Positions(torch.autograd.Function):
 
 def positions_mix(x, w, b, t0=0):
     return _Positions.apply(x, w, b, int(t0))
+
+
+# --------------------------------------------------------------------------- CTC
+class _CTCSum(torch.autograd.Function):
+    """sum_b -log p(labels_b | act_b) with the blank at class 0 and pre-softmax activations -- the
+    warpctc_pytorch.CTCLoss convention the reference trains with (legacy_code/train.py:42-46).  `layout`:
+    "tbc" = (T, B, C) as the reference passes it, "bct" = the classifier's (B, C, T) output, read in place."""
+
+    @staticmethod
+    def forward(ctx, act, labels, label_lengths, act_lengths, layout):
+        from . import _lib
+        ops._need_cuda(act)
+        ops.check_device()
+        if layout == "tbc":
+            T, B, L = act.shape
+            st, sb, sc = act.stride()
+        else:
+            B, L, T = act.shape
+            sb, sc, st = act.stride()
+        dev = act.device
+        ll = torch.as_tensor(label_lengths, dtype=torch.int64).cpu()
+        assert ll.numel() == B, "ctc: one label length per read"
+        max_len = int(ll.max()) if B > 0 else 0
+        offs = torch.zeros(B + 1, dtype=torch.int64)
+        offs[1:] = torch.cumsum(ll, 0)
+        labels = labels.to(device=dev, dtype=torch.int32).contiguous()
+        assert labels.numel() == int(offs[-1]), "ctc: labels must be the concatenation of the reads' labels"
+        offs = offs.to(dev, non_blocking=True)
+        al = None
+        if act_lengths is not None:
+            al = torch.as_tensor(act_lengths, dtype=torch.int32).to(dev, non_blocking=True).contiguous()
+        nbytes = _lib.load().wnb200_ctc_workspace_bytes(B, L, T, max_len)
+        ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=dev)
+        nll = torch.empty(B, dtype=torch.float32, device=dev)
+        _lib.call("wnb200_ctc_fwd", ops._dt(act), B, L, T, max_len, ops._p(act), sb, sc, st, ops._p(labels),
+                  ops._p(offs), ops._p(al), ops._p(ws), ops._p(nll), ops._stream())
+        ctx.dims = (B, L, T, max_len, sb, sc, st)
+        ctx.save_for_backward(act, labels, offs, al, ws, nll)
+        return ops.sum_f32(nll)
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import _lib
+        act, labels, offs, al, ws, nll = ctx.saved_tensors
+        B, L, T, max_len, sb, sc, st = ctx.dims
+        grad = torch.empty_strided(act.shape, act.stride(), dtype=act.dtype, device=act.device)
+        gs = g.detach().float().reshape(1).contiguous()
+        _lib.call("wnb200_ctc_bwd", ops._dt(act), B, L, T, max_len, ops._p(labels), ops._p(offs), ops._p(al),
+                  ops._p(ws), ops._p(nll), ops._p(gs), ops._p(grad), sb, sc, st, ops._stream())
+        return grad, None, None, None, None
+
+
+def ctc_loss_sum(act, labels, label_lengths, act_lengths=None, layout="bct"):
+    """CTC negative log-likelihood summed over the batch (blank = 0, softmax applied inside)."""
+    assert layout in ("bct", "tbc")
+    return _CTCSum.apply(act, labels, label_lengths, act_lengths, layout)
+
+
+class CTCLoss(torch.nn.Module):
+    """Call-compatible stand-in for warpctc_pytorch.CTCLoss as the reference uses it
+    (legacy_code/train.py:116,46: `ctc_loss_fn(probs, labels, prob_lengths, lengths)` with probs (T, B, C)
+    pre-softmax, labels a flat int tensor with 0 = blank, result summed over the batch, shape (1,))."""
+
+    def forward(self, acts, labels, act_lens, label_lens):
+        return ctc_loss_sum(acts, labels, label_lens, act_lens, layout="tbc").reshape(1)
