@@ -245,6 +245,11 @@ int wnb200_avgpool_ncl_to_nlc_bf16(int dtype, int B, int C, int T, int pool, con
  * [0,T) read as zero.  Weight gradient of every contraction of the residual stack on the bf16 training step. */
 int wnb200_wgrad_tc(int B, int T, int Cg, int m0, int N, int off, const void* g_nlc, const void* x_nlc, float* dw,
                     void* stream);
+/* Same with one or two X tensors sharing the G tiles (nsrc = 1 | 2, off: host int32[nsrc]):
+ *   dw[m, s*N + n] += sum_{b,t} g[b, t, m0+m] * x_s[b, t+off_s, n]        dw fp32 [256, nsrc*N]
+ * e.g. both taps of a dilated conv (x at two offsets) or [gate | x] for conv1x1_residual and residual_proj. */
+int wnb200_wgrad2_tc(int B, int T, int Cg, int m0, int N, int nsrc, const int32_t* off /*host*/, const void* g_nlc,
+                     const void* x_nlc, const void* x2_nlc, float* dw, void* stream);
 
 /* Gate backward on NLC bf16 tensors (block.py:185): dab[r, 0:C] = dact*sg*(1-th^2), dab[r, C:2C] = dact*th*sg*(1-sg)
  * for each of `rows` = B*T frames. */

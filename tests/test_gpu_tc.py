@@ -244,3 +244,29 @@ def test_wgrad_tc(B, T, Cg, m0, N, off):
     # accumulates into an existing buffer
     dw2 = FP.wgrad(g.cuda().bfloat16(), x.cuda().bfloat16(), off=off, m0=m0, dw=dw.clone())
     assert rel(dw2, 2 * ref) <= 2e-3
+
+
+@pytest.mark.parametrize("B,T,Cg,m0,N,offs", [(2, 300, 512, 256, 256, (-4, 0)), (1, 1000, 256, 0, 128, (0, 7)),
+                                              (3, 777, 256, 0, 256, (-512, 1))])
+def test_wgrad2_tc(B, T, Cg, m0, N, offs):
+    """Two X tensors sharing the G tiles (both taps of a conv / [gate | x]): dw = [dw_0 | dw_1]."""
+    torch.manual_seed(B + T)
+    g = r16(torch.randn(B, T, Cg) * 0.1)
+    xs = [r16(torch.randn(B, T, N)), r16(torch.randn(B, T, N))]
+
+    def shifted(x, off):
+        y = torch.zeros_like(x)
+        if off >= 0:
+            if off < T:
+                y[:, :T - off] = x[:, off:]
+        elif -off < T:
+            y[:, -off:] = x[:, :T + off]
+        return y
+
+    ref = torch.cat([torch.einsum("btm,btn->mn", g[:, :, m0:m0 + 256].double(), shifted(x, o).double())
+                     for x, o in zip(xs, offs)], 1).float()
+    if ref.shape[0] < 256:
+        ref = torch.cat([ref, torch.zeros(256 - ref.shape[0], ref.shape[1])], 0)
+    dw = FP.wgrad2(g.cuda().bfloat16(), [x.cuda().bfloat16() for x in xs], offs, m0=m0)
+    torch.cuda.synchronize()
+    assert rel(dw, ref) <= 2e-3, rel(dw, ref)

@@ -82,6 +82,8 @@ SIGNATURES = {
     "wnb200_featurize_nlc": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_avgpool_ncl_to_nlc_bf16": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "wnb200_wgrad_tc": [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_wgrad2_tc": [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                         c_void_p],
     "wnb200_gate_bwd_nlc": [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_colsum_nlc": [c_int64, c_int, c_void_p, c_void_p, c_void_p],
     "wnb200_ctc_workspace_bytes": [c_int, c_int, c_int, c_int],

@@ -302,20 +302,35 @@ __global__ void gate_bwd_nlc_kernel(long long rows, int C, const uint4* dact, co
   }
 }
 
-// column sums of an NLC bf16 tensor [rows][C]: block = 32 channel-pairs x 8 row lanes
-__global__ void __launch_bounds__(256) colsum_nlc_kernel(long long rows, int C, const __nv_bfloat16* x, float* out) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int ry = threadIdx.x >> 5;
-  float s = 0.f;
-  if (c < C)
-    for (long long r = blockIdx.y * 8ll + ry; r < rows; r += 8ll * gridDim.y) s += __bfloat162float(x[r * C + c]);
-  __shared__ float red[8][33];
-  red[ry][threadIdx.x & 31] = s;
-  __syncthreads();
-  if (ry == 0 && c < C) {
-    float t = 0.f;
+// column sums of an NLC bf16 tensor [rows][C], C % 8 == 0: a thread owns 8 channels (one 16-byte load per row), the
+// C/8 threads of a row sit side by side (a warp reads whole 512-byte rows), 256 / (C/8) rows per block pass,
+// grid-stride over rows; partials meet in shared memory, one atomicAdd per channel per block.
+__global__ void __launch_bounds__(256) colsum_nlc_kernel(long long rows, int C, const uint4* x, float* out) {
+  const int g = C >> 3;                       // 16-byte groups per row
+  const int rpb = 256 / g;                    // rows per block pass (g <= 256)
+  const int cg = threadIdx.x % g, rl = threadIdx.x / g;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (rl < rpb) {
+    for (long long r = blockIdx.x * (long long)rpb + rl; r < rows; r += (long long)gridDim.x * rpb) {
+      const uint4 v = __ldg(x + r * g + cg);
+      const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(p[k]);
+        acc[2 * k] += f.x;
+        acc[2 * k + 1] += f.y;
+      }
+    }
+  }
+  __shared__ float red[256][9];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[threadIdx.x][k] = acc[k];
+  __syncthreads();
+  // thread -> one channel: sum over the rpb row lanes
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const int gq = c >> 3, k = c & 7;
+    float t = 0.f;
+    for (int q = 0; q < rpb; ++q) t += red[q * g + gq][k];
     atomicAdd(&out[c], t);
   }
 }
@@ -526,10 +541,11 @@ extern "C" int wnb200_gate_bwd_nlc(int64_t rows, int C, const void* dact, const 
 extern "C" int wnb200_colsum_nlc(int64_t rows, int C, const void* x, float* out, void* stream) {
   if (rows == 0 || C == 0) return 0;
   WNB_CHECK_ARG(x && out, "colsum_nlc: null pointer");
-  long long gy = (rows + 1023) / 1024;
-  if (gy > 592) gy = 592;
-  dim3 grid((C + 31) / 32, (unsigned)gy);
-  colsum_nlc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rows, C, (const __nv_bfloat16*)x, out);
+  WNB_CHECK_ARG(C % 8 == 0 && C <= 2048, "colsum_nlc: C=%d must be a multiple of 8, <= 2048", C);
+  const int rpb = 256 / (C / 8);
+  long long grid = (rows + rpb - 1) / rpb;
+  if (grid > 148 * 8) grid = 148 * 8;
+  colsum_nlc_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(rows, C, (const uint4*)x, out);
   WNB_LAUNCH_OK();
   return 0;
 }

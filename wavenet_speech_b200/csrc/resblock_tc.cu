@@ -398,11 +398,16 @@ __device__ __forceinline__ void mma_kblock_2sm(uint32_t tmem_d, uint32_t a_addr,
                   (first && k4 == 0) ? 0u : 1u);
 }
 
-template <int C>
+// SAVE (training): the gate and its two factors are kept for backward.  E1 then works on whole 64-channel blocks:
+// tanh / sigmoid go through the two output staging buffers, the gate is stored straight from the shared tile that
+// feeds G2, all three by TMA (thread-level global stores from the TMEM-lane layout cost a 128-byte line per lane).
+template <int C, bool SAVE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RB_THREADS, 1)
 resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                  const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_res,
-                 const __grid_constant__ CUtensorMap map_skips, const ResDev p) {
+                 const __grid_constant__ CUtensorMap map_skips, const __grid_constant__ CUtensorMap map_act,
+                 const __grid_constant__ CUtensorMap map_th, const __grid_constant__ CUtensorMap map_sg,
+                 const ResDev p) {
   using K = R2Cfg<C>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -585,6 +590,51 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         tc_fence_after();
         if (issuer && rank == 0) RB_STAMP(8 + half);
         const uint32_t treg = (half == 0 ? tmemA : tmemB) + lane_off;
+        if constexpr (SAVE) {
+#pragma unroll 1
+          for (int c = 0; c < C / 128; ++c) {          // one 64-channel block of this half per pass
+            const int col = c * 64 + h * 32;
+            float a[32], g[32];
+            tmem_ld16(treg + col, a);
+            tmem_ld16(treg + col + 16, a + 16);
+            tmem_ld16(treg + C / 2 + col, g);
+            tmem_ld16(treg + C / 2 + col + 16, g + 16);
+            const float* bt = p.bias1 + half * C + col;
+            const float* bs = bt + C / 2;
+            tmem_wait_ld();
+            uint32_t pk[16], pt[16], ps[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float t0v = tanh_approx(a[i] + __ldg(bt + i)), s0v = sigmoid_approx(g[i] + __ldg(bs + i));
+              const float t1v = tanh_approx(a[i + 1] + __ldg(bt + i + 1));
+              const float s1v = sigmoid_approx(g[i + 1] + __ldg(bs + i + 1));
+              pk[i >> 1] = pack_bf16x2(t0v * s0v, t1v * s1v);
+              pt[i >> 1] = pack_bf16x2(t0v, t1v);
+              ps[i >> 1] = pack_bf16x2(s0v, s1v);
+            }
+            const int ch0 = half * (C / 2) + c * 64;   // first channel of the block
+            if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            epi_bar();
+            uint8_t* blk = smem_gen + (act_base - smem_base) + (ch0 >> 6) * RB_ABYTES + row * 128;
+            uint8_t* sth = smem_gen + (stg_base - smem_base) + row * 128;
+            uint8_t* ssg = sth + RB_ABYTES;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int o = ((4 * h + j) ^ sw) << 4;
+              *reinterpret_cast<uint4*>(blk + o) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              *reinterpret_cast<uint4*>(sth + o) = make_uint4(pt[4 * j], pt[4 * j + 1], pt[4 * j + 2], pt[4 * j + 3]);
+              *reinterpret_cast<uint4*>(ssg + o) = make_uint4(ps[4 * j], ps[4 * j + 1], ps[4 * j + 2], ps[4 * j + 3]);
+            }
+            fence_proxy_async_smem();
+            epi_bar();
+            if (issuer) {
+              tma_store_3d(&map_act, act_base + (ch0 >> 6) * RB_ABYTES, ch0, t0, b);
+              tma_store_3d(&map_th, stg_base, ch0, t0, b);
+              tma_store_3d(&map_sg, stg_base + RB_ABYTES, ch0, t0, b);
+              bulk_commit();
+            }
+          }
+        } else {
 #pragma unroll 1
         for (int cc = 0; cc < C / 4; cc += 16) {
           const int col = h * (C / 4) + cc;
@@ -601,35 +651,26 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             bsa[4 * j] = v.x; bsa[4 * j + 1] = v.y; bsa[4 * j + 2] = v.z; bsa[4 * j + 3] = v.w;
           }
           tmem_wait_ld();
-          uint32_t pk[8], pt[8], ps[8];
+          uint32_t pk[8];
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
-            const float t0v = tanh_approx(a[i] + bta[i]), s0v = sigmoid_approx(g[i] + bsa[i]);
-            const float t1v = tanh_approx(a[i + 1] + bta[i + 1]), s1v = sigmoid_approx(g[i + 1] + bsa[i + 1]);
-            pk[i >> 1] = pack_bf16x2(t0v * s0v, t1v * s1v);
-            pt[i >> 1] = pack_bf16x2(t0v, t1v);
-            ps[i >> 1] = pack_bf16x2(s0v, s1v);
+            const float v0 = tanh_approx(a[i] + bta[i]) * sigmoid_approx(g[i] + bsa[i]);
+            const float v1 = tanh_approx(a[i + 1] + bta[i + 1]) * sigmoid_approx(g[i + 1] + bsa[i + 1]);
+            pk[i >> 1] = pack_bf16x2(v0, v1);
           }
           const int ch = half * (C / 2) + col;
-          if (p.save_act && t0 + row < p.T) {          // training: keep the gate and its two factors for backward
-            const long long o = ((long long)b * p.T + t0 + row) * C + ch;
-            uint4* da = reinterpret_cast<uint4*>(p.save_act + o);
-            uint4* dt = reinterpret_cast<uint4*>(p.save_th + o);
-            uint4* ds = reinterpret_cast<uint4*>(p.save_sg + o);
-            da[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]); da[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            dt[0] = make_uint4(pt[0], pt[1], pt[2], pt[3]); dt[1] = make_uint4(pt[4], pt[5], pt[6], pt[7]);
-            ds[0] = make_uint4(ps[0], ps[1], ps[2], ps[3]); ds[1] = make_uint4(ps[4], ps[5], ps[6], ps[7]);
-          }
           const int kb = ch >> 6, ci = (ch & 63) >> 3;
           uint8_t* blk = smem_gen + (act_base - smem_base) + kb * RB_ABYTES + row * 128;
           *reinterpret_cast<uint4*>(blk + ((ci ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           *reinterpret_cast<uint4*>(blk + (((ci + 1) ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
         }
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive_cluster(half == 0 ? r_e1a : r_e1b);
       }
 
+      bool drain = SAVE;        // E1's stores still read the staging buffers: drain them before the first reuse
       // ---- E2a: res ----
       mbar_wait(accA_full, 1u);
       tc_fence_after();
@@ -653,7 +694,11 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 32; i += 2) pk[i >> 1] = pack_bf16x2(a[i] + bv[i], a[i + 1] + bv[i + 1]);
           const uint32_t boff = (nchunk & 1u) * RB_ABYTES;
-          if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (issuer) {
+            if (drain) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          }
+          drain = false;
           epi_bar();
           uint8_t* srow = smem_gen + (stg_base - smem_base) + boff + row * 128;
 #pragma unroll
@@ -689,7 +734,11 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
         tmem_wait_ld();
         const uint32_t boff = (nchunk & 1u) * RB_ABYTES;
-        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        if (issuer) {
+          if (drain) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+        drain = false;
         epi_bar();
         uint8_t* srow = smem_gen + (stg_base - smem_base) + boff + row * 128;
 #pragma unroll
@@ -739,13 +788,14 @@ static int launch_resblock(const CUtensorMap& mx, const CUtensorMap& mw1, const 
   return 0;
 }
 
-template <int C>
+template <int C, bool SAVE>
 static int launch_resblock2(const CUtensorMap& mx, const CUtensorMap& mw1, const CUtensorMap& mw2,
-                            const CUtensorMap& mres, const CUtensorMap& msk, const ResDev& p, cudaStream_t st) {
+                            const CUtensorMap& mres, const CUtensorMap& msk, const CUtensorMap& mact,
+                            const CUtensorMap& mth, const CUtensorMap& msg, const ResDev& p, cudaStream_t st) {
   using K = R2Cfg<C>;
   static bool attr_set = false;
   if (!attr_set) {
-    WNB_CUDA_OK(cudaFuncSetAttribute(resblock2_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+    WNB_CUDA_OK(cudaFuncSetAttribute(resblock2_kernel<C, SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
     attr_set = true;
   }
   int dev = 0, sms = 148;
@@ -753,7 +803,7 @@ static int launch_resblock2(const CUtensorMap& mx, const CUtensorMap& mw1, const
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int pairs = sms / 2;
   if (p.num_tiles < pairs) pairs = p.num_tiles;
-  resblock2_kernel<C><<<2 * pairs, RB_THREADS, K::SMEM, st>>>(mx, mw1, mw2, mres, msk, p);
+  resblock2_kernel<C, SAVE><<<2 * pairs, RB_THREADS, K::SMEM, st>>>(mx, mw1, mw2, mres, msk, mact, mth, msg, p);
   WNB_LAUNCH_OK();
   return 0;
 }
@@ -805,8 +855,16 @@ extern "C" int wnb200_resblock_fwd_tc(const wnb200_resblock_t* a, void* stream) 
   if (pair) {
     p.tiles_per_seq = ceil_div(a->T, 2 * RB_TILE);
     p.num_tiles = p.tiles_per_seq * a->B;
-    return C == 256 ? launch_resblock2<256>(mx, mw1, mw2, mres, msk, p, st)
-                    : launch_resblock2<128>(mx, mw1, mw2, mres, msk, p, st);
+    if (a->save_act) {
+      CUtensorMap mact, mth, msg;
+      if ((rc = rb_map_nlc(&mact, a->save_act, a->B, a->T, C, 2))) return rc;
+      if ((rc = rb_map_nlc(&mth, a->save_th, a->B, a->T, C, 2))) return rc;
+      if ((rc = rb_map_nlc(&msg, a->save_sg, a->B, a->T, C, 2))) return rc;
+      return C == 256 ? launch_resblock2<256, true>(mx, mw1, mw2, mres, msk, mact, mth, msg, p, st)
+                      : launch_resblock2<128, true>(mx, mw1, mw2, mres, msk, mact, mth, msg, p, st);
+    }
+    return C == 256 ? launch_resblock2<256, false>(mx, mw1, mw2, mres, msk, mx, mx, mx, p, st)
+                    : launch_resblock2<128, false>(mx, mw1, mw2, mres, msk, mx, mx, mx, p, st);
   }
   return C == 256 ? launch_resblock<256>(mx, mw1, mw2, mres, msk, p, st)
                   : launch_resblock<128>(mx, mw1, mw2, mres, msk, p, st);

@@ -23,12 +23,13 @@ using namespace tc;
 struct WgDev {
   int T, kblocks_per_seq, total_kblocks;
   int m0, N, off;
+  int nsrc, off2;        // optional second X tensor (same N): its dW block follows the first one's columns
 };
 
 constexpr int WG_THREADS = 192;                  // TMA warp, MMA warp, 4 epilogue warps
 constexpr int WG_BOX = 64 * 128;                 // one {64 ch, 64 frames} box = 8 KB
-constexpr int WG_STAGE = 4 * WG_BOX;             // A: 2 boxes (128 rows of dW), B: 2 boxes (this CTA's 128 of N)
-constexpr int WG_NSTAGE = 6;
+constexpr int WG_STAGE = 6 * WG_BOX;             // A: 2 boxes (128 rows of dW), B: up to 4 boxes (this CTA's share of X, X2)
+constexpr int WG_NSTAGE = 4;
 constexpr int WG_STAGING = RB_TILE * 128;
 constexpr int WG_SMEM = WG_NSTAGE * WG_STAGE + WG_STAGING + 1024 + 256;
 
@@ -45,7 +46,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t saddr, uint
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1)
 wgrad2_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_x,
-              const __grid_constant__ CUtensorMap map_dw, const WgDev p) {
+              const __grid_constant__ CUtensorMap map_x2, const __grid_constant__ CUtensorMap map_dw, const WgDev p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -65,11 +66,13 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__
   const int kb_end = (kb_begin + per) < p.total_kblocks ? (kb_begin + per) : p.total_kblocks;
   const int nkb = kb_end > kb_begin ? kb_end - kb_begin : 0;
   const int nhalf = p.N / 2;                                  // X channels held by this CTA
-  const uint32_t stage_bytes = (uint32_t)(2 * WG_BOX + (nhalf / 64) * WG_BOX);
+  const int xboxes = nhalf / 64;                              // boxes per X tensor per CTA
+  const uint32_t stage_bytes = (uint32_t)(2 * WG_BOX + p.nsrc * xboxes * WG_BOX);
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&map_g);
     prefetch_tensormap(&map_x);
+    if (p.nsrc > 1) prefetch_tensormap(&map_x2);
     prefetch_tensormap(&map_dw);
     for (int s = 0; s < WG_NSTAGE; ++s) {
       mbar_init(full_bar(s), 2);
@@ -79,7 +82,7 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc_2sm(tmem_slot, 256);
+    tmem_alloc_2sm(tmem_slot, 512);
     tmem_relinquish_2sm();
   }
   tc_fence_before();
@@ -102,8 +105,11 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__
         for (int i = 0; i < 2; ++i)
           tma_load_3d_2sm(sa + i * WG_BOX, &map_g, lfull, p.m0 + (int)rank * 128 + i * 64, t0, b);
         // B: this CTA's half of X's channels
-        for (int i = 0; i < nhalf / 64; ++i)
-          tma_load_3d_2sm(sa + 2 * WG_BOX + i * WG_BOX, &map_x, lfull, (int)rank * nhalf + i * 64, t0 + p.off, b);
+        for (int i = 0; i < xboxes; ++i)
+          tma_load_3d_2sm(sa + (2 + i) * WG_BOX, &map_x, lfull, (int)rank * nhalf + i * 64, t0 + p.off, b);
+        if (p.nsrc > 1)
+          for (int i = 0; i < xboxes; ++i)
+            tma_load_3d_2sm(sa + (2 + xboxes + i) * WG_BOX, &map_x2, lfull, (int)rank * nhalf + i * 64, t0 + p.off2, b);
         if (rank != 0) mbar_arrive_cluster(lfull);
         if (++stage == WG_NSTAGE) { stage = 0; phase ^= 1; }
       }
@@ -119,9 +125,14 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__
         tc_fence_after();
         const uint32_t sa = smem_base + stage * WG_STAGE;
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4)     // 64 frames = 4 K-steps of 16 frames = 2 eight-row groups each
-          umma_bf16_2sm(tmem_base, make_smem_desc_mn_sw128(sa + k4 * 2048, WG_BOX),
-                        make_smem_desc_mn_sw128(sa + 2 * WG_BOX + k4 * 2048, WG_BOX), idesc, (i == 0 && k4 == 0) ? 0u : 1u);
+        for (int k4 = 0; k4 < 4; ++k4) {   // 64 frames = 4 K-steps of 16 frames = 2 eight-row groups each
+          const uint64_t da = make_smem_desc_mn_sw128(sa + k4 * 2048, WG_BOX);
+          const uint32_t acc = (i == 0 && k4 == 0) ? 0u : 1u;
+          umma_bf16_2sm(tmem_base, da, make_smem_desc_mn_sw128(sa + 2 * WG_BOX + k4 * 2048, WG_BOX), idesc, acc);
+          if (p.nsrc > 1)
+            umma_bf16_2sm(tmem_base + (uint32_t)p.N, da,
+                          make_smem_desc_mn_sw128(sa + (2 + xboxes) * WG_BOX + k4 * 2048, WG_BOX), idesc, acc);
+        }
         umma_commit_2sm(empty_bar(stage));
         if (++stage == WG_NSTAGE) { stage = 0; phase ^= 1; }
       }
@@ -137,7 +148,7 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__
     mbar_wait(acc_full, 0u);
     tc_fence_after();
     uint8_t* srow = smem_gen + (stg_base - smem_base) + row * 128;
-    for (int c = 0; c < p.N / 32; ++c) {
+    for (int c = 0; c < p.nsrc * p.N / 32; ++c) {
       float a[32];
       tmem_ld16(tmem_base + lane_off + c * 32, a);
       tmem_ld16(tmem_base + lane_off + c * 32 + 16, a + 16);
@@ -164,7 +175,7 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__
   cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc_2sm(tmem_base, 256);
+    tmem_dealloc_2sm(tmem_base, 512);
   }
 }
 
@@ -202,23 +213,27 @@ static int wg_map_dw(CUtensorMap* m, const void* ptr, int rows, int N) {
 
 using namespace wnb;
 
-extern "C" int wnb200_wgrad_tc(int B, int T_, int Cg, int m0, int N, int off, const void* g_nlc, const void* x_nlc,
-                               float* dw, void* stream) {
+extern "C" int wnb200_wgrad2_tc(int B, int T_, int Cg, int m0, int N, int nsrc, const int32_t* off /*host*/,
+                                const void* g_nlc, const void* x_nlc, const void* x2_nlc, float* dw, void* stream) {
   WNB_CHECK_ARG(N == 128 || N == 256, "wgrad_tc: N=%d must be 128 or 256", N);
+  WNB_CHECK_ARG(nsrc == 1 || nsrc == 2, "wgrad_tc: nsrc=%d must be 1 or 2", nsrc);
   WNB_CHECK_ARG(m0 >= 0 && m0 < Cg && Cg % 8 == 0, "wgrad_tc: row offset %d outside the %d channels of g", m0, Cg);
   // rows beyond Cg are zero-filled by TMA (their dW rows receive zeros)
   if (B == 0 || T_ == 0) return 0;
-  WNB_CHECK_ARG(g_nlc && x_nlc && dw, "wgrad_tc: null pointer");
+  WNB_CHECK_ARG(g_nlc && x_nlc && dw && off && (nsrc == 1 || x2_nlc), "wgrad_tc: null pointer");
   WgDev p;
   p.T = T_;
   p.kblocks_per_seq = ceil_div(T_, 64);
   p.total_kblocks = p.kblocks_per_seq * B;
-  p.m0 = m0; p.N = N; p.off = off;
-  CUtensorMap mg, mx, mdw;
+  p.m0 = m0; p.N = N; p.off = off[0];
+  p.nsrc = nsrc; p.off2 = nsrc > 1 ? off[1] : 0;
+  CUtensorMap mg, mx, mx2, mdw;
   int rc;
   if ((rc = wg_map_nlc64(&mg, g_nlc, B, T_, Cg))) return rc;
   if ((rc = wg_map_nlc64(&mx, x_nlc, B, T_, N))) return rc;
-  if ((rc = wg_map_dw(&mdw, dw, 256, N))) return rc;
+  mx2 = mx;
+  if (nsrc > 1 && (rc = wg_map_nlc64(&mx2, x2_nlc, B, T_, N))) return rc;
+  if ((rc = wg_map_dw(&mdw, dw, 256, nsrc * N))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     WNB_CUDA_OK(cudaFuncSetAttribute(wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
@@ -229,7 +244,13 @@ extern "C" int wnb200_wgrad_tc(int B, int T_, int Cg, int m0, int N, int off, co
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int pairs = sms / 2;
   if (p.total_kblocks < pairs) pairs = p.total_kblocks;
-  wgrad2_kernel<<<2 * pairs, WG_THREADS, WG_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(mg, mx, mdw, p);
+  wgrad2_kernel<<<2 * pairs, WG_THREADS, WG_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(mg, mx, mx2, mdw, p);
   WNB_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int wnb200_wgrad_tc(int B, int T_, int Cg, int m0, int N, int off, const void* g_nlc, const void* x_nlc,
+                               float* dw, void* stream) {
+  const int32_t offs[2] = {off, 0};
+  return wnb200_wgrad2_tc(B, T_, Cg, m0, N, 1, offs, g_nlc, x_nlc, nullptr, dw, stream);
 }

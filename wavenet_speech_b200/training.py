@@ -71,10 +71,23 @@ def leaky_bwd(dy, ref):
     return ops.leaky_bwd(dy, ref)
 
 
+def wgrad_multi(g, rows, srcs):
+    """For every (x, off) in srcs: sum_{b,t} g[b,t,m] x[b,t+off,n], m < rows -> list of fp32 [rows, N].
+    256 rows of g and two x tensors per launch (the g tiles are read once for both)."""
+    N = srcs[0][0].shape[2]
+    outs = [[] for _ in srcs]
+    for m0 in range(0, rows, 256):
+        nr = min(256, rows - m0)
+        for i in range(0, len(srcs), 2):
+            pair = srcs[i:i + 2]
+            dw = FP.wgrad2(g, [q[0] for q in pair], [q[1] for q in pair], m0)
+            for q in range(len(pair)):
+                outs[i + q].append(dw[:nr, q * N:(q + 1) * N])
+    return [o[0] if len(o) == 1 else torch.cat(o, 0) for o in outs]
+
+
 def wgrad_rows(g, x, off, rows, N):
-    """sum_{b,t} g[b,t,m] x[b,t+off,n] for m < rows -> fp32 [rows, N] (256 rows of dW per launch)."""
-    parts = [FP.wgrad(g, x, off=off, m0=m0)[:min(256, rows - m0)] for m0 in range(0, rows, 256)]
-    return parts[0] if len(parts) == 1 else torch.cat(parts, 0)
+    return wgrad_multi(g, rows, [(x, off)])[0]
 
 
 class Stack(object):
@@ -138,14 +151,14 @@ def stack_backward(stack, saved, dskips, need_dx0):
                 dx = FP.dense(dab, neg, pb["wdx_taps"], zb, C)
             else:
                 dx = FP.dense(dab, neg, pb["wdx"], zb, C, x2=dres, offsets2=[0])
-        dwab = [wgrad_rows(dab, x, offs[j], 2 * C, C) for j in range(k)]            # k x [2C, C]
+        dwab = wgrad_multi(dab, 2 * C, [(x, offs[j]) for j in range(k)])            # k x [2C, C]
         dwt = torch.stack([d[:C] for d in dwab], 2)
         dws = torch.stack([d[C:] for d in dwab], 2)
         dbab = colsum(dab)
         dwres = dwproj = dbres = None
         if dres is not None:
-            dwres = wgrad_rows(dres, act, 0, C, C).unsqueeze(2)
-            dwproj = wgrad_rows(dres, x, 0, C, C)
+            dwres, dwproj = wgrad_multi(dres, C, [(act, 0), (x, 0)])
+            dwres = dwres.unsqueeze(2)
             dbres = colsum(dres)
         Ms[l] = wgrad_rows(dskips, act, 0, C, C)
         grads[l] = [dwt, dbab[:C], dws, dbab[C:], dwres, dbres, None, None, dwproj, dbres, None, csk]
@@ -257,7 +270,7 @@ class _WaveNetTrain(torch.autograd.Function):
         dskips, ghead = head_backward(dout.contiguous(), out, model.softmax, pk["head_bwd"], skips_act, h1)
         dh0, gl = stack_backward(pk["stack"], saved, dskips, True)
         C, in_dim = dh0.shape[2], x.shape[2]
-        dwe = torch.stack([wgrad_rows(dh0, x, o, C, in_dim) for o in offs], 2)
+        dwe = torch.stack(wgrad_multi(dh0, C, [(x, o) for o in offs]), 2)
         dbe = colsum(dh0)
         dsignal = None
         if ctx.needs_input_grad[2]:
