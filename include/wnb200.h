@@ -274,6 +274,18 @@ int wnb200_ctc_bwd(int dtype, int B, int L, int T, int max_label_len, const int3
                    const int64_t* label_offsets, const int32_t* act_lengths, const float* workspace, const float* nll,
                    const float* gscale, void* grad, int64_t sb, int64_t sc, int64_t st, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Greedy decoding (modules/sequence_decoders.py:9-23 argmax_decode; collapse-repeats + drop-blank as done by hand in
+ * ipynbs/Size 1 Pore Model Check.ipynb cell 24).  `act` is addressed by element strides (read, class, frame).
+ * frame_argmax: out[b, t] = argmax_c act[b, c, t] (int64, ties -> lowest class).
+ * ctc_greedy_decode: out_labels[b, 0:out_lengths[b]] = collapsed, blank-free label sequence of read b (int32 [B, T]
+ * buffer, entries past the length are left untouched); act_lengths int32[B] or NULL (= T). */
+int wnb200_frame_argmax(int dtype, int B, int L, int T, const void* act, int64_t sb, int64_t sc, int64_t st,
+                        int64_t* out, void* stream);
+int wnb200_ctc_greedy_decode(int dtype, int B, int L, int T, const void* act, int64_t sb, int64_t sc, int64_t st,
+                             const int32_t* act_lengths, int blank, int32_t* out_labels, int32_t* out_lengths,
+                             void* stream);
+
 /* y = bf16(LeakyReLU_0.01(x)), n a multiple of 4: turns the fp32 skip sum into the head's input
  * (first LeakyReLU of output_stack, wavenet.py:67). */
 int wnb200_leaky_to_bf16(int64_t n, const float* x, void* y, void* stream);

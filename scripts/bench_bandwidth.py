@@ -1,0 +1,80 @@
+"""Achieved HBM bandwidth of the bandwidth-bound kernels (B1 featuriser, B2 mean-pool, B3 softmax / x-ent,
+B4 LayerNorm, layout changes, gate backward, column sums) against the measured copy peak in MEASURED_PEAKS.json.
+One JSON line per kernel: algorithmic bytes (each input read once, each output written once) / CUDA-event time.
+Shapes are those of BASELINE config 2 (32 x 256 x 16384) unless noted; every tensor exceeds the 126 MB L2."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+import wavenet_speech_b200 as W
+from wavenet_speech_b200 import fastpath as FP, ops, training as TR, _lib
+
+peak = 6555.2
+p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+if os.path.exists(p):
+    peak = json.load(open(p))["hbm_gbs"]
+
+
+def timed(fn, steps=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def report(name, nbytes, fn, note=""):
+    ms = timed(fn)
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    print(json.dumps({"kernel": name, "ms": round(ms, 4), "algorithmic_MB": round(nbytes / 1e6, 1),
+                      "GB/s": round(gbs, 1), "frac_of_copy_peak": round(gbs / peak, 3), "peak_GB/s": peak, "note": note}),
+          flush=True)
+
+
+B, C, T = 32, 256, 16384
+n = B * C * T
+bf, f32 = torch.bfloat16, torch.float32
+x_ncl = torch.randn(B, C, T, device="cuda", dtype=bf)
+x_nlc = torch.randn(B, T, C, device="cuda", dtype=bf)
+x_f32 = torch.randn(B, T, C, device="cuda", dtype=f32)
+d2, d3 = torch.randn_like(x_nlc), torch.randn_like(x_nlc)
+tgt = torch.randint(0, C, (B, T), device="cuda")
+
+report("ncl_to_nlc_bf16 (input layout change)", 4 * n, lambda: FP.ncl_to_nlc_bf16(x_ncl))
+report("nlc_to_ncl (output layout change)", 4 * n, lambda: FP.nlc_to_ncl(x_nlc, bf))
+report("leaky_to_bf16 (fp32 skip sum -> head input)", 6 * n, lambda: FP.leaky_to_bf16(x_f32))
+report("softmax_fwd NCL bf16 (B3)", 4 * n, lambda: ops.softmax_fwd(x_ncl))
+report("xent_fwd NCL bf16: log-softmax + NLL (B3)", 2 * n + 16 * B * T, lambda: ops.xent_fwd(x_ncl, tgt))
+lse = ops.xent_fwd(x_ncl, tgt)[1]
+gs = torch.ones(1, device="cuda")
+report("xent_bwd NCL bf16", 4 * n + 12 * B * T, lambda: ops.xent_bwd(x_ncl, tgt, lse, gs))
+report("argmax_channels NCL bf16", 2 * n + 8 * B * T, lambda: ops.argmax_channels(x_ncl))
+h0 = torch.empty((B, T // 3, C), dtype=bf, device="cuda")
+report("avgpool(3) NCL -> NLC bf16 (B2)", 2 * n + 2 * (n // 3),
+       lambda: _lib.call("wnb200_avgpool_ncl_to_nlc_bf16", 1, B, C, T, 3, ops._p(x_ncl), ops._p(h0), ops._stream()))
+report("avgpool_fwd(3) NCL bf16 (B2, generic path)", 2 * n + 2 * (n // 3), lambda: ops.avgpool_fwd(x_ncl, 3))
+g = torch.ones(C, device="cuda")
+report("layernorm_fwd NCL bf16 (B4)", 4 * n + 8 * B * T, lambda: ops.layernorm_fwd(x_ncl, g, g, 1e-6))
+report("gate_bwd_nlc (3 reads, 2C write)", 10 * n, lambda: TR.gate_bwd_nlc(x_nlc, d2, d3))
+report("colsum_nlc (bias gradients)", 2 * n, lambda: TR.colsum(x_nlc))
+report("leaky_bwd bf16", 6 * n, lambda: ops.leaky_bwd(x_nlc, d2))
+# B1: raw-signal featuriser, ecoli RawCTCNet shape (fk = 3, F = 256): reads 4 B, writes F*2 B per sample
+Bf, Tf, F, fk = 256, 4000, 256, 3
+raw = torch.randn(Bf, 1, Tf, device="cuda", dtype=bf)
+w0, b0 = torch.randn(F, fk, device="cuda"), torch.randn(F, device="cuda")
+hf = torch.empty((Bf, Tf + fk - 1, F), dtype=bf, device="cuda")
+report("featurize_nlc (B1: Conv1d(1,F,3) + LeakyReLU -> NLC bf16)", Bf * Tf * 2 + hf.numel() * 2,
+       lambda: _lib.call("wnb200_featurize_nlc", 1, Bf, Tf, F, fk, ops._p(raw), ops._p(w0), ops._p(b0), ops._p(hf),
+                         ops._stream()), note="batch 256 x 4000")
+logits = torch.randn(1024, 5, 4002, device="cuda", dtype=bf)
+report("ctc_greedy_decode (argmax + collapse + pack)", logits.numel() * 2 + 1024 * 4002 * 2,
+       lambda: ops.ctc_greedy_decode(logits), note="1024 reads x 4002 frames x 5 classes; one CTA per read")

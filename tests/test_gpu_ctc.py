@@ -71,3 +71,25 @@ def test_ctc_infeasible_and_full_length_default():
     O.ctc_loss_sum(a.permute(2, 0, 1), labels[4:], torch.tensor([6], dtype=torch.int32),
                    torch.tensor([2], dtype=torch.int32)).backward()
     assert G.rel_linf(g.grad[1:].cpu(), a.grad) <= 1e-4 and float(ref) > 0
+
+
+@pytest.mark.parametrize("B,L,T,dtype", [(3, 5, 50, torch.float32), (2, 5, 3000, torch.float32), (4, 8, 1025, torch.bfloat16),
+                                         (1, 5, 1, torch.float32)])
+def test_greedy_decode_matches_oracle(B, L, T, dtype):
+    """Device argmax / collapse / drop-blank vs modules/sequence_decoders.py:9-23 + the notebook's collapse."""
+    torch.manual_seed(T)
+    # piecewise-constant winners so that repeats, blanks and chunk boundaries (1024 frames) all occur
+    win = torch.randint(0, L, (B, (T + 2) // 3)).repeat_interleave(3, dim=1)[:, :T]
+    x = (torch.randn(B, L, T) * 0.3).scatter_add_(1, win.unsqueeze(1), torch.full((B, 1, T), 3.0)).to(dtype)
+    lens = torch.tensor([T - (7 * b) % max(1, T) for b in range(B)], dtype=torch.int32)
+    ref_frames = O.argmax_decode(x.float().permute(0, 2, 1))
+    got_frames = W.argmax_decode(x.cuda().permute(0, 2, 1))
+    assert got_frames.dtype == torch.int64 and torch.equal(got_frames.cpu(), ref_frames)
+    lab, n = W.ops.ctc_greedy_decode(x.cuda(), lens)
+    for b in range(B):
+        ref = O.collapse_decode(ref_frames[b, :int(lens[b])])
+        assert int(n[b]) == len(ref) and lab[b, :int(n[b])].cpu().tolist() == [int(v) for v in ref], b
+    strings = W.greedy_ctc_decode(x[:, :5].cuda())
+    full = [O.collapse_decode(O.argmax_decode(x[:, :5].float().permute(0, 2, 1))[b]) for b in range(B)]
+    assert strings == ["".join("_AGCT"[int(v)] for v in r) for r in full]
+    assert W.Decoder('argmax').decode(x[:, :5].cuda())[1] == W.labels2strings(ref_frames.clamp(max=4)) or L > 5

@@ -21,7 +21,7 @@ def test_shard_range_and_halos():
     rn = W.RawCTCNet(8, 3, 5, [(8, 8, 2, d) for d in [1, 2, 4, 8, 16] * 3], 8, softmax=False)
     assert S.raw_ctcnet_halo(rn) == (51, 45)
     p = S.time_shard_plan(1000, 1, 4, 51, 45)
-    assert p == {"start": 250, "end": 500, "lo": 199, "hi": 545}
+    assert p == {"start": 250, "end": 500, "lo": 199, "hi": 545, "halo_left": 51, "halo_right": 45}
     p = S.time_shard_plan(1000, 0, 4, 51, 45, align=3)
     assert p["start"] == 0 and p["end"] == 252 and p["lo"] == 0
 
@@ -50,7 +50,6 @@ def _worker(rank, world, port, q):
         full = O.raw_ctcnet_forward(sd, x, layers, softmax=False)
         hl, hr = S.raw_ctcnet_halo(net)
         plan = S.time_shard_plan(T, rank, world, hl, hr)
-        plan["halo_left"], plan["halo_right"] = hl, hr
         x_ext = S.exchange_halo(x[:, :, plan["start"]:plan["end"]].contiguous(), plan, rank, world)
         assert torch.equal(x_ext, x[:, :, plan["lo"]:plan["hi"]])
         y = S.time_sharded_forward(lambda z: O.raw_ctcnet_forward(sd, z, layers, softmax=False), x_ext, plan, T,

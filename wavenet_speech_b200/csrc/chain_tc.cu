@@ -540,20 +540,52 @@ __global__ void ncl_to_nlc_kernel(int C, int Tn, const T* x, bf16* y) {
     if (t < Tn && c < C) y[((long long)b * Tn + t) * C + c] = __float2bfloat16_rn(tile[tx][i]);
   }
 }
-// NLC [B][T][C] (fp32 or bf16) -> NCL [B][C][T] (fp32 or bf16)
+// NLC [B][T][C] (fp32 or bf16) -> NCL [B][C][T] (fp32 or bf16): 64 x 64 (frames x channels) tiles through shared
+// memory; loads are 16 consecutive channels per thread, stores 16 consecutive frames per thread (16-byte accesses on
+// both sides when the row pitches allow it).
 template <typename TI, typename TO>
-__global__ void nlc_to_ncl_kernel(int C, int Tn, const TI* x, TO* y) {
-  __shared__ float tile[32][33];
-  const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  for (int i = ty; i < 32; i += 8) {
-    const int t = t0 + i, c = c0 + tx;
-    tile[i][tx] = (c < C && t < Tn) ? to_f32<TI>(x[((long long)b * Tn + t) * C + c]) : 0.f;
+__global__ void __launch_bounds__(256) nlc_to_ncl_kernel(int C, int Tn, const TI* x, TO* y) {
+  __shared__ float tile[64][65];              // [channel][frame]
+  const int b = blockIdx.z, c0 = blockIdx.y * 64, t0 = blockIdx.x * 64;
+  const int tid = threadIdx.x;
+  {   // load: thread -> (frame = tid / 4, 16 consecutive channels)
+    const int t = tid >> 2, cq = (tid & 3) * 16;
+    float v[16];
+    const TI* src = x + ((long long)b * Tn + t0 + t) * C + c0 + cq;
+    const bool tok = t0 + t < Tn;
+    if (tok && c0 + cq + 16 <= C && ((long long)C * sizeof(TI)) % 16 == 0) {
+      constexpr int NV = 16 * sizeof(TI) / 16;             // 16-byte vectors for 16 channels
+      uint4 raw[NV];
+#pragma unroll
+      for (int q = 0; q < NV; ++q) raw[q] = __ldg(reinterpret_cast<const uint4*>(src) + q);
+      const TI* e = reinterpret_cast<const TI*>(raw);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = to_f32<TI>(e[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = (tok && c0 + cq + i < C) ? to_f32<TI>(src[i]) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) tile[cq + i][t] = v[i];
   }
   __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    const int c = c0 + i, t = t0 + tx;
-    if (t < Tn && c < C) y[((long long)b * C + c) * Tn + t] = from_f32<TO>(tile[tx][i]);
+  {   // store: thread -> (channel = tid / 4, 16 consecutive frames)
+    const int c = tid >> 2, tq = (tid & 3) * 16;
+    if (c0 + c < C) {
+      TO* dst = y + ((long long)b * C + c0 + c) * Tn + t0 + tq;
+      if (t0 + tq + 16 <= Tn && ((long long)Tn * sizeof(TO)) % 16 == 0) {
+        constexpr int NV = 16 * sizeof(TO) / 16;
+        uint4 raw[NV];
+        TO* e = reinterpret_cast<TO*>(raw);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) e[i] = from_f32<TO>(tile[c][tq + i]);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) reinterpret_cast<uint4*>(dst)[q] = raw[q];
+      } else {
+        for (int i = 0; i < 16; ++i)
+          if (t0 + tq + i < Tn) dst[i] = from_f32<TO>(tile[c][tq + i]);
+      }
+    }
   }
 }
 }  // namespace wnb
@@ -562,7 +594,7 @@ extern "C" int wnb200_nlc_to_ncl(int out_dtype, int src_is_f32, int B, int C, in
                                  void* stream) {
   WNB_CHECK_ARG(x && y, "nlc_to_ncl: null pointer");
   if (B == 0 || C == 0 || T_ == 0) return 0;
-  dim3 grid(ceil_div(T_, 32), ceil_div(C, 32), B), block(32, 8);
+  dim3 grid(ceil_div(T_, 64), ceil_div(C, 64), B), block(256);
   cudaStream_t st = (cudaStream_t)stream;
   if (src_is_f32) {
     if (out_dtype == WNB200_F32) nlc_to_ncl_kernel<float, float><<<grid, block, 0, st>>>(C, T_, (const float*)x, (float*)y);

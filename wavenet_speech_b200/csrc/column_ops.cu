@@ -1,0 +1,512 @@
+// Channel-reduction kernels on NCL tensors -- channel softmax / log-softmax (wavenet.py:108-109), fused
+// log-softmax + NLL (legacy_code/train.py:36-39), LayerNorm (layernorm.py:25-28), per-frame argmax
+// (legacy_code/train.py:36) -- as TILED bandwidth kernels.
+//
+// A CTA stages one read's [C channels x TT frames] tile in shared memory with 16-byte coalesced loads (all of them
+// in flight at once), reduces every frame's column out of shared memory (TT columns x 256/TT partial reducers),
+// and streams the result back with 16-byte coalesced stores: each input byte is read from HBM once and each output
+// byte written once.  (The first version gave every (read, frame) column to one thread that walked the channels with
+// stride T, two or three times: 17-21 % of the copy bandwidth.)  TT is chosen so that the tile(s) fit in 64 KB; a
+// channel count too large for an 8-frame tile falls back to the per-column kernels in elementwise.cu.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace wnb {
+
+constexpr int CT_THREADS = 256;
+
+template <typename T>
+struct Vec16 {
+  static constexpr int N = 16 / sizeof(T);
+};
+
+// exp for the softmax family: exact expf for fp32 storage (parity 1e-5), ex2.approx for bf16 storage (4e-3 output ulp)
+template <typename T>
+__device__ __forceinline__ float exp_t(float x);
+template <>
+__device__ __forceinline__ float exp_t<float>(float x) { return expf(x); }
+template <>
+__device__ __forceinline__ float exp_t<__nv_bfloat16>(float x) { return __expf(x); }
+
+template <typename T>
+__device__ __forceinline__ float2 load2(const T* p);
+template <>
+__device__ __forceinline__ float2 load2<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
+template <>
+__device__ __forceinline__ float2 load2<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+
+// cooperative load of x[b, 0:C, t0:t0+TT] -> s[c * stride + tt]  (frames past Tn read as zero); four 16-byte loads in
+// flight per thread
+template <typename T>
+__device__ __forceinline__ void tile_load(T* s, int stride, const T* xb, int C, int Tn, int t0, int TT, bool vec) {
+  constexpr int V = Vec16<T>::N;
+  if (vec) {
+    const int nv = TT / V, total = C * nv;
+    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * CT_THREADS) {
+      uint4 val[4];
+      int off[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * CT_THREADS;
+        val[u] = make_uint4(0, 0, 0, 0);
+        off[u] = -1;
+        if (i < total) {
+          const int c = i / nv, v = i - c * nv, t = t0 + v * V;
+          off[u] = c * stride + v * V;
+          if (t + V <= Tn) val[u] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)c * Tn + t));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (off[u] >= 0) *reinterpret_cast<uint4*>(s + off[u]) = val[u];
+    }
+  } else {
+    for (int i = threadIdx.x; i < C * TT; i += CT_THREADS) {
+      const int c = i / TT, tt = i - c * TT;
+      s[c * stride + tt] = (t0 + tt < Tn) ? xb[(long long)c * Tn + t0 + tt] : from_f32<T>(0.f);
+    }
+  }
+}
+
+// cooperative store: y[b, c, t0 + tt] = f(c, tt), V consecutive frames per 16-byte store
+template <typename T, typename F>
+__device__ __forceinline__ void tile_store(T* yb, int C, int Tn, int t0, int TT, bool vec, F f) {
+  constexpr int V = Vec16<T>::N;
+  if (vec) {
+    const int nv = TT / V;
+    for (int i = threadIdx.x; i < C * nv; i += CT_THREADS) {
+      const int c = i / nv, v = i - c * nv, t = t0 + v * V;
+      if (t + V > Tn) continue;                 // Tn is a multiple of V on this path
+      uint4 val;
+      T* o = reinterpret_cast<T*>(&val);
+#pragma unroll
+      for (int k = 0; k < V; ++k) o[k] = from_f32<T>(f(c, v * V + k));
+      *reinterpret_cast<uint4*>(yb + (long long)c * Tn + t) = val;
+    }
+  } else {
+    for (int i = threadIdx.x; i < C * TT; i += CT_THREADS) {
+      const int c = i / TT, tt = i - c * TT;
+      if (t0 + tt < Tn) yb[(long long)c * Tn + t0 + tt] = from_f32<T>(f(c, tt));
+    }
+  }
+}
+
+struct TileGeom {
+  int TT, stride, nparts, tiles_per_read;      // nparts = 2 * CT_THREADS / TT partial reducers per frame PAIR
+};
+
+// thread -> (frame pair `pr` = frames 2pr, 2pr+1 ; part): every reducer walks channels part, part+nparts, ... with one
+// 4- or 8-byte shared load per channel for its two frames
+#define CT_PROLOGUE(NTILES)                                                                     \
+  extern __shared__ __align__(16) unsigned char ct_smem[];                                      \
+  const int b = blockIdx.x / g.tiles_per_read;                                                  \
+  const int t0 = (blockIdx.x - b * g.tiles_per_read) * g.TT;                                    \
+  const int TT = g.TT, stride = g.stride, nparts = g.nparts;                                    \
+  T* s0 = reinterpret_cast<T*>(ct_smem);                                                        \
+  T* s1 = s0 + (NTILES > 1 ? (size_t)C * stride : 0);                                           \
+  float* red = reinterpret_cast<float*>(ct_smem + (size_t)NTILES * C * stride * sizeof(T));     \
+  const int pr = threadIdx.x % (TT / 2), part = threadIdx.x / (TT / 2), f0 = 2 * pr;            \
+  const int tt = threadIdx.x;                  /* finalising thread of frame tt (tt < TT) */    \
+  const long long rb = (long long)b * C * Tn;                                                   \
+  (void)s1; (void)part; (void)nparts; (void)tt; (void)f0
+
+// red layout: K partial arrays [nparts][TT], then the per-frame finals
+template <typename T>
+__global__ void __launch_bounds__(CT_THREADS)
+softmax_fwd_tile(int C, int Tn, TileGeom g, bool vec, const T* x, T* y, int log_mode) {
+  CT_PROLOGUE(1);
+  tile_load(s0, stride, x + rb, C, Tn, t0, TT, vec);
+  __syncthreads();
+  float* fin = red + nparts * TT;              // [max | lse or 1/sum]
+  float m0 = -INFINITY, m1 = -INFINITY;
+  for (int c = part; c < C; c += nparts) {
+    const float2 v = load2<T>(s0 + c * stride + f0);
+    m0 = fmaxf(m0, v.x);
+    m1 = fmaxf(m1, v.y);
+  }
+  red[part * TT + f0] = m0;
+  red[part * TT + f0 + 1] = m1;
+  __syncthreads();
+  if (tt < TT) {
+    float M = -INFINITY;
+    for (int p = 0; p < nparts; ++p) M = fmaxf(M, red[p * TT + tt]);
+    fin[tt] = M;
+  }
+  __syncthreads();
+  m0 = fin[f0];
+  m1 = fin[f0 + 1];
+  float a0 = 0.f, a1 = 0.f;
+  for (int c = part; c < C; c += nparts) {
+    const float2 v = load2<T>(s0 + c * stride + f0);
+    a0 += exp_t<T>(v.x - m0);
+    a1 += exp_t<T>(v.y - m1);
+  }
+  red[part * TT + f0] = a0;
+  red[part * TT + f0 + 1] = a1;
+  __syncthreads();
+  if (tt < TT) {
+    float S = 0.f;
+    for (int p = 0; p < nparts; ++p) S += red[p * TT + tt];
+    fin[TT + tt] = log_mode ? fin[tt] + logf(S) : 1.f / S;
+  }
+  __syncthreads();
+  tile_store(y + rb, C, Tn, t0, TT, vec, [&](int c, int j) {
+    const float v = to_f32<T>(s0[c * stride + j]);
+    return log_mode ? v - fin[TT + j] : exp_t<T>(v - fin[j]) * fin[TT + j];
+  });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CT_THREADS)
+softmax_bwd_tile(int C, int Tn, TileGeom g, bool vec, const T* y, const T* dy, T* dx, int log_mode) {
+  CT_PROLOGUE(2);
+  tile_load(s0, stride, y + rb, C, Tn, t0, TT, vec);
+  tile_load(s1, stride, dy + rb, C, Tn, t0, TT, vec);
+  __syncthreads();
+  float d0 = 0.f, d1 = 0.f;
+  for (int c = part; c < C; c += nparts) {
+    const float2 gq = load2<T>(s1 + c * stride + f0);
+    if (log_mode) { d0 += gq.x; d1 += gq.y; }
+    else {
+      const float2 yy = load2<T>(s0 + c * stride + f0);
+      d0 += gq.x * yy.x;
+      d1 += gq.y * yy.y;
+    }
+  }
+  float* fin = red + nparts * TT;
+  red[part * TT + f0] = d0;
+  red[part * TT + f0 + 1] = d1;
+  __syncthreads();
+  if (tt < TT) {
+    float d = 0.f;
+    for (int p = 0; p < nparts; ++p) d += red[p * TT + tt];
+    fin[tt] = d;
+  }
+  __syncthreads();
+  tile_store(dx + rb, C, Tn, t0, TT, vec, [&](int c, int j) {
+    const float gq = to_f32<T>(s1[c * stride + j]), yy = to_f32<T>(s0[c * stride + j]);
+    return log_mode ? gq - exp_t<T>(yy) * fin[j] : yy * (gq - fin[j]);
+  });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CT_THREADS)
+xent_fwd_tile(int C, int Tn, TileGeom g, bool vec, const T* x, const long long* target, float* loss_bt,
+              float* lse_out) {
+  CT_PROLOGUE(1);
+  tile_load(s0, stride, x + rb, C, Tn, t0, TT, vec);
+  __syncthreads();
+  float* fin = red + nparts * TT;
+  float m0 = -INFINITY, m1 = -INFINITY;
+  for (int c = part; c < C; c += nparts) {
+    const float2 v = load2<T>(s0 + c * stride + f0);
+    m0 = fmaxf(m0, v.x);
+    m1 = fmaxf(m1, v.y);
+  }
+  red[part * TT + f0] = m0;
+  red[part * TT + f0 + 1] = m1;
+  __syncthreads();
+  if (tt < TT) {
+    float M = -INFINITY;
+    for (int p = 0; p < nparts; ++p) M = fmaxf(M, red[p * TT + tt]);
+    fin[tt] = M;
+  }
+  __syncthreads();
+  m0 = fin[f0];
+  m1 = fin[f0 + 1];
+  float a0 = 0.f, a1 = 0.f;
+  for (int c = part; c < C; c += nparts) {
+    const float2 v = load2<T>(s0 + c * stride + f0);
+    a0 += exp_t<T>(v.x - m0);
+    a1 += exp_t<T>(v.y - m1);
+  }
+  red[part * TT + f0] = a0;
+  red[part * TT + f0 + 1] = a1;
+  __syncthreads();
+  if (tt < TT && t0 + tt < Tn) {
+    float S = 0.f;
+    for (int p = 0; p < nparts; ++p) S += red[p * TT + tt];
+    const float lse = fin[tt] + logf(S);
+    const long long col = (long long)b * Tn + t0 + tt;
+    long long tg = target[col];
+    tg = tg < 0 ? 0 : (tg >= C ? C - 1 : tg);
+    loss_bt[col] = lse - to_f32<T>(s0[(int)tg * stride + tt]);
+    lse_out[col] = lse;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CT_THREADS)
+xent_bwd_tile(int C, int Tn, TileGeom g, bool vec, const T* x, const long long* target, const float* lse,
+              const float* gscale, T* dx) {
+  CT_PROLOGUE(1);
+  tile_load(s0, stride, x + rb, C, Tn, t0, TT, vec);
+  int* tgs = reinterpret_cast<int*>(red + TT);
+  if (tt < TT) {
+    const bool ok = t0 + tt < Tn;
+    const long long col = (long long)b * Tn + t0 + tt;
+    red[tt] = ok ? lse[col] : 0.f;
+    tgs[tt] = ok ? (int)target[col] : -1;
+  }
+  __syncthreads();
+  const float gs = *gscale;
+  tile_store(dx + rb, C, Tn, t0, TT, vec, [&](int c, int j) {
+    const float p = exp_t<T>(to_f32<T>(s0[c * stride + j]) - red[j]);
+    return (p - (c == tgs[j] ? 1.f : 0.f)) * gs;
+  });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CT_THREADS)
+layernorm_fwd_tile(int C, int Tn, TileGeom g, bool vec, const T* x, const float* gamma, const float* beta, float eps,
+                   T* y, float* stats) {
+  CT_PROLOGUE(1);
+  tile_load(s0, stride, x + rb, C, Tn, t0, TT, vec);
+  __syncthreads();
+  float* fin = red + nparts * TT;              // [mean | r]
+  float a0 = 0.f, a1 = 0.f;
+  for (int c = part; c < C; c += nparts) {
+    const float2 v = load2<T>(s0 + c * stride + f0);
+    a0 += v.x;
+    a1 += v.y;
+  }
+  red[part * TT + f0] = a0;
+  red[part * TT + f0 + 1] = a1;
+  __syncthreads();
+  if (tt < TT) {
+    float sm = 0.f;
+    for (int p = 0; p < nparts; ++p) sm += red[p * TT + tt];
+    fin[tt] = sm / (float)C;
+  }
+  __syncthreads();
+  const float mean0 = fin[f0], mean1 = fin[f0 + 1];
+  a0 = a1 = 0.f;
+  for (int c = part; c < C; c += nparts) {
+    const float2 v = load2<T>(s0 + c * stride + f0);
+    a0 += (v.x - mean0) * (v.x - mean0);
+    a1 += (v.y - mean1) * (v.y - mean1);
+  }
+  red[part * TT + f0] = a0;
+  red[part * TT + f0 + 1] = a1;
+  __syncthreads();
+  if (tt < TT) {
+    float var = 0.f;
+    for (int p = 0; p < nparts; ++p) var += red[p * TT + tt];
+    const float r = 1.f / (sqrtf(var / (float)(C - 1)) + eps);     // unbiased std, eps on the std (layernorm.py:27)
+    fin[TT + tt] = r;
+    if (stats && t0 + tt < Tn) {
+      const long long col = (long long)b * Tn + t0 + tt;
+      stats[col * 2] = fin[tt];
+      stats[col * 2 + 1] = r;
+    }
+  }
+  __syncthreads();
+  tile_store(y + rb, C, Tn, t0, TT, vec, [&](int c, int j) {
+    return gamma[c] * (to_f32<T>(s0[c * stride + j]) - fin[j]) * fin[TT + j] + beta[c];
+  });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CT_THREADS)
+layernorm_bwd_tile(int C, int Tn, TileGeom g, bool vec, const T* x, const float* gamma, const float* stats, float eps,
+                   const T* dy, T* dx) {
+  CT_PROLOGUE(2);
+  tile_load(s0, stride, x + rb, C, Tn, t0, TT, vec);
+  tile_load(s1, stride, dy + rb, C, Tn, t0, TT, vec);
+  float* fin = red + 2 * nparts * TT;           // [mean | r | k | mu]
+  if (tt < TT) {
+    const bool ok = t0 + tt < Tn;
+    const long long col = (long long)b * Tn + t0 + tt;
+    fin[tt] = ok ? stats[col * 2] : 0.f;
+    fin[TT + tt] = ok ? stats[col * 2 + 1] : 1.f;
+  }
+  __syncthreads();
+  const float mean0 = fin[f0], mean1 = fin[f0 + 1];
+  float p0 = 0.f, p1 = 0.f, q0 = 0.f, q1 = 0.f;       // sum(g), sum(g * xc),  g = dy * gamma
+  for (int c = part; c < C; c += nparts) {
+    const float gm = gamma[c];
+    const float2 gq = load2<T>(s1 + c * stride + f0), v = load2<T>(s0 + c * stride + f0);
+    p0 += gq.x * gm;
+    p1 += gq.y * gm;
+    q0 += gq.x * gm * (v.x - mean0);
+    q1 += gq.y * gm * (v.y - mean1);
+  }
+  red[part * TT + f0] = p0;
+  red[part * TT + f0 + 1] = p1;
+  red[(nparts + part) * TT + f0] = q0;
+  red[(nparts + part) * TT + f0 + 1] = q1;
+  __syncthreads();
+  if (tt < TT) {
+    float a1 = 0.f, a2 = 0.f;
+    for (int p = 0; p < nparts; ++p) { a1 += red[p * TT + tt]; a2 += red[(nparts + p) * TT + tt]; }
+    const float r = fin[TT + tt];
+    const float sd = 1.f / r - eps;
+    fin[2 * TT + tt] = (sd > 0.f) ? (-r * r * a2 / ((float)(C - 1) * sd)) : 0.f;
+    fin[3 * TT + tt] = r * a1 / (float)C;
+  }
+  __syncthreads();
+  tile_store(dx + rb, C, Tn, t0, TT, vec, [&](int c, int j) {
+    const float gq = to_f32<T>(s1[c * stride + j]) * gamma[c];
+    const float xc = to_f32<T>(s0[c * stride + j]) - fin[j];
+    return gq * fin[TT + j] + fin[2 * TT + j] * xc - fin[3 * TT + j];
+  });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CT_THREADS)
+argmax_tile(int C, int Tn, TileGeom g, bool vec, const T* x, long long* out) {
+  CT_PROLOGUE(1);
+  tile_load(s0, stride, x + rb, C, Tn, t0, TT, vec);
+  __syncthreads();
+  float m0 = -INFINITY, m1 = -INFINITY;
+  int g0 = C, g1 = C;                            // ascending c within a part: strict > keeps the lowest index
+  for (int c = part; c < C; c += nparts) {
+    const float2 v = load2<T>(s0 + c * stride + f0);
+    if (v.x > m0 || g0 == C) { m0 = v.x; g0 = c; }
+    if (v.y > m1 || g1 == C) { m1 = v.y; g1 = c; }
+  }
+  int* args = reinterpret_cast<int*>(red + nparts * TT);
+  red[part * TT + f0] = m0;
+  red[part * TT + f0 + 1] = m1;
+  args[part * TT + f0] = g0;
+  args[part * TT + f0 + 1] = g1;
+  __syncthreads();
+  if (tt < TT && t0 + tt < Tn) {
+    float M = red[tt];
+    int A = args[tt];
+    for (int p = 1; p < nparts; ++p) {
+      const float v = red[p * TT + tt];
+      const int a = args[p * TT + tt];
+      if (a < C && (A == C || v > M || (v == M && a < A))) { M = v; A = a; }
+    }
+    out[(long long)b * Tn + t0 + tt] = A;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+// largest TT in {256 .. 8} such that ntiles tiles of [C x (TT + pad)] elements + scratch fit in `budget` bytes
+static bool pick_geom(int C, int Tn, int esize, int ntiles, TileGeom* g, size_t* smem) {
+  const int V = 16 / esize;
+  for (int TT = 256; TT >= 8; TT >>= 1) {
+    if (TT > 8 && TT / 2 >= Tn) continue;                       // do not over-tile short reads
+    const int stride = TT + V;
+    const int nparts = 2 * CT_THREADS / TT;
+    const size_t bytes = (size_t)ntiles * C * stride * esize + sizeof(float) * (size_t)((2 * nparts + 4) * TT);
+    if (bytes <= 64 * 1024 || (TT == 8 && bytes <= 200 * 1024)) {
+      g->TT = TT; g->stride = stride; g->nparts = nparts;
+      g->tiles_per_read = (Tn + TT - 1) / TT;
+      *smem = bytes;
+      return true;
+    }
+  }
+  return false;
+}
+
+static inline bool vec_ok(const void* p0, const void* p1, const void* p2, int Tn, int esize) {
+  auto al = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return ((long long)Tn * esize) % 16 == 0 && al(p0) && al(p1) && al(p2);
+}
+
+}  // namespace wnb
+
+using namespace wnb;
+typedef __nv_bfloat16 bf16;
+
+// fallbacks (per-column kernels, elementwise.cu) for channel counts whose 8-frame tile does not fit in shared memory
+extern "C" int wnb200_softmax_fwd_col(int, int, int, int, const void*, void*, int, void*);
+extern "C" int wnb200_softmax_bwd_col(int, int, int, int, const void*, const void*, void*, int, void*);
+extern "C" int wnb200_xent_fwd_col(int, int, int, int, const void*, const int64_t*, float*, float*, void*);
+extern "C" int wnb200_xent_bwd_col(int, int, int, int, const void*, const int64_t*, const float*, const float*, void*,
+                                   void*);
+extern "C" int wnb200_layernorm_fwd_col(int, int, int, int, const void*, const float*, const float*, float, void*,
+                                        float*, void*);
+extern "C" int wnb200_layernorm_bwd_col(int, int, int, int, const void*, const float*, const float*, float,
+                                        const void*, void*, void*);
+extern "C" int wnb200_argmax_channels_col(int, int, int, int, const void*, int64_t*, void*);
+
+#define CT_LAUNCH(KERNEL, NTILES, P0, P1, P2, FALLBACK, ...)                                               \
+  do {                                                                                                     \
+    const int esize = dtype == WNB200_F32 ? 4 : 2;                                                         \
+    TileGeom g;                                                                                            \
+    size_t smem;                                                                                           \
+    if (dtype != WNB200_F32 && dtype != WNB200_BF16) { set_error(#KERNEL ": bad dtype %d", dtype); return 1; } \
+    if (!pick_geom(C, T_, esize, NTILES, &g, &smem)) return FALLBACK;                                      \
+    const bool vec = vec_ok(P0, P1, P2, T_, esize);                                                        \
+    const unsigned grid = (unsigned)((long long)B * g.tiles_per_read);                                     \
+    cudaStream_t st = (cudaStream_t)stream;                                                                \
+    if (dtype == WNB200_F32) {                                                                             \
+      using T = float;                                                                                     \
+      if (smem > 48 * 1024)                                                                                \
+        WNB_CUDA_OK(cudaFuncSetAttribute(KERNEL<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      KERNEL<T><<<grid, CT_THREADS, smem, st>>>(C, T_, g, vec, __VA_ARGS__);                                \
+    } else {                                                                                               \
+      using T = bf16;                                                                                      \
+      if (smem > 48 * 1024)                                                                                \
+        WNB_CUDA_OK(cudaFuncSetAttribute(KERNEL<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      KERNEL<T><<<grid, CT_THREADS, smem, st>>>(C, T_, g, vec, __VA_ARGS__);                                \
+    }                                                                                                      \
+    WNB_LAUNCH_OK();                                                                                       \
+    return 0;                                                                                              \
+  } while (0)
+
+extern "C" int wnb200_softmax_fwd(int dtype, int B, int C, int T_, const void* x, void* y, int log_mode,
+                                  void* stream) {
+  WNB_CHECK_ARG(x && y && C >= 1, "softmax_fwd: bad args");
+  if ((long long)B * T_ == 0) return 0;
+  CT_LAUNCH(softmax_fwd_tile, 1, x, y, nullptr, wnb200_softmax_fwd_col(dtype, B, C, T_, x, y, log_mode, stream),
+            (const T*)x, (T*)y, log_mode);
+}
+
+extern "C" int wnb200_softmax_bwd(int dtype, int B, int C, int T_, const void* y, const void* dy, void* dx,
+                                  int log_mode, void* stream) {
+  WNB_CHECK_ARG(y && dy && dx, "softmax_bwd: null pointer");
+  if ((long long)B * T_ == 0) return 0;
+  CT_LAUNCH(softmax_bwd_tile, 2, y, dy, dx, wnb200_softmax_bwd_col(dtype, B, C, T_, y, dy, dx, log_mode, stream),
+            (const T*)y, (const T*)dy, (T*)dx, log_mode);
+}
+
+extern "C" int wnb200_xent_fwd(int dtype, int B, int C, int T_, const void* logits, const int64_t* target,
+                               float* loss_bt, float* lse, void* stream) {
+  WNB_CHECK_ARG(logits && target && loss_bt && lse, "xent_fwd: null pointer");
+  if ((long long)B * T_ == 0) return 0;
+  CT_LAUNCH(xent_fwd_tile, 1, logits, nullptr, nullptr,
+            wnb200_xent_fwd_col(dtype, B, C, T_, logits, target, loss_bt, lse, stream), (const T*)logits,
+            (const long long*)target, loss_bt, lse);
+}
+
+extern "C" int wnb200_xent_bwd(int dtype, int B, int C, int T_, const void* logits, const int64_t* target,
+                               const float* lse, const float* gscale, void* dlogits, void* stream) {
+  WNB_CHECK_ARG(logits && target && lse && gscale && dlogits, "xent_bwd: null pointer");
+  if ((long long)B * T_ == 0) return 0;
+  CT_LAUNCH(xent_bwd_tile, 1, logits, dlogits, nullptr,
+            wnb200_xent_bwd_col(dtype, B, C, T_, logits, target, lse, gscale, dlogits, stream), (const T*)logits,
+            (const long long*)target, lse, gscale, (T*)dlogits);
+}
+
+extern "C" int wnb200_layernorm_fwd(int dtype, int B, int C, int T_, const void* x, const float* gamma,
+                                    const float* beta, float eps, void* y, float* stats, void* stream) {
+  WNB_CHECK_ARG(x && y && gamma && beta && C >= 2, "layernorm_fwd: bad args");
+  if ((long long)B * T_ == 0) return 0;
+  CT_LAUNCH(layernorm_fwd_tile, 1, x, y, nullptr,
+            wnb200_layernorm_fwd_col(dtype, B, C, T_, x, gamma, beta, eps, y, stats, stream), (const T*)x, gamma, beta,
+            eps, (T*)y, stats);
+}
+
+extern "C" int wnb200_layernorm_bwd(int dtype, int B, int C, int T_, const void* x, const float* gamma,
+                                    const float* stats, float eps, const void* dy, void* dx, void* stream) {
+  WNB_CHECK_ARG(x && gamma && stats && dy && dx, "layernorm_bwd: null pointer");
+  if ((long long)B * T_ == 0) return 0;
+  CT_LAUNCH(layernorm_bwd_tile, 2, x, dy, dx,
+            wnb200_layernorm_bwd_col(dtype, B, C, T_, x, gamma, stats, eps, dy, dx, stream), (const T*)x, gamma, stats,
+            eps, (const T*)dy, (T*)dx);
+}
+
+extern "C" int wnb200_argmax_channels(int dtype, int B, int C, int T_, const void* x, int64_t* out, void* stream) {
+  WNB_CHECK_ARG(x && out && C >= 1, "argmax_channels: bad args");
+  if ((long long)B * T_ == 0) return 0;
+  CT_LAUNCH(argmax_tile, 1, x, nullptr, nullptr, wnb200_argmax_channels_col(dtype, B, C, T_, x, out, stream),
+            (const T*)x, (long long*)out);
+}

@@ -328,36 +328,58 @@ __global__ void __launch_bounds__(256) ncl_to_nlc_v2_kernel(int C, int Tn, const
 // RawCTCNet featuriser, first layer (raw_ctcnet.py:57-59): Conv1d(1, F, fk, padding=fk-1) + LeakyReLU on the raw
 // 1-channel signal, written as NLC bf16 [B, T+fk-1, F].  Bandwidth kernel: 4 B read, 2F B written per frame.
 // Block = 32 frames x F channels; thread = 8 consecutive channels of one frame -> 16-byte coalesced stores.
-template <typename T>
+// A thread owns 8 consecutive channels for the whole block (its fk x 8 weights and 8 biases live in registers when
+// fk <= 4), the F/8 threads of a frame sit side by side (a warp writes whole 512-byte rows at F = 256), and a block
+// walks FEAT_FRAMES frames so that the per-block set-up (weights, signal window) is amortised.
+constexpr int FEAT_FRAMES = 512;
+template <typename T, int FKR>      // FKR = fk when the weights fit in registers (1..4), 0 = weights read from smem
 __global__ void __launch_bounds__(256) featurize_nlc_kernel(int Tn, int F, int fk, const T* x, const float* w,
                                                             const float* bias, bf16* y) {
-  extern __shared__ float fsm[];            // [fk][F] weights (tap-major), [F] bias, [32 + fk] signal window
+  extern __shared__ float fsm[];            // [fk][F] weights (tap-major), [FEAT_FRAMES + fk] signal window
   float* ws = fsm;
-  float* bs = fsm + fk * F;
-  float* xs = bs + F;
-  const int b = blockIdx.y, t0 = blockIdx.x * 32, To = Tn + fk - 1;
-  for (int i = threadIdx.x; i < fk * F; i += blockDim.x) {
-    const int j = i / F, f = i - j * F;
-    ws[i] = w[f * fk + j];
-  }
-  for (int i = threadIdx.x; i < F; i += blockDim.x) bs[i] = bias[i];
-  for (int i = threadIdx.x; i < 32 + fk - 1; i += blockDim.x) {
+  float* xs = fsm + fk * F;
+  const int b = blockIdx.y, t0 = blockIdx.x * FEAT_FRAMES, To = Tn + fk - 1;
+  if (FKR == 0)
+    for (int i = threadIdx.x; i < fk * F; i += blockDim.x) {
+      const int j = i / F, f = i - j * F;
+      ws[i] = w[f * fk + j];
+    }
+  for (int i = threadIdx.x; i < FEAT_FRAMES + fk - 1; i += blockDim.x) {
     const int t = t0 + i - (fk - 1);
     xs[i] = (t >= 0 && t < Tn) ? to_f32<T>(x[(long long)b * Tn + t]) : 0.f;
   }
+  const int groups = F / 8, rows = 256 / groups;          // rows of frames per pass (groups <= 256)
+  const int gq = threadIdx.x % groups, rl = threadIdx.x / groups, f0 = gq * 8;
+  float wr[(FKR > 0 ? FKR : 1) * 8], br[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) br[k] = bias[f0 + k];
+  if (FKR > 0) {
+#pragma unroll
+    for (int j = 0; j < FKR; ++j)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) wr[j * 8 + k] = w[(f0 + k) * FKR + j];
+  }
   __syncthreads();
-  const int groups = F / 8;
-  for (int i = threadIdx.x; i < 32 * groups; i += blockDim.x) {
-    const int tl = i / groups, f0 = (i - tl * groups) * 8;
+  if (rl >= rows) return;
+  for (int tl = rl; tl < FEAT_FRAMES; tl += rows) {
     const int t = t0 + tl;
-    if (t >= To) continue;
+    if (t >= To) break;
     float acc[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = bs[f0 + k];
-    for (int j = 0; j < fk; ++j) {
-      const float xv = xs[tl + j];
+    for (int k = 0; k < 8; ++k) acc[k] = br[k];
+    if (FKR > 0) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] = fmaf(ws[j * F + f0 + k], xv, acc[k]);
+      for (int j = 0; j < FKR; ++j) {
+        const float xv = xs[tl + j];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(wr[j * 8 + k], xv, acc[k]);
+      }
+    } else {
+      for (int j = 0; j < fk; ++j) {
+        const float xv = xs[tl + j];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(ws[j * F + f0 + k], xv, acc[k]);
+      }
     }
     uint4 o;
     o.x = pack_bf16x2(leaky(acc[0]), leaky(acc[1]));
@@ -473,14 +495,23 @@ extern "C" int wnb200_featurize_nlc(int dtype, int B, int T_, int F, int fk, con
   WNB_CHECK_ARG(x && w && bias && y, "featurize_nlc: null pointer");
   WNB_CHECK_ARG(B <= 65535, "featurize_nlc: batch too large");
   const int To = T_ + fk - 1;
-  const size_t smem = sizeof(float) * ((size_t)fk * F + F + 32 + fk);
+  WNB_CHECK_ARG(F <= 2048, "featurize_nlc: F=%d too large", F);
+  const size_t smem = sizeof(float) * ((size_t)fk * F + FEAT_FRAMES + fk);
   WNB_CHECK_ARG(smem <= 48 * 1024, "featurize_nlc: fk*F too large for the weight cache");
-  dim3 grid(ceil_div(To, 32), B);
+  dim3 grid(ceil_div(To, FEAT_FRAMES), B);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == WNB200_F32)
-    featurize_nlc_kernel<float><<<grid, 256, smem, st>>>(T_, F, fk, (const float*)x, w, bias, (bf16*)y);
-  else
-    featurize_nlc_kernel<bf16><<<grid, 256, smem, st>>>(T_, F, fk, (const bf16*)x, w, bias, (bf16*)y);
+#define FEAT_LAUNCH(TT, FKR) featurize_nlc_kernel<TT, FKR><<<grid, 256, smem, st>>>(T_, F, fk, (const TT*)x, w, bias, (bf16*)y)
+#define FEAT_DISPATCH(TT)                         \
+  switch (fk) {                                   \
+    case 1: FEAT_LAUNCH(TT, 1); break;            \
+    case 2: FEAT_LAUNCH(TT, 2); break;            \
+    case 3: FEAT_LAUNCH(TT, 3); break;            \
+    case 4: FEAT_LAUNCH(TT, 4); break;            \
+    default: FEAT_LAUNCH(TT, 0); break;           \
+  }
+  if (dtype == WNB200_F32) { FEAT_DISPATCH(float) } else { FEAT_DISPATCH(bf16) }
+#undef FEAT_DISPATCH
+#undef FEAT_LAUNCH
   WNB_LAUNCH_OK();
   return 0;
 }

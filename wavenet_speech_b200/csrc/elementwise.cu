@@ -1,8 +1,7 @@
-// Bandwidth-bound kernels of the hot path (NCL layout): gate backward, LeakyReLU backward,
-// channel softmax / log-softmax (+ fused NLL), mean-pool, LayerNorm, position mixing, argmax.
-// One thread per (batch, frame) column for the channel reductions: consecutive threads read
-// consecutive frames, so every global access is coalesced and no transposing copies
-// (reshape_in / reshape_out, reference conv_ops.py:91-101) are ever materialised.
+// Bandwidth-bound kernels of the hot path (NCL layout): gate backward, LeakyReLU backward, mean-pool, position
+// mixing, column sums; plus the per-column fallbacks (`*_col`: one thread per (batch, frame) column) of the tiled
+// channel-reduction kernels in column_ops.cu, used only when a channel count is too large for a shared-memory tile.
+// No transposing copies (reshape_in / reshape_out, reference conv_ops.py:91-101) are ever materialised.
 #include "common.cuh"
 
 namespace wnb {
@@ -69,6 +68,25 @@ __global__ void leaky_bwd_kernel(long long n, const T* dy, const T* ref, T* dx) 
        i += (long long)gridDim.x * blockDim.x) {
     const float g = to_f32<T>(dy[i]);
     dx[i] = from_f32<T>(to_f32<T>(ref[i]) > 0.f ? g : 0.01f * g);
+  }
+}
+
+// 16 bytes per thread per tensor (the scalar kernel above handles the tail / unaligned buffers)
+template <typename T>
+__global__ void leaky_bwd_vec_kernel(long long nv, const uint4* dy, const uint4* ref, uint4* dx) {
+  constexpr int V = 16 / sizeof(T);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 g4 = __ldg(dy + i), r4 = __ldg(ref + i);
+    uint4 o4;
+    const T* g = reinterpret_cast<const T*>(&g4);
+    const T* r = reinterpret_cast<const T*>(&r4);
+    T* o = reinterpret_cast<T*>(&o4);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float gv = to_f32<T>(g[k]);
+      o[k] = from_f32<T>(to_f32<T>(r[k]) > 0.f ? gv : 0.01f * gv);
+    }
+    dx[i] = o4;
   }
 }
 
@@ -393,12 +411,19 @@ extern "C" int wnb200_leaky_bwd(int dtype, int64_t n, const void* dy, const void
   WNB_CHECK_ARG(dy && ref && dx, "leaky_bwd: null pointer");
   if (n == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  DISPATCH(dtype, "leaky_bwd", (leaky_bwd_kernel<T><<<grid_for(n), 256, 0, st>>>(n, (const T*)dy, (const T*)ref, (T*)dx)));
+  const bool aligned = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(ref) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+  const int V = dtype == WNB200_F32 ? 4 : 8;
+  const long long nv = aligned ? n / V : 0, done = nv * V;
+  if (nv > 0)
+    DISPATCH(dtype, "leaky_bwd", (leaky_bwd_vec_kernel<T><<<grid_for(nv), 256, 0, st>>>(nv, (const uint4*)dy, (const uint4*)ref, (uint4*)dx)));
+  if (done < n)
+    DISPATCH(dtype, "leaky_bwd", (leaky_bwd_kernel<T><<<grid_for(n - done), 256, 0, st>>>(
+                                      n - done, (const T*)dy + done, (const T*)ref + done, (T*)dx + done)));
   WNB_LAUNCH_OK();
   return 0;
 }
 
-extern "C" int wnb200_softmax_fwd(int dtype, int B, int C, int T_, const void* x, void* y, int log_mode,
+extern "C" int wnb200_softmax_fwd_col(int dtype, int B, int C, int T_, const void* x, void* y, int log_mode,
                                   void* stream) {
   WNB_CHECK_ARG(x && y && C >= 1, "softmax_fwd: bad args");
   const long long cols = (long long)B * T_;
@@ -410,7 +435,7 @@ extern "C" int wnb200_softmax_fwd(int dtype, int B, int C, int T_, const void* x
   return 0;
 }
 
-extern "C" int wnb200_softmax_bwd(int dtype, int B, int C, int T_, const void* y, const void* dy, void* dx,
+extern "C" int wnb200_softmax_bwd_col(int dtype, int B, int C, int T_, const void* y, const void* dy, void* dx,
                                   int log_mode, void* stream) {
   WNB_CHECK_ARG(y && dy && dx, "softmax_bwd: null pointer");
   const long long cols = (long long)B * T_;
@@ -422,7 +447,7 @@ extern "C" int wnb200_softmax_bwd(int dtype, int B, int C, int T_, const void* y
   return 0;
 }
 
-extern "C" int wnb200_xent_fwd(int dtype, int B, int C, int T_, const void* logits, const int64_t* target,
+extern "C" int wnb200_xent_fwd_col(int dtype, int B, int C, int T_, const void* logits, const int64_t* target,
                                float* loss_bt, float* lse, void* stream) {
   WNB_CHECK_ARG(logits && target && loss_bt && lse, "xent_fwd: null pointer");
   const long long cols = (long long)B * T_;
@@ -434,7 +459,7 @@ extern "C" int wnb200_xent_fwd(int dtype, int B, int C, int T_, const void* logi
   return 0;
 }
 
-extern "C" int wnb200_xent_bwd(int dtype, int B, int C, int T_, const void* logits, const int64_t* target,
+extern "C" int wnb200_xent_bwd_col(int dtype, int B, int C, int T_, const void* logits, const int64_t* target,
                                const float* lse, const float* gscale, void* dlogits, void* stream) {
   WNB_CHECK_ARG(logits && target && lse && gscale && dlogits, "xent_bwd: null pointer");
   const long long cols = (long long)B * T_;
@@ -481,7 +506,7 @@ extern "C" int wnb200_avgpool_bwd(int dtype, int B, int C, int T_, int pool, con
   return 0;
 }
 
-extern "C" int wnb200_layernorm_fwd(int dtype, int B, int C, int T_, const void* x, const float* gamma,
+extern "C" int wnb200_layernorm_fwd_col(int dtype, int B, int C, int T_, const void* x, const float* gamma,
                                     const float* beta, float eps, void* y, float* stats, void* stream) {
   WNB_CHECK_ARG(x && y && gamma && beta && C >= 2, "layernorm_fwd: bad args");
   const long long cols = (long long)B * T_;
@@ -493,7 +518,7 @@ extern "C" int wnb200_layernorm_fwd(int dtype, int B, int C, int T_, const void*
   return 0;
 }
 
-extern "C" int wnb200_layernorm_bwd(int dtype, int B, int C, int T_, const void* x, const float* gamma,
+extern "C" int wnb200_layernorm_bwd_col(int dtype, int B, int C, int T_, const void* x, const float* gamma,
                                     const float* stats, float eps, const void* dy, void* dx, void* stream) {
   WNB_CHECK_ARG(x && gamma && stats && dy && dx, "layernorm_bwd: null pointer");
   const long long cols = (long long)B * T_;
@@ -516,7 +541,7 @@ extern "C" int wnb200_positions_add(int dtype, int B, int F, int T_, int t0, con
   return 0;
 }
 
-extern "C" int wnb200_argmax_channels(int dtype, int B, int C, int T_, const void* x, int64_t* out, void* stream) {
+extern "C" int wnb200_argmax_channels_col(int dtype, int B, int C, int T_, const void* x, int64_t* out, void* stream) {
   WNB_CHECK_ARG(x && out && C >= 1, "argmax_channels: bad args");
   const long long cols = (long long)B * T_;
   if (cols == 0) return 0;

@@ -10,8 +10,10 @@ from .conv_ops import CausalConv1d, NonCausalConv1d, autopad, compute_new_length
 from .layernorm import LayerNorm
 from .linear_conv_ops import LinearConv1d
 from .raw_ctcnet import RawCTCNet
+from .sequence_decoders import Decoder, argmax_decode, greedy_ctc_decode, labels2strings
 from .wavenet import WaveNet
 
 __all__ = ["CausalConv1d", "NonCausalConv1d", "ResidualBlock", "GatedActivationUnit", "MultiplicativeUnit",
            "ResidualMUBlock", "ResidualReLUBlock", "WaveNet", "RawCTCNet", "WaveNetClassifier", "LayerNorm",
-           "LinearConv1d", "autopad", "compute_new_length", "reshape_in", "reshape_out"]
+           "LinearConv1d", "autopad", "compute_new_length", "reshape_in", "reshape_out", "argmax_decode", "labels2strings",
+           "greedy_ctc_decode", "Decoder"]

@@ -269,3 +269,35 @@ def argmax_channels(x):
     out = torch.empty((B, T), dtype=torch.int64, device=x.device)
     _lib.call("wnb200_argmax_channels", _dt(x), B, C, T, _p(x), _p(out), _stream())
     return out
+
+
+def _bct_strides(x, layout):
+    """(B, L, T, sb, sc, st) of a 3-D activation tensor given as "bct" (network output), "btc" or "tbc"."""
+    ix = {"bct": (0, 1, 2), "btc": (0, 2, 1), "tbc": (1, 2, 0)}[layout]
+    return tuple(x.shape[i] for i in ix) + tuple(x.stride(i) for i in ix)
+
+
+def frame_argmax(x, layout="bct"):
+    """Per-frame argmax over the classes -> int64 (B, T); any of the three layouts is read in place."""
+    _need_cuda(x)
+    check_device()
+    B, L, T, sb, sc, st = _bct_strides(x, layout)
+    out = torch.empty((B, T), dtype=torch.int64, device=x.device)
+    _lib.call("wnb200_frame_argmax", _dt(x), B, L, T, _p(x), sb, sc, st, _p(out), _stream())
+    return out
+
+
+def ctc_greedy_decode(x, act_lengths=None, blank=0, layout="bct"):
+    """Argmax -> collapse repeats -> drop blanks, on the device.  Returns (labels int32 (B, T) with the decoded
+    sequence of read b in labels[b, :lengths[b]], lengths int32 (B,))."""
+    _need_cuda(x)
+    check_device()
+    B, L, T, sb, sc, st = _bct_strides(x, layout)
+    labels = torch.zeros((B, T), dtype=torch.int32, device=x.device)
+    lengths = torch.zeros((B,), dtype=torch.int32, device=x.device)
+    al = None
+    if act_lengths is not None:
+        al = torch.as_tensor(act_lengths, dtype=torch.int32).to(x.device).contiguous()
+    _lib.call("wnb200_ctc_greedy_decode", _dt(x), B, L, T, _p(x), sb, sc, st, _p(al), int(blank), _p(labels),
+              _p(lengths), _stream())
+    return labels, lengths

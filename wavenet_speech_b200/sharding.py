@@ -83,31 +83,35 @@ def time_shard_plan(T, rank, world, halo_left, halo_right, align=1):
     per = -(-T // world)
     per = -(-per // align) * align
     start, end = min(T, rank * per), min(T, (rank + 1) * per)
-    return {"start": start, "end": end, "lo": max(0, start - halo_left), "hi": min(T, end + halo_right)}
+    return {"start": start, "end": end, "lo": max(0, start - halo_left), "hi": min(T, end + halo_right),
+            "halo_left": halo_left, "halo_right": halo_right}
 
 
 def exchange_halo(x_shard, plan, rank, world, group=None):
     """x_shard holds frames [start, end) of a (B, C, T) tensor split along time.  Fetch the missing
-    [lo, start) from the left neighbour(s) and [end, hi) from the right one(s) with point-to-point sends;
-    returns the extended tensor for frames [lo, hi).  Halos are assumed not to span more than one neighbour."""
+    [lo, start) from the left neighbour and [end, hi) from the right one; returns the extended tensor for frames
+    [lo, hi).  All sends and receives of a rank go out as ONE batch (ncclGroupStart/End under NCCL: neighbour
+    exchanges posted one by one would deadlock on a single stream).  Halos must not span more than one neighbour."""
     import torch.distributed as dist
     need_l, need_r = plan["start"] - plan["lo"], plan["hi"] - plan["end"]
-    B, C, _ = x_shard.shape
+    hl, hr = plan["halo_left"], plan["halo_right"]
+    B, C, n = x_shard.shape
+    assert world == 1 or (hl <= n and hr <= n), "halo wider than a shard"
     left = x_shard.new_empty((B, C, need_l))
     right = x_shard.new_empty((B, C, need_r))
-    reqs = []
-    # what the neighbours need from me mirrors what I need from them (same halo widths everywhere)
+    ops = []
     if rank > 0 and need_l > 0:
-        reqs.append(dist.irecv(left, src=rank - 1, group=group))
+        ops.append(dist.P2POp(dist.irecv, left, rank - 1, group))
     if rank < world - 1 and need_r > 0:
-        reqs.append(dist.irecv(right, src=rank + 1, group=group))
-    hl, hr = plan.get("halo_left", need_l), plan.get("halo_right", need_r)
+        ops.append(dist.P2POp(dist.irecv, right, rank + 1, group))
+    # what the neighbours need from me mirrors what I need from them (same halo widths everywhere)
     if rank < world - 1 and hl > 0:
-        reqs.append(dist.isend(x_shard[:, :, -hl:].contiguous(), dst=rank + 1, group=group))
+        ops.append(dist.P2POp(dist.isend, x_shard[:, :, -hl:].contiguous(), rank + 1, group))
     if rank > 0 and hr > 0:
-        reqs.append(dist.isend(x_shard[:, :, :hr].contiguous(), dst=rank - 1, group=group))
-    for r in reqs:
-        r.wait()
+        ops.append(dist.P2POp(dist.isend, x_shard[:, :, :hr].contiguous(), rank - 1, group))
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
     return torch.cat([left, x_shard, right], 2)
 
 
