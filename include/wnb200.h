@@ -286,6 +286,12 @@ int wnb200_ctc_greedy_decode(int dtype, int B, int L, int T, const void* act, in
                              const int32_t* act_lengths, int blank, int32_t* out_labels, int32_t* out_lengths,
                              void* stream);
 
+/* Backward of the RawCTCNet featuriser's first layer (raw_ctcnet.py:57-59) on the tensor-core training path, one pass:
+ * df, fact: NLC bf16 [B, T+fk-1, F] (gradient w.r.t. the LeakyReLU output, and that output); seq [B, T] (seq_dtype);
+ * w fp32 [F, fk].  Accumulates dw fp32 [F, fk], db fp32 [F] and (if not NULL) dseq fp32 [B, T]; zero them first. */
+int wnb200_featurize_bwd_nlc(int seq_dtype, int B, int T, int F, int fk, const void* df, const void* fact,
+                             const void* seq, const float* w, float* dw, float* db, float* dseq, void* stream);
+
 /* y = bf16(LeakyReLU_0.01(x)), n a multiple of 4: turns the fp32 skip sum into the head's input
  * (first LeakyReLU of output_stack, wavenet.py:67). */
 int wnb200_leaky_to_bf16(int64_t n, const float* x, void* y, void* stream);

@@ -169,6 +169,51 @@ if "train_tc" in which:    # config 3 on the tensor-core path: bf16 operands, fp
                       "phases_ms": {k: round(v, 2) for k, v in ph.items()},
                       "kernels_ms": {k: [v[0], round(v[1], 3)] for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])}}))
 
+if "rawctc_train" in which:   # RawCTCNet CTC training step (legacy_code/run_raw_ctc.py:53-66) on the tensor-core path
+    from wavenet_speech_b200 import _lib
+    torch.manual_seed(0)
+    net = ecoli_net().cuda()
+    bn = torch.nn.BatchNorm1d(1).cuda()                     # run_raw_ctc.py:38,58 normalises the raw signal (outside the path)
+    opt = torch.optim.Adam(list(net.parameters()) + list(bn.parameters()), lr=1e-5, weight_decay=1e-4, fused=True)
+    B, T = int(opts.get("B", 128)), int(opts.get("T", 4000))
+    sigs, labels = [], []
+    rng = __import__("numpy").random.default_rng(9)
+    for _ in range(min(B, 16)):
+        sg_, lb_ = SG.raw_signal(T, rng, with_labels=True)
+        sigs.append(torch.from_numpy(sg_).float())
+        labels.append(torch.from_numpy(lb_))
+    rep = (B + 15) // 16
+    x = torch.stack(sigs).unsqueeze(1).repeat(rep, 1, 1)[:B].cuda()
+    labels = (labels * rep)[:B]
+    lengths = torch.tensor([len(l) for l in labels], dtype=torch.int32)
+    seq = torch.cat(labels).int().cuda()
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        trans = net(bn(x).bfloat16())
+        ctc = W.functional.ctc_loss_sum(trans, seq, lengths, layout="bct")
+        loss = ctc / trans.shape[2]
+        loss.backward()
+        opt.step()
+        return loss
+
+    l0 = float(step())
+    ms = timed(step, int(opts.get("steps", 5)), warmup=2)
+    l1 = float(step())
+    _lib.kernel_timing(True)
+    step()
+    torch.cuda.synchronize()
+    agg = {}
+    for name, e0, e1 in _lib.kernel_timing(False):
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += e0.elapsed_time(e1)
+    print(json.dumps({"config": "rawctcnet_ecoli_ctc_train_step_bf16_tensor_core", "batch": B, "T": T, "ms_per_step": ms,
+                      "samples_per_s": B * T / (ms * 1e-3), "tflops_as_written_3x_fwd": B * T / (ms * 1e-3) * 3 * 17043456 / 1e12,
+                      "loss_first": l0, "loss_after": l1, "labels_per_read": float(lengths.float().mean()),
+                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+                      "kernels_ms": {k: [v[0], round(v[1], 3)] for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])}}))
+
 if "longread" in which:    # config 5: 1M-sample read, time-sharded in 8 shards (emulated on one GPU) vs one pass
     net = ecoli_net().cuda().bfloat16().eval()
     T = 1000000

@@ -195,6 +195,35 @@ def test_classifier_train_tc():
     _compare(net, gref)
 
 
+@pytest.mark.parametrize("C,fk,T,B,causal,need_dx", [(128, 3, 300, 2, False, True), (256, 2, 700, 1, True, False),
+                                                       (128, 1, 520, 2, False, True)])
+def test_raw_ctcnet_train_tc(C, fk, T, B, causal, need_dx):
+    """RawCTCNet (featuriser + stack + head) training path: the caller of legacy_code/run_raw_ctc.py:53-66."""
+    torch.manual_seed(C + fk)
+    layers = [(C, C, 2, d) for d in (1, 2, 4)]
+    net = W.RawCTCNet(C, fk, 5, layers, C, softmax=False, causal=causal)
+    _perturb_biases(net)
+    sd = {k: r16(v) for k, v in net.state_dict().items()}
+    net.load_state_dict(sd)
+    x = r16(torch.randn(B, 1, T))
+    To = T + fk - 1
+    R = r16(torch.randn(B, 5, To))
+    fwd = lambda q: (lambda s, xx: O.raw_ctcnet_forward(s, xx, layers, softmax=False, causal=causal, q=q))
+    yref, _, _ = _oracle_grads(sd, fwd(None), x, R)
+    net = net.cuda()
+    xg = x.cuda().bfloat16().requires_grad_(need_dx)
+    y = net(xg)
+    assert y.shape == (B, 5, To) and y.grad_fn is not None
+    assert G.rel_linf(y.float().cpu(), yref) <= 2e-2
+    _seq, f, saved, skips_act, h1, _out = y.grad_fn.keep
+    _, gref, dxref = _oracle_grads(sd, fwd(_Stored([f, saved[0][0]] + _stored_stack(saved, skips_act, h1))), x, R)
+    (y.float() * R.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    if need_dx:
+        assert G.rel_linf(xg.grad.float().cpu(), dxref) <= TOL_LINF
+    _compare(net, gref)
+
+
 def test_train_step_tc_matches_oracle_step():
     """legacy_code/train.py:24-55 on the tensor-core path: joint loss and every gradient vs the oracle."""
     torch.manual_seed(3)

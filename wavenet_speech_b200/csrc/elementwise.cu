@@ -353,6 +353,90 @@ __global__ void __launch_bounds__(256) colsum_nlc_kernel(long long rows, int C, 
   }
 }
 
+// Backward of the RawCTCNet featuriser's first layer (raw_ctcnet.py:57-59: Conv1d(1, F, fk, padding=fk-1) + LeakyReLU)
+// in ONE pass over the NLC bf16 tensors: with dpre = df * LeakyReLU'(f),
+//   dw[f, j] += sum_{b,t'} dpre[b,t',f] * seq[b, t'+j-(fk-1)]      db[f] += sum dpre[b,t',f]
+//   dseq[b, t] += sum_j sum_f w[f, j] * dpre[b, t+(fk-1)-j, f]      (fp32, atomics; fk values per frame)
+// Thread = 8 channels of a frame (one 16-byte load per tensor), the F/8 threads of a frame sit side by side (a power
+// of two <= 32: the per-frame dot products over F are warp-shuffle reductions), a block walks FB_FRAMES frames of one
+// read with its fk x 8 weight-gradient accumulators in registers.
+constexpr int FB_FRAMES = 512;
+template <typename TS, int FK>
+__global__ void __launch_bounds__(256)
+featurize_bwd_nlc_kernel(int Tn, int F, const uint4* df, const uint4* fact, const TS* seq, const float* w, float* dw,
+                         float* db, float* dseq) {
+  __shared__ float xs[FB_FRAMES + FK];
+  __shared__ float red[256][FK * 8 + 9];
+  const int b = blockIdx.y, t0 = blockIdx.x * FB_FRAMES, To = Tn + FK - 1;
+  const int groups = F / 8, rows = 256 / groups;
+  const int gq = threadIdx.x % groups, rl = threadIdx.x / groups, f0 = gq * 8;
+  for (int i = threadIdx.x; i < FB_FRAMES + FK - 1; i += 256) {
+    const int t = t0 + i - (FK - 1);
+    xs[i] = (t >= 0 && t < Tn) ? to_f32<TS>(seq[(long long)b * Tn + t]) : 0.f;
+  }
+  float wr[FK * 8], acc[FK * 8], accb[8];
+#pragma unroll
+  for (int j = 0; j < FK; ++j)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { wr[j * 8 + k] = w[(f0 + k) * FK + j]; acc[j * 8 + k] = 0.f; }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) accb[k] = 0.f;
+  __syncthreads();
+  for (int tl = rl; tl < FB_FRAMES; tl += rows) {
+    const int t = t0 + tl;
+    const bool live = t < To;                  // no early exit: every lane takes part in the shuffles below
+    const long long o = ((long long)b * To + (live ? t : 0)) * groups + gq;
+    uint4 d4 = make_uint4(0, 0, 0, 0), f4 = d4;
+    if (live) { d4 = __ldg(df + o); f4 = __ldg(fact + o); }
+    const __nv_bfloat162* dp = reinterpret_cast<const __nv_bfloat162*>(&d4);
+    const __nv_bfloat162* fp = reinterpret_cast<const __nv_bfloat162*>(&f4);
+    float d[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 dv = __bfloat1622float2(dp[k]), fv = __bfloat1622float2(fp[k]);
+      d[2 * k] = fv.x > 0.f ? dv.x : 0.01f * dv.x;
+      d[2 * k + 1] = fv.y > 0.f ? dv.y : 0.01f * dv.y;
+    }
+    float pj[FK];
+#pragma unroll
+    for (int j = 0; j < FK; ++j) {
+      const float xv = xs[tl + j];
+      float p = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        acc[j * 8 + k] = fmaf(d[k], xv, acc[j * 8 + k]);
+        p = fmaf(wr[j * 8 + k], d[k], p);
+      }
+      pj[j] = p;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) accb[k] += d[k];
+    if (dseq) {
+#pragma unroll
+      for (int j = 0; j < FK; ++j) {
+        float p = pj[j];
+        for (int o2 = groups >> 1; o2 > 0; o2 >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o2);
+        const int ts = t + j - (FK - 1);
+        if (live && gq == 0 && ts >= 0 && ts < Tn) atomicAdd(&dseq[(long long)b * Tn + ts], p);
+      }
+    }
+  }
+  // block reduction over the row lanes, then one atomic per (channel, tap) per block
+#pragma unroll
+  for (int i = 0; i < FK * 8; ++i) red[threadIdx.x][i] = acc[i];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[threadIdx.x][FK * 8 + k] = accb[k];
+  __syncthreads();
+  for (int i = threadIdx.x; i < F * (FK + 1); i += 256) {
+    const int c = i / (FK + 1), j = i - c * (FK + 1);          // j == FK: bias
+    const int g2 = c >> 3, k = c & 7;
+    float tsum = 0.f;
+    for (int q = 0; q < rows; ++q) tsum += red[q * groups + g2][j * 8 + k];
+    if (j < FK) atomicAdd(&dw[c * FK + j], tsum);
+    else atomicAdd(&db[c], tsum);
+  }
+}
+
 static inline int grid_for(long long n, int block = 256) {
   long long g = (n + block - 1) / block;
   const long long cap = 148ll * 32;
@@ -571,6 +655,36 @@ extern "C" int wnb200_colsum_nlc(int64_t rows, int C, const void* x, float* out,
   long long grid = (rows + rpb - 1) / rpb;
   if (grid > 148 * 8) grid = 148 * 8;
   colsum_nlc_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(rows, C, (const uint4*)x, out);
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_featurize_bwd_nlc(int seq_dtype, int B, int T_, int F, int fk, const void* df, const void* fact,
+                                        const void* seq, const float* w, float* dw, float* db, float* dseq,
+                                        void* stream) {
+  WNB_CHECK_ARG(F >= 8 && F <= 256 && (F & (F - 1)) == 0, "featurize_bwd_nlc: F=%d must be a power of two in 8..256", F);
+  WNB_CHECK_ARG(fk >= 1 && fk <= 4, "featurize_bwd_nlc: fk=%d not in 1..4", fk);
+  if (B == 0 || T_ == 0) return 0;
+  WNB_CHECK_ARG(df && fact && seq && w && dw && db, "featurize_bwd_nlc: null pointer");
+  WNB_CHECK_ARG(B <= 65535, "featurize_bwd_nlc: batch too large");
+  const int To = T_ + fk - 1;
+  dim3 grid((To + FB_FRAMES - 1) / FB_FRAMES, B);
+  cudaStream_t st = (cudaStream_t)stream;
+#define FB_LAUNCH(TS, FK)                                                                                         \
+  featurize_bwd_nlc_kernel<TS, FK><<<grid, 256, 0, st>>>(T_, F, (const uint4*)df, (const uint4*)fact, (const TS*)seq, \
+                                                         w, dw, db, dseq)
+#define FB_DISPATCH(TS)                  \
+  switch (fk) {                          \
+    case 1: FB_LAUNCH(TS, 1); break;     \
+    case 2: FB_LAUNCH(TS, 2); break;     \
+    case 3: FB_LAUNCH(TS, 3); break;     \
+    default: FB_LAUNCH(TS, 4); break;    \
+  }
+  if (seq_dtype == WNB200_F32) { FB_DISPATCH(float) }
+  else if (seq_dtype == WNB200_BF16) { FB_DISPATCH(bf16) }
+  else { set_error("featurize_bwd_nlc: bad dtype %d", seq_dtype); return 1; }
+#undef FB_DISPATCH
+#undef FB_LAUNCH
   WNB_LAUNCH_OK();
   return 0;
 }

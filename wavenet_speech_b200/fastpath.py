@@ -298,7 +298,10 @@ def try_raw_ctcnet_forward(model, seq):
     if seq.dtype != torch.bfloat16 or not seq.is_cuda or seq.dim() != 3 or seq.shape[1] != 1:
         return None
     C, F = model.layers[0][0], model.num_features
-    if not (_no_graph(model, seq) and F == C and model.out_dim == C and C in (128, 256) and not model.positions
+    if not _no_graph(model, seq):
+        from . import training
+        return training.raw_ctcnet_forward_train(model, seq) if training.raw_ctcnet_train_eligible(model, seq) else None
+    if not (F == C and model.out_dim == C and C in (128, 256) and not model.positions
             and _stack_ok(C, model.layers) and model.input_kernel_size <= 3 and model.feature_kwidth * F <= 8192
             and seq.shape[0] > 0 and seq.shape[2] > 0):
         return None

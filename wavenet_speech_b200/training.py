@@ -347,3 +347,76 @@ def classifier_forward_train(model, seq):
     pk = FP._cached(model, "classifier_train", lambda: _classifier_pack(model))
     params = pk["stack"].params() + _head_params(model.output_block)
     return _ClassifierTrain.apply(model, pk, seq.contiguous(), *params)
+
+
+# --------------------------------------------------------------------------- RawCTCNet
+def _raw_ctcnet_pack(model):
+    C = model.layers[0][0]
+    f0, f2 = model.feature_layer[0], model.feature_layer[2]
+    w2 = f2.weight.detach().float()[:, :, 0]
+    return {"f0w": f0.weight.detach().float()[:, 0, :].contiguous(), "f0b": f0.bias.detach().float().contiguous(),
+            "f2w": FP._bf16(w2), "f2b": f2.bias.detach().float().contiguous(), "f2wt": FP._bf16(w2.t()),
+            "stack": Stack([model.input_block] + list(model.convolutions),
+                           [model.input_skip_bottleneck] + list(model.bottlenecks)),
+            "head": FP.pack_head(model.output_block, C), "head_bwd": pack_head_bwd(model.output_block, C)}
+
+
+class _RawCTCNetTrain(torch.autograd.Function):
+    """RawCTCNet.forward (reference raw_ctcnet.py:117-153, positions=False) with its backward on the tensor-core
+    kernels: featuriser Conv1d(1,F,fk,pad fk-1) + LeakyReLU (bandwidth kernel), 1x1 + LeakyReLU (dense), residual
+    stack, head.  The output is fk-1 frames longer than the input (raw_ctcnet.py:58)."""
+
+    @staticmethod
+    def forward(ctx, model, pk, seq, *params):
+        C, F, fk = model.layers[0][0], model.num_features, model.feature_kwidth
+        B, _, T = seq.shape
+        To = T + fk - 1
+        f = torch.empty((B, To, F), dtype=torch.bfloat16, device=seq.device)
+        _lib.call("wnb200_featurize_nlc", ops._dt(seq), B, T, F, fk, ops._p(seq), ops._p(pk["f0w"]), ops._p(pk["f0b"]),
+                  ops._p(f), ops._stream())
+        h0 = FP.dense(f, [0], pk["f2w"], pk["f2b"], F, leaky=1)
+        skips = torch.empty((B, To, C), dtype=torch.float32, device=seq.device)
+        saved = stack_forward(h0, pk["stack"], skips)
+        out, skips_act, h1 = head_forward(skips, pk["head"], seq.dtype, model.softmax)
+        del skips
+        ctx.model, ctx.pk, ctx.params = model, pk, params
+        ctx.keep = (seq, f, saved, skips_act, h1, out if model.softmax else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        model, pk, params = ctx.model, ctx.pk, ctx.params
+        seq, f, saved, skips_act, h1, out = ctx.keep
+        ctx.keep = None
+        F, fk = model.num_features, model.feature_kwidth
+        B, _, T = seq.shape
+        dev = seq.device
+        h0 = saved[0][0]
+        dskips, ghead = head_backward(dout.contiguous(), out, model.softmax, pk["head_bwd"], skips_act, h1)
+        dh0, gl = stack_backward(pk["stack"], saved, dskips, True)
+        dpre2 = leaky_bwd(dh0, h0)                                       # through the second LeakyReLU
+        dw2 = wgrad_rows(dpre2, f, 0, F, F).unsqueeze(2)
+        db2 = colsum(dpre2)
+        df = FP.dense(dpre2, [0], pk["f2wt"], _zeros(F, dev), F)
+        dw0, db0 = torch.zeros((F, fk), dtype=torch.float32, device=dev), _zeros(F, dev)
+        need_dx = ctx.needs_input_grad[2]
+        dseq = torch.zeros((B, T), dtype=torch.float32, device=dev) if need_dx else None
+        _lib.call("wnb200_featurize_bwd_nlc", ops._dt(seq), B, T, F, fk, ops._p(df), ops._p(f), ops._p(seq),
+                  ops._p(pk["f0w"]), ops._p(dw0), ops._p(db0), ops._p(dseq), ops._stream())
+        grads = [dw0.unsqueeze(1), db0, dw2, db2] + [g for layer in gl for g in layer] + ghead
+        return (None, None, dseq.view(B, 1, T).to(seq.dtype) if need_dx else None) + _cast(grads, params)
+
+
+def raw_ctcnet_train_eligible(model, seq):
+    C, F = model.layers[0][0], model.num_features
+    return (seq.dtype == torch.bfloat16 and seq.is_cuda and seq.dim() == 3 and seq.shape[1] == 1 and F == C
+            and model.out_dim == C and C in (128, 256) and not model.positions and FP._stack_ok(C, model.layers)
+            and model.input_kernel_size <= 3 and model.feature_kwidth <= 4 and seq.shape[0] > 0 and seq.shape[2] > 0)
+
+
+def raw_ctcnet_forward_train(model, seq):
+    ops.check_device()
+    pk = FP._cached(model, "raw_ctcnet_train", lambda: _raw_ctcnet_pack(model))
+    f0, f2 = model.feature_layer[0], model.feature_layer[2]
+    params = [f0.weight, f0.bias, f2.weight, f2.bias] + pk["stack"].params() + _head_params(model.output_block)
+    return _RawCTCNetTrain.apply(model, pk, seq.contiguous(), *params)
