@@ -252,8 +252,10 @@ int wnb200_wgrad2_tc(int B, int T, int Cg, int m0, int N, int nsrc, const int32_
                      const void* x_nlc, const void* x2_nlc, float* dw, void* stream);
 
 /* Gate backward on NLC bf16 tensors (block.py:185): dab[r, 0:C] = dact*sg*(1-th^2), dab[r, C:2C] = dact*th*sg*(1-sg)
- * for each of `rows` = B*T frames. */
-int wnb200_gate_bwd_nlc(int64_t rows, int C, const void* dact, const void* th, const void* sg, void* dab, void* stream);
+ * for each of `rows` = B*T frames; if dbias != NULL, dbias[0:2C] (fp32) += the column sums of dab (the two conv
+ * biases' gradients). */
+int wnb200_gate_bwd_nlc(int64_t rows, int C, const void* dact, const void* th, const void* sg, void* dab, float* dbias,
+                        void* stream);
 
 /* out[c] += sum over rows of x[r, c]  (x NLC bf16 [rows, C]; bias gradients on the tensor-core training path). */
 int wnb200_colsum_nlc(int64_t rows, int C, const void* x, float* out, void* stream);

@@ -87,9 +87,10 @@ def test_colsum_and_gate_bwd_nlc(rows, C):
     assert G.rel_linf(s.cpu(), x.sum((0, 1))) <= 1e-5
     d, a, b = r16(torch.randn(1, rows, C)), torch.randn(1, rows, C), torch.randn(1, rows, C)
     th, sg = r16(torch.tanh(a)), r16(torch.sigmoid(b))
-    dab = TR.gate_bwd_nlc(d.cuda().bfloat16(), th.cuda().bfloat16(), sg.cuda().bfloat16()).float().cpu()
+    dab, dbias = TR.gate_bwd_nlc(d.cuda().bfloat16(), th.cuda().bfloat16(), sg.cuda().bfloat16(), want_bias=True)
     ref = torch.cat([d * sg * (1 - th * th), d * th * sg * (1 - sg)], 2)
-    assert G.rel_linf(dab, ref) <= 1e-2
+    assert G.rel_linf(dab.float().cpu(), ref) <= 1e-2
+    assert G.rel_linf(dbias.cpu(), ref.sum((0, 1))) <= 1e-4
 
 
 @pytest.mark.parametrize("Cin,Cin2,N,k,k2,T,B", [(256, 256, 256, 1, 1, 300, 2), (512, 256, 256, 2, 1, 700, 2),

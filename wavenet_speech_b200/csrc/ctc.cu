@@ -16,6 +16,10 @@
 //                         w_t(s) = exp(alpha_t(s) + beta_t(s) - lp_t(lab(s)) + offsets_t + nll)  -- the w_t(s) of one frame lie in
 //                         [0, 1] and sum to 1, so they are added in the linear domain; one warp per (read, frame).
 //
+// Only the band of states that are reachable from the start AND can still reach the end is computed, stored and
+// read: at frame t these are the pairs j in [len - (Ta - t), t] (both trellises share it), about half of the
+// (frame, state) plane when the label sequence is about as long as the read.
+//
 // The activation tensor is addressed by strides, so both the reference's (T, B, C) layout and the classifier's
 // native (B, C, T) output are read in place.
 #include <float.h>
@@ -91,7 +95,8 @@ ctc_alpha_beta_kernel(int L, int Tn, int Smax, const float* __restrict__ lp, con
   float* lpb = sm + 2 * W;                    // [2][CTC_MAX_L]
   float* red = lpb + 2 * CTC_MAX_L;           // [32] per-warp maxima
   double* co = coff + ((long long)dir * gridDim.x + b) * Tn;
-  float* out = (dir == 0 ? alpha : beta) + (long long)b * Tn * Smax;
+  const int SP = Smax + 1;                    // even row pitch: (blank, label) pairs are stored as float2
+  float* out = (dir == 0 ? alpha : beta) + (long long)b * Tn * SP;
   const float* lpr = lp + (long long)b * Tn * L;
   const int tid = threadIdx.x, nt = blockDim.x;
   if (Ta <= 0) {
@@ -125,13 +130,10 @@ ctc_alpha_beta_kernel(int L, int Tn, int Smax, const float* __restrict__ lp, con
     if (live[i]) {
       const int s0 = 2 * j, s1 = 2 * j + 1;
       const float v0 = (dir == 0 ? s0 < 2 : s0 >= S - 2) ? lpb[0] : CTC_NEG;
+      const float v1 = (haslab[i] && (dir == 0 ? s1 < 2 : s1 >= S - 2)) ? lpb[cls[i]] : CTC_NEG;
       buf0[s0] = v0;
-      out[(long long)tfirst * Smax + s0] = v0;
-      if (haslab[i]) {
-        const float v1 = (dir == 0 ? s1 < 2 : s1 >= S - 2) ? lpb[cls[i]] : CTC_NEG;
-        buf0[s1] = v1;
-        out[(long long)tfirst * Smax + s1] = v1;
-      }
+      if (haslab[i]) buf0[s1] = v1;
+      *reinterpret_cast<float2*>(out + (long long)tfirst * SP + s0) = make_float2(v0, v1);
     }
   }
   if (tid == 0) co[tfirst] = 0.0;
@@ -145,12 +147,18 @@ ctc_alpha_beta_kernel(int L, int Tn, int Smax, const float* __restrict__ lp, con
     float* lpc = lpb + (k & 1) * CTC_MAX_L;
     if (tid < L) lpc[tid] = nxt;
     __syncthreads();
+    // band of useful pairs at this frame and at the previous one (see the header)
+    const int jlo = max(0, len - (Ta - t)), jhi = min(len, t);
+    const int tp = t - tstep;
+    const int plo = max(0, len - (Ta - tp)), phi = min(len, tp);
     float m = 0.f;
     if ((k % CTC_RENORM) == 0) {              // take the frame maximum out of the state vector
       float lm = CTC_NEG;
 #pragma unroll
-      for (int i = 0; i < NP; ++i)
-        if (live[i]) lm = fmaxf(lm, fmaxf(prev[2 * (tid + i * nt)], prev[2 * (tid + i * nt) + 1]));   // guard = NEG
+      for (int i = 0; i < NP; ++i) {
+        const int j = tid + i * nt;
+        if (j >= plo && j <= phi) lm = fmaxf(lm, fmaxf(prev[2 * j], prev[2 * j + 1]));   // guard = NEG
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) lm = fmaxf(lm, __shfl_xor_sync(0xffffffffu, lm, o));
       if ((tid & 31) == 0) red[tid >> 5] = lm;
@@ -161,12 +169,12 @@ ctc_alpha_beta_kernel(int L, int Tn, int Smax, const float* __restrict__ lp, con
       C += (double)m;
     }
     if (tid == 0) co[t] = C;
-    float* orow = out + (long long)t * Smax;
+    float* orow = out + (long long)t * SP;
     const float lpblank = lpc[0] - m;
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
       const int j = tid + i * nt;
-      if (live[i]) {
+      if (j >= jlo && j <= jhi) {
         const int s0 = 2 * j;
         float r0, r1;
         if (dir == 0) {
@@ -178,12 +186,10 @@ ctc_alpha_beta_kernel(int L, int Tn, int Smax, const float* __restrict__ lp, con
           r0 = lse2(q0, q1) + lpblank;
           r1 = lse3(q1, q2, skip[i] ? q3 : CTC_NEG) + (lpc[cls[i]] - m);
         }
+        if (!haslab[i]) r1 = CTC_NEG;
         cur[s0] = r0;
-        orow[s0] = r0;
-        if (haslab[i]) {
-          cur[s0 + 1] = r1;
-          orow[s0 + 1] = r1;
-        }
+        if (haslab[i]) cur[s0 + 1] = r1;
+        *reinterpret_cast<float2*>(orow + s0) = make_float2(r0, r1);
       }
     }
   }
@@ -211,7 +217,6 @@ ctc_grad_kernel(int B, int L, int Tn, int Smax, const float* __restrict__ lp, co
   if (w >= (long long)B * Tn) return;
   const int b = (int)(w / Tn), t = (int)(w - (long long)b * Tn);
   const int len = (int)(lab_off[b + 1] - lab_off[b]);
-  const int S = 2 * len + 1;
   const int Ta = act_len ? min(act_len[b], Tn) : Tn;
   T* g = grad + b * sb + t * st;
   const double nd = nll_d[b];
@@ -224,17 +229,23 @@ ctc_grad_kernel(int B, int L, int Tn, int Smax, const float* __restrict__ lp, co
   const float n = (float)(coff[(long long)b * Tn + t] + coff[((long long)B + b) * Tn + t] + nd / CTC_LN2);
   for (int c = lane; c < L; c += 32) acc[warp][c] = 0.f;
   __syncwarp();
-  const float* a = alpha + ((long long)b * Tn + t) * Smax;
-  const float* be = beta + ((long long)b * Tn + t) * Smax;
+  const int SP = Smax + 1;
+  const float2* a = reinterpret_cast<const float2*>(alpha + ((long long)b * Tn + t) * SP);
+  const float2* be = reinterpret_cast<const float2*>(beta + ((long long)b * Tn + t) * SP);
   const float* lpt = lp + ((long long)b * Tn + t) * L;
   const int* lab = labels + lab_off[b];
-  // blanks (even states): one class, plain sum; labels (odd states): shared-memory atomics per class
+  // one float2 per (blank, label) pair, band of useful pairs only; blanks are one class (plain sum), labels go
+  // through shared-memory atomics per class
   float blank = 0.f;
   const float lp0 = lpt[0];
-  for (int s = 2 * lane; s < S; s += 64) blank += ex2f(a[s] + be[s] - lp0 + n);
-  for (int j = lane; j < len; j += 32) {
-    const int s = 2 * j + 1, c = lab[j];
-    atomicAdd(&acc[warp][c], ex2f(a[s] + be[s] - lpt[c] + n));
+  const int jlo = max(0, len - (Ta - t)), jhi = min(len, t);
+  for (int j = jlo + lane; j <= jhi; j += 32) {
+    const float2 av = a[j], bv = be[j];
+    blank += ex2f(av.x + bv.x - lp0 + n);
+    if (j < len) {
+      const int c = lab[j];
+      atomicAdd(&acc[warp][c], ex2f(av.y + bv.y - lpt[c] + n));
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) blank += __shfl_xor_sync(0xffffffffu, blank, o);
@@ -249,10 +260,10 @@ ctc_grad_kernel(int B, int L, int Tn, int Smax, const float* __restrict__ lp, co
 
 using namespace wnb;
 
-// workspace: lp [B,T,L] f32 | alpha [B,T,S] f32 | beta [B,T,S] f32 | (8-byte aligned) offsets [2,B,T] f64 | nll [B] f64
+// workspace: lp [B,T,L] f32 (padded to even) | alpha [B,T,S+1] f32 | beta [B,T,S+1] f32 | offsets [2,B,T] f64 | nll [B] f64
+static inline size_t ctc_lp_count(int B, int L, int T_) { return ((size_t)B * T_ * L + 1) & ~(size_t)1; }
 static inline size_t ctc_f32_count(int B, int L, int T_, int Smax) {
-  const size_t n = (size_t)B * T_ * L + 2 * (size_t)B * T_ * Smax;
-  return (n + 1) & ~(size_t)1;
+  return ctc_lp_count(B, L, T_) + 2 * (size_t)B * T_ * (Smax + 1);      // even row pitch Smax + 1
 }
 
 extern "C" size_t wnb200_ctc_workspace_bytes(int B, int L, int T_, int max_label_len) {
@@ -271,8 +282,8 @@ extern "C" int wnb200_ctc_fwd(int dtype, int B, int L, int T_, int max_label_len
   cudaStream_t s = (cudaStream_t)stream;
   const int Smax = 2 * max_label_len + 1;
   float* lp = workspace;
-  float* alpha = lp + (size_t)B * T_ * L;
-  float* beta = alpha + (size_t)B * T_ * Smax;
+  float* alpha = lp + ctc_lp_count(B, L, T_);
+  float* beta = alpha + (size_t)B * T_ * (Smax + 1);
   double* coff = reinterpret_cast<double*>(workspace + ctc_f32_count(B, L, T_, Smax));
   double* nll_d = coff + 2 * (size_t)B * T_;
   WNB_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 7) == 0, "ctc_fwd: workspace must be 8-byte aligned");
@@ -322,8 +333,8 @@ extern "C" int wnb200_ctc_bwd(int dtype, int B, int L, int T_, int max_label_len
   cudaStream_t s = (cudaStream_t)stream;
   const int Smax = 2 * max_label_len + 1;
   const float* lp = workspace;
-  const float* alpha = lp + (size_t)B * T_ * L;
-  const float* beta = alpha + (size_t)B * T_ * Smax;
+  const float* alpha = lp + ctc_lp_count(B, L, T_);
+  const float* beta = alpha + (size_t)B * T_ * (Smax + 1);
   const double* coff = reinterpret_cast<const double*>(workspace + ctc_f32_count(B, L, T_, Smax));
   const double* nll_d = coff + 2 * (size_t)B * T_;
   (void)nll;

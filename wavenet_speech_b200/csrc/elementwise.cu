@@ -295,28 +295,50 @@ __global__ void argmax_kernel(int B, int C, int Tn, const T* x, long long* out) 
 }
 
 // gate backward on NLC bf16: 8 channels (16 B) per thread
-__global__ void gate_bwd_nlc_kernel(long long rows, int C, const uint4* dact, const uint4* th, const uint4* sg,
-                                    uint4* dab) {
-  const int g = C / 8;
-  const long long n = rows * g;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / g;
-    const int cg = (int)(i - r * g);
-    const uint4 d4 = dact[i], t4 = th[i], s4 = sg[i];
-    const __nv_bfloat162* dp = reinterpret_cast<const __nv_bfloat162*>(&d4);
-    const __nv_bfloat162* tp = reinterpret_cast<const __nv_bfloat162*>(&t4);
-    const __nv_bfloat162* sp = reinterpret_cast<const __nv_bfloat162*>(&s4);
-    uint4 oa, ob;
-    __nv_bfloat162* ap = reinterpret_cast<__nv_bfloat162*>(&oa);
-    __nv_bfloat162* bp = reinterpret_cast<__nv_bfloat162*>(&ob);
+// A thread owns one 8-channel group for the whole launch (C/8 threads per frame side by side, 256/(C/8) frames per
+// block pass, grid-stride over frames), so the bias gradients -- the column sums of dab -- ride along in registers:
+// dbias[0:C] += sum_rows da, dbias[C:2C] += sum_rows ds (fp32, one atomicAdd per channel per block; optional).
+__global__ void __launch_bounds__(256)
+gate_bwd_nlc_kernel(long long rows, int C, const uint4* dact, const uint4* th, const uint4* sg, uint4* dab,
+                    float* dbias) {
+  const int g = C / 8, rpb = 256 / g;
+  const int cg = threadIdx.x % g, rl = threadIdx.x / g;
+  float sa[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, sb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (rl < rpb) {
+    for (long long r = blockIdx.x * (long long)rpb + rl; r < rows; r += (long long)gridDim.x * rpb) {
+      const long long i = r * g + cg;
+      const uint4 d4 = __ldg(dact + i), t4 = __ldg(th + i), s4 = __ldg(sg + i);
+      const __nv_bfloat162* dp = reinterpret_cast<const __nv_bfloat162*>(&d4);
+      const __nv_bfloat162* tp = reinterpret_cast<const __nv_bfloat162*>(&t4);
+      const __nv_bfloat162* sp = reinterpret_cast<const __nv_bfloat162*>(&s4);
+      uint4 oa, ob;
+      __nv_bfloat162* ap = reinterpret_cast<__nv_bfloat162*>(&oa);
+      __nv_bfloat162* bp = reinterpret_cast<__nv_bfloat162*>(&ob);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 d = __bfloat1622float2(dp[k]), t = __bfloat1622float2(tp[k]), s_ = __bfloat1622float2(sp[k]);
-      ap[k] = __floats2bfloat162_rn(d.x * s_.x * (1.f - t.x * t.x), d.y * s_.y * (1.f - t.y * t.y));
-      bp[k] = __floats2bfloat162_rn(d.x * t.x * s_.x * (1.f - s_.x), d.y * t.y * s_.y * (1.f - s_.y));
+      for (int k = 0; k < 4; ++k) {
+        const float2 d = __bfloat1622float2(dp[k]), t = __bfloat1622float2(tp[k]), s_ = __bfloat1622float2(sp[k]);
+        const float a0 = d.x * s_.x * (1.f - t.x * t.x), a1 = d.y * s_.y * (1.f - t.y * t.y);
+        const float b0 = d.x * t.x * s_.x * (1.f - s_.x), b1 = d.y * t.y * s_.y * (1.f - s_.y);
+        ap[k] = __floats2bfloat162_rn(a0, a1);
+        bp[k] = __floats2bfloat162_rn(b0, b1);
+        sa[2 * k] += a0; sa[2 * k + 1] += a1;
+        sb[2 * k] += b0; sb[2 * k + 1] += b1;
+      }
+      dab[r * (2 * g) + cg] = oa;
+      dab[r * (2 * g) + g + cg] = ob;
     }
-    dab[r * (2 * g) + cg] = oa;
-    dab[r * (2 * g) + g + cg] = ob;
+  }
+  if (dbias == nullptr) return;
+  __shared__ float red[256][17];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { red[threadIdx.x][k] = sa[k]; red[threadIdx.x][8 + k] = sb[k]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += 256) {
+    const int half = c >= C, cc = c - half * C;
+    const int gq = cc >> 3, k = (cc & 7) + 8 * half;
+    float tsum = 0.f;
+    for (int q = 0; q < rpb; ++q) tsum += red[q * g + gq][k];
+    atomicAdd(&dbias[c], tsum);
   }
 }
 
@@ -637,12 +659,15 @@ extern "C" int wnb200_argmax_channels_col(int dtype, int B, int C, int T_, const
 }
 
 extern "C" int wnb200_gate_bwd_nlc(int64_t rows, int C, const void* dact, const void* th, const void* sg, void* dab,
-                                   void* stream) {
-  WNB_CHECK_ARG(C % 8 == 0, "gate_bwd_nlc: C must be a multiple of 8");
+                                   float* dbias, void* stream) {
+  WNB_CHECK_ARG(C % 8 == 0 && C <= 2048, "gate_bwd_nlc: C=%d must be a multiple of 8, <= 2048", C);
   if (rows == 0) return 0;
   WNB_CHECK_ARG(dact && th && sg && dab, "gate_bwd_nlc: null pointer");
-  gate_bwd_nlc_kernel<<<grid_for(rows * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
-      rows, C, (const uint4*)dact, (const uint4*)th, (const uint4*)sg, (uint4*)dab);
+  const int rpb = 256 / (C / 8);
+  long long grid = (rows + rpb - 1) / rpb;
+  if (grid > 148 * 8) grid = 148 * 8;
+  gate_bwd_nlc_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+      rows, C, (const uint4*)dact, (const uint4*)th, (const uint4*)sg, (uint4*)dab, dbias);
   WNB_LAUNCH_OK();
   return 0;
 }

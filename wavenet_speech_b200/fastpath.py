@@ -179,14 +179,15 @@ def wgrad(g_nlc, x_nlc, off=0, m0=0, dw=None):
     return dw
 
 
-def wgrad2(g_nlc, xs, offs, m0=0):
+def wgrad2(g_nlc, xs, offs, m0=0, dw=None):
     """dw[m, s*N + n] = sum_{b,t} g[b,t,m0+m] * xs[s][b,t+offs[s],n] for one or two X tensors sharing the G tiles;
     returns fp32 [256, len(xs)*N]."""
     B, T, Cg = g_nlc.shape
     N = xs[0].shape[2]
     ns = len(xs)
     assert ns in (1, 2) and all(x.shape == xs[0].shape for x in xs)
-    dw = torch.zeros((256, ns * N), dtype=torch.float32, device=g_nlc.device)
+    if dw is None:
+        dw = torch.zeros((256, ns * N), dtype=torch.float32, device=g_nlc.device)
     off = (ctypes.c_int32 * 2)(int(offs[0]), int(offs[1]) if ns > 1 else 0)
     _lib.current_tag = "wgrad"
     try:

@@ -24,8 +24,46 @@ def _t(w):
     return w.detach().float().t()
 
 
+class _ZeroPool(object):
+    """fp32 zero-initialised scratch handed out in slices: ONE memset per backward pass instead of one fill launch per
+    accumulator (weight-gradient tiles, bias sums) -- several hundred 2-microsecond launches per step otherwise."""
+    current = None
+
+    def __init__(self, dev, nfloats):
+        self.buf = torch.zeros(int(nfloats), dtype=torch.float32, device=dev)
+        self.off = 0
+
+    def take(self, *shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        n_al = (n + 63) // 64 * 64                      # 256-byte aligned slices (TMA reduce-add targets)
+        if self.off + n_al > self.buf.numel():
+            return torch.zeros(shape, dtype=torch.float32, device=self.buf.device)
+        out = self.buf[self.off:self.off + n].view(*shape)
+        self.off += n_al
+        return out
+
+
 def _zeros(n, dev):
+    pool = _ZeroPool.current
+    if pool is not None and pool.buf.device == torch.device(dev):
+        return pool.take(n)
     return torch.zeros(n, dtype=torch.float32, device=dev)
+
+
+class zero_pool(object):
+    """with zero_pool(device, nfloats): ... -> `_zeros` and the weight-gradient launches draw from one buffer."""
+
+    def __init__(self, dev, nfloats):
+        self.dev, self.n = dev, nfloats
+
+    def __enter__(self):
+        self.prev = _ZeroPool.current
+        _ZeroPool.current = _ZeroPool(self.dev, self.n)
+
+    def __exit__(self, *exc):
+        _ZeroPool.current = self.prev
 
 
 def pack_block_bwd(block, bottleneck):
@@ -59,11 +97,14 @@ def colsum(x_nlc, out=None):
     return out
 
 
-def gate_bwd_nlc(dgate, th, sg):
+def gate_bwd_nlc(dgate, th, sg, want_bias=False):
+    """dab = [dgate sg (1-th^2) ; dgate th sg (1-sg)]; with want_bias also its fp32 column sums [2C]."""
     B, T, C = dgate.shape
     dab = torch.empty((B, T, 2 * C), dtype=torch.bfloat16, device=dgate.device)
-    _lib.call("wnb200_gate_bwd_nlc", B * T, C, ops._p(dgate), ops._p(th), ops._p(sg), ops._p(dab), ops._stream())
-    return dab
+    dbias = _zeros(2 * C, dgate.device) if want_bias else None
+    _lib.call("wnb200_gate_bwd_nlc", B * T, C, ops._p(dgate), ops._p(th), ops._p(sg), ops._p(dab), ops._p(dbias),
+              ops._stream())
+    return (dab, dbias) if want_bias else dab
 
 
 def leaky_bwd(dy, ref):
@@ -80,7 +121,7 @@ def wgrad_multi(g, rows, srcs):
         nr = min(256, rows - m0)
         for i in range(0, len(srcs), 2):
             pair = srcs[i:i + 2]
-            dw = FP.wgrad2(g, [q[0] for q in pair], [q[1] for q in pair], m0)
+            dw = FP.wgrad2(g, [q[0] for q in pair], [q[1] for q in pair], m0, dw=_zeros(256 * len(pair) * N, g.device).view(256, len(pair) * N))
             for q in range(len(pair)):
                 outs[i + q].append(dw[:nr, q * N:(q + 1) * N])
     return [o[0] if len(o) == 1 else torch.cat(o, 0) for o in outs]
@@ -107,6 +148,13 @@ class Stack(object):
                     b.conv1x1_skip.weight, b.conv1x1_skip.bias, b.residual_proj.weight, b.residual_proj.bias,
                     n.weight, n.bias]
         return out
+
+
+def _pool_floats(stack):
+    """Upper bound of the fp32 accumulators one backward pass draws from the zero pool."""
+    C = stack.fwd[0]["C"]
+    per_layer = 4 * 256 * 2 * C + 8 * 2 * C + 1024
+    return (len(stack.fwd) + 4) * per_layer + 16 * 256 * 2 * 256
 
 
 def stack_forward(h0, stack, skips):
@@ -142,7 +190,7 @@ def stack_backward(stack, saved, dskips, need_dx0):
             dg = FP.dense(dskips, [0], pb["wdg_skip"], zb, C)
         else:
             dg = FP.dense(dres, [0], pb["wdg"], zb, C, x2=dskips, offsets2=[0])
-        dab = gate_bwd_nlc(dg, th, sg)
+        dab, dbab = gate_bwd_nlc(dg, th, sg, want_bias=True)
         del dg
         dx = None
         if l > 0 or need_dx0:
@@ -154,7 +202,6 @@ def stack_backward(stack, saved, dskips, need_dx0):
         dwab = wgrad_multi(dab, 2 * C, [(x, offs[j]) for j in range(k)])            # k x [2C, C]
         dwt = torch.stack([d[:C] for d in dwab], 2)
         dws = torch.stack([d[C:] for d in dwab], 2)
-        dbab = colsum(dab)
         dwres = dwproj = dbres = None
         if dres is not None:
             dwres, dwproj = wgrad_multi(dres, C, [(act, 0), (x, 0)])
@@ -264,6 +311,11 @@ class _WaveNetTrain(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
+        with zero_pool(dout.device, _pool_floats(ctx.pk["stack"])):
+            return _WaveNetTrain._backward(ctx, dout)
+
+    @staticmethod
+    def _backward(ctx, dout):
         model, pk, params = ctx.model, ctx.pk, ctx.params
         x, offs, saved, skips_act, h1, out = ctx.keep
         ctx.keep = None
@@ -322,6 +374,11 @@ class _ClassifierTrain(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
+        with zero_pool(dout.device, _pool_floats(ctx.pk["stack"])):
+            return _ClassifierTrain._backward(ctx, dout)
+
+    @staticmethod
+    def _backward(ctx, dout):
         model, pk, params = ctx.model, ctx.pk, ctx.params
         saved, skips_act, h1, out = ctx.keep
         ctx.keep = None
@@ -385,6 +442,11 @@ class _RawCTCNetTrain(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
+        with zero_pool(dout.device, _pool_floats(ctx.pk["stack"])):
+            return _RawCTCNetTrain._backward(ctx, dout)
+
+    @staticmethod
+    def _backward(ctx, dout):
         model, pk, params = ctx.model, ctx.pk, ctx.params
         seq, f, saved, skips_act, h1, out = ctx.keep
         ctx.keep = None
