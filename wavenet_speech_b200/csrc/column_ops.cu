@@ -386,6 +386,249 @@ argmax_tile(int C, int Tn, TileGeom g, bool vec, const T* x, long long* out) {
   }
 }
 
+// ------------------------------------------------------------------------------------------ register tiles
+// For C <= 256 (the networks' 256 signal levels) the tile never touches shared memory: a CTA of 256 threads owns
+// [C channels x 8 vectors of 16 bytes] (64 frames in bf16, 32 in fp32); thread (g = tid / 8, v = tid % 8) keeps vector v of
+// channels g, g+32, ..., g+32(KC-1) in registers (KC 16-byte loads in flight per thread), reduces its channels
+// locally, meets the 31 other channel groups of its frames through an 8 KB shared array, and stores straight from
+// registers.  ~8 instructions per element instead of ~15 for the shared-memory tile, whose budget at 2 B/element is
+// ~10 per element at HBM speed.
+template <typename T, int KC>
+struct RegTile {
+  static constexpr int V = 16 / sizeof(T);
+  static constexpr int TT = 8 * V;
+  uint4 raw[KC];
+  bool cok[KC];
+  bool tok;
+  int g, v;
+  __device__ __forceinline__ void load(const T* xb, int C, int Tn, int t0, uint32_t fill) {
+    g = threadIdx.x >> 3;
+    v = threadIdx.x & 7;
+    const int t = t0 + v * V;
+    tok = t + V <= Tn;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const int c = g + 32 * k;
+      cok[k] = c < C;
+      raw[k] = make_uint4(fill, fill, fill, fill);
+      if (cok[k] && tok) raw[k] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)c * Tn + t));
+      else if (!tok) raw[k] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  __device__ __forceinline__ float get(int k, int i) const { return to_f32<T>(reinterpret_cast<const T*>(&raw[k])[i]); }
+};
+
+template <typename T> struct NegInf;
+template <> struct NegInf<float> { static constexpr uint32_t bits = 0xFF800000u; };
+template <> struct NegInf<__nv_bfloat16> { static constexpr uint32_t bits = 0xFF80FF80u; };
+
+// p[i] (one partial per frame of this thread) -> total over all channels.  Two shuffle steps merge the four channel
+// groups of a warp (lanes v, v+8, v+16, v+24), the eight warps meet in shared memory (red: 8 x TT floats), one thread
+// per frame merges them.  MAXOP: max instead of sum.
+template <int V, bool MAXOP>
+__device__ __forceinline__ void frames_combine(float (&p)[V], float* red, float* fin, int v) {
+  constexpr int TT = 8 * V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      const float q = __shfl_xor_sync(0xffffffffu, p[i], o);
+      p[i] = MAXOP ? fmaxf(p[i], q) : p[i] + q;
+    }
+    if (lane < 8) red[warp * TT + v * V + i] = p[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < TT) {
+    float a = red[threadIdx.x];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      const float q = red[w * TT + threadIdx.x];
+      a = MAXOP ? fmaxf(a, q) : a + q;
+    }
+    fin[threadIdx.x] = a;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < V; ++i) p[i] = fin[v * V + i];
+}
+
+// global max then global sum of exp(x - max) of this thread's V frames (two combines; exps only on the elements)
+template <typename T, int KC>
+__device__ __forceinline__ void softmax_stats(const RegTile<T, KC>& r, float (&m)[RegTile<T, KC>::V],
+                                              float (&s)[RegTile<T, KC>::V], float* red, float* fin) {
+  constexpr int V = RegTile<T, KC>::V;
+#pragma unroll
+  for (int i = 0; i < V; ++i) m[i] = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < KC; ++k)
+#pragma unroll
+    for (int i = 0; i < V; ++i) m[i] = fmaxf(m[i], r.get(k, i));
+  frames_combine<V, true>(m, red, fin, r.v);
+#pragma unroll
+  for (int i = 0; i < V; ++i) s[i] = 0.f;
+#pragma unroll
+  for (int k = 0; k < KC; ++k)
+#pragma unroll
+    for (int i = 0; i < V; ++i) s[i] += exp_t<T>(r.get(k, i) - m[i]);
+  frames_combine<V, false>(s, red + 8 * 8 * V, fin + 8 * V, r.v);
+}
+
+template <typename T, int KC>
+__global__ void __launch_bounds__(CT_THREADS, 2)
+softmax_fwd_reg(int C, int Tn, int tiles_per_read, const T* x, T* y, int log_mode) {
+  using RT = RegTile<T, KC>;
+  constexpr int V = RT::V, TT = RT::TT;
+  __shared__ float red[16 * TT], fin[2 * TT];
+  const int b = blockIdx.x / tiles_per_read, t0 = (blockIdx.x - b * tiles_per_read) * TT;
+  const long long rb = (long long)b * C * Tn;
+  RT r;
+  r.load(x + rb, C, Tn, t0, NegInf<T>::bits);
+  float m[V], sum[V];
+  softmax_stats<T, KC>(r, m, sum, red, fin);
+  if (!r.tok) return;
+#pragma unroll
+  for (int i = 0; i < V; ++i) sum[i] = log_mode ? m[i] + logf(sum[i]) : 1.f / sum[i];
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    if (!r.cok[k]) continue;
+    uint4 val;
+    T* o = reinterpret_cast<T*>(&val);
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+      o[i] = from_f32<T>(log_mode ? r.get(k, i) - sum[i] : exp_t<T>(r.get(k, i) - m[i]) * sum[i]);
+    *reinterpret_cast<uint4*>(y + rb + (long long)(r.g + 32 * k) * Tn + t0 + r.v * V) = val;
+  }
+}
+
+template <typename T, int KC>
+__global__ void __launch_bounds__(CT_THREADS, 2)
+xent_fwd_reg(int C, int Tn, int tiles_per_read, const T* x, const long long* target, float* loss_bt, float* lse_out) {
+  using RT = RegTile<T, KC>;
+  constexpr int V = RT::V, TT = RT::TT;
+  __shared__ float red[16 * TT], fin[2 * TT], xt[TT];
+  const int b = blockIdx.x / tiles_per_read, t0 = (blockIdx.x - b * tiles_per_read) * TT;
+  const long long rb = (long long)b * C * Tn;
+  RT r;
+  r.load(x + rb, C, Tn, t0, NegInf<T>::bits);
+  __shared__ int tgs[TT];
+  if (threadIdx.x < TT) {
+    const int t = t0 + threadIdx.x;
+    long long tg = t < Tn ? target[(long long)b * Tn + t] : 0;
+    tgs[threadIdx.x] = (int)(tg < 0 ? 0 : (tg >= C ? C - 1 : tg));
+  }
+  float m[V], sum[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) m[i] = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < KC; ++k)
+#pragma unroll
+    for (int i = 0; i < V; ++i) m[i] = fmaxf(m[i], r.get(k, i));
+  frames_combine<V, true>(m, red, fin, r.v);
+  // the logit of the target class of each of this thread's frames, if this thread holds it (tgs is visible: the
+  // combine above went through two barriers)
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int tg = tgs[r.v * V + i];
+    if ((tg & 31) == r.g) {
+      const int kq = tg >> 5;
+      float val = 0.f;
+#pragma unroll
+      for (int k = 0; k < KC; ++k)
+        if (k == kq) val = r.get(k, i);
+      xt[r.v * V + i] = val;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) sum[i] = 0.f;
+#pragma unroll
+  for (int k = 0; k < KC; ++k)
+#pragma unroll
+    for (int i = 0; i < V; ++i) sum[i] += exp_t<T>(r.get(k, i) - m[i]);
+  frames_combine<V, false>(sum, red + 8 * 8 * V, fin + 8 * V, r.v);
+  if (r.g == 0 && r.tok) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float lse = m[i] + logf(sum[i]);
+      const long long col = (long long)b * Tn + t0 + r.v * V + i;
+      loss_bt[col] = lse - xt[r.v * V + i];
+      lse_out[col] = lse;
+    }
+  }
+}
+
+template <typename T, int KC>
+__global__ void __launch_bounds__(CT_THREADS)
+xent_bwd_reg(int C, int Tn, int tiles_per_read, const T* x, const long long* target, const float* lse,
+             const float* gscale, T* dx) {
+  using RT = RegTile<T, KC>;
+  constexpr int V = RT::V, TT = RT::TT;
+  const int b = blockIdx.x / tiles_per_read, t0 = (blockIdx.x - b * tiles_per_read) * TT;
+  const long long rb = (long long)b * C * Tn;
+  RT r;
+  r.load(x + rb, C, Tn, t0, 0u);
+  if (!r.tok) return;
+  float l[V];
+  int tg[V];
+  const long long col0 = (long long)b * Tn + t0 + r.v * V;
+#pragma unroll
+  for (int i = 0; i < V; ++i) { l[i] = lse[col0 + i]; tg[i] = (int)target[col0 + i]; }
+  const float gs = *gscale;
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    if (!r.cok[k]) continue;
+    const int c = r.g + 32 * k;
+    uint4 val;
+    T* o = reinterpret_cast<T*>(&val);
+#pragma unroll
+    for (int i = 0; i < V; ++i) o[i] = from_f32<T>((exp_t<T>(r.get(k, i) - l[i]) - (c == tg[i] ? 1.f : 0.f)) * gs);
+    *reinterpret_cast<uint4*>(dx + rb + (long long)c * Tn + t0 + r.v * V) = val;
+  }
+}
+
+template <typename T, int KC>
+__global__ void __launch_bounds__(CT_THREADS, 2)
+argmax_reg(int C, int Tn, int tiles_per_read, const T* x, long long* out) {
+  using RT = RegTile<T, KC>;
+  constexpr int V = RT::V, TT = RT::TT;
+  __shared__ float redv[8 * TT];
+  __shared__ int redc[8 * TT];
+  const int b = blockIdx.x / tiles_per_read, t0 = (blockIdx.x - b * tiles_per_read) * TT;
+  const long long rb = (long long)b * C * Tn;
+  RT r;
+  r.load(x + rb, C, Tn, t0, NegInf<T>::bits);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    float m = r.cok[0] ? r.get(0, i) : -INFINITY;
+    int a = r.cok[0] ? r.g : C;                   // ascending channels within a thread: strict > keeps the lowest
+#pragma unroll
+    for (int k = 1; k < KC; ++k) {
+      const float val = r.get(k, i);
+      if (r.cok[k] && val > m) { m = val; a = r.g + 32 * k; }
+    }
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+      const int a2 = __shfl_xor_sync(0xffffffffu, a, o);
+      if (a2 < C && (a >= C || m2 > m || (m2 == m && a2 < a))) { m = m2; a = a2; }
+    }
+    if (lane < 8) { redv[warp * TT + r.v * V + i] = m; redc[warp * TT + r.v * V + i] = a; }
+  }
+  __syncthreads();
+  if (threadIdx.x < TT && t0 + threadIdx.x < Tn) {
+    float M = redv[threadIdx.x];
+    int A = redc[threadIdx.x];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) {
+      const float val = redv[q * TT + threadIdx.x];
+      const int a = redc[q * TT + threadIdx.x];
+      if (a < C && (A >= C || val > M || (val == M && a < A))) { M = val; A = a; }
+    }
+    out[(long long)b * Tn + t0 + threadIdx.x] = A;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 // largest TT in {256 .. 8} such that ntiles tiles of [C x (TT + pad)] elements + scratch fit in `budget` bytes
 static bool pick_geom(int C, int Tn, int esize, int ntiles, TileGeom* g, size_t* smem) {
@@ -427,6 +670,32 @@ extern "C" int wnb200_layernorm_bwd_col(int, int, int, int, const void*, const f
                                         const void*, void*, void*);
 extern "C" int wnb200_argmax_channels_col(int, int, int, int, const void*, int64_t*, void*);
 
+// register-tile path: C <= 256, 16-byte aligned rows
+#define RT_TRY(KERNEL, P0, P1, ...)                                                                        \
+  do {                                                                                                     \
+    const int esize_ = dtype == WNB200_F32 ? 4 : 2;                                                        \
+    if (C <= 256 && (dtype == WNB200_F32 || dtype == WNB200_BF16) && vec_ok(P0, P1, nullptr, T_, esize_)) { \
+      const int TT_ = 8 * (16 / esize_);                                                                   \
+      const int tiles_ = (T_ + TT_ - 1) / TT_;                                                             \
+      const unsigned grid_ = (unsigned)((long long)B * tiles_);                                            \
+      cudaStream_t st_ = (cudaStream_t)stream;                                                             \
+      const int kc_ = C <= 64 ? 2 : (C <= 128 ? 4 : 8);                                                    \
+      if (dtype == WNB200_F32) {                                                                           \
+        using T = float;                                                                                   \
+        if (kc_ == 2) KERNEL<T, 2><<<grid_, CT_THREADS, 0, st_>>>(C, T_, tiles_, __VA_ARGS__);              \
+        else if (kc_ == 4) KERNEL<T, 4><<<grid_, CT_THREADS, 0, st_>>>(C, T_, tiles_, __VA_ARGS__);         \
+        else KERNEL<T, 8><<<grid_, CT_THREADS, 0, st_>>>(C, T_, tiles_, __VA_ARGS__);                       \
+      } else {                                                                                             \
+        using T = bf16;                                                                                    \
+        if (kc_ == 2) KERNEL<T, 2><<<grid_, CT_THREADS, 0, st_>>>(C, T_, tiles_, __VA_ARGS__);              \
+        else if (kc_ == 4) KERNEL<T, 4><<<grid_, CT_THREADS, 0, st_>>>(C, T_, tiles_, __VA_ARGS__);         \
+        else KERNEL<T, 8><<<grid_, CT_THREADS, 0, st_>>>(C, T_, tiles_, __VA_ARGS__);                       \
+      }                                                                                                    \
+      WNB_LAUNCH_OK();                                                                                     \
+      return 0;                                                                                            \
+    }                                                                                                      \
+  } while (0)
+
 #define CT_LAUNCH(KERNEL, NTILES, P0, P1, P2, FALLBACK, ...)                                               \
   do {                                                                                                     \
     const int esize = dtype == WNB200_F32 ? 4 : 2;                                                         \
@@ -456,6 +725,7 @@ extern "C" int wnb200_softmax_fwd(int dtype, int B, int C, int T_, const void* x
                                   void* stream) {
   WNB_CHECK_ARG(x && y && C >= 1, "softmax_fwd: bad args");
   if ((long long)B * T_ == 0) return 0;
+  RT_TRY(softmax_fwd_reg, x, y, (const T*)x, (T*)y, log_mode);
   CT_LAUNCH(softmax_fwd_tile, 1, x, y, nullptr, wnb200_softmax_fwd_col(dtype, B, C, T_, x, y, log_mode, stream),
             (const T*)x, (T*)y, log_mode);
 }
@@ -472,6 +742,7 @@ extern "C" int wnb200_xent_fwd(int dtype, int B, int C, int T_, const void* logi
                                float* loss_bt, float* lse, void* stream) {
   WNB_CHECK_ARG(logits && target && loss_bt && lse, "xent_fwd: null pointer");
   if ((long long)B * T_ == 0) return 0;
+  RT_TRY(xent_fwd_reg, logits, nullptr, (const T*)logits, (const long long*)target, loss_bt, lse);
   CT_LAUNCH(xent_fwd_tile, 1, logits, nullptr, nullptr,
             wnb200_xent_fwd_col(dtype, B, C, T_, logits, target, loss_bt, lse, stream), (const T*)logits,
             (const long long*)target, loss_bt, lse);
@@ -481,6 +752,7 @@ extern "C" int wnb200_xent_bwd(int dtype, int B, int C, int T_, const void* logi
                                const float* lse, const float* gscale, void* dlogits, void* stream) {
   WNB_CHECK_ARG(logits && target && lse && gscale && dlogits, "xent_bwd: null pointer");
   if ((long long)B * T_ == 0) return 0;
+  RT_TRY(xent_bwd_reg, logits, dlogits, (const T*)logits, (const long long*)target, lse, gscale, (T*)dlogits);
   CT_LAUNCH(xent_bwd_tile, 1, logits, dlogits, nullptr,
             wnb200_xent_bwd_col(dtype, B, C, T_, logits, target, lse, gscale, dlogits, stream), (const T*)logits,
             (const long long*)target, lse, gscale, (T*)dlogits);
@@ -507,6 +779,7 @@ extern "C" int wnb200_layernorm_bwd(int dtype, int B, int C, int T_, const void*
 extern "C" int wnb200_argmax_channels(int dtype, int B, int C, int T_, const void* x, int64_t* out, void* stream) {
   WNB_CHECK_ARG(x && out && C >= 1, "argmax_channels: bad args");
   if ((long long)B * T_ == 0) return 0;
+  RT_TRY(argmax_reg, x, nullptr, (const T*)x, (long long*)out);
   CT_LAUNCH(argmax_tile, 1, x, nullptr, nullptr, wnb200_argmax_channels_col(dtype, B, C, T_, x, out, stream),
             (const T*)x, (long long*)out);
 }
