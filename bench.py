@@ -159,6 +159,50 @@ def cpu_baseline(w, target_s=12.0, threads=None):
                       "%.2f s" % (B, T, dt)}
 
 
+def train_step_measure(w, rank, world, dist, max_over_ranks, barrier, steps=5, warmup=2):
+    """The metric's "fwd+bwd" half: BASELINE configs[2], the WaveNet-CTC train step (legacy_code/train.py:24-61) on
+    the same WaveNet plus the ecoli classifier, batch-sharded (weak scaling), bf16 tensor-core kernels with fp32
+    master weights, fused Adam, gradient all-reduce when N > 1.  Inputs resident on the device."""
+    import wavenet_speech_b200 as W
+    from wavenet_speech_b200 import train as TRN
+    from wavenet_speech_b200.utils import signal_gen as S
+    torch.manual_seed(0)
+    C = w["C"]
+    wn = W.WaveNet(w["in_dim"], w["entry_k"], [(C, C, 2, d) for d in w["dil"]], C, softmax=False).cuda()
+    cn = W.WaveNetClassifier(C, 5, [(C, C, 2, d) for d in [1, 2, 4, 8, 16] * 3], C, pool_kernel_size=3,
+                             softmax=False).cuda()
+    opt = torch.optim.Adam(list(wn.parameters()) + list(cn.parameters()), lr=1e-5, fused=True)
+    B, T = w["batch"], w["T"]
+    nb = min(B, 8)
+    lev, labels = S.quantized_batch(nb, T, num_levels=w["in_dim"], seed=77 + rank, with_labels=True)
+    rep = (B + nb - 1) // nb
+    sig = torch.from_numpy(S.one_hot(lev, num_levels=w["in_dim"])).repeat(rep, 1, 1)[:B].cuda().bfloat16()
+    labels = (labels * rep)[:B]
+    nlab = T // 3 // 2                               # labels per read that an alignment over T/3 frames can carry
+    lengths = torch.tensor([min(len(l), nlab) for l in labels], dtype=torch.int32)
+    seq = (torch.cat([torch.from_numpy(l[:nlab]) for l in labels]) - 1).int().cuda()       # 0-based, as the reference
+
+    def step():
+        return TRN.train_step(wn, cn, sig, seq, lengths, opt, world=world)
+
+    for _ in range(warmup):
+        losses = step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        losses = step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    fl = 3 * (flops_per_timestep(w) + 16910848 / 3.0)
+    return {"metric": "raw-signal samples/sec (WaveNet-CTC train step: fwd + bwd + Adam)", "value": world * B * T / (ms * 1e-3),
+            "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": warmup, "batch_per_gpu": B, "T": T,
+            "classifier": "WaveNetClassifier 1+15 blocks, pool 3, 5 labels", "labels_per_read": int(lengths.max()),
+            "tflops_as_written_3x_fwd": world * B * T / (ms * 1e-3) * fl / 1e12, "joint_loss": float(losses[2]),
+            "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
+
+
 def run_reference(args, w):
     """--impl reference: the reference is Python/torch and cannot travel to the GPU box (and is not
     pip-installable: it has no setup.py), so this arm times the oracle port of its CPU path."""
@@ -206,6 +250,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the fwd+bwd (config 3 train step) measurement")
     ap.add_argument("--e2e-chunks", type=int, default=2)
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
@@ -330,6 +375,12 @@ def main():
                 "share_of_step": float(sum(per[dom])) / tot if tot > 0 else None,
                 "avg_launch_ms": avg_ms}
 
+    input_mb = x_dev.numel() * x_dev.element_size() / 1e6
+    fwd_bwd = None
+    if not args.no_train and args.workload == DEFAULT_WORKLOAD and args.dtype == "bf16":
+        del net, x_dev
+        torch.cuda.empty_cache()
+        fwd_bwd = train_step_measure(w, rank, world, dist, max_over_ranks, barrier)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -342,10 +393,10 @@ def main():
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": args.workload, "batch_per_gpu": w["batch"], "T": w["T"], "channels": C,
                    "layers": len(w["dil"]), "softmax": True, "sharding": "batch x%d" % world,
-                   "l2": "input %.0f MB and every inter-layer tensor exceed the 126 MB L2" % (
-                       x_dev.numel() * x_dev.element_size() / 1e6),
+                   "l2": "input %.0f MB and every inter-layer tensor exceed the 126 MB L2" % input_mb,
                    "flop_per_sample": flops_per_timestep(w)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "fwd_bwd": fwd_bwd,
         "tflops": value * flops_per_timestep(w) / 1e12,
     }
     print(json.dumps(out))

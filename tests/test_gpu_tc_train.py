@@ -274,3 +274,25 @@ def test_train_step_tc_matches_oracle_step():
     torch.cuda.synchronize()
     _compare(wn, {k: v.grad for k, v in w_.items()})
     _compare(cn, {k: v.grad for k, v in c_.items()})
+
+
+def test_train_step_api_reduces_the_loss():
+    """wavenet_speech_b200.train.train_step = legacy_code/train.py:24-61 (zero_grad, forward both nets, x-ent + CTC,
+    backward, optimiser step) with 0-based labels shifted so that 0 is the blank."""
+    from wavenet_speech_b200 import train as TRN
+    torch.manual_seed(4)
+    C, B, T = 128, 2, 301
+    wn = W.WaveNet(C, 2, [(C, C, 2, d) for d in (1, 2, 4)], C, softmax=False).cuda()
+    cn = W.WaveNetClassifier(C, 5, [(C, C, 2, d) for d in (1, 2)], C, pool_kernel_size=3, softmax=False).cuda()
+    opt = torch.optim.Adam(list(wn.parameters()) + list(cn.parameters()), lr=1e-4)
+    lev = torch.randint(0, C, (B, T))
+    sig = torch.zeros(B, C, T).scatter_(1, lev.unsqueeze(1), 1.0).cuda().bfloat16()
+    lengths = torch.tensor([30, 22], dtype=torch.int32)
+    seq = torch.randint(0, 4, (int(lengths.sum()),))
+    first = last = None
+    for i in range(12):
+        xe, ctc, joint = TRN.train_step(wn, cn, sig, seq, lengths, opt)
+        assert torch.isfinite(joint)
+        first = float(joint) if first is None else first
+        last = float(joint)
+    assert last < first, (first, last)
