@@ -28,27 +28,34 @@ def joint_loss_for_backward(xe_local_sum_over_t, ctc_local_sum, T, T_ctc, world)
     return xe_local_sum_over_t / (T * world) + ctc_local_sum / T_ctc
 
 
-def allreduce_gradients(params, group=None, bucket_bytes=32 << 20):
+def allreduce_gradients(params, group=None, bucket_bytes=256 << 20):
     """Bucketed SUM all-reduce of .grad over the process group (NCCL over NVLink on GPUs).  Buckets are filled in
-    reverse parameter order -- the order backward produces them -- and each is reduced as one flat tensor."""
+    reverse parameter order -- the order backward produces them.  Each bucket is ONE flat tensor: the gradients are
+    gathered into it with a fused multi-tensor copy, reduced in place, and the parameters' .grad are re-pointed at
+    views of it (no copy back) -- 442 parameters cost 3 launches instead of ~900."""
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return 0
-    grads = [p.grad for p in reversed(list(params)) if p.grad is not None]
+    plist = [p for p in reversed(list(params)) if p.grad is not None]
     n_buckets, i = 0, 0
-    while i < len(grads):
+    while i < len(plist):
         bucket, size = [], 0
-        dt, dev = grads[i].dtype, grads[i].device
-        while i < len(grads) and grads[i].dtype == dt and (not bucket or size < bucket_bytes):
-            bucket.append(grads[i])
-            size += grads[i].numel() * grads[i].element_size()
+        dt, dev = plist[i].grad.dtype, plist[i].grad.device
+        while i < len(plist) and plist[i].grad.dtype == dt and (not bucket or size < bucket_bytes):
+            bucket.append(plist[i])
+            size += plist[i].grad.numel() * plist[i].grad.element_size()
             i += 1
-        flat = torch.cat([g.reshape(-1) for g in bucket])
+        flat = torch.empty(sum(p.grad.numel() for p in bucket), dtype=dt, device=dev)
+        views = list(flat.split([p.grad.numel() for p in bucket]))
+        srcs = [p.grad.reshape(-1) for p in bucket]
+        if hasattr(torch, "_foreach_copy_"):
+            torch._foreach_copy_(views, srcs)
+        else:  # pragma: no cover
+            for v, g in zip(views, srcs):
+                v.copy_(g)
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        off = 0
-        for g in bucket:
-            g.copy_(flat[off:off + g.numel()].view_as(g))
-            off += g.numel()
+        for p, v in zip(bucket, views):
+            p.grad = v.view_as(p)
         n_buckets += 1
     return n_buckets
 

@@ -131,13 +131,71 @@ def wgrad_rows(g, x, off, rows, N):
     return wgrad_multi(g, rows, [(x, off)])[0]
 
 
+def _stk(ts, f=lambda t: t):
+    return torch.stack([f(t.detach().float()) for t in ts])
+
+
+def pack_stack(blocks, necks):
+    """Forward and backward weight packs of a whole stack in a few batched tensor ops (the packs are rebuilt after
+    every optimiser step: per-layer packing was ~60 small launches per layer).  All blocks must share (C, k).
+    Returns (fwd, bwd): per-layer dicts of views into the batched tensors, same keys as FP.pack_block /
+    pack_block_bwd."""
+    L = len(blocks)
+    C = blocks[0].out_channels
+    wt = _stk([b.conv_tanh.conv1d.weight for b in blocks])                      # [L, C, C, k]
+    ws = _stk([b.conv_sigmoid.conv1d.weight for b in blocks])
+    k = wt.shape[3]
+    bt = _stk([b.conv_tanh.conv1d.bias for b in blocks])
+    bs = _stk([b.conv_sigmoid.conv1d.bias for b in blocks])
+    wres = _stk([b.conv1x1_residual.weight for b in blocks])[:, :, :, 0]
+    wskip = _stk([b.conv1x1_skip.weight for b in blocks])[:, :, :, 0]
+    wproj = _stk([b.residual_proj.weight for b in blocks])
+    wbn = _stk([n.weight for n in necks])[:, :, :, 0]
+    bres = _stk([b.conv1x1_residual.bias for b in blocks])
+    bproj = _stk([b.residual_proj.bias for b in blocks])
+    bskip = _stk([b.conv1x1_skip.bias for b in blocks])
+    bbn = _stk([n.bias for n in necks])
+    tm = lambda w: w.permute(0, 1, 3, 2).reshape(L, C, k * C)                     # tap-major columns
+    w1 = torch.cat([tm(wt), tm(ws)], 1)                                           # [L, 2C, kC]
+    b1 = torch.cat([bt, bs], 1)
+    hc = C // 2
+    order = torch.cat([torch.arange(0, hc), torch.arange(C, C + hc), torch.arange(hc, C),
+                       torch.arange(C + hc, 2 * C)]).to(w1.device)
+    fold = torch.bmm(wbn, wskip)
+    w2 = torch.cat([torch.cat([wres, wproj], 2), torch.cat([fold, torch.zeros_like(fold)], 2)], 1)
+    b2 = torch.cat([bres + bproj, torch.bmm(wbn, bskip.unsqueeze(2))[:, :, 0] + bbn], 1)
+    w1h, b1h, w2b = w1[:, order].to(torch.bfloat16).contiguous(), b1[:, order].contiguous(), w2.to(torch.bfloat16)
+    b2 = b2.contiguous()
+    # backward: dgate = [Wres^T | fold^T] [dres ; dskips];  dx = sum_j [Wt_j^T | Ws_j^T] dab(t - off_j) + Wproj^T dres
+    wdg = torch.cat([wres.transpose(1, 2), fold.transpose(1, 2)], 2).to(torch.bfloat16).contiguous()
+    wdg_skip = fold.transpose(1, 2).to(torch.bfloat16).contiguous()
+    cols = []
+    for j in range(k):
+        cols += [wt[:, :, :, j].transpose(1, 2), ws[:, :, :, j].transpose(1, 2)]
+    wdx_taps = torch.cat(cols, 2)
+    wdx = torch.cat([wdx_taps, wproj.transpose(1, 2)], 2).to(torch.bfloat16).contiguous()
+    wdx_taps = wdx_taps.to(torch.bfloat16).contiguous()
+    fwd = [{"w1h": w1h[l], "b1h": b1h[l], "w2": w2b[l], "b2": b2[l], "offsets": list(blocks[l].offsets), "C": C}
+           for l in range(L)]
+    bwd = [{"wdg": wdg[l], "wdg_skip": wdg_skip[l], "wdx": wdx[l], "wdx_taps": wdx_taps[l], "k": k, "C": C}
+           for l in range(L)]
+    return fwd, bwd
+
+
 class Stack(object):
     """The blocks + bottlenecks of one network with their forward / backward weight packs."""
 
     def __init__(self, blocks, bottlenecks):
         self.blocks, self.necks = list(blocks), list(bottlenecks)
-        self.fwd = [FP.pack_block(b, n) for b, n in zip(self.blocks, self.necks)]
-        self.bwd = [pack_block_bwd(b, n) for b, n in zip(self.blocks, self.necks)]
+        L = len(self.blocks)
+        self.fwd, self.bwd = [None] * L, [None] * L
+        groups = {}
+        for l, b in enumerate(self.blocks):                    # blocks of equal kernel width are packed together
+            groups.setdefault(b.kernel_width, []).append(l)
+        for idx in groups.values():
+            f, g = pack_stack([self.blocks[l] for l in idx], [self.necks[l] for l in idx])
+            for q, l in enumerate(idx):
+                self.fwd[l], self.bwd[l] = f[q], g[q]
 
     def params(self):
         """Per layer, in this order: wt, bt, ws, bs, wres, bres, wskip, bskip, wproj, bproj, wbn, bbn."""
