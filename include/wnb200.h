@@ -294,6 +294,14 @@ int wnb200_ctc_greedy_decode(int dtype, int B, int L, int T, const void* act, in
 int wnb200_featurize_bwd_nlc(int seq_dtype, int B, int T, int F, int fk, const void* df, const void* fact,
                              const void* seq, const float* w, float* dw, float* db, float* dseq, void* stream);
 
+/* MultiplicativeUnit gate (block.py:213-220) on NCL tensors: pre [B, 4C, T] = outputs of (gate1; gate2; gate3;
+ * update) stacked on the channel axis, h [B, C, T]:  out = sig(pre1) * tanh(sig(pre2) * h + sig(pre3) * tanh(pre4)).
+ * bwd: dpre [B, 4C, T] and the direct term of dh [B, C, T] from dout (the convolutions' share of dh is added by
+ * their own backward). */
+int wnb200_mu_gate_fwd(int dtype, int B, int C, int T, const void* pre, const void* h, void* out, void* stream);
+int wnb200_mu_gate_bwd(int dtype, int B, int C, int T, const void* pre, const void* h, const void* dout, void* dpre,
+                       void* dh, void* stream);
+
 /* y = bf16(LeakyReLU_0.01(x)), n a multiple of 4: turns the fp32 skip sum into the head's input
  * (first LeakyReLU of output_stack, wavenet.py:67). */
 int wnb200_leaky_to_bf16(int64_t n, const float* x, void* y, void* stream);

@@ -191,6 +191,8 @@ def test_backward_networks():
                      torch.randn(2, 12, 50))
     net = W.LayerNorm(7).cuda()
     _grads_vs_oracle(net, lambda sd, xx: O.layernorm(xx, sd["gamma"], sd["beta"]), torch.randn(2, 7, 19))
+    net = W.MultiplicativeUnit(6, 3, dilation=2).cuda()        # fused four-conv launch + gate kernel, fwd and bwd
+    _grads_vs_oracle(net, lambda sd, xx: O.multiplicative_unit(sd, "", xx, 2), torch.randn(2, 6, 33))
 
 
 def test_xent_and_train_step_golden():

@@ -96,6 +96,8 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p],
     "wnb200_featurize_bwd_nlc": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p],
+    "wnb200_mu_gate_fwd": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_mu_gate_bwd": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_leaky_to_bf16": [c_int64, c_void_p, c_void_p, c_void_p],
     "wnb200_ncl_to_nlc_bf16": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "wnb200_nlc_to_ncl": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],

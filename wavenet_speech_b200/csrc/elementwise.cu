@@ -459,6 +459,41 @@ featurize_bwd_nlc_kernel(int Tn, int F, const uint4* df, const uint4* fact, cons
   }
 }
 
+// MultiplicativeUnit gate (block.py:213-220): pre = the four convolutions' outputs stacked on the channel axis
+// [B, 4C, T] = (gate1 ; gate2 ; gate3 ; update), h [B, C, T]:
+//   g_i = sigmoid(pre_i), u = tanh(pre_4), out = g1 * tanh(g2 * h + g3 * u)
+template <typename T>
+__global__ void mu_gate_fwd_kernel(int B, int C, int Tn, const T* pre, const T* h, T* out) {
+  const long long n = (long long)B * C * Tn, plane = (long long)C * Tn;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / plane, r = i - b * plane;
+    const T* p = pre + b * 4 * plane + r;
+    const float g1 = sigmoid_precise(to_f32<T>(p[0])), g2 = sigmoid_precise(to_f32<T>(p[plane]));
+    const float g3 = sigmoid_precise(to_f32<T>(p[2 * plane])), u = tanhf(to_f32<T>(p[3 * plane]));
+    out[i] = from_f32<T>(g1 * tanhf(g2 * to_f32<T>(h[i]) + g3 * u));
+  }
+}
+
+template <typename T>
+__global__ void mu_gate_bwd_kernel(int B, int C, int Tn, const T* pre, const T* h, const T* dout, T* dpre, T* dh) {
+  const long long n = (long long)B * C * Tn, plane = (long long)C * Tn;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / plane, r = i - b * plane;
+    const T* p = pre + b * 4 * plane + r;
+    T* q = dpre + b * 4 * plane + r;
+    const float g1 = sigmoid_precise(to_f32<T>(p[0])), g2 = sigmoid_precise(to_f32<T>(p[plane]));
+    const float g3 = sigmoid_precise(to_f32<T>(p[2 * plane])), u = tanhf(to_f32<T>(p[3 * plane]));
+    const float hv = to_f32<T>(h[i]), d = to_f32<T>(dout[i]);
+    const float ts = tanhf(g2 * hv + g3 * u);
+    const float ds = d * g1 * (1.f - ts * ts);
+    q[0] = from_f32<T>(d * ts * g1 * (1.f - g1));
+    q[plane] = from_f32<T>(ds * hv * g2 * (1.f - g2));
+    q[2 * plane] = from_f32<T>(ds * u * g3 * (1.f - g3));
+    q[3 * plane] = from_f32<T>(ds * g3 * (1.f - u * u));
+    dh[i] = from_f32<T>(ds * g2);
+  }
+}
+
 static inline int grid_for(long long n, int block = 256) {
   long long g = (n + block - 1) / block;
   const long long cap = 148ll * 32;
@@ -710,6 +745,30 @@ extern "C" int wnb200_featurize_bwd_nlc(int seq_dtype, int B, int T_, int F, int
   else { set_error("featurize_bwd_nlc: bad dtype %d", seq_dtype); return 1; }
 #undef FB_DISPATCH
 #undef FB_LAUNCH
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_mu_gate_fwd(int dtype, int B, int C, int T_, const void* pre, const void* h, void* out,
+                                  void* stream) {
+  const long long n = (long long)B * C * T_;
+  if (n == 0) return 0;
+  WNB_CHECK_ARG(pre && h && out, "mu_gate_fwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(dtype, "mu_gate_fwd", (mu_gate_fwd_kernel<T><<<grid_for(n), 256, 0, st>>>(B, C, T_, (const T*)pre,
+                                                                                    (const T*)h, (T*)out)));
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_mu_gate_bwd(int dtype, int B, int C, int T_, const void* pre, const void* h, const void* dout,
+                                  void* dpre, void* dh, void* stream) {
+  const long long n = (long long)B * C * T_;
+  if (n == 0) return 0;
+  WNB_CHECK_ARG(pre && h && dout && dpre && dh, "mu_gate_bwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(dtype, "mu_gate_bwd", (mu_gate_bwd_kernel<T><<<grid_for(n), 256, 0, st>>>(
+                                      B, C, T_, (const T*)pre, (const T*)h, (const T*)dout, (T*)dpre, (T*)dh)));
   WNB_LAUNCH_OK();
   return 0;
 }

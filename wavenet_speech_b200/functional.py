@@ -382,6 +382,39 @@ def gated_activation(a, b):
     return _Gate.apply(a, b)
 
 
+class _MUGate(torch.autograd.Function):
+    """g1 * tanh(g2 * h + g3 * u) from the four stacked pre-activations (reference block.py:213-220)."""
+
+    @staticmethod
+    def forward(ctx, pre, h):
+        from . import _lib
+        pre, h = pre.contiguous(), h.contiguous()
+        B, C, T = h.shape
+        out = torch.empty_like(h)
+        _lib.call("wnb200_mu_gate_fwd", ops._dt(h), B, C, T, ops._p(pre), ops._p(h), ops._p(out), ops._stream())
+        ctx.save_for_backward(pre, h)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from . import _lib
+        pre, h = ctx.saved_tensors
+        B, C, T = h.shape
+        dpre, dh = torch.empty_like(pre), torch.empty_like(h)
+        _lib.call("wnb200_mu_gate_bwd", ops._dt(h), B, C, T, ops._p(pre), ops._p(h), ops._p(dout.contiguous()),
+                  ops._p(dpre), ops._p(dh), ops._stream())
+        return dpre, dh
+
+
+def multiplicative_unit(h, convs, offsets):
+    """MultiplicativeUnit.forward: ONE tap-sum launch for the four causal convolutions (their filters stacked on
+    the output-channel axis) + one gate launch.  convs = (gate1, gate2, gate3, update) nn.Conv1d holders."""
+    w = torch.cat([c.weight for c in convs], 0)
+    b = torch.cat([c.bias for c in convs], 0)
+    pre = conv_taps(h, w, b, offsets)
+    return _MUGate.apply(pre, h)
+
+
 class _Positions(torch.autograd.Function):
     """out + hardtanh(w * t + b) (reference raw_ctcnet.py:131-135).  Parameter gradients of the
     position layer are not propagated (the reference never trains with positions=True)."""
