@@ -302,6 +302,18 @@ int wnb200_mu_gate_fwd(int dtype, int B, int C, int T, const void* pre, const vo
 int wnb200_mu_gate_bwd(int dtype, int B, int C, int T, const void* pre, const void* h, const void* dout, void* dpre,
                        void* dh, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * On-device synthetic pore-model signal (utils/raw_signal_generator.py:77-118,189-203; utils/pore_model.py:58-96).
+ * siggen_raw: per read, `nbases` bases ~ U{1..4} -> 5-mer ids -> samples per k-mer max(1, int(Gamma(2.461964,
+ * 1/587.2858) * 800)) -> T picoamp samples mean[k] + stdv[k] * z.  Outputs the draws too: bases int32 [B, nbases],
+ * reps int32 [B, nbases-4], z fp32 [B, T] (optional), n_used int32 [B] = bases covered by the T samples (the CTC
+ * labels are bases[2 : 2 + n_used]; -1 if nbases was too small: retry with more), sig fp32 [B, T].
+ * siggen_onehot: per read mu-law quantisation to `levels` and one-hot NCL [B, levels, T]; lev_out int64 [B, T] optional. */
+int wnb200_siggen_raw(int B, int T, int nbases, uint64_t seed, const float* means, const float* stdvs, int32_t* bases,
+                      int32_t* reps, int32_t* n_used, float* z, float* sig, void* stream);
+int wnb200_siggen_onehot(int dtype, int B, int T, int levels, const float* sig, void* onehot, int64_t* lev_out,
+                         void* stream);
+
 /* y = bf16(LeakyReLU_0.01(x)), n a multiple of 4: turns the fp32 skip sum into the head's input
  * (first LeakyReLU of output_stack, wavenet.py:67). */
 int wnb200_leaky_to_bf16(int64_t n, const float* x, void* y, void* stream);

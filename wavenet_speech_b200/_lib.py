@@ -98,6 +98,9 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p],
     "wnb200_mu_gate_fwd": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_mu_gate_bwd": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_siggen_raw": [c_int, c_int, c_int, ctypes.c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                          c_void_p, c_void_p],
+    "wnb200_siggen_onehot": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_leaky_to_bf16": [c_int64, c_void_p, c_void_p, c_void_p],
     "wnb200_ncl_to_nlc_bf16": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "wnb200_nlc_to_ncl": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],

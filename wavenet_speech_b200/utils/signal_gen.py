@@ -104,3 +104,49 @@ def one_hot(levels, num_levels=256, dtype=np.float32):
     out = np.zeros((B, num_levels, T), dtype=dtype)
     out[np.arange(B)[:, None], levels, np.arange(T)[None, :]] = 1
     return out
+
+
+# ------------------------------------------------------------------------------------------------ on the device
+def device_raw_batch(B, T, seed=1234, device="cuda", return_draws=False):
+    """Same generator on the GPU (csrc/siggen.cu): -> (sig fp32 (B, 1, T) in pA, labels: list of int64 tensors with
+    values 1..4).  With return_draws also the random draws (bases, reps, z) for an exact check against the numpy
+    restatement above."""
+    import torch
+
+    from .. import _lib, ops
+    ops.check_device()
+    means, stdvs = load_pore_model()
+    dev = torch.device(device)
+    m, s = torch.from_numpy(means.copy()).to(dev), torch.from_numpy(stdvs.copy()).to(dev)
+    nb = int(T / 2.5) + 64
+    while True:
+        bases = torch.empty((B, nb), dtype=torch.int32, device=dev)
+        reps = torch.empty((B, nb - 4), dtype=torch.int32, device=dev)
+        n_used = torch.empty((B,), dtype=torch.int32, device=dev)
+        z = torch.empty((B, T), dtype=torch.float32, device=dev) if return_draws else None
+        sig = torch.empty((B, T), dtype=torch.float32, device=dev)
+        _lib.call("wnb200_siggen_raw", B, T, nb, int(seed), ops._p(m), ops._p(s), ops._p(bases), ops._p(reps),
+                  ops._p(n_used), ops._p(z), ops._p(sig), ops._stream())
+        nu = n_used.cpu()
+        if int(nu.min()) >= 0:
+            break
+        nb *= 2
+    labels = [bases[b, 2:2 + int(nu[b])].long() for b in range(B)]
+    if return_draws:
+        return sig.unsqueeze(1), labels, (bases, reps, z)
+    return sig.unsqueeze(1), labels
+
+
+def device_one_hot(sig, num_levels=256, dtype=None, return_levels=False):
+    """(B, 1, T) or (B, T) fp32 pA signal on the GPU -> one-hot (B, num_levels, T) of its per-read mu-law levels."""
+    import torch
+
+    from .. import _lib, ops
+    x = sig.reshape(sig.shape[0], -1).float().contiguous()
+    B, T = x.shape
+    dtype = dtype or torch.bfloat16
+    oh = torch.empty((B, num_levels, T), dtype=dtype, device=x.device)
+    lev = torch.empty((B, T), dtype=torch.int64, device=x.device) if return_levels else None
+    _lib.call("wnb200_siggen_onehot", ops._DT[dtype], B, T, num_levels, ops._p(x), ops._p(oh), ops._p(lev),
+              ops._stream())
+    return (oh, lev) if return_levels else oh
