@@ -296,3 +296,35 @@ def test_train_step_api_reduces_the_loss():
         first = float(joint) if first is None else first
         last = float(joint)
     assert last < first, (first, last)
+
+
+@pytest.mark.parametrize("T,B", [(1, 1), (3, 2), (129, 1)])
+def test_tc_paths_on_tiny_reads(T, B):
+    """Reads shorter than one 128-frame tile (TMA boxes larger than the tensor) through inference and training."""
+    torch.manual_seed(T)
+    C = 128
+    layers = [(C, C, 2, d) for d in (1, 2, 512)]
+    net = W.WaveNet(C, 2, layers, C, softmax=False)
+    sd = {k: r16(v) for k, v in net.state_dict().items()}
+    net.load_state_dict(sd)
+    x = r16(torch.randn(B, C, T))
+    ref = O.wavenet_forward(sd, x, layers, softmax=False)
+    net = net.cuda()
+    with torch.no_grad():
+        y = net(x.cuda().bfloat16())
+    assert y.shape == ref.shape and G.rel_linf(y.float().cpu(), ref) <= 2e-2
+    xg = x.cuda().bfloat16().requires_grad_(True)
+    yt = net(xg)
+    assert G.rel_linf(yt.float().cpu(), ref) <= 2e-2
+    yt.float().sum().backward()
+    torch.cuda.synchronize()
+    assert xg.grad is not None and torch.isfinite(xg.grad.float()).all()
+    assert all(p.grad is None or torch.isfinite(p.grad).all() for p in net.parameters())
+    if T >= 3:
+        cn = W.WaveNetClassifier(C, 5, [(C, C, 2, 1)], C, pool_kernel_size=3, softmax=False)
+        csd = {k: r16(v) for k, v in cn.state_dict().items()}
+        cn.load_state_dict(csd)
+        cref = O.classifier_forward(csd, x, [(C, C, 2, 1)], pool_kernel_size=3, softmax=False)
+        ct = cn.cuda()(x.cuda().bfloat16().requires_grad_(True))
+        assert ct.shape == cref.shape and G.rel_linf(ct.float().cpu(), cref) <= 2e-2
+        ct.float().sum().backward()
