@@ -58,6 +58,13 @@ lse = ops.xent_fwd(x_ncl, tgt)[1]
 gs = torch.ones(1, device="cuda")
 report("xent_bwd NCL bf16", 4 * n + 12 * B * T, lambda: ops.xent_bwd(x_ncl, tgt, lse, gs))
 report("argmax_channels NCL bf16", 2 * n + 8 * B * T, lambda: ops.argmax_channels(x_ncl))
+# odd T (the train step works on T-1 = 16383 frames): rows are not 16-byte aligned -> element-wise tile path
+xo, tgo = x_ncl[:, :, :T - 1].contiguous(), tgt[:, :T - 1].contiguous()
+no = xo.numel()
+report("xent_fwd NCL bf16, T = 16383 (unaligned rows)", 2 * no + 16 * B * (T - 1), lambda: ops.xent_fwd(xo, tgo))
+lseo = ops.xent_fwd(xo, tgo)[1]
+report("xent_bwd NCL bf16, T = 16383 (unaligned rows)", 4 * no + 12 * B * (T - 1), lambda: ops.xent_bwd(xo, tgo, lseo, gs))
+report("argmax_channels NCL bf16, T = 16383 (unaligned rows)", 2 * no + 8 * B * (T - 1), lambda: ops.argmax_channels(xo))
 h0 = torch.empty((B, T // 3, C), dtype=bf, device="cuda")
 report("avgpool(3) NCL -> NLC bf16 (B2)", 2 * n + 2 * (n // 3),
        lambda: _lib.call("wnb200_avgpool_ncl_to_nlc_bf16", 1, B, C, T, 3, ops._p(x_ncl), ops._p(h0), ops._stream()))

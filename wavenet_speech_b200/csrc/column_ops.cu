@@ -64,9 +64,21 @@ __device__ __forceinline__ void tile_load(T* s, int stride, const T* xb, int C, 
         if (off[u] >= 0) *reinterpret_cast<uint4*>(s + off[u]) = val[u];
     }
   } else {
-    for (int i = threadIdx.x; i < C * TT; i += CT_THREADS) {
-      const int c = i / TT, tt = i - c * TT;
-      s[c * stride + tt] = (t0 + tt < Tn) ? xb[(long long)c * Tn + t0 + tt] : from_f32<T>(0.f);
+    // rows that are not 16-byte aligned (odd T): element loads, lane <-> consecutive frames (coalesced), TT is a power
+    // of two, four loads in flight per thread
+    const int sh = 31 - __clz(TT), total = C * TT;
+    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * CT_THREADS) {
+      T val[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * CT_THREADS, c = i >> sh, tt = i & (TT - 1);
+        val[u] = (i < total && t0 + tt < Tn) ? xb[(long long)c * Tn + t0 + tt] : from_f32<T>(0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * CT_THREADS;
+        if (i < total) s[(i >> sh) * stride + (i & (TT - 1))] = val[u];
+      }
     }
   }
 }
@@ -87,8 +99,9 @@ __device__ __forceinline__ void tile_store(T* yb, int C, int Tn, int t0, int TT,
       *reinterpret_cast<uint4*>(yb + (long long)c * Tn + t) = val;
     }
   } else {
+    const int sh = 31 - __clz(TT);
     for (int i = threadIdx.x; i < C * TT; i += CT_THREADS) {
-      const int c = i / TT, tt = i - c * TT;
+      const int c = i >> sh, tt = i & (TT - 1);
       if (t0 + tt < Tn) yb[(long long)c * Tn + t0 + tt] = from_f32<T>(f(c, tt));
     }
   }
