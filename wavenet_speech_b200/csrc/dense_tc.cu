@@ -39,7 +39,8 @@ constexpr int DN_STAGE = 2 * DN_ABYTES;        // A block + up to 128 weight row
 constexpr int DN_NSTAGE = 5;
 constexpr int DN_STAGING = 2 * DN_ABYTES;
 constexpr int DN_SCRATCH = 2 * RB_TILE * 8;    // softmax partials (max, sum) per column half
-constexpr int DN_SMEM = DN_NSTAGE * DN_STAGE + DN_STAGING + DN_SCRATCH + 1024 + 256;
+constexpr int DN_BIAS = 256 * 4;                // head: bias (x log2 e under softmax) staged once per CTA
+constexpr int DN_SMEM = DN_NSTAGE * DN_STAGE + DN_STAGING + DN_SCRATCH + DN_BIAS + 1024 + 256;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DN_THREADS, 1)
 dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_x2,
@@ -49,7 +50,8 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t stg_base = smem_base + DN_NSTAGE * DN_STAGE;
   const uint32_t scr_base = stg_base + DN_STAGING;
-  const uint32_t bar_base = scr_base + DN_SCRATCH;
+  const uint32_t sbias_base = scr_base + DN_SCRATCH;
+  const uint32_t bar_base = sbias_base + DN_BIAS;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (DN_NSTAGE + s); };
   const uint32_t bb = bar_base + 8u * (2 * DN_NSTAGE);
@@ -149,6 +151,12 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     const bool issuer = (threadIdx.x == 64);
     const int sw = row & 7;
     float* scratch = reinterpret_cast<float*>(smem_gen + (scr_base - smem_base));
+    float* sbias = reinterpret_cast<float*>(smem_gen + (sbias_base - smem_base));
+    if (p.mode == 1) {                           // head: bias (pre-scaled by log2 e under softmax), zero past n_out
+      const int t256 = threadIdx.x - 64;
+      if (t256 < p.N) sbias[t256] = (t256 < p.n_out) ? __ldg(p.bias + t256) * (p.softmax ? 1.4426950408889634f : 1.f) : 0.f;
+      epi_bar();
+    }
     uint32_t nchunk = 0;
     int it = 0;
     for (int pt = pair; pt < p.num_tiles; pt += npairs, ++it) {
@@ -198,31 +206,38 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         }
       } else {
         // -------- HEAD: optional channel softmax, output NCL --------
+        // log2 domain: z = acc * log2(e) + bias * log2(e) (bias pre-scaled in shared memory), softmax = 2^(z - max) / sum.
+        // Two cheap sweeps over the TMEM row (max, then sum) instead of an online update with a branch per element.
+        constexpr float L2E = 1.4426950408889634f;
+        const float sc = p.softmax ? L2E : 1.f;
         float mx = 0.f, inv = 1.f;
         if (p.softmax) {
-          float m = -INFINITY, s = 0.f;
           const int cbeg = h * (p.N / 2);
           const int cend = (cbeg + p.N / 2) < p.n_out ? (cbeg + p.N / 2) : p.n_out;   // this warp's valid columns
+          float m = -INFINITY;
           for (int c0 = cbeg; c0 < cend; c0 += 16) {
             float a[16];
             tmem_ld16(tacc + c0, a);
             tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (c0 + i < cend) {
-                const float v = a[i] + __ldg(p.bias + c0 + i);
-                if (v > m) { s *= __expf(m - v); m = v; }
-                s += __expf(v - m);
-              }
-            }
+            for (int i = 0; i < 16; ++i)
+              if (c0 + i < cend) m = fmaxf(m, fmaf(a[i], L2E, sbias[c0 + i]));
           }
           scratch[(h * RB_TILE + row) * 2] = m;
-          scratch[(h * RB_TILE + row) * 2 + 1] = s;
           epi_bar();
-          const float m2 = scratch[((h ^ 1) * RB_TILE + row) * 2], s2 = scratch[((h ^ 1) * RB_TILE + row) * 2 + 1];
-          mx = fmaxf(m, m2);
-          const float tot = (m == -INFINITY ? 0.f : s * __expf(m - mx)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mx));
-          inv = 1.f / tot;
+          mx = fmaxf(m, scratch[((h ^ 1) * RB_TILE + row) * 2]);
+          float sum = 0.f;
+          for (int c0 = cbeg; c0 < cend; c0 += 16) {
+            float a[16];
+            tmem_ld16(tacc + c0, a);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c0 + i < cend) sum += fast_ex2(fmaf(a[i], L2E, sbias[c0 + i]) - mx);
+          }
+          scratch[(h * RB_TILE + row) * 2 + 1] = sum;
+          epi_bar();
+          inv = 1.f / (sum + scratch[((h ^ 1) * RB_TILE + row) * 2 + 1]);
           epi_bar();      // scratch may be rewritten by the next tile only after everyone has read it
         }
         const int esize = p.out_f32 ? 4 : 2;
@@ -234,10 +249,8 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const int c = col + i;
-            float x = a[i] + ((c < p.n_out) ? __ldg(p.bias + c) : 0.f);
-            if (p.softmax) x = __expf(x - mx) * inv;
-            v[i] = x;
+            const float x = fmaf(a[i], sc, sbias[col + i]);          // columns >= n_out hold zero weights and bias
+            v[i] = p.softmax ? fast_ex2(x - mx) * inv : x;
           }
           if (p.tma_out) {
             const uint32_t boff = (nchunk & 1u) * DN_ABYTES;
