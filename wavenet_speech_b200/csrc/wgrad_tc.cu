@@ -147,14 +147,22 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__
     const bool issuer = (threadIdx.x == 64);
     mbar_wait(acc_full, 0u);
     tc_fence_after();
-    uint8_t* srow = smem_gen + (stg_base - smem_base) + row * 128;
+    // All MMAs have completed (acc_full), so the operand ring is idle: its 12 x 16 KB slots (4 stages x 48 KB) serve
+    // as staging buffers, one per 32-column chunk -- the TMA reduce-adds of up to 12 chunks are in flight while the
+    // next chunks are drained from TMEM (a single staging buffer serialised every chunk behind the previous TMA read:
+    // ~24 us per launch for the 256 x 512 tile).
+    constexpr int NSLOT = WG_NSTAGE * WG_STAGE / WG_STAGING;      // 12
     for (int c = 0; c < p.nsrc * p.N / 32; ++c) {
       float a[32];
       tmem_ld16(tmem_base + lane_off + c * 32, a);
       tmem_ld16(tmem_base + lane_off + c * 32 + 16, a + 16);
       tmem_wait_ld();
-      if (issuer) bulk_wait_read0();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t slot = smem_base + (uint32_t)(c % NSLOT) * WG_STAGING;
+      if (c >= NSLOT) {                                           // the slot's previous reduce-add must have read it
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NSLOT - 1) : "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      uint8_t* srow = smem_gen + (slot - smem_base) + row * 128;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         *reinterpret_cast<float4*>(srow + ((j ^ sw) << 4)) = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
@@ -163,7 +171,7 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__
       if (issuer) {
         asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                          reinterpret_cast<uint64_t>(&map_dw)),
-                     "r"(stg_base), "r"(c * 32), "r"((int)rank * 128)
+                     "r"(slot), "r"(c * 32), "r"((int)rank * 128)
                      : "memory");
         bulk_commit();
       }
