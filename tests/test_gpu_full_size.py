@@ -5,7 +5,7 @@ Tolerance at FULL DEPTH.  The north_star's bf16 bound (2e-2 on the logits) is me
 about ten blocks (tests/test_gpu_tc.py); with the reference's own initialisation the residual path is a random
 nn.Linear, perturbations grow ~1.15x per block, and at 16-20 blocks ANY bf16 evaluation is 5e-2 to 8e-2 from the
 fp32 one -- PyTorch's own bf16 evaluation of the reference's modules included (SURVEY section 7, hard part 1;
-scripts/diag_bf16_depth.py).  So the full-depth slices are held to the envelope that evaluation defines: the oracle
+tests/tools/diag_bf16_depth.py).  So the full-depth slices are held to the envelope that evaluation defines: the oracle
 run in bf16 on the CPU (same weights, same input) against the oracle in fp32."""
 import pytest
 import torch

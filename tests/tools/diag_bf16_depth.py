@@ -1,7 +1,7 @@
 """bf16 error vs depth: tensor-core path vs torch's own bf16 evaluation (CPU), both against the fp32 oracle on the
 same bf16-rounded weights/input (diagnostic for the bf16 tolerance; SURVEY 7 hard part 1)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import wavenet_speech_b200 as W
 from oracle import wavenet_oracle as O

@@ -1,7 +1,7 @@
 """Layer-by-layer fp32 error growth of the CUDA path vs the fp32 oracle, both measured against an fp64 oracle
 (diagnostic for the deep-stack tolerance; run on the GPU box)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import wavenet_speech_b200 as W
 from wavenet_speech_b200 import functional as WF
