@@ -77,7 +77,7 @@ __global__ void ctc_logprobs_kernel(int B, int L, int Tn, const T* act, long lon
 
 // grid (B, 2): blockIdx.y = 0 alpha, 1 beta.  Each thread owns NP (blank, label) state pairs j = tid + i * blockDim:
 // states 2j and 2j+1 (the last pair is the final blank alone).  A pair costs 5 MUFU ops per frame.
-// Dynamic smem: 2 * (Smax + 5) floats (state vectors with guards) + 2 * CTC_MAX_L (log-probs) + 32 (maxima).
+// Dynamic smem: 2 * (Smax + 7) floats (state vectors with guards) + 2 * CTC_MAX_L (log-probs) + 32 (maxima).
 template <int NP>
 __global__ void __launch_bounds__(1024)
 ctc_alpha_beta_kernel(int L, int Tn, int Smax, const float* __restrict__ lp, const int* __restrict__ labels,
@@ -89,9 +89,9 @@ ctc_alpha_beta_kernel(int L, int Tn, int Smax, const float* __restrict__ lp, con
   const int S = 2 * len + 1;
   const int Ta = act_len ? min(act_len[b], Tn) : Tn;
   const int* lab = labels + lab_off[b];
-  const int W = Smax + 5;
-  float* buf0 = sm + 1;                       // states -1 .. Smax+3 addressable; guards hold CTC_NEG
-  float* buf1 = sm + W + 1;
+  const int W = Smax + 7;                     // even: both buffers keep their (blank, label) pairs 8-byte aligned
+  float* buf0 = sm + 2;                       // states -2 .. Smax+4 addressable; guards hold CTC_NEG
+  float* buf1 = sm + W + 2;
   float* lpb = sm + 2 * W;                    // [2][CTC_MAX_L]
   float* red = lpb + 2 * CTC_MAX_L;           // [32] per-warp maxima
   double* co = coff + ((long long)dir * gridDim.x + b) * Tn;
@@ -120,7 +120,7 @@ ctc_alpha_beta_kernel(int L, int Tn, int Smax, const float* __restrict__ lp, con
       else skip[i] = j + 1 < len && lab[j + 1] != cls[i];                 // beta:  2j+1 <- 2j+3
     }
   }
-  for (int s = tid - 1; s < W - 1; s += nt) { buf0[s] = CTC_NEG; buf1[s] = CTC_NEG; }
+  for (int s = tid - 2; s < W - 2; s += nt) { buf0[s] = CTC_NEG; buf1[s] = CTC_NEG; }
   const int tfirst = dir == 0 ? 0 : Ta - 1, tstep = dir == 0 ? 1 : -1;
   if (tid < L) lpb[tid] = lpr[(long long)tfirst * L + tid];
   __syncthreads();
@@ -131,21 +131,25 @@ ctc_alpha_beta_kernel(int L, int Tn, int Smax, const float* __restrict__ lp, con
       const int s0 = 2 * j, s1 = 2 * j + 1;
       const float v0 = (dir == 0 ? s0 < 2 : s0 >= S - 2) ? lpb[0] : CTC_NEG;
       const float v1 = (haslab[i] && (dir == 0 ? s1 < 2 : s1 >= S - 2)) ? lpb[cls[i]] : CTC_NEG;
-      buf0[s0] = v0;
-      if (haslab[i]) buf0[s1] = v1;
+      *reinterpret_cast<float2*>(buf0 + s0) = make_float2(v0, v1);      // v1 = NEG lands on the guard after the last state
       *reinterpret_cast<float2*>(out + (long long)tfirst * SP + s0) = make_float2(v0, v1);
     }
   }
   if (tid == 0) co[tfirst] = 0.0;
+  // log-probs of the NEXT frame are fetched one iteration ahead (an L2 round trip per frame otherwise sits in front
+  // of the barrier: the load was issued and consumed in the same iteration)
   float nxt = 0.f;
+  if (tid < L && Ta > 1) nxt = lpr[(long long)(tfirst + tstep) * L + tid];
   double C = 0.0;                             // every thread tracks the same offset
   for (int k = 1; k < Ta; ++k) {
     const int t = tfirst + k * tstep;
-    if (tid < L) nxt = lpr[(long long)t * L + tid];
     const float* prev = (k & 1) ? buf0 : buf1;
     float* cur = (k & 1) ? buf1 : buf0;
     float* lpc = lpb + (k & 1) * CTC_MAX_L;
-    if (tid < L) lpc[tid] = nxt;
+    if (tid < L) {
+      lpc[tid] = nxt;
+      if (k + 1 < Ta) nxt = lpr[(long long)(t + tstep) * L + tid];
+    }
     __syncthreads();
     // band of useful pairs at this frame and at the previous one (see the header)
     const int jlo = max(0, len - (Ta - t)), jhi = min(len, t);
@@ -178,18 +182,19 @@ ctc_alpha_beta_kernel(int L, int Tn, int Smax, const float* __restrict__ lp, con
         const int s0 = 2 * j;
         float r0, r1;
         if (dir == 0) {
-          const float p0 = prev[s0 - 1], p1 = prev[s0], p2 = prev[s0 + 1];
-          r0 = lse2(p1, p0) + lpblank;
-          r1 = lse3(p2, p1, skip[i] ? p0 : CTC_NEG) + (lpc[cls[i]] - m);
+          const float p0 = prev[s0 - 1];
+          const float2 p12 = *reinterpret_cast<const float2*>(prev + s0);
+          r0 = lse2(p12.x, p0) + lpblank;
+          r1 = lse3(p12.y, p12.x, skip[i] ? p0 : CTC_NEG) + (lpc[cls[i]] - m);
         } else {
-          const float q0 = prev[s0], q1 = prev[s0 + 1], q2 = prev[s0 + 2], q3 = prev[s0 + 3];
-          r0 = lse2(q0, q1) + lpblank;
-          r1 = lse3(q1, q2, skip[i] ? q3 : CTC_NEG) + (lpc[cls[i]] - m);
+          const float2 q01 = *reinterpret_cast<const float2*>(prev + s0), q23 = *reinterpret_cast<const float2*>(prev + s0 + 2);
+          r0 = lse2(q01.x, q01.y) + lpblank;
+          r1 = lse3(q01.y, q23.x, skip[i] ? q23.y : CTC_NEG) + (lpc[cls[i]] - m);
         }
         if (!haslab[i]) r1 = CTC_NEG;
-        cur[s0] = r0;
-        if (haslab[i]) cur[s0 + 1] = r1;
-        *reinterpret_cast<float2*>(orow + s0) = make_float2(r0, r1);
+        const float2 rr = make_float2(r0, r1);
+        *reinterpret_cast<float2*>(cur + s0) = rr;
+        *reinterpret_cast<float2*>(orow + s0) = rr;
       }
     }
   }
@@ -239,12 +244,35 @@ ctc_grad_kernel(int B, int L, int Tn, int Smax, const float* __restrict__ lp, co
   float blank = 0.f;
   const float lp0 = lpt[0];
   const int jlo = max(0, len - (Ta - t)), jhi = min(len, t);
-  for (int j = jlo + lane; j <= jhi; j += 32) {
-    const float2 av = a[j], bv = be[j];
-    blank += ex2f(av.x + bv.x - lp0 + n);
-    if (j < len) {
-      const int c = lab[j];
-      atomicAdd(&acc[warp][c], ex2f(av.y + bv.y - lpt[c] + n));
+  if (L <= 8) {
+    // few classes (nucleotides): per-lane register accumulators, one warp reduction per class at the end
+    // (shared-memory atomics from 32 lanes onto 4 addresses serialise)
+    float occ[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = jlo + lane; j <= jhi; j += 32) {
+      const float2 av = a[j], bv = be[j];
+      blank += ex2f(av.x + bv.x - lp0 + n);
+      if (j < len) {
+        const int c = lab[j];
+        const float wl = ex2f(av.y + bv.y - lpt[c] + n);
+#pragma unroll
+        for (int q = 1; q < 8; ++q) occ[q] += (c == q) ? wl : 0.f;
+      }
+    }
+#pragma unroll
+    for (int q = 1; q < 8; ++q) {
+      float v = occ[q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && q < L) acc[warp][q] = v;
+    }
+  } else {
+    for (int j = jlo + lane; j <= jhi; j += 32) {
+      const float2 av = a[j], bv = be[j];
+      blank += ex2f(av.x + bv.x - lp0 + n);
+      if (j < len) {
+        const int c = lab[j];
+        atomicAdd(&acc[warp][c], ex2f(av.y + bv.y - lpt[c] + n));
+      }
     }
   }
 #pragma unroll
@@ -302,7 +330,7 @@ extern "C" int wnb200_ctc_fwd(int dtype, int B, int L, int T_, int max_label_len
   int threads = ((pairs + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
   if (threads < 64) threads = 64;
-  const size_t smem = sizeof(float) * (2 * ((size_t)Smax + 5) + 2 * CTC_MAX_L + 32);
+  const size_t smem = sizeof(float) * (2 * ((size_t)Smax + 7) + 2 * CTC_MAX_L + 32);
   const int np = (pairs + threads - 1) / threads;
 #define CTC_LAUNCH(NP)                                                                                              \
   do {                                                                                                              \
