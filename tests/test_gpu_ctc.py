@@ -27,6 +27,9 @@ def test_reference_known_answers():
     (4, 8, 1500, [700, 300, 512, 1], "bct", torch.float32),        # > 1024 states: several states per thread
     (2, 5, 200, [60, 40], "bct", torch.bfloat16),
     (2, 40, 64, [20, 9], "tbc", torch.float32),
+    (3, 5, 400, [150, 0, 1], "bct", torch.float32),                # an empty and a 1-label read beside a long one
+    (2, 5, 200, [129, 64], "bct", torch.float32),
+    (40, 5, 300, [90] * 40, "bct", torch.float32),                 # more reads than fit one wave of the grad kernel's first blocks
 ])
 def test_ctc_matches_oracle(B, L, T, lens, layout, dtype):
     torch.manual_seed(B * 100 + T)
