@@ -431,9 +431,73 @@ struct RegTile {
   __device__ __forceinline__ float get(int k, int i) const { return to_f32<T>(reinterpret_cast<const T*>(&raw[k])[i]); }
 };
 
+// One tile per CTA: tile = blockIdx.x.  (A persistent variant -- 2 CTAs per SM walking tiles with the next tile's
+// loads issued ahead of the current tile's reduction -- measured SLOWER, 0.35-0.47 of the copy bandwidth against
+// 0.38-0.57: at 2 bytes per element these reductions sit on the issue / MUFU rate, ~6 instructions and one ex2 per
+// element against a budget of ~5 per element at HBM speed, and many short CTAs overlap better than a few long ones.)
+template <typename T, int KC, typename Body>
+__device__ __forceinline__ void reg_tiles(int C, int Tn, int tiles_per_read, int ntiles, const T* x, uint32_t fill,
+                                          Body body) {
+  using RT = RegTile<T, KC>;
+  const int tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  const int b = tile / tiles_per_read, t0 = (tile - b * tiles_per_read) * RT::TT;
+  RT r;
+  r.load(x + (long long)b * C * Tn, C, Tn, t0, fill);
+  body(r, b, t0);
+}
+
 template <typename T> struct NegInf;
 template <> struct NegInf<float> { static constexpr uint32_t bits = 0xFF800000u; };
 template <> struct NegInf<__nv_bfloat16> { static constexpr uint32_t bits = 0xFF80FF80u; };
+
+// exp(x - m) with one FFMA feeding the ex2: e = 2^(x * log2e - m * log2e); `ml` = m * log2e is formed once per frame.
+// bf16 storage only (ex2.approx, like exp_t<bf16>); fp32 storage keeps the exact expf for its 1e-5 parity.
+template <typename T>
+struct ExpSub {
+  static __device__ __forceinline__ float scale(float m) { return m; }
+  static __device__ __forceinline__ float eval(float x, float ml) { return expf(x - ml); }
+};
+template <>
+struct ExpSub<__nv_bfloat16> {
+  static __device__ __forceinline__ float scale(float m) { return m * 1.4426950408889634f; }
+  static __device__ __forceinline__ float eval(float x, float ml) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaf(x, 1.4426950408889634f, -ml)));
+    return y;
+  }
+};
+
+// per-frame maximum over this thread's KC channels; bf16 tiles compare packed pairs (max is exact in any format)
+template <typename T, int KC>
+__device__ __forceinline__ void tile_max(const RegTile<T, KC>& r, float (&m)[RegTile<T, KC>::V]) {
+  constexpr int V = RegTile<T, KC>::V;
+#pragma unroll
+  for (int i = 0; i < V; ++i) m[i] = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < KC; ++k)
+#pragma unroll
+    for (int i = 0; i < V; ++i) m[i] = fmaxf(m[i], r.get(k, i));
+}
+template <int KC>
+__device__ __forceinline__ void tile_max(const RegTile<__nv_bfloat16, KC>& r, float (&m)[8]) {
+  __nv_bfloat162 a[4];
+  const __nv_bfloat162* p0 = reinterpret_cast<const __nv_bfloat162*>(&r.raw[0]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) a[j] = p0[j];
+#pragma unroll
+  for (int k = 1; k < KC; ++k) {
+    const __nv_bfloat162* pk = reinterpret_cast<const __nv_bfloat162*>(&r.raw[k]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] = __hmax2(a[j], pk[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(a[j]);
+    m[2 * j] = f.x;
+    m[2 * j + 1] = f.y;
+  }
+}
 
 // p[i] (one partial per frame of this thread) -> total over all channels.  Two shuffle steps merge the four channel
 // groups of a warp (lanes v, v+8, v+16, v+24), the eight warps meet in shared memory (red: 8 x TT floats), one thread
@@ -471,103 +535,139 @@ template <typename T, int KC>
 __device__ __forceinline__ void softmax_stats(const RegTile<T, KC>& r, float (&m)[RegTile<T, KC>::V],
                                               float (&s)[RegTile<T, KC>::V], float* red, float* fin) {
   constexpr int V = RegTile<T, KC>::V;
-#pragma unroll
-  for (int i = 0; i < V; ++i) m[i] = -INFINITY;
-#pragma unroll
-  for (int k = 0; k < KC; ++k)
-#pragma unroll
-    for (int i = 0; i < V; ++i) m[i] = fmaxf(m[i], r.get(k, i));
+  tile_max(r, m);
   frames_combine<V, true>(m, red, fin, r.v);
+  float ml[V];
 #pragma unroll
-  for (int i = 0; i < V; ++i) s[i] = 0.f;
+  for (int i = 0; i < V; ++i) { s[i] = 0.f; ml[i] = ExpSub<T>::scale(m[i]); }
 #pragma unroll
   for (int k = 0; k < KC; ++k)
 #pragma unroll
-    for (int i = 0; i < V; ++i) s[i] += exp_t<T>(r.get(k, i) - m[i]);
+    for (int i = 0; i < V; ++i) s[i] += ExpSub<T>::eval(r.get(k, i), ml[i]);
   frames_combine<V, false>(s, red + 8 * 8 * V, fin + 8 * V, r.v);
 }
 
 template <typename T, int KC>
 __global__ void __launch_bounds__(CT_THREADS, 2)
-softmax_fwd_reg(int C, int Tn, int tiles_per_read, const T* x, T* y, int log_mode) {
+softmax_fwd_reg(int C, int Tn, int tiles_per_read, int ntiles, const T* x, T* y, int log_mode) {
   using RT = RegTile<T, KC>;
   constexpr int V = RT::V, TT = RT::TT;
   __shared__ float red[16 * TT], fin[2 * TT];
-  const int b = blockIdx.x / tiles_per_read, t0 = (blockIdx.x - b * tiles_per_read) * TT;
-  const long long rb = (long long)b * C * Tn;
-  RT r;
-  r.load(x + rb, C, Tn, t0, NegInf<T>::bits);
-  float m[V], sum[V];
-  softmax_stats<T, KC>(r, m, sum, red, fin);
-  if (!r.tok) return;
+  reg_tiles<T, KC>(C, Tn, tiles_per_read, ntiles, x, NegInf<T>::bits, [&](const RT& r, int b, int t0) {
+    const long long rb = (long long)b * C * Tn;
+    float m[V], sum[V];
+    softmax_stats<T, KC>(r, m, sum, red, fin);
+    if (!r.tok) return;
 #pragma unroll
-  for (int i = 0; i < V; ++i) sum[i] = log_mode ? m[i] + logf(sum[i]) : 1.f / sum[i];
+    for (int i = 0; i < V; ++i) {
+      sum[i] = log_mode ? m[i] + logf(sum[i]) : 1.f / sum[i];
+      m[i] = ExpSub<T>::scale(m[i]);
+    }
 #pragma unroll
-  for (int k = 0; k < KC; ++k) {
-    if (!r.cok[k]) continue;
-    uint4 val;
-    T* o = reinterpret_cast<T*>(&val);
+    for (int k = 0; k < KC; ++k) {
+      if (!r.cok[k]) continue;
+      uint4 val;
+      T* o = reinterpret_cast<T*>(&val);
 #pragma unroll
-    for (int i = 0; i < V; ++i)
-      o[i] = from_f32<T>(log_mode ? r.get(k, i) - sum[i] : exp_t<T>(r.get(k, i) - m[i]) * sum[i]);
-    *reinterpret_cast<uint4*>(y + rb + (long long)(r.g + 32 * k) * Tn + t0 + r.v * V) = val;
-  }
+      for (int i = 0; i < V; ++i)
+        o[i] = from_f32<T>(log_mode ? r.get(k, i) - sum[i] : ExpSub<T>::eval(r.get(k, i), m[i]) * sum[i]);
+      *reinterpret_cast<uint4*>(y + rb + (long long)(r.g + 32 * k) * Tn + t0 + r.v * V) = val;
+    }
+  });
 }
 
 template <typename T, int KC>
 __global__ void __launch_bounds__(CT_THREADS, 2)
-xent_fwd_reg(int C, int Tn, int tiles_per_read, const T* x, const long long* target, float* loss_bt, float* lse_out) {
+xent_fwd_reg(int C, int Tn, int tiles_per_read, int ntiles, const T* x, const long long* target, float* loss_bt,
+             float* lse_out) {
   using RT = RegTile<T, KC>;
   constexpr int V = RT::V, TT = RT::TT;
   __shared__ float red[16 * TT], fin[2 * TT], xt[TT];
-  const int b = blockIdx.x / tiles_per_read, t0 = (blockIdx.x - b * tiles_per_read) * TT;
-  const long long rb = (long long)b * C * Tn;
-  RT r;
-  r.load(x + rb, C, Tn, t0, NegInf<T>::bits);
-  __shared__ int tgs[TT];
-  if (threadIdx.x < TT) {
-    const int t = t0 + threadIdx.x;
-    long long tg = t < Tn ? target[(long long)b * Tn + t] : 0;
-    tgs[threadIdx.x] = (int)(tg < 0 ? 0 : (tg >= C ? C - 1 : tg));
-  }
-  float m[V], sum[V];
-#pragma unroll
-  for (int i = 0; i < V; ++i) m[i] = -INFINITY;
-#pragma unroll
-  for (int k = 0; k < KC; ++k)
-#pragma unroll
-    for (int i = 0; i < V; ++i) m[i] = fmaxf(m[i], r.get(k, i));
-  frames_combine<V, true>(m, red, fin, r.v);
-  // the logit of the target class of each of this thread's frames, if this thread holds it (tgs is visible: the
-  // combine above went through two barriers)
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const int tg = tgs[r.v * V + i];
-    if ((tg & 31) == r.g) {
-      const int kq = tg >> 5;
+  reg_tiles<T, KC>(C, Tn, tiles_per_read, ntiles, x, NegInf<T>::bits, [&](const RT& r, int b, int t0) {
+    // the target's logit comes straight from global memory (the line is in L1: this CTA has just loaded it)
+    if (threadIdx.x < TT) {
+      const int t = t0 + threadIdx.x;
       float val = 0.f;
-#pragma unroll
-      for (int k = 0; k < KC; ++k)
-        if (k == kq) val = r.get(k, i);
-      xt[r.v * V + i] = val;
+      if (t < Tn) {
+        long long tg = target[(long long)b * Tn + t];
+        tg = tg < 0 ? 0 : (tg >= C ? C - 1 : tg);
+        val = to_f32<T>(__ldg(x + (long long)b * C * Tn + tg * Tn + t));
+      }
+      xt[threadIdx.x] = val;
     }
-  }
+    float m[V], sum[V];
+    softmax_stats<T, KC>(r, m, sum, red, fin);      // (its barriers also publish xt)
+    if (r.g == 0 && r.tok) {
 #pragma unroll
-  for (int i = 0; i < V; ++i) sum[i] = 0.f;
-#pragma unroll
-  for (int k = 0; k < KC; ++k)
-#pragma unroll
-    for (int i = 0; i < V; ++i) sum[i] += exp_t<T>(r.get(k, i) - m[i]);
-  frames_combine<V, false>(sum, red + 8 * 8 * V, fin + 8 * V, r.v);
-  if (r.g == 0 && r.tok) {
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const float lse = m[i] + logf(sum[i]);
-      const long long col = (long long)b * Tn + t0 + r.v * V + i;
-      loss_bt[col] = lse - xt[r.v * V + i];
-      lse_out[col] = lse;
+      for (int i = 0; i < V; ++i) {
+        const float lse = m[i] + logf(sum[i]);
+        const long long col = (long long)b * Tn + t0 + r.v * V + i;
+        loss_bt[col] = lse - xt[r.v * V + i];
+        lse_out[col] = lse;
+      }
     }
+  });
+}
+
+// LayerNorm over channels (layernorm.py:25-28: unbiased std, eps added to the std), register tile
+template <typename T, int KC>
+__global__ void __launch_bounds__(CT_THREADS, 2)
+layernorm_fwd_reg(int C, int Tn, int tiles_per_read, int ntiles, const T* x, const float* gamma, const float* beta,
+                  float eps, T* y, float* stats) {
+  using RT = RegTile<T, KC>;
+  constexpr int V = RT::V, TT = RT::TT;
+  __shared__ float red[16 * TT], fin[2 * TT];
+  float gm[KC], bt[KC];
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const int c = (threadIdx.x >> 3) + 32 * k;
+    gm[k] = c < C ? gamma[c] : 0.f;
+    bt[k] = c < C ? beta[c] : 0.f;
   }
+  const float invC = 1.f / (float)C, invC1 = 1.f / (float)(C - 1);
+  reg_tiles<T, KC>(C, Tn, tiles_per_read, ntiles, x, 0u, [&](const RT& r, int b, int t0) {
+    const long long rb = (long long)b * C * Tn;
+    float mean[V], rr[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) mean[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KC; ++k)
+#pragma unroll
+      for (int i = 0; i < V; ++i) mean[i] += r.get(k, i);            // channels >= C were filled with zeros
+    frames_combine<V, false>(mean, red, fin, r.v);
+#pragma unroll
+    for (int i = 0; i < V; ++i) { mean[i] *= invC; rr[i] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      if (!r.cok[k]) continue;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float d = r.get(k, i) - mean[i];
+        rr[i] = fmaf(d, d, rr[i]);
+      }
+    }
+    frames_combine<V, false>(rr, red + 8 * 8 * V, fin + 8 * V, r.v);
+    if (!r.tok) return;
+#pragma unroll
+    for (int i = 0; i < V; ++i) rr[i] = 1.f / (sqrtf(rr[i] * invC1) + eps);
+    if (stats && r.g == 0) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const long long col = (long long)b * Tn + t0 + r.v * V + i;
+        stats[col * 2] = mean[i];
+        stats[col * 2 + 1] = rr[i];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      if (!r.cok[k]) continue;
+      uint4 val;
+      T* o = reinterpret_cast<T*>(&val);
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = from_f32<T>(gm[k] * (r.get(k, i) - mean[i]) * rr[i] + bt[k]);
+      *reinterpret_cast<uint4*>(y + rb + (long long)(r.g + 32 * k) * Tn + t0 + r.v * V) = val;
+    }
+  });
 }
 
 template <typename T, int KC>
@@ -601,45 +701,47 @@ xent_bwd_reg(int C, int Tn, int tiles_per_read, const T* x, const long long* tar
 
 template <typename T, int KC>
 __global__ void __launch_bounds__(CT_THREADS, 2)
-argmax_reg(int C, int Tn, int tiles_per_read, const T* x, long long* out) {
+argmax_reg(int C, int Tn, int tiles_per_read, int ntiles, const T* x, long long* out) {
   using RT = RegTile<T, KC>;
   constexpr int V = RT::V, TT = RT::TT;
-  __shared__ float redv[8 * TT];
-  __shared__ int redc[8 * TT];
-  const int b = blockIdx.x / tiles_per_read, t0 = (blockIdx.x - b * tiles_per_read) * TT;
-  const long long rb = (long long)b * C * Tn;
-  RT r;
-  r.load(x + rb, C, Tn, t0, NegInf<T>::bits);
+  __shared__ float redv[2][8 * TT];              // double-buffered: one barrier per tile
+  __shared__ int redc[2][8 * TT];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int par = 0;
+  reg_tiles<T, KC>(C, Tn, tiles_per_read, ntiles, x, NegInf<T>::bits, [&](const RT& r, int b, int t0) {
+    float* rv = redv[par];
+    int* rc = redc[par];
+    par ^= 1;
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    float m = r.cok[0] ? r.get(0, i) : -INFINITY;
-    int a = r.cok[0] ? r.g : C;                   // ascending channels within a thread: strict > keeps the lowest
+    for (int i = 0; i < V; ++i) {
+      float m = r.cok[0] ? r.get(0, i) : -INFINITY;
+      int a = r.cok[0] ? r.g : C;                   // ascending channels within a thread: strict > keeps the lowest
 #pragma unroll
-    for (int k = 1; k < KC; ++k) {
-      const float val = r.get(k, i);
-      if (r.cok[k] && val > m) { m = val; a = r.g + 32 * k; }
+      for (int k = 1; k < KC; ++k) {
+        const float val = r.get(k, i);
+        if (r.cok[k] && val > m) { m = val; a = r.g + 32 * k; }
+      }
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+        const int a2 = __shfl_xor_sync(0xffffffffu, a, o);
+        if (a2 < C && (a >= C || m2 > m || (m2 == m && a2 < a))) { m = m2; a = a2; }
+      }
+      if (lane < 8) { rv[warp * TT + r.v * V + i] = m; rc[warp * TT + r.v * V + i] = a; }
     }
+    __syncthreads();
+    if (threadIdx.x < TT && t0 + threadIdx.x < Tn) {
+      float M = rv[threadIdx.x];
+      int A = rc[threadIdx.x];
 #pragma unroll
-    for (int o = 8; o <= 16; o <<= 1) {
-      const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
-      const int a2 = __shfl_xor_sync(0xffffffffu, a, o);
-      if (a2 < C && (a >= C || m2 > m || (m2 == m && a2 < a))) { m = m2; a = a2; }
+      for (int q = 1; q < 8; ++q) {
+        const float val = rv[q * TT + threadIdx.x];
+        const int a = rc[q * TT + threadIdx.x];
+        if (a < C && (A >= C || val > M || (val == M && a < A))) { M = val; A = a; }
+      }
+      out[(long long)b * Tn + t0 + threadIdx.x] = A;
     }
-    if (lane < 8) { redv[warp * TT + r.v * V + i] = m; redc[warp * TT + r.v * V + i] = a; }
-  }
-  __syncthreads();
-  if (threadIdx.x < TT && t0 + threadIdx.x < Tn) {
-    float M = redv[threadIdx.x];
-    int A = redc[threadIdx.x];
-#pragma unroll
-    for (int q = 1; q < 8; ++q) {
-      const float val = redv[q * TT + threadIdx.x];
-      const int a = redc[q * TT + threadIdx.x];
-      if (a < C && (A >= C || val > M || (val == M && a < A))) { M = val; A = a; }
-    }
-    out[(long long)b * Tn + t0 + threadIdx.x] = A;
-  }
+  });
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -709,6 +811,35 @@ extern "C" int wnb200_argmax_channels_col(int, int, int, int, const void*, int64
     }                                                                                                      \
   } while (0)
 
+static inline int rt_persistent_grid(long long ntiles) { return (int)ntiles; }
+#define RT_TRY_P(KERNEL, P0, P1, ...)                                                                      \
+  do {                                                                                                     \
+    const int esize_ = dtype == WNB200_F32 ? 4 : 2;                                                        \
+    const int TT_ = 8 * (16 / esize_);                                                                     \
+    const long long ntiles_ = (long long)B * ((T_ + TT_ - 1) / TT_);                                       \
+    if (C <= 256 && (dtype == WNB200_F32 || dtype == WNB200_BF16) && vec_ok(P0, P1, nullptr, T_, esize_) && \
+        ntiles_ < (1LL << 31)) {                                                                           \
+      const int tiles_ = (T_ + TT_ - 1) / TT_;                                                             \
+      const unsigned grid_ = (unsigned)rt_persistent_grid(ntiles_);                                        \
+      const int nt_ = (int)ntiles_;                                                                        \
+      cudaStream_t st_ = (cudaStream_t)stream;                                                             \
+      const int kc_ = C <= 64 ? 2 : (C <= 128 ? 4 : 8);                                                    \
+      if (dtype == WNB200_F32) {                                                                           \
+        using T = float;                                                                                   \
+        if (kc_ == 2) KERNEL<T, 2><<<grid_, CT_THREADS, 0, st_>>>(C, T_, tiles_, nt_, __VA_ARGS__);         \
+        else if (kc_ == 4) KERNEL<T, 4><<<grid_, CT_THREADS, 0, st_>>>(C, T_, tiles_, nt_, __VA_ARGS__);    \
+        else KERNEL<T, 8><<<grid_, CT_THREADS, 0, st_>>>(C, T_, tiles_, nt_, __VA_ARGS__);                  \
+      } else {                                                                                             \
+        using T = bf16;                                                                                    \
+        if (kc_ == 2) KERNEL<T, 2><<<grid_, CT_THREADS, 0, st_>>>(C, T_, tiles_, nt_, __VA_ARGS__);         \
+        else if (kc_ == 4) KERNEL<T, 4><<<grid_, CT_THREADS, 0, st_>>>(C, T_, tiles_, nt_, __VA_ARGS__);    \
+        else KERNEL<T, 8><<<grid_, CT_THREADS, 0, st_>>>(C, T_, tiles_, nt_, __VA_ARGS__);                  \
+      }                                                                                                    \
+      WNB_LAUNCH_OK();                                                                                     \
+      return 0;                                                                                            \
+    }                                                                                                      \
+  } while (0)
+
 #define CT_LAUNCH(KERNEL, NTILES, P0, P1, P2, FALLBACK, ...)                                               \
   do {                                                                                                     \
     const int esize = dtype == WNB200_F32 ? 4 : 2;                                                         \
@@ -738,7 +869,7 @@ extern "C" int wnb200_softmax_fwd(int dtype, int B, int C, int T_, const void* x
                                   void* stream) {
   WNB_CHECK_ARG(x && y && C >= 1, "softmax_fwd: bad args");
   if ((long long)B * T_ == 0) return 0;
-  RT_TRY(softmax_fwd_reg, x, y, (const T*)x, (T*)y, log_mode);
+  RT_TRY_P(softmax_fwd_reg, x, y, (const T*)x, (T*)y, log_mode);
   CT_LAUNCH(softmax_fwd_tile, 1, x, y, nullptr, wnb200_softmax_fwd_col(dtype, B, C, T_, x, y, log_mode, stream),
             (const T*)x, (T*)y, log_mode);
 }
@@ -755,7 +886,7 @@ extern "C" int wnb200_xent_fwd(int dtype, int B, int C, int T_, const void* logi
                                float* loss_bt, float* lse, void* stream) {
   WNB_CHECK_ARG(logits && target && loss_bt && lse, "xent_fwd: null pointer");
   if ((long long)B * T_ == 0) return 0;
-  RT_TRY(xent_fwd_reg, logits, nullptr, (const T*)logits, (const long long*)target, loss_bt, lse);
+  RT_TRY_P(xent_fwd_reg, logits, nullptr, (const T*)logits, (const long long*)target, loss_bt, lse);
   CT_LAUNCH(xent_fwd_tile, 1, logits, nullptr, nullptr,
             wnb200_xent_fwd_col(dtype, B, C, T_, logits, target, loss_bt, lse, stream), (const T*)logits,
             (const long long*)target, loss_bt, lse);
@@ -775,6 +906,7 @@ extern "C" int wnb200_layernorm_fwd(int dtype, int B, int C, int T_, const void*
                                     const float* beta, float eps, void* y, float* stats, void* stream) {
   WNB_CHECK_ARG(x && y && gamma && beta && C >= 2, "layernorm_fwd: bad args");
   if ((long long)B * T_ == 0) return 0;
+  RT_TRY_P(layernorm_fwd_reg, x, y, (const T*)x, gamma, beta, eps, (T*)y, stats);
   CT_LAUNCH(layernorm_fwd_tile, 1, x, y, nullptr,
             wnb200_layernorm_fwd_col(dtype, B, C, T_, x, gamma, beta, eps, y, stats, stream), (const T*)x, gamma, beta,
             eps, (T*)y, stats);
@@ -792,7 +924,7 @@ extern "C" int wnb200_layernorm_bwd(int dtype, int B, int C, int T_, const void*
 extern "C" int wnb200_argmax_channels(int dtype, int B, int C, int T_, const void* x, int64_t* out, void* stream) {
   WNB_CHECK_ARG(x && out && C >= 1, "argmax_channels: bad args");
   if ((long long)B * T_ == 0) return 0;
-  RT_TRY(argmax_reg, x, nullptr, (const T*)x, (long long*)out);
+  RT_TRY_P(argmax_reg, x, nullptr, (const T*)x, (long long*)out);
   CT_LAUNCH(argmax_tile, 1, x, nullptr, nullptr, wnb200_argmax_channels_col(dtype, B, C, T_, x, out, stream),
             (const T*)x, (long long*)out);
 }

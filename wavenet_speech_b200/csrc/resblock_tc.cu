@@ -386,6 +386,7 @@ struct R2Cfg {
   static constexpr int ACT = KB * RB_ABYTES;
   static constexpr int STAGING = 2 * RB_ABYTES;                // double-buffered output staging
   static constexpr int NSTAGE = (C == 256) ? 4 : 6;
+  static constexpr bool RETAIN = (NSTAGE == KB);               // a phase of KB K-blocks walks the whole ring once
   static constexpr int SMEM = NSTAGE * STAGE + ACT + STAGING + 1024 + 256;
 };
 
@@ -462,6 +463,9 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         if (++stage == K::NSTAGE) { stage = 0; phase ^= 1; }
       };
       const int wrow = (int)rank * (C / 2);       // this CTA's rows inside a [C x 64] weight block
+      int ord[3] = {0, 1, 2};                     // tap order: the zero-offset tap (x(t)) first
+      for (int j = 1; j < p.ntaps; ++j)
+        if (p.t_off[j] == 0) { ord[0] = j; for (int i = 1; i <= j; ++i) ord[i] = i - 1; }
       auto begin_stage = [&](uint32_t bytes_per_cta) -> uint32_t {
         mbar_wait(empty_bar(stage), phase ^ 1);
         if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * bytes_per_cta);
@@ -474,20 +478,28 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       for (int pt = pair; pt < p.num_tiles; pt += npairs) {
         const int b = pt / p.tiles_per_seq;
         const int t0 = (pt - b * p.tiles_per_seq) * (2 * RB_TILE) + (int)rank * RB_TILE;
+        // G1a walks the taps as ord[0..ntaps), G1b backwards, the projection follows G1b's last tap (= ord[0],
+        // the zero-offset tap when there is one).  When the ring is exactly KB stages deep, the activation blocks
+        // of the tap a phase starts with are still sitting in the stages it is about to use: only the weight half
+        // of those stages is reloaded (12 instead of 20 activation blocks per tile at k = 2, C = 256).
         for (int half = 0; half < 2; ++half) {
-          for (int kb = 0; kb < p.ntaps * K::KB; ++kb) {
-            const uint32_t sa = smem_base + stage * K::STAGE;
-            const uint32_t lfull = begin_stage(K::STAGE);
-            const int tap = kb / K::KB, cb = kb - tap * K::KB;
-            tma_load_3d_2sm(sa, &map_x, lfull, cb * 64, t0 + p.t_off[tap], b);
-            tma_load_2d_2sm(sa + RB_ABYTES, &map_w1, lfull, kb * 64, half * C + wrow);
-            end_stage(lfull);
+          for (int jj = 0; jj < p.ntaps; ++jj) {
+            const int tap = half == 0 ? ord[jj] : ord[p.ntaps - 1 - jj];
+            const bool keep = K::RETAIN && half == 1 && jj == 0;
+            for (int cb = 0; cb < K::KB; ++cb) {
+              const uint32_t sa = smem_base + stage * K::STAGE;
+              const uint32_t lfull = begin_stage(keep ? K::BHBYTES : K::STAGE);
+              if (!keep) tma_load_3d_2sm(sa, &map_x, lfull, cb * 64, t0 + p.t_off[tap], b);
+              tma_load_2d_2sm(sa + RB_ABYTES, &map_w1, lfull, (tap * K::KB + cb) * 64, half * C + wrow);
+              end_stage(lfull);
+            }
           }
         }
+        const bool keep_x = K::RETAIN && p.t_off[ord[0]] == 0;
         for (int kb = 0; kb < K::KB; ++kb) {
           const uint32_t sa = smem_base + stage * K::STAGE;
-          const uint32_t lfull = begin_stage(K::STAGE);
-          tma_load_3d_2sm(sa, &map_x, lfull, kb * 64, t0, b);
+          const uint32_t lfull = begin_stage(keep_x ? K::BHBYTES : K::STAGE);
+          if (!keep_x) tma_load_3d_2sm(sa, &map_x, lfull, kb * 64, t0, b);
           tma_load_2d_2sm(sa + RB_ABYTES, &map_w2, lfull, C + kb * 64, wrow);
           end_stage(lfull);
         }
