@@ -28,6 +28,28 @@ def test_layout_roundtrip():
     assert torch.equal(z.cpu(), x.bfloat16().float().cpu())
 
 
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("B,C,T,pool", [(2, 64, 300, 3), (3, 256, 1001, 3), (1, 128, 16383, 3), (2, 70, 257, 2),
+                                        (1, 64, 64, 1), (2, 64, 999, 7), (1, 64, 5, 3), (2, 64, 100, 40),
+                                        (1, 33, 50, 3)])
+def test_avgpool_to_nlc(B, C, T, pool, dt):
+    """AvgPool1d(pool) fused with the NCL -> NLC bf16 layout change (classifier.py:53,102) on rows of any alignment,
+    including the very last bytes of the tensor, partial channel / frame tiles and the fallback shapes."""
+    from wavenet_speech_b200 import _lib, ops
+    torch.manual_seed(B * 1000 + T)
+    x = torch.randn(B, C, T).to(dt)
+    To = T // pool
+    ref = torch.nn.functional.avg_pool1d(x.float(), pool).bfloat16().float().permute(0, 2, 1) if To > 0 else None
+    xg = x.cuda()
+    y = torch.full((B, To, C), 7.0, dtype=torch.bfloat16, device="cuda")
+    _lib.call("wnb200_avgpool_ncl_to_nlc_bf16", 1 if dt == torch.bfloat16 else 0, B, C, T, pool, ops._p(xg), ops._p(y),
+              ops._stream())
+    torch.cuda.synchronize()
+    if To > 0:
+        # fp32 accumulation order inside a window may differ from torch's: one bf16 ulp
+        assert (y.float().cpu() - ref).abs().max() <= 2 ** -7 * max(1.0, float(ref.abs().max()))
+
+
 @pytest.mark.parametrize("C,k,T,B", [(64, 2, 128, 1), (64, 1, 200, 2), (128, 2, 300, 2), (256, 2, 257, 2),
                                      (256, 3, 100, 1)])
 def test_single_contraction(C, k, T, B):

@@ -427,6 +427,66 @@ __global__ void __launch_bounds__(256) avgpool_ncl_to_nlc_kernel(int C, int Tn, 
   }
 }
 
+// v2: rows are brought in with ALIGNED 16-byte loads whatever the row alignment (T - 1 = 16383 frames in the train
+// step makes every row start on a different 2-byte phase): the vectors covering a row's segment land in shared memory
+// at their natural position, the row's lead (0..15 bytes) is added when the pooled frames are read back.  A CTA owns
+// 64 channels x TF pooled frames; a warp pools 8 channels with its lanes over frames (conflict-free shared reads),
+// the bf16 results cross a padded [TF][66] tile and leave as 128-byte rows (one pooled frame x 64 channels).
+template <typename T>
+__global__ void __launch_bounds__(256)
+avgpool_ncl_to_nlc_v2_kernel(int C, int Tn, int To, int pool, int TF, int RS, long long total_bytes, const T* x,
+                             bf16* y) {
+  extern __shared__ __align__(16) uint8_t pool_smem[];
+  constexpr int ES = (int)sizeof(T);
+  uint8_t* in_s = pool_smem;                                   // [64][RS]
+  bf16* out_s = reinterpret_cast<bf16*>(pool_smem + 64 * RS);  // [TF][66]
+  __shared__ int lead_s[64];
+  const int b = blockIdx.z, c0 = blockIdx.y * 64, t0 = blockIdx.x * TF;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = (TF * pool * ES + 15) / 16 + 1;
+  const uint8_t* xb = reinterpret_cast<const uint8_t*>(x);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = warp + 8 * i, c = c0 + row;
+    const long long start = (((long long)b * C + c) * Tn + (long long)t0 * pool) * ES;
+    const long long a0 = start & ~15LL;
+    if (lane == 0) lead_s[row] = (int)(start - a0);
+    for (int j = lane; j < nvec; j += 32) {
+      const long long a = a0 + 16LL * j;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (c < C) {
+        if (a + 16 <= total_bytes) {
+          v = __ldg(reinterpret_cast<const uint4*>(xb + a));
+        } else {                                               // the tensor's last bytes: element by element
+          T* e = reinterpret_cast<T*>(&v);
+          for (int q = 0; q < 16 / ES; ++q)
+            if (a + (q + 1) * ES <= total_bytes) e[q] = *reinterpret_cast<const T*>(xb + a + q * ES);
+        }
+      }
+      *reinterpret_cast<uint4*>(in_s + row * RS + 16 * j) = v;
+    }
+  }
+  __syncthreads();
+  const float inv = 1.f / (float)pool;
+  for (int f = lane; f < TF; f += 32) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int row = warp * 8 + j;
+      const T* src = reinterpret_cast<const T*>(in_s + row * RS + lead_s[row]) + f * pool;
+      float acc = 0.f;
+      for (int k = 0; k < pool; ++k) acc += to_f32<T>(src[k]);
+      out_s[f * 66 + row] = __float2bfloat16_rn(acc * inv);
+    }
+  }
+  __syncthreads();
+  const uint32_t* ow = reinterpret_cast<const uint32_t*>(out_s);
+  for (int idx = threadIdx.x; idx < TF * 32; idx += 256) {
+    const int f = idx >> 5, wc = idx & 31;
+    if (t0 + f < To && c0 + 2 * wc + 1 < C)
+      *reinterpret_cast<uint32_t*>(y + ((long long)b * To + t0 + f) * C + c0 + 2 * wc) = ow[f * 33 + wc];
+  }
+}
+
 }  // namespace wnb
 
 using namespace wnb;
@@ -536,8 +596,27 @@ extern "C" int wnb200_avgpool_ncl_to_nlc_bf16(int dtype, int B, int C, int T_, i
   const int To = T_ / pool;
   if (B == 0 || C == 0 || To == 0) return 0;
   WNB_CHECK_ARG(x && y, "avgpool_ncl_to_nlc_bf16: null pointer");
-  dim3 grid(ceil_div(To, 32), ceil_div(C, 32), B);
   cudaStream_t st = (cudaStream_t)stream;
+  const int es = dtype == WNB200_F32 ? 4 : 2;
+  // v2 (aligned vector loads, any row alignment): C even, base pointers 16-byte aligned, a [64 x TF*pool] tile in 40 KB
+  int TF = 64;
+  while (TF > 8 && TF * pool * es > 576) TF >>= 1;
+  if (C % 2 == 0 && TF * pool * es <= 576 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(y) & 3) == 0) {
+    const int RS = ((TF * pool * es + 15) / 16 + 1) * 16 + 16;
+    const size_t smem = (size_t)64 * RS + (size_t)TF * 66 * 2;
+    const long long total = (long long)B * C * T_ * es;
+    dim3 grid2(ceil_div(To, TF), ceil_div(C, 64), B);
+    if (dtype == WNB200_F32)
+      avgpool_ncl_to_nlc_v2_kernel<float><<<grid2, 256, smem, st>>>(C, T_, To, pool, TF, RS, total, (const float*)x,
+                                                                    (bf16*)y);
+    else
+      avgpool_ncl_to_nlc_v2_kernel<bf16><<<grid2, 256, smem, st>>>(C, T_, To, pool, TF, RS, total, (const bf16*)x,
+                                                                   (bf16*)y);
+    WNB_LAUNCH_OK();
+    return 0;
+  }
+  dim3 grid(ceil_div(To, 32), ceil_div(C, 32), B);
   if (dtype == WNB200_F32)
     avgpool_ncl_to_nlc_kernel<float><<<grid, 256, 0, st>>>(C, T_, To, pool, (const float*)x, (bf16*)y);
   else
