@@ -188,6 +188,41 @@ def test_wavenet_tc(C, nl, T, B, softmax):
         assert agree > 0.97, agree
 
 
+def test_reduced_precision_switch_routes_fp32_models():
+    """An fp32 model with fp32 inputs stays on the fp32 FFMA kernels (<= 1e-5) unless `reduced_precision(True)`
+    opts in to the tensor-core kernels: then outputs and gradients are fp32 tensors within the bf16 tolerance."""
+    torch.manual_seed(5)
+    C, T, B = 128, 700, 2
+    layers = [(C, C, 2, 2 ** i) for i in range(4)]
+    net = W.WaveNet(C, 2, layers, C, softmax=False)
+    sd32 = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    sd16 = {k: r16(v) for k, v in sd32.items()}
+    lev = torch.randint(0, C, (B, T))
+    x = torch.zeros(B, C, T).scatter_(1, lev.unsqueeze(1), 1.0)
+    ref32 = O.wavenet_forward(sd32, x, layers, softmax=False)
+    ref16 = O.wavenet_forward(sd16, x, layers, softmax=False)
+    net = net.cuda()
+    xg = x.cuda()
+    with torch.no_grad():
+        y = net(xg)
+    assert y.dtype == torch.float32 and rel(y, ref32) <= 1e-5            # default: true fp32 arithmetic
+    with W.reduced_precision(True):
+        with torch.no_grad():
+            before = W._lib.launch_count
+            y2 = net(xg)
+            assert W._lib.launch_count - before == len(layers) + 5         # the tensor-core launch sequence
+        assert y2.dtype == torch.float32 and rel(y2, ref16) <= BF16_TOL
+        xr = xg.clone().requires_grad_(True)
+        out = net(xr)
+        out.square().mean().backward()
+        assert xr.grad is not None and xr.grad.dtype == torch.float32 and torch.isfinite(xr.grad).all()
+        g = net.convolutions[1].conv_tanh.conv1d.weight.grad
+        assert g is not None and g.dtype == torch.float32 and torch.isfinite(g).all() and float(g.abs().max()) > 0
+    with torch.no_grad():
+        y3 = net(xg)
+    assert torch.equal(y3, y)                                               # the switch is scoped
+
+
 @pytest.mark.parametrize("C,fk,T,B,causal,softmax", [(256, 3, 500, 2, False, False), (128, 1, 300, 3, True, True),
                                                      (256, 2, 4000, 2, False, False)])
 def test_raw_ctcnet_tc(C, fk, T, B, causal, softmax):

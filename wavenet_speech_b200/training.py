@@ -392,7 +392,7 @@ class _WaveNetTrain(torch.autograd.Function):
 
 def wavenet_train_eligible(model, signal):
     C = model.layers[0][0]
-    return (signal.dtype == torch.bfloat16 and signal.is_cuda and signal.dim() == 3 and C in (128, 256)
+    return (FP.tc_dtype_ok(signal) and signal.is_cuda and signal.dim() == 3 and C in (128, 256)
             and model.in_dim in (128, 256) and model.out_dim == C and FP._stack_ok(C, model.layers)
             and model.entry_kwidth <= 3 and signal.shape[0] > 0 and signal.shape[2] > 0)
 
@@ -452,7 +452,7 @@ class _ClassifierTrain(torch.autograd.Function):
 
 def classifier_train_eligible(model, seq):
     C = model.layers[0][0]
-    return (seq.dtype == torch.bfloat16 and seq.is_cuda and seq.dim() == 3 and C in (128, 256) and model.in_dim == C
+    return (FP.tc_dtype_ok(seq) and seq.is_cuda and seq.dim() == 3 and C in (128, 256) and model.in_dim == C
             and model.out_dim == C and FP._stack_ok(C, model.layers) and model.input_kernel_size <= 3
             and seq.shape[0] > 0 and seq.shape[2] // model.pool_kernel_size > 0)
 
@@ -529,7 +529,7 @@ class _RawCTCNetTrain(torch.autograd.Function):
 
 def raw_ctcnet_train_eligible(model, seq):
     C, F = model.layers[0][0], model.num_features
-    return (seq.dtype == torch.bfloat16 and seq.is_cuda and seq.dim() == 3 and seq.shape[1] == 1 and F == C
+    return (FP.tc_dtype_ok(seq) and seq.is_cuda and seq.dim() == 3 and seq.shape[1] == 1 and F == C
             and model.out_dim == C and C in (128, 256) and not model.positions and FP._stack_ok(C, model.layers)
             and model.input_kernel_size <= 3 and model.feature_kwidth <= 4 and seq.shape[0] > 0 and seq.shape[2] > 0)
 
