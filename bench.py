@@ -348,11 +348,14 @@ def main():
                           ".wait() once at the end" % args.e2e_chunks}
 
         # ---- roofline of the dominant kernel: per-launch CUDA-event timing on the launching stream ------
+        # (a second pass of the same K steps, so that the per-launch average sees the same sustained clocks as `value`:
+        # the first steps after an idle period run ~10 % faster, before the power limiter pulls the SM clock down)
         _lib.kernel_timing(True)
-        for _ in range(2):
+        for _ in range(args.steps):
             net(x_dev)
         torch.cuda.synchronize()
         log = _lib.kernel_timing(False)
+    n_pass = args.steps
     per = {}
     for name, a, b in log:
         per.setdefault(name, []).append(a.elapsed_time(b))
@@ -366,7 +369,7 @@ def main():
         avg_ms = float(np.mean(per[dom]))
     else:                                                           # generic path: all contraction launches together
         flops_launch = flops_per_timestep(w) * samples
-        avg_ms = float(sum(per[dom])) / 2.0
+        avg_ms = float(sum(per[dom])) / float(n_pass)
     achieved = flops_launch / (avg_ms * 1e-3) / 1e12
     # DRAM bytes per launch of the fused block kernel from the committed `ncu --set full` capture of this same
     # workload (profiles/r1_ncu_full_resblock2_kernel_ctapair.csv): 806.7 MB read + 748.7 MB written

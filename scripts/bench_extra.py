@@ -42,6 +42,18 @@ if "rawctc" in which:      # config 4: RawCTCNet from configs/ecoli_testrun.json
         print(json.dumps({"config": "rawctcnet_ecoli_fk3_bf16_fwd", "batch": B, "T": 4000, "ms_per_step": ms,
                           "samples_per_s": sps, "tflops_as_written": sps * flop / 1e12}))
 
+if "graph" in which:       # small-batch basecalling latency: eager launches vs one CUDA-graph replay
+    from wavenet_speech_b200.pipeline import GraphedForward
+    net = ecoli_net().cuda().bfloat16().eval()
+    for B in (1, 4, 16):
+        x = torch.from_numpy(SG.raw_batch(B, 4000, seed=9)).cuda().bfloat16()
+        with torch.no_grad():
+            ms_eager = timed(lambda: net(x), 50, warmup=5)
+        g = GraphedForward(net, x)
+        ms_graph = timed(lambda: g(x), 50, warmup=5)
+        print(json.dumps({"config": "rawctcnet_ecoli_fk3_bf16_fwd_latency", "batch": B, "T": 4000, "ms_eager": ms_eager,
+                          "ms_cuda_graph": ms_graph, "samples_per_s_graph": B * 4000 / (ms_graph * 1e-3)}))
+
 if "example" in which:     # config 1: RawCTCNet from configs/example.json, fp32, 8 x 4000 (generic fp32 kernels)
     torch.manual_seed(0)
     layers = [(1, 1, 1, 1)]

@@ -188,6 +188,25 @@ def test_wavenet_tc(C, nl, T, B, softmax):
         assert agree > 0.97, agree
 
 
+def test_graphed_forward_replays_bitwise():
+    """The whole forward captured in a CUDA graph (pipeline.GraphedForward) reproduces the eager result bit for bit,
+    for new inputs as well, on the tensor-core and on the generic kernels."""
+    from wavenet_speech_b200.pipeline import GraphedForward
+    torch.manual_seed(11)
+    net = W.RawCTCNet(256, 3, 5, [(256, 256, 2, d) for d in (1, 2, 4, 8)], 256, softmax=False).cuda().bfloat16().eval()
+    xs = [torch.randn(1, 1, 1000, device="cuda").bfloat16() for _ in range(3)]
+    g = GraphedForward(net, xs[0])
+    for x in xs:
+        with torch.no_grad():
+            ref = net(x)
+        assert torch.equal(g(x), ref)
+    net32 = W.WaveNet(16, 2, [(16, 16, 2, d) for d in (1, 2)], 16, softmax=True).cuda().eval()      # generic fp32 path
+    x32 = torch.randn(2, 16, 100, device="cuda")
+    g32 = GraphedForward(net32, x32)
+    with torch.no_grad():
+        assert torch.equal(g32(x32), net32(x32))
+
+
 def test_reduced_precision_switch_routes_fp32_models():
     """An fp32 model with fp32 inputs stays on the fp32 FFMA kernels (<= 1e-5) unless `reduced_precision(True)`
     opts in to the tensor-core kernels: then outputs and gradients are fp32 tensors within the bf16 tolerance."""
