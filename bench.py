@@ -347,6 +347,32 @@ def main():
                    "api": "wavenet_speech_b200.pipeline.HostPipeline(model, chunks=%d).submit(x_pinned, y_pinned) per step, "
                           ".wait() once at the end" % args.e2e_chunks}
 
+        # ---- the same end to end, with the host handing over the quantised LEVELS (B, T) uint8 instead of their
+        # one-hot encoding: what the reference's loaders hold before fns.py:6-15; the one-hot never exists on this path
+        # (the entry conv is a gather).  Extra information, not the contract's `e2e` (which keeps the reference call).
+        e2e_levels = None
+        if not args.no_e2e and args.dtype == "bf16" and w["in_dim"] == w["C"] and w["C"] in (128, 256):
+            from wavenet_speech_b200.pipeline import HostPipeline
+            lev_host = x_host.float().argmax(1).to(torch.uint8).pin_memory()
+            pipe2 = HostPipeline(net, chunks=args.e2e_chunks, fn=net.forward_levels)
+            for k in range(2):
+                pipe2(lev_host, y_hosts[k])
+            barrier()
+            t0 = time.perf_counter()
+            e0.record()
+            for k in range(args.steps):
+                pipe2.submit(lev_host, y_hosts[k & 1])
+            pipe2.wait()
+            e1.record()
+            barrier()
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            ms_l = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
+            e2e_levels = {"value": samples * world * args.steps / (ms_l * 1e-3), "unit": UNIT,
+                          "h2d_bytes_per_step": lev_host.numel(), "d2h_bytes_per_step": y_host.numel() * y_host.element_size(),
+                          "ms_per_step": ms_l / args.steps,
+                          "api": "HostPipeline(model, chunks=%d, fn=model.forward_levels).submit(levels_u8_pinned, y_pinned)"
+                                 % args.e2e_chunks}
+
         # ---- roofline of the dominant kernel: per-launch CUDA-event timing on the launching stream ------
         # (a second pass of the same K steps, so that the per-launch average sees the same sustained clocks as `value`:
         # the first steps after an idle period run ~10 % faster, before the power limiter pulls the SM clock down)
@@ -401,7 +427,8 @@ def main():
                    "layers": len(w["dil"]), "softmax": True, "sharding": "batch x%d" % world,
                    "l2": "input %.0f MB and every inter-layer tensor exceed the 126 MB L2" % input_mb,
                    "flop_per_sample": flops_per_timestep(w)},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": clocks, "e2e": e2e, "e2e_levels": e2e_levels, "gpu_launches": launches, "roofline": roofline,
+        "cpu_baseline": cpu,
         "fwd_bwd": fwd_bwd,
         "tflops": value * flops_per_timestep(w) / 1e12,
     }

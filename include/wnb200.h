@@ -234,6 +234,13 @@ int wnb200_dense_fwd_tc(const wnb200_dense_t* args /*host*/, void* stream);
 int wnb200_featurize_nlc(int dtype, int B, int T, int F, int fk, const void* x, const float* w, const float* bias,
                          void* y, void* stream);
 
+/* WaveNet entry conv (wavenet.py:54,93) on quantised LEVELS instead of their one-hot encoding (fns.py:6-15,
+ * pore_model.py:88-96): y[b,t,:] = bias + sum_j wemb[j][levels[b,t+t_off[j]]][:], taps outside [0,T) contribute nothing.
+ * levels int32 [B,T] (clamped to [0,in_dim)), wemb bf16 [ntaps][in_dim][C] (= conv weight [C,in_dim,ntaps] permuted),
+ * bias fp32 [C], y NLC bf16 [B,T,C]; t_off: host int32[ntaps].  Bit-identical to the dense kernel on the one-hot input. */
+int wnb200_entry_embed_nlc(int B, int T, int C, int in_dim, int ntaps, const int32_t* t_off /*host*/,
+                           const int32_t* levels, const void* wemb, const float* bias, void* y, void* stream);
+
 /* AvgPool1d(pool) (classifier.py:53,102) fused with the NCL -> NLC bf16 layout change:
  * x NCL [B, C, T] -> y NLC bf16 [B, floor(T/pool), C]. */
 int wnb200_avgpool_ncl_to_nlc_bf16(int dtype, int B, int C, int T, int pool, const void* x, void* y, void* stream);

@@ -188,6 +188,28 @@ def test_wavenet_tc(C, nl, T, B, softmax):
         assert agree > 0.97, agree
 
 
+@pytest.mark.parametrize("C,nl,T,B,softmax,ldt", [(256, 3, 700, 2, True, torch.uint8), (128, 4, 257, 3, False, torch.int64),
+                                                  (256, 2, 1, 1, True, torch.int32)])
+def test_wavenet_forward_levels_equals_one_hot_call(C, nl, T, B, softmax, ldt):
+    """forward_levels(levels) (entry conv as a gather of weight columns) is bit-identical to forward(one_hot(levels))."""
+    torch.manual_seed(C + T)
+    layers = [(C, C, 2, 2 ** i) for i in range(nl)]
+    net = W.WaveNet(C, 2, layers, C, softmax=softmax)
+    with torch.no_grad():
+        net.entry_conv1d.conv1d.bias.add_(torch.randn(C) * 0.1)
+    net = net.cuda().bfloat16().eval()
+    lev = torch.randint(0, C, (B, T))
+    x = torch.zeros(B, C, T).scatter_(1, lev.unsqueeze(1), 1.0).cuda().bfloat16()
+    with torch.no_grad():
+        ref = net(x)
+    y = net.forward_levels(lev.to(ldt).cuda())
+    assert y.dtype == ref.dtype and torch.equal(y, ref)
+    from wavenet_speech_b200.pipeline import HostPipeline
+    lev_host = lev.to(ldt).pin_memory()
+    out = HostPipeline(net, chunks=2, fn=net.forward_levels)(lev_host)
+    assert torch.equal(out, ref.cpu())
+
+
 def test_graphed_forward_replays_bitwise():
     """The whole forward captured in a CUDA graph (pipeline.GraphedForward) reproduces the eager result bit for bit,
     for new inputs as well, on the tensor-core and on the generic kernels."""

@@ -487,9 +487,75 @@ avgpool_ncl_to_nlc_v2_kernel(int C, int Tn, int To, int pool, int TF, int RS, lo
   }
 }
 
+// Entry conv of a WaveNet fed with quantised LEVELS instead of their one-hot encoding (wavenet.py:93 applied to
+// fns.py:6-15 / pore_model.py:88-96): a convolution over a one-hot signal is a gather,
+//     y[b, t, :] = bias + sum_j Wemb[j][lev[b, t + off_j]][:]          (taps outside [0, T) contribute nothing),
+// with Wemb[j][l][c] = W[c, l, j] in bf16.  One warp per frame, a lane owns 8 channels per 256 (16-byte loads from the
+// L1-resident table, one 16-byte store).  Same products, same fp32 accumulation order as the dense kernel on the one-hot
+// tensor, without the 2 x 256-fold larger input.
+__global__ void __launch_bounds__(256)
+entry_embed_nlc_kernel(long long frames, int Tn, int C, int in_dim, int ntaps, int o0, int o1, int o2,
+                       const int* __restrict__ lev, const bf16* __restrict__ wemb, const float* __restrict__ bias,
+                       bf16* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const long long f = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  if (f >= frames) return;
+  const int t = (int)(f % Tn);
+  const int offs[3] = {o0, o1, o2};
+  int l[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    l[j] = -1;
+    if (j < ntaps) {
+      const int tt = t + offs[j];
+      if (tt >= 0 && tt < Tn) {
+        const int v = lev[f + offs[j]];
+        l[j] = v < 0 ? 0 : (v >= in_dim ? in_dim - 1 : v);
+      }
+    }
+  }
+  for (int c0 = lane * 8; c0 < C; c0 += 256) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (l[j] < 0) continue;
+      const uint4 w = __ldg(reinterpret_cast<const uint4*>(wemb + ((long long)j * in_dim + l[j]) * C + c0));
+      const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 v = __bfloat1622float2(w2[q]);
+        acc[2 * q] += v.x;
+        acc[2 * q + 1] += v.y;
+      }
+    }
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
+    uint4 o;
+    o.x = pack_bf16x2(acc[0] + b0.x, acc[1] + b0.y);
+    o.y = pack_bf16x2(acc[2] + b0.z, acc[3] + b0.w);
+    o.z = pack_bf16x2(acc[4] + b1.x, acc[5] + b1.y);
+    o.w = pack_bf16x2(acc[6] + b1.z, acc[7] + b1.w);
+    *reinterpret_cast<uint4*>(y + f * C + c0) = o;
+  }
+}
+
 }  // namespace wnb
 
 using namespace wnb;
+
+extern "C" int wnb200_entry_embed_nlc(int B, int T_, int C, int in_dim, int ntaps, const int32_t* t_off,
+                                      const int32_t* levels, const void* wemb, const float* bias, void* y,
+                                      void* stream) {
+  WNB_CHECK_ARG(C >= 8 && C % 8 == 0 && in_dim >= 1 && ntaps >= 1 && ntaps <= 3, "entry_embed_nlc: bad sizes");
+  if (B == 0 || T_ == 0) return 0;
+  WNB_CHECK_ARG(t_off && levels && wemb && bias && y, "entry_embed_nlc: null pointer");
+  const long long frames = (long long)B * T_;
+  WNB_CHECK_ARG(frames / 8 + 1 < (1ll << 31), "entry_embed_nlc: too many frames");
+  entry_embed_nlc_kernel<<<(unsigned)ceil_div64(frames, 8), 256, 0, (cudaStream_t)stream>>>(
+      frames, T_, C, in_dim, ntaps, t_off[0], ntaps > 1 ? t_off[1] : 0, ntaps > 2 ? t_off[2] : 0, levels,
+      (const bf16*)wemb, bias, (bf16*)y);
+  WNB_LAUNCH_OK();
+  return 0;
+}
 
 extern "C" int wnb200_dense_fwd_tc(const wnb200_dense_t* a, void* stream) {
   WNB_CHECK_ARG(a != nullptr, "dense_fwd_tc: null argument");

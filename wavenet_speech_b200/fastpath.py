@@ -315,6 +315,40 @@ def try_wavenet_forward(model, signal):
     return run_head(skips_act, pk["head"], signal.dtype, model.softmax)
 
 
+def wavenet_forward_levels(model, levels, out_dtype=torch.bfloat16):
+    """WaveNet.forward(one_hot(levels)) without materialising the one-hot tensor: `levels` (B, T) integers in
+    [0, in_dim) -- what pore_model.py:78-86 / np.digitize produce before the one-hot step (pore_model.py:88-96).  The entry
+    conv becomes a gather of weight columns (`wnb200_entry_embed_nlc`), everything after it is the usual pipeline; the
+    result is bit-identical to the one-hot call on the tensor-core path.  Inference only (no autograd graph)."""
+    assert levels.is_cuda and levels.dim() == 2, "forward_levels expects a CUDA (B, T) integer tensor"
+    C = model.layers[0][0]
+    if not (model.in_dim == C and model.out_dim == C and C in (128, 256) and _stack_ok(C, model.layers)
+            and model.entry_kwidth <= 3):
+        raise RuntimeError("forward_levels: this WaveNet is not eligible for the tensor-core path "
+                           "(in_dim = C = out_dim in {128, 256}, kernel widths <= 3)")
+    ops.check_device()
+
+    def build():
+        ec = model.entry_conv1d
+        return {"wemb": _bf16(ec.conv1d.weight.detach().float().permute(2, 1, 0)),        # [k][in_dim][C]
+                "b1": ec.conv1d.bias.detach().float().contiguous(), "offsets": list(ec.offsets),
+                "blocks": [pack_block(b, n) for b, n in zip(model.convolutions, model.bottlenecks)],
+                "head": pack_head(model.output_stack, C)}
+
+    pk = _cached(model, "wavenet_levels", build)
+    B, T = levels.shape
+    lev = levels.to(torch.int32).contiguous()
+    h = torch.empty((B, T, C), dtype=torch.bfloat16, device=levels.device)
+    if B * T > 0:
+        offs = (ctypes.c_int32 * len(pk["offsets"]))(*[int(o) for o in pk["offsets"]])
+        _lib.call("wnb200_entry_embed_nlc", B, T, C, model.in_dim, len(pk["offsets"]), offs, ops._p(lev),
+                  ops._p(pk["wemb"]), ops._p(pk["b1"]), ops._p(h), ops._stream())
+    skips = torch.empty((B, T, C), dtype=torch.float32, device=levels.device)
+    with torch.no_grad():
+        _, skips_act = run_blocks(h, model.convolutions, model.bottlenecks, pk["blocks"], skips, True, True)
+        return run_head(skips_act, pk["head"], out_dtype, model.softmax)
+
+
 def _stack_packs(model):
     packs = [pack_block(model.input_block, model.input_skip_bottleneck)]
     packs += [pack_block(b, n) for b, n in zip(model.convolutions, model.bottlenecks)]

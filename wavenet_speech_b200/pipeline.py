@@ -10,8 +10,11 @@ import torch
 
 
 class HostPipeline(object):
-    def __init__(self, model, chunks=4, device=None):
-        self.model = model
+    """`fn` (default: the model itself) is what runs on each device chunk; `HostPipeline(net, fn=net.forward_levels)`
+    streams (B, T) uint8 / integer level tensors instead of (B, 256, T) one-hot tensors: 1/512 of the bytes."""
+
+    def __init__(self, model, chunks=4, device=None, fn=None):
+        self.model = model if fn is None else fn
         self.chunks = int(chunks)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.s_in = torch.cuda.Stream(self.device)
