@@ -398,8 +398,8 @@ def main():
         avg_ms = float(sum(per[dom])) / float(n_pass)
     achieved = flops_launch / (avg_ms * 1e-3) / 1e12
     # DRAM bytes per launch of the fused block kernel from the committed `ncu --set full` capture of this same
-    # workload (profiles/r1_ncu_full_resblock2_kernel_ctapair.csv): 806.7 MB read + 748.7 MB written
-    traffic = 1555.3e6 if (tagged and args.workload == DEFAULT_WORKLOAD and not args.batch and not args.T) else None
+    # workload (profiles/r1_ncu_full_v8_resblock2.csv): 806.9 MB read + 749.9 MB written
+    traffic = 1556.8e6 if (tagged and args.workload == DEFAULT_WORKLOAD and not args.batch and not args.T) else None
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
                 "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": traffic,
                 "achieved_executed": achieved * 14.0 / 16.0 if tagged else achieved,
