@@ -203,6 +203,8 @@ typedef struct {
   void* save_act;         /* optional (training): gate, tanh(.) and sigmoid(.) as NLC bf16 [B,T,C] each */
   void* save_th;
   void* save_sg;
+  void* skips_act;        /* optional (last layer of an inference stack, res = NULL): NLC bf16 [B,T,C] that receives
+                             LeakyReLU(skips + contribution) (wavenet.py:100-103); `skips` is then read, not updated */
 } wnb200_resblock_t;
 int wnb200_resblock_fwd_tc(const wnb200_resblock_t* args /*host*/, void* stream);
 

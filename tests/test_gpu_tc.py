@@ -180,7 +180,7 @@ def test_wavenet_tc(C, nl, T, B, softmax):
         before = W._lib.launch_count
         y = net(x.cuda().bfloat16())
         assert y.dtype == torch.bfloat16 and tuple(y.shape) == tuple(ref.shape)
-    assert W._lib.launch_count - before == nl + 4 + (1 if C in (128, 256) else 0)   # transpose, entry, blocks, [leaky], 2 x head
+    assert W._lib.launch_count - before == nl + 4        # transpose, entry, blocks (the last one emits the head's input), 2 x head
     e = rel(y, ref)
     assert e <= BF16_TOL, e
     if not softmax:
@@ -208,6 +208,25 @@ def test_wavenet_forward_levels_equals_one_hot_call(C, nl, T, B, softmax, ldt):
     lev_host = lev.to(ldt).pin_memory()
     out = HostPipeline(net, chunks=2, fn=net.forward_levels)(lev_host)
     assert torch.equal(out, ref.cpu())
+
+
+@pytest.mark.parametrize("C,dil,T,B", [(256, [1, 2, 4], 700, 2), (128, [1, 2], 130, 3), (256, [4], 257, 1)])
+def test_last_layer_emits_head_input_bitwise(C, dil, T, B):
+    """The last block launch of an inference stack writes LeakyReLU(skip sum) as bf16 itself (TMA-loads the running
+    sum, adds its tile in registers): bit-identical to reduce-add + the separate conversion pass, also for a one-layer
+    stack (nothing to load) and for tiles that straddle T."""
+    torch.manual_seed(C + T)
+    net = W.WaveNet(C, 2, [(C, C, 2, d) for d in dil], C, softmax=False).cuda().bfloat16().eval()
+    x = torch.randn(B, C, T, device="cuda").bfloat16()
+    try:
+        with torch.no_grad():
+            FP.FUSE_FINAL = False
+            ref = net(x)
+            FP.FUSE_FINAL = True
+            y = net(x)
+    finally:
+        FP.FUSE_FINAL = True
+    assert torch.equal(y, ref)
 
 
 def test_graphed_forward_replays_bitwise():
@@ -251,7 +270,7 @@ def test_reduced_precision_switch_routes_fp32_models():
         with torch.no_grad():
             before = W._lib.launch_count
             y2 = net(xg)
-            assert W._lib.launch_count - before == len(layers) + 5         # the tensor-core launch sequence
+            assert W._lib.launch_count - before == len(layers) + 4         # the tensor-core launch sequence
         assert y2.dtype == torch.float32 and rel(y2, ref16) <= BF16_TOL
         xr = xg.clone().requires_grad_(True)
         out = net(xr)

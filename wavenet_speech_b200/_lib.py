@@ -36,7 +36,8 @@ class ResBlock(ctypes.Structure):
                 ("t_off", ctypes.c_int32 * 3), ("skips_init", ctypes.c_int32), ("variant", ctypes.c_int32),
                 ("_pad", ctypes.c_int32), ("x", c_void_p), ("w1", c_void_p),
                 ("bias1", c_void_p), ("w2", c_void_p), ("bias2", c_void_p), ("res", c_void_p), ("skips", c_void_p),
-                ("dbg", c_void_p), ("save_act", c_void_p), ("save_th", c_void_p), ("save_sg", c_void_p)]
+                ("dbg", c_void_p), ("save_act", c_void_p), ("save_th", c_void_p), ("save_sg", c_void_p),
+                ("skips_act", c_void_p)]
 
 
 class Dense(ctypes.Structure):

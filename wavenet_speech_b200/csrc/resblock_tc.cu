@@ -33,6 +33,7 @@ struct ResDev {
   const float* bias1;   // [2C] packed like W1 rows
   const float* bias2;   // [2C] = [res ; skip]
   int write_res, skips_init;
+  int final_act;    // last layer (CTA-pair kernel, inference): emit LeakyReLU(running sum + contribution) as bf16 instead
   long long* dbg;
   bf16* save_act;   // training: gate / tanh / sigmoid, NLC bf16 (CTA-pair kernel only)
   bf16* save_th;
@@ -420,7 +421,7 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   auto empty_bar = [&](int s) { return bar_base + 8u * (K::NSTAGE + s); };
   const uint32_t bb = bar_base + 8u * (2 * K::NSTAGE);
   const uint32_t accA_full = bb, accB_full = bb + 8, e1a_done = bb + 16, e1b_done = bb + 24, e2a_done = bb + 32,
-                 e2b_done = bb + 40, tmem_slot = bb + 48;
+                 e2b_done = bb + 40, tmem_slot = bb + 48, ld_bar = bb + 56;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -442,6 +443,7 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     mbar_init(e1b_done, 2 * RB_EPI_THREADS);
     mbar_init(e2a_done, 2 * RB_EPI_THREADS);
     mbar_init(e2b_done, 2 * RB_EPI_THREADS);
+    mbar_init(ld_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -591,6 +593,7 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const int sw = row & 7;
     const uint32_t r_e1a = mapa_shared(e1a_done, 0), r_e1b = mapa_shared(e1b_done, 0),
                    r_e2a = mapa_shared(e2a_done, 0), r_e2b = mapa_shared(e2b_done, 0);
+    uint32_t ld_phase = 0;
     int it = 0;
     for (int pt = pair; pt < p.num_tiles; pt += npairs, ++it) {
       const int b = pt / p.tiles_per_seq;
@@ -744,6 +747,70 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       tc_fence_after();
       if (issuer && rank == 0) RB_STAMP(11);
       constexpr int NBUF = K::KB + 2;            // gate blocks, then the two staging buffers
+      if (!SAVE && p.final_act) {
+        // Last layer of an inference stack (wavenet.py:100-103): nothing accumulates after this launch, so instead
+        // of adding the tile into the running sum and leaving LeakyReLU + bf16 conversion to another pass over it,
+        // the running sum's fp32 chunks come IN by TMA (KB at a time, into the idle gate blocks), meet the
+        // accumulator in registers and leave as bf16 64-channel chunks through the staging buffers:
+        // skips_act = LeakyReLU(sum + (acc + bias)) -- the same fp32 additions the L2 adder would have done.
+#pragma unroll 1
+        for (int w0 = 0; w0 < C / 32; w0 += K::KB) {
+          if (w0 > 0) epi_bar();                 // every thread is done with the previous wave's landing buffers
+          if (issuer) {
+            if (!p.skips_init) {
+              mbar_expect_tx(ld_bar, K::KB * RB_ABYTES);
+#pragma unroll
+              for (int u = 0; u < K::KB; ++u)
+                tma_load_3d(act_base + u * RB_ABYTES, &map_skips, ld_bar, (w0 + u) * 32, t0, b);
+            }
+            bulk_wait_read0();                   // staging buffers: E2a's / the previous wave's stores have left
+          }
+          if (!p.skips_init) {
+            mbar_wait(ld_bar, ld_phase);
+            ld_phase ^= 1u;
+          }
+          epi_bar();
+#pragma unroll
+          for (int u = 0; u < K::KB; ++u) {
+            const int col = (w0 + u) * 32 + h * 16;
+            float a[16];
+            tmem_ld16(tmemB + lane_off + col, a);
+            const float4* bp = reinterpret_cast<const float4*>(p.bias2 + C + col);
+            float bv[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 v4 = __ldg(bp + j);
+              bv[4 * j] = v4.x; bv[4 * j + 1] = v4.y; bv[4 * j + 2] = v4.z; bv[4 * j + 3] = v4.w;
+            }
+            float sm[16];
+            const uint8_t* lrow = smem_gen + (act_base - smem_base) + u * RB_ABYTES + row * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (!p.skips_init) q = *reinterpret_cast<const float4*>(lrow + (((4 * h + j) ^ sw) << 4));
+              sm[4 * j] = q.x; sm[4 * j + 1] = q.y; sm[4 * j + 2] = q.z; sm[4 * j + 3] = q.w;
+            }
+            tmem_wait_ld();
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 16; i += 2)
+              pk[i >> 1] = pack_bf16x2(leaky(sm[i] + (a[i] + bv[i])), leaky(sm[i + 1] + (a[i + 1] + bv[i + 1])));
+            // bf16 row of 64 channels = 8 sixteen-byte pieces; this thread's 16 channels are pieces (u&1)*4 + 2h, +1
+            uint8_t* orow = smem_gen + (stg_base - smem_base) + (u >> 1) * RB_ABYTES + row * 128;
+            const int c16 = (u & 1) * 4 + 2 * h;
+            *reinterpret_cast<uint4*>(orow + ((c16 ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(orow + (((c16 + 1) ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+          fence_proxy_async_smem();
+          epi_bar();
+          if (issuer) {
+#pragma unroll
+            for (int g = 0; g < K::KB / 2; ++g)
+              tma_store_3d(&map_act, stg_base + g * RB_ABYTES, w0 * 32 + g * 64, t0, b);
+            bulk_commit();
+          }
+        }
+      } else
 #pragma unroll 1
       for (int rr = 0; rr < C / 64; ++rr) {
         float v[2][16];
@@ -878,6 +945,9 @@ extern "C" int wnb200_resblock_fwd_tc(const wnb200_resblock_t* a, void* stream) 
   for (int j = 0; j < 3; ++j) p.t_off[j] = a->t_off[j];
   p.bias1 = a->bias1; p.bias2 = a->bias2;
   p.write_res = a->res != nullptr; p.skips_init = a->skips_init;
+  p.final_act = a->skips_act != nullptr;
+  WNB_CHECK_ARG(!p.final_act || (a->variant != 1 && !a->save_act && !a->res),
+                "resblock_fwd_tc: skips_act needs the CTA-pair kernel, the last layer (res = NULL) and no saved factors");
   p.dbg = (long long*)a->dbg;
   p.save_act = (bf16*)a->save_act; p.save_th = (bf16*)a->save_th; p.save_sg = (bf16*)a->save_sg;
   WNB_CHECK_ARG(!a->save_act || (a->save_th && a->save_sg && a->variant != 1),
@@ -903,8 +973,10 @@ extern "C" int wnb200_resblock_fwd_tc(const wnb200_resblock_t* a, void* stream) 
       return C == 256 ? launch_resblock2<256, true>(mx, mw1, mw2, mres, msk, mact, mth, msg, p, st)
                       : launch_resblock2<128, true>(mx, mw1, mw2, mres, msk, mact, mth, msg, p, st);
     }
-    return C == 256 ? launch_resblock2<256, false>(mx, mw1, mw2, mres, msk, mx, mx, mx, p, st)
-                    : launch_resblock2<128, false>(mx, mw1, mw2, mres, msk, mx, mx, mx, p, st);
+    CUtensorMap mfin = mx;
+    if (p.final_act && (rc = rb_map_nlc(&mfin, a->skips_act, a->B, a->T, C, 2))) return rc;
+    return C == 256 ? launch_resblock2<256, false>(mx, mw1, mw2, mres, msk, mfin, mx, mx, p, st)
+                    : launch_resblock2<128, false>(mx, mw1, mw2, mres, msk, mfin, mx, mx, p, st);
   }
   return C == 256 ? launch_resblock<256>(mx, mw1, mw2, mres, msk, p, st)
                   : launch_resblock<128>(mx, mw1, mw2, mres, msk, p, st);

@@ -115,7 +115,10 @@ def chain(x_nlc, C, offsets, epi1, w1, b1, n1, n2=0, use_x2=0, epi2=0, w2=None, 
 RESBLOCK_VARIANT = int(__import__("os").environ.get("WNB200_RESBLOCK_VARIANT", "0"))
 
 
-def resblock(x_nlc, pk, res, skips, skips_init, dbg=None, variant=None, save=None):
+FUSE_FINAL = True     # last layer of an inference stack emits LeakyReLU(skip sum) as bf16 itself (no separate pass)
+
+
+def resblock(x_nlc, pk, res, skips, skips_init, dbg=None, variant=None, save=None, skips_act=None):
     """Pipelined fused block (C = 128 / 256).  variant 0/2 = CTA-pair kernel, 1 = single-CTA kernel.
     save = (gate, th, sg) NLC bf16 buffers: training keeps the gate and its two factors for backward."""
     a = _lib.ResBlock()
@@ -130,6 +133,7 @@ def resblock(x_nlc, pk, res, skips, skips_init, dbg=None, variant=None, save=Non
     a.res, a.skips, a.dbg = p(res), p(skips), p(dbg)
     if save is not None:
         a.save_act, a.save_th, a.save_sg = p(save[0]), p(save[1]), p(save[2])
+    a.skips_act = p(skips_act)
     _lib.current_tag = "resblock"
     try:
         _lib.call("wnb200_resblock_fwd_tc", ctypes.byref(a), ops._stream())
@@ -261,11 +265,16 @@ def run_blocks(h, blocks, bottlenecks, packs, skips, first_init, want_act):
     buf = [h, torch.empty_like(h)]
     n = len(packs)
     if C in (128, 256):
+        fuse = want_act and FUSE_FINAL and RESBLOCK_VARIANT != 1
+        skips_act = torch.empty_like(h) if fuse else None
         for l, pk in enumerate(packs):
             last = l == n - 1
-            resblock(buf[0], pk, None if last else buf[1], skips, first_init and l == 0)
+            resblock(buf[0], pk, None if last else buf[1], skips, first_init and l == 0,
+                     skips_act=skips_act if last else None)
             if not last:
                 buf = [buf[1], buf[0]]
+        if fuse:
+            return buf[0], skips_act
         return buf[0], (leaky_to_bf16(skips) if want_act else None)
     skips_act = torch.empty_like(h) if want_act else None
     for l, pk in enumerate(packs):
