@@ -236,6 +236,10 @@ int wnb200_dense_fwd_tc(const wnb200_dense_t* args /*host*/, void* stream);
 int wnb200_featurize_nlc(int dtype, int B, int T, int F, int fk, const void* x, const float* w, const float* bias,
                          void* y, void* stream);
 
+/* Backward of the above: dh NLC bf16 [B, floor(T/pool), C] -> dx NCL [B, C, T] (bf16 or fp32),
+ * dx[b,c,t] = dh[b, t/pool, c] / pool for t < floor(T/pool)*pool, 0 after (autograd of nn.AvgPool1d). */
+int wnb200_avgpool_bwd_nlc_to_ncl(int dtype_out, int B, int C, int T, int pool, const void* dh, void* dx, void* stream);
+
 /* WaveNet entry conv (wavenet.py:54,93) on quantised LEVELS instead of their one-hot encoding (fns.py:6-15,
  * pore_model.py:88-96): y[b,t,:] = bias + sum_j wemb[j][levels[b,t+t_off[j]]][:], taps outside [0,T) contribute nothing.
  * levels int32 [B,T] (clamped to [0,in_dim)), wemb bf16 [ntaps][in_dim][C] (= conv weight [C,in_dim,ntaps] permuted),

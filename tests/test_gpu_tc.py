@@ -50,6 +50,29 @@ def test_avgpool_to_nlc(B, C, T, pool, dt):
         assert (y.float().cpu() - ref).abs().max() <= 2 ** -7 * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("B,C,T,pool", [(2, 256, 1001, 3), (1, 128, 16383, 3), (2, 64, 130, 2), (1, 72, 64, 1),
+                                        (2, 64, 999, 7), (1, 64, 2, 3), (3, 128, 200, 65)])
+def test_avgpool_bwd_from_nlc(B, C, T, pool, dt):
+    """Backward of AvgPool1d (classifier.py:102) fused with the NLC -> NCL layout change, against autograd."""
+    from wavenet_speech_b200 import _lib, ops
+    torch.manual_seed(T + pool)
+    To = T // pool
+    dh = torch.randn(B, To, C).bfloat16()
+    x = torch.zeros(B, C, T, requires_grad=True)
+    if To > 0:
+        torch.nn.functional.avg_pool1d(x, pool).backward(dh.float().permute(0, 2, 1))
+        ref = x.grad
+    else:
+        ref = torch.zeros(B, C, T)
+    dx = torch.full((B, C, T), 7.0, dtype=dt, device="cuda")
+    _lib.call("wnb200_avgpool_bwd_nlc_to_ncl", 1 if dt == torch.bfloat16 else 0, B, C, T, pool, ops._p(dh.cuda()),
+              ops._p(dx), ops._stream())
+    torch.cuda.synchronize()
+    want = ref.to(dt).float() if dt == torch.bfloat16 else ref
+    assert torch.equal(dx.float().cpu(), want)
+
+
 @pytest.mark.parametrize("C,k,T,B", [(64, 2, 128, 1), (64, 1, 200, 2), (128, 2, 300, 2), (256, 2, 257, 2),
                                      (256, 3, 100, 1)])
 def test_single_contraction(C, k, T, B):

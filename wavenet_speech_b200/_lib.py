@@ -82,6 +82,7 @@ SIGNATURES = {
     "wnb200_dense_fwd_tc": [ctypes.POINTER(Dense), c_void_p],
     "wnb200_featurize_nlc": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_avgpool_ncl_to_nlc_bf16": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "wnb200_avgpool_bwd_nlc_to_ncl": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "wnb200_entry_embed_nlc": [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32), c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p],
     "wnb200_wgrad_tc": [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],

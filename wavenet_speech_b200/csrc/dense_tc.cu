@@ -538,9 +538,68 @@ entry_embed_nlc_kernel(long long frames, int Tn, int C, int in_dim, int ntaps, i
   }
 }
 
+// Backward of the mean-pool + layout change above, fused the other way round: the classifier's input gradient
+// dh [B, To, C] (NLC bf16) -> dx [B, C, T] (NCL): dx[b, c, t] = dh[b, t / pool, c] / pool for t < To * pool, 0 after
+// (autograd of nn.AvgPool1d, classifier.py:102).  [64 pooled frames x 64 channels] tiles through shared memory; a
+// warp owns 8 channels, its lanes walk pooled frames and write the `pool` copies -- no division in the loop.
+template <typename TO>
+__global__ void __launch_bounds__(256)
+avgpool_bwd_nlc_to_ncl_kernel(int C, int Tn, int To, int pool, const bf16* __restrict__ dh, TO* __restrict__ dx) {
+  __shared__ __align__(16) bf16 tile[64][72];      // [pooled frame][channel]
+  const int b = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 64 * 8; i += 256) {
+    const int pf = i >> 3, v = i & 7;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (p0 + pf < To && c0 + v * 8 + 8 <= C)
+      val = __ldg(reinterpret_cast<const uint4*>(dh + ((long long)b * To + p0 + pf) * C + c0 + v * 8));
+    *reinterpret_cast<uint4*>(&tile[pf][v * 8]) = val;
+  }
+  __syncthreads();
+  const float fpool = (float)pool;                 // a true division, like autograd's grad / kernel_size
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + warp * 8 + j;
+    if (c >= C) break;
+    TO* row = dx + ((long long)b * C + c) * Tn;
+    for (int pf = lane; pf < 64; pf += 32) {
+      if (p0 + pf >= To) break;
+      const TO val = from_f32<TO>(__fdiv_rn(__bfloat162float(tile[pf][warp * 8 + j]), fpool));
+      TO* dst = row + (long long)(p0 + pf) * pool;
+      for (int k = 0; k < pool; ++k) dst[k] = val;
+    }
+    if (p0 + 64 >= To)                             // this tile ends the pooled range: zero the tail [To * pool, T)
+      for (int t = To * pool + lane; t < Tn; t += 32) row[t] = from_f32<TO>(0.f);
+  }
+}
+
 }  // namespace wnb
 
 using namespace wnb;
+
+extern "C" int wnb200_avgpool_bwd_nlc_to_ncl(int dtype_out, int B, int C, int T_, int pool, const void* dh, void* dx,
+                                             void* stream) {
+  WNB_CHECK_ARG(dtype_out == WNB200_F32 || dtype_out == WNB200_BF16, "avgpool_bwd_nlc_to_ncl: bad dtype");
+  WNB_CHECK_ARG(pool >= 1 && C % 8 == 0, "avgpool_bwd_nlc_to_ncl: pool >= 1 and C %% 8 == 0 required");
+  if (B == 0 || C == 0 || T_ == 0) return 0;
+  WNB_CHECK_ARG(dx != nullptr, "avgpool_bwd_nlc_to_ncl: null pointer");
+  const int To = T_ / pool;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t es = dtype_out == WNB200_F32 ? 4 : 2;
+  if (To == 0) {
+    WNB_CUDA_OK(cudaMemsetAsync(dx, 0, (size_t)B * C * T_ * es, st));
+    return 0;
+  }
+  WNB_CHECK_ARG(dh != nullptr, "avgpool_bwd_nlc_to_ncl: null pointer");
+  WNB_CHECK_ARG(B <= 65535 && ceil_div(C, 64) <= 65535, "avgpool_bwd_nlc_to_ncl: shape too large");
+  dim3 grid(ceil_div(To, 64), ceil_div(C, 64), B);
+  if (dtype_out == WNB200_F32)
+    avgpool_bwd_nlc_to_ncl_kernel<float><<<grid, 256, 0, st>>>(C, T_, To, pool, (const bf16*)dh, (float*)dx);
+  else
+    avgpool_bwd_nlc_to_ncl_kernel<bf16><<<grid, 256, 0, st>>>(C, T_, To, pool, (const bf16*)dh, (bf16*)dx);
+  WNB_LAUNCH_OK();
+  return 0;
+}
 
 extern "C" int wnb200_entry_embed_nlc(int B, int T_, int C, int in_dim, int ntaps, const int32_t* t_off,
                                       const int32_t* levels, const void* wemb, const float* bias, void* y,

@@ -445,7 +445,10 @@ class _ClassifierTrain(torch.autograd.Function):
         dh0, gl = stack_backward(pk["stack"], saved, dskips, need_dx)
         dseq = None
         if need_dx:
-            dseq = ops.avgpool_bwd(FP.nlc_to_ncl(dh0, ctx.in_dtype), ctx.T, model.pool_kernel_size)
+            B, _To, C = dh0.shape                 # layout change + AvgPool1d backward in one pass
+            dseq = torch.empty((B, C, ctx.T), dtype=ctx.in_dtype, device=dh0.device)
+            _lib.call("wnb200_avgpool_bwd_nlc_to_ncl", ops._DT[ctx.in_dtype], B, C, ctx.T, model.pool_kernel_size,
+                      ops._p(dh0.contiguous()), ops._p(dseq), ops._stream())
         grads = [g for layer in gl for g in layer] + ghead
         return (None, None, dseq) + _cast(grads, params)
 
