@@ -227,6 +227,8 @@ typedef struct {
   const float* bias;
   void* y;
   const void* x2;         /* NULL = single source */
+  float* colsum;          /* mode 0, optional: fp32 [N], += the column sums of y over all frames (the bias gradient of
+                             the contraction that consumes y as its output gradient: autograd of conv biases) */
 } wnb200_dense_t;
 int wnb200_dense_fwd_tc(const wnb200_dense_t* args /*host*/, void* stream);
 

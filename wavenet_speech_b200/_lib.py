@@ -47,7 +47,7 @@ class Dense(ctypes.Structure):
                 ("leaky", ctypes.c_int32), ("n_out", ctypes.c_int32), ("softmax", ctypes.c_int32),
                 ("out_f32", ctypes.c_int32), ("Cin2", ctypes.c_int32), ("ntaps2", ctypes.c_int32),
                 ("t_off2", ctypes.c_int32 * 3), ("x", c_void_p), ("w", c_void_p),
-                ("bias", c_void_p), ("y", c_void_p), ("x2", c_void_p)]
+                ("bias", c_void_p), ("y", c_void_p), ("x2", c_void_p), ("colsum", c_void_p)]
 
 
 # name -> argtypes (return type is int unless listed in _RESTYPES)

@@ -31,6 +31,7 @@ struct DenseDev {
   int n_out, softmax, out_f32, tma_out;
   const float* bias;
   void* out;        // HEAD direct-store fallback: NCL [B, n_out, T]
+  float* colsum;    // NLC mode, optional: fp32 [N] += column sums of the (bf16-rounded) output over all valid frames
 };
 
 constexpr int DN_THREADS = 320;
@@ -158,6 +159,9 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       epi_bar();
     }
     uint32_t nchunk = 0;
+    float csum[4] = {0.f, 0.f, 0.f, 0.f};        // column sums: thread -> column (tid & 63) of each 64-channel chunk,
+    const int cs_col = (threadIdx.x - 64) & 63;  // rows [32 rq, 32 rq + 32) of the tile
+    const int cs_rq = (threadIdx.x - 64) >> 6;
     int it = 0;
     for (int pt = pair; pt < p.num_tiles; pt += npairs, ++it) {
       const int b = pt / p.tiles_per_seq;
@@ -202,6 +206,21 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
           if (issuer) {
             tma_store_3d(&map_y, stg_base + boff, c * 64, t0, b);
             bulk_commit();
+          }
+          if (p.colsum) {
+            // bias gradient of the NEXT contraction for free: the staged tile is summed over its valid frames while
+            // the TMA store reads it (the buffer is rewritten two chunks and two barriers from now)
+            const int nvalid = min(RB_TILE, p.T - t0) - cs_rq * 32;
+            const uint8_t* sb = smem_gen + (stg_base - smem_base) + boff + (cs_rq * 32) * 128 + (cs_col & 7) * 2;
+            const int ch16 = cs_col >> 3;
+            float acc = 0.f;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr)
+              if (rr < nvalid)
+                acc += __bfloat162float(*reinterpret_cast<const bf16*>(sb + rr * 128 + ((ch16 ^ (rr & 7)) << 4)));
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (q == c) csum[q] += acc;
           }
         }
       } else {
@@ -288,6 +307,8 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       tc_fence_before();
       mbar_arrive_cluster(mapa_shared(acc_empty(r), 0));
     }
+    if (p.colsum && p.mode == 0)
+      for (int q = 0; q < p.N / 64; ++q) atomicAdd(p.colsum + q * 64 + cs_col, csum[q]);
     if (issuer) bulk_wait0();
   }
 
@@ -642,6 +663,7 @@ extern "C" int wnb200_dense_fwd_tc(const wnb200_dense_t* a, void* stream) {
   p.N = a->N; p.mode = a->mode; p.leaky = a->leaky;
   p.n_out = a->n_out; p.softmax = a->softmax; p.out_f32 = a->out_f32;
   p.bias = a->bias; p.out = a->y;
+  p.colsum = a->mode == 0 ? a->colsum : nullptr;
   const int esize = a->out_f32 ? 4 : 2;
   p.tma_out = (a->mode == 1 && ((long long)a->T * esize) % 16 == 0) ? 1 : 0;
   CUtensorMap mx, mx2, mw, my;

@@ -141,9 +141,10 @@ def resblock(x_nlc, pk, res, skips, skips_init, dbg=None, variant=None, save=Non
         _lib.current_tag = None
 
 
-def dense(x_nlc, offsets, w, bias, N, mode=0, leaky=0, out=None, n_out=0, softmax=0, x2=None, offsets2=()):
+def dense(x_nlc, offsets, w, bias, N, mode=0, leaky=0, out=None, n_out=0, softmax=0, x2=None, offsets2=(), colsum=None):
     """CTA-pair dense contraction.  mode 0 -> NLC bf16 [B,T,N]; mode 1 -> NCL `out` [B,n_out,T].
-    Optional second source x2 [B,T,Cin2] with its own taps: its columns follow x's in `w`."""
+    Optional second source x2 [B,T,Cin2] with its own taps: its columns follow x's in `w`.
+    colsum (mode 0): fp32 [N] tensor that the column sums of the output are ADDED to."""
     B, T, Cin = x_nlc.shape
     a = _lib.Dense()
     a.B, a.T, a.Cin, a.ntaps = B, T, Cin, len(offsets)
@@ -154,6 +155,9 @@ def dense(x_nlc, offsets, w, bias, N, mode=0, leaky=0, out=None, n_out=0, softma
         out = torch.empty((B, T, N), dtype=torch.bfloat16, device=x_nlc.device)
     a.out_f32 = 1 if out.dtype == torch.float32 else 0
     a.x, a.w, a.bias, a.y = x_nlc.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr()
+    if colsum is not None:
+        assert mode == 0 and colsum.dtype == torch.float32 and colsum.numel() >= N
+        a.colsum = colsum.data_ptr()
     if x2 is not None:
         assert x2.shape[:2] == x_nlc.shape[:2]
         a.x2, a.Cin2, a.ntaps2 = x2.data_ptr(), x2.shape[2], len(offsets2)

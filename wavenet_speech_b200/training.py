@@ -231,7 +231,8 @@ def stack_forward(h0, stack, skips):
 
 
 def stack_backward(stack, saved, dskips, need_dx0):
-    """-> (dh0 or None, list of per-layer parameter gradients in Stack.params() order, fp32)."""
+    """-> (dh0 or None, list of per-layer parameter gradients in Stack.params() order, fp32).  The column sums of dh0
+    (the bias gradient of whatever produced the stack's input) are left in `stack_backward.dh0_colsum`."""
     B, T, C = dskips.shape
     dev = dskips.device
     zb = _zeros(C, dev)
@@ -239,7 +240,7 @@ def stack_backward(stack, saved, dskips, need_dx0):
     L = len(saved)
     grads = [None] * L
     Ms = [None] * L
-    dres = None
+    dres = dres_cs = None
     for l in range(L - 1, -1, -1):
         x, act, th, sg = saved[l]
         pb, offs = stack.bwd[l], stack.fwd[l]["offsets"]
@@ -250,13 +251,14 @@ def stack_backward(stack, saved, dskips, need_dx0):
             dg = FP.dense(dres, [0], pb["wdg"], zb, C, x2=dskips, offsets2=[0])
         dab, dbab = gate_bwd_nlc(dg, th, sg, want_bias=True)
         del dg
-        dx = None
+        dx = dx_cs = None
         if l > 0 or need_dx0:
             neg = [-o for o in offs]
+            dx_cs = _zeros(C, dev)               # column sums of dx come out of the same launch (bias gradients below)
             if dres is None:
-                dx = FP.dense(dab, neg, pb["wdx_taps"], zb, C)
+                dx = FP.dense(dab, neg, pb["wdx_taps"], zb, C, colsum=dx_cs)
             else:
-                dx = FP.dense(dab, neg, pb["wdx"], zb, C, x2=dres, offsets2=[0])
+                dx = FP.dense(dab, neg, pb["wdx"], zb, C, x2=dres, offsets2=[0], colsum=dx_cs)
         dwab = wgrad_multi(dab, 2 * C, [(x, offs[j]) for j in range(k)])            # k x [2C, C]
         dwt = torch.stack([d[:C] for d in dwab], 2)
         dws = torch.stack([d[C:] for d in dwab], 2)
@@ -264,11 +266,12 @@ def stack_backward(stack, saved, dskips, need_dx0):
         if dres is not None:
             dwres, dwproj = wgrad_multi(dres, C, [(act, 0), (x, 0)])
             dwres = dwres.unsqueeze(2)
-            dbres = colsum(dres)
+            dbres = dres_cs
         Ms[l] = wgrad_rows(dskips, act, 0, C, C)
         grads[l] = [dwt, dbab[:C], dws, dbab[C:], dwres, dbres, None, None, dwproj, dbres, None, csk]
         saved[l] = None                                     # free this layer's activations
-        dres = dx
+        dres, dres_cs = dx, dx_cs
+    stack_backward.dh0_colsum = dres_cs
     # weight-space algebra of the folded skip -> bottleneck product, batched over layers
     M = torch.stack(Ms)                                                               # [L, C, C]
     wbn = torch.stack([n.weight.detach().float()[:, :, 0] for n in stack.necks])
@@ -381,7 +384,7 @@ class _WaveNetTrain(torch.autograd.Function):
         dh0, gl = stack_backward(pk["stack"], saved, dskips, True)
         C, in_dim = dh0.shape[2], x.shape[2]
         dwe = torch.stack(wgrad_multi(dh0, C, [(x, o) for o in offs]), 2)
-        dbe = colsum(dh0)
+        dbe = stack_backward.dh0_colsum
         dsignal = None
         if ctx.needs_input_grad[2]:
             dxn = FP.dense(dh0, [-o for o in offs], pk["entry_wt"], _zeros(in_dim, dh0.device), in_dim)
