@@ -747,7 +747,7 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       tc_fence_after();
       if (issuer && rank == 0) RB_STAMP(11);
       constexpr int NBUF = K::KB + 2;            // gate blocks, then the two staging buffers
-      if (!SAVE && p.final_act) {
+      if (p.final_act) {
         // Last layer of an inference stack (wavenet.py:100-103): nothing accumulates after this launch, so instead
         // of adding the tile into the running sum and leaving LeakyReLU + bf16 conversion to another pass over it,
         // the running sum's fp32 chunks come IN by TMA (KB at a time, into the idle gate blocks), meet the
@@ -806,7 +806,7 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           if (issuer) {
 #pragma unroll
             for (int g = 0; g < K::KB / 2; ++g)
-              tma_store_3d(&map_act, stg_base + g * RB_ABYTES, w0 * 32 + g * 64, t0, b);
+              tma_store_3d(&map_res, stg_base + g * RB_ABYTES, w0 * 32 + g * 64, t0, b);   // (res is not written)
             bulk_commit();
           }
         }
@@ -946,8 +946,8 @@ extern "C" int wnb200_resblock_fwd_tc(const wnb200_resblock_t* a, void* stream) 
   p.bias1 = a->bias1; p.bias2 = a->bias2;
   p.write_res = a->res != nullptr; p.skips_init = a->skips_init;
   p.final_act = a->skips_act != nullptr;
-  WNB_CHECK_ARG(!p.final_act || (a->variant != 1 && !a->save_act && !a->res),
-                "resblock_fwd_tc: skips_act needs the CTA-pair kernel, the last layer (res = NULL) and no saved factors");
+  WNB_CHECK_ARG(!p.final_act || (a->variant != 1 && !a->res),
+                "resblock_fwd_tc: skips_act needs the CTA-pair kernel and the last layer (res = NULL)");
   p.dbg = (long long*)a->dbg;
   p.save_act = (bf16*)a->save_act; p.save_th = (bf16*)a->save_th; p.save_sg = (bf16*)a->save_sg;
   WNB_CHECK_ARG(!a->save_act || (a->save_th && a->save_sg && a->variant != 1),
@@ -963,6 +963,8 @@ extern "C" int wnb200_resblock_fwd_tc(const wnb200_resblock_t* a, void* stream) 
   if ((rc = rb_map_nlc(&msk, a->skips, a->B, a->T, C, 4))) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (pair) {
+    // last layer: the `res` map carries the bf16 head input instead
+    if (p.final_act && (rc = rb_map_nlc(&mres, a->skips_act, a->B, a->T, C, 2))) return rc;
     p.tiles_per_seq = ceil_div(a->T, 2 * RB_TILE);
     p.num_tiles = p.tiles_per_seq * a->B;
     if (a->save_act) {
@@ -973,10 +975,8 @@ extern "C" int wnb200_resblock_fwd_tc(const wnb200_resblock_t* a, void* stream) 
       return C == 256 ? launch_resblock2<256, true>(mx, mw1, mw2, mres, msk, mact, mth, msg, p, st)
                       : launch_resblock2<128, true>(mx, mw1, mw2, mres, msk, mact, mth, msg, p, st);
     }
-    CUtensorMap mfin = mx;
-    if (p.final_act && (rc = rb_map_nlc(&mfin, a->skips_act, a->B, a->T, C, 2))) return rc;
-    return C == 256 ? launch_resblock2<256, false>(mx, mw1, mw2, mres, msk, mfin, mx, mx, p, st)
-                    : launch_resblock2<128, false>(mx, mw1, mw2, mres, msk, mfin, mx, mx, p, st);
+    return C == 256 ? launch_resblock2<256, false>(mx, mw1, mw2, mres, msk, mx, mx, mx, p, st)
+                    : launch_resblock2<128, false>(mx, mw1, mw2, mres, msk, mx, mx, mx, p, st);
   }
   return C == 256 ? launch_resblock<256>(mx, mw1, mw2, mres, msk, p, st)
                   : launch_resblock<128>(mx, mw1, mw2, mres, msk, p, st);

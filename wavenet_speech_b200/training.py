@@ -216,18 +216,20 @@ def _pool_floats(stack):
 
 
 def stack_forward(h0, stack, skips):
-    """Residual stack keeping (x, gate, th, sg) of every layer.  Returns the saved list."""
+    """Residual stack keeping (x, gate, th, sg) of every layer.  Returns (saved list, skips_act): the last launch emits
+    LeakyReLU(skip sum) as bf16 itself (the fp32 sum is not needed after the forward)."""
     saved = []
     h = h0
     n = len(stack.fwd)
+    skips_act = torch.empty_like(h0) if FP.FUSE_FINAL else None
     for l, pk in enumerate(stack.fwd):
         last = l == n - 1
         act, th, sg = torch.empty_like(h), torch.empty_like(h), torch.empty_like(h)
         res = None if last else torch.empty_like(h)
-        FP.resblock(h, pk, res, skips, l == 0, save=(act, th, sg))
+        FP.resblock(h, pk, res, skips, l == 0, save=(act, th, sg), skips_act=skips_act if last else None)
         saved.append((h, act, th, sg))
         h = res
-    return saved
+    return saved, skips_act
 
 
 def stack_backward(stack, saved, dskips, need_dx0):
@@ -285,10 +287,11 @@ def stack_backward(stack, saved, dskips, need_dx0):
     return dres, grads
 
 
-def head_forward(skips, hd, out_dtype, softmax):
+def head_forward(skips, hd, out_dtype, softmax, skips_act=None):
     """LeakyReLU -> 1x1 -> LeakyReLU -> 1x1 [-> softmax]; returns (out NCL, skips_act, h1)."""
     B, T, C = skips.shape
-    skips_act = FP.leaky_to_bf16(skips)
+    if skips_act is None:
+        skips_act = FP.leaky_to_bf16(skips)
     h1 = FP.dense(skips_act, [0], hd["w1"], hd["b1"], C, leaky=1)
     out = torch.empty((B, hd["n_out"], T), dtype=out_dtype, device=skips.device)
     FP.dense(h1, [0], hd["w2"], hd["b2"], hd["n2"], mode=1, out=out, n_out=hd["n_out"], softmax=softmax)
@@ -362,8 +365,8 @@ class _WaveNetTrain(torch.autograd.Function):
         offs = list(model.entry_conv1d.offsets)
         h0 = FP.dense(x, offs, pk["entry_w"], pk["entry_b"], C)
         skips = torch.empty((B, T, C), dtype=torch.float32, device=signal.device)
-        saved = stack_forward(h0, pk["stack"], skips)
-        out, skips_act, h1 = head_forward(skips, pk["head"], signal.dtype, model.softmax)
+        saved, sk_act = stack_forward(h0, pk["stack"], skips)
+        out, skips_act, h1 = head_forward(skips, pk["head"], signal.dtype, model.softmax, sk_act)
         del skips
         ctx.model, ctx.pk, ctx.params = model, pk, params
         ctx.keep = (x, offs, saved, skips_act, h1, out if model.softmax else None)
@@ -426,8 +429,8 @@ class _ClassifierTrain(torch.autograd.Function):
         h0 = torch.empty((B, To, C), dtype=torch.bfloat16, device=seq.device)
         _lib.call("wnb200_avgpool_ncl_to_nlc_bf16", ops._dt(seq), B, C, T, pool, ops._p(seq), ops._p(h0), ops._stream())
         skips = torch.empty((B, To, C), dtype=torch.float32, device=seq.device)
-        saved = stack_forward(h0, pk["stack"], skips)
-        out, skips_act, h1 = head_forward(skips, pk["head"], seq.dtype, model.softmax)
+        saved, sk_act = stack_forward(h0, pk["stack"], skips)
+        out, skips_act, h1 = head_forward(skips, pk["head"], seq.dtype, model.softmax, sk_act)
         ctx.model, ctx.pk, ctx.params = model, pk, params
         ctx.keep = (saved, skips_act, h1, out if model.softmax else None)
         ctx.T, ctx.in_dtype = T, seq.dtype
@@ -497,8 +500,8 @@ class _RawCTCNetTrain(torch.autograd.Function):
                   ops._p(f), ops._stream())
         h0 = FP.dense(f, [0], pk["f2w"], pk["f2b"], F, leaky=1)
         skips = torch.empty((B, To, C), dtype=torch.float32, device=seq.device)
-        saved = stack_forward(h0, pk["stack"], skips)
-        out, skips_act, h1 = head_forward(skips, pk["head"], seq.dtype, model.softmax)
+        saved, sk_act = stack_forward(h0, pk["stack"], skips)
+        out, skips_act, h1 = head_forward(skips, pk["head"], seq.dtype, model.softmax, sk_act)
         del skips
         ctx.model, ctx.pk, ctx.params = model, pk, params
         ctx.keep = (seq, f, saved, skips_act, h1, out if model.softmax else None)
