@@ -593,7 +593,7 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const int sw = row & 7;
     const uint32_t r_e1a = mapa_shared(e1a_done, 0), r_e1b = mapa_shared(e1b_done, 0),
                    r_e2a = mapa_shared(e2a_done, 0), r_e2b = mapa_shared(e2b_done, 0);
-    uint32_t ld_phase = 0;
+    uint32_t nchunk = 0, ld_phase = 0;
     int it = 0;
     for (int pt = pair; pt < p.num_tiles; pt += npairs, ++it) {
       const int b = pt / p.tiles_per_seq;
@@ -603,10 +603,6 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         mbar_wait(half == 0 ? accA_full : accB_full, 0u);
         tc_fence_after();
         if (issuer && rank == 0) RB_STAMP(8 + half);
-        if (half == 0 && it > 0) {       // the previous tile's skip rounds were staged in the gate blocks
-          if (issuer) bulk_wait_read0();
-          epi_bar();
-        }
         const uint32_t treg = (half == 0 ? tmemA : tmemB) + lane_off;
         if constexpr (SAVE) {
 #pragma unroll 1
@@ -688,65 +684,56 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         mbar_arrive_cluster(half == 0 ? r_e1a : r_e1b);
       }
 
-      // ---- E2: two chunks per round.  A round = TMEM loads of both chunks, one wait, both staging writes, one proxy
-      // fence, one barrier, two TMA operations: half as many latency chains per tile as one chunk per round.  `res` rounds
-      // go through the two staging buffers; `skips` rounds rotate over SIX buffers -- the gate tile's blocks are idle
-      // between G2s and the next E1a -- so a round never waits for the reduce-add of the round before it.
+      bool drain = SAVE;        // E1's stores still read the staging buffers: drain them before the first reuse
       // ---- E2a: res ----
       mbar_wait(accA_full, 1u);
       tc_fence_after();
       if (issuer && rank == 0) RB_STAMP(10);
       if (p.write_res) {
 #pragma unroll 1
-        for (int rr = 0; rr < C / 128; ++rr) {
-          uint32_t pk[2][16];
+        for (int c = 0; c < C / 64; ++c, ++nchunk) {
+          const int col = c * 64 + h * 32;
+          float a[32];
+          tmem_ld16(tmemA + lane_off + col, a);
+          tmem_ld16(tmemA + lane_off + col + 16, a + 16);
+          const float4* bp = reinterpret_cast<const float4*>(p.bias2 + col);
+          float bv[32];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int col = (2 * rr + u) * 64 + h * 32;
-            float a[32];
-            tmem_ld16(tmemA + lane_off + col, a);
-            tmem_ld16(tmemA + lane_off + col + 16, a + 16);
-            const float4* bp = reinterpret_cast<const float4*>(p.bias2 + col);
-            float bv[32];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 v4 = __ldg(bp + j);
-              bv[4 * j] = v4.x; bv[4 * j + 1] = v4.y; bv[4 * j + 2] = v4.z; bv[4 * j + 3] = v4.w;
-            }
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) pk[u][i >> 1] = pack_bf16x2(a[i] + bv[i], a[i + 1] + bv[i + 1]);
+          for (int j = 0; j < 8; ++j) {
+            const float4 u = __ldg(bp + j);
+            bv[4 * j] = u.x; bv[4 * j + 1] = u.y; bv[4 * j + 2] = u.z; bv[4 * j + 3] = u.w;
           }
-          if (issuer) bulk_wait_read0();         // both staging buffers free (E1's tanh / sigmoid stores under SAVE,
-          epi_bar();                             //  the previous round, the previous tile's skip rounds)
+          tmem_wait_ld();
+          uint32_t pk[16];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            uint8_t* srow = smem_gen + (stg_base - smem_base) + u * RB_ABYTES + row * 128;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(srow + (((4 * h + j) ^ sw) << 4)) =
-                  make_uint4(pk[u][4 * j], pk[u][4 * j + 1], pk[u][4 * j + 2], pk[u][4 * j + 3]);
+          for (int i = 0; i < 32; i += 2) pk[i >> 1] = pack_bf16x2(a[i] + bv[i], a[i + 1] + bv[i + 1]);
+          const uint32_t boff = (nchunk & 1u) * RB_ABYTES;
+          if (issuer) {
+            if (drain) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           }
+          drain = false;
+          epi_bar();
+          uint8_t* srow = smem_gen + (stg_base - smem_base) + boff + row * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(srow + (((4 * h + j) ^ sw) << 4)) =
+                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
           fence_proxy_async_smem();
           epi_bar();
           if (issuer) {
-            tma_store_3d(&map_res, stg_base, (2 * rr) * 64, t0, b);
-            tma_store_3d(&map_res, stg_base + RB_ABYTES, (2 * rr + 1) * 64, t0, b);
+            tma_store_3d(&map_res, stg_base + boff, c * 64, t0, b);
             bulk_commit();
           }
         }
-      } else if constexpr (SAVE) {               // (no res rounds to do the draining)
-        if (issuer) bulk_wait_read0();
-        epi_bar();
       }
       tc_fence_before();
       mbar_arrive_cluster(r_e2a);
 
       // ---- E2b: skips ----
-      mbar_wait(accB_full, 1u);                  // G2s complete: nothing reads the gate tile any more
+      mbar_wait(accB_full, 1u);
       tc_fence_after();
       if (issuer && rank == 0) RB_STAMP(11);
-      constexpr int NBUF = K::KB + 2;            // gate blocks, then the two staging buffers
       if (p.final_act) {
         // Last layer of an inference stack (wavenet.py:100-103): nothing accumulates after this launch, so instead
         // of adding the tile into the running sum and leaving LeakyReLU + bf16 conversion to another pass over it,
@@ -757,13 +744,15 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         for (int w0 = 0; w0 < C / 32; w0 += K::KB) {
           if (w0 > 0) epi_bar();                 // every thread is done with the previous wave's landing buffers
           if (issuer) {
+            // every store this thread issued has left shared memory: the previous wave's (staging buffers) and, when
+            // the gate factors are saved, E1's stores of the gate blocks the loads below land in
+            bulk_wait_read0();
             if (!p.skips_init) {
               mbar_expect_tx(ld_bar, K::KB * RB_ABYTES);
 #pragma unroll
               for (int u = 0; u < K::KB; ++u)
                 tma_load_3d(act_base + u * RB_ABYTES, &map_skips, ld_bar, (w0 + u) * 32, t0, b);
             }
-            bulk_wait_read0();                   // staging buffers: E2a's / the previous wave's stores have left
           }
           if (!p.skips_init) {
             mbar_wait(ld_bar, ld_phase);
@@ -812,52 +801,36 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
       } else
 #pragma unroll 1
-      for (int rr = 0; rr < C / 64; ++rr) {
-        float v[2][16];
+      for (int c = 0; c < C / 32; ++c, ++nchunk) {
+        const int col = c * 32 + h * 16;
+        float a[16];
+        tmem_ld16(tmemB + lane_off + col, a);
+        const float4* bp = reinterpret_cast<const float4*>(p.bias2 + C + col);
+        float bv[16];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int col = (2 * rr + u) * 32 + h * 16;
-          float a[16];
-          tmem_ld16(tmemB + lane_off + col, a);
-          const float4* bp = reinterpret_cast<const float4*>(p.bias2 + C + col);
-          float bv[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 v4 = __ldg(bp + j);
-            bv[4 * j] = v4.x; bv[4 * j + 1] = v4.y; bv[4 * j + 2] = v4.z; bv[4 * j + 3] = v4.w;
-          }
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[u][i] = a[i] + bv[i];
+        for (int j = 0; j < 4; ++j) {
+          const float4 u = __ldg(bp + j);
+          bv[4 * j] = u.x; bv[4 * j + 1] = u.y; bv[4 * j + 2] = u.z; bv[4 * j + 3] = u.w;
         }
-        const int i0 = (2 * rr) % NBUF;          // NBUF is even: a round's two buffers never straddle the wrap
-        const uint32_t buf0 = i0 < K::KB ? act_base + (uint32_t)i0 * RB_ABYTES : stg_base + (uint32_t)(i0 - K::KB) * RB_ABYTES;
-        const uint32_t buf1 = buf0 + RB_ABYTES;
-        if (2 * rr >= K::KB) {                   // staging buffers (E2a's stores) or a gate block used NBUF/2 rounds ago
-          if (issuer) {
-            if (NBUF / 2 - 1 >= 2 && rr >= 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
-            else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          }
-          epi_bar();
+        tmem_wait_ld();
+        const uint32_t boff = (nchunk & 1u) * RB_ABYTES;
+        if (issuer) {
+          if (drain) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         }
+        drain = false;
+        epi_bar();
+        uint8_t* srow = smem_gen + (stg_base - smem_base) + boff + row * 128;
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          uint8_t* srow = smem_gen + ((u ? buf1 : buf0) - smem_base) + row * 128;
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float4*>(srow + (((4 * h + j) ^ sw) << 4)) =
-                make_float4(v[u][4 * j], v[u][4 * j + 1], v[u][4 * j + 2], v[u][4 * j + 3]);
-        }
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(srow + (((4 * h + j) ^ sw) << 4)) =
+              make_float4(a[4 * j] + bv[4 * j], a[4 * j + 1] + bv[4 * j + 1], a[4 * j + 2] + bv[4 * j + 2],
+                          a[4 * j + 3] + bv[4 * j + 3]);
         fence_proxy_async_smem();
         epi_bar();
         if (issuer) {
-          if (p.skips_init) {
-            tma_store_3d(&map_skips, buf0, (2 * rr) * 32, t0, b);
-            tma_store_3d(&map_skips, buf1, (2 * rr + 1) * 32, t0, b);
-          } else {
-            tma_reduce_add_3d(&map_skips, buf0, (2 * rr) * 32, t0, b);
-            tma_reduce_add_3d(&map_skips, buf1, (2 * rr + 1) * 32, t0, b);
-          }
+          if (p.skips_init) tma_store_3d(&map_skips, stg_base + boff, c * 32, t0, b);
+          else tma_reduce_add_3d(&map_skips, stg_base + boff, c * 32, t0, b);
           bulk_commit();
         }
       }
