@@ -336,6 +336,10 @@ int wnb200_leaky_to_bf16(int64_t n, const float* x, void* y, void* stream);
 /* NCL (fp32/bf16) -> NLC bf16, and NLC (fp32/bf16) -> NCL (fp32/bf16): layout change at the module
  * boundary only (the reference's reshape_in/reshape_out, conv_ops.py:91-101, ran once per block). */
 int wnb200_ncl_to_nlc_bf16(int dtype, int B, int C, int T, const void* x, void* y, void* stream);
+/* Same for x[b,c,t] at x + b*sb + c*sc + t (element strides): a time slice of a longer tensor is read in place
+ * (legacy_code/train.py:30 feeds sig[:, :, 0:-1]). */
+int wnb200_ncl_to_nlc_bf16_strided(int dtype, int B, int C, int T, int64_t sb, int64_t sc, const void* x, void* y,
+                                   void* stream);
 int wnb200_nlc_to_ncl(int out_dtype, int src_is_f32, int B, int C, int T, const void* x, void* y, void* stream);
 
 #ifdef __cplusplus

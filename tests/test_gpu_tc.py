@@ -252,6 +252,29 @@ def test_last_layer_emits_head_input_bitwise(C, dil, T, B):
     assert torch.equal(y, ref)
 
 
+def test_time_slice_input_is_read_in_place():
+    """train.py:30 feeds sig[:, :, 0:-1]: the layout kernel reads the non-contiguous slice in place (no copy), for
+    inference and for the training forward / backward, with the same bits as a contiguous copy."""
+    torch.manual_seed(3)
+    C, T, B = 128, 520, 2
+    net = W.WaveNet(C, 2, [(C, C, 2, d) for d in (1, 2, 4)], C, softmax=False).cuda()
+    sig = torch.randn(B, C, T, device="cuda").bfloat16()
+    view = sig[:, :, 0:-1]
+    assert not view.is_contiguous()
+    with torch.no_grad():
+        assert torch.equal(net(view), net(view.contiguous()))
+    outs = []
+    for x in (view, view.contiguous()):
+        net.zero_grad(set_to_none=True)
+        y = net(x)
+        y.float().square().mean().backward()
+        outs.append((y.detach().clone(), net.entry_conv1d.conv1d.weight.grad.detach().clone()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    # (the weight-gradient kernels meet their per-CTA partial sums by fp32 reduce-add in no fixed order)
+    assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-3, atol=1e-7)
+    assert torch.equal(FP.ncl_to_nlc_bf16(sig[:, 3:77, 5:400].float()), FP.ncl_to_nlc_bf16(sig[:, 3:77, 5:400].float().contiguous()))
+
+
 def test_graphed_forward_replays_bitwise():
     """The whole forward captured in a CUDA graph (pipeline.GraphedForward) reproduces the eager result bit for bit,
     for new inputs as well, on the tensor-core and on the generic kernels."""

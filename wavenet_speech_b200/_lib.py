@@ -107,6 +107,7 @@ SIGNATURES = {
     "wnb200_siggen_onehot": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_leaky_to_bf16": [c_int64, c_void_p, c_void_p, c_void_p],
     "wnb200_ncl_to_nlc_bf16": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "wnb200_ncl_to_nlc_bf16_strided": [c_int, c_int, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p],
     "wnb200_nlc_to_ncl": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
 }
 _RESTYPES = {"wnb200_last_error": ctypes.c_char_p, "wnb200_ctc_workspace_bytes": ctypes.c_size_t}

@@ -322,16 +322,19 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
 
 // NCL -> NLC bf16: 64 x 64 (channels x frames) tiles through shared memory, 16/32-byte accesses on both sides
 template <typename T>
-__global__ void __launch_bounds__(256) ncl_to_nlc_v2_kernel(int C, int Tn, const T* x, bf16* y) {
+__global__ void __launch_bounds__(256) ncl_to_nlc_v2_kernel(int C, int Tn, long long sb, long long sc, bool vec,
+                                                            const T* x, bf16* y) {
+  // x[b, c, t] at x + b * sb + c * sc + t: a (B, C, T) tensor or a time slice of a longer one (train.py:30 feeds
+  // sig[:, :, 0:-1]) is read in place; `vec`: every row starts 16-byte aligned
   __shared__ __align__(16) bf16 tile[64][72];     // [frame][channel], 144-byte rows
   const int b = blockIdx.z, c0 = blockIdx.y * 64, t0 = blockIdx.x * 64;
   const int tid = threadIdx.x;
   {   // load: thread -> (channel = tid % 64, 16 consecutive frames)
     const int c = tid & 63, tq = (tid >> 6) * 16;
-    const T* src = x + ((long long)b * C + (c0 + c)) * Tn + t0 + tq;
+    const T* src = x + (long long)b * sb + (long long)(c0 + c) * sc + t0 + tq;
     bf16 v[16];
     const bool cok = (c0 + c) < C;
-    if (cok && t0 + tq + 16 <= Tn && (Tn % 8 == 0) && sizeof(T) == 2) {
+    if (cok && t0 + tq + 16 <= Tn && vec && sizeof(T) == 2) {
       *reinterpret_cast<uint4*>(&v[0]) = __ldg(reinterpret_cast<const uint4*>(src));
       *reinterpret_cast<uint4*>(&v[8]) = __ldg(reinterpret_cast<const uint4*>(src) + 1);
     } else {
@@ -694,17 +697,26 @@ extern "C" int wnb200_dense_fwd_tc(const wnb200_dense_t* a, void* stream) {
   return 0;
 }
 
-extern "C" int wnb200_ncl_to_nlc_bf16(int dtype, int B, int C, int T_, const void* x, void* y, void* stream) {
+extern "C" int wnb200_ncl_to_nlc_bf16_strided(int dtype, int B, int C, int T_, int64_t sb, int64_t sc, const void* x,
+                                              void* y, void* stream) {
   WNB_CHECK_ARG(dtype == WNB200_F32 || dtype == WNB200_BF16, "ncl_to_nlc_bf16: bad dtype");
   if (B == 0 || C == 0 || T_ == 0) return 0;
   WNB_CHECK_ARG(x && y, "ncl_to_nlc_bf16: null pointer");
   WNB_CHECK_ARG(B <= 65535 && ceil_div(C, 64) <= 65535, "ncl_to_nlc_bf16: shape too large");
+  WNB_CHECK_ARG(sc >= T_ && sb >= 0, "ncl_to_nlc_bf16: bad strides");
   dim3 grid(ceil_div(T_, 64), ceil_div(C, 64), B);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == WNB200_F32) ncl_to_nlc_v2_kernel<float><<<grid, 256, 0, st>>>(C, T_, (const float*)x, (bf16*)y);
-  else ncl_to_nlc_v2_kernel<bf16><<<grid, 256, 0, st>>>(C, T_, (const bf16*)x, (bf16*)y);
+  const bool vec = dtype == WNB200_BF16 && sb % 8 == 0 && sc % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  if (dtype == WNB200_F32)
+    ncl_to_nlc_v2_kernel<float><<<grid, 256, 0, st>>>(C, T_, sb, sc, vec, (const float*)x, (bf16*)y);
+  else
+    ncl_to_nlc_v2_kernel<bf16><<<grid, 256, 0, st>>>(C, T_, sb, sc, vec, (const bf16*)x, (bf16*)y);
   WNB_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int wnb200_ncl_to_nlc_bf16(int dtype, int B, int C, int T_, const void* x, void* y, void* stream) {
+  return wnb200_ncl_to_nlc_bf16_strided(dtype, B, C, T_, (int64_t)C * T_, (int64_t)T_, x, y, stream);
 }
 
 extern "C" int wnb200_featurize_nlc(int dtype, int B, int T_, int F, int fk, const void* x, const float* w,

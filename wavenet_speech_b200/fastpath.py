@@ -213,10 +213,15 @@ def leaky_to_bf16(x):
 
 
 def ncl_to_nlc_bf16(x):
-    x = x.contiguous()
+    """(B, C, T) -> NLC bf16 (B, T, C).  A tensor whose frames are contiguous (stride 1 along T, e.g. the time slice
+    sig[:, :, 0:-1] of train.py:30) is read in place; anything else is made contiguous first."""
     B, C, T = x.shape
+    if B * C * T > 0 and not (x.stride(2) == 1 and x.stride(1) >= T and x.stride(0) >= 0):
+        x = x.contiguous()
     y = torch.empty((B, T, C), dtype=torch.bfloat16, device=x.device)
-    _lib.call("wnb200_ncl_to_nlc_bf16", ops._dt(x), B, C, T, ops._p(x), ops._p(y), ops._stream())
+    if B * C * T > 0:
+        _lib.call("wnb200_ncl_to_nlc_bf16_strided", ops._dt(x), B, C, T, x.stride(0), x.stride(1), ops._p(x), ops._p(y),
+                  ops._stream())
     return y
 
 

@@ -23,7 +23,9 @@ def train_step(wavenet, ctcnet, sig, seq, lengths, opt, batch_size=None, average
     opt.zero_grad(set_to_none=True)
     pred = wavenet(sig[:, :, 0:-1])                                        # train.py:30
     trans = ctcnet(pred)                                                   # train.py:33
-    dense = ops.argmax_channels(sig[:, :, 1:].contiguous())                # train.py:36
+    # train.py:36 -- the per-frame argmax of the WHOLE signal, then the shift: the same integers as argmax(sig[:, :, 1:])
+    # without copying the (B, levels, T-1) slice, and on rows that stay 16-byte aligned
+    dense = ops.argmax_channels(sig)[:, 1:].contiguous()
     xe = WF.cross_entropy_sum(pred, dense) / B                             # train.py:37-39 (batch mean per frame)
     labels = seq.to(device=sig.device, dtype=torch.int32)
     if labels_are_zero_based:

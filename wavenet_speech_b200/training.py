@@ -406,7 +406,7 @@ def wavenet_train_eligible(model, signal):
 def wavenet_forward_train(model, signal):
     ops.check_device()
     pk = FP._cached(model, "wavenet_train", lambda: _wavenet_pack(model))
-    return _WaveNetTrain.apply(model, pk, signal.contiguous(), *_wavenet_params(model, pk))
+    return _WaveNetTrain.apply(model, pk, signal, *_wavenet_params(model, pk))     # (time slices are read in place)
 
 
 # --------------------------------------------------------------------------- WaveNetClassifier
