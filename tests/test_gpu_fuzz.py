@@ -145,3 +145,48 @@ def test_dense_kernel_random_shapes(i, Cin, N, offs, two, Cin2, offs2, T, B, lea
     assert rel(y.float().permute(0, 2, 1), ref) <= 1e-2
     want_cs = y.float().sum((0, 1))                       # sums of the bf16-rounded outputs, as a colsum launch would see
     assert torch.allclose(cs, want_cs, rtol=1e-4, atol=1e-3 * max(1.0, float(want_cs.abs().max())))
+
+
+def _net_cases(n):
+    rng = random.Random(4242)
+    out = []
+    for i in range(n):
+        kind = rng.choice(["wavenet", "rawctc", "classifier"])
+        C = rng.choice([128, 256])
+        nl = rng.choice([1, 2, 3, 4])
+        layers = [(C, C, rng.choice([1, 2, 2, 3]), rng.choice([1, 2, 4, 7, 16, 33])) for _ in range(nl)]
+        T = rng.choice([5, 64, 130, 257, 500, 999])
+        B = rng.choice([1, 2, 3])
+        out.append((i, kind, C, tuple(layers), T, B, rng.random() < 0.5, rng.choice([1, 2, 3, 4]), rng.random() < 0.5))
+    return out
+
+
+@pytest.mark.parametrize("i,kind,C,layers,T,B,softmax,aux,causal", _net_cases(12))
+def test_networks_random_configs(i, kind, C, layers, T, B, softmax, aux, causal):
+    """The three drop-in networks on the tensor-core path, random layer lists / lengths / batch sizes, against the oracle
+    evaluated on the same bf16-rounded weights and inputs (logits within 2e-2 of the largest |logit|)."""
+    torch.manual_seed(9000 + i)
+    layers = [tuple(l) for l in layers]
+    if kind == "wavenet":
+        net = W.WaveNet(C, 2, layers, C, softmax=softmax)
+        lev = torch.randint(0, C, (B, T))
+        x = torch.zeros(B, C, T).scatter_(1, lev.unsqueeze(1), 1.0)
+        ref_fn = lambda sd: O.wavenet_forward(sd, x, layers, softmax=softmax)
+    elif kind == "rawctc":
+        net = W.RawCTCNet(C, aux, 5, layers, C, softmax=softmax, causal=causal)      # aux = feature kernel width
+        x = r16(torch.randn(B, 1, T))
+        ref_fn = lambda sd: O.raw_ctcnet_forward(sd, x, layers, softmax=softmax, causal=causal)
+    else:
+        T = max(T, aux)                                                               # aux = pool width
+        net = W.WaveNetClassifier(C, 5, layers, C, pool_kernel_size=aux, softmax=softmax)
+        x = r16(torch.randn(B, C, T))
+        ref_fn = lambda sd: O.classifier_forward(sd, x, layers, pool_kernel_size=aux, softmax=softmax)
+    ref = ref_fn({k: r16(v) for k, v in net.state_dict().items()})
+    net = net.cuda().bfloat16().eval()
+    with torch.no_grad():
+        before = W._lib.launch_count
+        y = net(x.cuda().bfloat16())
+    # the tensor-core pipeline ran (one fused launch per block), not the generic kernels (three per block)
+    assert W._lib.launch_count - before <= len(layers) + 6
+    assert tuple(y.shape) == tuple(ref.shape)
+    assert rel(y, ref) <= BF16_TOL
