@@ -233,8 +233,8 @@ def stack_forward(h0, stack, skips):
 
 
 def stack_backward(stack, saved, dskips, need_dx0):
-    """-> (dh0 or None, list of per-layer parameter gradients in Stack.params() order, fp32).  The column sums of dh0
-    (the bias gradient of whatever produced the stack's input) are left in `stack_backward.dh0_colsum`."""
+    """-> (dh0 or None, list of per-layer parameter gradients in Stack.params() order (fp32), fp32 column sums of dh0
+    or None -- the bias gradient of whatever produced the stack's input, summed by the launch that wrote dh0)."""
     B, T, C = dskips.shape
     dev = dskips.device
     zb = _zeros(C, dev)
@@ -273,7 +273,6 @@ def stack_backward(stack, saved, dskips, need_dx0):
         grads[l] = [dwt, dbab[:C], dws, dbab[C:], dwres, dbres, None, None, dwproj, dbres, None, csk]
         saved[l] = None                                     # free this layer's activations
         dres, dres_cs = dx, dx_cs
-    stack_backward.dh0_colsum = dres_cs
     # weight-space algebra of the folded skip -> bottleneck product, batched over layers
     M = torch.stack(Ms)                                                               # [L, C, C]
     wbn = torch.stack([n.weight.detach().float()[:, :, 0] for n in stack.necks])
@@ -284,7 +283,7 @@ def stack_backward(stack, saved, dskips, need_dx0):
     dbskip = torch.matmul(wbn.transpose(1, 2), csk)
     for l in range(L):
         grads[l][6], grads[l][7], grads[l][10] = dwskip[l].unsqueeze(2), dbskip[l], dwbn[l].unsqueeze(2)
-    return dres, grads
+    return dres, grads, dres_cs
 
 
 def head_forward(skips, hd, out_dtype, softmax, skips_act=None):
@@ -384,10 +383,9 @@ class _WaveNetTrain(torch.autograd.Function):
         x, offs, saved, skips_act, h1, out = ctx.keep
         ctx.keep = None
         dskips, ghead = head_backward(dout.contiguous(), out, model.softmax, pk["head_bwd"], skips_act, h1)
-        dh0, gl = stack_backward(pk["stack"], saved, dskips, True)
+        dh0, gl, dbe = stack_backward(pk["stack"], saved, dskips, True)
         C, in_dim = dh0.shape[2], x.shape[2]
         dwe = torch.stack(wgrad_multi(dh0, C, [(x, o) for o in offs]), 2)
-        dbe = stack_backward.dh0_colsum
         dsignal = None
         if ctx.needs_input_grad[2]:
             dxn = FP.dense(dh0, [-o for o in offs], pk["entry_wt"], _zeros(in_dim, dh0.device), in_dim)
@@ -448,7 +446,7 @@ class _ClassifierTrain(torch.autograd.Function):
         ctx.keep = None
         need_dx = ctx.needs_input_grad[2]
         dskips, ghead = head_backward(dout.contiguous(), out, model.softmax, pk["head_bwd"], skips_act, h1)
-        dh0, gl = stack_backward(pk["stack"], saved, dskips, need_dx)
+        dh0, gl, _ = stack_backward(pk["stack"], saved, dskips, need_dx)
         dseq = None
         if need_dx:
             B, _To, C = dh0.shape                 # layout change + AvgPool1d backward in one pass
@@ -522,7 +520,7 @@ class _RawCTCNetTrain(torch.autograd.Function):
         dev = seq.device
         h0 = saved[0][0]
         dskips, ghead = head_backward(dout.contiguous(), out, model.softmax, pk["head_bwd"], skips_act, h1)
-        dh0, gl = stack_backward(pk["stack"], saved, dskips, True)
+        dh0, gl, _ = stack_backward(pk["stack"], saved, dskips, True)
         dpre2 = leaky_bwd(dh0, h0)                                       # through the second LeakyReLU
         dw2 = wgrad_rows(dpre2, f, 0, F, F).unsqueeze(2)
         db2 = colsum(dpre2)
