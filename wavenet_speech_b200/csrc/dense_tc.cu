@@ -230,29 +230,51 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         constexpr float L2E = 1.4426950408889634f;
         const float sc = p.softmax ? L2E : 1.f;
         float mx = 0.f, inv = 1.f;
+        auto ld_bias16 = [&](int c, float (&bb)[16]) {         // 16 consecutive (pre-scaled) biases: four 16-byte loads
+          const float4* q4 = reinterpret_cast<const float4*>(sbias + c);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 u = q4[j];
+            bb[4 * j] = u.x; bb[4 * j + 1] = u.y; bb[4 * j + 2] = u.z; bb[4 * j + 3] = u.w;
+          }
+        };
         if (p.softmax) {
           const int cbeg = h * (p.N / 2);
           const int cend = (cbeg + p.N / 2) < p.n_out ? (cbeg + p.N / 2) : p.n_out;   // this warp's valid columns
+          // (the epilogue issues ~25 instructions per output element when every element drags its own shared-memory
+          // bias load and bounds predicate along: whole 16-column groups take the straight-line path below)
           float m = -INFINITY;
           for (int c0 = cbeg; c0 < cend; c0 += 16) {
-            float a[16];
+            float a[16], bb[16];
             tmem_ld16(tacc + c0, a);
+            ld_bias16(c0, bb);
             tmem_wait_ld();
+            if (c0 + 16 <= cend) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (c0 + i < cend) m = fmaxf(m, fmaf(a[i], L2E, sbias[c0 + i]));
+              for (int i = 0; i < 16; ++i) m = fmaxf(m, fmaf(a[i], L2E, bb[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c0 + i < cend) m = fmaxf(m, fmaf(a[i], L2E, bb[i]));
+            }
           }
           scratch[(h * RB_TILE + row) * 2] = m;
           epi_bar();
           mx = fmaxf(m, scratch[((h ^ 1) * RB_TILE + row) * 2]);
           float sum = 0.f;
           for (int c0 = cbeg; c0 < cend; c0 += 16) {
-            float a[16];
+            float a[16], bb[16];
             tmem_ld16(tacc + c0, a);
+            ld_bias16(c0, bb);
             tmem_wait_ld();
+            if (c0 + 16 <= cend) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (c0 + i < cend) sum += fast_ex2(fmaf(a[i], L2E, sbias[c0 + i]) - mx);
+              for (int i = 0; i < 16; ++i) sum += fast_ex2(fmaf(a[i], L2E, bb[i]) - mx);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c0 + i < cend) sum += fast_ex2(fmaf(a[i], L2E, bb[i]) - mx);
+            }
           }
           scratch[(h * RB_TILE + row) * 2 + 1] = sum;
           epi_bar();
@@ -262,25 +284,31 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         const int esize = p.out_f32 ? 4 : 2;
         for (int c32 = 0; c32 * 32 < p.n_out; ++c32, ++nchunk) {
           const int col = c32 * 32 + h * 16;
-          float a[16];
+          float a[16], bb[16];
           tmem_ld16(tacc + col, a);
+          ld_bias16(col, bb);
           tmem_wait_ld();
-          float v[16];
+          float v[16];                                           // columns >= n_out hold zero weights and bias
+          if (p.softmax) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float x = fmaf(a[i], sc, sbias[col + i]);          // columns >= n_out hold zero weights and bias
-            v[i] = p.softmax ? fast_ex2(x - mx) * inv : x;
+            for (int i = 0; i < 16; ++i) v[i] = fast_ex2(fmaf(a[i], L2E, bb[i]) - mx) * inv;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaf(a[i], sc, bb[i]);
           }
           if (p.tma_out) {
             const uint32_t boff = (nchunk & 1u) * DN_ABYTES;
             if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             epi_bar();
             uint8_t* sbase = smem_gen + (stg_base - smem_base) + boff;     // [32 channels][128 frames]
+            if (p.out_f32) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              uint8_t* dst = sbase + ((h * 16 + i) * RB_TILE + row) * esize;
-              if (p.out_f32) *reinterpret_cast<float*>(dst) = v[i];
-              else *reinterpret_cast<bf16*>(dst) = __float2bfloat16_rn(v[i]);
+              for (int i = 0; i < 16; ++i)
+                *reinterpret_cast<float*>(sbase + ((h * 16 + i) * RB_TILE + row) * 4) = v[i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                *reinterpret_cast<bf16*>(sbase + ((h * 16 + i) * RB_TILE + row) * 2) = __float2bfloat16_rn(v[i]);
             }
             fence_proxy_async_smem();
             epi_bar();
