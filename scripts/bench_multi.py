@@ -134,8 +134,26 @@ if "longread" in which:
         x_ext = S.exchange_halo(mine, plan, rank, world) if world > 1 else mine
         out["y"] = S.time_sharded_forward(net, x_ext, plan, T, out_extra=extra)
 
+    peer = None
+    if world > 1 and opts.get("halo", "both") != "nccl":      # NVLink peer-memory exchange (no NCCL on the data path)
+        try:
+            peer = S.PeerHaloExchange(1, 1, hl, hr, mine.dtype, rank, world)
+        except Exception as e:                                 # symmetric memory unavailable on this box
+            emit({"config": "peer_halo_exchange_unavailable", "error": str(e)[:200]})
+
+    def run_peer():
+        out["y"] = S.time_sharded_forward(net, peer.exchange(mine, plan), plan, T, out_extra=extra)
+
     with torch.no_grad():
+        if peer is not None:
+            ms_peer = timed(run_peer, 5)
+            y_peer = out["y"].clone()
         ms = timed(run, 5)
+        if peer is not None:
+            same = torch.tensor([int(torch.equal(out["y"], y_peer))], device="cuda")
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            emit({"config": "rawctcnet_ecoli_1M_read_time_sharded_peer_memory_halo", "T": T, "ms_per_read": ms_peer,
+                  "samples_per_s": T / (ms_peer * 1e-3), "equals_nccl_exchange_bitwise": bool(int(same))})
         # exactness: every rank checks its span against the full read computed locally in one pass
         full = net(xfull.cuda())
         stop = plan["end"] + (extra if plan["end"] == T else 0)

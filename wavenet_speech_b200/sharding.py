@@ -122,6 +122,58 @@ def exchange_halo(x_shard, plan, rank, world, group=None):
     return torch.cat([left, x_shard, right], 2)
 
 
+class PeerHaloExchange(object):
+    """The same exchange through NVLink peer memory instead of NCCL point-to-point operations.  Every rank owns one
+    symmetric buffer (torch symmetric memory: the allocation of each process of the node is mapped into all the
+    others); a rank WRITES the frames its neighbours miss straight into THEIR buffers -- peer stores over NVLink /
+    NVSwitch issued by a copy kernel on the current stream --, raises a signal in the neighbour's signal pad and waits
+    for its own two signals.  No NCCL on the data path, no staging copy, nothing on the host.
+
+    Buffer of a rank: 2 slots (step parity) x [left halo (B, C, halo_left) | right halo (B, C, halo_right)].  A neighbour
+    may start writing step k+1 while this rank still reads step k (other slot); it cannot reach step k+2 before this rank
+    has sent its step k+1 signal, which is stream-ordered after the read of step k."""
+
+    def __init__(self, B, C, halo_left, halo_right, dtype, rank, world, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.B, self.C, self.hl, self.hr, self.dtype = B, C, int(halo_left), int(halo_right), dtype
+        self.rank, self.world = rank, world
+        self.slot_elems = B * C * (self.hl + self.hr)
+        self.buf = symm.empty(max(1, 2 * self.slot_elems), dtype=dtype, device=torch.device("cuda", torch.cuda.current_device()))
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.step = 0
+
+    def _slot(self, peer, side, parity):
+        """(B, C, h) view of `peer`'s left (side 0) or right (side 1) halo slot of the given step parity."""
+        h = self.hl if side == 0 else self.hr
+        off = parity * self.slot_elems + (0 if side == 0 else self.B * self.C * self.hl)
+        return self.hdl.get_buffer(peer, (self.B, self.C, h), self.dtype, off)
+
+    def exchange(self, x_shard, plan):
+        """x_shard: frames [start, end) of a (B, C, T) tensor -> frames [lo, hi) (same result as exchange_halo)."""
+        rank, world, hl, hr = self.rank, self.world, self.hl, self.hr
+        B, C, n = x_shard.shape
+        assert (B, C) == (self.B, self.C) and x_shard.dtype == self.dtype and hl <= n and hr <= n
+        par = self.step & 1
+        self.step += 1
+        if rank < world - 1 and hl > 0:                       # my last frames -> right neighbour's LEFT halo slot
+            self._slot(rank + 1, 0, par).copy_(x_shard[:, :, n - hl:])
+            self.hdl.put_signal(rank + 1, channel=2 * par)
+        if rank > 0 and hr > 0:                               # my first frames -> left neighbour's RIGHT halo slot
+            self._slot(rank - 1, 1, par).copy_(x_shard[:, :, :hr])
+            self.hdl.put_signal(rank - 1, channel=2 * par + 1)
+        need_l, need_r = plan["start"] - plan["lo"], plan["hi"] - plan["end"]
+        parts = []
+        if rank > 0 and hl > 0:
+            self.hdl.wait_signal(rank - 1, channel=2 * par)
+            parts.append(self._slot(rank, 0, par)[:, :, hl - need_l:])
+        parts.append(x_shard)
+        if rank < world - 1 and hr > 0:
+            self.hdl.wait_signal(rank + 1, channel=2 * par + 1)
+            parts.append(self._slot(rank, 1, par)[:, :, :need_r])
+        return torch.cat(parts, 2) if len(parts) > 1 else x_shard
+
+
 def time_sharded_forward(forward_fn, x_ext, plan, T, out_extra=0):
     """Run `forward_fn` on the halo-extended input of one rank and keep the output frames this rank owns.
     Output frame g of the full read corresponds to local frame g - lo.  `out_extra` = frames the network appends
