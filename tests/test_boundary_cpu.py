@@ -97,3 +97,37 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.replace("# oracle", ""), os.path.join(dp, f)
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """The ctypes mirrors in _lib.py have the same size and field offsets as the C structs of include/wnb200.h
+    (compiled here with gcc: the header is plain C and needs no CUDA)."""
+    import ctypes
+    import shutil
+    import subprocess
+    from wavenet_speech_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    pairs = {"wnb200_src_t": _lib.Src, "wnb200_chain_t": _lib.Chain, "wnb200_resblock_t": _lib.ResBlock,
+             "wnb200_dense_t": _lib.Dense}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "wnb200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append('  printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ftype in cls._fields_:
+            if fname.startswith("_"):
+                continue                                    # explicit padding in the mirror
+            lines.append('  printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    for line in out.strip().splitlines():
+        cname, fname, val = line.split()
+        cls = pairs[cname]
+        if fname == "sizeof":
+            assert ctypes.sizeof(cls) == int(val), (cname, ctypes.sizeof(cls), int(val))
+        else:
+            assert getattr(cls, fname).offset == int(val), (cname, fname, getattr(cls, fname).offset, int(val))
