@@ -131,3 +131,36 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
             assert ctypes.sizeof(cls) == int(val), (cname, ctypes.sizeof(cls), int(val))
         else:
             assert getattr(cls, fname).offset == int(val), (cname, fname, getattr(cls, fname).offset, int(val))
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Argument count and kind (pointer / 32-bit int / 64-bit int / float) of every ctypes binding against the header."""
+    hdr = open(os.path.join(ROOT, "include", "wnb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = re.findall(r"\b(?:int|size_t|const char\s*\*)\s*(wnb200_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S)
+    assert len(protos) >= 15
+
+    def c_kind(arg):
+        arg = " ".join(arg.split())
+        if "*" in arg:
+            return "ptr"
+        if re.search(r"\b(int64_t|uint64_t|long long|size_t)\b", arg):
+            return "i64"
+        if re.search(r"\bfloat\b", arg):
+            return "f32"
+        return "i32"
+
+    def py_kind(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or getattr(t, "_type_", None) not in (
+                "i", "l", "q", "Q", "L", "I", "f"):
+            return "ptr"
+        return {"f": "f32"}.get(t._type_, "i64" if ctypes.sizeof(t) == 8 else "i32")
+
+    seen = 0
+    for name, args in protos:
+        args = args.strip()
+        kinds = [] if args in ("", "void") else [c_kind(a) for a in args.split(",")]
+        bound = [py_kind(t) for t in _lib.SIGNATURES[name]]
+        assert kinds == bound, (name, kinds, bound)
+        seen += 1
+    assert seen == len(_lib.SIGNATURES)
