@@ -275,6 +275,39 @@ def test_time_slice_input_is_read_in_place():
     assert torch.equal(FP.ncl_to_nlc_bf16(sig[:, 3:77, 5:400].float()), FP.ncl_to_nlc_bf16(sig[:, 3:77, 5:400].float().contiguous()))
 
 
+@pytest.mark.parametrize("name", ["wavenet_c128_bf16w", "rawctcnet_c128_bf16w", "classifier_c128_bf16w"])
+def test_tensor_core_path_against_reference_fixtures(name):
+    """The tcgen05 path against outputs written by the REFERENCE's own modules (oracle/gen_golden_tc.py; weights and
+    inputs bf16-representable, reference arithmetic fp32): logits within the stated bf16 tolerance, same per-frame
+    argmax and the same collapsed greedy decode on (nearly) every frame."""
+    g = G.load(name)
+    m = g["meta"]
+    if name.startswith("wavenet"):
+        net = W.WaveNet(m["in_dim"], m["entry_kwidth"], m["layers"], m["out_dim"], softmax=m["softmax"])
+    elif name.startswith("rawctcnet"):
+        net = W.RawCTCNet(m["num_features"], m["feature_kwidth"], m["num_labels"], m["layers"], m["out_dim"],
+                          positions=m["positions"], softmax=m["softmax"], causal=m["causal"])
+    else:
+        net = W.WaveNetClassifier(m["in_dim"], m["num_labels"], m["layers"], m["out_dim"],
+                                  pool_kernel_size=m["pool_kernel_size"], softmax=m["softmax"])
+    net.load_state_dict(g["sd"], strict=True)
+    net = net.cuda().bfloat16().eval()
+    ref = g["out"]["y"]
+    with torch.no_grad():
+        before = W._lib.launch_count
+        y = net(g["inp"]["x"].cuda().bfloat16())
+    assert W._lib.launch_count - before <= len(m["layers"]) + 6          # the fused (one launch per block) pipeline
+    assert tuple(y.shape) == tuple(ref.shape)
+    assert rel(y, ref) <= BF16_TOL
+    agree = (y.float().cpu().argmax(1) == ref.argmax(1)).float().mean().item()
+    assert agree >= 0.97, agree
+    # fp32 tensors through the same kernels (reduced_precision): same tolerance, fp32 out
+    net32 = net.float()
+    with W.reduced_precision(True), torch.no_grad():
+        y32 = net32(g["inp"]["x"].cuda())
+    assert y32.dtype == torch.float32 and rel(y32, ref) <= BF16_TOL
+
+
 def test_graphed_forward_replays_bitwise():
     """The whole forward captured in a CUDA graph (pipeline.GraphedForward) reproduces the eager result bit for bit,
     for new inputs as well, on the tensor-core and on the generic kernels."""

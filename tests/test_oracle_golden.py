@@ -50,7 +50,7 @@ def test_residual_block(name):
     _exact(skip, g["out"]["skip"])
 
 
-@pytest.mark.parametrize("name", ["wavenet_test_shape", "wavenet_onehot_c32"])
+@pytest.mark.parametrize("name", ["wavenet_test_shape", "wavenet_onehot_c32", "wavenet_c128_bf16w"])
 def test_wavenet(name):
     g = G.load(name)
     m = g["meta"]
@@ -61,7 +61,7 @@ def test_wavenet(name):
 
 
 @pytest.mark.parametrize("name", ["rawctcnet_default", "rawctcnet_positions", "rawctcnet_causal",
-                                  "rawctcnet_example_json"])
+                                  "rawctcnet_example_json", "rawctcnet_c128_bf16w"])
 def test_raw_ctcnet(name):
     g = G.load(name)
     m = g["meta"]
@@ -71,8 +71,9 @@ def test_raw_ctcnet(name):
     assert y.shape[2] == g["inp"]["x"].shape[2] + m["feature_kwidth"] - 1
 
 
-def test_classifier():
-    g = G.load("classifier_pool3")
+@pytest.mark.parametrize("name", ["classifier_pool3", "classifier_c128_bf16w"])
+def test_classifier(name):
+    g = G.load(name)
     m = g["meta"]
     y = O.classifier_forward(g["sd"], g["inp"]["x"], m["layers"], pool_kernel_size=m["pool_kernel_size"],
                              softmax=m["softmax"])
