@@ -203,6 +203,135 @@ def train_step_measure(w, rank, world, dist, max_over_ranks, barrier, steps=5, w
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
 
 
+def stock_torch_gpu(w, rank):
+    """What a user of the reference runs on this GPU today: the reference's module semantics (modules/wavenet.py:88-111,
+    block.py:54-82 -- nn.Conv1d padded + sliced, permute/contiguous + nn.Linear, F.tanh / F.sigmoid, per-layer add)
+    issued as stock torch ops on `cuda` (cuDNN / cuBLAS / ATen), in fp32 (the reference's dtype) and in bf16.  The
+    functional restatement under oracle/ issues exactly those ops; nothing of libwnb200 is on this path.  Forward on the
+    full workload; fwd+bwd (cross-entropy + CTC through torch autograd, torch's own ctc_loss) on a bounded batch."""
+    from oracle import wavenet_oracle as O
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    net, layers = build_model(w)
+    B, T, D = w["batch"], w["T"], w["in_dim"]
+    x = make_input(w, rank)
+    out = {}
+
+    def timed(fn, n):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    for name, dt in (("bf16", torch.bfloat16), ("fp32", torch.float32)):
+        sd = {k: v.detach().cuda().to(dt) for k, v in net.state_dict().items()}
+        xd = x.cuda().to(dt)
+        try:
+            with torch.no_grad():
+                ms = timed(lambda: O.wavenet_forward(sd, xd, layers, softmax=True), 3)
+            out["fwd_" + name] = {"samples_per_s": B * T / (ms * 1e-3), "ms_per_step": ms, "batch": B, "T": T}
+        except RuntimeError as e:                    # out of memory on a smaller card: say so, do not fail the bench
+            out["fwd_" + name] = {"error": str(e)[:120]}
+        del sd, xd
+        torch.cuda.empty_cache()
+    # train step (legacy_code/train.py:24-61 semantics) with stock autograd, bf16, bounded batch
+    try:
+        from wavenet_speech_b200.utils import signal_gen as S
+        Bt = min(B, 4)
+        C = w["C"]
+        import wavenet_speech_b200 as W
+        cls_layers = [(C, C, 2, d) for d in [1, 2, 4, 8, 16] * 3]
+        cn = W.WaveNetClassifier(C, 5, cls_layers, C, pool_kernel_size=3, softmax=False)
+        sd_w = {k: v.detach().cuda().bfloat16().requires_grad_(True) for k, v in net.state_dict().items()}
+        sd_c = {k: v.detach().cuda().bfloat16().requires_grad_(True) for k, v in cn.state_dict().items()}
+        lev, labels = S.quantized_batch(Bt, T, num_levels=D, seed=77, with_labels=True)
+        sig = torch.from_numpy(S.one_hot(lev, num_levels=D)).cuda().bfloat16()
+        nlab = T // 3 // 2
+        lengths = torch.tensor([min(len(l), nlab) for l in labels], dtype=torch.int64)
+        seq = torch.cat([torch.from_numpy(l[:nlab]) for l in labels]).long().cuda()
+        params = list(sd_w.values()) + list(sd_c.values())
+        opt = torch.optim.Adam(params, lr=1e-5, fused=True)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            pred = O.wavenet_forward(sd_w, sig[:, :, 0:-1], layers, softmax=False)
+            trans = O.classifier_forward(sd_c, pred, cls_layers, pool_kernel_size=3, softmax=False)
+            tgt = sig[:, :, 1:].argmax(1)
+            xe = F.cross_entropy(pred.float(), tgt, reduction="sum") / Bt          # sum over t of batch means
+            lp = F.log_softmax(trans.float().permute(2, 0, 1), 2)
+            ctc = F.ctc_loss(lp, seq, torch.full((Bt,), lp.shape[0], dtype=torch.int64), lengths, blank=0,
+                             reduction="sum")
+            (xe / T + ctc / lp.shape[0]).backward()
+            opt.step()
+
+        ms = timed(step, 2)
+        out["train_step_bf16"] = {"samples_per_s": Bt * T / (ms * 1e-3), "ms_per_step": ms, "batch": Bt, "T": T,
+                                  "note": "stock autograd + torch ctc_loss + fused Adam; bounded batch (autograd keeps "
+                                          "every intermediate of every layer)"}
+    except RuntimeError as e:
+        out["train_step_bf16"] = {"error": str(e)[:120]}
+    torch.cuda.empty_cache()
+    return out
+
+
+def long_read_measure(rank, world, dist, max_over_ranks, barrier, T=1000000, steps=5):
+    """BASELINE configs[4]: one 1M-sample read through the ecoli RawCTCNet, time-sharded over the ranks with the
+    receptive-field halo (51 / 45 samples) exchanged over NVLink (NCCL point-to-point); every rank checks its span
+    bit for bit against the single-pass output."""
+    import wavenet_speech_b200 as W
+    from wavenet_speech_b200 import sharding as S
+    from wavenet_speech_b200.utils import signal_gen as SG
+    torch.manual_seed(0)
+    net = W.RawCTCNet(256, 3, 5, [(256, 256, 2, d) for d in [1, 2, 4, 8, 16] * 3], 256, softmax=False)
+    net = net.cuda().bfloat16().eval()
+    xfull = torch.from_numpy(SG.raw_batch(1, T, seed=11)).bfloat16()
+    hl, hr = S.raw_ctcnet_halo(net)
+    plan = S.time_shard_plan(T, rank, world, hl, hr)
+    mine = xfull[:, :, plan["start"]:plan["end"]].contiguous().cuda()
+    extra = net.feature_kwidth - 1
+    out = {}
+
+    def run():
+        x_ext = S.exchange_halo(mine, plan, rank, world) if world > 1 else mine
+        out["y"] = S.time_sharded_forward(net, x_ext, plan, T, out_extra=extra)
+
+    def halo_only():
+        if world > 1:
+            S.exchange_halo(mine, plan, rank, world)
+
+    with torch.no_grad():
+        for _ in range(2):
+            run()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            run()
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+        e0.record()
+        for _ in range(steps):
+            halo_only()
+        e1.record()
+        barrier()
+        ms_halo = max_over_ranks(e0.elapsed_time(e1)) / steps
+        full = net(xfull.cuda())
+        stop = plan["end"] + (extra if plan["end"] == T else 0)
+        ok = torch.tensor([int(torch.equal(out["y"], full[:, :, plan["start"]:stop]))], device="cuda")
+        if dist is not None:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    return {"workload": "rawctcnet_ecoli_fk3_1x%d_time_sharded" % T, "samples_per_s": T / (ms * 1e-3),
+            "ms_per_read": ms, "halo": [hl, hr], "halo_bytes_per_boundary": 2 * (hl + hr),
+            "exchange": "nccl p2p (batched isend/irecv over NVLink)" if world > 1 else "none (1 rank)",
+            "halo_exchange_ms": ms_halo, "sharded_equals_full_bitwise": bool(int(ok)), "scaling": "strong"}
+
+
 def run_reference(args, w):
     """--impl reference: the reference is Python/torch and cannot travel to the GPU box (and is not
     pip-installable: it has no setup.py), so this arm times the oracle port of its CPU path."""
@@ -255,6 +384,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the fwd+bwd (config 3 train step) measurement")
     ap.add_argument("--e2e-chunks", type=int, default=2)
+    ap.add_argument("--precision", default="precise", choices=["precise", "fast"],
+                    help="tensor-core activation format: precise = fp16 operands + fp16 (hi, lo) residual stream + exact "
+                         "gate (meets 2e-2 at 20 blocks); fast = bf16 stream + tanh.approx (round-1 format)")
+    ap.add_argument("--no-stock", action="store_true", help="skip the stock-PyTorch-on-GPU comparator")
+    ap.add_argument("--no-longread", action="store_true", help="skip the time-sharded 1M-sample read (config 5)")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.batch:
@@ -279,6 +413,7 @@ def main():
 
     import wavenet_speech_b200 as W
     from wavenet_speech_b200 import _lib
+    W.tc_precision(args.precision)
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     net, layers = build_model(w)
     net = net.cuda().to(dtype).eval()
@@ -319,6 +454,23 @@ def main():
         ms = max_over_ranks(e0.elapsed_time(e1))
         launches = _lib.launch_count - l0
         clocks = sampler.stop()
+
+        # ---- the other activation format on the same input, same steps (reported under config) -----------
+        other = "fast" if args.precision == "precise" else "precise"
+        other_fmt = None
+        if args.dtype == "bf16":
+            with W.tc_precision(other):
+                for _ in range(2):
+                    net(x_dev)
+                barrier()
+                e0.record()
+                for _ in range(args.steps):
+                    net(x_dev)
+                e1.record()
+                barrier()
+            ms_o = max_over_ranks(e0.elapsed_time(e1))
+            other_fmt = {"precision": other, "value": samples * world * args.steps / (ms_o * 1e-3), "unit": UNIT,
+                         "ms_per_step": ms_o / args.steps}
 
         # ---- end-to-end: pinned host input -> H2D -> forward -> D2H of the output ------------------------
         e2e = None
@@ -387,6 +539,7 @@ def main():
         per.setdefault(name, []).append(a.elapsed_time(b))
     peaks = load_peaks()
     C = w["C"]
+    precise = args.precision == "precise" and args.dtype == "bf16" and C in (128, 256)
     tagged = [k for k in per if k.endswith(":resblock")]
     dom = tagged[0] if tagged else "wnb200_taps_fwd"
     tot = sum(sum(v) for v in per.values())
@@ -397,22 +550,41 @@ def main():
         flops_launch = flops_per_timestep(w) * samples
         avg_ms = float(sum(per[dom])) / float(n_pass)
     achieved = flops_launch / (avg_ms * 1e-3) / 1e12
-    # DRAM bytes per launch of the fused block kernel from the committed `ncu --set full` capture of this same
-    # workload (profiles/r1_ncu_full_v8_resblock2.csv): 806.9 MB read + 749.9 MB written
-    traffic = 1556.8e6 if (tagged and args.workload == DEFAULT_WORKLOAD and not args.batch and not args.T) else None
+    # DRAM bytes per launch of the fused block kernel: read from the ncu summary of THIS kernel / format / workload
+    # that scripts/ncu_traffic.py wrote under profiles/ (dram__bytes_read.sum + dram__bytes_write.sum of one
+    # `ncu --set full` launch); null when no capture of this format exists -- never a constant in this file
+    traffic, traffic_src = None, None
+    if tagged and args.workload == DEFAULT_WORKLOAD and not args.batch and not args.T:
+        tp = os.path.join(ROOT, "profiles", "r2_resblock_traffic.json")
+        if os.path.exists(tp):
+            ent = json.load(open(tp)).get(args.precision)
+            if ent:
+                traffic, traffic_src = ent["dram_bytes_per_launch"], ent.get("source")
+    # executed MACs per frame: bf16 format 7 C^2 (skip -> bottleneck folded); precise 8 C^2 (+ the stream's lo half
+    # through the projection); as written in the reference: 8 C^2 (16 C^2 FLOP)
+    exec_ratio = (16.0 if precise else 14.0) / 16.0
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
                 "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": traffic,
-                "achieved_executed": achieved * 14.0 / 16.0 if tagged else achieved,
+                "traffic_source": traffic_src,
+                "achieved_executed": achieved * exec_ratio if tagged else achieved,
                 "peak_source": peaks["source"] + " (bf16_tflops_sustained)",
                 "share_of_step": float(sum(per[dom])) / tot if tot > 0 else None,
                 "avg_launch_ms": avg_ms}
 
     input_mb = x_dev.numel() * x_dev.element_size() / 1e6
     fwd_bwd = None
+    del net, x_dev
+    torch.cuda.empty_cache()
     if not args.no_train and args.workload == DEFAULT_WORKLOAD and args.dtype == "bf16":
-        del net, x_dev
-        torch.cuda.empty_cache()
         fwd_bwd = train_step_measure(w, rank, world, dist, max_over_ranks, barrier)
+        torch.cuda.empty_cache()
+    long_read = None
+    if not args.no_longread and args.workload == DEFAULT_WORKLOAD and args.dtype == "bf16":
+        long_read = long_read_measure(rank, world, dist, max_over_ranks, barrier)
+        torch.cuda.empty_cache()
+    stock = None
+    if not args.no_stock and world == 1 and args.workload == DEFAULT_WORKLOAD:
+        stock = stock_torch_gpu(w, rank)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -426,7 +598,16 @@ def main():
         "config": {"workload": args.workload, "batch_per_gpu": w["batch"], "T": w["T"], "channels": C,
                    "layers": len(w["dil"]), "softmax": True, "sharding": "batch x%d" % world,
                    "l2": "input %.0f MB and every inter-layer tensor exceed the 126 MB L2" % input_mb,
-                   "flop_per_sample": flops_per_timestep(w)},
+                   "flop_per_sample": flops_per_timestep(w),
+                   "precision": ("precise: bf16 in/out, fp16 tensor-core operands, residual stream as an fp16 (hi, lo) pair, "
+                                 "fp32 accumulation (<= 2e-2 at 20 blocks, tests/test_gpu_precise.py)") if precise else
+                                "fast: bf16 operands and residual stream, tanh.approx gate",
+                   # the rest of BASELINE.json's metric, measured in this same run at this N (the driver keeps `config`):
+                   "other_format": other_fmt,
+                   "fwd_bwd": fwd_bwd,                 # configs[2]: WaveNet-CTC train step, batch-sharded + grad all-reduce
+                   "time_sharded": long_read,          # configs[4]: 1M-sample read, time-sharded + halo exchange
+                   "e2e_levels": e2e_levels,           # host hands over uint8 levels instead of the one-hot tensor
+                   "stock_torch_gpu": stock},          # the reference's module semantics as stock torch ops on this GPU
         "clocks": clocks, "e2e": e2e, "e2e_levels": e2e_levels, "gpu_launches": launches, "roofline": roofline,
         "cpu_baseline": cpu,
         "fwd_bwd": fwd_bwd,

@@ -16,6 +16,9 @@
  *     always fp32; gradients of parameters are always written as fp32;
  *   - "NCL" = (batch, channels, time) with time contiguous (the reference's layout);
  *     "NLC" = (batch, time, channels) with channels contiguous (the tensor-core path's layout);
+ *   - every argument STRUCT starts with `uint32_t struct_size`: the caller sets it to sizeof(the struct) as it
+ *     was compiled; a mismatch (binding written against another version of this header) is refused with an
+ *     error instead of reading garbage as pointers.  Zero-initialise the struct, then fill it in;
  *   - sm_100a only.  There is no CPU fallback and no other-arch fallback.
  */
 #ifndef WNB200_H_
@@ -30,6 +33,18 @@ extern "C" {
 
 #define WNB200_F32 0
 #define WNB200_BF16 1
+
+/* Two-byte activation / weight format of the tensor-core path.
+ *   WNB200_ACT_BF16  : bf16 operands; the residual stream is one bf16 tensor per layer (fastest; also the training
+ *                      format).  Rounding of the stream is amplified by every following block: about 2e-2 of the
+ *                      logits at 10 blocks and 5e-2..9e-2 at 16-20 with the reference's initialisation.
+ *   WNB200_ACT_F16X2 : fp16 operands (same tensor-core rate, 3 more mantissa bits; bf16-rounded weights are exact in
+ *                      fp16), the residual stream is carried as an fp16 (hi, lo) PAIR of tensors (hi = fp16(v),
+ *                      lo = fp16(v - hi)); dilated taps read hi, the residual projection contracts both halves; the
+ *                      gate is evaluated with ex2/rcp instead of tanh.approx.  Holds 2e-2 at 20 blocks (measured
+ *                      6e-3..1e-2).  Range: |stream| <= 65504 (saturating). */
+#define WNB200_ACT_BF16 0
+#define WNB200_ACT_F16X2 1
 
 #define WNB200_EPI_NONE 0  /* y = acc + bias                                              */
 #define WNB200_EPI_LEAKY 1 /* y = LeakyReLU_0.01(acc + bias)   (wavenet.py:67-71)         */
@@ -153,6 +168,7 @@ int wnb200_argmax_channels(int dtype, int B, int C, int T, const void* x, int64_
 #define WNB200_TC_EPI2_HEAD 2
 
 typedef struct {
+  uint32_t struct_size;   /* = sizeof(wnb200_chain_t)                                            */
   int32_t B, T, C;        /* C = contracted channels = width of act; 64, 128 or 256              */
   int32_t ntaps;          /* 1..3                                                               */
   int32_t t_off[3];
@@ -188,11 +204,14 @@ int wnb200_chain_fwd_tc(const wnb200_chain_t* args /*host*/, void* stream);
  *   w2   bf16 [2C][2C] = [[Wres, Wproj], [Wbn*Wskip, 0]];   b2 fp32 [2C] = [bres+bproj ; Wbn*bskip+bbn]
  *   res  bf16 NLC [B,T,C] or NULL (last layer: not needed);  skips fp32 NLC [B,T,C]. */
 typedef struct {
+  uint32_t struct_size;   /* = sizeof(wnb200_resblock_t) */
   int32_t B, T, C, ntaps;
   int32_t t_off[3];
   int32_t skips_init;     /* 1: skips = contribution, 0: skips += contribution */
   int32_t variant;        /* 0 = default (CTA-pair kernel, cta_group::2), 1 = single-CTA kernel */
-  const void* x;          /* NLC bf16 [B,T,C] */
+  int32_t act_fmt;        /* WNB200_ACT_BF16 | WNB200_ACT_F16X2 (CTA-pair kernel, inference): format of x, w1, w2, res,
+                             skips_act.  F16X2: bias1 is PRE-SCALED (tanh rows by -2 log2 e, sigmoid rows by -log2 e) */
+  const void* x;          /* NLC [B,T,C], 2-byte elements of act_fmt (F16X2: the hi half of the stream) */
   const void* w1;
   const float* bias1;
   const void* w2;
@@ -205,6 +224,8 @@ typedef struct {
   void* save_sg;
   void* skips_act;        /* optional (last layer of an inference stack, res = NULL): NLC bf16 [B,T,C] that receives
                              LeakyReLU(skips + contribution) (wavenet.py:100-103); `skips` is then read, not updated */
+  const void* x_lo;       /* F16X2: lo half of the input stream, NLC fp16 [B,T,C]; NULL = the input is exactly x */
+  void* res_lo;           /* F16X2: lo half of the output stream (required when res != NULL) */
 } wnb200_resblock_t;
 int wnb200_resblock_fwd_tc(const wnb200_resblock_t* args /*host*/, void* stream);
 
@@ -216,6 +237,7 @@ int wnb200_resblock_fwd_tc(const wnb200_resblock_t* args /*host*/, void* stream)
  * mode 1: y = NCL [B,n_out,T] (bf16 or fp32), optional channel softmax -- last 1x1 of the heads + softmax
  *         (wavenet.py:70-71,103-109).  N = n_out rounded up to 16, padded rows of W / bias are zero. */
 typedef struct {
+  uint32_t struct_size;   /* = sizeof(wnb200_dense_t) */
   int32_t B, T, Cin, ntaps;
   int32_t t_off[3];
   int32_t N;
@@ -229,14 +251,18 @@ typedef struct {
   const void* x2;         /* NULL = single source */
   float* colsum;          /* mode 0, optional: fp32 [N], += the column sums of y over all frames (the bias gradient of
                              the contraction that consumes y as its output gradient: autograd of conv biases) */
+  int32_t act_fmt;        /* WNB200_ACT_BF16 | WNB200_ACT_F16X2: format of x, x2, w and of the NLC output */
+  int32_t reserved0;
+  void* y_lo;             /* F16X2, mode 0, optional: y leaves as an fp16 (hi, lo) pair (y, y_lo) -- the producer of a
+                             residual stream (entry conv, RawCTCNet feature 1x1) */
 } wnb200_dense_t;
 int wnb200_dense_fwd_tc(const wnb200_dense_t* args /*host*/, void* stream);
 
 
 /* RawCTCNet featuriser, first layer: Conv1d(1, F, fk, padding=fk-1) + LeakyReLU (raw_ctcnet.py:57-59) on the raw
- * signal x [B, 1, T] -> y NLC bf16 [B, T+fk-1, F].  w fp32 [F, fk], bias fp32 [F]. */
+ * signal x [B, 1, T] -> y NLC [B, T+fk-1, F] in act_fmt (bf16 / fp16).  w fp32 [F, fk], bias fp32 [F]. */
 int wnb200_featurize_nlc(int dtype, int B, int T, int F, int fk, const void* x, const float* w, const float* bias,
-                         void* y, void* stream);
+                         int act_fmt, void* y, void* stream);
 
 /* Backward of the above: dh NLC bf16 [B, floor(T/pool), C] -> dx NCL [B, C, T] (bf16 or fp32),
  * dx[b,c,t] = dh[b, t/pool, c] / pool for t < floor(T/pool)*pool, 0 after (autograd of nn.AvgPool1d). */
@@ -245,13 +271,16 @@ int wnb200_avgpool_bwd_nlc_to_ncl(int dtype_out, int B, int C, int T, int pool, 
 /* WaveNet entry conv (wavenet.py:54,93) on quantised LEVELS instead of their one-hot encoding (fns.py:6-15,
  * pore_model.py:88-96): y[b,t,:] = bias + sum_j wemb[j][levels[b,t+t_off[j]]][:], taps outside [0,T) contribute nothing.
  * levels int32 [B,T] (clamped to [0,in_dim)), wemb bf16 [ntaps][in_dim][C] (= conv weight [C,in_dim,ntaps] permuted),
- * bias fp32 [C], y NLC bf16 [B,T,C]; t_off: host int32[ntaps].  Bit-identical to the dense kernel on the one-hot input. */
+ * bias fp32 [C], y NLC bf16 [B,T,C]; t_off: host int32[ntaps].  Bit-identical to the dense kernel on the one-hot input.
+ * act_fmt = WNB200_ACT_F16X2: wemb is fp16 and y (y_lo, optional) receive the fp16 (hi, lo) pair. */
 int wnb200_entry_embed_nlc(int B, int T, int C, int in_dim, int ntaps, const int32_t* t_off /*host*/,
-                           const int32_t* levels, const void* wemb, const float* bias, void* y, void* stream);
+                           const int32_t* levels, const void* wemb, const float* bias, int act_fmt, void* y, void* y_lo,
+                           void* stream);
 
-/* AvgPool1d(pool) (classifier.py:53,102) fused with the NCL -> NLC bf16 layout change:
- * x NCL [B, C, T] -> y NLC bf16 [B, floor(T/pool), C]. */
-int wnb200_avgpool_ncl_to_nlc_bf16(int dtype, int B, int C, int T, int pool, const void* x, void* y, void* stream);
+/* AvgPool1d(pool) (classifier.py:53,102) fused with the NCL -> NLC layout change:
+ * x NCL [B, C, T] -> y NLC [B, floor(T/pool), C] in act_fmt (bf16 / fp16). */
+int wnb200_avgpool_ncl_to_nlc(int dtype, int B, int C, int T, int pool, const void* x, int act_fmt, void* y,
+                              void* stream);
 
 
 /* Weight gradient on tensor cores (CTA pair, MN-major operands):
@@ -340,6 +369,9 @@ int wnb200_ncl_to_nlc_bf16(int dtype, int B, int C, int T, const void* x, void* 
  * (legacy_code/train.py:30 feeds sig[:, :, 0:-1]). */
 int wnb200_ncl_to_nlc_bf16_strided(int dtype, int B, int C, int T, int64_t sb, int64_t sc, const void* x, void* y,
                                    void* stream);
+/* Same with the 2-byte output format chosen by act_fmt (bf16 / fp16). */
+int wnb200_ncl_to_nlc_act(int dtype, int act_fmt, int B, int C, int T, int64_t sb, int64_t sc, const void* x, void* y,
+                          void* stream);
 int wnb200_nlc_to_ncl(int out_dtype, int src_is_f32, int B, int C, int T, const void* x, void* y, void* stream);
 
 #ifdef __cplusplus

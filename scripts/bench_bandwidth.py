@@ -67,7 +67,7 @@ report("xent_bwd NCL bf16, T = 16383 (unaligned rows)", 4 * no + 12 * B * (T - 1
 report("argmax_channels NCL bf16, T = 16383 (unaligned rows)", 2 * no + 8 * B * (T - 1), lambda: ops.argmax_channels(xo))
 h0 = torch.empty((B, T // 3, C), dtype=bf, device="cuda")
 report("avgpool(3) NCL -> NLC bf16 (B2)", 2 * n + 2 * (n // 3),
-       lambda: _lib.call("wnb200_avgpool_ncl_to_nlc_bf16", 1, B, C, T, 3, ops._p(x_ncl), ops._p(h0), ops._stream()))
+       lambda: _lib.call("wnb200_avgpool_ncl_to_nlc", 1, B, C, T, 3, ops._p(x_ncl), 0, ops._p(h0), ops._stream()))
 report("avgpool_fwd(3) NCL bf16 (B2, generic path)", 2 * n + 2 * (n // 3), lambda: ops.avgpool_fwd(x_ncl, 3))
 g = torch.ones(C, device="cuda")
 report("layernorm_fwd NCL bf16 (B4)", 4 * n + 8 * B * T, lambda: ops.layernorm_fwd(x_ncl, g, g, 1e-6))
@@ -80,7 +80,7 @@ raw = torch.randn(Bf, 1, Tf, device="cuda", dtype=bf)
 w0, b0 = torch.randn(F, fk, device="cuda"), torch.randn(F, device="cuda")
 hf = torch.empty((Bf, Tf + fk - 1, F), dtype=bf, device="cuda")
 report("featurize_nlc (B1: Conv1d(1,F,3) + LeakyReLU -> NLC bf16)", Bf * Tf * 2 + hf.numel() * 2,
-       lambda: _lib.call("wnb200_featurize_nlc", 1, Bf, Tf, F, fk, ops._p(raw), ops._p(w0), ops._p(b0), ops._p(hf),
+       lambda: _lib.call("wnb200_featurize_nlc", 1, Bf, Tf, F, fk, ops._p(raw), ops._p(w0), ops._p(b0), 0, ops._p(hf),
                          ops._stream()), note="batch 256 x 4000")
 logits = torch.randn(1024, 5, 4002, device="cuda", dtype=bf)
 report("ctc_greedy_decode (argmax + collapse + pack)", logits.numel() * 2 + 1024 * 4002 * 2,

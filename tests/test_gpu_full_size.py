@@ -1,12 +1,14 @@
 """Parity at BASELINE.json's full sizes, where the CPU oracle cannot evaluate the whole tensor in seconds:
 size-independent properties of the hot path plus oracle checks on causal slices of the full-size output.
 
-Tolerance at FULL DEPTH.  The north_star's bf16 bound (2e-2 on the logits) is met per block and for stacks up to
-about ten blocks (tests/test_gpu_tc.py); with the reference's own initialisation the residual path is a random
-nn.Linear, perturbations grow ~1.15x per block, and at 16-20 blocks ANY bf16 evaluation is 5e-2 to 8e-2 from the
-fp32 one -- PyTorch's own bf16 evaluation of the reference's modules included (hard part 1;
-tests/tools/diag_bf16_depth.py).  So the full-depth slices are held to the envelope that evaluation defines: the oracle
-run in bf16 on the CPU (same weights, same input) against the oracle in fp32."""
+Tolerance at FULL DEPTH.  With the reference's own initialisation the residual path is a random nn.Linear, perturbations
+grow ~1.45x per block, and at 16-20 blocks a plain bf16 evaluation is 5e-2 to 9e-2 from the fp32 one -- PyTorch's own
+bf16 evaluation of the reference's modules included (hard part 1; profiles/r2_parity_vs_depth.json).
+The default `precise` format of the tensor-core path (fp16 operands, residual stream as an fp16 (hi, lo) pair, exact
+gate) is held to the north star's bound itself, 2e-2 on the outputs with NO envelope, and to >= 99 % identical per-frame
+argmax; the numbers measured by these tests are written to gpurun_out/ (WNB200_PARITY_LOG) for profiles/."""
+import json
+import os
 import pytest
 import torch
 
@@ -22,6 +24,13 @@ DIL = [1, 2, 4, 8, 16, 32, 64, 128, 256, 512] * 2
 
 def r16(t):
     return t.detach().bfloat16().float()
+
+
+def _log(name, **kw):
+    path = os.environ.get("WNB200_PARITY_LOG")
+    if path:
+        with open(path, "a") as f:
+            f.write(json.dumps(dict(test=name, **kw)) + "\n")
 
 
 def bf16_envelope(fwd, sd, x):
@@ -65,10 +74,12 @@ def test_wavenet_config2_full_size():
         ref, env, low = bf16_envelope(lambda s_, x_: O.wavenet_forward(s_, x_, layers, softmax=True), sd, x[b:b + 1, :, :n])
         got = y[b:b + 1, :, :n].float().cpu()
         err = G.rel_linf(got, ref)
-        assert err <= max(2e-2, env), (b, err, env)
         agree = float((got.argmax(1) == ref.argmax(1)).float().mean())
         agree_env = float((low.argmax(1) == ref.argmax(1)).float().mean())
-        assert agree >= agree_env - 0.03, (agree, agree_env)
+        _log("config2_32x16384", read=b, frames=n, err=err, torch_bf16_err=env, argmax_agree=agree,
+             torch_bf16_argmax_agree=agree_env)
+        assert err <= 2e-2, (b, err, env)
+        assert agree >= 0.99, (agree, agree_env)
 
 
 def test_raw_ctcnet_config4_full_size_and_long_read():
@@ -93,8 +104,12 @@ def test_raw_ctcnet_config4_full_size_and_long_read():
             assert lab[b, :int(n[b])].cpu().tolist() == [int(v) for v in O.collapse_decode(fr[b])]
     fwd = lambda s_, x_: O.raw_ctcnet_forward(s_, x_, layers, softmax=False)
     ref, env, _ = bf16_envelope(fwd, sd, x[200:201])
-    err = G.rel_linf(y[200:201].float().cpu(), ref)
-    assert err <= max(2e-2, env), (err, env)
+    got = y[200:201].float().cpu()
+    err = G.rel_linf(got, ref)
+    agree = float((got.argmax(1) == ref.argmax(1)).float().mean())
+    _log("config4_256x4000", read=200, err=err, torch_bf16_err=env, argmax_agree=agree)
+    assert err <= 2e-2, (err, env)
+    assert agree >= 0.99, agree
     # long read: 8 shards with 51 / 45 halo samples equal the single pass bit for bit; the oracle on one window
     T = 1000000
     xl = torch.from_numpy(SG.raw_batch(1, T, seed=11)).bfloat16()
@@ -111,4 +126,5 @@ def test_raw_ctcnet_config4_full_size_and_long_read():
     win = xl[:, :, lo - hl:lo + 1000 + hr].float()
     ref, env, _ = bf16_envelope(fwd, sd, win)
     err = G.rel_linf(full[:, :, lo:lo + 1000].float().cpu(), ref[:, :, hl:hl + 1000])
-    assert err <= max(2e-2, 1.5 * env), (err, env)
+    _log("config5_1x1M_window", err=err, torch_bf16_err=env)
+    assert err <= 2e-2, (err, env)

@@ -42,8 +42,8 @@ def test_avgpool_to_nlc(B, C, T, pool, dt):
     ref = torch.nn.functional.avg_pool1d(x.float(), pool).bfloat16().float().permute(0, 2, 1) if To > 0 else None
     xg = x.cuda()
     y = torch.full((B, To, C), 7.0, dtype=torch.bfloat16, device="cuda")
-    _lib.call("wnb200_avgpool_ncl_to_nlc_bf16", 1 if dt == torch.bfloat16 else 0, B, C, T, pool, ops._p(xg), ops._p(y),
-              ops._stream())
+    _lib.call("wnb200_avgpool_ncl_to_nlc", 1 if dt == torch.bfloat16 else 0, B, C, T, pool, ops._p(xg), _lib.ACT_BF16,
+              ops._p(y), ops._stream())
     torch.cuda.synchronize()
     if To > 0:
         # fp32 accumulation order inside a window may differ from torch's: one bf16 ulp
@@ -378,17 +378,22 @@ def test_raw_ctcnet_tc(C, fk, T, B, causal, softmax):
         y = net(x.cuda().bfloat16())
     assert tuple(y.shape) == (B, 5, T + fk - 1) and y.dtype == torch.bfloat16
     e = rel(y, ref)
-    # Deep untrained stacks amplify bf16 operand rounding ~1.15x per layer (hard part 1): 2e-2 holds up
-    # to ~6 blocks; beyond that the bar is "no worse than torch's own bf16 evaluation of the same network"
-    # (measured by scripts/diag_bf16_depth.py: 15 blocks -> ours 7.0e-2, torch bf16 1.0e-1).
-    sd16 = {k: v.bfloat16() for k, v in sd.items()}
-    e_torch = rel(O.raw_ctcnet_forward(sd16, x.bfloat16(), layers, softmax=softmax, causal=causal).float(), ref)
-    assert e <= max(BF16_TOL, e_torch), (e, e_torch)
-    # greedy decode (per-frame argmax, sequence_decoders.py:21-23): near-ties between the 5 logits may flip
+    # Deep untrained stacks amplify operand rounding ~1.45x per layer (hard part 1).  The default `precise`
+    # format (fp16 operands, (hi, lo) stream, exact gate) holds 2e-2 at this depth with no envelope; the bf16 `fast`
+    # format is held to "no worse than torch's own bf16 evaluation of the same network" (15 blocks: 7e-2 vs 1e-1).
+    assert e <= BF16_TOL, e
     agree = (y.float().cpu().argmax(1) == ref.argmax(1)).float().mean().item()
-    agree_torch = (O.raw_ctcnet_forward(sd16, x.bfloat16(), layers, softmax=softmax, causal=causal).float().argmax(1)
-                   == ref.argmax(1)).float().mean().item()
-    assert agree >= min(0.97, agree_torch - 0.01), (agree, agree_torch)
+    assert agree >= 0.99, agree
+    sd16 = {k: v.bfloat16() for k, v in sd.items()}
+    t16 = O.raw_ctcnet_forward(sd16, x.bfloat16(), layers, softmax=softmax, causal=causal).float()
+    e_torch = rel(t16, ref)
+    with FP.tc_precision("fast"), torch.no_grad():
+        yf = net(x.cuda().bfloat16())
+    ef = rel(yf, ref)
+    assert ef <= max(BF16_TOL, e_torch), (ef, e_torch)
+    agree_f = (yf.float().cpu().argmax(1) == ref.argmax(1)).float().mean().item()
+    agree_torch = (t16.argmax(1) == ref.argmax(1)).float().mean().item()
+    assert agree_f >= min(0.97, agree_torch - 0.01), (agree_f, agree_torch)
 
 
 def test_classifier_tc():

@@ -7,9 +7,21 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libwnb200.so")
+LIB_PATH = os.path.join(_PKG, "libwnb200_timeline.so" if os.environ.get("WNB200_TIMELINE", "0") == "1"
+                        else "libwnb200.so")
 
 c_void_p, c_int, c_int64, c_float_p = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p
+
+
+ACT_BF16, ACT_F16X2 = 0, 1
+
+
+class _Sized(ctypes.Structure):
+    """Argument structs start with `struct_size` (= sizeof as this binding lays it out); the library refuses a mismatch."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.struct_size = ctypes.sizeof(self)
 
 
 class Src(ctypes.Structure):
@@ -19,9 +31,10 @@ class Src(ctypes.Structure):
                 ("pre_act", ctypes.c_int32)]
 
 
-class Chain(ctypes.Structure):
+class Chain(_Sized):
     """Mirror of wnb200_chain_t."""
-    _fields_ = [("B", ctypes.c_int32), ("T", ctypes.c_int32), ("C", ctypes.c_int32), ("ntaps", ctypes.c_int32),
+    _fields_ = [("struct_size", ctypes.c_uint32),
+                ("B", ctypes.c_int32), ("T", ctypes.c_int32), ("C", ctypes.c_int32), ("ntaps", ctypes.c_int32),
                 ("t_off", ctypes.c_int32 * 3), ("epi1", ctypes.c_int32), ("n1", ctypes.c_int32),
                 ("n2", ctypes.c_int32), ("use_x2", ctypes.c_int32), ("epi2", ctypes.c_int32),
                 ("skips_init", ctypes.c_int32), ("out_f32", ctypes.c_int32), ("n_out", ctypes.c_int32),
@@ -30,24 +43,27 @@ class Chain(ctypes.Structure):
                 ("skips_act", c_void_p), ("out_ncl", c_void_p), ("dbg", c_void_p)]
 
 
-class ResBlock(ctypes.Structure):
+class ResBlock(_Sized):
     """Mirror of wnb200_resblock_t."""
-    _fields_ = [("B", ctypes.c_int32), ("T", ctypes.c_int32), ("C", ctypes.c_int32), ("ntaps", ctypes.c_int32),
+    _fields_ = [("struct_size", ctypes.c_uint32),
+                ("B", ctypes.c_int32), ("T", ctypes.c_int32), ("C", ctypes.c_int32), ("ntaps", ctypes.c_int32),
                 ("t_off", ctypes.c_int32 * 3), ("skips_init", ctypes.c_int32), ("variant", ctypes.c_int32),
-                ("_pad", ctypes.c_int32), ("x", c_void_p), ("w1", c_void_p),
+                ("act_fmt", ctypes.c_int32), ("x", c_void_p), ("w1", c_void_p),
                 ("bias1", c_void_p), ("w2", c_void_p), ("bias2", c_void_p), ("res", c_void_p), ("skips", c_void_p),
                 ("dbg", c_void_p), ("save_act", c_void_p), ("save_th", c_void_p), ("save_sg", c_void_p),
-                ("skips_act", c_void_p)]
+                ("skips_act", c_void_p), ("x_lo", c_void_p), ("res_lo", c_void_p)]
 
 
-class Dense(ctypes.Structure):
+class Dense(_Sized):
     """Mirror of wnb200_dense_t."""
-    _fields_ = [("B", ctypes.c_int32), ("T", ctypes.c_int32), ("Cin", ctypes.c_int32), ("ntaps", ctypes.c_int32),
+    _fields_ = [("struct_size", ctypes.c_uint32),
+                ("B", ctypes.c_int32), ("T", ctypes.c_int32), ("Cin", ctypes.c_int32), ("ntaps", ctypes.c_int32),
                 ("t_off", ctypes.c_int32 * 3), ("N", ctypes.c_int32), ("mode", ctypes.c_int32),
                 ("leaky", ctypes.c_int32), ("n_out", ctypes.c_int32), ("softmax", ctypes.c_int32),
                 ("out_f32", ctypes.c_int32), ("Cin2", ctypes.c_int32), ("ntaps2", ctypes.c_int32),
                 ("t_off2", ctypes.c_int32 * 3), ("x", c_void_p), ("w", c_void_p),
-                ("bias", c_void_p), ("y", c_void_p), ("x2", c_void_p), ("colsum", c_void_p)]
+                ("bias", c_void_p), ("y", c_void_p), ("x2", c_void_p), ("colsum", c_void_p),
+                ("act_fmt", ctypes.c_int32), ("reserved0", ctypes.c_int32), ("y_lo", c_void_p)]
 
 
 # name -> argtypes (return type is int unless listed in _RESTYPES)
@@ -80,11 +96,11 @@ SIGNATURES = {
     "wnb200_chain_fwd_tc": [ctypes.POINTER(Chain), c_void_p],
     "wnb200_resblock_fwd_tc": [ctypes.POINTER(ResBlock), c_void_p],
     "wnb200_dense_fwd_tc": [ctypes.POINTER(Dense), c_void_p],
-    "wnb200_featurize_nlc": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
-    "wnb200_avgpool_ncl_to_nlc_bf16": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "wnb200_featurize_nlc": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    "wnb200_avgpool_ncl_to_nlc": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p],
     "wnb200_avgpool_bwd_nlc_to_ncl": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "wnb200_entry_embed_nlc": [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32), c_void_p, c_void_p,
-                               c_void_p, c_void_p, c_void_p],
+                               c_void_p, c_int, c_void_p, c_void_p, c_void_p],
     "wnb200_wgrad_tc": [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_wgrad2_tc": [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                          c_void_p],
@@ -108,6 +124,7 @@ SIGNATURES = {
     "wnb200_leaky_to_bf16": [c_int64, c_void_p, c_void_p, c_void_p],
     "wnb200_ncl_to_nlc_bf16": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "wnb200_ncl_to_nlc_bf16_strided": [c_int, c_int, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p],
+    "wnb200_ncl_to_nlc_act": [c_int, c_int, c_int, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p],
     "wnb200_nlc_to_ncl": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
 }
 _RESTYPES = {"wnb200_last_error": ctypes.c_char_p, "wnb200_ctc_workspace_bytes": ctypes.c_size_t}

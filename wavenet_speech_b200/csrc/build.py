@@ -7,11 +7,14 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-LIB = os.path.join(PKG, "libwnb200.so")
-STAMP = os.path.join(PKG, ".libwnb200.stamp")
+# WNB200_TIMELINE=1: diagnostic build with the clock64 phase stamps compiled in (scripts/timeline.py), kept apart
+# from the shipped library
+TIMELINE = os.environ.get("WNB200_TIMELINE", "0") == "1"
+LIB = os.path.join(PKG, "libwnb200_timeline.so" if TIMELINE else "libwnb200.so")
+STAMP = os.path.join(PKG, ".libwnb200_timeline.stamp" if TIMELINE else ".libwnb200.stamp")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--shared",
-         "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + (["-DWNB200_TIMELINE"] if TIMELINE else [])
 
 
 def _sources():
@@ -43,7 +46,7 @@ def build(force=False, verbose=False):
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
         return LIB
-    objdir = os.path.join(HERE, "_obj")
+    objdir = os.path.join(HERE, "_obj_timeline" if TIMELINE else "_obj")
     os.makedirs(objdir, exist_ok=True)
     headers = sorted(glob.glob(os.path.join(HERE, "*.cuh"))) + [os.path.join(os.path.dirname(PKG), "include", "wnb200.h")]
     cflags = [f for f in FLAGS if f != "--shared"]

@@ -23,7 +23,11 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 
+#ifdef WNB200_TIMELINE
 #define WNB_STAMP(slot) do { if (p.dbg && blockIdx.x == 0 && it < 8) p.dbg[it * 16 + (slot)] = clock64(); } while (0)
+#else
+#define WNB_STAMP(slot) do { } while (0)
+#endif
 
 namespace wnb {
 using namespace tc;
@@ -447,11 +451,7 @@ template <int C>
 static int launch_chain(const CUtensorMap& mx, const CUtensorMap& mw1, const CUtensorMap& mw2a,
                         const CUtensorMap& mw2x, const ChainDev& p, cudaStream_t st) {
   using K = Cfg<C>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    WNB_CUDA_OK(cudaFuncSetAttribute(chain_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
-    attr_set = true;
-  }
+  WNB_SET_SMEM_ATTR(K::SMEM_BYTES, chain_kernel<C>);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -467,6 +467,7 @@ using namespace wnb;
 
 extern "C" int wnb200_chain_fwd_tc(const wnb200_chain_t* a, void* stream) {
   WNB_CHECK_ARG(a != nullptr, "chain_fwd_tc: null argument");
+  WNB_CHECK_STRUCT(a, wnb200_chain_t, "chain_fwd_tc");
   const int C = a->C;
   WNB_CHECK_ARG(C == 64 || C == 128 || C == 256, "chain_fwd_tc: C=%d not in {64,128,256}", C);
   WNB_CHECK_ARG(a->ntaps >= 1 && a->ntaps <= 3, "chain_fwd_tc: ntaps=%d not in 1..3", a->ntaps);

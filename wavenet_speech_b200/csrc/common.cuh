@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/wnb200.h"
 
 namespace wnb {
@@ -37,6 +39,26 @@ void set_error(const char* fmt, ...);
                      __LINE__);                                                            \
       return 3;                                                                            \
     }                                                                                      \
+  } while (0)
+
+// Every argument struct of the C-ABI starts with `uint32_t struct_size` = sizeof(the struct) as the CALLER compiled it:
+// a host built against an older header (shorter struct) is refused instead of having garbage read as pointers.
+#define WNB_CHECK_STRUCT(a, type, what)                                                                          \
+  WNB_CHECK_ARG((a)->struct_size == sizeof(type), what ": struct_size %u != sizeof(" #type ") = %u (header / "   \
+                "binding out of date?)", (unsigned)(a)->struct_size, (unsigned)sizeof(type))
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: set it once per (kernel instantiation,
+// device), thread-safely (one process may drive several GPUs from several threads).
+#define WNB_SET_SMEM_ATTR(bytes, ...)                                                                          \
+  do {                                                                                                         \
+    static std::atomic<unsigned long long> done_{0};                                                           \
+    int dev_ = 0;                                                                                              \
+    cudaGetDevice(&dev_);                                                                                      \
+    const unsigned long long bit_ = (dev_ >= 0 && dev_ < 64) ? (1ull << dev_) : 0ull;                          \
+    if (!bit_ || !(done_.load(std::memory_order_acquire) & bit_)) {                                            \
+      WNB_CUDA_OK(cudaFuncSetAttribute((__VA_ARGS__), cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes)));  \
+      done_.fetch_or(bit_, std::memory_order_release);                                                         \
+    }                                                                                                          \
   } while (0)
 
 template <typename T>

@@ -20,6 +20,15 @@ namespace wnb {
 using namespace tc;
 typedef __nv_bfloat16 bf16;
 
+// one fp32 value -> the 16-bit word of the activation format (bf16, or fp16 bits carried in a bf16-typed slot)
+__device__ __forceinline__ bf16 act16(bool f16, float v) {
+  if (f16) {
+    const __half hv = __float2half_rn(v);
+    return *reinterpret_cast<const bf16*>(&hv);
+  }
+  return __float2bfloat16_rn(v);
+}
+
 struct DenseDev {
   int B, T, tiles_per_seq, num_tiles;
   int ntaps, t_off[3];
@@ -32,6 +41,8 @@ struct DenseDev {
   const float* bias;
   void* out;        // HEAD direct-store fallback: NCL [B, n_out, T]
   float* colsum;    // NLC mode, optional: fp32 [N] += column sums of the (bf16-rounded) output over all valid frames
+  int f16;          // operands (and NLC output) are fp16 instead of bf16 (WNB200_ACT_F16X2)
+  int split;        // NLC mode, fp16: the output leaves as an fp16 (hi, lo) pair (map_y, map_ylo)
 };
 
 constexpr int DN_THREADS = 320;
@@ -45,7 +56,8 @@ constexpr int DN_SMEM = DN_NSTAGE * DN_STAGE + DN_STAGING + DN_SCRATCH + DN_BIAS
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DN_THREADS, 1)
 dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_x2,
-              const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_y, const DenseDev p) {
+              const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_y,
+              const __grid_constant__ CUtensorMap map_ylo, const DenseDev p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -72,6 +84,7 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     if (p.ntaps2 > 0) prefetch_tensormap(&map_x2);
     prefetch_tensormap(&map_w);
     prefetch_tensormap(&map_y);
+    if (p.split) prefetch_tensormap(&map_ylo);
     for (int s = 0; s < DN_NSTAGE; ++s) {
       mbar_init(full_bar(s), 2);
       mbar_init(empty_bar(s), 1);
@@ -121,7 +134,7 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t idesc = make_idesc_bf16(2 * RB_TILE, p.N);
+      const uint32_t idesc = p.f16 ? make_idesc_f16(2 * RB_TILE, p.N) : make_idesc_bf16(2 * RB_TILE, p.N);
       int it = 0;
       for (int pt = pair; pt < p.num_tiles; pt += npairs, ++it) {
         const int r = it & 1, use = it >> 1;
@@ -187,11 +200,39 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
           }
           tmem_wait_ld();
           uint32_t pk[16];
+          if (p.split) {
+            // fp16 (hi, lo) pair: both staging buffers per chunk, one bulk group
+            uint32_t pl[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float v0 = a[i] + bv[i], v1 = a[i + 1] + bv[i + 1];
+              if (p.leaky) { v0 = leaky(v0); v1 = leaky(v1); }
+              split_f16x2(v0, v1, pk[i >> 1], pl[i >> 1]);
+            }
+            if (issuer) bulk_wait_read0();
+            epi_bar();
+            uint8_t* srow = smem_gen + (stg_base - smem_base) + row * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int o = ((4 * h + j) ^ sw) << 4;
+              *reinterpret_cast<uint4*>(srow + o) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              *reinterpret_cast<uint4*>(srow + DN_ABYTES + o) =
+                  make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+            }
+            fence_proxy_async_smem();
+            epi_bar();
+            if (issuer) {
+              tma_store_3d(&map_y, stg_base, c * 64, t0, b);
+              tma_store_3d(&map_ylo, stg_base + DN_ABYTES, c * 64, t0, b);
+              bulk_commit();
+            }
+            continue;
+          }
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             float v0 = a[i] + bv[i], v1 = a[i + 1] + bv[i + 1];
             if (p.leaky) { v0 = leaky(v0); v1 = leaky(v1); }
-            pk[i >> 1] = pack_bf16x2(v0, v1);
+            pk[i >> 1] = pack_act2(p.f16 != 0, v0, v1);
           }
           const uint32_t boff = (nchunk & 1u) * DN_ABYTES;
           if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -350,7 +391,7 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
 
 // NCL -> NLC bf16: 64 x 64 (channels x frames) tiles through shared memory, 16/32-byte accesses on both sides
 template <typename T>
-__global__ void __launch_bounds__(256) ncl_to_nlc_v2_kernel(int C, int Tn, long long sb, long long sc, bool vec,
+__global__ void __launch_bounds__(256) ncl_to_nlc_v2_kernel(int C, int Tn, long long sb, long long sc, bool vec, bool f16,
                                                             const T* x, bf16* y) {
   // x[b, c, t] at x + b * sb + c * sc + t: a (B, C, T) tensor or a time slice of a longer one (train.py:30 feeds
   // sig[:, :, 0:-1]) is read in place; `vec`: every row starts 16-byte aligned
@@ -365,6 +406,19 @@ __global__ void __launch_bounds__(256) ncl_to_nlc_v2_kernel(int C, int Tn, long 
     if (cok && t0 + tq + 16 <= Tn && vec && sizeof(T) == 2) {
       *reinterpret_cast<uint4*>(&v[0]) = __ldg(reinterpret_cast<const uint4*>(src));
       *reinterpret_cast<uint4*>(&v[8]) = __ldg(reinterpret_cast<const uint4*>(src) + 1);
+      if (f16) {       // bf16 -> fp16 bit patterns (exact for |v| in [2^-14, 65504]; the tile holds raw 16-bit words)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const __half hv = __float2half_rn(__bfloat162float(v[i]));
+          v[i] = *reinterpret_cast<const bf16*>(&hv);
+        }
+      }
+    } else if (f16) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const __half hv = __float2half_rn((cok && t0 + tq + i < Tn) ? to_f32<T>(src[i]) : 0.f);
+        v[i] = *reinterpret_cast<const bf16*>(&hv);
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < 16; ++i)
@@ -398,7 +452,7 @@ __global__ void __launch_bounds__(256) ncl_to_nlc_v2_kernel(int C, int Tn, long 
 // walks FEAT_FRAMES frames so that the per-block set-up (weights, signal window) is amortised.
 constexpr int FEAT_FRAMES = 512;
 template <typename T, int FKR>      // FKR = fk when the weights fit in registers (1..4), 0 = weights read from smem
-__global__ void __launch_bounds__(256) featurize_nlc_kernel(int Tn, int F, int fk, const T* x, const float* w,
+__global__ void __launch_bounds__(256) featurize_nlc_kernel(int Tn, int F, int fk, bool f16, const T* x, const float* w,
                                                             const float* bias, bf16* y) {
   extern __shared__ float fsm[];            // [fk][F] weights (tap-major), [FEAT_FRAMES + fk] signal window
   float* ws = fsm;
@@ -447,10 +501,10 @@ __global__ void __launch_bounds__(256) featurize_nlc_kernel(int Tn, int F, int f
       }
     }
     uint4 o;
-    o.x = pack_bf16x2(leaky(acc[0]), leaky(acc[1]));
-    o.y = pack_bf16x2(leaky(acc[2]), leaky(acc[3]));
-    o.z = pack_bf16x2(leaky(acc[4]), leaky(acc[5]));
-    o.w = pack_bf16x2(leaky(acc[6]), leaky(acc[7]));
+    o.x = pack_act2(f16, leaky(acc[0]), leaky(acc[1]));
+    o.y = pack_act2(f16, leaky(acc[2]), leaky(acc[3]));
+    o.z = pack_act2(f16, leaky(acc[4]), leaky(acc[5]));
+    o.w = pack_act2(f16, leaky(acc[6]), leaky(acc[7]));
     *reinterpret_cast<uint4*>(y + ((long long)b * To + t) * F + f0) = o;
   }
 }
@@ -458,7 +512,7 @@ __global__ void __launch_bounds__(256) featurize_nlc_kernel(int Tn, int F, int f
 // AvgPool1d(pool) on an NCL tensor fused with the NCL -> NLC bf16 layout change (classifier.py:53,102):
 // y[b, to, c] = mean_i x[b, c, to*pool + i].  32 x 32 (channels x pooled frames) tiles through shared memory.
 template <typename T>
-__global__ void __launch_bounds__(256) avgpool_ncl_to_nlc_kernel(int C, int Tn, int To, int pool, const T* x, bf16* y) {
+__global__ void __launch_bounds__(256) avgpool_ncl_to_nlc_kernel(int C, int Tn, int To, int pool, bool f16, const T* x, bf16* y) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
@@ -475,7 +529,7 @@ __global__ void __launch_bounds__(256) avgpool_ncl_to_nlc_kernel(int C, int Tn, 
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int to = t0 + i, c = c0 + tx;
-    if (to < To && c < C) y[((long long)b * To + to) * C + c] = __float2bfloat16_rn(tile[tx][i]);
+    if (to < To && c < C) y[((long long)b * To + to) * C + c] = act16(f16, tile[tx][i]);
   }
 }
 
@@ -486,8 +540,8 @@ __global__ void __launch_bounds__(256) avgpool_ncl_to_nlc_kernel(int C, int Tn, 
 // the bf16 results cross a padded [TF][66] tile and leave as 128-byte rows (one pooled frame x 64 channels).
 template <typename T>
 __global__ void __launch_bounds__(256)
-avgpool_ncl_to_nlc_v2_kernel(int C, int Tn, int To, int pool, int TF, int RS, long long total_bytes, const T* x,
-                             bf16* y) {
+avgpool_ncl_to_nlc_v2_kernel(int C, int Tn, int To, int pool, int TF, int RS, long long total_bytes, bool f16,
+                             const T* x, bf16* y) {
   extern __shared__ __align__(16) uint8_t pool_smem[];
   constexpr int ES = (int)sizeof(T);
   uint8_t* in_s = pool_smem;                                   // [64][RS]
@@ -527,7 +581,7 @@ avgpool_ncl_to_nlc_v2_kernel(int C, int Tn, int To, int pool, int TF, int RS, lo
       const T* src = reinterpret_cast<const T*>(in_s + row * RS + lead_s[row]) + f * pool;
       float acc = 0.f;
       for (int k = 0; k < pool; ++k) acc += to_f32<T>(src[k]);
-      out_s[f * 66 + row] = __float2bfloat16_rn(acc * inv);
+      out_s[f * 66 + row] = act16(f16, acc * inv);
     }
   }
   __syncthreads();
@@ -548,7 +602,7 @@ avgpool_ncl_to_nlc_v2_kernel(int C, int Tn, int To, int pool, int TF, int RS, lo
 __global__ void __launch_bounds__(256)
 entry_embed_nlc_kernel(long long frames, int Tn, int C, int in_dim, int ntaps, int o0, int o1, int o2,
                        const int* __restrict__ lev, const bf16* __restrict__ wemb, const float* __restrict__ bias,
-                       bf16* __restrict__ y) {
+                       bf16* __restrict__ y, bf16* __restrict__ y_lo, bool f16) {
   const int lane = threadIdx.x & 31;
   const long long f = blockIdx.x * 8ll + (threadIdx.x >> 5);
   if (f >= frames) return;
@@ -573,19 +627,29 @@ entry_embed_nlc_kernel(long long frames, int Tn, int C, int in_dim, int ntaps, i
       if (l[j] < 0) continue;
       const uint4 w = __ldg(reinterpret_cast<const uint4*>(wemb + ((long long)j * in_dim + l[j]) * C + c0));
       const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&w);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&w);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float2 v = __bfloat1622float2(w2[q]);
+        const float2 v = f16 ? __half22float2(h2[q]) : __bfloat1622float2(w2[q]);
         acc[2 * q] += v.x;
         acc[2 * q + 1] += v.y;
       }
     }
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
     uint4 o;
-    o.x = pack_bf16x2(acc[0] + b0.x, acc[1] + b0.y);
-    o.y = pack_bf16x2(acc[2] + b0.z, acc[3] + b0.w);
-    o.z = pack_bf16x2(acc[4] + b1.x, acc[5] + b1.y);
-    o.w = pack_bf16x2(acc[6] + b1.z, acc[7] + b1.w);
+    if (y_lo) {      // fp16 (hi, lo) pair
+      uint4 l;
+      split_f16x2(acc[0] + b0.x, acc[1] + b0.y, o.x, l.x);
+      split_f16x2(acc[2] + b0.z, acc[3] + b0.w, o.y, l.y);
+      split_f16x2(acc[4] + b1.x, acc[5] + b1.y, o.z, l.z);
+      split_f16x2(acc[6] + b1.z, acc[7] + b1.w, o.w, l.w);
+      *reinterpret_cast<uint4*>(y_lo + f * C + c0) = l;
+    } else {
+      o.x = pack_act2(f16, acc[0] + b0.x, acc[1] + b0.y);
+      o.y = pack_act2(f16, acc[2] + b0.z, acc[3] + b0.w);
+      o.z = pack_act2(f16, acc[4] + b1.x, acc[5] + b1.y);
+      o.w = pack_act2(f16, acc[6] + b1.z, acc[7] + b1.w);
+    }
     *reinterpret_cast<uint4*>(y + f * C + c0) = o;
   }
 }
@@ -654,8 +718,10 @@ extern "C" int wnb200_avgpool_bwd_nlc_to_ncl(int dtype_out, int B, int C, int T_
 }
 
 extern "C" int wnb200_entry_embed_nlc(int B, int T_, int C, int in_dim, int ntaps, const int32_t* t_off,
-                                      const int32_t* levels, const void* wemb, const float* bias, void* y,
-                                      void* stream) {
+                                      const int32_t* levels, const void* wemb, const float* bias, int act_fmt, void* y,
+                                      void* y_lo, void* stream) {
+  WNB_CHECK_ARG(act_fmt == WNB200_ACT_BF16 || act_fmt == WNB200_ACT_F16X2, "entry_embed_nlc: bad act_fmt");
+  WNB_CHECK_ARG(!y_lo || act_fmt == WNB200_ACT_F16X2, "entry_embed_nlc: y_lo needs the fp16 (hi, lo) format");
   WNB_CHECK_ARG(C >= 8 && C % 8 == 0 && in_dim >= 1 && ntaps >= 1 && ntaps <= 3, "entry_embed_nlc: bad sizes");
   if (B == 0 || T_ == 0) return 0;
   WNB_CHECK_ARG(t_off && levels && wemb && bias && y, "entry_embed_nlc: null pointer");
@@ -663,13 +729,14 @@ extern "C" int wnb200_entry_embed_nlc(int B, int T_, int C, int in_dim, int ntap
   WNB_CHECK_ARG(frames / 8 + 1 < (1ll << 31), "entry_embed_nlc: too many frames");
   entry_embed_nlc_kernel<<<(unsigned)ceil_div64(frames, 8), 256, 0, (cudaStream_t)stream>>>(
       frames, T_, C, in_dim, ntaps, t_off[0], ntaps > 1 ? t_off[1] : 0, ntaps > 2 ? t_off[2] : 0, levels,
-      (const bf16*)wemb, bias, (bf16*)y);
+      (const bf16*)wemb, bias, (bf16*)y, (bf16*)y_lo, act_fmt == WNB200_ACT_F16X2);
   WNB_LAUNCH_OK();
   return 0;
 }
 
 extern "C" int wnb200_dense_fwd_tc(const wnb200_dense_t* a, void* stream) {
   WNB_CHECK_ARG(a != nullptr, "dense_fwd_tc: null argument");
+  WNB_CHECK_STRUCT(a, wnb200_dense_t, "dense_fwd_tc");
   if (a->B == 0 || a->T == 0) return 0;
   WNB_CHECK_ARG(a->Cin >= 64 && a->Cin % 64 == 0, "dense_fwd_tc: Cin=%d must be a multiple of 64", a->Cin);
   WNB_CHECK_ARG(a->ntaps >= 1 && a->ntaps <= 3, "dense_fwd_tc: ntaps=%d not in 1..3", a->ntaps);
@@ -695,9 +762,14 @@ extern "C" int wnb200_dense_fwd_tc(const wnb200_dense_t* a, void* stream) {
   p.n_out = a->n_out; p.softmax = a->softmax; p.out_f32 = a->out_f32;
   p.bias = a->bias; p.out = a->y;
   p.colsum = a->mode == 0 ? a->colsum : nullptr;
+  WNB_CHECK_ARG(a->act_fmt == WNB200_ACT_BF16 || a->act_fmt == WNB200_ACT_F16X2, "dense_fwd_tc: bad act_fmt %d", a->act_fmt);
+  p.f16 = a->act_fmt == WNB200_ACT_F16X2;
+  p.split = p.f16 && a->mode == 0 && a->y_lo != nullptr;
+  WNB_CHECK_ARG(!a->y_lo || p.split, "dense_fwd_tc: y_lo needs act_fmt = WNB200_ACT_F16X2 and the NLC mode");
+  WNB_CHECK_ARG(!p.f16 || !p.colsum, "dense_fwd_tc: colsum is a bf16 (training) feature");
   const int esize = a->out_f32 ? 4 : 2;
   p.tma_out = (a->mode == 1 && ((long long)a->T * esize) % 16 == 0) ? 1 : 0;
-  CUtensorMap mx, mx2, mw, my;
+  CUtensorMap mx, mx2, mw, my, mylo;
   int rc;
   if ((rc = rb_map_nlc(&mx, a->x, a->B, a->T, a->Cin, 2))) return rc;
   mx2 = mx;
@@ -710,24 +782,24 @@ extern "C" int wnb200_dense_fwd_tc(const wnb200_dense_t* a, void* stream) {
   } else {
     my = mx;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    WNB_CUDA_OK(cudaFuncSetAttribute(dense2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DN_SMEM));
-    attr_set = true;
-  }
+  mylo = my;
+  if (p.split && (rc = rb_map_nlc(&mylo, a->y_lo, a->B, a->T, a->N, 2))) return rc;
+  WNB_SET_SMEM_ATTR(DN_SMEM, dense2_kernel);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int pairs = sms / 2;
   if (p.num_tiles < pairs) pairs = p.num_tiles;
-  dense2_kernel<<<2 * pairs, DN_THREADS, DN_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(mx, mx2, mw, my, p);
+  dense2_kernel<<<2 * pairs, DN_THREADS, DN_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(mx, mx2, mw, my, mylo, p);
   WNB_LAUNCH_OK();
   return 0;
 }
 
-extern "C" int wnb200_ncl_to_nlc_bf16_strided(int dtype, int B, int C, int T_, int64_t sb, int64_t sc, const void* x,
-                                              void* y, void* stream) {
+extern "C" int wnb200_ncl_to_nlc_act(int dtype, int act_fmt, int B, int C, int T_, int64_t sb, int64_t sc, const void* x,
+                                     void* y, void* stream) {
   WNB_CHECK_ARG(dtype == WNB200_F32 || dtype == WNB200_BF16, "ncl_to_nlc_bf16: bad dtype");
+  WNB_CHECK_ARG(act_fmt == WNB200_ACT_BF16 || act_fmt == WNB200_ACT_F16X2, "ncl_to_nlc_act: bad act_fmt");
+  const bool f16 = act_fmt == WNB200_ACT_F16X2;
   if (B == 0 || C == 0 || T_ == 0) return 0;
   WNB_CHECK_ARG(x && y, "ncl_to_nlc_bf16: null pointer");
   WNB_CHECK_ARG(B <= 65535 && ceil_div(C, 64) <= 65535, "ncl_to_nlc_bf16: shape too large");
@@ -736,11 +808,16 @@ extern "C" int wnb200_ncl_to_nlc_bf16_strided(int dtype, int B, int C, int T_, i
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = dtype == WNB200_BF16 && sb % 8 == 0 && sc % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
   if (dtype == WNB200_F32)
-    ncl_to_nlc_v2_kernel<float><<<grid, 256, 0, st>>>(C, T_, sb, sc, vec, (const float*)x, (bf16*)y);
+    ncl_to_nlc_v2_kernel<float><<<grid, 256, 0, st>>>(C, T_, sb, sc, vec, f16, (const float*)x, (bf16*)y);
   else
-    ncl_to_nlc_v2_kernel<bf16><<<grid, 256, 0, st>>>(C, T_, sb, sc, vec, (const bf16*)x, (bf16*)y);
+    ncl_to_nlc_v2_kernel<bf16><<<grid, 256, 0, st>>>(C, T_, sb, sc, vec, f16, (const bf16*)x, (bf16*)y);
   WNB_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int wnb200_ncl_to_nlc_bf16_strided(int dtype, int B, int C, int T_, int64_t sb, int64_t sc, const void* x,
+                                              void* y, void* stream) {
+  return wnb200_ncl_to_nlc_act(dtype, WNB200_ACT_BF16, B, C, T_, sb, sc, x, y, stream);
 }
 
 extern "C" int wnb200_ncl_to_nlc_bf16(int dtype, int B, int C, int T_, const void* x, void* y, void* stream) {
@@ -748,8 +825,10 @@ extern "C" int wnb200_ncl_to_nlc_bf16(int dtype, int B, int C, int T_, const voi
 }
 
 extern "C" int wnb200_featurize_nlc(int dtype, int B, int T_, int F, int fk, const void* x, const float* w,
-                                    const float* bias, void* y, void* stream) {
+                                    const float* bias, int act_fmt, void* y, void* stream) {
   WNB_CHECK_ARG(dtype == WNB200_F32 || dtype == WNB200_BF16, "featurize_nlc: bad dtype");
+  WNB_CHECK_ARG(act_fmt == WNB200_ACT_BF16 || act_fmt == WNB200_ACT_F16X2, "featurize_nlc: bad act_fmt");
+  const bool f16 = act_fmt == WNB200_ACT_F16X2;
   WNB_CHECK_ARG(F >= 8 && F % 8 == 0 && fk >= 1 && fk <= 64, "featurize_nlc: F=%d fk=%d unsupported", F, fk);
   if (B == 0 || T_ == 0) return 0;
   WNB_CHECK_ARG(x && w && bias && y, "featurize_nlc: null pointer");
@@ -760,7 +839,7 @@ extern "C" int wnb200_featurize_nlc(int dtype, int B, int T_, int F, int fk, con
   WNB_CHECK_ARG(smem <= 48 * 1024, "featurize_nlc: fk*F too large for the weight cache");
   dim3 grid(ceil_div(To, FEAT_FRAMES), B);
   cudaStream_t st = (cudaStream_t)stream;
-#define FEAT_LAUNCH(TT, FKR) featurize_nlc_kernel<TT, FKR><<<grid, 256, smem, st>>>(T_, F, fk, (const TT*)x, w, bias, (bf16*)y)
+#define FEAT_LAUNCH(TT, FKR) featurize_nlc_kernel<TT, FKR><<<grid, 256, smem, st>>>(T_, F, fk, f16, (const TT*)x, w, bias, (bf16*)y)
 #define FEAT_DISPATCH(TT)                         \
   switch (fk) {                                   \
     case 1: FEAT_LAUNCH(TT, 1); break;            \
@@ -776,13 +855,15 @@ extern "C" int wnb200_featurize_nlc(int dtype, int B, int T_, int F, int fk, con
   return 0;
 }
 
-extern "C" int wnb200_avgpool_ncl_to_nlc_bf16(int dtype, int B, int C, int T_, int pool, const void* x, void* y,
-                                              void* stream) {
-  WNB_CHECK_ARG(dtype == WNB200_F32 || dtype == WNB200_BF16, "avgpool_ncl_to_nlc_bf16: bad dtype");
-  WNB_CHECK_ARG(pool >= 1, "avgpool_ncl_to_nlc_bf16: bad pool");
+extern "C" int wnb200_avgpool_ncl_to_nlc(int dtype, int B, int C, int T_, int pool, const void* x, int act_fmt, void* y,
+                                         void* stream) {
+  WNB_CHECK_ARG(dtype == WNB200_F32 || dtype == WNB200_BF16, "avgpool_ncl_to_nlc: bad dtype");
+  WNB_CHECK_ARG(act_fmt == WNB200_ACT_BF16 || act_fmt == WNB200_ACT_F16X2, "avgpool_ncl_to_nlc: bad act_fmt");
+  const bool f16 = act_fmt == WNB200_ACT_F16X2;
+  WNB_CHECK_ARG(pool >= 1, "avgpool_ncl_to_nlc: bad pool");
   const int To = T_ / pool;
   if (B == 0 || C == 0 || To == 0) return 0;
-  WNB_CHECK_ARG(x && y, "avgpool_ncl_to_nlc_bf16: null pointer");
+  WNB_CHECK_ARG(x && y, "avgpool_ncl_to_nlc: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int es = dtype == WNB200_F32 ? 4 : 2;
   // v2 (aligned vector loads, any row alignment): C even, base pointers 16-byte aligned, a [64 x TF*pool] tile in 40 KB
@@ -795,19 +876,19 @@ extern "C" int wnb200_avgpool_ncl_to_nlc_bf16(int dtype, int B, int C, int T_, i
     const long long total = (long long)B * C * T_ * es;
     dim3 grid2(ceil_div(To, TF), ceil_div(C, 64), B);
     if (dtype == WNB200_F32)
-      avgpool_ncl_to_nlc_v2_kernel<float><<<grid2, 256, smem, st>>>(C, T_, To, pool, TF, RS, total, (const float*)x,
-                                                                    (bf16*)y);
+      avgpool_ncl_to_nlc_v2_kernel<float><<<grid2, 256, smem, st>>>(C, T_, To, pool, TF, RS, total, f16,
+                                                                    (const float*)x, (bf16*)y);
     else
-      avgpool_ncl_to_nlc_v2_kernel<bf16><<<grid2, 256, smem, st>>>(C, T_, To, pool, TF, RS, total, (const bf16*)x,
-                                                                   (bf16*)y);
+      avgpool_ncl_to_nlc_v2_kernel<bf16><<<grid2, 256, smem, st>>>(C, T_, To, pool, TF, RS, total, f16,
+                                                                   (const bf16*)x, (bf16*)y);
     WNB_LAUNCH_OK();
     return 0;
   }
   dim3 grid(ceil_div(To, 32), ceil_div(C, 32), B);
   if (dtype == WNB200_F32)
-    avgpool_ncl_to_nlc_kernel<float><<<grid, 256, 0, st>>>(C, T_, To, pool, (const float*)x, (bf16*)y);
+    avgpool_ncl_to_nlc_kernel<float><<<grid, 256, 0, st>>>(C, T_, To, pool, f16, (const float*)x, (bf16*)y);
   else
-    avgpool_ncl_to_nlc_kernel<bf16><<<grid, 256, 0, st>>>(C, T_, To, pool, (const bf16*)x, (bf16*)y);
+    avgpool_ncl_to_nlc_kernel<bf16><<<grid, 256, 0, st>>>(C, T_, To, pool, f16, (const bf16*)x, (bf16*)y);
   WNB_LAUNCH_OK();
   return 0;
 }

@@ -38,6 +38,7 @@ struct ResDev {
   bf16* save_act;   // training: gate / tanh / sigmoid, NLC bf16 (CTA-pair kernel only)
   bf16* save_th;
   bf16* save_sg;
+  int has_lo;       // PREC kernels: x_lo is present (the stream's fp16 low half joins the projection)
 };
 
 constexpr int RB_THREADS = 320;
@@ -65,7 +66,13 @@ __device__ __forceinline__ void mma_kblock(uint32_t tmem_d, uint32_t a_addr, uin
               (first && k4 == 0) ? 0u : 1u);
 }
 
+// Per-phase clock64 stamps of CTA 0 (scripts/timeline.py): compiled in only with -DWNB200_TIMELINE (a separate
+// diagnostic build, WNB200_TIMELINE=1 python -m wavenet_speech_b200.csrc.build); the shipped kernels carry none.
+#ifdef WNB200_TIMELINE
 #define RB_STAMP(slot) do { if (p.dbg && blockIdx.x == 0 && it < 8) p.dbg[it * 16 + (slot)] = clock64(); } while (0)
+#else
+#define RB_STAMP(slot) do { } while (0)
+#endif
 
 template <int C>
 __global__ void __launch_bounds__(RB_THREADS, 1)
@@ -391,9 +398,9 @@ struct R2Cfg {
   static constexpr int SMEM = NSTAGE * STAGE + ACT + STAGING + 1024 + 256;
 };
 
-template <int C>
+template <int C, bool F16 = false>
 __device__ __forceinline__ void mma_kblock_2sm(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, bool first) {
-  constexpr uint32_t idesc = make_idesc_bf16(2 * RB_TILE, C);
+  constexpr uint32_t idesc = make_idesc(F16, 2 * RB_TILE, C);
 #pragma unroll
   for (int k4 = 0; k4 < 4; ++k4)
     umma_bf16_2sm(tmem_d, make_smem_desc_sw128(a_addr + k4 * 32), make_smem_desc_sw128(b_addr + k4 * 32), idesc,
@@ -403,14 +410,27 @@ __device__ __forceinline__ void mma_kblock_2sm(uint32_t tmem_d, uint32_t a_addr,
 // SAVE (training): the gate and its two factors are kept for backward.  E1 then works on whole 64-channel blocks:
 // tanh / sigmoid go through the two output staging buffers, the gate is stored straight from the shared tile that
 // feeds G2, all three by TMA (thread-level global stores from the TMEM-lane layout cost a 128-byte line per lane).
-template <int C, bool SAVE>
+//
+// PREC (WNB200_ACT_F16X2, inference): the accuracy mode that holds the stated bf16-class tolerance (2e-2 on the logits)
+// at the depth of the benchmarked stacks.  With the reference's initialisation the residual projection is a random
+// nn.Linear (block.py:48,77-78), the stream grows ~1.45x per block and every rounding of it is amplified by the blocks
+// that follow; a bf16 stream + bf16 gate + tanh.approx is 5e-2..9e-2 off at 16-20 blocks (so is PyTorch's own bf16
+// evaluation).  Here operands are fp16 (same tensor-core rate, 3 more mantissa bits; weights that were rounded to bf16
+// are exact in fp16), the stream is carried between layers as an fp16 (hi, lo) pair -- the dilated taps read hi, the
+// projection contracts hi AND lo against the same Wproj blocks (one extra K slab: 8 C^2 instead of 7 C^2 MAC per
+// frame; its MMAs run while E1b is still producing the second half of the gate) -- and the gate is evaluated with
+// ex2/rcp (1e-6) instead of tanh.approx (5e-4).  map_act / map_th double as the x_lo / res_lo maps.
+template <int C, bool SAVE, bool PREC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RB_THREADS, 1)
 resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                  const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_res,
                  const __grid_constant__ CUtensorMap map_skips, const __grid_constant__ CUtensorMap map_act,
                  const __grid_constant__ CUtensorMap map_th, const __grid_constant__ CUtensorMap map_sg,
                  const ResDev p) {
+  static_assert(!(SAVE && PREC), "the training forward keeps the bf16 format");
   using K = R2Cfg<C>;
+  const CUtensorMap& map_xlo = map_act;      // PREC: fp16 low half of the input stream / of the output stream
+  const CUtensorMap& map_reslo = map_th;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -433,6 +453,10 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     prefetch_tensormap(&map_w2);
     prefetch_tensormap(&map_res);
     prefetch_tensormap(&map_skips);
+    if (PREC) {
+      prefetch_tensormap(&map_xlo);
+      prefetch_tensormap(&map_reslo);
+    }
     for (int s = 0; s < K::NSTAGE; ++s) {
       mbar_init(full_bar(s), 2);
       mbar_init(empty_bar(s), 1);
@@ -505,6 +529,17 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           tma_load_2d_2sm(sa + RB_ABYTES, &map_w2, lfull, C + kb * 64, wrow);
           end_stage(lfull);
         }
+        if (PREC && p.has_lo) {
+          // the stream's low half against the same Wproj blocks: with a ring exactly KB deep the weight half of each
+          // stage still holds the block the hi pass used -- only the 16 KB activation block is loaded
+          for (int kb = 0; kb < K::KB; ++kb) {
+            const uint32_t sa = smem_base + stage * K::STAGE;
+            const uint32_t lfull = begin_stage(K::RETAIN ? RB_ABYTES : K::STAGE);
+            tma_load_3d_2sm(sa, &map_xlo, lfull, kb * 64, t0, b);
+            if (!K::RETAIN) tma_load_2d_2sm(sa + RB_ABYTES, &map_w2, lfull, C + kb * 64, wrow);
+            end_stage(lfull);
+          }
+        }
         for (int part = 0; part < 2; ++part) {
           for (int kb = 0; kb < K::KB; ++kb) {
             const uint32_t sa = smem_base + stage * K::STAGE;
@@ -526,7 +561,9 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       int it = 0;
       for (int pt = pair; pt < p.num_tiles; pt += npairs, ++it) {
         const uint32_t prev = (uint32_t)((it - 1) & 1), cur = (uint32_t)(it & 1);
+#ifdef WNB200_TIMELINE
         long long wfull = 0;
+#endif
         RB_STAMP(0);
         for (int half = 0; half < 2; ++half) {
           if (it > 0) {
@@ -534,16 +571,22 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             tc_fence_after();
           }
           for (int kb = 0; kb < p.ntaps * K::KB; ++kb) {
+#ifdef WNB200_TIMELINE
             { const long long c0 = clock64(); mbar_wait(full_bar(stage), phase); wfull += clock64() - c0; }
+#else
+            mbar_wait(full_bar(stage), phase);
+#endif
             tc_fence_after();
             const uint32_t sa = smem_base + stage * K::STAGE;
-            mma_kblock_2sm<C>(half == 0 ? tmemA : tmemB, sa, sa + RB_ABYTES, kb == 0);
+            mma_kblock_2sm<C, PREC>(half == 0 ? tmemA : tmemB, sa, sa + RB_ABYTES, kb == 0);
             umma_commit_2sm(empty_bar(stage));
             next();
           }
           umma_commit_2sm(half == 0 ? accA_full : accB_full);
           RB_STAMP(1 + half);
+#ifdef WNB200_TIMELINE
           if (p.dbg && blockIdx.x == 0 && it < 8) p.dbg[it * 16 + 13 + half] = wfull;
+#endif
         }
         mbar_wait(e1a_done, cur);
         tc_fence_after();
@@ -552,9 +595,19 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * K::STAGE;
-          mma_kblock_2sm<C>(tmemA, sa, sa + RB_ABYTES, kb == 0);
+          mma_kblock_2sm<C, PREC>(tmemA, sa, sa + RB_ABYTES, kb == 0);
           umma_commit_2sm(empty_bar(stage));
           next();
+        }
+        if (PREC && p.has_lo) {
+          for (int kb = 0; kb < K::KB; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * K::STAGE;
+            mma_kblock_2sm<C, PREC>(tmemA, sa, sa + RB_ABYTES, false);
+            umma_commit_2sm(empty_bar(stage));
+            next();
+          }
         }
         for (int kb = 0; kb < K::KB; ++kb) {
           if (kb == K::KB / 2) {
@@ -565,7 +618,7 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * K::STAGE;
-          mma_kblock_2sm<C>(tmemA, act_base + kb * RB_ABYTES, sa + RB_ABYTES, false);
+          mma_kblock_2sm<C, PREC>(tmemA, act_base + kb * RB_ABYTES, sa + RB_ABYTES, false);
           umma_commit_2sm(empty_bar(stage));
           next();
         }
@@ -575,7 +628,7 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * K::STAGE;
-          mma_kblock_2sm<C>(tmemB, act_base + kb * RB_ABYTES, sa + RB_ABYTES, kb == 0);
+          mma_kblock_2sm<C, PREC>(tmemB, act_base + kb * RB_ABYTES, sa + RB_ABYTES, kb == 0);
           umma_commit_2sm(empty_bar(stage));
           next();
         }
@@ -666,11 +719,22 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           }
           tmem_wait_ld();
           uint32_t pk[8];
+          if constexpr (PREC) {
+            // bias1 arrives pre-scaled: tanh rows by -2 log2(e), sigmoid rows by -log2(e)
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            const float v0 = tanh_approx(a[i] + bta[i]) * sigmoid_approx(g[i] + bsa[i]);
-            const float v1 = tanh_approx(a[i + 1] + bta[i + 1]) * sigmoid_approx(g[i + 1] + bsa[i + 1]);
-            pk[i >> 1] = pack_bf16x2(v0, v1);
+            for (int i = 0; i < 16; i += 2) {
+              const float v0 = gate_precise(fmaf(a[i], -2.885390081777927f, bta[i]), fmaf(g[i], -1.4426950408889634f, bsa[i]));
+              const float v1 = gate_precise(fmaf(a[i + 1], -2.885390081777927f, bta[i + 1]),
+                                            fmaf(g[i + 1], -1.4426950408889634f, bsa[i + 1]));
+              pk[i >> 1] = pack_f16x2(v0, v1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              const float v0 = tanh_approx(a[i] + bta[i]) * sigmoid_approx(g[i] + bsa[i]);
+              const float v1 = tanh_approx(a[i + 1] + bta[i + 1]) * sigmoid_approx(g[i + 1] + bsa[i + 1]);
+              pk[i >> 1] = pack_bf16x2(v0, v1);
+            }
           }
           const int ch = half * (C / 2) + col;
           const int kb = ch >> 6, ci = (ch & 63) >> 3;
@@ -705,27 +769,52 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           }
           tmem_wait_ld();
           uint32_t pk[16];
+          if constexpr (PREC) {
+            // the stream leaves as an fp16 (hi, lo) pair: both staging buffers per 64-channel chunk
+            uint32_t pl[16];
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) pk[i >> 1] = pack_bf16x2(a[i] + bv[i], a[i + 1] + bv[i + 1]);
-          const uint32_t boff = (nchunk & 1u) * RB_ABYTES;
-          if (issuer) {
-            if (drain) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          }
-          drain = false;
-          epi_bar();
-          uint8_t* srow = smem_gen + (stg_base - smem_base) + boff + row * 128;
+            for (int i = 0; i < 32; i += 2) split_f16x2(a[i] + bv[i], a[i + 1] + bv[i + 1], pk[i >> 1], pl[i >> 1]);
+            if (issuer) bulk_wait_read0();
+            epi_bar();
+            uint8_t* srow = smem_gen + (stg_base - smem_base) + row * 128;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(srow + (((4 * h + j) ^ sw) << 4)) =
-                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          fence_proxy_async_smem();
-          epi_bar();
-          if (issuer) {
-            tma_store_3d(&map_res, stg_base + boff, c * 64, t0, b);
-            bulk_commit();
+            for (int j = 0; j < 4; ++j) {
+              const int o = ((4 * h + j) ^ sw) << 4;
+              *reinterpret_cast<uint4*>(srow + o) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              *reinterpret_cast<uint4*>(srow + RB_ABYTES + o) =
+                  make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+            }
+            fence_proxy_async_smem();
+            epi_bar();
+            if (issuer) {
+              tma_store_3d(&map_res, stg_base, c * 64, t0, b);
+              tma_store_3d(&map_reslo, stg_base + RB_ABYTES, c * 64, t0, b);
+              bulk_commit();
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) pk[i >> 1] = pack_bf16x2(a[i] + bv[i], a[i + 1] + bv[i + 1]);
+            const uint32_t boff = (nchunk & 1u) * RB_ABYTES;
+            if (issuer) {
+              if (drain) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            }
+            drain = false;
+            epi_bar();
+            uint8_t* srow = smem_gen + (stg_base - smem_base) + boff + row * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(srow + (((4 * h + j) ^ sw) << 4)) =
+                  make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            fence_proxy_async_smem();
+            epi_bar();
+            if (issuer) {
+              tma_store_3d(&map_res, stg_base + boff, c * 64, t0, b);
+              bulk_commit();
+            }
           }
         }
+        if (PREC) drain = true;      // one bulk group reads both buffers: the skip chunks start after it has drained
       }
       tc_fence_before();
       mbar_arrive_cluster(r_e2a);
@@ -783,7 +872,7 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             uint32_t pk[8];
 #pragma unroll
             for (int i = 0; i < 16; i += 2)
-              pk[i >> 1] = pack_bf16x2(leaky(sm[i] + (a[i] + bv[i])), leaky(sm[i + 1] + (a[i + 1] + bv[i + 1])));
+              pk[i >> 1] = pack_act2<PREC>(leaky(sm[i] + (a[i] + bv[i])), leaky(sm[i + 1] + (a[i + 1] + bv[i + 1])));
             // bf16 row of 64 channels = 8 sixteen-byte pieces; this thread's 16 channels are pieces (u&1)*4 + 2h, +1
             uint8_t* orow = smem_gen + (stg_base - smem_base) + (u >> 1) * RB_ABYTES + row * 128;
             const int c16 = (u & 1) * 4 + 2 * h;
@@ -854,11 +943,7 @@ template <int C>
 static int launch_resblock(const CUtensorMap& mx, const CUtensorMap& mw1, const CUtensorMap& mw2,
                            const CUtensorMap& mres, const CUtensorMap& msk, const ResDev& p, cudaStream_t st) {
   using K = RCfg<C>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    WNB_CUDA_OK(cudaFuncSetAttribute(resblock_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
-    attr_set = true;
-  }
+  WNB_SET_SMEM_ATTR(K::SMEM, resblock_kernel<C>);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -868,22 +953,18 @@ static int launch_resblock(const CUtensorMap& mx, const CUtensorMap& mw1, const 
   return 0;
 }
 
-template <int C, bool SAVE>
+template <int C, bool SAVE, bool PREC = false>
 static int launch_resblock2(const CUtensorMap& mx, const CUtensorMap& mw1, const CUtensorMap& mw2,
                             const CUtensorMap& mres, const CUtensorMap& msk, const CUtensorMap& mact,
                             const CUtensorMap& mth, const CUtensorMap& msg, const ResDev& p, cudaStream_t st) {
   using K = R2Cfg<C>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    WNB_CUDA_OK(cudaFuncSetAttribute(resblock2_kernel<C, SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
-    attr_set = true;
-  }
+  WNB_SET_SMEM_ATTR(K::SMEM, resblock2_kernel<C, SAVE, PREC>);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int pairs = sms / 2;
   if (p.num_tiles < pairs) pairs = p.num_tiles;
-  resblock2_kernel<C, SAVE><<<2 * pairs, RB_THREADS, K::SMEM, st>>>(mx, mw1, mw2, mres, msk, mact, mth, msg, p);
+  resblock2_kernel<C, SAVE, PREC><<<2 * pairs, RB_THREADS, K::SMEM, st>>>(mx, mw1, mw2, mres, msk, mact, mth, msg, p);
   WNB_LAUNCH_OK();
   return 0;
 }
@@ -904,6 +985,7 @@ using namespace wnb;
 
 extern "C" int wnb200_resblock_fwd_tc(const wnb200_resblock_t* a, void* stream) {
   WNB_CHECK_ARG(a != nullptr, "resblock_fwd_tc: null argument");
+  WNB_CHECK_STRUCT(a, wnb200_resblock_t, "resblock_fwd_tc");
   const int C = a->C;
   WNB_CHECK_ARG(C == 128 || C == 256, "resblock_fwd_tc: C=%d not in {128,256}", C);
   WNB_CHECK_ARG(a->ntaps >= 1 && a->ntaps <= 3, "resblock_fwd_tc: ntaps=%d not in 1..3", a->ntaps);
@@ -926,6 +1008,12 @@ extern "C" int wnb200_resblock_fwd_tc(const wnb200_resblock_t* a, void* stream) 
   WNB_CHECK_ARG(!a->save_act || (a->save_th && a->save_sg && a->variant != 1),
                 "resblock_fwd_tc: saving the gate factors needs all three buffers and the CTA-pair kernel");
   const bool pair = a->variant != 1;     // 0 / 2: CTA-pair kernel (default); 1: single-CTA kernel
+  const bool prec = a->act_fmt == WNB200_ACT_F16X2;
+  WNB_CHECK_ARG(a->act_fmt == WNB200_ACT_BF16 || prec, "resblock_fwd_tc: bad act_fmt %d", a->act_fmt);
+  WNB_CHECK_ARG(!prec || (pair && !a->save_act), "resblock_fwd_tc: the fp16 (hi, lo) format needs the CTA-pair kernel, inference only");
+  WNB_CHECK_ARG(!prec || !a->res || a->res_lo, "resblock_fwd_tc: the fp16 (hi, lo) format writes res AND res_lo");
+  WNB_CHECK_ARG(prec || (!a->x_lo && !a->res_lo), "resblock_fwd_tc: x_lo / res_lo belong to the fp16 (hi, lo) format");
+  p.has_lo = prec && a->x_lo != nullptr;
   const int wbox = pair ? C / 2 : C;
   CUtensorMap mx, mw1, mw2, mres, msk;
   int rc;
@@ -947,6 +1035,13 @@ extern "C" int wnb200_resblock_fwd_tc(const wnb200_resblock_t* a, void* stream) 
       if ((rc = rb_map_nlc(&msg, a->save_sg, a->B, a->T, C, 2))) return rc;
       return C == 256 ? launch_resblock2<256, true>(mx, mw1, mw2, mres, msk, mact, mth, msg, p, st)
                       : launch_resblock2<128, true>(mx, mw1, mw2, mres, msk, mact, mth, msg, p, st);
+    }
+    if (prec) {
+      CUtensorMap mxlo = mx, mreslo = mx;
+      if (a->x_lo && (rc = rb_map_nlc(&mxlo, a->x_lo, a->B, a->T, C, 2))) return rc;
+      if (a->res && (rc = rb_map_nlc(&mreslo, a->res_lo, a->B, a->T, C, 2))) return rc;
+      return C == 256 ? launch_resblock2<256, false, true>(mx, mw1, mw2, mres, msk, mxlo, mreslo, mx, p, st)
+                      : launch_resblock2<128, false, true>(mx, mw1, mw2, mres, msk, mxlo, mreslo, mx, p, st);
     }
     return C == 256 ? launch_resblock2<256, false>(mx, mw1, mw2, mres, msk, mx, mx, mx, p, st)
                     : launch_resblock2<128, false>(mx, mw1, mw2, mres, msk, mx, mx, mx, p, st);

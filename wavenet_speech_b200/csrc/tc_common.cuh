@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -112,6 +113,14 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// fp16 x fp16 -> fp32 (a_format = b_format = 0): three more mantissa bits than bf16, range 65504
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t make_idesc(bool f16, int M, int N) {
+  return f16 ? make_idesc_f16(M, N) : make_idesc_bf16(M, N);
 }
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -262,6 +271,36 @@ __device__ __forceinline__ float sigmoid_approx(float x) { return fmaf(0.5f, tan
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// two-byte activation formats of the tensor-core path (WNB200_ACT_*): 0 = bf16, 1 = fp16
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
+  return F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ uint32_t pack_act2(bool f16, float lo, float hi) {
+  return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+// fp16 (hi, lo) split of two fp32 values: hi = fp16(v) (clamped to the finite range), lo = fp16(v - hi):
+// hi + lo carries 22 mantissa bits of v
+__device__ __forceinline__ void split_f16x2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  v0 = fminf(fmaxf(v0, -65504.f), 65504.f);
+  v1 = fminf(fmaxf(v1, -65504.f), 65504.f);
+  const __half2 h = __floats2half2_rn(v0, v1);
+  const float2 hf = __half22float2(h);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = pack_f16x2(v0 - hf.x, v1 - hf.y);
+}
+// tanh(a) * sigmoid(b) from the pre-scaled arguments ua = -2 log2(e) a, ub = -log2(e) b:
+//   (1 - 2^ua) / ((1 + 2^ua) (1 + 2^ub))        -- 2 ex2 + 1 rcp, relative error ~1e-6 (tanh.approx: 5e-4)
+__device__ __forceinline__ float gate_precise(float ua, float ub) {
+  const float eu = fast_ex2(fminf(ua, 60.f)), ev = fast_ex2(fminf(ub, 60.f));
+  const float opv = 1.f + ev;
+  return __fdividef(1.f - eu, fmaf(eu, opv, opv));
 }
 
 }  // namespace tc

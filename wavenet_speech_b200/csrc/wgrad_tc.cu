@@ -242,11 +242,7 @@ extern "C" int wnb200_wgrad2_tc(int B, int T_, int Cg, int m0, int N, int nsrc, 
   mx2 = mx;
   if (nsrc > 1 && (rc = wg_map_nlc64(&mx2, x2_nlc, B, T_, N))) return rc;
   if ((rc = wg_map_dw(&mdw, dw, 256, nsrc * N))) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    WNB_CUDA_OK(cudaFuncSetAttribute(wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
-    attr_set = true;
-  }
+  WNB_SET_SMEM_ATTR(WG_SMEM, wgrad2_kernel);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -20,12 +20,21 @@ class HostPipeline(object):
         self.s_in = torch.cuda.Stream(self.device)
         self.s_out = torch.cuda.Stream(self.device)
         self._bufs = None
+        # per staging slot: the event after which the slot may be overwritten (its last consumer's kernels are done).
+        # Instance state, not per-submit state: the slots persist across submits, so the first copy-ins of batch k+1
+        # must wait for the last chunks of batch k that still read them.
+        self._buf_free = [None, None]
 
     def _buffers(self, n, x_shape, x_dtype):
         key = (n, tuple(x_shape), x_dtype)
         if self._bufs is None or self._bufs[0] != key:
             xs = [torch.empty(x_shape, dtype=x_dtype, device=self.device) for _ in range(min(n, 2))]
             self._bufs = (key, xs)
+            # fresh blocks come from the compute stream's pool: whatever used that memory before is ordered on the
+            # compute stream, so the copy stream waits for this point before its first write
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._buf_free = [ev, ev]
         return self._bufs[1]
 
     def __call__(self, x_host, y_host=None):
@@ -52,7 +61,7 @@ class HostPipeline(object):
         cur = torch.cuda.current_stream(self.device)
         in_done = [torch.cuda.Event() for _ in range(n)]
         comp_done = [torch.cuda.Event() for _ in range(n)]
-        buf_free = [None, None]
+        buf_free = self._buf_free
         outs = []
         for i, (s, e) in enumerate(bounds):
             slot = i % len(xbuf)

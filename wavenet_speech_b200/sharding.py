@@ -130,8 +130,10 @@ class PeerHaloExchange(object):
     for its own two signals.  No NCCL on the data path, no staging copy, nothing on the host.
 
     Buffer of a rank: 2 slots (step parity) x [left halo (B, C, halo_left) | right halo (B, C, halo_right)].  A neighbour
-    may start writing step k+1 while this rank still reads step k (other slot); it cannot reach step k+2 before this rank
-    has sent its step k+1 signal, which is stream-ordered after the read of step k."""
+    may start writing step k+1 while this rank still reads step k (other slot).  Before it rewrites the slot of step k at
+    step k+2 it waits for this rank's ACK of step k (a signal raised after the read, stream-ordered): with one-directional
+    halos (any causal network: halo_right = 0) the writer never waits on the reader otherwise, and nothing else would
+    keep it from running two steps ahead.  Channels: 2 * parity + side for the data, 4 + 2 * parity + side for the acks."""
 
     def __init__(self, B, C, halo_left, halo_right, dtype, rank, world, group=None):
         import torch.distributed as dist
@@ -155,11 +157,16 @@ class PeerHaloExchange(object):
         B, C, n = x_shard.shape
         assert (B, C) == (self.B, self.C) and x_shard.dtype == self.dtype and hl <= n and hr <= n
         par = self.step & 1
+        reuse = self.step >= 2                                # this parity's slots were written two steps ago
         self.step += 1
         if rank < world - 1 and hl > 0:                       # my last frames -> right neighbour's LEFT halo slot
+            if reuse:
+                self.hdl.wait_signal(rank + 1, channel=4 + 2 * par)       # ... and it has read them
             self._slot(rank + 1, 0, par).copy_(x_shard[:, :, n - hl:])
             self.hdl.put_signal(rank + 1, channel=2 * par)
         if rank > 0 and hr > 0:                               # my first frames -> left neighbour's RIGHT halo slot
+            if reuse:
+                self.hdl.wait_signal(rank - 1, channel=4 + 2 * par + 1)
             self._slot(rank - 1, 1, par).copy_(x_shard[:, :, :hr])
             self.hdl.put_signal(rank - 1, channel=2 * par + 1)
         need_l, need_r = plan["start"] - plan["lo"], plan["hi"] - plan["end"]
@@ -171,7 +178,13 @@ class PeerHaloExchange(object):
         if rank < world - 1 and hr > 0:
             self.hdl.wait_signal(rank + 1, channel=2 * par + 1)
             parts.append(self._slot(rank, 1, par)[:, :, :need_r])
-        return torch.cat(parts, 2) if len(parts) > 1 else x_shard
+        out = torch.cat(parts, 2) if len(parts) > 1 else x_shard
+        # acks: the halo slots of this step have been read (the cat above is ordered before these on the stream)
+        if rank > 0 and hl > 0:
+            self.hdl.put_signal(rank - 1, channel=4 + 2 * par)
+        if rank < world - 1 and hr > 0:
+            self.hdl.put_signal(rank + 1, channel=4 + 2 * par + 1)
+        return out
 
 
 def time_sharded_forward(forward_fn, x_ext, plan, T, out_extra=0):

@@ -425,7 +425,7 @@ class _ClassifierTrain(torch.autograd.Function):
         B, _, T = seq.shape
         To = T // pool
         h0 = torch.empty((B, To, C), dtype=torch.bfloat16, device=seq.device)
-        _lib.call("wnb200_avgpool_ncl_to_nlc_bf16", ops._dt(seq), B, C, T, pool, ops._p(seq), ops._p(h0), ops._stream())
+        _lib.call("wnb200_avgpool_ncl_to_nlc", ops._dt(seq), B, C, T, pool, ops._p(seq), _lib.ACT_BF16, ops._p(h0), ops._stream())
         skips = torch.empty((B, To, C), dtype=torch.float32, device=seq.device)
         saved, sk_act = stack_forward(h0, pk["stack"], skips)
         out, skips_act, h1 = head_forward(skips, pk["head"], seq.dtype, model.softmax, sk_act)
@@ -495,7 +495,7 @@ class _RawCTCNetTrain(torch.autograd.Function):
         To = T + fk - 1
         f = torch.empty((B, To, F), dtype=torch.bfloat16, device=seq.device)
         _lib.call("wnb200_featurize_nlc", ops._dt(seq), B, T, F, fk, ops._p(seq), ops._p(pk["f0w"]), ops._p(pk["f0b"]),
-                  ops._p(f), ops._stream())
+                  _lib.ACT_BF16, ops._p(f), ops._stream())
         h0 = FP.dense(f, [0], pk["f2w"], pk["f2b"], F, leaky=1)
         skips = torch.empty((B, To, C), dtype=torch.float32, device=seq.device)
         saved, sk_act = stack_forward(h0, pk["stack"], skips)
