@@ -140,6 +140,11 @@ int wnb200_sum_f32(int64_t n, const float* x, float* out, float* scratch, void* 
 int wnb200_positions_add(int dtype, int B, int F, int T, int t0, const float* w, const float* bias,
                          void* out, void* stream);
 
+/* Gradients of the position layer's parameters (autograd of raw_ctcnet.py:131-135; trained by pretrain_tnt.py:121-124):
+ * dw[f] += sum_{b,t} g[b,f,t] (t + t0) [|w[f](t+t0)+bias[f]| < 1];  db[f] += sum_{b,t} g[b,f,t] [..]; g NCL [B,F,T]. */
+int wnb200_positions_bwd(int dtype, int B, int F, int T, int t0, const float* w, const float* bias, const void* g,
+                         float* dw, float* db, void* stream);
+
 /* Per-frame argmax over channels of NCL logits -> int64 [B,T]  (sequence_decoders.py:21-23,
  * legacy_code/train.py:36). */
 int wnb200_argmax_channels(int dtype, int B, int C, int T, const void* x, int64_t* out, void* stream);

@@ -1,5 +1,5 @@
 """Per-phase clock64 timeline of CTA 0 of the fused residual-block kernels (diagnostic).
-usage: timeline.py <dilation> [v2]"""
+usage: WNB200_TIMELINE=1 timeline.py <dilation> [v2|v3] [p[flags]]     (p = precise format; flags: experiment bits)"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -13,8 +13,15 @@ variant = int(sys.argv[2][1:]) - 1 if v2 else 0   # "v2" -> single-CTA (1), "v3"
 torch.manual_seed(0)
 blk = W.ResidualBlock(C, C, 2, d, causal=True)
 bn = torch.nn.Conv1d(C, C, 1)
-pk = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in FP.pack_block(blk, bn).items()}
-x = torch.randn(B, T, C, device="cuda").bfloat16()
+prec = len(sys.argv) > 3 and sys.argv[3].startswith("p")
+xflags = int(sys.argv[3][1:] or 0) if prec else 0
+nolo = len(sys.argv) > 4 and sys.argv[4] == "nolo"
+pk = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in FP.pack_block(blk, bn, precise=prec).items()}
+x = torch.randn(B, T, C, device="cuda").to(torch.float16 if prec else torch.bfloat16)
+x_lo = (torch.randn(B, T, C, device="cuda") * 1e-3).half() if (prec and not nolo) else None
+res_lo = torch.empty_like(x) if prec else None
+if prec:
+    variant |= xflags << 2
 res = torch.empty_like(x)
 skips = torch.zeros(B, T, C, device="cuda")
 dbg = torch.zeros(8 * 16, dtype=torch.int64, device="cuda")
@@ -23,7 +30,7 @@ for i in range(4):
     if i == 3:
         ev[0].record()
     if v2:
-        FP.resblock(x, pk, res, skips, False, dbg=dbg, variant=variant)
+        FP.resblock(x, pk, res, skips, False, dbg=dbg, variant=variant, x_lo=x_lo, res_lo=res_lo)
     else:
         FP.chain(x, C, pk["offsets"], FP.TC_GATE, pk["w1"], pk["b1"], 2 * C, n2=2 * C, use_x2=1,
                  epi2=FP.EPI2_RESBLOCK, w2=pk["w2"], b2=pk["b2"], y_nlc=res, skips=skips, skips_init=0, dbg=dbg)

@@ -296,3 +296,36 @@ def test_standalone_gate():
     (y * r.cuda()).sum().backward()
     check(y, ref.detach(), what="gate")
     assert G.rel_linf(ag.grad.cpu(), a.grad) <= 1e-5 and G.rel_linf(bg.grad.cpu(), b.grad) <= 1e-5
+
+
+def test_positions_parameters_get_gradients():
+    """RawCTCNet(positions=True) is trained by the reference (pretrain_tnt.py:121-124, tests/kmer_stay_prediction.py:52):
+    the position layer's weight and bias receive the oracle's gradients (round 1 returned None for them)."""
+    torch.manual_seed(21)
+    layers = [(12, 12, 2, dd) for dd in (1, 2)]
+    net = W.RawCTCNet(12, 3, 5, layers, 12, positions=True, softmax=False).cuda()
+    with torch.no_grad():                     # spread w*t+b over (-1, 1) so that hardtanh's linear region is populated
+        pc = net.positions_conv1x1[0]
+        pc.weight.copy_((torch.rand_like(pc.weight) - 0.5) * 0.08)
+        pc.bias.copy_((torch.rand_like(pc.bias) - 0.5) * 1.5)
+    _grads_vs_oracle(net, lambda sd, xx: O.raw_ctcnet_forward(sd, xx, layers, positions=True, softmax=False),
+                     torch.randn(2, 1, 40))
+    assert net.positions_conv1x1[0].weight.grad is not None and net.positions_conv1x1[0].bias.grad is not None
+    assert float(net.positions_conv1x1[0].weight.grad.abs().sum()) > 0
+
+
+@pytest.mark.parametrize("k,d,causal", [(8, 1, True), (6, 3, False), (16, 2, False)])
+def test_wide_kernel_block(k, d, causal):
+    """Kernel widths above the 4 taps one launch takes (the reference trains with widths up to 32,
+    pretrain_tnt.py:98,120): chained tap chunks + the stand-alone gate kernel, forward and backward."""
+    torch.manual_seed(31 + k)
+    blk = W.ResidualBlock(6, 10, k, d, causal=causal).cuda()
+    _grads_vs_oracle(blk, lambda sd, xx: O.residual_block(sd, "", xx, d, causal), torch.randn(2, 6, 70))
+
+
+def test_wide_featuriser():
+    """RawCTCNet with feature_kwidth = 9 on the generic path (LeakyReLU applied after the chained tap chunks)."""
+    torch.manual_seed(41)
+    layers = [(8, 8, 2, 1)]
+    net = W.RawCTCNet(8, 9, 5, layers, 8, softmax=False).cuda()
+    _grads_vs_oracle(net, lambda sd, xx: O.raw_ctcnet_forward(sd, xx, layers, softmax=False), torch.randn(2, 1, 60))

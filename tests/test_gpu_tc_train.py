@@ -328,3 +328,38 @@ def test_tc_paths_on_tiny_reads(T, B):
         ct = cn.cuda()(x.cuda().bfloat16().requires_grad_(True))
         assert ct.shape == cref.shape and G.rel_linf(ct.float().cpu(), cref) <= 2e-2
         ct.float().sum().backward()
+
+
+def test_gradients_do_not_alias_between_parameters():
+    """one bias-sum tensor was returned for conv1x1_residual.bias and residual_proj.bias, and one d(skip sum)
+    for every layer's bottleneck bias; AccumulateGrad stole them as-is, so clip_grad_norm_ scaled the shared memory once
+    per alias and a second backward without set_to_none accumulated L times.  Every parameter owns its gradient memory,
+    two accumulated backward passes give exactly twice one pass, and clipping scales every gradient once."""
+    torch.manual_seed(5)
+    C, nl, T, B = 128, 3, 260, 2
+    layers = [(C, C, 2, 2 ** i) for i in range(nl)]
+    net = W.WaveNet(C, 2, layers, C, softmax=False).cuda()          # fp32 master weights, bf16 input: tensor-core path
+    x = torch.randn(B, C, T, device="cuda").bfloat16()
+    R = torch.randn(B, C, T, device="cuda")
+
+    def backward_once():
+        y = net(x)
+        assert y.grad_fn is not None and type(y.grad_fn).__name__.startswith("_WaveNetTrain")
+        (y.float() * R).sum().backward()
+
+    backward_once()
+    named = [(n, p) for n, p in net.named_parameters() if p.grad is not None]
+    ptrs = {}
+    for n, p in named:
+        assert p.grad.data_ptr() not in ptrs, (n, ptrs[p.grad.data_ptr()])
+        ptrs[p.grad.data_ptr()] = n
+    g1 = {n: p.grad.detach().clone() for n, p in named}
+    backward_once()                                                  # accumulates into the existing .grad tensors
+    for n, p in named:
+        assert torch.allclose(p.grad, 2 * g1[n], rtol=1e-5, atol=1e-6), n
+    net.zero_grad(set_to_none=False)
+    backward_once()
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in g1.values()))
+    torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=float(total) / 4)
+    for n, p in named:
+        assert torch.allclose(p.grad, g1[n] / 4, rtol=1e-4, atol=1e-7), n

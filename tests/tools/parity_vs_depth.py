@@ -63,6 +63,8 @@ if __name__ == "__main__":
     rows = []
     for kind in ("wavenet", "raw_ctcnet"):
         for depth in DEPTHS:
+            if kind == "raw_ctcnet" and depth == 1:
+                depth = 2                    # RawCTCNet always has the input block + at least one more
             for seed in (0, 1):
                 r = run(kind, depth, seed)
                 rows.append(r)

@@ -92,6 +92,7 @@ SIGNATURES = {
     "wnb200_xent_bwd": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_sum_f32": [c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_positions_add": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_positions_bwd": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_argmax_channels": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "wnb200_chain_fwd_tc": [ctypes.POINTER(Chain), c_void_p],
     "wnb200_resblock_fwd_tc": [ctypes.POINTER(ResBlock), c_void_p],

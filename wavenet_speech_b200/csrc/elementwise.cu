@@ -279,6 +279,45 @@ __global__ void positions_add_kernel(int B, int F, int Tn, int t0, const float* 
   }
 }
 
+// Gradients of the position layer's two parameters (autograd of raw_ctcnet.py:131-135; the reference trains RawCTCNet
+// with positions=True in pretrain_tnt.py:121-124): with u = w[f] * (t + t0) + bias[f],
+//   dw[f] += sum_{b,t} g[b,f,t] * (t + t0) * [|u| < 1],   db[f] += sum_{b,t} g[b,f,t] * [|u| < 1]     (hardtanh's slope)
+// grid (F, time chunks): coalesced along t, one pair of atomics per block.
+template <typename T>
+__global__ void __launch_bounds__(256) positions_bwd_kernel(int B, int F, int Tn, int t0, int tchunk, const float* w,
+                                                            const float* bias, const T* g, float* dw, float* db) {
+  const int f = blockIdx.x;
+  const int tb = blockIdx.y * tchunk, te = min(Tn, tb + tchunk);
+  const float wf = w[f], bf = bias[f];
+  float sw = 0.f, sb = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const T* gp = g + ((long long)b * F + f) * Tn;
+    for (int t = tb + threadIdx.x; t < te; t += blockDim.x) {
+      const float tt = (float)(t + t0);
+      const float u = wf * tt + bf;
+      if (u > -1.f && u < 1.f) {
+        const float gv = to_f32<T>(gp[t]);
+        sw += gv * tt;
+        sb += gv;
+      }
+    }
+  }
+  __shared__ float red[2][8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sw += __shfl_xor_sync(0xffffffffu, sw, o);
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sw; red[1][threadIdx.x >> 5] = sb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c = 0.f;
+    for (int i = 0; i < 8; ++i) { a += red[0][i]; c += red[1][i]; }
+    atomicAdd(dw + f, a);
+    atomicAdd(db + f, c);
+  }
+}
+
 template <typename T>
 __global__ void argmax_kernel(int B, int C, int Tn, const T* x, long long* out) {
   const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -678,6 +717,20 @@ extern "C" int wnb200_positions_add(int dtype, int B, int F, int T_, int t0, con
   if (n == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   DISPATCH(dtype, "positions_add", (positions_add_kernel<T><<<grid_for(n), 256, 0, st>>>(B, F, T_, t0, w, bias, (T*)out)));
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_positions_bwd(int dtype, int B, int F, int T_, int t0, const float* w, const float* bias,
+                                    const void* g, float* dw, float* db, void* stream) {
+  if (B == 0 || F == 0 || T_ == 0) return 0;
+  WNB_CHECK_ARG(w && bias && g && dw && db, "positions_bwd: null pointer");
+  WNB_CHECK_ARG(F <= 65535 * 32, "positions_bwd: F too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tchunk = 4096;
+  dim3 grid(F, ceil_div(T_, tchunk));
+  DISPATCH(dtype, "positions_bwd", (positions_bwd_kernel<T><<<grid, 256, 0, st>>>(B, F, T_, t0, tchunk, w, bias,
+                                                                                  (const T*)g, dw, db)));
   WNB_LAUNCH_OK();
   return 0;
 }

@@ -39,6 +39,7 @@ struct ResDev {
   bf16* save_th;
   bf16* save_sg;
   int has_lo;       // PREC kernels: x_lo is present (the stream's fp16 low half joins the projection)
+  int xflags;       // WNB200_TIMELINE builds only: experiment switches (variant >> 2): 1 approx gate, 2 no lo store
 };
 
 constexpr int RB_THREADS = 320;
@@ -719,6 +720,18 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           }
           tmem_wait_ld();
           uint32_t pk[8];
+#ifdef WNB200_TIMELINE
+          if (PREC && (p.xflags & 1)) {        // experiment: the approximate gate on the pre-scaled arguments
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              const float v0 = tanh_approx(fmaf(a[i], -2.885390081777927f, bta[i]) * -0.34657359f) *
+                               sigmoid_approx(fmaf(g[i], -1.4426950408889634f, bsa[i]) * -0.69314718f);
+              const float v1 = tanh_approx(fmaf(a[i + 1], -2.885390081777927f, bta[i + 1]) * -0.34657359f) *
+                               sigmoid_approx(fmaf(g[i + 1], -1.4426950408889634f, bsa[i + 1]) * -0.69314718f);
+              pk[i >> 1] = pack_f16x2(v0, v1);
+            }
+          } else
+#endif
           if constexpr (PREC) {
             // bias1 arrives pre-scaled: tanh rows by -2 log2(e), sigmoid rows by -log2(e)
 #pragma unroll
@@ -788,6 +801,9 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             epi_bar();
             if (issuer) {
               tma_store_3d(&map_res, stg_base, c * 64, t0, b);
+#ifdef WNB200_TIMELINE
+              if (!(p.xflags & 2))
+#endif
               tma_store_3d(&map_reslo, stg_base + RB_ABYTES, c * 64, t0, b);
               bulk_commit();
             }
@@ -1001,13 +1017,14 @@ extern "C" int wnb200_resblock_fwd_tc(const wnb200_resblock_t* a, void* stream) 
   p.bias1 = a->bias1; p.bias2 = a->bias2;
   p.write_res = a->res != nullptr; p.skips_init = a->skips_init;
   p.final_act = a->skips_act != nullptr;
-  WNB_CHECK_ARG(!p.final_act || (a->variant != 1 && !a->res),
+  WNB_CHECK_ARG(!p.final_act || ((a->variant & 3) != 1 && !a->res),
                 "resblock_fwd_tc: skips_act needs the CTA-pair kernel and the last layer (res = NULL)");
   p.dbg = (long long*)a->dbg;
   p.save_act = (bf16*)a->save_act; p.save_th = (bf16*)a->save_th; p.save_sg = (bf16*)a->save_sg;
-  WNB_CHECK_ARG(!a->save_act || (a->save_th && a->save_sg && a->variant != 1),
+  WNB_CHECK_ARG(!a->save_act || (a->save_th && a->save_sg && (a->variant & 3) != 1),
                 "resblock_fwd_tc: saving the gate factors needs all three buffers and the CTA-pair kernel");
-  const bool pair = a->variant != 1;     // 0 / 2: CTA-pair kernel (default); 1: single-CTA kernel
+  const bool pair = (a->variant & 3) != 1;     // 0 / 2: CTA-pair kernel (default); 1: single-CTA kernel
+  p.xflags = a->variant >> 2;
   const bool prec = a->act_fmt == WNB200_ACT_F16X2;
   WNB_CHECK_ARG(a->act_fmt == WNB200_ACT_BF16 || prec, "resblock_fwd_tc: bad act_fmt %d", a->act_fmt);
   WNB_CHECK_ARG(!prec || (pair && !a->save_act), "resblock_fwd_tc: the fp16 (hi, lo) format needs the CTA-pair kernel, inference only");

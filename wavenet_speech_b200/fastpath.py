@@ -124,6 +124,15 @@ def _version_key(module):
     return tuple((p.data_ptr(), p._version) for p in module.parameters())
 
 
+def invalidate_packs(module):
+    """Drop the cached weight packs of `module` and of every sub-module.  The cache is keyed on the parameters'
+    (data_ptr, _version): in-place updates through the parameter (optimisers, load_state_dict, p.copy_) are seen, but
+    writes through an alias with its own version counter -- `p.data.copy_(...)`, `p.data[...] = ...`, a raw-pointer write
+    from outside torch -- are not.  Call this after such an update."""
+    for m in module.modules():
+        m.__dict__.pop("_wnb_pack_cache", None)
+
+
 def _cached(module, name, build):
     key = _version_key(module)
     cache = module.__dict__.setdefault("_wnb_pack_cache", {})

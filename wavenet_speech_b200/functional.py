@@ -157,16 +157,26 @@ class _ResBlock(torch.autograd.Function):
         x = ops.time_major(x)
         dtype = x.dtype
         M, C, k = wt.shape
-        if k > ops.MAX_SRC:
-            raise NotImplementedError("gated conv with kernel width > %d" % ops.MAX_SRC)
         T = x.shape[2]
-        wg, bg = _pack_gate(wt, ws, bt, bs, dtype)
         need_bwd = any(ctx.needs_input_grad)
-        gterms = [Term(x, wg[j], offsets[j]) for j in range(k)]
-        if need_bwd:
-            act, th, sg = ops.taps_fwd(gterms, bg, M, T, EPI_GATE, want_gate_parts=True)
+        if k > ops.MAX_SRC:
+            # wide kernels (the reference trains with widths up to 32: pretrain_tnt.py:98,120): the two pre-activations
+            # are accumulated over chunks of MAX_SRC taps (chained launches), then gated by the stand-alone gate kernel
+            wts, wss = _slabs(wt, dtype), _slabs(ws, dtype)
+            a = ops.taps_fwd([Term(x, wts[j], offsets[j]) for j in range(k)], _f32(bt), M, T)
+            b = ops.taps_fwd([Term(x, wss[j], offsets[j]) for j in range(k)], _f32(bs), M, T)
+            if need_bwd:
+                act, th, sg = ops.gate_fwd(a, b, want_parts=True)
+            else:
+                act, th, sg = ops.gate_fwd(a, b), None, None
+            del a, b
         else:
-            act, th, sg = ops.taps_fwd(gterms, bg, M, T, EPI_GATE), None, None
+            wg, bg = _pack_gate(wt, ws, bt, bs, dtype)
+            gterms = [Term(x, wg[j], offsets[j]) for j in range(k)]
+            if need_bwd:
+                act, th, sg = ops.taps_fwd(gterms, bg, M, T, EPI_GATE, want_gate_parts=True)
+            else:
+                act, th, sg = ops.taps_fwd(gterms, bg, M, T, EPI_GATE), None, None
         wres2, wproj2, wskip2 = _slabs(wres, dtype)[0], _slabs(wproj, dtype)[0], _slabs(wskip, dtype)[0]
         b_res = _f32(bres) + _f32(bproj)
         res = ops.taps_fwd([Term(act, wres2), Term(x, wproj2)], b_res, M, T)
@@ -416,19 +426,33 @@ def multiplicative_unit(h, convs, offsets):
 
 
 class _Positions(torch.autograd.Function):
-    """out + hardtanh(w * t + b) (reference raw_ctcnet.py:131-135).  Parameter gradients of the
-    position layer are not propagated (the reference never trains with positions=True)."""
+    """out + hardtanh(w * t + b) (reference raw_ctcnet.py:131-135), with the gradients of x AND of the position layer's
+    two parameters (the reference trains RawCTCNet(positions=True): pretrain_tnt.py:121-124, tests/kmer_stay_prediction.py:52)."""
 
     @staticmethod
     def forward(ctx, x, w, b, t0):
         out = x.contiguous().clone()
-        ops.positions_add_(out, w.detach().float().reshape(-1).contiguous(),
-                           b.detach().float().reshape(-1).contiguous(), t0)
+        wf = w.detach().float().reshape(-1).contiguous()
+        bf = b.detach().float().reshape(-1).contiguous()
+        ops.positions_add_(out, wf, bf, t0)
+        ctx.save_for_backward(wf, bf)
+        ctx.t0, ctx.wshape, ctx.wdt, ctx.bdt = t0, w.shape, w.dtype, b.dtype
         return out
 
     @staticmethod
     def backward(ctx, g):
-        return g, None, None, None
+        from . import _lib
+        wf, bf = ctx.saved_tensors
+        dw = db = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            gc = g.contiguous()
+            B, F, T = gc.shape
+            dw = torch.zeros(F, dtype=torch.float32, device=g.device)
+            db = torch.zeros(F, dtype=torch.float32, device=g.device)
+            _lib.call("wnb200_positions_bwd", ops._dt(gc), B, F, T, int(ctx.t0), ops._p(wf), ops._p(bf), ops._p(gc),
+                      ops._p(dw), ops._p(db), ops._stream())
+            dw, db = dw.view(ctx.wshape).to(ctx.wdt), db.to(ctx.bdt)
+        return g, dw, db, None
 
 
 def positions_mix(x, w, b, t0=0):

@@ -3,6 +3,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as WF
+from ..ops import device_guard
 from ..ops import EPI_NONE
 from .conv_ops import CausalConv1d, NonCausalConv1d
 from .layernorm import LayerNorm
@@ -12,6 +13,7 @@ class GatedActivationUnit(nn.Module):
     """tanh(x) * sigmoid(y) (reference block.py:177-188).  Inside ResidualBlock the gate is fused into the
     contraction epilogue; called on its own it runs the stand-alone gate kernel."""
 
+    @device_guard
     def forward(self, x, y):
         return WF.gated_activation(x, y)
 
@@ -45,6 +47,7 @@ class ResidualBlock(nn.Module):
     def offsets(self):
         return self.conv_tanh.offsets
 
+    @device_guard
     def forward(self, seq):
         return WF.residual_block(seq, self, self.offsets)
 
@@ -63,6 +66,7 @@ class MultiplicativeUnit(nn.Module):
         self.receptive_field = max(self.gate1.receptive_field, self.gate2.receptive_field,
                                    self.gate3.receptive_field, self.update.receptive_field)
 
+    @device_guard
     def forward(self, h):
         # one contraction launch for the four convolutions + one fused gate launch (forward and backward)
         return WF.multiplicative_unit(h, (self.gate1.conv1d, self.gate2.conv1d, self.gate3.conv1d, self.update.conv1d),
@@ -77,6 +81,7 @@ class MultiplicativeUnit(nn.Module):
 
 
 class _ByteNetBlock(nn.Module):
+    @device_guard
     def forward(self, seq):
         return seq + self.stack(seq)
 
@@ -91,11 +96,13 @@ class _ByteNetBlock(nn.Module):
 class _Conv1x1(nn.Conv1d):
     """nn.Conv1d(k=1) parameter container whose forward is the libwnb200 contraction."""
 
+    @device_guard
     def forward(self, x):
         return WF.conv_taps(x, self.weight, self.bias, [0])
 
 
 class _ReLU(nn.Module):
+    @device_guard
     def forward(self, x):
         return torch.relu(x)
 

@@ -3,6 +3,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as WF
+from ..ops import device_guard
 from . import _stack
 from .block import ResidualBlock
 
@@ -46,6 +47,7 @@ class WaveNetClassifier(nn.Module):
                 zero(p)
         _stack.kaiming_weights_(self.output_block.parameters(), zero)
 
+    @device_guard
     def forward(self, seq):
         from .. import fastpath
         y = fastpath.try_classifier_forward(self, seq)

@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as WF
+from ..ops import device_guard
 
 
 def autopad(k, d):
@@ -55,6 +56,7 @@ class _DilatedConv1d(nn.Module):
     def offsets(self):
         return WF.tap_offsets(self.kernel_width, self.dilation, self.causal)
 
+    @device_guard
     def forward(self, seq):
         return WF.conv_taps(seq, self.conv1d.weight, self.conv1d.bias, self.offsets)
 

@@ -3,6 +3,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as WF
+from ..ops import device_guard
 
 
 class LayerNorm(nn.Module):
@@ -16,6 +17,7 @@ class LayerNorm(nn.Module):
         self.eps = eps
         self.dim = dim
 
+    @device_guard
     def forward(self, x):
         if self.dim != 1 or x.dim() != 3:
             raise NotImplementedError("LayerNorm kernel normalises dim=1 of a (B, C, T) tensor")

@@ -6,6 +6,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as WF
+from ..ops import device_guard
 from .conv_ops import autopad, compute_new_length, reshape_in, reshape_out  # re-exported like the reference
 
 
@@ -37,6 +38,7 @@ class LinearConv1d(nn.Conv1d):
         out = WF.conv_taps(frame, self.weight, self.bias, self._ker_ixs, T_out=1)
         return out if keep_dims else out.squeeze(2)
 
+    @device_guard
     def forward(self, in_seq):
         k, d, p = self.kernel_size[0], self.dilation[0], self.padding[0]
         t_out = in_seq.size(2) + 2 * p - d * (k - 1)

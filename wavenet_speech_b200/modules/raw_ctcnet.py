@@ -3,6 +3,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as WF
+from ..ops import device_guard
 from ..ops import EPI_LEAKY
 from . import _stack
 from .block import ResidualBlock
@@ -76,6 +77,7 @@ class RawCTCNet(nn.Module):
                          T_out=t_out)
         return WF.conv_taps(h, f2.weight, f2.bias, [0], epilogue=EPI_LEAKY)
 
+    @device_guard
     def forward(self, seq, t0=0):
         """seq: (batch, 1, T) -> (batch, num_labels, T + feature_kwidth - 1).  `t0` (extension, default 0)
         is the global frame index of seq[..., 0] for position mixing on a time shard."""

@@ -3,6 +3,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as WF
+from ..ops import device_guard
 from . import _stack
 from .block import ResidualBlock
 from .conv_ops import CausalConv1d
@@ -44,12 +45,14 @@ class WaveNet(nn.Module):
                 zero(p)
         _stack.kaiming_weights_(self.output_stack.parameters(), zero)
 
+    @device_guard
     def forward_levels(self, levels, out_dtype=torch.bfloat16):
         """forward(one_hot(levels)) for a (B, T) integer tensor of quantised levels, without the one-hot tensor
         (tensor-core path only; not in the reference, whose loaders one-hot on the host: fns.py:6-15)."""
         from .. import fastpath
         return fastpath.wavenet_forward_levels(self, levels, out_dtype)
 
+    @device_guard
     def forward(self, signal):
         from .. import fastpath
         y = fastpath.try_wavenet_forward(self, signal)

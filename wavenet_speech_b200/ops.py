@@ -36,6 +36,20 @@ def _p(t):
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
 
 
+def device_guard(fn):
+    """Run a module's forward with the INPUT tensor's device current: streams, the device check and every launch then
+    address that device even if the caller's current device is another one (one process driving several GPUs)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, x, *a, **k):
+        if torch.is_tensor(x) and x.is_cuda and x.device.index != torch.cuda.current_device():
+            with torch.cuda.device(x.device):
+                return fn(self, x, *a, **k)
+        return fn(self, x, *a, **k)
+    return wrapper
+
+
 _checked = {}
 
 
@@ -93,14 +107,19 @@ def taps_fwd(terms, bias, M, T_out, epilogue=EPI_NONE, out=None, accumulate=Fals
         assert bias.dtype == torch.float32 and bias.is_contiguous()
     # more than MAX_SRC terms: chain launches through the accumulate path (epilogue applied last)
     chunks = [terms[i:i + MAX_SRC] for i in range(0, len(terms), MAX_SRC)]
+    late_leaky = len(chunks) > 1 and epilogue == EPI_LEAKY      # wide kernels (RawCTCNet featuriser, fk up to 64)
     if len(chunks) > 1:
-        assert epilogue == EPI_NONE, "more than %d terms only supported without epilogue" % MAX_SRC
+        assert epilogue in (EPI_NONE, EPI_LEAKY) and not (late_leaky and accumulate), \
+            "more than %d terms: the gate epilogue is applied by the caller (functional._ResBlock)" % MAX_SRC
     for ci, chunk in enumerate(chunks):
         arr = (_lib.Src * len(chunk))()
         for i, tm in enumerate(chunk):
             _fill(arr[i], tm)
         _lib.call("wnb200_taps_fwd", dt, B, T_out, M, len(chunk), arr, _p(bias if ci == 0 else None),
-                  epilogue, 1 if (accumulate or ci > 0) else 0, _p(out), _p(th), _p(sg), _stream())
+                  EPI_NONE if late_leaky else epilogue, 1 if (accumulate or ci > 0) else 0, _p(out), _p(th), _p(sg),
+                  _stream())
+    if late_leaky:       # x * (x > 0 ? 1 : 0.01), in place, with the LeakyReLU-backward kernel applied to (x, x)
+        _lib.call("wnb200_leaky_bwd", dt, out.numel(), _p(out), _p(out), _p(out), _stream())
     if want_gate_parts:
         return out, th, sg
     return out

@@ -240,6 +240,7 @@ def stack_backward(stack, saved, dskips, need_dx0):
     zb = _zeros(C, dev)
     csk = colsum(dskips)                                    # d(bottleneck bias), identical for every layer
     L = len(saved)
+    csk_rows = csk.unsqueeze(0).repeat(L, 1)                # ... but every layer's parameter gets its own memory
     grads = [None] * L
     Ms = [None] * L
     dres = dres_cs = None
@@ -270,7 +271,7 @@ def stack_backward(stack, saved, dskips, need_dx0):
             dwres = dwres.unsqueeze(2)
             dbres = dres_cs
         Ms[l] = wgrad_rows(dskips, act, 0, C, C)
-        grads[l] = [dwt, dbab[:C], dws, dbab[C:], dwres, dbres, None, None, dwproj, dbres, None, csk]
+        grads[l] = [dwt, dbab[:C], dws, dbab[C:], dwres, dbres, None, None, dwproj, dbres, None, csk_rows[l]]
         saved[l] = None                                     # free this layer's activations
         dres, dres_cs = dx, dx_cs
     # weight-space algebra of the folded skip -> bottleneck product, batched over layers
@@ -334,7 +335,21 @@ def _head_params(head):
 
 
 def _cast(grads, params):
-    return tuple(None if g is None else g.reshape(p.shape).to(p.dtype) for g, p in zip(grads, params))
+    """Gradients in the parameters' shapes / dtypes.  Every parameter gets its OWN memory: the same tensor handed to two
+    parameters (one bias sum serves conv1x1_residual.bias and residual_proj.bias; the bottleneck biases of all layers
+    share d(skip sum)) would be stolen as-is by AccumulateGrad, and clip_grad_norm_ / zero_grad(set_to_none=False) /
+    gradient accumulation would then act on the shared memory once per alias."""
+    seen, out = set(), []
+    for g, p in zip(grads, params):
+        if g is None:
+            out.append(None)
+            continue
+        g = g.reshape(p.shape).to(p.dtype)
+        if g.data_ptr() in seen:
+            g = g.clone()
+        seen.add(g.data_ptr())
+        out.append(g)
+    return tuple(out)
 
 
 # --------------------------------------------------------------------------- WaveNet
