@@ -387,6 +387,7 @@ def main():
     ap.add_argument("--precision", default="precise", choices=["precise", "fast"],
                     help="tensor-core activation format: precise = fp16 operands + fp16 (hi, lo) residual stream + exact "
                          "gate (meets 2e-2 at 20 blocks); fast = bf16 stream + tanh.approx (round-1 format)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--no-stock", action="store_true", help="skip the stock-PyTorch-on-GPU comparator")
     ap.add_argument("--no-longread", action="store_true", help="skip the time-sharded 1M-sample read (config 5)")
     args = ap.parse_args()
@@ -406,6 +407,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = None
+    if not args.no_numa_bind:          # before any pinned allocation: first touch places the staging buffers
+        from wavenet_speech_b200.utils import numa as _numa
+        numa = _numa.bind_to_gpu_node(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -498,6 +503,35 @@ def main():
                    "ms_per_step": ms_e2e / args.steps,
                    "api": "wavenet_speech_b200.pipeline.HostPipeline(model, chunks=%d).submit(x_pinned, y_pinned) per step, "
                           ".wait() once at the end" % args.e2e_chunks}
+
+        # ---- what the HOST can deliver: every rank moves the step's bytes in and out (same pinned buffers, same two
+        # copy streams) with no kernels at all.  e2e cannot be faster than this; at N = 8 it is the limiter.
+        e2e_ceiling = None
+        if not args.no_e2e:
+            s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+            xd2 = torch.empty_like(x_dev)
+            yd2 = torch.empty(y_host.shape, dtype=y_host.dtype, device="cuda")
+            for _ in range(2):
+                xd2.copy_(x_host, non_blocking=True)
+                y_hosts[0].copy_(yd2, non_blocking=True)
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(args.steps):
+                with torch.cuda.stream(s_in):
+                    xd2.copy_(x_host, non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    y_hosts[k & 1].copy_(yd2, non_blocking=True)
+            s_in.synchronize()
+            s_out.synchronize()
+            barrier()
+            ms_c = max_over_ranks((time.perf_counter() - t0) * 1e3)
+            nbytes = (x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size())
+            e2e_ceiling = {"value": samples * world * args.steps / (ms_c * 1e-3), "unit": UNIT,
+                           "ms_per_step": ms_c / args.steps,
+                           "host_gb_per_s_all_ranks": world * nbytes * args.steps / (ms_c * 1e-3) / 1e9,
+                           "what": "H2D of the input + D2H of the output per step on two copy streams, no kernels: "
+                                   "the copy ceiling of this host at this N"}
+            del xd2, yd2
 
         # ---- the same end to end, with the host handing over the quantised LEVELS (B, T) uint8 instead of their
         # one-hot encoding: what the reference's loaders hold before fns.py:6-15; the one-hot never exists on this path
@@ -607,6 +641,9 @@ def main():
                    "fwd_bwd": fwd_bwd,                 # configs[2]: WaveNet-CTC train step, batch-sharded + grad all-reduce
                    "time_sharded": long_read,          # configs[4]: 1M-sample read, time-sharded + halo exchange
                    "e2e_levels": e2e_levels,           # host hands over uint8 levels instead of the one-hot tensor
+                   "e2e_copy_ceiling": e2e_ceiling,    # pure H2D + D2H of the same bytes at this N: the host's limit
+                   "e2e_frac_of_copy_ceiling": (e2e["value"] / e2e_ceiling["value"]) if (e2e and e2e_ceiling) else None,
+                   "numa": numa,
                    "stock_torch_gpu": stock},          # the reference's module semantics as stock torch ops on this GPU
         "clocks": clocks, "e2e": e2e, "e2e_levels": e2e_levels, "gpu_launches": launches, "roofline": roofline,
         "cpu_baseline": cpu,

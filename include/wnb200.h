@@ -264,6 +264,59 @@ typedef struct {
 int wnb200_dense_fwd_tc(const wnb200_dense_t* args /*host*/, void* stream);
 
 
+/* ------------------------------------------------------------------------------------------
+ * Weight packing (pack.cu): the operand matrices above, built on the device straight from the reference's parameter
+ * tensors (state_dict layout: conv weights [out, in, k], nn.Linear weight [out, in]) -- one launch per block / head.
+ * w_dtype = dtype of ALL source parameters (WNB200_F32 master weights or WNB200_BF16).
+ *   w1  [2C][k*C]  act_fmt words, tap-major columns; row_order 1 = [tanh 0:C/2; sig 0:C/2; tanh C/2:C; sig C/2:C]
+ *                  (wnb200_resblock_fwd_tc), 0 = [tanh 0:C; sig 0:C] (wnb200_chain_fwd_tc)
+ *   b1  [2C] fp32 in w1's row order; for WNB200_ACT_F16X2 pre-scaled (tanh rows x -2 log2 e, sigmoid rows x -log2 e)
+ *   w2  [2C][2C] = [[Wres, Wproj], [Wbn*Wskip, 0]];   b2 [2C] = [bres + bproj ; Wbn*bskip + bbn]
+ *   backward (optional, all four or none, bf16):  wdg [C][2C] = [Wres^T | (Wbn Wskip)^T],  wdg_skip [C][C],
+ *   wdx [C][k*2C + C] = [Wt_0^T | Ws_0^T | ... | Wproj^T],  wdx_taps [C][k*2C] (autograd of block.py:66-79).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  uint32_t struct_size;   /* = sizeof(wnb200_pack_block_t) */
+  int32_t C, k;           /* channels (in = out = bottleneck width), kernel width 1..3 */
+  int32_t act_fmt;        /* WNB200_ACT_* of w1 / w2 */
+  int32_t w_dtype;        /* WNB200_F32 | WNB200_BF16 */
+  int32_t row_order;
+  const void *wt, *bt, *ws, *bs;      /* conv_tanh / conv_sigmoid .conv1d.weight [C,C,k], .bias [C]  (block.py:35-44) */
+  const void *wres, *bres;            /* conv1x1_residual (block.py:45)                                                */
+  const void *wskip, *bskip;          /* conv1x1_skip (block.py:46)                                                    */
+  const void *wproj, *bproj;          /* residual_proj, nn.Linear (block.py:48)                                        */
+  const void *wbn, *bbn;              /* the block's skip bottleneck (wavenet.py:60-63)                                */
+  void* w1; float* b1; void* w2; float* b2;
+  void *wdg, *wdg_skip, *wdx, *wdx_taps;
+} wnb200_pack_block_t;
+int wnb200_pack_block(const wnb200_pack_block_t* args /*host*/, void* stream);
+
+/* Output head (LeakyReLU -> 1x1 -> LeakyReLU -> 1x1; wavenet.py:67-71): pw1 [C][C], pb1 [C], pw2 [n2][C] and pb2 [n2]
+ * with n2 = n_out rounded up to 16 (padded rows zero); backward (optional, bf16): w3t [C][npad] = W3^T with npad = n_out
+ * rounded up to 64, w1t [C][C] = W1^T. */
+typedef struct {
+  uint32_t struct_size;   /* = sizeof(wnb200_pack_head_t) */
+  int32_t C, n_out, act_fmt, w_dtype;
+  int32_t reserved0;
+  const void *w1, *b1, *w3, *b3;      /* output_stack.1 / .3 weight [C,C,1] / [n_out,C,1] and bias */
+  void* pw1; float* pb1; void* pw2; float* pb2;
+  void *w3t, *w1t;
+} wnb200_pack_head_t;
+int wnb200_pack_head(const wnb200_pack_head_t* args /*host*/, void* stream);
+
+/* Gradients of the two factors of the folded skip -> bottleneck product, from weight space, all L <= 64 layers in one
+ * launch: with M[l] = dskips (x) gate_l (fp32 [L][C][C], written by wnb200_wgrad2_tc) and csk = column sums of dskips,
+ *   dwskip[l] = Wbn_l^T M[l]     dwbn[l] = M[l] Wskip_l^T + csk (x) bskip_l     dbskip[l] = Wbn_l^T csk
+ * wbn / wskip / bskip: HOST arrays of L device pointers to the parameters (w_dtype). */
+int wnb200_fold_grads(int w_dtype, int L, int C, const void* const* wbn /*host*/, const void* const* wskip /*host*/,
+                      const void* const* bskip /*host*/, const float* M, const float* csk, float* dwskip, float* dwbn,
+                      float* dbskip, void* stream);
+
+/* Bytes of device memory one forward of a C-channel residual stack over B x T frames needs besides its input and
+ * output (stream ping-pong -- twice that for the fp16 (hi, lo) format --, fp32 skip sum, the head's two activations),
+ * for hosts that allocate the buffers themselves. */
+size_t wnb200_workspace_bytes(int B, int T, int C, int act_fmt);
+
 /* RawCTCNet featuriser, first layer: Conv1d(1, F, fk, padding=fk-1) + LeakyReLU (raw_ctcnet.py:57-59) on the raw
  * signal x [B, 1, T] -> y NLC [B, T+fk-1, F] in act_fmt (bf16 / fp16).  w fp32 [F, fk], bias fp32 [F]. */
 int wnb200_featurize_nlc(int dtype, int B, int T, int F, int fk, const void* x, const float* w, const float* bias,

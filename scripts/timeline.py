@@ -8,20 +8,26 @@ from wavenet_speech_b200 import fastpath as FP
 
 C, B, T = 256, 32, 16384
 d = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-v2 = len(sys.argv) > 2
-variant = int(sys.argv[2][1:]) - 1 if v2 else 0   # "v2" -> single-CTA (1), "v3" -> CTA pair (2)
+toks = sys.argv[2:]
+v2 = any(t in ("v2", "v3") for t in toks)
+variant = 1 if "v2" in toks else (2 if "v3" in toks else 0)     # "v2" -> single-CTA, "v3" -> CTA pair
+ptok = [t for t in toks if t.startswith("p")]
+prec = bool(ptok)
+xflags = int(ptok[0][1:] or 0) if prec else 0
+nolo = "nolo" in toks
+if "old" in toks:
+    variant |= 16                                               # CTA-wide output epilogues
+for t in toks:
+    if t.startswith("s"):
+        variant |= int(t[1:]) << 8                              # stagger odd pairs by N x 1024 cycles
 torch.manual_seed(0)
 blk = W.ResidualBlock(C, C, 2, d, causal=True)
 bn = torch.nn.Conv1d(C, C, 1)
-prec = len(sys.argv) > 3 and sys.argv[3].startswith("p")
-xflags = int(sys.argv[3][1:] or 0) if prec else 0
-nolo = len(sys.argv) > 4 and sys.argv[4] == "nolo"
 pk = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in FP.pack_block(blk, bn, precise=prec).items()}
 x = torch.randn(B, T, C, device="cuda").to(torch.float16 if prec else torch.bfloat16)
 x_lo = (torch.randn(B, T, C, device="cuda") * 1e-3).half() if (prec and not nolo) else None
 res_lo = torch.empty_like(x) if prec else None
-if prec:
-    variant |= xflags << 2
+variant |= xflags << 2
 res = torch.empty_like(x)
 skips = torch.zeros(B, T, C, device="cuda")
 dbg = torch.zeros(8 * 16, dtype=torch.int64, device="cuda")

@@ -164,3 +164,27 @@ def test_ctypes_signatures_match_the_header_prototypes():
         assert kinds == bound, (name, kinds, bound)
         seen += 1
     assert seen == len(_lib.SIGNATURES)
+
+
+def test_integration_doc_structs_match_the_binding():
+    """INTEGRATION.md shows the ctypes structs a maintainer of another binding would mirror.  Round 1's copy had fallen
+    behind the header (a missing trailing pointer): execute the documented class statements and compare them with
+    `_lib.py` (itself checked against the header above), field by field."""
+    import ctypes
+    import re
+    from wavenet_speech_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = text[text.index("```python\nimport ctypes, torch"):]
+    block = block[len("```python\n"):block.index("\n```")]
+    classes = re.findall(r"(class (wnb200_\w+_t)\(ctypes\.Structure\):.*?\n    _fields_ = \[.*?\]\n)\n", block, flags=re.S)
+    assert {n for _, n in classes} == {"wnb200_pack_block_t", "wnb200_resblock_t"}
+    ns = {"ctypes": ctypes, "vp": ctypes.c_void_p, "i32": ctypes.c_int32}
+    for src, _name in classes:
+        exec(src, ns)
+    for name, mirror in (("wnb200_pack_block_t", _lib.PackBlock), ("wnb200_resblock_t", _lib.ResBlock)):
+        doc = ns[name]
+        assert [f[0] for f in doc._fields_] == [f[0] for f in mirror._fields_], name
+        assert ctypes.sizeof(doc) == ctypes.sizeof(mirror), name
+        for (n, t), (_n2, t2) in zip(doc._fields_, mirror._fields_):
+            assert ctypes.sizeof(t) == ctypes.sizeof(t2), (name, n)

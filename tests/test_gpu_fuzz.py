@@ -184,6 +184,7 @@ def test_networks_random_configs(i, kind, C, layers, T, B, softmax, aux, causal)
     ref = ref_fn({k: r16(v) for k, v in net.state_dict().items()})
     net = net.cuda().bfloat16().eval()
     with torch.no_grad():
+        net(x.cuda().bfloat16())                     # first call packs the weights (one pack launch per block, cached)
         before = W._lib.launch_count
         y = net(x.cuda().bfloat16())
     # the tensor-core pipeline ran (one fused launch per block), not the generic kernels (three per block)

@@ -355,11 +355,13 @@ def test_gradients_do_not_alias_between_parameters():
         ptrs[p.grad.data_ptr()] = n
     g1 = {n: p.grad.detach().clone() for n, p in named}
     backward_once()                                                  # accumulates into the existing .grad tensors
+    # (the time-split weight-gradient partials meet by fp32 reduce-add in an order that varies from run to run: compare in
+    # norm, not element by element)
     for n, p in named:
-        assert torch.allclose(p.grad, 2 * g1[n], rtol=1e-5, atol=1e-6), n
+        assert G.rel_l2(p.grad.cpu(), 2 * g1[n].cpu()) <= 1e-4, (n, G.rel_l2(p.grad.cpu(), 2 * g1[n].cpu()))
     net.zero_grad(set_to_none=False)
     backward_once()
     total = torch.sqrt(sum((g.double() ** 2).sum() for g in g1.values()))
     torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=float(total) / 4)
     for n, p in named:
-        assert torch.allclose(p.grad, g1[n] / 4, rtol=1e-4, atol=1e-7), n
+        assert G.rel_l2(p.grad.cpu(), g1[n].cpu() / 4) <= 1e-4, (n, G.rel_l2(p.grad.cpu(), g1[n].cpu() / 4))

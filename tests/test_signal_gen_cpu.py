@@ -34,3 +34,26 @@ def test_mu_law_one_hot():
     assert np.array_equal(oh.argmax(1), lev)
     sig, labels = S.raw_signal(300, np.random.default_rng(2), with_labels=True)
     assert sig.shape == (300,) and labels.min() >= 1 and labels.max() <= 4 and 40 < len(labels) < 200
+
+
+def test_generator_reproduces_the_reference_on_recorded_draws():
+    """Pin (missing 7): oracle/gen_golden_siggen.py ran the reference's OWN generator code
+    (utils/raw_signal_generator.py:91-118,189-203 and the quantiser of utils/gaussian_kmer_model.py:78-96) on seeded
+    draws and recorded draws + outputs.  The restatement must give the same k-mers, the same picoamp samples and the same
+    mu-law levels; csrc/siggen.cu is held to the restatement on its own draws (tests/test_gpu_siggen.py)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "siggen_reference.npz"))
+    for c in range(3):
+        g = {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith("c%d/" % c)}
+        assert np.array_equal(S.kmer_indices(g["bases"]), g["kmers"])
+        sig = S.signal_from_draws(g["bases"], g["reps"], g["z"])
+        assert sig.shape == g["sig"].shape and np.array_equal(sig, g["sig"])            # bit for bit (float64)
+        # the duration law: max(1, int(gamma * 800)) -- the recorded reps come from the reference's random_upsample
+        assert g["reps"].min() >= 1
+        if "levels" in g:
+            ref_lev = g["levels"]
+            got = S.mu_law_levels(g["sig"], 256)
+            # np.digitize gives 1..256 on linspace(-1, 1, 256); the reference indexes a 256-row one-hot array with it, so
+            # a sample that maps to exactly +1 would fail there -- the restatement clips; everything else is identical
+            assert np.array_equal(got, np.clip(ref_lev, 0, 255))
+            assert np.array_equal(g["onehot_argmax"], ref_lev)

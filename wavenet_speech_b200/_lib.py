@@ -66,6 +66,21 @@ class Dense(_Sized):
                 ("act_fmt", ctypes.c_int32), ("reserved0", ctypes.c_int32), ("y_lo", c_void_p)]
 
 
+class PackBlock(_Sized):
+    """Mirror of wnb200_pack_block_t."""
+    _fields_ = [("struct_size", ctypes.c_uint32), ("C", ctypes.c_int32), ("k", ctypes.c_int32),
+                ("act_fmt", ctypes.c_int32), ("w_dtype", ctypes.c_int32), ("row_order", ctypes.c_int32)] + \
+               [(n, c_void_p) for n in ("wt", "bt", "ws", "bs", "wres", "bres", "wskip", "bskip", "wproj", "bproj",
+                                        "wbn", "bbn", "w1", "b1", "w2", "b2", "wdg", "wdg_skip", "wdx", "wdx_taps")]
+
+
+class PackHead(_Sized):
+    """Mirror of wnb200_pack_head_t."""
+    _fields_ = [("struct_size", ctypes.c_uint32), ("C", ctypes.c_int32), ("n_out", ctypes.c_int32),
+                ("act_fmt", ctypes.c_int32), ("w_dtype", ctypes.c_int32), ("reserved0", ctypes.c_int32)] + \
+               [(n, c_void_p) for n in ("w1", "b1", "w3", "b3", "pw1", "pb1", "pw2", "pb2", "w3t", "w1t")]
+
+
 # name -> argtypes (return type is int unless listed in _RESTYPES)
 SIGNATURES = {
     "wnb200_last_error": [],
@@ -97,6 +112,11 @@ SIGNATURES = {
     "wnb200_chain_fwd_tc": [ctypes.POINTER(Chain), c_void_p],
     "wnb200_resblock_fwd_tc": [ctypes.POINTER(ResBlock), c_void_p],
     "wnb200_dense_fwd_tc": [ctypes.POINTER(Dense), c_void_p],
+    "wnb200_pack_block": [ctypes.POINTER(PackBlock), c_void_p],
+    "wnb200_pack_head": [ctypes.POINTER(PackHead), c_void_p],
+    "wnb200_fold_grads": [c_int, c_int, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
+                          ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_workspace_bytes": [c_int, c_int, c_int, c_int],
     "wnb200_featurize_nlc": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
     "wnb200_avgpool_ncl_to_nlc": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p],
     "wnb200_avgpool_bwd_nlc_to_ncl": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
@@ -128,7 +148,8 @@ SIGNATURES = {
     "wnb200_ncl_to_nlc_act": [c_int, c_int, c_int, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p],
     "wnb200_nlc_to_ncl": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
 }
-_RESTYPES = {"wnb200_last_error": ctypes.c_char_p, "wnb200_ctc_workspace_bytes": ctypes.c_size_t}
+_RESTYPES = {"wnb200_last_error": ctypes.c_char_p, "wnb200_ctc_workspace_bytes": ctypes.c_size_t,
+             "wnb200_workspace_bytes": ctypes.c_size_t}
 
 _lib = None
 
@@ -162,7 +183,8 @@ def load():
 
 # kernel launches issued per C-ABI call (for bench.py's `gpu_launches` claim)
 _LAUNCHES_PER_CALL = {"wnb200_sum_f32": 2, "wnb200_last_error": 0, "wnb200_version": 0, "wnb200_check_device": 0,
-                      "wnb200_tc_pack_bytes": 0, "wnb200_ctc_workspace_bytes": 0, "wnb200_ctc_fwd": 2}
+                      "wnb200_tc_pack_bytes": 0, "wnb200_ctc_workspace_bytes": 0, "wnb200_ctc_fwd": 2,
+                      "wnb200_workspace_bytes": 0}
 launch_count = 0
 _event_log = None     # list of (name, start_event, end_event) while kernel timing is on
 current_tag = None    # optional label (e.g. "resblock") attached to timed calls by the caller

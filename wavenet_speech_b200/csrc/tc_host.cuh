@@ -40,12 +40,12 @@ static inline int rb_map_2d(CUtensorMap* m, const void* ptr, int rows, int cols,
 }
 
 // NLC tensor [B][T][C] of `esize`-byte elements -> boxes [1][128 frames][128 bytes], 128B swizzle
-static inline int rb_map_nlc(CUtensorMap* m, const void* ptr, int B, int T, int C, int esize) {
+static inline int rb_map_nlc(CUtensorMap* m, const void* ptr, int B, int T, int C, int esize, int box_rows = RB_TILE) {
   EncodeTiledFn enc = rb_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return 5; }
   cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)C * esize, (cuuint64_t)T * C * esize};
-  cuuint32_t box[3] = {(cuuint32_t)(128 / esize), RB_TILE, 1};
+  cuuint32_t box[3] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = enc(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                    const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -73,51 +73,89 @@ def _taps_matrix(w):
     return w.detach().float().permute(0, 2, 1).reshape(M, k * C)
 
 
-def pack_block(block, bottleneck, precise=False):
-    """-> dict(w1, b1, w2, b2, offsets) for one ResidualBlock + its skip bottleneck.
-    precise: fp16 weight matrices and the gate biases pre-scaled for the ex2-based gate (wnb200.h, WNB200_ACT_F16X2)."""
+def _sources(tensors):
+    """The parameter tensors as the pack kernels read them: on the GPU, contiguous, ONE dtype (fp32 master weights or
+    bf16; anything mixed is promoted to fp32)."""
+    dt = tensors[0].dtype
+    if dt not in (torch.float32, torch.bfloat16) or any(t.dtype != dt for t in tensors):
+        dt = torch.float32
+    out = []
+    for t in tensors:
+        t = t.detach()
+        if not t.is_cuda:
+            t = t.cuda()
+        out.append(t.to(dt).contiguous())
+    return out, ops._DT[dt]
+
+
+def pack_block(block, bottleneck, precise=False, bwd=False, natural=True):
+    """-> dict(w1, b1, w2, b2, offsets, ...) for one ResidualBlock + its skip bottleneck: ONE launch of
+    `wnb200_pack_block` (the layouts are documented in wnb200.h), fold product Wbn * Wskip included.
+    precise: fp16 weight matrices and gate biases pre-scaled for the ex2-based gate (WNB200_ACT_F16X2).
+    bwd: also the transposed bf16 matrices of the two data-gradient contractions (training).
+    natural: for C in {128, 256} also the [tanh ; sigmoid] row order of the generic chain kernel (keys w1 / b1) next to
+    the pipelined kernels' order (w1h / b1h); the training step, which re-packs after every optimiser step, skips it."""
     C = block.out_channels
     wt, ws = block.conv_tanh.conv1d, block.conv_sigmoid.conv1d
-    w1 = torch.cat([_taps_matrix(wt.weight), _taps_matrix(ws.weight)], 0)
-    b1 = torch.cat([wt.bias.detach().float(), ws.bias.detach().float()], 0)
-    wres = block.conv1x1_residual.weight.detach().float()[:, :, 0]
-    wskip = block.conv1x1_skip.weight.detach().float()[:, :, 0]
-    wproj = block.residual_proj.weight.detach().float()
-    wbn = bottleneck.weight.detach().float()[:, :, 0]
-    fold = wbn @ wskip
-    w2 = torch.cat([torch.cat([wres, wproj], 1), torch.cat([fold, torch.zeros_like(fold)], 1)], 0)
-    b2 = torch.cat([block.conv1x1_residual.bias.detach().float() + block.residual_proj.bias.detach().float(),
-                    wbn @ block.conv1x1_skip.bias.detach().float() + bottleneck.bias.detach().float()], 0)
-    cast = _f16 if precise else _bf16
-    pk = {"w1": cast(w1), "b1": b1.contiguous(), "w2": cast(w2), "b2": b2.contiguous(),
-          "offsets": list(block.offsets), "C": C, "fmt": _lib.ACT_F16X2 if precise else _lib.ACT_BF16}
-    if C in (128, 256):
-        # pipelined kernel: rows per half = [tanh C/2 ; sigmoid C/2]
-        hc = C // 2
-        order = torch.cat([torch.arange(0, hc), torch.arange(C, C + hc), torch.arange(hc, C),
-                           torch.arange(C + hc, 2 * C)]).to(w1.device)
-        pk["w1h"] = cast(w1[order])
-        if precise:     # gate = (1 - 2^ua) / ((1 + 2^ua)(1 + 2^ub)), ua = -2 log2(e) (a + bt), ub = -log2(e) (g + bs)
-            scale = torch.cat([torch.full((C,), -2.0 * _LOG2E), torch.full((C,), -_LOG2E)]).to(b1.device)
-            pk["b1h"] = (b1 * scale)[order].contiguous()
-        else:
-            pk["b1h"] = b1[order].contiguous()
+    k = wt.weight.shape[2]
+    src, wdt = _sources([wt.weight, wt.bias, ws.weight, ws.bias, block.conv1x1_residual.weight,
+                         block.conv1x1_residual.bias, block.conv1x1_skip.weight, block.conv1x1_skip.bias,
+                         block.residual_proj.weight, block.residual_proj.bias, bottleneck.weight, bottleneck.bias])
+    dev = src[0].device
+    wdtype = torch.float16 if precise else torch.bfloat16
+    fmt = _lib.ACT_F16X2 if precise else _lib.ACT_BF16
+    pk = {"offsets": list(block.offsets), "C": C, "fmt": fmt, "k": k}
+    with torch.cuda.device(dev):
+        orders = [(0, ("w1", "b1"))] if (natural and not precise) or C not in (128, 256) else []
+        if C in (128, 256):
+            orders.append((1, ("w1h", "b1h")))
+        for order, names in orders:
+            a = _lib.PackBlock()
+            a.C, a.k, a.act_fmt, a.w_dtype, a.row_order = C, k, fmt, wdt, order
+            for name, t in zip(("wt", "bt", "ws", "bs", "wres", "bres", "wskip", "bskip", "wproj", "bproj", "wbn", "bbn"),
+                               src):
+                setattr(a, name, t.data_ptr())
+            w1 = torch.empty((2 * C, k * C), dtype=wdtype, device=dev)
+            b1 = torch.empty(2 * C, dtype=torch.float32, device=dev)
+            w2 = torch.empty((2 * C, 2 * C), dtype=wdtype, device=dev)
+            b2 = torch.empty(2 * C, dtype=torch.float32, device=dev)
+            a.w1, a.b1, a.w2, a.b2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
+            if bwd and "wdg" not in pk:
+                bf = torch.bfloat16
+                pk["wdg"] = torch.empty((C, 2 * C), dtype=bf, device=dev)
+                pk["wdg_skip"] = torch.empty((C, C), dtype=bf, device=dev)
+                pk["wdx"] = torch.empty((C, k * 2 * C + C), dtype=bf, device=dev)
+                pk["wdx_taps"] = torch.empty((C, k * 2 * C), dtype=bf, device=dev)
+                a.wdg, a.wdg_skip, a.wdx, a.wdx_taps = (pk[n].data_ptr() for n in ("wdg", "wdg_skip", "wdx", "wdx_taps"))
+            _lib.call("wnb200_pack_block", ctypes.byref(a), ops._stream())
+            pk[names[0]], pk[names[1]], pk["w2"], pk["b2"] = w1, b1, w2, b2
+    pk["_src"] = src            # the launches above read these asynchronously: keep them alive with the pack
     return pk
 
 
-def pack_head(head, C, precise=False):
-    """LeakyReLU -> 1x1 -> LeakyReLU -> 1x1: the first LeakyReLU is applied by the producer of the skip sum."""
-    _bf16 = _f16 if precise else globals()["_bf16"]
-    w1 = head[1].weight.detach().float()[:, :, 0]
-    w3 = head[3].weight.detach().float()[:, :, 0]
-    n_out = w3.shape[0]
-    n2 = _pad16(n_out)
-    w2 = torch.zeros(n2, C, device=w3.device)
-    w2[:n_out] = w3
-    b2 = torch.zeros(n2, device=w3.device)
-    b2[:n_out] = head[3].bias.detach().float()
-    return {"w1": _bf16(w1), "b1": head[1].bias.detach().float().contiguous(), "w2": _bf16(w2), "b2": b2,
-            "n_out": n_out, "n2": n2, "fmt": _lib.ACT_F16X2 if precise else _lib.ACT_BF16}
+def pack_head(head, C, precise=False, bwd=False):
+    """LeakyReLU -> 1x1 -> LeakyReLU -> 1x1: the first LeakyReLU is applied by the producer of the skip sum.  One launch
+    of `wnb200_pack_head`; bwd adds the transposed bf16 matrices of the head's data gradients."""
+    src, wdt = _sources([head[1].weight, head[1].bias, head[3].weight, head[3].bias])
+    dev = src[0].device
+    n_out = head[3].weight.shape[0]
+    n2, npad = _pad16(n_out), (n_out + 63) // 64 * 64
+    wdtype = torch.float16 if precise else torch.bfloat16
+    fmt = _lib.ACT_F16X2 if precise else _lib.ACT_BF16
+    pk = {"w1": torch.empty((C, C), dtype=wdtype, device=dev), "b1": torch.empty(C, dtype=torch.float32, device=dev),
+          "w2": torch.empty((n2, C), dtype=wdtype, device=dev), "b2": torch.empty(n2, dtype=torch.float32, device=dev),
+          "n_out": n_out, "n2": n2, "fmt": fmt, "npad": npad, "_src": src}
+    a = _lib.PackHead()
+    a.C, a.n_out, a.act_fmt, a.w_dtype = C, n_out, fmt, wdt
+    a.w1, a.b1, a.w3, a.b3 = (t.data_ptr() for t in src)
+    a.pw1, a.pb1, a.pw2, a.pb2 = (pk[n].data_ptr() for n in ("w1", "b1", "w2", "b2"))
+    if bwd:
+        pk["w3t"] = torch.empty((C, npad), dtype=torch.bfloat16, device=dev)
+        pk["w1t"] = torch.empty((C, C), dtype=torch.bfloat16, device=dev)
+        a.w3t, a.w1t = pk["w3t"].data_ptr(), pk["w1t"].data_ptr()
+    with torch.cuda.device(dev):
+        _lib.call("wnb200_pack_head", ctypes.byref(a), ops._stream())
+    return pk
 
 
 def _version_key(module):

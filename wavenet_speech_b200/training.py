@@ -15,6 +15,8 @@ Everything is NLC bf16 between kernels, fp32 accumulation in TMEM, fp32 paramete
 
 `dskips` (gradient of the running skip sum) is the same tensor for every layer.
 """
+import ctypes
+
 import torch
 
 from . import _lib, fastpath as FP, ops
@@ -66,28 +68,6 @@ class zero_pool(object):
         _ZeroPool.current = self.prev
 
 
-def pack_block_bwd(block, bottleneck):
-    """K-major bf16 matrices of the two data-gradient contractions of one block."""
-    C = block.out_channels
-    wt = block.conv_tanh.conv1d.weight.detach().float()         # [C, C, k]
-    ws = block.conv_sigmoid.conv1d.weight.detach().float()
-    k = wt.shape[2]
-    wres = block.conv1x1_residual.weight.detach().float()[:, :, 0]
-    wskip = block.conv1x1_skip.weight.detach().float()[:, :, 0]
-    wproj = block.residual_proj.weight.detach().float()
-    wbn = bottleneck.weight.detach().float()[:, :, 0]
-    fold = wbn @ wskip
-    # dgate[n] = sum_m Wres[m, n] dres[m] + sum_m fold[m, n] dskips[m]
-    wdg = torch.cat([wres.t(), fold.t()], 1)                     # [C, 2C]
-    # dx[n] = sum_j sum_m Wt[m, n, j] da[m](t - off_j) + Ws[m, n, j] ds[m](t - off_j)  +  sum_m Wproj[m, n] dres[m]
-    cols = []
-    for j in range(k):
-        cols += [wt[:, :, j].t(), ws[:, :, j].t()]
-    wdx_taps = torch.cat(cols, 1)                                # [C, k * 2C]
-    return {"wdg": FP._bf16(wdg), "wdg_skip": FP._bf16(fold.t()), "wdx": FP._bf16(torch.cat([wdx_taps, wproj.t()], 1)),
-            "wdx_taps": FP._bf16(wdx_taps), "k": k, "C": C}
-
-
 def colsum(x_nlc, out=None):
     """fp32 column sums of an NLC bf16 tensor [B, T, C] (accumulates into `out`)."""
     B, T, C = x_nlc.shape
@@ -131,71 +111,14 @@ def wgrad_rows(g, x, off, rows, N):
     return wgrad_multi(g, rows, [(x, off)])[0]
 
 
-def _stk(ts, f=lambda t: t):
-    return torch.stack([f(t.detach().float()) for t in ts])
-
-
-def pack_stack(blocks, necks):
-    """Forward and backward weight packs of a whole stack in a few batched tensor ops (the packs are rebuilt after
-    every optimiser step: per-layer packing was ~60 small launches per layer).  All blocks must share (C, k).
-    Returns (fwd, bwd): per-layer dicts of views into the batched tensors, same keys as FP.pack_block /
-    pack_block_bwd."""
-    L = len(blocks)
-    C = blocks[0].out_channels
-    wt = _stk([b.conv_tanh.conv1d.weight for b in blocks])                      # [L, C, C, k]
-    ws = _stk([b.conv_sigmoid.conv1d.weight for b in blocks])
-    k = wt.shape[3]
-    bt = _stk([b.conv_tanh.conv1d.bias for b in blocks])
-    bs = _stk([b.conv_sigmoid.conv1d.bias for b in blocks])
-    wres = _stk([b.conv1x1_residual.weight for b in blocks])[:, :, :, 0]
-    wskip = _stk([b.conv1x1_skip.weight for b in blocks])[:, :, :, 0]
-    wproj = _stk([b.residual_proj.weight for b in blocks])
-    wbn = _stk([n.weight for n in necks])[:, :, :, 0]
-    bres = _stk([b.conv1x1_residual.bias for b in blocks])
-    bproj = _stk([b.residual_proj.bias for b in blocks])
-    bskip = _stk([b.conv1x1_skip.bias for b in blocks])
-    bbn = _stk([n.bias for n in necks])
-    tm = lambda w: w.permute(0, 1, 3, 2).reshape(L, C, k * C)                     # tap-major columns
-    w1 = torch.cat([tm(wt), tm(ws)], 1)                                           # [L, 2C, kC]
-    b1 = torch.cat([bt, bs], 1)
-    hc = C // 2
-    order = torch.cat([torch.arange(0, hc), torch.arange(C, C + hc), torch.arange(hc, C),
-                       torch.arange(C + hc, 2 * C)]).to(w1.device)
-    fold = torch.bmm(wbn, wskip)
-    w2 = torch.cat([torch.cat([wres, wproj], 2), torch.cat([fold, torch.zeros_like(fold)], 2)], 1)
-    b2 = torch.cat([bres + bproj, torch.bmm(wbn, bskip.unsqueeze(2))[:, :, 0] + bbn], 1)
-    w1h, b1h, w2b = w1[:, order].to(torch.bfloat16).contiguous(), b1[:, order].contiguous(), w2.to(torch.bfloat16)
-    b2 = b2.contiguous()
-    # backward: dgate = [Wres^T | fold^T] [dres ; dskips];  dx = sum_j [Wt_j^T | Ws_j^T] dab(t - off_j) + Wproj^T dres
-    wdg = torch.cat([wres.transpose(1, 2), fold.transpose(1, 2)], 2).to(torch.bfloat16).contiguous()
-    wdg_skip = fold.transpose(1, 2).to(torch.bfloat16).contiguous()
-    cols = []
-    for j in range(k):
-        cols += [wt[:, :, :, j].transpose(1, 2), ws[:, :, :, j].transpose(1, 2)]
-    wdx_taps = torch.cat(cols, 2)
-    wdx = torch.cat([wdx_taps, wproj.transpose(1, 2)], 2).to(torch.bfloat16).contiguous()
-    wdx_taps = wdx_taps.to(torch.bfloat16).contiguous()
-    fwd = [{"w1h": w1h[l], "b1h": b1h[l], "w2": w2b[l], "b2": b2[l], "offsets": list(blocks[l].offsets), "C": C}
-           for l in range(L)]
-    bwd = [{"wdg": wdg[l], "wdg_skip": wdg_skip[l], "wdx": wdx[l], "wdx_taps": wdx_taps[l], "k": k, "C": C}
-           for l in range(L)]
-    return fwd, bwd
-
-
 class Stack(object):
-    """The blocks + bottlenecks of one network with their forward / backward weight packs."""
+    """The blocks + bottlenecks of one network with their forward / backward weight packs: one `wnb200_pack_block`
+    launch per layer (pipelined row order + the transposed matrices of the data gradients; fold product on the device)."""
 
     def __init__(self, blocks, bottlenecks):
         self.blocks, self.necks = list(blocks), list(bottlenecks)
-        L = len(self.blocks)
-        self.fwd, self.bwd = [None] * L, [None] * L
-        groups = {}
-        for l, b in enumerate(self.blocks):                    # blocks of equal kernel width are packed together
-            groups.setdefault(b.kernel_width, []).append(l)
-        for idx in groups.values():
-            f, g = pack_stack([self.blocks[l] for l in idx], [self.necks[l] for l in idx])
-            for q, l in enumerate(idx):
-                self.fwd[l], self.bwd[l] = f[q], g[q]
+        self.fwd = [FP.pack_block(b, n, precise=False, bwd=True, natural=False) for b, n in zip(self.blocks, self.necks)]
+        self.bwd = self.fwd                   # same dicts: wdg / wdg_skip / wdx / wdx_taps / k / C live next to w1h ...
 
     def params(self):
         """Per layer, in this order: wt, bt, ws, bs, wres, bres, wskip, bskip, wproj, bproj, wbn, bbn."""
@@ -242,7 +165,7 @@ def stack_backward(stack, saved, dskips, need_dx0):
     L = len(saved)
     csk_rows = csk.unsqueeze(0).repeat(L, 1)                # ... but every layer's parameter gets its own memory
     grads = [None] * L
-    Ms = [None] * L
+    M_all = _zeros(L * C * C, dev).view(L, C, C)            # M[l] = dskips (x) gate_l, the fold's weight-space gradient
     dres = dres_cs = None
     for l in range(L - 1, -1, -1):
         x, act, th, sg = saved[l]
@@ -270,18 +193,28 @@ def stack_backward(stack, saved, dskips, need_dx0):
             dwres, dwproj = wgrad_multi(dres, C, [(act, 0), (x, 0)])
             dwres = dwres.unsqueeze(2)
             dbres = dres_cs
-        Ms[l] = wgrad_rows(dskips, act, 0, C, C)
+        if C == 256:
+            FP.wgrad2(dskips, [act], [0], 0, dw=M_all[l])      # written in place (one 256-row tile)
+        else:
+            M_all[l].copy_(wgrad_rows(dskips, act, 0, C, C))
         grads[l] = [dwt, dbab[:C], dws, dbab[C:], dwres, dbres, None, None, dwproj, dbres, None, csk_rows[l]]
         saved[l] = None                                     # free this layer's activations
         dres, dres_cs = dx, dx_cs
-    # weight-space algebra of the folded skip -> bottleneck product, batched over layers
-    M = torch.stack(Ms)                                                               # [L, C, C]
-    wbn = torch.stack([n.weight.detach().float()[:, :, 0] for n in stack.necks])
-    wskip = torch.stack([b.conv1x1_skip.weight.detach().float()[:, :, 0] for b in stack.blocks])
-    bskip = torch.stack([b.conv1x1_skip.bias.detach().float() for b in stack.blocks])
-    dwskip = torch.bmm(wbn.transpose(1, 2), M)
-    dwbn = torch.bmm(M, wskip.transpose(1, 2)) + csk.view(1, C, 1) * bskip.view(L, 1, C)
-    dbskip = torch.matmul(wbn.transpose(1, 2), csk)
+    # weight-space algebra of the folded skip -> bottleneck product: dWskip = Wbn^T M, dWbn = M Wskip^T + csk (x) bskip,
+    # dbskip = Wbn^T csk -- every layer in ONE launch of wnb200_fold_grads (fp32; these were cuBLAS bmm calls in round 1)
+    wbn_p = [n.weight for n in stack.necks]
+    wsk_p = [b.conv1x1_skip.weight for b in stack.blocks]
+    bsk_p = [b.conv1x1_skip.bias for b in stack.blocks]
+    srcs, wdt = FP._sources(wbn_p + wsk_p + bsk_p)
+    dwskip = torch.empty((L, C, C), dtype=torch.float32, device=dev)
+    dwbn = torch.empty((L, C, C), dtype=torch.float32, device=dev)
+    dbskip = torch.empty((L, C), dtype=torch.float32, device=dev)
+    for l0 in range(0, L, 64):
+        n = min(64, L - l0)
+        sl = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts[l0:l0 + n]])
+        _lib.call("wnb200_fold_grads", wdt, n, C, sl(srcs[0:L]), sl(srcs[L:2 * L]), sl(srcs[2 * L:3 * L]),
+                  ops._p(M_all[l0:]), ops._p(csk), ops._p(dwskip[l0:]), ops._p(dwbn[l0:]), ops._p(dbskip[l0:]),
+                  ops._stream())
     for l in range(L):
         grads[l][6], grads[l][7], grads[l][10] = dwskip[l].unsqueeze(2), dbskip[l], dwbn[l].unsqueeze(2)
     return dres, grads, dres_cs
@@ -296,16 +229,6 @@ def head_forward(skips, hd, out_dtype, softmax, skips_act=None):
     out = torch.empty((B, hd["n_out"], T), dtype=out_dtype, device=skips.device)
     FP.dense(h1, [0], hd["w2"], hd["b2"], hd["n2"], mode=1, out=out, n_out=hd["n_out"], softmax=softmax)
     return out, skips_act, h1
-
-
-def pack_head_bwd(head, C):
-    w1 = head[1].weight.detach().float()[:, :, 0]
-    w3 = head[3].weight.detach().float()[:, :, 0]               # [n_out, C]
-    n_out = w3.shape[0]
-    npad = (n_out + 63) // 64 * 64
-    w3t = torch.zeros(C, npad, device=w3.device)
-    w3t[:, :n_out] = w3.t()
-    return {"w3t": FP._bf16(w3t), "w1t": FP._bf16(w1.t()), "npad": npad, "n_out": n_out}
 
 
 def head_backward(dout, out, softmax, hb, skips_act, h1):
@@ -360,7 +283,7 @@ def _wavenet_pack(model):
     return {"entry_w": FP._bf16(FP._taps_matrix(ec.weight)), "entry_b": ec.bias.detach().float().contiguous(),
             "entry_wt": FP._bf16(torch.cat([w[:, :, j].t() for j in range(w.shape[2])], 1)),   # [in_dim, k*C]
             "stack": Stack(model.convolutions, model.bottlenecks),
-            "head": FP.pack_head(model.output_stack, C), "head_bwd": pack_head_bwd(model.output_stack, C)}
+            "head": FP.pack_head(model.output_stack, C, bwd=True)}
 
 
 def _wavenet_params(model, pk):
@@ -397,7 +320,7 @@ class _WaveNetTrain(torch.autograd.Function):
         model, pk, params = ctx.model, ctx.pk, ctx.params
         x, offs, saved, skips_act, h1, out = ctx.keep
         ctx.keep = None
-        dskips, ghead = head_backward(dout.contiguous(), out, model.softmax, pk["head_bwd"], skips_act, h1)
+        dskips, ghead = head_backward(dout.contiguous(), out, model.softmax, pk["head"], skips_act, h1)
         dh0, gl, dbe = stack_backward(pk["stack"], saved, dskips, True)
         C, in_dim = dh0.shape[2], x.shape[2]
         dwe = torch.stack(wgrad_multi(dh0, C, [(x, o) for o in offs]), 2)
@@ -427,7 +350,7 @@ def _classifier_pack(model):
     C = model.layers[0][0]
     return {"stack": Stack([model.input_block] + list(model.convolutions),
                            [model.input_skip_bottleneck] + list(model.bottlenecks)),
-            "head": FP.pack_head(model.output_block, C), "head_bwd": pack_head_bwd(model.output_block, C)}
+            "head": FP.pack_head(model.output_block, C, bwd=True)}
 
 
 class _ClassifierTrain(torch.autograd.Function):
@@ -460,7 +383,7 @@ class _ClassifierTrain(torch.autograd.Function):
         saved, skips_act, h1, out = ctx.keep
         ctx.keep = None
         need_dx = ctx.needs_input_grad[2]
-        dskips, ghead = head_backward(dout.contiguous(), out, model.softmax, pk["head_bwd"], skips_act, h1)
+        dskips, ghead = head_backward(dout.contiguous(), out, model.softmax, pk["head"], skips_act, h1)
         dh0, gl, _ = stack_backward(pk["stack"], saved, dskips, need_dx)
         dseq = None
         if need_dx:
@@ -495,7 +418,7 @@ def _raw_ctcnet_pack(model):
             "f2w": FP._bf16(w2), "f2b": f2.bias.detach().float().contiguous(), "f2wt": FP._bf16(w2.t()),
             "stack": Stack([model.input_block] + list(model.convolutions),
                            [model.input_skip_bottleneck] + list(model.bottlenecks)),
-            "head": FP.pack_head(model.output_block, C), "head_bwd": pack_head_bwd(model.output_block, C)}
+            "head": FP.pack_head(model.output_block, C, bwd=True)}
 
 
 class _RawCTCNetTrain(torch.autograd.Function):
@@ -534,7 +457,7 @@ class _RawCTCNetTrain(torch.autograd.Function):
         B, _, T = seq.shape
         dev = seq.device
         h0 = saved[0][0]
-        dskips, ghead = head_backward(dout.contiguous(), out, model.softmax, pk["head_bwd"], skips_act, h1)
+        dskips, ghead = head_backward(dout.contiguous(), out, model.softmax, pk["head"], skips_act, h1)
         dh0, gl, _ = stack_backward(pk["stack"], saved, dskips, True)
         dpre2 = leaky_bwd(dh0, h0)                                       # through the second LeakyReLU
         dw2 = wgrad_rows(dpre2, f, 0, F, F).unsqueeze(2)

@@ -32,6 +32,18 @@ def kmer_indices(bases):
     return win @ _KMER_W
 
 
+def signal_from_draws(bases, reps, z, T=None):
+    """The deterministic part of the generator: bases (1..4), samples per k-mer and standard-normal draws in, picoamp
+    samples out (float64) -- what utils/raw_signal_generator.py:101-118 computes once its random draws are fixed.
+    tests/golden/siggen_reference.npz holds the reference's own outputs for recorded draws."""
+    means, stdvs = load_pore_model()
+    seq = np.repeat(kmer_indices(bases), np.asarray(reps, dtype=np.int64))
+    if T is not None:
+        seq = seq[:T]
+    z = np.asarray(z, dtype=np.float64)[:len(seq)]
+    return means[seq].astype(np.float64) + stdvs[seq].astype(np.float64) * z
+
+
 def raw_signal(T, rng, with_labels=False):
     """One read of exactly T picoamp samples (float32).  Optionally also returns the bases (labels 1..4)
     whose k-mers were (at least partly) emitted."""
