@@ -54,6 +54,25 @@ def main():
     GG.save("classifier_c128_bf16w", m, {"x": x}, {"y": m(x)},
             {"in_dim": C, "num_labels": 5, "layers": layers, "out_dim": C, "pool_kernel_size": 3, "softmax": False})
 
+    # ---- reference-written GRADIENTS at a tensor-core shape: the reference's own modules and
+    # torch autograd, parameters and input bf16-representable, loss = sum(y * R) for a stored R.  The tensor-core
+    # training path is compared with these numbers directly -- an oracle nobody modified.
+    torch.manual_seed(1304)
+    glayers = [(C, C, 2, 1), (C, C, 2, 4)]
+    m = GG.WaveNet(C, 2, glayers, C, softmax=False)
+    GG.randomize_biases(m, 0.05)
+    _round_params_to_bf16(m)
+    lev = torch.randint(0, C, (2, 200))
+    x = (torch.zeros(2, C, 200).scatter_(1, lev.unsqueeze(1), 1.0) + 0.05 * torch.randn(2, C, 200)).bfloat16().float()
+    x.requires_grad_(True)
+    R = torch.randn(2, C, 200).bfloat16().float()
+    y = m(x)
+    (y * R).sum().backward()
+    grads = {"grad/" + n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
+    grads["grad/__input__"] = x.grad.detach().clone()
+    GG.save("wavenet_c128_bf16w_grads", m, {"x": x.detach(), "R": R}, dict({"y": y.detach()}, **grads),
+            {"in_dim": C, "entry_kwidth": 2, "layers": glayers, "out_dim": C, "softmax": False})
+
 
 if __name__ == "__main__":
     main()

@@ -15,8 +15,6 @@ ptok = [t for t in toks if t.startswith("p")]
 prec = bool(ptok)
 xflags = int(ptok[0][1:] or 0) if prec else 0
 nolo = "nolo" in toks
-if "old" in toks:
-    variant |= 16                                               # CTA-wide output epilogues
 for t in toks:
     if t.startswith("s"):
         variant |= int(t[1:]) << 8                              # stagger odd pairs by N x 1024 cycles

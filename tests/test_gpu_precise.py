@@ -215,30 +215,3 @@ def test_host_pipeline_back_to_back_submits():
         pipe.wait()
         for o, d in zip(outs, direct):
             assert torch.equal(o, d), chunks
-
-
-@pytest.mark.parametrize("precise", [False, True])
-@pytest.mark.parametrize("C,T,B,d", [(256, 700, 2, 4), (128, 130, 3, 1), (256, 97, 1, 2)])
-def test_lsu_stream_epilogue_equals_tma_store_epilogue(precise, C, T, B, d):
-    """The two implementations of the stream's output epilogue in the CTA-pair kernel (staged rows leaving through
-    coalesced st.global -- the default -- or through TMA stores, variant bit 4) write the same bits, also on tiles that
-    straddle T."""
-    torch.manual_seed(C + T)
-    blk = W.ResidualBlock(C, C, 2, d, causal=True)
-    bn = torch.nn.Conv1d(C, C, 1)
-    pk = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in FP.pack_block(blk, bn, precise=precise).items()}
-    dt = torch.float16 if precise else torch.bfloat16
-    x = torch.randn(B, T, C, device="cuda").to(dt)
-    x_lo = (torch.randn(B, T, C, device="cuda") * 1e-3).to(dt) if precise else None
-    prev = torch.randn(B, T, C, device="cuda")
-    outs = []
-    for variant in (2, 2 | 16):
-        res, res_lo = torch.full_like(x, 7.0), (torch.full_like(x, 7.0) if precise else None)
-        skips = prev.clone()
-        FP.resblock(x, pk, res, skips, False, variant=variant, x_lo=x_lo, res_lo=res_lo)
-        skips2 = torch.full_like(prev, 1e9)
-        FP.resblock(x, pk, None, skips2, True, variant=variant, x_lo=x_lo)
-        torch.cuda.synchronize()
-        outs.append((res, res_lo, skips, skips2))
-    for a, b in zip(outs[0], outs[1]):
-        assert (a is None and b is None) or torch.equal(a, b)

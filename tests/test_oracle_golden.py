@@ -128,3 +128,24 @@ def test_flop_model_matches_baseline_md():
     layers = [(256, 256, 2, d) for d in [1, 2, 4, 8, 16, 32, 64, 128, 256, 512] * 2]
     assert O.block_flops(256, 256, 2, 256) == 1048576
     assert O.wavenet_flops_per_timestep(256, 2, layers, 256) == 21495808
+
+
+def test_oracle_gradients_match_reference_written_gradients():
+    """tests/golden/wavenet_c128_bf16w_grads.npz holds gradients computed by the REFERENCE's modules + torch autograd
+    (oracle/gen_golden_tc.py).  Autograd through the oracle must reproduce them: this pins the backward half of the oracle
+    that the tensor-core training tests lean on."""
+    import torch
+    from oracle import wavenet_oracle as O
+    from tests import _golden as G
+    g = G.load("wavenet_c128_bf16w_grads")
+    layers = g["meta"]["layers"]
+    sd = {k: v.clone().requires_grad_(True) for k, v in g["sd"].items()}
+    x = g["inp"]["x"].clone().requires_grad_(True)
+    y = O.wavenet_forward(sd, x, layers, softmax=False)
+    assert G.rel_linf(y.detach(), g["out"]["y"]) <= 2e-6
+    (y * g["inp"]["R"]).sum().backward()
+    refs = {k[len("grad/"):]: v for k, v in g["out"].items() if k.startswith("grad/")}
+    assert G.rel_linf(x.grad, refs.pop("__input__")) <= 1e-5
+    assert len(refs) > 20
+    for n, ref in refs.items():
+        assert G.rel_linf(sd[n].grad, ref) <= 1e-5, n

@@ -40,9 +40,6 @@ struct ResDev {
   bf16* save_sg;
   int has_lo;       // PREC kernels: x_lo is present (the stream's fp16 low half joins the projection)
   int xflags;       // WNB200_TIMELINE builds only: experiment switches: 1 approx gate, 2 no lo store
-  int e2_lsu;       // CTA-pair inference kernels: the stream leaves through staged, coalesced st.global instead of TMA
-  void* res_ptr;    // ... which needs the raw output pointers
-  void* res_lo_ptr;
   int stagger;      // WNB200_TIMELINE builds only: odd CTA pairs start this many cycles late (L2 phase experiment)
 };
 
@@ -664,6 +661,17 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       const int t0 = (pt - b * p.tiles_per_seq) * (2 * RB_TILE) + (int)rank * RB_TILE;
 
       for (int half = 0; half < 2; ++half) {
+        // The biases come from L2 (the unified L1 is all shared memory here): ~400 cycles per load round if they are
+        // fetched where they are used (ncu, r2: 12 % of the epilogue warps' samples sat on the first FADD/FFMA after
+        // them).  Every epilogue phase therefore fetches the NEXT step's biases while it works on the current one, the
+        // first step's before it waits for its accumulator.
+        float4 nb_t[4], nb_s[4];
+        if constexpr (!SAVE) {
+          const float4* bt = reinterpret_cast<const float4*>(p.bias1 + half * C + h * (C / 4));
+          const float4* bs = reinterpret_cast<const float4*>(p.bias1 + half * C + C / 2 + h * (C / 4));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { nb_t[j] = __ldg(bt + j); nb_s[j] = __ldg(bs + j); }
+        }
         mbar_wait(half == 0 ? accA_full : accB_full, 0u);
         tc_fence_after();
         if (issuer && rank == 0) RB_STAMP(8 + half);
@@ -713,30 +721,25 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             }
           }
         } else {
-        // software-pipelined over the four 16-channel steps: the TMEM loads of step i+1 are in flight while step i's
-        // 32-48 MUFU operations issue (a step was ld -> wait -> math in sequence: ~1.2k cycles, 0.8k of them MUFU)
-        float a[16], g[16];
-        tmem_ld16(treg + h * (C / 4), a);
-        tmem_ld16(treg + C / 2 + h * (C / 4), g);
-#pragma unroll
+#pragma unroll 1
         for (int cc = 0; cc < C / 4; cc += 16) {
           const int col = h * (C / 4) + cc;
-          const float4* bt = reinterpret_cast<const float4*>(p.bias1 + half * C + col);
-          const float4* bs = reinterpret_cast<const float4*>(p.bias1 + half * C + C / 2 + col);
+          float ac[16], gc[16];
+          tmem_ld16(treg + col, ac);
+          tmem_ld16(treg + C / 2 + col, gc);
           float bta[16], bsa[16];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 u = __ldg(bt + j), v = __ldg(bs + j);
+            const float4 u = nb_t[j], v = nb_s[j];
             bta[4 * j] = u.x; bta[4 * j + 1] = u.y; bta[4 * j + 2] = u.z; bta[4 * j + 3] = u.w;
             bsa[4 * j] = v.x; bsa[4 * j + 1] = v.y; bsa[4 * j + 2] = v.z; bsa[4 * j + 3] = v.w;
           }
           tmem_wait_ld();
-          float ac[16], gc[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) { ac[i] = a[i]; gc[i] = g[i]; }
           if (cc + 16 < C / 4) {
-            tmem_ld16(treg + col + 16, a);
-            tmem_ld16(treg + C / 2 + col + 16, g);
+            const float4* bt = reinterpret_cast<const float4*>(p.bias1 + half * C + col + 16);
+            const float4* bs = reinterpret_cast<const float4*>(p.bias1 + half * C + C / 2 + col + 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { nb_t[j] = __ldg(bt + j); nb_s[j] = __ldg(bs + j); }
           }
           uint32_t pk[8];
 #ifdef WNB200_TIMELINE
@@ -782,106 +785,16 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 
       bool drain = SAVE;        // E1's stores still read the staging buffers: drain them before the first reuse
       // ---- E2a: res ----
+      float4 nbv[8];                                  // biases of the next chunk (see E1)
+      if (p.write_res) {
+        const float4* bp = reinterpret_cast<const float4*>(p.bias2 + h * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) nbv[j] = __ldg(bp + j);
+      }
       mbar_wait(accA_full, 1u);
       tc_fence_after();
       if (issuer && rank == 0) RB_STAMP(10);
-      bool e2a_done_here = false;
-      if constexpr (!SAVE) {
-        if (p.e2_lsu && !p.final_act) {
-          // The next tile's G1a cannot start before region A has been drained, so E2a sits on the critical path, and a
-          // TMA store of a staged chunk is SLOW to release its buffer: it queues in the CTA's TMA unit behind the
-          // producer's operand loads (up to four 32 KB stages), ~1.4k cycles from issue to `wait_group.read` -- 900
-          // cycles per 16 KB chunk with two buffers, 3.6k cycles for the bf16 stream and 7.1k for the fp16 (hi, lo) pair
-          // (timeline: profiles/r2_timeline_resblock2.txt).  Here the staged rows leave through the LSU instead: both
-          // 16 KB buffers per round (precise: hi | lo of 64 channels; bf16: 128 channels), two barriers, and a coalesced
-          // copy-out -- 8 consecutive threads move one 128-byte row segment, a warp four full lines.
-          if (p.write_res) {
-            constexpr int NR = PREC ? C / 64 : C / 128;
-            uint8_t* stg = smem_gen + (stg_base - smem_base);
-            const int t256 = (int)threadIdx.x - 64;
-            const int cp_piece = t256 & 7, cp_row0 = t256 >> 3;           // copy-out: rows cp_row0 + 32 i
-            uint8_t* g0 = reinterpret_cast<uint8_t*>(p.res_ptr);
-            uint8_t* g1 = PREC ? reinterpret_cast<uint8_t*>(p.res_lo_ptr) : g0;
-            const long long grow = ((long long)b * p.T + t0) * (C * 2);    // byte offset of the tile's first row
-#pragma unroll 1
-            for (int r = 0; r < NR; ++r) {
-              uint32_t w0[16], w1[16];          // this thread's 32 channels for buffer 0 / buffer 1
-              if constexpr (PREC) {
-                const int col = r * 64 + h * 32;
-                float a[32];
-                tmem_ld16(tmemA + lane_off + col, a);
-                tmem_ld16(tmemA + lane_off + col + 16, a + 16);
-                const float4* bp = reinterpret_cast<const float4*>(p.bias2 + col);
-                float bv[32];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 u = __ldg(bp + j);
-                  bv[4 * j] = u.x; bv[4 * j + 1] = u.y; bv[4 * j + 2] = u.z; bv[4 * j + 3] = u.w;
-                }
-                tmem_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) split_f16x2(a[i] + bv[i], a[i + 1] + bv[i + 1], w0[i >> 1], w1[i >> 1]);
-              } else {
-#pragma unroll
-                for (int blk = 0; blk < 2; ++blk) {
-                  const int col = r * 128 + blk * 64 + h * 32;
-                  float a[32];
-                  tmem_ld16(tmemA + lane_off + col, a);
-                  tmem_ld16(tmemA + lane_off + col + 16, a + 16);
-                  const float4* bp = reinterpret_cast<const float4*>(p.bias2 + col);
-                  float bv[32];
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    const float4 u = __ldg(bp + j);
-                    bv[4 * j] = u.x; bv[4 * j + 1] = u.y; bv[4 * j + 2] = u.z; bv[4 * j + 3] = u.w;
-                  }
-                  tmem_wait_ld();
-#pragma unroll
-                  for (int i = 0; i < 32; i += 2) {
-                    const uint32_t v = pack_bf16x2(a[i] + bv[i], a[i + 1] + bv[i + 1]);
-                    if (blk == 0) w0[i >> 1] = v; else w1[i >> 1] = v;
-                  }
-                }
-              }
-              if (r == NR - 1) {               // region A has been read: the next tile's G1a may overwrite it
-                tc_fence_before();
-                mbar_arrive_cluster(r_e2a);
-                e2a_done_here = true;
-              }
-              if (r == 0 && issuer) bulk_wait_read0();     // the previous tile's skip chunks have left the buffers
-              epi_bar();                                   // ... and everybody is done with the previous copy-out
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int o = ((4 * h + j) ^ sw) << 4;
-                *reinterpret_cast<uint4*>(stg + row * 128 + o) = make_uint4(w0[4 * j], w0[4 * j + 1], w0[4 * j + 2], w0[4 * j + 3]);
-                *reinterpret_cast<uint4*>(stg + RB_ABYTES + row * 128 + o) =
-                    make_uint4(w1[4 * j], w1[4 * j + 1], w1[4 * j + 2], w1[4 * j + 3]);
-              }
-              epi_bar();
-              const int ch0 = PREC ? r * 64 : r * 128;     // channel of buffer 0's first column
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int rr = cp_row0 + 32 * i;
-                if (t0 + rr < p.T) {
-                  const int so = rr * 128 + ((cp_piece ^ (rr & 7)) << 4);
-                  const uint4 v0 = *reinterpret_cast<const uint4*>(stg + so);
-                  const uint4 v1 = *reinterpret_cast<const uint4*>(stg + RB_ABYTES + so);
-                  const long long go = grow + (long long)rr * (C * 2) + ch0 * 2 + cp_piece * 16;
-                  *reinterpret_cast<uint4*>(g0 + go) = v0;
-                  *reinterpret_cast<uint4*>(g1 + go + (PREC ? 0 : 128)) = v1;
-                }
-              }
-            }
-            drain = true;          // (no TMA group reads the buffers now, but E2b starts its own double buffering afresh)
-          }
-          if (!e2a_done_here) {
-            tc_fence_before();
-            mbar_arrive_cluster(r_e2a);
-            e2a_done_here = true;
-          }
-        }
-      }
-      if (!e2a_done_here) {
+      {
       if (p.write_res) {
 #pragma unroll 1
         for (int c = 0; c < C / 64; ++c, ++nchunk) {
@@ -889,12 +802,16 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           float a[32];
           tmem_ld16(tmemA + lane_off + col, a);
           tmem_ld16(tmemA + lane_off + col + 16, a + 16);
-          const float4* bp = reinterpret_cast<const float4*>(p.bias2 + col);
           float bv[32];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 u = __ldg(bp + j);
+            const float4 u = nbv[j];
             bv[4 * j] = u.x; bv[4 * j + 1] = u.y; bv[4 * j + 2] = u.z; bv[4 * j + 3] = u.w;
+          }
+          if (c + 1 < C / 64) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias2 + col + 64);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) nbv[j] = __ldg(bp + j);
           }
           tmem_wait_ld();
           uint32_t pk[16];
@@ -953,6 +870,12 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       }
 
       // ---- E2b: skips ----
+      float4 nb2[4];
+      if (!p.final_act) {
+        const float4* bp = reinterpret_cast<const float4*>(p.bias2 + C + h * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) nb2[j] = __ldg(bp + j);
+      }
       mbar_wait(accB_full, 1u);
       tc_fence_after();
       if (issuer && rank == 0) RB_STAMP(11);
@@ -1027,12 +950,16 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         const int col = c * 32 + h * 16;
         float a[16];
         tmem_ld16(tmemB + lane_off + col, a);
-        const float4* bp = reinterpret_cast<const float4*>(p.bias2 + C + col);
         float bv[16];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 u = __ldg(bp + j);
+          const float4 u = nb2[j];
           bv[4 * j] = u.x; bv[4 * j + 1] = u.y; bv[4 * j + 2] = u.z; bv[4 * j + 3] = u.w;
+        }
+        if (c + 1 < C / 32) {
+          const float4* bp = reinterpret_cast<const float4*>(p.bias2 + C + col + 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) nb2[j] = __ldg(bp + j);
         }
         tmem_wait_ld();
         const uint32_t boff = (nchunk & 1u) * RB_ABYTES;
@@ -1142,8 +1069,6 @@ extern "C" int wnb200_resblock_fwd_tc(const wnb200_resblock_t* a, void* stream) 
                 "resblock_fwd_tc: saving the gate factors needs all three buffers and the CTA-pair kernel");
   const bool pair = (a->variant & 3) != 1;     // 0 / 2: CTA-pair kernel (default); 1: single-CTA kernel
   p.xflags = (a->variant >> 2) & 3;
-  p.e2_lsu = (a->variant & 16) ? 0 : 1;        // bit 4: keep the TMA-store epilogue for the stream (A/B runs)
-  p.res_ptr = a->res; p.res_lo_ptr = a->res_lo;
   p.stagger = (a->variant >> 8) * 1024;
   const bool prec = a->act_fmt == WNB200_ACT_F16X2;
   WNB_CHECK_ARG(a->act_fmt == WNB200_ACT_BF16 || prec, "resblock_fwd_tc: bad act_fmt %d", a->act_fmt);
@@ -1157,7 +1082,6 @@ extern "C" int wnb200_resblock_fwd_tc(const wnb200_resblock_t* a, void* stream) 
   if ((rc = rb_map_nlc(&mx, a->x, a->B, a->T, C, 2))) return rc;
   if ((rc = rb_map_2d(&mw1, a->w1, 2 * C, a->ntaps * C, wbox))) return rc;
   if ((rc = rb_map_2d(&mw2, a->w2, 2 * C, 2 * C, wbox))) return rc;
-  p.e2_lsu = p.e2_lsu && pair && !p.final_act && !a->save_act;
   if ((rc = rb_map_nlc(&mres, a->res ? a->res : a->x, a->B, a->T, C, 2))) return rc;
   if ((rc = rb_map_nlc(&msk, a->skips, a->B, a->T, C, 4))) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
