@@ -224,9 +224,9 @@ typedef struct {
   void* res;
   float* skips;
   void* dbg;              /* optional int64[8*16] timeline buffer */
-  void* save_act;         /* optional (training): gate, tanh(.) and sigmoid(.) as NLC bf16 [B,T,C] each */
-  void* save_th;
-  void* save_sg;
+  void* save_act;         /* optional (training): the gate tanh(.)*sigmoid(.), NLC bf16 [B,T,C] ...                 */
+  void* save_th;          /* ... optionally tanh(.) (NULL: not kept -- backward derives it as gate / sigmoid) ...      */
+  void* save_sg;          /* ... and sigmoid(.) (required with save_act)                                              */
   void* skips_act;        /* optional (last layer of an inference stack, res = NULL): NLC bf16 [B,T,C] that receives
                              LeakyReLU(skips + contribution) (wavenet.py:100-103); `skips` is then read, not updated */
   const void* x_lo;       /* F16X2: lo half of the input stream, NLC fp16 [B,T,C]; NULL = the input is exactly x */
@@ -358,6 +358,10 @@ int wnb200_wgrad2_tc(int B, int T, int Cg, int m0, int N, int nsrc, const int32_
  * biases' gradients). */
 int wnb200_gate_bwd_nlc(int64_t rows, int C, const void* dact, const void* th, const void* sg, void* dab, float* dbias,
                         void* stream);
+
+/* Same from what the training forward keeps (gate = tanh * sigmoid, and sigmoid): tanh = gate / sigmoid. */
+int wnb200_gate_bwd_nlc_from_gate(int64_t rows, int C, const void* dact, const void* gate, const void* sg, void* dab,
+                                  float* dbias, void* stream);
 
 /* out[c] += sum over rows of x[r, c]  (x NLC bf16 [rows, C]; bias gradients on the tensor-core training path). */
 int wnb200_colsum_nlc(int64_t rows, int C, const void* x, float* out, void* stream);

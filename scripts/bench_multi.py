@@ -164,5 +164,34 @@ if "longread" in which:
           "samples_per_s": T / (ms * 1e-3), "sharded_equals_full_bitwise": bool(int(ok)),
           "halo_bytes_per_boundary": 2 * (hl + hr), "scaling": "strong"})
 
+if "peercausal" in which and world > 1:
+    # one-directional halos (any causal network: halo_right = 0).  A rank only WRITES to its right neighbour
+    # and never waits on it, so without the explicit ack a fast writer could rewrite a parity slot two steps later while the
+    # reader still held step k.  Eight steps with a different read each, the reader artificially slowed on odd ranks; every
+    # step must equal the NCCL exchange bit for bit.
+    torch.manual_seed(0)
+    net = W.RawCTCNet(256, 3, 5, [(256, 256, 2, d) for d in (1, 2, 4, 8)], 256, softmax=False, causal=True)
+    net = net.cuda().bfloat16().eval()
+    T = 200000
+    hl, hr = S.raw_ctcnet_halo(net)
+    assert hr == 0 and hl > 0
+    plan = S.time_shard_plan(T, rank, world, hl, hr)
+    peer = S.PeerHaloExchange(1, 1, hl, hr, torch.bfloat16, rank, world)
+    ok = True
+    with torch.no_grad():
+        mines = [torch.from_numpy(SG.raw_batch(1, T, seed=100 + step)).bfloat16()[:, :, plan["start"]:plan["end"]]
+                 .contiguous().cuda() for step in range(8)]
+        got = []
+        for step in range(8):                              # nothing but the protocol's own signals orders the ranks here
+            if rank % 2 == 1:
+                torch.cuda._sleep(20_000_000)              # a slow reader: ~10 ms late into every step
+            got.append(peer.exchange(mines[step], plan).clone())
+        for step in range(8):
+            ok = ok and torch.equal(got[step], S.exchange_halo(mines[step], plan, rank, world))
+    flag = torch.tensor([int(ok)], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    emit({"config": "peer_halo_exchange_causal_one_directional_8_steps", "halo": [hl, hr],
+          "equals_nccl_exchange_bitwise_every_step": bool(int(flag))})
+
 if world > 1:
     dist.destroy_process_group()

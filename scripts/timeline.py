@@ -15,9 +15,6 @@ ptok = [t for t in toks if t.startswith("p")]
 prec = bool(ptok)
 xflags = int(ptok[0][1:] or 0) if prec else 0
 nolo = "nolo" in toks
-for t in toks:
-    if t.startswith("s"):
-        variant |= int(t[1:]) << 8                              # stagger odd pairs by N x 1024 cycles
 torch.manual_seed(0)
 blk = W.ResidualBlock(C, C, 2, d, causal=True)
 bn = torch.nn.Conv1d(C, C, 1)

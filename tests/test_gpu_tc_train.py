@@ -56,7 +56,7 @@ class _Stored(object):
 
 def _stored_stack(saved, skips_act, h1):
     ts = []
-    for l, (x, act, th, sg) in enumerate(saved):
+    for l, (x, act, sg) in enumerate(saved):
         ts += [act, saved[l + 1][0] if l + 1 < len(saved) else None]
     sa = skips_act.detach().float()
     skips = torch.where(sa > 0, sa, sa / 0.01)       # the (fp32) skip sum is not kept: undo the LeakyReLU
@@ -91,6 +91,16 @@ def test_colsum_and_gate_bwd_nlc(rows, C):
     ref = torch.cat([d * sg * (1 - th * th), d * th * sg * (1 - sg)], 2)
     assert G.rel_linf(dab.float().cpu(), ref) <= 1e-2
     assert G.rel_linf(dbias.cpu(), ref.sum((0, 1))) <= 1e-4
+    # what the training forward keeps since round 2: the gate and the sigmoid; tanh = gate / sigmoid in the kernel
+    gate = r16(th * sg)
+    dab2, dbias2 = TR.gate_bwd_nlc(d.cuda().bfloat16(), gate.cuda().bfloat16(), sg.cuda().bfloat16(), want_bias=True,
+                                   th_is_gate=True)
+    assert G.rel_linf(dab2.float().cpu(), ref) <= 2e-2
+    assert G.rel_l2(dab2.float().cpu(), ref) <= 1e-2
+    z = torch.zeros(1, 8, C)                                 # sigmoid underflowed to 0 (gate 0 too): no NaN, zero gradient
+    dz, _ = TR.gate_bwd_nlc(torch.ones(1, 8, C).cuda().bfloat16(), z.cuda().bfloat16(), z.cuda().bfloat16(),
+                            want_bias=True, th_is_gate=True)
+    assert torch.isfinite(dz.float()).all() and float(dz.float().abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("Cin,Cin2,N,k,k2,T,B", [(256, 256, 256, 1, 1, 300, 2), (512, 256, 256, 2, 1, 700, 2),
@@ -129,6 +139,12 @@ def test_block_saves_gate_factors(C, k, d, causal, T, B):
     torch.cuda.synchronize()
     for got, ref in zip(save, (th * sg, th, sg)):
         assert G.rel_linf(got.float().cpu().permute(0, 2, 1), ref) <= 1e-2
+    # tanh is optional: without it the same gate / sigmoid / res / skips come out (this is what training.py asks for)
+    act2, sg2 = torch.full_like(xn, 7.0), torch.full_like(xn, 7.0)
+    res2, skips2 = torch.empty_like(xn), torch.empty(B, T, C, device="cuda")
+    FP.resblock(xn, pk, res2, skips2, True, save=(act2, None, sg2))
+    torch.cuda.synchronize()
+    assert torch.equal(act2, save[0]) and torch.equal(sg2, save[2]) and torch.equal(res2, res) and torch.equal(skips2, skips)
 
 
 def _perturb_biases(net):

@@ -126,6 +126,7 @@ SIGNATURES = {
     "wnb200_wgrad2_tc": [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                          c_void_p],
     "wnb200_gate_bwd_nlc": [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_gate_bwd_nlc_from_gate": [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_colsum_nlc": [c_int64, c_int, c_void_p, c_void_p, c_void_p],
     "wnb200_ctc_workspace_bytes": [c_int, c_int, c_int, c_int],
     "wnb200_ctc_fwd": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,

@@ -339,7 +339,7 @@ __global__ void argmax_kernel(int B, int C, int Tn, const T* x, long long* out) 
 // dbias[0:C] += sum_rows da, dbias[C:2C] += sum_rows ds (fp32, one atomicAdd per channel per block; optional).
 __global__ void __launch_bounds__(256)
 gate_bwd_nlc_kernel(long long rows, int C, const uint4* dact, const uint4* th, const uint4* sg, uint4* dab,
-                    float* dbias) {
+                    float* dbias, bool th_is_gate) {
   const int g = C / 8, rpb = 256 / g;
   const int cg = threadIdx.x % g, rl = threadIdx.x / g;
   float sa[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, sb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -355,7 +355,12 @@ gate_bwd_nlc_kernel(long long rows, int C, const uint4* dact, const uint4* th, c
       __nv_bfloat162* bp = reinterpret_cast<__nv_bfloat162*>(&ob);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float2 d = __bfloat1622float2(dp[k]), t = __bfloat1622float2(tp[k]), s_ = __bfloat1622float2(sp[k]);
+        const float2 d = __bfloat1622float2(dp[k]), s_ = __bfloat1622float2(sp[k]);
+        float2 t = __bfloat1622float2(tp[k]);
+        if (th_is_gate) {            // the forward kept gate = tanh * sigmoid and sigmoid: tanh = gate / sigmoid (0 / 0 -> 0)
+          t.x = s_.x > 0.f ? fminf(1.f, fmaxf(-1.f, __fdividef(t.x, s_.x))) : 0.f;
+          t.y = s_.y > 0.f ? fminf(1.f, fmaxf(-1.f, __fdividef(t.y, s_.y))) : 0.f;
+        }
         const float a0 = d.x * s_.x * (1.f - t.x * t.x), a1 = d.y * s_.y * (1.f - t.y * t.y);
         const float b0 = d.x * t.x * s_.x * (1.f - s_.x), b1 = d.y * t.y * s_.y * (1.f - s_.y);
         ap[k] = __floats2bfloat162_rn(a0, a1);
@@ -746,8 +751,8 @@ extern "C" int wnb200_argmax_channels_col(int dtype, int B, int C, int T_, const
   return 0;
 }
 
-extern "C" int wnb200_gate_bwd_nlc(int64_t rows, int C, const void* dact, const void* th, const void* sg, void* dab,
-                                   float* dbias, void* stream) {
+static int gate_bwd_nlc_launch(int64_t rows, int C, const void* dact, const void* th, const void* sg, void* dab,
+                               float* dbias, bool th_is_gate, void* stream) {
   WNB_CHECK_ARG(C % 8 == 0 && C <= 2048, "gate_bwd_nlc: C=%d must be a multiple of 8, <= 2048", C);
   if (rows == 0) return 0;
   WNB_CHECK_ARG(dact && th && sg && dab, "gate_bwd_nlc: null pointer");
@@ -755,9 +760,19 @@ extern "C" int wnb200_gate_bwd_nlc(int64_t rows, int C, const void* dact, const 
   long long grid = (rows + rpb - 1) / rpb;
   if (grid > 148 * 8) grid = 148 * 8;
   gate_bwd_nlc_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
-      rows, C, (const uint4*)dact, (const uint4*)th, (const uint4*)sg, (uint4*)dab, dbias);
+      rows, C, (const uint4*)dact, (const uint4*)th, (const uint4*)sg, (uint4*)dab, dbias, th_is_gate);
   WNB_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int wnb200_gate_bwd_nlc(int64_t rows, int C, const void* dact, const void* th, const void* sg, void* dab,
+                                   float* dbias, void* stream) {
+  return gate_bwd_nlc_launch(rows, C, dact, th, sg, dab, dbias, false, stream);
+}
+
+extern "C" int wnb200_gate_bwd_nlc_from_gate(int64_t rows, int C, const void* dact, const void* gate, const void* sg,
+                                             void* dab, float* dbias, void* stream) {
+  return gate_bwd_nlc_launch(rows, C, dact, gate, sg, dab, dbias, true, stream);
 }
 
 extern "C" int wnb200_colsum_nlc(int64_t rows, int C, const void* x, float* out, void* stream) {

@@ -40,7 +40,6 @@ struct ResDev {
   bf16* save_sg;
   int has_lo;       // PREC kernels: x_lo is present (the stream's fp16 low half joins the projection)
   int xflags;       // WNB200_TIMELINE builds only: experiment switches: 1 approx gate, 2 no lo store
-  int stagger;      // WNB200_TIMELINE builds only: odd CTA pairs start this many cycles late (L2 phase experiment)
 };
 
 constexpr int RB_THREADS = 320;
@@ -490,12 +489,6 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       auto next = [&]() {
         if (++stage == K::NSTAGE) { stage = 0; phase ^= 1; }
       };
-#ifdef WNB200_TIMELINE
-      if (p.stagger > 0 && (pair & 1)) {          // experiment: odd pairs run half a tile period out of phase
-        const long long c0 = clock64();
-        while (clock64() - c0 < p.stagger) { }
-      }
-#endif
       const int wrow = (int)rank * (C / 2);       // this CTA's rows inside a [C x 64] weight block
       int ord[3] = {0, 1, 2};                     // tap order: the zero-offset tap (x(t)) first
       for (int j = 1; j < p.ntaps; ++j)
@@ -699,24 +692,34 @@ resblock2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
               ps[i >> 1] = pack_bf16x2(s0v, s1v);
             }
             const int ch0 = half * (C / 2) + c * 64;   // first channel of the block
-            if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            // backward needs the gate (an MMA operand of two weight gradients) and ONE of its factors: with sigmoid kept,
+            // tanh = gate / sigmoid in the gate-backward kernel.  tanh is stored only on request (save_th): without it
+            // the two staging buffers alternate between passes and a pass no longer waits for the previous pass's stores.
+            const bool keep_th = p.save_th != nullptr;
+            const uint32_t sgoff = keep_th ? RB_ABYTES : (nchunk & 1u) * RB_ABYTES;
+            if (issuer) {
+              if (keep_th) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            }
             epi_bar();
             uint8_t* blk = smem_gen + (act_base - smem_base) + (ch0 >> 6) * RB_ABYTES + row * 128;
             uint8_t* sth = smem_gen + (stg_base - smem_base) + row * 128;
-            uint8_t* ssg = sth + RB_ABYTES;
+            uint8_t* ssg = sth + sgoff;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int o = ((4 * h + j) ^ sw) << 4;
               *reinterpret_cast<uint4*>(blk + o) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-              *reinterpret_cast<uint4*>(sth + o) = make_uint4(pt[4 * j], pt[4 * j + 1], pt[4 * j + 2], pt[4 * j + 3]);
+              if (keep_th)
+                *reinterpret_cast<uint4*>(sth + o) = make_uint4(pt[4 * j], pt[4 * j + 1], pt[4 * j + 2], pt[4 * j + 3]);
               *reinterpret_cast<uint4*>(ssg + o) = make_uint4(ps[4 * j], ps[4 * j + 1], ps[4 * j + 2], ps[4 * j + 3]);
             }
             fence_proxy_async_smem();
             epi_bar();
+            ++nchunk;
             if (issuer) {
               tma_store_3d(&map_act, act_base + (ch0 >> 6) * RB_ABYTES, ch0, t0, b);
-              tma_store_3d(&map_th, stg_base, ch0, t0, b);
-              tma_store_3d(&map_sg, stg_base + RB_ABYTES, ch0, t0, b);
+              if (keep_th) tma_store_3d(&map_th, stg_base, ch0, t0, b);
+              tma_store_3d(&map_sg, stg_base + sgoff, ch0, t0, b);
               bulk_commit();
             }
           }
@@ -1065,11 +1068,11 @@ extern "C" int wnb200_resblock_fwd_tc(const wnb200_resblock_t* a, void* stream) 
                 "resblock_fwd_tc: skips_act needs the CTA-pair kernel and the last layer (res = NULL)");
   p.dbg = (long long*)a->dbg;
   p.save_act = (bf16*)a->save_act; p.save_th = (bf16*)a->save_th; p.save_sg = (bf16*)a->save_sg;
-  WNB_CHECK_ARG(!a->save_act || (a->save_th && a->save_sg && (a->variant & 3) != 1),
-                "resblock_fwd_tc: saving the gate factors needs all three buffers and the CTA-pair kernel");
+  WNB_CHECK_ARG(!a->save_act || (a->save_sg && (a->variant & 3) != 1),
+                "resblock_fwd_tc: saving for backward needs save_act and save_sg (save_th optional) and the CTA-pair kernel");
+  WNB_CHECK_ARG(a->save_act || (!a->save_th && !a->save_sg), "resblock_fwd_tc: save_th / save_sg without save_act");
   const bool pair = (a->variant & 3) != 1;     // 0 / 2: CTA-pair kernel (default); 1: single-CTA kernel
   p.xflags = (a->variant >> 2) & 3;
-  p.stagger = (a->variant >> 8) * 1024;
   const bool prec = a->act_fmt == WNB200_ACT_F16X2;
   WNB_CHECK_ARG(a->act_fmt == WNB200_ACT_BF16 || prec, "resblock_fwd_tc: bad act_fmt %d", a->act_fmt);
   WNB_CHECK_ARG(!prec || (pair && !a->save_act), "resblock_fwd_tc: the fp16 (hi, lo) format needs the CTA-pair kernel, inference only");
@@ -1093,7 +1096,8 @@ extern "C" int wnb200_resblock_fwd_tc(const wnb200_resblock_t* a, void* stream) 
     if (a->save_act) {
       CUtensorMap mact, mth, msg;
       if ((rc = rb_map_nlc(&mact, a->save_act, a->B, a->T, C, 2))) return rc;
-      if ((rc = rb_map_nlc(&mth, a->save_th, a->B, a->T, C, 2))) return rc;
+      mth = mact;
+      if (a->save_th && (rc = rb_map_nlc(&mth, a->save_th, a->B, a->T, C, 2))) return rc;
       if ((rc = rb_map_nlc(&msg, a->save_sg, a->B, a->T, C, 2))) return rc;
       return C == 256 ? launch_resblock2<256, true>(mx, mw1, mw2, mres, msk, mact, mth, msg, p, st)
                       : launch_resblock2<128, true>(mx, mw1, mw2, mres, msk, mact, mth, msg, p, st);

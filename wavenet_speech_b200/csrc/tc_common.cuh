@@ -287,13 +287,15 @@ __device__ __forceinline__ uint32_t pack_act2(bool f16, float lo, float hi) {
 }
 // fp16 (hi, lo) split of two fp32 values: hi = fp16(v) (clamped to the finite range), lo = fp16(v - hi):
 // hi + lo carries 22 mantissa bits of v
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {      // one F2FP.SATFINITE: +-65504 beyond the range
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 __device__ __forceinline__ void split_f16x2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-  v0 = fminf(fmaxf(v0, -65504.f), 65504.f);
-  v1 = fminf(fmaxf(v1, -65504.f), 65504.f);
-  const __half2 h = __floats2half2_rn(v0, v1);
-  const float2 hf = __half22float2(h);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = pack_f16x2(v0 - hf.x, v1 - hf.y);
+  hi = pack_f16x2_sat(v0, v1);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = pack_f16x2_sat(v0 - hf.x, v1 - hf.y);
 }
 // tanh(a) * sigmoid(b) from the pre-scaled arguments ua = -2 log2(e) a, ub = -log2(e) b:
 //   (1 - 2^ua) / ((1 + 2^ua) (1 + 2^ub))        -- 2 ex2 + 1 rcp, relative error ~1e-6 (tanh.approx: 5e-4)

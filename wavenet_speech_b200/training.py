@@ -77,13 +77,14 @@ def colsum(x_nlc, out=None):
     return out
 
 
-def gate_bwd_nlc(dgate, th, sg, want_bias=False):
-    """dab = [dgate sg (1-th^2) ; dgate th sg (1-sg)]; with want_bias also its fp32 column sums [2C]."""
+def gate_bwd_nlc(dgate, th, sg, want_bias=False, th_is_gate=False):
+    """dab = [dgate sg (1-th^2) ; dgate th sg (1-sg)]; with want_bias also its fp32 column sums [2C].
+    th_is_gate: `th` holds the gate tanh * sigmoid (what the training forward keeps): tanh = gate / sigmoid."""
     B, T, C = dgate.shape
     dab = torch.empty((B, T, 2 * C), dtype=torch.bfloat16, device=dgate.device)
     dbias = _zeros(2 * C, dgate.device) if want_bias else None
-    _lib.call("wnb200_gate_bwd_nlc", B * T, C, ops._p(dgate), ops._p(th), ops._p(sg), ops._p(dab), ops._p(dbias),
-              ops._stream())
+    _lib.call("wnb200_gate_bwd_nlc_from_gate" if th_is_gate else "wnb200_gate_bwd_nlc", B * T, C, ops._p(dgate),
+              ops._p(th), ops._p(sg), ops._p(dab), ops._p(dbias), ops._stream())
     return (dab, dbias) if want_bias else dab
 
 
@@ -139,18 +140,19 @@ def _pool_floats(stack):
 
 
 def stack_forward(h0, stack, skips):
-    """Residual stack keeping (x, gate, th, sg) of every layer.  Returns (saved list, skips_act): the last launch emits
-    LeakyReLU(skip sum) as bf16 itself (the fp32 sum is not needed after the forward)."""
+    """Residual stack keeping (x, gate, sigmoid) of every layer -- backward recovers tanh as gate / sigmoid, so the third
+    tensor round 1 wrote and read back per layer (2 x 268 MB at the config-3 shape) is gone.  Returns (saved list,
+    skips_act): the last launch emits LeakyReLU(skip sum) as bf16 itself (the fp32 sum is not needed after the forward)."""
     saved = []
     h = h0
     n = len(stack.fwd)
     skips_act = torch.empty_like(h0) if FP.FUSE_FINAL else None
     for l, pk in enumerate(stack.fwd):
         last = l == n - 1
-        act, th, sg = torch.empty_like(h), torch.empty_like(h), torch.empty_like(h)
+        act, sg = torch.empty_like(h), torch.empty_like(h)
         res = None if last else torch.empty_like(h)
-        FP.resblock(h, pk, res, skips, l == 0, save=(act, th, sg), skips_act=skips_act if last else None)
-        saved.append((h, act, th, sg))
+        FP.resblock(h, pk, res, skips, l == 0, save=(act, None, sg), skips_act=skips_act if last else None)
+        saved.append((h, act, sg))
         h = res
     return saved, skips_act
 
@@ -168,14 +170,14 @@ def stack_backward(stack, saved, dskips, need_dx0):
     M_all = _zeros(L * C * C, dev).view(L, C, C)            # M[l] = dskips (x) gate_l, the fold's weight-space gradient
     dres = dres_cs = None
     for l in range(L - 1, -1, -1):
-        x, act, th, sg = saved[l]
+        x, act, sg = saved[l]
         pb, offs = stack.bwd[l], stack.fwd[l]["offsets"]
         k = pb["k"]
         if dres is None:
             dg = FP.dense(dskips, [0], pb["wdg_skip"], zb, C)
         else:
             dg = FP.dense(dres, [0], pb["wdg"], zb, C, x2=dskips, offsets2=[0])
-        dab, dbab = gate_bwd_nlc(dg, th, sg, want_bias=True)
+        dab, dbab = gate_bwd_nlc(dg, act, sg, want_bias=True, th_is_gate=True)
         del dg
         dx = dx_cs = None
         if l > 0 or need_dx0:
