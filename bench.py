@@ -577,7 +577,16 @@ def main():
     tagged = [k for k in per if k.endswith(":resblock")]
     dom = tagged[0] if tagged else "wnb200_taps_fwd"
     tot = sum(sum(v) for v in per.values())
-    if tagged:
+    from wavenet_speech_b200 import fastpath as _FP
+    deferred = bool(tagged) and _FP.DEFER_SKIP and any(k.endswith(":skipsum") for k in per)
+    L = len(w["dil"])
+    if tagged and deferred:
+        # deferred skip: a block launch computes the two dilated convs, conv1x1_residual and residual_proj (12 C^2 FLOP per
+        # frame as written, block.py:66-79; the last layer has no residual output: 8 C^2); conv1x1_skip + the bottleneck
+        # (4 C^2 per layer as written, block.py:74 + wavenet.py:100) are the stack-wide skip contraction, reported apart
+        flops_launch = ((L - 1) * 12 + 8) / float(L) * C * C * samples
+        avg_ms = float(np.mean(per[dom]))
+    elif tagged:
         flops_launch = 16 * C * C * samples                        # block + bottleneck as written
         avg_ms = float(np.mean(per[dom]))
     else:                                                           # generic path: all contraction launches together
@@ -596,14 +605,26 @@ def main():
                 traffic, traffic_src = ent["dram_bytes_per_launch"], ent.get("source")
     # executed MACs per frame: bf16 format 7 C^2 (skip -> bottleneck folded); precise 8 C^2 (+ the stream's lo half
     # through the projection); as written in the reference: 8 C^2 (16 C^2 FLOP)
-    exec_ratio = (16.0 if precise else 14.0) / 16.0
+    if deferred:       # executed: + the lo half through the projection in the precise format (14 of 12 as written)
+        exec_ratio = (((L - 1) * 14 + 8) / float((L - 1) * 12 + 8)) if precise else 1.0
+    else:
+        exec_ratio = (16.0 if precise else 14.0) / 16.0
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
                 "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": traffic,
                 "traffic_source": traffic_src,
                 "achieved_executed": achieved * exec_ratio if tagged else achieved,
                 "peak_source": peaks["source"] + " (bf16_tflops_sustained)",
                 "share_of_step": float(sum(per[dom])) / tot if tot > 0 else None,
-                "avg_launch_ms": avg_ms}
+                "avg_launch_ms": avg_ms,
+                "flops_per_launch_as_written": flops_launch}
+    if deferred:
+        sk = [k for k in per if k.endswith(":skipsum")][0]
+        sk_ms = float(np.mean(per[sk]))
+        roofline["skip_contraction"] = {
+            "kernel": sk, "avg_launch_ms": sk_ms, "launches_per_step": len(per[sk]) // n_pass,
+            "tflops_as_written": 4 * C * C * L * samples / (sk_ms * 1e-3) / 1e12,
+            "tflops_executed": 2 * C * C * L * samples / (sk_ms * 1e-3) / 1e12,
+            "what": "sum_l (Wbn_l Wskip_l) gate_l over K = layers x channels, accumulated in TMEM (wavenet.py:97-100)"}
 
     input_mb = x_dev.numel() * x_dev.element_size() / 1e6
     fwd_bwd = None

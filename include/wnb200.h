@@ -207,7 +207,9 @@ int wnb200_chain_fwd_tc(const wnb200_chain_t* args /*host*/, void* stream);
  *   w1   bf16 [2C][ntaps*C]: rows = [tanh 0:C/2 ; sigmoid 0:C/2 ; tanh C/2:C ; sigmoid C/2:C], tap-major columns
  *   b1   fp32 [2C] in the same row order
  *   w2   bf16 [2C][2C] = [[Wres, Wproj], [Wbn*Wskip, 0]];   b2 fp32 [2C] = [bres+bproj ; Wbn*bskip+bbn]
- *   res  bf16 NLC [B,T,C] or NULL (last layer: not needed);  skips fp32 NLC [B,T,C]. */
+ *   res  bf16 NLC [B,T,C] or NULL (last layer: not needed);  skips fp32 NLC [B,T,C].
+ * Two ways to get the skip sum (wavenet.py:97-100): `skips` accumulated in HBM by every call (TMA reduce-add; the training
+ * forward and the single-CTA kernel), or `gate_out` (deferred: see the field) -- the inference default. */
 typedef struct {
   uint32_t struct_size;   /* = sizeof(wnb200_resblock_t) */
   int32_t B, T, C, ntaps;
@@ -231,6 +233,11 @@ typedef struct {
                              LeakyReLU(skips + contribution) (wavenet.py:100-103); `skips` is then read, not updated */
   const void* x_lo;       /* F16X2: lo half of the input stream, NLC fp16 [B,T,C]; NULL = the input is exactly x */
   void* res_lo;           /* F16X2: lo half of the output stream (required when res != NULL) */
+  void* gate_out;         /* optional (inference): NLC [B,T,C] in act_fmt that receives the gate tanh(.)*sigmoid(.).  When
+                             given, the call does NOT touch `skips` (may be NULL): the skip sum of the whole stack,
+                             sum_l (Wbn_l Wskip_l) gate_l + biases, is left to ONE wnb200_dense_fwd_tc call with
+                             `nlayers` over the stacked gates (K = layers x channels, accumulated in tensor memory).
+                             res = NULL on the last layer skips the residual contraction altogether. */
 } wnb200_resblock_t;
 int wnb200_resblock_fwd_tc(const wnb200_resblock_t* args /*host*/, void* stream);
 
@@ -257,7 +264,9 @@ typedef struct {
   float* colsum;          /* mode 0, optional: fp32 [N], += the column sums of y over all frames (the bias gradient of
                              the contraction that consumes y as its output gradient: autograd of conv biases) */
   int32_t act_fmt;        /* WNB200_ACT_BF16 | WNB200_ACT_F16X2: format of x, x2, w and of the NLC output */
-  int32_t reserved0;
+  int32_t nlayers;        /* > 0: x is a stack [nlayers][B][T][Cin] (ntaps = 1, offset 0, no x2) and W is [N][nlayers*Cin]:
+                             y = epi(sum_l W_l x_l + bias) -- the skip sum of a whole residual stack in ONE contraction,
+                             accumulated in tensor memory over K = layers x channels (wavenet.py:97-100) */
   void* y_lo;             /* F16X2, mode 0, optional: y leaves as an fp16 (hi, lo) pair (y, y_lo) -- the producer of a
                              residual stream (entry conv, RawCTCNet feature 1x1) */
 } wnb200_dense_t;

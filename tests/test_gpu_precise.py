@@ -215,3 +215,42 @@ def test_host_pipeline_back_to_back_submits():
         pipe.wait()
         for o, d in zip(outs, direct):
             assert torch.equal(o, d), chunks
+
+
+@pytest.mark.parametrize("fmt", ["fast", "precise"])
+@pytest.mark.parametrize("L,B,T,C", [(3, 2, 300, 256), (5, 1, 130, 128), (20, 1, 257, 256)])
+def test_stack_wide_skip_contraction(fmt, L, B, T, C):
+    """wnb200_dense_fwd_tc with `nlayers`: y = LeakyReLU(sum_l W_l g_l + bias) over a gate stack [L, B, T, C] -- the skip
+    sum of a whole residual stack as one contraction (K = L * C, accumulated in tensor memory)."""
+    torch.manual_seed(L * 100 + C)
+    dt = torch.float16 if fmt == "precise" else torch.bfloat16
+    g = (torch.rand(L, B, T, C) * 2 - 1).to(dt)
+    w = (torch.randn(C, L * C) / (L * C) ** 0.5).to(dt)
+    bias = torch.randn(C) * 0.1
+    y = FP.dense(g.cuda(), [0], w.cuda(), bias.cuda(), C, leaky=1,
+                 fmt=W._lib.ACT_F16X2 if fmt == "precise" else W._lib.ACT_BF16, nlayers=L)
+    torch.cuda.synchronize()
+    ref = bias.view(1, 1, C) + sum(g[l].float() @ w[:, l * C:(l + 1) * C].float().t() for l in range(L))
+    ref = torch.nn.functional.leaky_relu(ref, 0.01)
+    assert y.dtype == dt and tuple(y.shape) == (B, T, C)
+    assert G.rel_linf(y.float().cpu(), ref) <= (2e-3 if fmt == "precise" else 1e-2)
+
+
+@pytest.mark.parametrize("fmt", ["fast", "precise"])
+def test_deferred_skip_equals_running_sum_pipeline(fmt):
+    """The two ways to the skip sum (gates stored + one stack-wide contraction / a running fp32 sum in HBM updated by
+    every layer) agree to rounding: same gates, fp32 accumulation in both, only the summation order and the rounding of
+    the folded weights' products differ."""
+    torch.manual_seed(17)
+    C = 256
+    layers = [(C, C, 2, d) for d in (1, 2, 4, 8, 16, 32)]
+    net = W.RawCTCNet(C, 3, 5, layers, C, softmax=False).cuda().bfloat16().eval()
+    x = torch.randn(3, 1, 900, device="cuda").bfloat16()
+    try:
+        with torch.no_grad(), FP.tc_precision(fmt):
+            y = net(x)
+            FP.DEFER_SKIP = False
+            y0 = net(x)
+    finally:
+        FP.DEFER_SKIP = True
+    assert G.rel_linf(y.float().cpu(), y0.float().cpu()) <= 8e-3

@@ -204,7 +204,8 @@ def test_wavenet_tc(C, nl, T, B, softmax):
         before = W._lib.launch_count
         y = net(x.cuda().bfloat16())
         assert y.dtype == torch.bfloat16 and tuple(y.shape) == tuple(ref.shape)
-    assert W._lib.launch_count - before == nl + 4        # transpose, entry, blocks (the last one emits the head's input), 2 x head
+    # transpose, entry, blocks (each stores its gate), the stack-wide skip contraction (C >= 128), 2 x head
+    assert W._lib.launch_count - before == nl + (5 if C >= 128 else 4)
     e = rel(y, ref)
     assert e <= BF16_TOL, e
     if not softmax:
@@ -243,13 +244,15 @@ def test_last_layer_emits_head_input_bitwise(C, dil, T, B):
     net = W.WaveNet(C, 2, [(C, C, 2, d) for d in dil], C, softmax=False).cuda().bfloat16().eval()
     x = torch.randn(B, C, T, device="cuda").bfloat16()
     try:
-        with torch.no_grad():
+        FP.DEFER_SKIP = False                     # this is about the in-HBM skip sum of the bf16 format (resblock2_kernel)
+        with torch.no_grad(), FP.tc_precision("fast"):
             FP.FUSE_FINAL = False
             ref = net(x)
             FP.FUSE_FINAL = True
             y = net(x)
     finally:
         FP.FUSE_FINAL = True
+        FP.DEFER_SKIP = True
     assert torch.equal(y, ref)
 
 
@@ -352,7 +355,7 @@ def test_reduced_precision_switch_routes_fp32_models():
             net(xg)                                  # packs
             before = W._lib.launch_count
             y2 = net(xg)
-            assert W._lib.launch_count - before == len(layers) + 4         # the tensor-core launch sequence
+            assert W._lib.launch_count - before == len(layers) + 5         # the tensor-core launch sequence
         assert y2.dtype == torch.float32 and rel(y2, ref16) <= BF16_TOL
         xr = xg.clone().requires_grad_(True)
         out = net(xr)

@@ -51,7 +51,7 @@ class ResBlock(_Sized):
                 ("act_fmt", ctypes.c_int32), ("x", c_void_p), ("w1", c_void_p),
                 ("bias1", c_void_p), ("w2", c_void_p), ("bias2", c_void_p), ("res", c_void_p), ("skips", c_void_p),
                 ("dbg", c_void_p), ("save_act", c_void_p), ("save_th", c_void_p), ("save_sg", c_void_p),
-                ("skips_act", c_void_p), ("x_lo", c_void_p), ("res_lo", c_void_p)]
+                ("skips_act", c_void_p), ("x_lo", c_void_p), ("res_lo", c_void_p), ("gate_out", c_void_p)]
 
 
 class Dense(_Sized):
@@ -63,7 +63,7 @@ class Dense(_Sized):
                 ("out_f32", ctypes.c_int32), ("Cin2", ctypes.c_int32), ("ntaps2", ctypes.c_int32),
                 ("t_off2", ctypes.c_int32 * 3), ("x", c_void_p), ("w", c_void_p),
                 ("bias", c_void_p), ("y", c_void_p), ("x2", c_void_p), ("colsum", c_void_p),
-                ("act_fmt", ctypes.c_int32), ("reserved0", ctypes.c_int32), ("y_lo", c_void_p)]
+                ("act_fmt", ctypes.c_int32), ("nlayers", ctypes.c_int32), ("y_lo", c_void_p)]
 
 
 class PackBlock(_Sized):

@@ -43,6 +43,7 @@ struct DenseDev {
   float* colsum;    // NLC mode, optional: fp32 [N] += column sums of the (bf16-rounded) output over all valid frames
   int f16;          // operands (and NLC output) are fp16 instead of bf16 (WNB200_ACT_F16X2)
   int split;        // NLC mode, fp16: the output leaves as an fp16 (hi, lo) pair (map_y, map_ylo)
+  int nlayers;      // > 0: x is a stack [nlayers][B][T][Cin] and K runs over (layer, channel): y = sum_l W_l x_l (+ bias)
 };
 
 constexpr int DN_THREADS = 320;
@@ -75,7 +76,7 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int nkb1 = p.ntaps * p.kb_per_tap;
+  const int nkb1 = (p.nlayers > 0 ? p.nlayers : p.ntaps) * p.kb_per_tap;
   const int nkb = nkb1 + p.ntaps2 * p.kb_per_tap2;
   const uint32_t bhalf_bytes = (uint32_t)(p.N / 2) * 128u;
 
@@ -118,7 +119,8 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
           const uint32_t lfull = mapa_shared(full_bar(stage), 0);
           if (kb < nkb1) {
             const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
-            tma_load_3d_2sm(sa, &map_x, lfull, cb * 64, t0 + p.t_off[tap], b);
+            if (p.nlayers > 0) tma_load_3d_2sm(sa, &map_x, lfull, cb * 64, t0, tap * p.B + b);     // tap = layer index
+            else tma_load_3d_2sm(sa, &map_x, lfull, cb * 64, t0 + p.t_off[tap], b);
           } else {
             const int k2 = kb - nkb1;
             const int tap = k2 / p.kb_per_tap2, cb = k2 - tap * p.kb_per_tap2;
@@ -765,16 +767,20 @@ extern "C" int wnb200_dense_fwd_tc(const wnb200_dense_t* a, void* stream) {
   WNB_CHECK_ARG(a->act_fmt == WNB200_ACT_BF16 || a->act_fmt == WNB200_ACT_F16X2, "dense_fwd_tc: bad act_fmt %d", a->act_fmt);
   p.f16 = a->act_fmt == WNB200_ACT_F16X2;
   p.split = p.f16 && a->mode == 0 && a->y_lo != nullptr;
+  p.nlayers = a->nlayers;
+  WNB_CHECK_ARG(a->nlayers >= 0 && (a->nlayers == 0 || (a->ntaps == 1 && a->t_off[0] == 0 && !a->x2)),
+                "dense_fwd_tc: a layer stack is contracted with one zero-offset tap and no second source");
   WNB_CHECK_ARG(!a->y_lo || p.split, "dense_fwd_tc: y_lo needs act_fmt = WNB200_ACT_F16X2 and the NLC mode");
   WNB_CHECK_ARG(!p.f16 || !p.colsum, "dense_fwd_tc: colsum is a bf16 (training) feature");
   const int esize = a->out_f32 ? 4 : 2;
   p.tma_out = (a->mode == 1 && ((long long)a->T * esize) % 16 == 0) ? 1 : 0;
   CUtensorMap mx, mx2, mw, my, mylo;
   int rc;
-  if ((rc = rb_map_nlc(&mx, a->x, a->B, a->T, a->Cin, 2))) return rc;
+  if ((rc = rb_map_nlc(&mx, a->x, a->B * (a->nlayers > 0 ? a->nlayers : 1), a->T, a->Cin, 2))) return rc;
   mx2 = mx;
   if (p.ntaps2 > 0 && (rc = rb_map_nlc(&mx2, a->x2, a->B, a->T, a->Cin2, 2))) return rc;
-  if ((rc = rb_map_2d(&mw, a->w, a->N, a->ntaps * a->Cin + p.ntaps2 * a->Cin2, a->N / 2))) return rc;
+  if ((rc = rb_map_2d(&mw, a->w, a->N, (a->nlayers > 0 ? a->nlayers : a->ntaps) * a->Cin + p.ntaps2 * a->Cin2,
+                      a->N / 2))) return rc;
   if (a->mode == 0) {
     if ((rc = rb_map_nlc(&my, a->y, a->B, a->T, a->N, 2))) return rc;
   } else if (p.tma_out) {

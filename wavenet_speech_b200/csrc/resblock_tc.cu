@@ -1046,6 +1046,10 @@ __global__ void leaky_to_bf16_kernel(long long n4, const float4* x, uint2* y) {
 
 using namespace wnb;
 
+namespace wnb {
+int resblock3_launch(const wnb200_resblock_t* a, void* stream);      // resblock3_tc.cu: deferred-skip variant
+}
+
 extern "C" int wnb200_resblock_fwd_tc(const wnb200_resblock_t* a, void* stream) {
   WNB_CHECK_ARG(a != nullptr, "resblock_fwd_tc: null argument");
   WNB_CHECK_STRUCT(a, wnb200_resblock_t, "resblock_fwd_tc");
@@ -1053,6 +1057,12 @@ extern "C" int wnb200_resblock_fwd_tc(const wnb200_resblock_t* a, void* stream) 
   WNB_CHECK_ARG(C == 128 || C == 256, "resblock_fwd_tc: C=%d not in {128,256}", C);
   WNB_CHECK_ARG(a->ntaps >= 1 && a->ntaps <= 3, "resblock_fwd_tc: ntaps=%d not in 1..3", a->ntaps);
   if (a->B == 0 || a->T == 0) return 0;
+  WNB_CHECK_ARG(a->act_fmt == WNB200_ACT_BF16 || a->act_fmt == WNB200_ACT_F16X2, "resblock_fwd_tc: bad act_fmt %d",
+                a->act_fmt);
+  if (a->gate_out) {       // deferred skip: the gate is stored, the skip sum is one stack-wide contraction afterwards
+    WNB_CHECK_ARG(a->x && a->w1 && a->w2 && a->bias1 && a->bias2, "resblock_fwd_tc: null pointer");
+    return resblock3_launch(a, stream);
+  }
   WNB_CHECK_ARG(a->x && a->w1 && a->w2 && a->bias1 && a->bias2 && a->skips, "resblock_fwd_tc: null pointer");
   ResDev p;
   memset(&p, 0, sizeof(p));

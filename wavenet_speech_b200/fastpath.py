@@ -210,7 +210,7 @@ FUSE_FINAL = True     # last layer of an inference stack emits LeakyReLU(skip su
 
 
 def resblock(x_nlc, pk, res, skips, skips_init, dbg=None, variant=None, save=None, skips_act=None, x_lo=None,
-             res_lo=None):
+             res_lo=None, gate_out=None):
     """Pipelined fused block (C = 128 / 256).  variant 0/2 = CTA-pair kernel, 1 = single-CTA kernel.
     save = (gate, th, sg) NLC bf16 buffers: training keeps the gate and its two factors for backward.
     x_lo / res_lo: low halves of the fp16 (hi, lo) stream when the pack is a `precise` one."""
@@ -229,6 +229,7 @@ def resblock(x_nlc, pk, res, skips, skips_init, dbg=None, variant=None, save=Non
     a.skips_act = p(skips_act)
     a.act_fmt = pk.get("fmt", _lib.ACT_BF16)
     a.x_lo, a.res_lo = p(x_lo), p(res_lo)
+    a.gate_out = p(gate_out)
     _lib.current_tag = "resblock"
     try:
         _lib.call("wnb200_resblock_fwd_tc", ctypes.byref(a), ops._stream())
@@ -237,11 +238,16 @@ def resblock(x_nlc, pk, res, skips, skips_init, dbg=None, variant=None, save=Non
 
 
 def dense(x_nlc, offsets, w, bias, N, mode=0, leaky=0, out=None, n_out=0, softmax=0, x2=None, offsets2=(), colsum=None,
-          fmt=0, split=False):
+          fmt=0, split=False, nlayers=0):
     """CTA-pair dense contraction.  mode 0 -> NLC bf16 [B,T,N]; mode 1 -> NCL `out` [B,n_out,T].
     Optional second source x2 [B,T,Cin2] with its own taps: its columns follow x's in `w`.
-    colsum (mode 0): fp32 [N] tensor that the column sums of the output are ADDED to."""
-    B, T, Cin = x_nlc.shape
+    colsum (mode 0): fp32 [N] tensor that the column sums of the output are ADDED to.
+    nlayers: x_nlc is a stack [L, B, T, Cin] and w is [N, L*Cin]: y = epi(sum_l W_l x_l + bias), one contraction."""
+    if nlayers:
+        assert x_nlc.dim() == 4 and x_nlc.shape[0] == nlayers and len(offsets) == 1 and x2 is None
+        _L, B, T, Cin = x_nlc.shape
+    else:
+        B, T, Cin = x_nlc.shape
     a = _lib.Dense()
     a.B, a.T, a.Cin, a.ntaps = B, T, Cin, len(offsets)
     for j, o in enumerate(offsets):
@@ -256,6 +262,7 @@ def dense(x_nlc, offsets, w, bias, N, mode=0, leaky=0, out=None, n_out=0, softma
             out_lo = torch.empty_like(out)
             a.y_lo = out_lo.data_ptr()
     a.act_fmt = fmt
+    a.nlayers = int(nlayers)
     a.out_f32 = 1 if out.dtype == torch.float32 else 0
     a.x, a.w, a.bias, a.y = x_nlc.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr()
     if colsum is not None:
@@ -266,8 +273,9 @@ def dense(x_nlc, offsets, w, bias, N, mode=0, leaky=0, out=None, n_out=0, softma
         a.x2, a.Cin2, a.ntaps2 = x2.data_ptr(), x2.shape[2], len(offsets2)
         for j, o in enumerate(offsets2):
             a.t_off2[j] = int(o)
-    assert w.shape[1] == Cin * len(offsets) + (0 if x2 is None else x2.shape[2] * len(offsets2)), "dense: K mismatch"
-    _lib.current_tag = "dense" if mode == 0 else "head"
+    assert w.shape[1] == Cin * (nlayers or len(offsets)) + (0 if x2 is None else x2.shape[2] * len(offsets2)), \
+        "dense: K mismatch"
+    _lib.current_tag = "skipsum" if nlayers else ("dense" if mode == 0 else "head")
     try:
         _lib.call("wnb200_dense_fwd_tc", ctypes.byref(a), ops._stream())
     finally:
@@ -371,10 +379,48 @@ def _stack_ok(C, layers):
     return C in _OK_C and all(ci == C and co == C and k <= 3 for (ci, co, k, _d) in layers)
 
 
-def run_blocks(h, blocks, bottlenecks, packs, skips, first_init, want_act, h_lo=None):
-    """Residual stack on NLC activations: one fused launch per layer.  Returns (h, skips_act).
-    Precise packs: `h` is the hi half of the fp16 stream, `h_lo` its lo half (None: the input is exactly `h`)."""
+DEFER_SKIP = True     # inference stacks (C = 128 / 256): gates stored per layer, the skip sum is ONE contraction at the end
+
+
+def skip_pack(packs):
+    """Operands of the stack-wide skip contraction: Wcat [C, L*C] = [fold_0 | fold_1 | ...] (fold_l = Wbn_l Wskip_l, the
+    lower-left block of the layer's w2) and the summed skip biases.  Built once per weight version (cached by the caller)."""
+    C = packs[0]["C"]
+    wcat = torch.cat([pk["w2"][C:, :C] for pk in packs], 1).contiguous()
+    bsum = torch.stack([pk["b2"][C:] for pk in packs]).sum(0).contiguous()
+    return wcat, bsum
+
+
+def run_blocks_deferred(h, packs, skip, h_lo=None):
+    """Residual stack with the skip sum deferred (resblock3_kernel + one `nlayers` contraction): returns the head's
+    input LeakyReLU(skip sum) as an NLC tensor in the packs' format.  The running sum never exists in HBM."""
     B, T, C = h.shape
+    L = len(packs)
+    prec = packs[0].get("fmt", 0) == _lib.ACT_F16X2
+    gates = torch.empty((L, B, T, C), dtype=h.dtype, device=h.device)
+    buf = [h, torch.empty_like(h)]
+    lo = [h_lo, torch.empty_like(h)] if prec else [None, None]
+    for l, pk in enumerate(packs):
+        last = l == L - 1
+        resblock(buf[0], pk, None if last else buf[1], None, False, x_lo=lo[0],
+                 res_lo=None if (last or not prec) else lo[1], gate_out=gates[l])
+        if not last:
+            buf = [buf[1], buf[0]]
+            if prec:
+                lo = [lo[1], lo[0] if lo[0] is not None else torch.empty_like(h)]
+    wcat, bsum = skip
+    return dense(gates, [0], wcat, bsum, C, leaky=1, fmt=packs[0].get("fmt", 0), nlayers=L)
+
+
+def run_blocks(h, blocks, bottlenecks, packs, skips, first_init, want_act, h_lo=None, skip=None):
+    """Residual stack on NLC activations: one fused launch per layer.  Returns (h, skips_act).
+    Precise packs: `h` is the hi half of the fp16 stream, `h_lo` its lo half (None: the input is exactly `h`).
+    skip = skip_pack(packs): use the deferred-skip pipeline (inference default for C = 128 / 256)."""
+    B, T, C = h.shape
+    if skip is not None and DEFER_SKIP and want_act and C in (128, 256) and RESBLOCK_VARIANT != 1:
+        return None, run_blocks_deferred(h, packs, skip, h_lo=h_lo)
+    if skips is None:
+        skips = torch.empty((B, T, C), dtype=torch.float32, device=h.device)
     buf = [h, torch.empty_like(h)]
     n = len(packs)
     if C in (128, 256) and packs[0].get("fmt", 0) == _lib.ACT_F16X2:
@@ -443,7 +489,7 @@ def try_wavenet_forward(model, signal):
                 "blocks": [pack_block(b, n, prec) for b, n in zip(model.convolutions, model.bottlenecks)],
                 "head": pack_head(model.output_stack, C, prec)}
 
-    pk = _cached(model, "wavenet_p" if prec else "wavenet", build)
+    pk = _with_skip(_cached(model, "wavenet_p" if prec else "wavenet", build))
     B, _, T = signal.shape
     x = ncl_to_nlc_bf16(signal, fmt)
     h_lo = None
@@ -451,8 +497,8 @@ def try_wavenet_forward(model, signal):
         h, h_lo = dense(x, pk["entry"]["offsets"], pk["entry"]["w1"], pk["entry"]["b1"], C, fmt=fmt, split=True)
     else:
         h = dense(x, pk["entry"]["offsets"], pk["entry"]["w1"], pk["entry"]["b1"], C)
-    skips = torch.empty((B, T, C), dtype=torch.float32, device=signal.device)
-    _, skips_act = run_blocks(h, model.convolutions, model.bottlenecks, pk["blocks"], skips, True, True, h_lo=h_lo)
+    _, skips_act = run_blocks(h, model.convolutions, model.bottlenecks, pk["blocks"], None, True, True, h_lo=h_lo,
+                              skip=pk["skip"])
     return run_head(skips_act, pk["head"], signal.dtype, model.softmax)
 
 
@@ -479,7 +525,7 @@ def wavenet_forward_levels(model, levels, out_dtype=torch.bfloat16):
                 "blocks": [pack_block(b, n, prec) for b, n in zip(model.convolutions, model.bottlenecks)],
                 "head": pack_head(model.output_stack, C, prec)}
 
-    pk = _cached(model, "wavenet_levels_p" if prec else "wavenet_levels", build)
+    pk = _with_skip(_cached(model, "wavenet_levels_p" if prec else "wavenet_levels", build))
     B, T = levels.shape
     lev = levels.to(torch.int32).contiguous()
     h = torch.empty((B, T, C), dtype=torch.float16 if prec else torch.bfloat16, device=levels.device)
@@ -488,10 +534,18 @@ def wavenet_forward_levels(model, levels, out_dtype=torch.bfloat16):
         offs = (ctypes.c_int32 * len(pk["offsets"]))(*[int(o) for o in pk["offsets"]])
         _lib.call("wnb200_entry_embed_nlc", B, T, C, model.in_dim, len(pk["offsets"]), offs, ops._p(lev),
                   ops._p(pk["wemb"]), ops._p(pk["b1"]), fmt, ops._p(h), ops._p(h_lo), ops._stream())
-    skips = torch.empty((B, T, C), dtype=torch.float32, device=levels.device)
     with torch.no_grad():
-        _, skips_act = run_blocks(h, model.convolutions, model.bottlenecks, pk["blocks"], skips, True, True, h_lo=h_lo)
+        _, skips_act = run_blocks(h, model.convolutions, model.bottlenecks, pk["blocks"], None, True, True, h_lo=h_lo,
+                                  skip=pk["skip"])
         return run_head(skips_act, pk["head"], out_dtype, model.softmax)
+
+
+def _with_skip(pk):
+    """Adds the stack-wide skip operands (Wcat, summed biases) to a cached pack dict (C = 128 / 256 stacks only)."""
+    if "skip" not in pk:
+        blocks = pk["blocks"]
+        pk["skip"] = skip_pack(blocks) if blocks and blocks[0]["C"] in (128, 256) else None
+    return pk
 
 
 def _stack_packs(model, precise=False):
@@ -523,7 +577,7 @@ def try_raw_ctcnet_forward(model, seq):
                 "f2w": cast(f2.weight.detach().float()[:, :, 0]), "f2b": f2.bias.detach().float().contiguous(),
                 "blocks": _stack_packs(model, prec), "head": pack_head(model.output_block, C, prec)}
 
-    pk = _cached(model, "raw_ctcnet_p" if prec else "raw_ctcnet", build)
+    pk = _with_skip(_cached(model, "raw_ctcnet_p" if prec else "raw_ctcnet", build))
     B, _, T = seq.shape
     fk = model.feature_kwidth
     To = T + fk - 1
@@ -536,8 +590,7 @@ def try_raw_ctcnet_forward(model, seq):
         h, h_lo = dense(h, [0], pk["f2w"], pk["f2b"], F, leaky=1, fmt=fmt, split=True)
     else:
         h = dense(h, [0], pk["f2w"], pk["f2b"], F, leaky=1)
-    skips = torch.empty((B, To, C), dtype=torch.float32, device=seq.device)
-    _, skips_act = run_blocks(h, None, None, pk["blocks"], skips, True, True, h_lo=h_lo)
+    _, skips_act = run_blocks(h, None, None, pk["blocks"], None, True, True, h_lo=h_lo, skip=pk["skip"])
     return run_head(skips_act, pk["head"], seq.dtype, model.softmax)
 
 
@@ -557,15 +610,14 @@ def try_classifier_forward(model, seq):
     ops.check_device()
     prec = precise_mode(C)
     fmt = _lib.ACT_F16X2 if prec else _lib.ACT_BF16
-    pk = _cached(model, "classifier_p" if prec else "classifier",
-                 lambda: {"blocks": _stack_packs(model, prec), "head": pack_head(model.output_block, C, prec)})
+    pk = _with_skip(_cached(model, "classifier_p" if prec else "classifier",
+                            lambda: {"blocks": _stack_packs(model, prec), "head": pack_head(model.output_block, C, prec)}))
     seq = seq.contiguous()
     B, _, T = seq.shape
     To = T // pool
     h = torch.empty((B, To, C), dtype=torch.float16 if prec else torch.bfloat16, device=seq.device)
     _lib.call("wnb200_avgpool_ncl_to_nlc", ops._dt(seq), B, C, T, pool, ops._p(seq), fmt, ops._p(h), ops._stream())
-    skips = torch.empty((B, To, C), dtype=torch.float32, device=seq.device)
-    _, skips_act = run_blocks(h, None, None, pk["blocks"], skips, True, True)
+    _, skips_act = run_blocks(h, None, None, pk["blocks"], None, True, True, skip=pk["skip"])
     return run_head(skips_act, pk["head"], seq.dtype, model.softmax)
 
 
