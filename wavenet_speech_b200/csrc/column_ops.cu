@@ -262,7 +262,10 @@ xent_bwd_tile(int C, int Tn, TileGeom g, bool vec, const T* x, const long long* 
     const bool ok = t0 + tt < Tn;
     const long long col = (long long)b * Tn + t0 + tt;
     red[tt] = ok ? lse[col] : 0.f;
-    tgs[tt] = ok ? (int)target[col] : -1;
+    // out-of-range targets are clamped exactly as the forward clamps them (the two must describe the same loss)
+    long long tgc = ok ? target[col] : -1;
+    if (ok) tgc = tgc < 0 ? 0 : (tgc >= C ? C - 1 : tgc);
+    tgs[tt] = (int)tgc;
   }
   __syncthreads();
   const float gs = *gscale;
@@ -685,7 +688,11 @@ xent_bwd_reg(int C, int Tn, int tiles_per_read, const T* x, const long long* tar
   int tg[V];
   const long long col0 = (long long)b * Tn + t0 + r.v * V;
 #pragma unroll
-  for (int i = 0; i < V; ++i) { l[i] = lse[col0 + i]; tg[i] = (int)target[col0 + i]; }
+  for (int i = 0; i < V; ++i) {
+    l[i] = lse[col0 + i];
+    const long long tv = target[col0 + i];
+    tg[i] = (int)(tv < 0 ? 0 : (tv >= C ? C - 1 : tv));       // clamped like the forward
+  }
   const float gs = *gscale;
 #pragma unroll
   for (int k = 0; k < KC; ++k) {

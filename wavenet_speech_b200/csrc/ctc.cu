@@ -113,7 +113,7 @@ ctc_alpha_beta_kernel(int L, int Tn, int Smax, const float* __restrict__ lp, con
     const int j = tid + i * nt;
     live[i] = j <= len;
     haslab[i] = j < len;
-    cls[i] = haslab[i] ? lab[j] : 0;
+    cls[i] = haslab[i] ? min(max(lab[j], 0), L - 1) : 0;      // labels outside [0, L) are clamped: never an out-of-range read
     skip[i] = false;
     if (haslab[i]) {
       if (dir == 0) skip[i] = j >= 1 && lab[j - 1] != cls[i];            // alpha: 2j+1 <- 2j-1
@@ -252,7 +252,7 @@ ctc_grad_kernel(int B, int L, int Tn, int Smax, const float* __restrict__ lp, co
       const float2 av = a[j], bv = be[j];
       blank += ex2f(av.x + bv.x - lp0 + n);
       if (j < len) {
-        const int c = lab[j];
+        const int c = min(max(lab[j], 0), L - 1);
         const float wl = ex2f(av.y + bv.y - lpt[c] + n);
 #pragma unroll
         for (int q = 1; q < 8; ++q) occ[q] += (c == q) ? wl : 0.f;
@@ -270,7 +270,7 @@ ctc_grad_kernel(int B, int L, int Tn, int Smax, const float* __restrict__ lp, co
       const float2 av = a[j], bv = be[j];
       blank += ex2f(av.x + bv.x - lp0 + n);
       if (j < len) {
-        const int c = lab[j];
+        const int c = min(max(lab[j], 0), L - 1);
         atomicAdd(&acc[warp][c], ex2f(av.y + bv.y - lpt[c] + n));
       }
     }
