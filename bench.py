@@ -332,6 +332,38 @@ def long_read_measure(rank, world, dist, max_over_ranks, barrier, T=1000000, ste
             "halo_exchange_ms": ms_halo, "sharded_equals_full_bitwise": bool(int(ok)), "scaling": "strong"}
 
 
+def rawctc_sweep(rank, world, dist, max_over_ranks, barrier, steps=3):
+    """BASELINE configs[3]: ecoli RawCTCNet (configs/ecoli_testrun.json: 256 channels, input block + (1,2,4,8,16) x 3,
+    fk = 3) forward throughput for global batches 64 ... 1024 x 4000 samples, the batch sharded over the ranks (no
+    collective: reads are independent).  bf16 in/out, precise format."""
+    import wavenet_speech_b200 as W
+    from wavenet_speech_b200 import sharding as S
+    from wavenet_speech_b200.utils import signal_gen as SG
+    torch.manual_seed(0)
+    net = W.RawCTCNet(256, 3, 5, [(256, 256, 2, d) for d in [1, 2, 4, 8, 16] * 3], 256, softmax=False)
+    net = net.cuda().bfloat16().eval()
+    base = torch.from_numpy(SG.raw_batch(64, 4000, seed=7 + rank)).bfloat16().cuda()
+    out = {}
+    with torch.no_grad():
+        for Bg in (64, 256, 1024):
+            s0, s1 = S.shard_range(Bg, rank, world)
+            n = s1 - s0
+            x = base.repeat((n + 63) // 64, 1, 1)[:n].contiguous() if n > 0 else base[:0]
+            for _ in range(2):
+                net(x)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                net(x)
+            e1.record()
+            barrier()
+            ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+            out["B%d" % Bg] = {"samples_per_s": Bg * 4000 / (ms * 1e-3), "ms_per_step": ms}
+    out["workload"] = "rawctcnet_ecoli_fk3 forward, global batch x 4000 samples, batch-sharded x%d" % world
+    return out
+
+
 def run_reference(args, w):
     """--impl reference: the reference is Python/torch and cannot travel to the GPU box (and is not
     pip-installable: it has no setup.py), so this arm times the oracle port of its CPU path."""
@@ -637,6 +669,10 @@ def main():
     if not args.no_longread and args.workload == DEFAULT_WORKLOAD and args.dtype == "bf16":
         long_read = long_read_measure(rank, world, dist, max_over_ranks, barrier)
         torch.cuda.empty_cache()
+    sweep = None
+    if not args.no_longread and args.workload == DEFAULT_WORKLOAD and args.dtype == "bf16":
+        sweep = rawctc_sweep(rank, world, dist, max_over_ranks, barrier)
+        torch.cuda.empty_cache()
     stock = None
     if not args.no_stock and world == 1 and args.workload == DEFAULT_WORKLOAD:
         stock = stock_torch_gpu(w, rank)
@@ -661,6 +697,7 @@ def main():
                    "other_format": other_fmt,
                    "fwd_bwd": fwd_bwd,                 # configs[2]: WaveNet-CTC train step, batch-sharded + grad all-reduce
                    "time_sharded": long_read,          # configs[4]: 1M-sample read, time-sharded + halo exchange
+                   "rawctcnet_batch_sweep": sweep,     # configs[3]: ecoli RawCTCNet forward, batch 64 .. 1024 x 4000
                    "e2e_levels": e2e_levels,           # host hands over uint8 levels instead of the one-hot tensor
                    "e2e_copy_ceiling": e2e_ceiling,    # pure H2D + D2H of the same bytes at this N: the host's limit
                    "e2e_frac_of_copy_ceiling": (e2e["value"] / e2e_ceiling["value"]) if (e2e and e2e_ceiling) else None,

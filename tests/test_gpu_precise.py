@@ -254,3 +254,24 @@ def test_deferred_skip_equals_running_sum_pipeline(fmt):
     finally:
         FP.DEFER_SKIP = True
     assert G.rel_linf(y.float().cpu(), y0.float().cpu()) <= 8e-3
+
+
+def test_gate_stack_budget_chunks_the_batch():
+    """A batch whose gate stack (layers x batch x frames x channels x 2 bytes) exceeds the budget is walked in batch
+    chunks; one read that does not fit falls back to the in-HBM running sum.  Same bits either way."""
+    torch.manual_seed(23)
+    C = 128
+    layers = [(C, C, 2, d) for d in (1, 2, 4)]
+    net = W.RawCTCNet(C, 3, 5, layers, C, softmax=False).cuda().bfloat16().eval()
+    x = torch.randn(5, 1, 700, device="cuda").bfloat16()
+    with torch.no_grad():
+        ref = net(x)
+        old = FP.GATE_STACK_BUDGET
+        try:
+            FP.GATE_STACK_BUDGET = 4 * 2 * 702 * C * 2 + 1            # room for two reads of the 4-block stack
+            y = net(x)
+            one = net(x[:1])                                          # a single read does not fit: running-sum pipeline
+        finally:
+            FP.GATE_STACK_BUDGET = old
+    assert torch.equal(y, ref)
+    assert G.rel_linf(one.float().cpu(), ref[:1].float().cpu()) <= 8e-3

@@ -169,6 +169,8 @@ def invalidate_packs(module):
     from outside torch -- are not.  Call this after such an update."""
     for m in module.modules():
         m.__dict__.pop("_wnb_pack_cache", None)
+    from . import functional
+    functional.clear_layout_cache()
 
 
 def _cached(module, name, build):
@@ -391,11 +393,28 @@ def skip_pack(packs):
     return wcat, bsum
 
 
+GATE_STACK_BUDGET = 48 << 30      # bytes; also capped at half of the free device memory
+
+
+def _gate_stack_budget(dev):
+    free, _total = torch.cuda.mem_get_info(dev)
+    return min(GATE_STACK_BUDGET, free // 2)
+
+
 def run_blocks_deferred(h, packs, skip, h_lo=None):
     """Residual stack with the skip sum deferred (resblock3_kernel + one `nlayers` contraction): returns the head's
-    input LeakyReLU(skip sum) as an NLC tensor in the packs' format.  The running sum never exists in HBM."""
+    input LeakyReLU(skip sum) as an NLC tensor in the packs' format.  The running sum never exists in HBM.
+    The gate stack costs L x B x T x C x 2 bytes (5.4 GB for config 2, 33.6 GB for the ecoli RawCTCNet at B = 1024): a
+    batch whose stack would not fit the budget is walked in batch chunks (reads are independent)."""
     B, T, C = h.shape
     L = len(packs)
+    need = L * B * T * C * 2
+    budget = _gate_stack_budget(h.device)
+    if need > budget and B > 1:
+        nchunk = min(B, -(-need // max(budget, 1)))
+        bounds = [(B * i // nchunk, B * (i + 1) // nchunk) for i in range(nchunk)]
+        outs = [run_blocks_deferred(h[s:e], packs, skip, None if h_lo is None else h_lo[s:e]) for s, e in bounds if e > s]
+        return torch.cat(outs, 0)
     prec = packs[0].get("fmt", 0) == _lib.ACT_F16X2
     gates = torch.empty((L, B, T, C), dtype=h.dtype, device=h.device)
     buf = [h, torch.empty_like(h)]
@@ -417,7 +436,9 @@ def run_blocks(h, blocks, bottlenecks, packs, skips, first_init, want_act, h_lo=
     Precise packs: `h` is the hi half of the fp16 stream, `h_lo` its lo half (None: the input is exactly `h`).
     skip = skip_pack(packs): use the deferred-skip pipeline (inference default for C = 128 / 256)."""
     B, T, C = h.shape
-    if skip is not None and DEFER_SKIP and want_act and C in (128, 256) and RESBLOCK_VARIANT != 1:
+    if skip is not None and DEFER_SKIP and want_act and C in (128, 256) and RESBLOCK_VARIANT != 1 and (
+            B > 1 or len(packs) * T * C * 2 <= _gate_stack_budget(h.device)):
+        # (one read whose gate stack does not fit -- tens of millions of frames -- keeps the running sum in HBM instead)
         return None, run_blocks_deferred(h, packs, skip, h_lo=h_lo)
     if skips is None:
         skips = torch.empty((B, T, C), dtype=torch.float32, device=h.device)

@@ -25,23 +25,73 @@ def tap_offsets(k, d, causal):
 
 
 # --------------------------------------------------------------------------- weight re-layouts
+# The kernels want one contiguous [rows, C] slab per tap.  Re-laying the weights out on every call was most of what the
+# generic path launched in inference (round 1's smoke: 93 libwnb200 kernels among 242 ATen copies / fills / cats): the
+# layouts are cached per tensor and rebuilt when its (data_ptr, _version) changes, like the tensor-core packs
+# (`fastpath.invalidate_packs` also clears this cache, for writes through `.data` that bypass the version counter).
+import weakref
+
+_LAYOUTS = {}      # id(tensor) -> (weakref to it, {(kind, dtype): (version key, layout)}); entries die with the tensor
+                   # (a WeakKeyDictionary would compare tensors with ==, which is element-wise)
+
+
+def clear_layout_cache():
+    _LAYOUTS.clear()
+
+
+def _layout_slot(owner):
+    k = id(owner)
+    ent = _LAYOUTS.get(k)
+    if ent is None or ent[0]() is not owner:
+        def _gone(ref, k=k):
+            cur = _LAYOUTS.get(k)
+            if cur is not None and cur[0] is ref:
+                _LAYOUTS.pop(k, None)
+        ent = (weakref.ref(owner, _gone), {})
+        _LAYOUTS[k] = ent
+    return ent[1]
+
+
+def _cached_layout(key_tensors, kind, dtype, build):
+    """build() cached on the identity and version of every tensor in key_tensors (the first one owns the entry)."""
+    owner = key_tensors[0]
+    if torch.is_grad_enabled() and any(t.requires_grad for t in key_tensors if t is not None):
+        return build()                     # training: the weights change every step, caching would only hold memory
+    ver = tuple((None if t is None else (t.data_ptr(), t._version, t.dtype)) for t in key_tensors)
+    try:
+        slot = _layout_slot(owner)
+    except TypeError:                      # not weak-referenceable: no caching
+        return build()
+    hit = slot.get((kind, dtype))
+    if hit is None or hit[0] != ver:
+        hit = (ver, build())
+        slot[(kind, dtype)] = hit
+    return hit[1]
+
+
 def _slabs(w, dtype):
     """[M, C, k] (or [M, C]) -> [k, M, C] contiguous in the compute dtype."""
-    if w.dim() == 2:
-        w = w.unsqueeze(2)
-    return w.detach().to(dtype).permute(2, 0, 1).contiguous()
+    def build():
+        ww = w.unsqueeze(2) if w.dim() == 2 else w
+        return ww.detach().to(dtype).permute(2, 0, 1).contiguous()
+    return _cached_layout([w], "slabs", dtype, build)
 
 
 def _slabs_t(w, dtype):
     """[M, C, k] -> [k, C, M] contiguous (transposed slabs for the data gradient)."""
-    if w.dim() == 2:
-        w = w.unsqueeze(2)
-    return w.detach().to(dtype).permute(2, 1, 0).contiguous()
+    def build():
+        ww = w.unsqueeze(2) if w.dim() == 2 else w
+        return ww.detach().to(dtype).permute(2, 1, 0).contiguous()
+    return _cached_layout([w], "slabs_t", dtype, build)
 
 
 def _pack_gate(wt, ws, bt, bs, dtype):
     """Interleave tanh / sigmoid filters per 64 output channels: rows [128i, 128i+64) = tanh
     channels 64i.., rows [128i+64, 128i+128) = sigmoid channels 64i.. (see wnb200.h, EPI_GATE)."""
+    return _cached_layout([wt, ws, bt, bs], "gate", dtype, lambda: _pack_gate_build(wt, ws, bt, bs, dtype))
+
+
+def _pack_gate_build(wt, ws, bt, bs, dtype):
     M, C, k = wt.shape
     Mp = (M + 63) // 64 * 64
     nb = Mp // 64
@@ -64,7 +114,11 @@ def _pack_gate(wt, ws, bt, bs, dtype):
 
 
 def _f32(b):
-    return None if b is None else b.detach().float().contiguous()
+    if b is None:
+        return None
+    if b.dtype == torch.float32 and b.is_contiguous():
+        return b.detach()                  # no copy: the kernels read the parameter in place
+    return _cached_layout([b], "f32", torch.float32, lambda: b.detach().float().contiguous())
 
 
 # --------------------------------------------------------------------------- generic conv
