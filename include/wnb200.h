@@ -238,6 +238,9 @@ typedef struct {
                              sum_l (Wbn_l Wskip_l) gate_l + biases, is left to ONE wnb200_dense_fwd_tc call with
                              `nlayers` over the stacked gates (K = layers x channels, accumulated in tensor memory).
                              res = NULL on the last layer skips the residual contraction altogether. */
+  int32_t* sat_flag;      /* optional (F16X2 with gate_out): device int that is OR-ed with 1 when a value of the output
+                             stream reached the end of the fp16 range (|v| >= 65504: stored saturated, not inf).  The
+                             host falls back to WNB200_ACT_BF16 for such a model (fastpath.py). */
 } wnb200_resblock_t;
 int wnb200_resblock_fwd_tc(const wnb200_resblock_t* args /*host*/, void* stream);
 

@@ -275,3 +275,38 @@ def test_gate_stack_budget_chunks_the_batch():
             FP.GATE_STACK_BUDGET = old
     assert torch.equal(y, ref)
     assert G.rel_linf(one.float().cpu(), ref[:1].float().cpu()) <= 8e-3
+
+
+def test_fp16_range_guard_falls_back_to_bf16_format():
+    """A stream that leaves the fp16 range (here: the projections scaled so that it grows 30x per block) raises the block
+    kernel's saturation flag; the first forward of that weight version notices, warns, and repeats in the bf16 format
+    -- the result is bitwise the tc_precision("fast") one and finite -- and the model stays on that format until its
+    weights change.  A well-scaled model never warns and is marked verified after one forward."""
+    import warnings
+    torch.manual_seed(5)
+    C = 128
+    layers = [(C, C, 2, d) for d in (1, 2, 4, 8, 16, 32)]
+    net = W.WaveNet(C, 2, layers, C, softmax=False).cuda().bfloat16().eval()
+    x = torch.randn(2, C, 600, device="cuda").bfloat16()
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("error", RuntimeWarning)
+        y_ok = net(x)
+        assert FP.stream_saturated(net) is False
+        saved = [b.residual_proj.weight.clone() for b in net.convolutions]
+        for b in net.convolutions:
+            b.residual_proj.weight.mul_(30.0)
+    with torch.no_grad():
+        with FP.tc_precision("fast"):
+            y_fast = net(x)
+        with pytest.warns(RuntimeWarning, match="fp16 range"):
+            y = net(x)
+        assert FP.stream_saturated(net) is True
+        assert torch.isfinite(y.float()).all() and float(y.float().abs().max()) > 0
+        assert torch.equal(y, y_fast)
+        with warnings.catch_warnings():
+            warnings.simplefilter("error", RuntimeWarning)
+            assert torch.equal(net(x), y_fast)             # remembered: no second warning, no precise attempt
+            for b, w in zip(net.convolutions, saved):
+                b.residual_proj.weight.copy_(w)
+            assert torch.equal(net(x), y_ok)               # new weight version: precise again
+            assert FP.stream_saturated(net) is False

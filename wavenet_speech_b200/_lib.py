@@ -51,7 +51,8 @@ class ResBlock(_Sized):
                 ("act_fmt", ctypes.c_int32), ("x", c_void_p), ("w1", c_void_p),
                 ("bias1", c_void_p), ("w2", c_void_p), ("bias2", c_void_p), ("res", c_void_p), ("skips", c_void_p),
                 ("dbg", c_void_p), ("save_act", c_void_p), ("save_th", c_void_p), ("save_sg", c_void_p),
-                ("skips_act", c_void_p), ("x_lo", c_void_p), ("res_lo", c_void_p), ("gate_out", c_void_p)]
+                ("skips_act", c_void_p), ("x_lo", c_void_p), ("res_lo", c_void_p), ("gate_out", c_void_p),
+                ("sat_flag", c_void_p)]
 
 
 class Dense(_Sized):

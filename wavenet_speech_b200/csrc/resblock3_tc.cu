@@ -38,6 +38,7 @@ struct Res3Dev {
   const float* bias1;   // [2C] packed like W1 rows (pre-scaled in the fp16 format)
   const float* bias2;   // [>= C] bres + bproj
   int write_res, has_lo;
+  int* sat_flag;        // optional: set to 1 when a stream value left the fp16 range (the hi half saturated)
 };
 
 constexpr int R3_THREADS = 320;
@@ -384,8 +385,15 @@ resblock3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         uint32_t pk[16];
         if constexpr (PREC) {
           uint32_t pl[16];
+          uint32_t sat = 0;
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) split_f16x2(a[i] + bv[i], a[i + 1] + bv[i + 1], pk[i >> 1], pl[i >> 1]);
+          for (int i = 0; i < 32; i += 2) {
+            split_f16x2(a[i] + bv[i], a[i + 1] + bv[i + 1], pk[i >> 1], pl[i >> 1]);
+            // |hi| = 65504 (0x7bff): the value was at or beyond the fp16 range (cvt.satfinite clamps instead of inf)
+            const uint32_t m = pk[i >> 1] & 0x7fff7fffu;
+            sat |= (uint32_t)((m & 0xffffu) == 0x7bffu) | (uint32_t)((m >> 16) == 0x7bffu);
+          }
+          if (sat && p.sat_flag) atomicOr(p.sat_flag, 1);
           if (issuer) bulk_wait_read0();
           epi_bar();
           uint8_t* srow = smem_gen + (stg_base - smem_base) + row * 128;
@@ -468,6 +476,7 @@ int resblock3_launch(const wnb200_resblock_t* a, void* stream) {
   p.bias1 = a->bias1; p.bias2 = a->bias2;
   p.write_res = a->res != nullptr;
   p.has_lo = prec && a->x_lo != nullptr;
+  p.sat_flag = prec ? reinterpret_cast<int*>(a->sat_flag) : nullptr;
   CUtensorMap mx, mw1, mw2, mres, mgate, mxlo, mreslo;
   int rc;
   if ((rc = rb_map_nlc(&mx, a->x, a->B, a->T, C, 2))) return rc;

@@ -62,9 +62,106 @@ class tc_precision(object):
         return False
 
 
-def precise_mode(C):
-    """The fp16 (hi, lo) format runs on the CTA-pair kernels only (C = 128 / 256)."""
-    return _PRECISE and C in (128, 256) and RESBLOCK_VARIANT != 1
+# ---- range guard of the precise format ---------------------------------------------------------------------------
+# fp16 ends at 65504.  With the reference's initialisation the stream grows ~1.45x per block: 20 blocks reach ~1.5e3, but a
+# 30-block 256-channel stack (the reference's tests/test_classifier.py shape) is at the limit and deeper ones beyond it.
+# The block kernel stores saturated values (never inf) and raises a device flag; here the flag is read synchronously on
+# the FIRST precise forward of every weight version (depth / initialisation problems show up there) -- if it is set the
+# forward is repeated in the bf16 format and the model stays on it -- and asynchronously afterwards (a later,
+# data-dependent overflow switches the model over from the next call on, with a warning).
+_sat_ctx = None
+
+
+def _sat_state(model, dev):
+    st = model.__dict__.get("_wnb_sat")
+    if st is None or st["flag"].device != dev:
+        st = {"flag": torch.zeros(1, dtype=torch.int32, device=dev), "pinned": torch.zeros(1, dtype=torch.int32).pin_memory(),
+              "event": None, "verified": None, "fast_key": None, "ran": False}
+        model.__dict__["_wnb_sat"] = st
+    return st
+
+
+def _warn_saturated(model):
+    import warnings
+    warnings.warn("wavenet_speech_b200: the residual stream of %s left the fp16 range (|x| >= 65504) in the precise "
+                  "tensor-core format; this model now runs in the bf16 format (tc_precision('fast') accuracy)"
+                  % type(model).__name__, RuntimeWarning, stacklevel=3)
+
+
+def precise_mode(C, model=None, dev=None):
+    """The fp16 (hi, lo) format runs on the CTA-pair kernels only (C = 128 / 256).  With `model`: also consults / arms
+    the range guard above (a model whose stream saturated fp16 stays on the bf16 format for that weight version)."""
+    global _sat_ctx
+    _sat_ctx = None
+    ok = _PRECISE and C in (128, 256) and RESBLOCK_VARIANT != 1
+    if not ok or model is None or dev is None:
+        return ok
+    key = _version_key(model)
+    if torch.cuda.is_current_stream_capturing():
+        # no allocations, event queries or read-backs inside a capture: a graph replays the format its warm-up chose
+        # (GraphedForward warms up first); captured without a verified warm-up, the forward runs unguarded.
+        st = model.__dict__.get("_wnb_sat")
+        if st is not None and st["flag"].device == dev and st["fast_key"] == key:
+            return False
+        if st is not None and st["flag"].device == dev and st["verified"] == key:
+            st["key"] = key
+            _sat_ctx = st
+        return True
+    st = _sat_state(model, dev)
+    if st["event"] is not None and st["event"].query():          # an earlier forward's asynchronous read-back
+        st["event"] = None
+        if int(st["pinned"][0]) != 0 and st["fast_key"] != key:
+            st["fast_key"] = key
+            _warn_saturated(model)
+    if st["fast_key"] == key:
+        return False
+    if st["fast_key"] is not None or st["verified"] not in (None, key):     # new weights: start over
+        st["fast_key"] = None
+        st["verified"] = None
+        st["flag"].zero_()
+    st["key"] = key
+    _sat_ctx = st
+    return True
+
+
+def stream_saturated(model):
+    """True if the last checked forward of `model` (current weights) left the fp16 range and the model was moved to the
+    bf16 format; False if its precise forward was verified in range; None if it has not run in the precise format."""
+    st = model.__dict__.get("_wnb_sat")
+    if st is None:
+        return None
+    key = _version_key(model)
+    if st["fast_key"] == key:
+        return True
+    return False if st["verified"] == key else None
+
+
+def range_guard(fn):
+    """Wraps a try_*_forward: after a precise forward, act on the saturation flag (see above)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(model, x, *a, **k):
+        global _sat_ctx
+        y = fn(model, x, *a, **k)
+        st, _sat_ctx = _sat_ctx, None
+        if y is None or st is None or not st["ran"]:
+            return y
+        st["ran"] = False
+        if torch.cuda.is_current_stream_capturing():
+            return y
+        if st["verified"] != st["key"]:
+            if int(st["flag"].item()) != 0:                      # one synchronisation per weight version
+                st["fast_key"] = st["key"]
+                _warn_saturated(model)
+                return fn(model, x, *a, **k)                     # precise_mode() now answers False for this model
+            st["verified"] = st["key"]
+        elif st["event"] is None:
+            st["pinned"].copy_(st["flag"], non_blocking=True)
+            st["event"] = torch.cuda.Event()
+            st["event"].record()
+        return y
+    return wrapper
 
 
 def _taps_matrix(w):
@@ -212,7 +309,7 @@ FUSE_FINAL = True     # last layer of an inference stack emits LeakyReLU(skip su
 
 
 def resblock(x_nlc, pk, res, skips, skips_init, dbg=None, variant=None, save=None, skips_act=None, x_lo=None,
-             res_lo=None, gate_out=None):
+             res_lo=None, gate_out=None, sat_flag=None):
     """Pipelined fused block (C = 128 / 256).  variant 0/2 = CTA-pair kernel, 1 = single-CTA kernel.
     save = (gate, th, sg) NLC bf16 buffers: training keeps the gate and its two factors for backward.
     x_lo / res_lo: low halves of the fp16 (hi, lo) stream when the pack is a `precise` one."""
@@ -232,6 +329,7 @@ def resblock(x_nlc, pk, res, skips, skips_init, dbg=None, variant=None, save=Non
     a.act_fmt = pk.get("fmt", _lib.ACT_BF16)
     a.x_lo, a.res_lo = p(x_lo), p(res_lo)
     a.gate_out = p(gate_out)
+    a.sat_flag = p(sat_flag)
     _lib.current_tag = "resblock"
     try:
         _lib.call("wnb200_resblock_fwd_tc", ctypes.byref(a), ops._stream())
@@ -419,10 +517,14 @@ def run_blocks_deferred(h, packs, skip, h_lo=None):
     gates = torch.empty((L, B, T, C), dtype=h.dtype, device=h.device)
     buf = [h, torch.empty_like(h)]
     lo = [h_lo, torch.empty_like(h)] if prec else [None, None]
+    sat = None
+    if prec and _sat_ctx is not None:
+        sat = _sat_ctx["flag"]
+        _sat_ctx["ran"] = True
     for l, pk in enumerate(packs):
         last = l == L - 1
         resblock(buf[0], pk, None if last else buf[1], None, False, x_lo=lo[0],
-                 res_lo=None if (last or not prec) else lo[1], gate_out=gates[l])
+                 res_lo=None if (last or not prec) else lo[1], gate_out=gates[l], sat_flag=sat)
         if not last:
             buf = [buf[1], buf[0]]
             if prec:
@@ -487,6 +589,7 @@ def run_head(skips_act, hd, out_dtype, softmax):
     return dense(h1, [0], hd["w2"], hd["b2"], hd["n2"], mode=1, out=out, n_out=hd["n_out"], softmax=softmax, fmt=fmt)
 
 
+@range_guard
 def try_wavenet_forward(model, signal):
     """WaveNet.forward (reference wavenet.py:88-111) on the tensor-core path, or None if not eligible."""
     if not tc_dtype_ok(signal) or not signal.is_cuda or signal.dim() != 3:
@@ -499,7 +602,7 @@ def try_wavenet_forward(model, signal):
             and model.entry_kwidth <= 3 and signal.shape[0] > 0 and signal.shape[2] > 0):
         return None
     ops.check_device()
-    prec = precise_mode(C)
+    prec = precise_mode(C, model, signal.device)
     cast = _f16 if prec else _bf16
     fmt = _lib.ACT_F16X2 if prec else _lib.ACT_BF16
 
@@ -523,6 +626,7 @@ def try_wavenet_forward(model, signal):
     return run_head(skips_act, pk["head"], signal.dtype, model.softmax)
 
 
+@range_guard
 def wavenet_forward_levels(model, levels, out_dtype=torch.bfloat16):
     """WaveNet.forward(one_hot(levels)) without materialising the one-hot tensor: `levels` (B, T) integers in
     [0, in_dim) -- what pore_model.py:78-86 / np.digitize produce before the one-hot step (pore_model.py:88-96).  The entry
@@ -535,7 +639,7 @@ def wavenet_forward_levels(model, levels, out_dtype=torch.bfloat16):
         raise RuntimeError("forward_levels: this WaveNet is not eligible for the tensor-core path "
                            "(in_dim = C = out_dim in {128, 256}, kernel widths <= 3)")
     ops.check_device()
-    prec = precise_mode(C)
+    prec = precise_mode(C, model, levels.device)
     cast = _f16 if prec else _bf16
     fmt = _lib.ACT_F16X2 if prec else _lib.ACT_BF16
 
@@ -575,6 +679,7 @@ def _stack_packs(model, precise=False):
     return packs
 
 
+@range_guard
 def try_raw_ctcnet_forward(model, seq):
     """RawCTCNet.forward (reference raw_ctcnet.py:117-153) on the tensor-core path, or None if not eligible."""
     if not tc_dtype_ok(seq) or not seq.is_cuda or seq.dim() != 3 or seq.shape[1] != 1:
@@ -588,7 +693,7 @@ def try_raw_ctcnet_forward(model, seq):
             and seq.shape[0] > 0 and seq.shape[2] > 0):
         return None
     ops.check_device()
-    prec = precise_mode(C)
+    prec = precise_mode(C, model, seq.device)
     cast = _f16 if prec else _bf16
     fmt = _lib.ACT_F16X2 if prec else _lib.ACT_BF16
 
@@ -615,6 +720,7 @@ def try_raw_ctcnet_forward(model, seq):
     return run_head(skips_act, pk["head"], seq.dtype, model.softmax)
 
 
+@range_guard
 def try_classifier_forward(model, seq):
     """WaveNetClassifier.forward (reference classifier.py:91-120) on the tensor-core path, or None."""
     if not tc_dtype_ok(seq) or not seq.is_cuda or seq.dim() != 3:
@@ -629,7 +735,7 @@ def try_classifier_forward(model, seq):
             and seq.shape[2] // pool > 0):
         return None
     ops.check_device()
-    prec = precise_mode(C)
+    prec = precise_mode(C, model, seq.device)
     fmt = _lib.ACT_F16X2 if prec else _lib.ACT_BF16
     pk = _with_skip(_cached(model, "classifier_p" if prec else "classifier",
                             lambda: {"blocks": _stack_packs(model, prec), "head": pack_head(model.output_block, C, prec)}))
