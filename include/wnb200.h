@@ -208,8 +208,9 @@ int wnb200_chain_fwd_tc(const wnb200_chain_t* args /*host*/, void* stream);
  *   b1   fp32 [2C] in the same row order
  *   w2   bf16 [2C][2C] = [[Wres, Wproj], [Wbn*Wskip, 0]];   b2 fp32 [2C] = [bres+bproj ; Wbn*bskip+bbn]
  *   res  bf16 NLC [B,T,C] or NULL (last layer: not needed);  skips fp32 NLC [B,T,C].
- * Two ways to get the skip sum (wavenet.py:97-100): `skips` accumulated in HBM by every call (TMA reduce-add; the training
- * forward and the single-CTA kernel), or `gate_out` (deferred: see the field) -- the inference default. */
+ * Two ways to get the skip sum (wavenet.py:97-100): `skips` accumulated in HBM by every call (TMA reduce-add; the
+ * single-CTA kernel and the round-1 pipeline), or `gate_out` (deferred: see the field) -- the default of the inference
+ * AND the training forward (training adds `save_sg`: the gate stack is also what backward reads). */
 typedef struct {
   uint32_t struct_size;   /* = sizeof(wnb200_resblock_t) */
   int32_t B, T, C, ntaps;
@@ -228,12 +229,13 @@ typedef struct {
   void* dbg;              /* optional int64[8*16] timeline buffer */
   void* save_act;         /* optional (training): the gate tanh(.)*sigmoid(.), NLC bf16 [B,T,C] ...                 */
   void* save_th;          /* ... optionally tanh(.) (NULL: not kept -- backward derives it as gate / sigmoid) ...      */
-  void* save_sg;          /* ... and sigmoid(.) (required with save_act)                                              */
+  void* save_sg;          /* ... and sigmoid(.) (required with save_act; with gate_out it is the only save_* allowed:
+                             the stored gate is the saved activation)                                                 */
   void* skips_act;        /* optional (last layer of an inference stack, res = NULL): NLC bf16 [B,T,C] that receives
                              LeakyReLU(skips + contribution) (wavenet.py:100-103); `skips` is then read, not updated */
   const void* x_lo;       /* F16X2: lo half of the input stream, NLC fp16 [B,T,C]; NULL = the input is exactly x */
   void* res_lo;           /* F16X2: lo half of the output stream (required when res != NULL) */
-  void* gate_out;         /* optional (inference): NLC [B,T,C] in act_fmt that receives the gate tanh(.)*sigmoid(.).  When
+  void* gate_out;         /* optional: NLC [B,T,C] in act_fmt that receives the gate tanh(.)*sigmoid(.).  When
                              given, the call does NOT touch `skips` (may be NULL): the skip sum of the whole stack,
                              sum_l (Wbn_l Wskip_l) gate_l + biases, is left to ONE wnb200_dense_fwd_tc call with
                              `nlayers` over the stacked gates (K = layers x channels, accumulated in tensor memory).
@@ -272,6 +274,12 @@ typedef struct {
                              accumulated in tensor memory over K = layers x channels (wavenet.py:97-100) */
   void* y_lo;             /* F16X2, mode 0, optional: y leaves as an fp16 (hi, lo) pair (y, y_lo) -- the producer of a
                              residual stream (entry conv, RawCTCNet feature 1x1) */
+  const void* gb_gate;    /* BF16, mode 0, optional (training): gate-backward epilogue.  The contraction's result is
+                             d(gate) of a residual block (block.py:66-71 backwards); with the forward's stored gate =
+                             tanh*sigmoid and ... */
+  const void* gb_sg;      /* ... sigmoid (both NLC bf16 [B,T,N], 16-byte aligned), y is NLC bf16 [B,T,2N]:
+                             y[..,0:N] = d * sg * (1 - th^2), y[..,N:2N] = d * th * sg * (1 - sg), th = gate / sg;
+                             colsum is then fp32 [2N].  Replaces wnb200_gate_bwd_nlc_from_gate + one HBM round trip. */
 } wnb200_dense_t;
 int wnb200_dense_fwd_tc(const wnb200_dense_t* args /*host*/, void* stream);
 

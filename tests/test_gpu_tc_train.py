@@ -466,3 +466,105 @@ def test_loss_curve_tracks_the_oracle_over_20_steps():
     assert ref_curve[-1] < ref_curve[0] and curve[-1] < curve[0]
     worst = max(abs(a - b) / abs(b) for a, b in zip(curve, ref_curve))
     assert worst <= 2e-2, (worst, curve, ref_curve)
+
+
+@pytest.mark.parametrize("C,T,B", [(256, 777, 2), (128, 300, 3)])
+def test_training_forward_deferred_skip_equals_running_sum(C, T, B):
+    """The training forward on the deferred-skip kernel (gate stack + sigmoid kept, ONE skip contraction over
+    K = layers x channels) against the round-1 pipeline (fp32 running sum in HBM, FP.DEFER_SKIP = False): the same
+    saved activations bit for bit (same gate arithmetic), outputs and gradients within bf16 rounding of each other."""
+    torch.manual_seed(C + T)
+    layers = [(C, C, 2, d) for d in (1, 2, 4, 8, 16)]
+    net = W.WaveNet(C, 2, layers, C, softmax=False).cuda()
+    x = torch.randn(B, C, T, device="cuda").bfloat16()
+    R = torch.randn(B, C, T, device="cuda")
+
+    def run():
+        net.zero_grad(set_to_none=True)
+        y = net(x)
+        assert type(y.grad_fn).__name__.startswith("_WaveNetTrain")
+        (y.float() * R).sum().backward()
+        return y.detach().float().cpu(), {n: p.grad.detach().float().cpu() for n, p in net.named_parameters()
+                                              if p.grad is not None}
+
+    assert FP.DEFER_SKIP
+    y1, g1 = run()
+    FP.DEFER_SKIP = False
+    try:
+        y0, g0 = run()
+    finally:
+        FP.DEFER_SKIP = True
+    assert G.rel_linf(y1, y0) <= 1e-2, G.rel_linf(y1, y0)
+    for n in g0:
+        assert G.rel_l2(g1[n], g0[n]) <= 3e-2, (n, G.rel_l2(g1[n], g0[n]))
+    # saved activations: gate and sigmoid of a layer are identical in both pipelines
+    pk = TR._wavenet_pack(net)
+    h0 = FP.dense(FP.ncl_to_nlc_bf16(x), list(net.entry_conv1d.offsets), pk["entry_w"], pk["entry_b"], C)
+    s1, a1 = TR.stack_forward(h0, pk["stack"], torch.empty((B, T, C), dtype=torch.float32, device="cuda"))
+    FP.DEFER_SKIP = False
+    try:
+        s0, a0 = TR.stack_forward(h0, pk["stack"], torch.empty((B, T, C), dtype=torch.float32, device="cuda"))
+    finally:
+        FP.DEFER_SKIP = True
+    for (xa, ga, sa), (xb, gb, sb) in zip(s1, s0):
+        assert torch.equal(xa, xb) and torch.equal(ga, gb) and torch.equal(sa, sb)
+    assert G.rel_linf(a1.float().cpu(), a0.float().cpu()) <= 1e-2
+
+
+@pytest.mark.parametrize("N,T,B,two", [(256, 300, 2, True), (128, 257, 3, True), (256, 129, 1, False)])
+def test_dense_gate_backward_epilogue(N, T, B, two):
+    """The d(gate) contraction with the gate's backward in its epilogue (wnb200_dense_t.gb_gate / gb_sg) against an
+    fp32 evaluation of block.py:66-71 backwards on the same bf16 inputs: dab [B,T,2N] within bf16 rounding, the bias
+    gradients (column sums of the stored tile) within 1e-2; and against the two-launch path it replaces."""
+    torch.manual_seed(N + T)
+    dres = r16(torch.randn(B, T, N)).cuda().bfloat16()
+    dsk = r16(torch.randn(B, T, N)).cuda().bfloat16()
+    w = r16(torch.randn(N, 2 * N if two else N) / (2 * N) ** 0.5).cuda().bfloat16()
+    th = torch.tanh(torch.randn(B, T, N) * 1.5)
+    sg = torch.sigmoid(torch.randn(B, T, N) * 2.0).bfloat16()
+    gate = (th * sg.float()).bfloat16()
+    gate, sg = gate.cuda(), sg.cuda()
+    zb = torch.zeros(N, device="cuda")
+    cs = torch.zeros(2 * N, device="cuda")
+    if two:
+        dab = FP.dense(dres, [0], w, zb, N, x2=dsk, offsets2=[0], gate_bwd=(gate, sg), colsum=cs)
+        dg = FP.dense(dres, [0], w, zb, N, x2=dsk, offsets2=[0])
+        dgf = torch.cat([dres, dsk], 2).float() @ w.float().t()
+    else:
+        dab = FP.dense(dres, [0], w, zb, N, gate_bwd=(gate, sg), colsum=cs)
+        dg = FP.dense(dres, [0], w, zb, N)
+        dgf = dres.float() @ w.float().t()
+    assert dab.shape == (B, T, 2 * N)
+    s = sg.float()
+    t = torch.where(s > 0, (gate.float() / s).clamp(-1, 1), torch.zeros_like(s))
+    ref = torch.cat([dgf * s * (1 - t * t), dgf * t * s * (1 - s)], 2)
+    assert G.rel_linf(dab.float().cpu(), ref.cpu()) <= 1e-2
+    assert G.rel_linf(cs.cpu(), ref.sum((0, 1)).cpu()) <= 1e-2
+    dab2, cs2 = TR.gate_bwd_nlc(dg, gate, sg, want_bias=True, th_is_gate=True)
+    assert G.rel_linf(dab.float().cpu(), dab2.float().cpu()) <= 1.5e-2          # (that path rounds d(gate) to bf16 first)
+    assert G.rel_linf(cs.cpu(), cs2.cpu()) <= 1e-2
+
+
+def test_fused_gate_backward_gives_the_same_gradients():
+    """TR.FUSE_GATE_BWD routes the d(gate) contractions through the gate-backward epilogue: same gradients as the
+    two-launch default (which rounds d(gate) to bf16 in between) within bf16 rounding."""
+    torch.manual_seed(9)
+    C, T, B = 256, 515, 2
+    net = W.WaveNet(C, 2, [(C, C, 2, d) for d in (1, 2, 4, 8)], C, softmax=False).cuda()
+    x = torch.randn(B, C, T, device="cuda").bfloat16()
+    R = torch.randn(B, C, T, device="cuda")
+
+    def run():
+        net.zero_grad(set_to_none=True)
+        (net(x).float() * R).sum().backward()
+        return {n: p.grad.detach().float().cpu() for n, p in net.named_parameters() if p.grad is not None}
+
+    assert not TR.FUSE_GATE_BWD
+    g0 = run()
+    TR.FUSE_GATE_BWD = True
+    try:
+        g1 = run()
+    finally:
+        TR.FUSE_GATE_BWD = False
+    for n in g0:
+        assert G.rel_l2(g1[n], g0[n]) <= 1e-2, (n, G.rel_l2(g1[n], g0[n]))

@@ -64,7 +64,8 @@ class Dense(_Sized):
                 ("out_f32", ctypes.c_int32), ("Cin2", ctypes.c_int32), ("ntaps2", ctypes.c_int32),
                 ("t_off2", ctypes.c_int32 * 3), ("x", c_void_p), ("w", c_void_p),
                 ("bias", c_void_p), ("y", c_void_p), ("x2", c_void_p), ("colsum", c_void_p),
-                ("act_fmt", ctypes.c_int32), ("nlayers", ctypes.c_int32), ("y_lo", c_void_p)]
+                ("act_fmt", ctypes.c_int32), ("nlayers", ctypes.c_int32), ("y_lo", c_void_p),
+                ("gb_gate", c_void_p), ("gb_sg", c_void_p)]
 
 
 class PackBlock(_Sized):

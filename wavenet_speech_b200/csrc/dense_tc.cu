@@ -44,6 +44,8 @@ struct DenseDev {
   int f16;          // operands (and NLC output) are fp16 instead of bf16 (WNB200_ACT_F16X2)
   int split;        // NLC mode, fp16: the output leaves as an fp16 (hi, lo) pair (map_y, map_ylo)
   int nlayers;      // > 0: x is a stack [nlayers][B][T][Cin] and K runs over (layer, channel): y = sum_l W_l x_l (+ bias)
+  const bf16* gb_gate;   // gate-backward epilogue (training, NLC mode, bf16): acc is d(gate); with the forward's gate and
+  const bf16* gb_sg;     // sigmoid (NLC [B,T,N]) y[.., 0:N] = d(tanh pre-act), y[.., N:2N] = d(sigmoid pre-act); colsum [2N]
 };
 
 constexpr int DN_THREADS = 320;
@@ -53,7 +55,8 @@ constexpr int DN_NSTAGE = 5;
 constexpr int DN_STAGING = 2 * DN_ABYTES;
 constexpr int DN_SCRATCH = 2 * RB_TILE * 8;    // softmax partials (max, sum) per column half
 constexpr int DN_BIAS = 256 * 4;                // head: bias (x log2 e under softmax) staged once per CTA
-constexpr int DN_SMEM = DN_NSTAGE * DN_STAGE + DN_STAGING + DN_SCRATCH + DN_BIAS + 1024 + 256;
+constexpr int DN_CSACC = 8 * 512 * 4;           // gate-backward epilogue: per-warp column sums of the 2N outputs
+constexpr int DN_SMEM = DN_NSTAGE * DN_STAGE + DN_STAGING + DN_SCRATCH + DN_BIAS + DN_CSACC + 1024 + 256;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DN_THREADS, 1)
 dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_x2,
@@ -65,7 +68,8 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   const uint32_t stg_base = smem_base + DN_NSTAGE * DN_STAGE;
   const uint32_t scr_base = stg_base + DN_STAGING;
   const uint32_t sbias_base = scr_base + DN_SCRATCH;
-  const uint32_t bar_base = sbias_base + DN_BIAS;
+  const uint32_t csacc_base = sbias_base + DN_BIAS;
+  const uint32_t bar_base = csacc_base + DN_CSACC;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (DN_NSTAGE + s); };
   const uint32_t bb = bar_base + 8u * (2 * DN_NSTAGE);
@@ -79,6 +83,9 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   const int nkb1 = (p.nlayers > 0 ? p.nlayers : p.ntaps) * p.kb_per_tap;
   const int nkb = nkb1 + p.ntaps2 * p.kb_per_tap2;
   const uint32_t bhalf_bytes = (uint32_t)(p.N / 2) * 128u;
+  // the gate-backward epilogue stages two tiles per chunk and wants them double-buffered: it runs a 4-deep ring and
+  // uses the fifth stage's 32 KB as its second staging pair (K = 2C there: eight K-blocks per tile)
+  const int NST = p.gb_gate ? DN_NSTAGE - 1 : DN_NSTAGE;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&map_x);
@@ -128,7 +135,7 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
           }
           tma_load_2d_2sm(sa + DN_ABYTES, &map_w, lfull, kb * 64, (int)rank * (p.N / 2));
           if (rank != 0) mbar_arrive_cluster(lfull);
-          if (++stage == DN_NSTAGE) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -154,7 +161,7 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
             umma_bf16_2sm(tacc, make_smem_desc_sw128(sa + k4 * 32), make_smem_desc_sw128(sa + DN_ABYTES + k4 * 32),
                           idesc, (kb == 0 && k4 == 0) ? 0u : 1u);
           umma_commit_2sm(empty_bar(stage));
-          if (++stage == DN_NSTAGE) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
         umma_commit_2sm(acc_full(r));
       }
@@ -168,9 +175,17 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     const int sw = row & 7;
     float* scratch = reinterpret_cast<float*>(smem_gen + (scr_base - smem_base));
     float* sbias = reinterpret_cast<float*>(smem_gen + (sbias_base - smem_base));
-    if (p.mode == 1) {                           // head: bias (pre-scaled by log2 e under softmax), zero past n_out
+    float* csacc = reinterpret_cast<float*>(smem_gen + (csacc_base - smem_base));
+    {
+      // bias staged once per CTA (head: pre-scaled by log2 e under softmax, zero past n_out); the gate-backward
+      // epilogue also keeps its 2N column sums here (scratch) until the last tile
       const int t256 = threadIdx.x - 64;
-      if (t256 < p.N) sbias[t256] = (t256 < p.n_out) ? __ldg(p.bias + t256) * (p.softmax ? 1.4426950408889634f : 1.f) : 0.f;
+      if (t256 < p.N) {
+        if (p.mode == 1) sbias[t256] = (t256 < p.n_out) ? __ldg(p.bias + t256) * (p.softmax ? 1.4426950408889634f : 1.f) : 0.f;
+        else sbias[t256] = __ldg(p.bias + t256);
+      }
+      if (p.gb_gate)
+        for (int i = t256; i < DN_CSACC / 4; i += 256) csacc[i] = 0.f;
       epi_bar();
     }
     uint32_t nchunk = 0;
@@ -183,6 +198,19 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       const int t0 = (pt - b * p.tiles_per_seq) * (2 * RB_TILE) + (int)rank * RB_TILE;
       const int r = it & 1, use = it >> 1;
       const uint32_t tacc = tmem_base + (uint32_t)r * 256u + lane_off;
+      // gate-backward epilogue: this thread's 32 gate / sigmoid values of the coming chunk, fetched one chunk ahead
+      // (64 contiguous bytes per tensor and row; the first chunk's loads are in flight while the contraction finishes)
+      uint4 ng[4], ns[4];
+      const bool gb_row = p.gb_gate != nullptr && t0 + row < p.T;
+      const size_t gb_base = ((size_t)b * p.T + t0 + row) * (size_t)p.N + h * 32;
+      auto gb_fetch = [&](int c) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ng[j] = gb_row ? __ldg(reinterpret_cast<const uint4*>(p.gb_gate + gb_base + c * 64) + j) : make_uint4(0, 0, 0, 0);
+          ns[j] = gb_row ? __ldg(reinterpret_cast<const uint4*>(p.gb_sg + gb_base + c * 64) + j) : make_uint4(0, 0, 0, 0);
+        }
+      };
+      if (p.gb_gate) gb_fetch(0);
       mbar_wait(acc_full(r), (uint32_t)(use & 1));
       tc_fence_after();
 
@@ -193,15 +221,93 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
           float a[32];
           tmem_ld16(tacc + col, a);
           tmem_ld16(tacc + col + 16, a + 16);
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
+          const float4* bp = reinterpret_cast<const float4*>(sbias + col);
           float bv[32];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 u = __ldg(bp + j);
+            const float4 u = bp[j];
             bv[4 * j] = u.x; bv[4 * j + 1] = u.y; bv[4 * j + 2] = u.z; bv[4 * j + 3] = u.w;
           }
           tmem_wait_ld();
           uint32_t pk[16];
+          if (p.gb_gate) {
+            // ---- gate backward (block.py:66-71): acc = d(gate); the forward kept gate = tanh * sigmoid and sigmoid
+            uint32_t pl[16], wg[16], ws[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              wg[4 * j] = ng[j].x; wg[4 * j + 1] = ng[j].y; wg[4 * j + 2] = ng[j].z; wg[4 * j + 3] = ng[j].w;
+              ws[4 * j] = ns[j].x; ws[4 * j + 1] = ns[j].y; ws[4 * j + 2] = ns[j].z; ws[4 * j + 3] = ns[j].w;
+            }
+            if (c + 1 < p.N / 64) gb_fetch(c + 1);
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float gx = __uint_as_float(wg[i >> 1] << 16), gy = __uint_as_float(wg[i >> 1] & 0xffff0000u);
+              const float sx = __uint_as_float(ws[i >> 1] << 16), sy = __uint_as_float(ws[i >> 1] & 0xffff0000u);
+              // tanh = gate / sigmoid (0 / 0 -> 0); 1 - tanh^2 held at >= 0 against the rounding of the two bf16 factors;
+              // tanh * sigmoid is the stored gate itself
+              const float tx = gx * rcp_approx(fmaxf(sx, 1e-30f)), ty = gy * rcp_approx(fmaxf(sy, 1e-30f));
+              const float ux = fmaxf(fmaf(-tx, tx, 1.f), 0.f), uy = fmaxf(fmaf(-ty, ty, 1.f), 0.f);
+              const float d0 = a[i] + bv[i], d1 = a[i + 1] + bv[i + 1];
+              pk[i >> 1] = pack_bf16x2(d0 * sx * ux, d1 * sy * uy);
+              pl[i >> 1] = pack_bf16x2(d0 * gx * (1.f - sx), d1 * gy * (1.f - sy));
+            }
+            const uint32_t pbase = (nchunk & 1u) ? smem_base + (DN_NSTAGE - 1) * DN_STAGE : stg_base;
+            if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            epi_bar();
+            uint8_t* srow = smem_gen + (pbase - smem_base) + row * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int o = ((4 * h + j) ^ sw) << 4;
+              *reinterpret_cast<uint4*>(srow + o) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              *reinterpret_cast<uint4*>(srow + DN_ABYTES + o) =
+                  make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+            }
+            fence_proxy_async_smem();
+            epi_bar();
+            if (issuer) {
+              tma_store_3d(&map_y, pbase, c * 64, t0, b);
+              tma_store_3d(&map_y, pbase + DN_ABYTES, p.N + c * 64, t0, b);
+              bulk_commit();
+            }
+            if (p.colsum) {
+              // bias gradients = column sums of both staged tiles (rows past T hold zeros: their gate / sigmoid were
+              // fetched as 0).  A thread sums one 16-byte unit (8 channels) over 4 rows, the 4 lanes that share a unit
+              // meet by shuffle, and 8 lanes per warp add into that WARP's 2N shared accumulators (no atomics: a shared
+              // fp32 atomicAdd is a compare-and-swap loop).
+              const int t256 = threadIdx.x - 64, ci = t256 & 7, r0 = t256 >> 3;
+              float s1[8], s2[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+              const uint8_t* rp = smem_gen + (pbase - smem_base) + r0 * 128 + ((ci ^ (r0 & 7)) << 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint4 u = *reinterpret_cast<const uint4*>(rp + k * 32 * 128);
+                const uint4 v = *reinterpret_cast<const uint4*>(rp + DN_ABYTES + k * 32 * 128);
+                const uint32_t uw[4] = {u.x, u.y, u.z, u.w}, vw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  s1[2 * j] += __uint_as_float(uw[j] << 16); s1[2 * j + 1] += __uint_as_float(uw[j] & 0xffff0000u);
+                  s2[2 * j] += __uint_as_float(vw[j] << 16); s2[2 * j + 1] += __uint_as_float(vw[j] & 0xffff0000u);
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8);  s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
+                s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8);  s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+              }
+              if (lane < 8) {
+                float4* q1 = reinterpret_cast<float4*>(csacc + (warp - 2) * 512 + c * 64 + ci * 8);
+                float4* q2 = q1 + 64;              // + 256 floats: the second half of the output columns
+                float4 u0 = q1[0], u1 = q1[1], v0 = q2[0], v1 = q2[1];
+                u0.x += s1[0]; u0.y += s1[1]; u0.z += s1[2]; u0.w += s1[3];
+                u1.x += s1[4]; u1.y += s1[5]; u1.z += s1[6]; u1.w += s1[7];
+                v0.x += s2[0]; v0.y += s2[1]; v0.z += s2[2]; v0.w += s2[3];
+                v1.x += s2[4]; v1.y += s2[5]; v1.z += s2[6]; v1.w += s2[7];
+                q1[0] = u0; q1[1] = u1; q2[0] = v0; q2[1] = v1;
+              }
+            }
+            continue;
+          }
           if (p.split) {
             // fp16 (hi, lo) pair: both staging buffers per chunk, one bulk group
             uint32_t pl[16];
@@ -379,7 +485,21 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       mbar_arrive_cluster(mapa_shared(acc_empty(r), 0));
     }
     if (p.colsum && p.mode == 0)
-      for (int q = 0; q < p.N / 64; ++q) atomicAdd(p.colsum + q * 64 + cs_col, csum[q]);
+    {
+      if (p.gb_gate) {                           // the CTA's shared accumulators, one global add per column
+        epi_bar();
+        const int t256 = threadIdx.x - 64;
+        if (t256 < p.N) {
+          float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+          for (int wq = 0; wq < 8; ++wq) { a1 += csacc[wq * 512 + t256]; a2 += csacc[wq * 512 + 256 + t256]; }
+          atomicAdd(p.colsum + t256, a1);
+          atomicAdd(p.colsum + p.N + t256, a2);
+        }
+      } else {
+        for (int q = 0; q < p.N / 64; ++q) atomicAdd(p.colsum + q * 64 + cs_col, csum[q]);
+      }
+    }
     if (issuer) bulk_wait0();
   }
 
@@ -772,6 +892,13 @@ extern "C" int wnb200_dense_fwd_tc(const wnb200_dense_t* a, void* stream) {
                 "dense_fwd_tc: a layer stack is contracted with one zero-offset tap and no second source");
   WNB_CHECK_ARG(!a->y_lo || p.split, "dense_fwd_tc: y_lo needs act_fmt = WNB200_ACT_F16X2 and the NLC mode");
   WNB_CHECK_ARG(!p.f16 || !p.colsum, "dense_fwd_tc: colsum is a bf16 (training) feature");
+  WNB_CHECK_ARG((a->gb_gate == nullptr) == (a->gb_sg == nullptr), "dense_fwd_tc: gb_gate and gb_sg come together");
+  WNB_CHECK_ARG(!a->gb_gate || (a->mode == 0 && !p.f16 && !a->leaky),
+                "dense_fwd_tc: the gate-backward epilogue is an NLC, bf16, linear one");
+  WNB_CHECK_ARG(!a->gb_gate || ((reinterpret_cast<uintptr_t>(a->gb_gate) | reinterpret_cast<uintptr_t>(a->gb_sg)) & 15) == 0,
+                "dense_fwd_tc: gb_gate / gb_sg must be 16-byte aligned");
+  p.gb_gate = reinterpret_cast<const bf16*>(a->gb_gate);
+  p.gb_sg = reinterpret_cast<const bf16*>(a->gb_sg);
   const int esize = a->out_f32 ? 4 : 2;
   p.tma_out = (a->mode == 1 && ((long long)a->T * esize) % 16 == 0) ? 1 : 0;
   CUtensorMap mx, mx2, mw, my, mylo;
@@ -782,7 +909,7 @@ extern "C" int wnb200_dense_fwd_tc(const wnb200_dense_t* a, void* stream) {
   if ((rc = rb_map_2d(&mw, a->w, a->N, (a->nlayers > 0 ? a->nlayers : a->ntaps) * a->Cin + p.ntaps2 * a->Cin2,
                       a->N / 2))) return rc;
   if (a->mode == 0) {
-    if ((rc = rb_map_nlc(&my, a->y, a->B, a->T, a->N, 2))) return rc;
+    if ((rc = rb_map_nlc(&my, a->y, a->B, a->T, a->gb_gate ? 2 * a->N : a->N, 2))) return rc;
   } else if (p.tma_out) {
     if ((rc = rb_map_ncl(&my, a->y, a->B, a->n_out, a->T, esize, RB_TILE, a->n_out < 32 ? a->n_out : 32))) return rc;
   } else {

@@ -39,6 +39,7 @@ struct Res3Dev {
   const float* bias2;   // [>= C] bres + bproj
   int write_res, has_lo;
   int* sat_flag;        // optional: set to 1 when a stream value left the fp16 range (the hi half saturated)
+  bf16* sg_out;         // SAVE (training, bf16 format): NLC [B,T,C] that receives sigmoid(.) -- backward's second factor
 };
 
 constexpr int R3_THREADS = 320;
@@ -66,7 +67,7 @@ __device__ __forceinline__ void mma3_kblock(uint32_t tmem_d, uint32_t a_addr, ui
                   (first && k4 == 0) ? 0u : 1u);
 }
 
-template <int C, bool PREC>
+template <int C, bool PREC, bool SAVE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R3_THREADS, 1)
 resblock3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                  const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_res,
@@ -323,6 +324,21 @@ resblock3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                                             fmaf(gc[i + 1], -1.4426950408889634f, bsa[i + 1]));
               pk[i >> 1] = pack_f16x2(v0, v1);
             }
+          } else if constexpr (SAVE) {
+            // training: the sigmoid factor goes straight from registers to HBM (32 contiguous bytes per thread and step;
+            // no shared staging is left in this kernel, and a register copy-out measured the same as a TMA store)
+            uint32_t ps[8];
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              const float s0 = sigmoid_approx(gc[i] + bsa[i]), s1 = sigmoid_approx(gc[i + 1] + bsa[i + 1]);
+              pk[i >> 1] = pack_bf16x2(tanh_approx(ac[i] + bta[i]) * s0, tanh_approx(ac[i + 1] + bta[i + 1]) * s1);
+              ps[i >> 1] = pack_bf16x2(s0, s1);
+            }
+            if (t0 + row < p.T) {
+              uint4* dst = reinterpret_cast<uint4*>(p.sg_out + ((size_t)b * p.T + t0 + row) * C + half * (C / 2) + col);
+              dst[0] = make_uint4(ps[0], ps[1], ps[2], ps[3]);
+              dst[1] = make_uint4(ps[4], ps[5], ps[6], ps[7]);
+            }
           } else {
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
@@ -443,18 +459,18 @@ resblock3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   }
 }
 
-template <int C, bool PREC>
+template <int C, bool PREC, bool SAVE>
 static int launch_resblock3(const CUtensorMap& mx, const CUtensorMap& mw1, const CUtensorMap& mw2,
                             const CUtensorMap& mres, const CUtensorMap& mgate, const CUtensorMap& mxlo,
                             const CUtensorMap& mreslo, const Res3Dev& p, cudaStream_t st) {
   using K = R3Cfg<C>;
-  WNB_SET_SMEM_ATTR(K::SMEM, resblock3_kernel<C, PREC>);
+  WNB_SET_SMEM_ATTR(K::SMEM, (resblock3_kernel<C, PREC, SAVE>));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int pairs = sms / 2;
   if (p.num_tiles < pairs) pairs = p.num_tiles;
-  resblock3_kernel<C, PREC><<<2 * pairs, R3_THREADS, K::SMEM, st>>>(mx, mw1, mw2, mres, mgate, mxlo, mreslo, p);
+  resblock3_kernel<C, PREC, SAVE><<<2 * pairs, R3_THREADS, K::SMEM, st>>>(mx, mw1, mw2, mres, mgate, mxlo, mreslo, p);
   WNB_LAUNCH_OK();
   return 0;
 }
@@ -463,7 +479,9 @@ static int launch_resblock3(const CUtensorMap& mx, const CUtensorMap& mw1, const
 int resblock3_launch(const wnb200_resblock_t* a, void* stream) {
   const int C = a->C;
   const bool prec = a->act_fmt == WNB200_ACT_F16X2;
-  WNB_CHECK_ARG(!a->save_act && !a->skips_act, "resblock_fwd_tc: gate_out (deferred skip) is an inference path");
+  WNB_CHECK_ARG(!a->save_act && !a->save_th && !a->skips_act,
+                "resblock_fwd_tc: with gate_out the gate IS the saved activation; only save_sg may accompany it");
+  WNB_CHECK_ARG(!a->save_sg || !prec, "resblock_fwd_tc: save_sg (training) belongs to the bf16 format");
   WNB_CHECK_ARG(prec || (!a->x_lo && !a->res_lo), "resblock_fwd_tc: x_lo / res_lo belong to the fp16 (hi, lo) format");
   WNB_CHECK_ARG(!prec || !a->res || a->res_lo, "resblock_fwd_tc: the fp16 (hi, lo) format writes res AND res_lo");
   Res3Dev p;
@@ -477,6 +495,7 @@ int resblock3_launch(const wnb200_resblock_t* a, void* stream) {
   p.write_res = a->res != nullptr;
   p.has_lo = prec && a->x_lo != nullptr;
   p.sat_flag = prec ? reinterpret_cast<int*>(a->sat_flag) : nullptr;
+  p.sg_out = reinterpret_cast<bf16*>(a->save_sg);
   CUtensorMap mx, mw1, mw2, mres, mgate, mxlo, mreslo;
   int rc;
   if ((rc = rb_map_nlc(&mx, a->x, a->B, a->T, C, 2))) return rc;
@@ -489,10 +508,13 @@ int resblock3_launch(const wnb200_resblock_t* a, void* stream) {
   if (prec && a->res && (rc = rb_map_nlc(&mreslo, a->res_lo, a->B, a->T, C, 2))) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (prec)
-    return C == 256 ? launch_resblock3<256, true>(mx, mw1, mw2, mres, mgate, mxlo, mreslo, p, st)
-                    : launch_resblock3<128, true>(mx, mw1, mw2, mres, mgate, mxlo, mreslo, p, st);
-  return C == 256 ? launch_resblock3<256, false>(mx, mw1, mw2, mres, mgate, mxlo, mreslo, p, st)
-                  : launch_resblock3<128, false>(mx, mw1, mw2, mres, mgate, mxlo, mreslo, p, st);
+    return C == 256 ? launch_resblock3<256, true, false>(mx, mw1, mw2, mres, mgate, mxlo, mreslo, p, st)
+                    : launch_resblock3<128, true, false>(mx, mw1, mw2, mres, mgate, mxlo, mreslo, p, st);
+  if (p.sg_out)
+    return C == 256 ? launch_resblock3<256, false, true>(mx, mw1, mw2, mres, mgate, mxlo, mreslo, p, st)
+                    : launch_resblock3<128, false, true>(mx, mw1, mw2, mres, mgate, mxlo, mreslo, p, st);
+  return C == 256 ? launch_resblock3<256, false, false>(mx, mw1, mw2, mres, mgate, mxlo, mreslo, p, st)
+                  : launch_resblock3<128, false, false>(mx, mw1, mw2, mres, mgate, mxlo, mreslo, p, st);
 }
 
 }  // namespace wnb

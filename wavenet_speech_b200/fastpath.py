@@ -338,11 +338,13 @@ def resblock(x_nlc, pk, res, skips, skips_init, dbg=None, variant=None, save=Non
 
 
 def dense(x_nlc, offsets, w, bias, N, mode=0, leaky=0, out=None, n_out=0, softmax=0, x2=None, offsets2=(), colsum=None,
-          fmt=0, split=False, nlayers=0):
+          fmt=0, split=False, nlayers=0, gate_bwd=None):
     """CTA-pair dense contraction.  mode 0 -> NLC bf16 [B,T,N]; mode 1 -> NCL `out` [B,n_out,T].
     Optional second source x2 [B,T,Cin2] with its own taps: its columns follow x's in `w`.
     colsum (mode 0): fp32 [N] tensor that the column sums of the output are ADDED to.
-    nlayers: x_nlc is a stack [L, B, T, Cin] and w is [N, L*Cin]: y = epi(sum_l W_l x_l + bias), one contraction."""
+    nlayers: x_nlc is a stack [L, B, T, Cin] and w is [N, L*Cin]: y = epi(sum_l W_l x_l + bias), one contraction.
+    gate_bwd = (gate, sigmoid) NLC bf16 [B,T,N]: the result is d(gate) and the epilogue applies the gate's backward:
+    returns NLC bf16 [B,T,2N] = [d tanh-pre-activation | d sigmoid-pre-activation]; colsum is then fp32 [2N]."""
     if nlayers:
         assert x_nlc.dim() == 4 and x_nlc.shape[0] == nlayers and len(offsets) == 1 and x2 is None
         _L, B, T, Cin = x_nlc.shape
@@ -355,8 +357,13 @@ def dense(x_nlc, offsets, w, bias, N, mode=0, leaky=0, out=None, n_out=0, softma
     a.N, a.mode, a.leaky, a.n_out, a.softmax = N, mode, int(leaky), n_out, int(softmax)
     out_lo = None
     if mode == 0:
-        out = torch.empty((B, T, N), dtype=torch.float16 if fmt == _lib.ACT_F16X2 else torch.bfloat16,
-                          device=x_nlc.device)
+        out = torch.empty((B, T, 2 * N if gate_bwd is not None else N),
+                          dtype=torch.float16 if fmt == _lib.ACT_F16X2 else torch.bfloat16, device=x_nlc.device)
+        if gate_bwd is not None:
+            g, s = gate_bwd
+            assert g.shape == (B, T, N) and s.shape == (B, T, N) and g.is_contiguous() and s.is_contiguous()
+            assert g.dtype == torch.bfloat16 and s.dtype == torch.bfloat16
+            a.gb_gate, a.gb_sg = g.data_ptr(), s.data_ptr()
         if split:
             assert fmt == _lib.ACT_F16X2
             out_lo = torch.empty_like(out)
@@ -366,7 +373,7 @@ def dense(x_nlc, offsets, w, bias, N, mode=0, leaky=0, out=None, n_out=0, softma
     a.out_f32 = 1 if out.dtype == torch.float32 else 0
     a.x, a.w, a.bias, a.y = x_nlc.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr()
     if colsum is not None:
-        assert mode == 0 and colsum.dtype == torch.float32 and colsum.numel() >= N
+        assert mode == 0 and colsum.dtype == torch.float32 and colsum.numel() >= (2 * N if gate_bwd is not None else N)
         a.colsum = colsum.data_ptr()
     if x2 is not None:
         assert x2.shape[:2] == x_nlc.shape[:2]

@@ -68,6 +68,15 @@ class zero_pool(object):
         _ZeroPool.current = self.prev
 
 
+# True: the d(gate) contraction applies the gate's backward in its epilogue (wnb200_dense_t.gb_gate / gb_sg) instead of a
+# separate elementwise launch.  Measured at the config-3 layer shape (scripts/bench_gatebwd.py, 32 x 16383 x 256): fused
+# 0.39 ms, DRAM traffic at the algorithmic minimum (1.07 GB read + 0.50 GB written) -- but the contraction + the
+# elementwise launch take 0.145 + 0.207 = 0.35 ms: the elementwise kernel runs 64 warps per SM at 6.4 TB/s, the fused
+# epilogue has the kernel's 8 epilogue warps per SM to do the same arithmetic and is latency-bound there (0.2 IPC).
+# So the two-launch form stays the default; the fused form is kept, tested, for shapes where launches dominate.
+FUSE_GATE_BWD = False
+
+
 def colsum(x_nlc, out=None):
     """fp32 column sums of an NLC bf16 tensor [B, T, C] (accumulates into `out`)."""
     B, T, C = x_nlc.shape
@@ -77,12 +86,14 @@ def colsum(x_nlc, out=None):
     return out
 
 
-def gate_bwd_nlc(dgate, th, sg, want_bias=False, th_is_gate=False):
+def gate_bwd_nlc(dgate, th, sg, want_bias=False, th_is_gate=False, out=None, dbias=None):
     """dab = [dgate sg (1-th^2) ; dgate th sg (1-sg)]; with want_bias also its fp32 column sums [2C].
-    th_is_gate: `th` holds the gate tanh * sigmoid (what the training forward keeps): tanh = gate / sigmoid."""
+    th_is_gate: `th` holds the gate tanh * sigmoid (what the training forward keeps): tanh = gate / sigmoid.
+    out / dbias: write into / accumulate into caller-owned tensors (a batch walked in chunks)."""
     B, T, C = dgate.shape
-    dab = torch.empty((B, T, 2 * C), dtype=torch.bfloat16, device=dgate.device)
-    dbias = _zeros(2 * C, dgate.device) if want_bias else None
+    dab = torch.empty((B, T, 2 * C), dtype=torch.bfloat16, device=dgate.device) if out is None else out
+    if want_bias and dbias is None:
+        dbias = _zeros(2 * C, dgate.device)
     _lib.call("wnb200_gate_bwd_nlc_from_gate" if th_is_gate else "wnb200_gate_bwd_nlc", B * T, C, ops._p(dgate),
               ops._p(th), ops._p(sg), ops._p(dab), ops._p(dbias), ops._stream())
     return (dab, dbias) if want_bias else dab
@@ -120,6 +131,12 @@ class Stack(object):
         self.blocks, self.necks = list(blocks), list(bottlenecks)
         self.fwd = [FP.pack_block(b, n, precise=False, bwd=True, natural=False) for b, n in zip(self.blocks, self.necks)]
         self.bwd = self.fwd                   # same dicts: wdg / wdg_skip / wdx / wdx_taps / k / C live next to w1h ...
+        self._skip = None
+
+    def skip_pack(self):
+        if self._skip is None:
+            self._skip = FP.skip_pack(self.fwd)
+        return self._skip
 
     def params(self):
         """Per layer, in this order: wt, bt, ws, bs, wres, bres, wskip, bskip, wproj, bproj, wbn, bbn."""
@@ -146,6 +163,20 @@ def stack_forward(h0, stack, skips):
     saved = []
     h = h0
     n = len(stack.fwd)
+    if FP.DEFER_SKIP and h0.shape[2] in (128, 256) and FP.RESBLOCK_VARIANT != 1:
+        # deferred skip (resblock3_kernel): every layer stores its gate into a stack -- the activation backward keeps
+        # anyway -- plus the sigmoid factor; the skip sum is ONE contraction over K = layers x channels afterwards, so
+        # the fp32 running sum (1.07 GB of read-modify-write per layer at the config-3 shape) never exists in HBM.
+        gates = torch.empty((n,) + tuple(h0.shape), dtype=h0.dtype, device=h0.device)
+        for l, pk in enumerate(stack.fwd):
+            last = l == n - 1
+            sg = torch.empty_like(h)
+            res = None if last else torch.empty_like(h)
+            FP.resblock(h, pk, res, None, False, save=(None, None, sg), gate_out=gates[l])
+            saved.append((h, gates[l], sg))
+            h = res
+        wcat, bsum = stack.skip_pack()
+        return saved, FP.dense(gates, [0], wcat, bsum, h0.shape[2], leaky=1, nlayers=n)
     skips_act = torch.empty_like(h0) if FP.FUSE_FINAL else None
     for l, pk in enumerate(stack.fwd):
         last = l == n - 1
@@ -173,12 +204,16 @@ def stack_backward(stack, saved, dskips, need_dx0):
         x, act, sg = saved[l]
         pb, offs = stack.bwd[l], stack.fwd[l]["offsets"]
         k = pb["k"]
-        if dres is None:
-            dg = FP.dense(dskips, [0], pb["wdg_skip"], zb, C)
+        dbab = _zeros(2 * C, dev)
+        if not FUSE_GATE_BWD:
+            dg = (FP.dense(dskips, [0], pb["wdg_skip"], zb, C) if dres is None
+                  else FP.dense(dres, [0], pb["wdg"], zb, C, x2=dskips, offsets2=[0]))
+            dab, dbab = gate_bwd_nlc(dg, act, sg, want_bias=True, th_is_gate=True)
+            del dg
+        elif dres is None:
+            dab = FP.dense(dskips, [0], pb["wdg_skip"], zb, C, gate_bwd=(act, sg), colsum=dbab)
         else:
-            dg = FP.dense(dres, [0], pb["wdg"], zb, C, x2=dskips, offsets2=[0])
-        dab, dbab = gate_bwd_nlc(dg, act, sg, want_bias=True, th_is_gate=True)
-        del dg
+            dab = FP.dense(dres, [0], pb["wdg"], zb, C, x2=dskips, offsets2=[0], gate_bwd=(act, sg), colsum=dbab)
         dx = dx_cs = None
         if l > 0 or need_dx0:
             neg = [-o for o in offs]
