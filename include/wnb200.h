@@ -372,6 +372,20 @@ int wnb200_wgrad_tc(int B, int T, int Cg, int m0, int N, int off, const void* g_
  * e.g. both taps of a dilated conv (x at two offsets) or [gate | x] for conv1x1_residual and residual_proj. */
 int wnb200_wgrad2_tc(int B, int T, int Cg, int m0, int N, int nsrc, const int32_t* off /*host*/, const void* g_nlc,
                      const void* x_nlc, const void* x2_nlc, float* dw, void* stream);
+/* Up to 6 such products over the same frames in ONE launch -- all weight gradients of a residual block (block.py:60-78:
+ * [dtanh ; dsigmoid] x the taps of x, dres x [gate | x], dskips x gate).  The CTA pairs are divided over the jobs by MMA
+ * work and all jobs sweep the frames at the same pace, so x, the gate and the gradients come from HBM once per launch and
+ * from L2 for the other jobs.  jobs: host array. */
+typedef struct {
+  const void* g;          /* NLC bf16 [B,T,Cg] */
+  int32_t Cg, m0;
+  const void* x;          /* NLC bf16 [B,T,N] */
+  const void* x2;         /* second source (nsrc = 2) or NULL */
+  int32_t N, nsrc;
+  int32_t off[2];
+  float* dw;              /* fp32 [256][nsrc*N], accumulated into */
+} wnb200_wgrad_job_t;
+int wnb200_wgrad_jobs_tc(int B, int T, int njobs, const wnb200_wgrad_job_t* jobs /*host*/, void* stream);
 
 /* Gate backward on NLC bf16 tensors (block.py:185): dab[r, 0:C] = dact*sg*(1-th^2), dab[r, C:2C] = dact*th*sg*(1-sg)
  * for each of `rows` = B*T frames; if dbias != NULL, dbias[0:2C] (fp32) += the column sums of dab (the two conv

@@ -68,6 +68,12 @@ class Dense(_Sized):
                 ("gb_gate", c_void_p), ("gb_sg", c_void_p)]
 
 
+class WgradJob(ctypes.Structure):
+    """Mirror of wnb200_wgrad_job_t."""
+    _fields_ = [("g", c_void_p), ("Cg", ctypes.c_int32), ("m0", ctypes.c_int32), ("x", c_void_p), ("x2", c_void_p),
+                ("N", ctypes.c_int32), ("nsrc", ctypes.c_int32), ("off", ctypes.c_int32 * 2), ("dw", c_void_p)]
+
+
 class PackBlock(_Sized):
     """Mirror of wnb200_pack_block_t."""
     _fields_ = [("struct_size", ctypes.c_uint32), ("C", ctypes.c_int32), ("k", ctypes.c_int32),
@@ -127,6 +133,7 @@ SIGNATURES = {
     "wnb200_wgrad_tc": [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_wgrad2_tc": [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                          c_void_p],
+    "wnb200_wgrad_jobs_tc": [c_int, c_int, c_int, c_void_p, c_void_p],
     "wnb200_gate_bwd_nlc": [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_gate_bwd_nlc_from_gate": [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_colsum_nlc": [c_int64, c_int, c_void_p, c_void_p, c_void_p],

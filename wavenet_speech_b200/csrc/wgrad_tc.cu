@@ -11,6 +11,13 @@
 // 256 x N partial in TMEM (CTA r of the pair owns output rows [128r, 128r+128) and loads half of X's channels) and
 // adds it to dW with TMA reduce-add (fp32; the order of the cross-pair additions is not fixed).
 // Replaces autograd's weight gradients of conv_ops.py:43,78 / block.py:73-78 on the training step.
+//
+// One launch carries up to WG_MAXJOBS such products ("jobs") over the SAME frames -- all weight gradients of one residual
+// block: [dtanh ; dsigmoid] x the taps of x (two 256-row jobs), dres x (gate, x), dskips x gate.  The CTA pairs are
+// divided over the jobs in proportion to their MMA work, and a pair walks the (batch, 64-frame) blocks with the stride
+// of its job's pair count, so every job sweeps the frames front to back at the same pace: x, the gate and the
+// gradients are fetched from HBM once per launch and found in L2 by the other jobs (as four separate launches the
+// block's weight gradients read 2.95 GB at the config-3 shape, 1.6 GB of them distinct).
 #include <string.h>
 
 #include "common.cuh"
@@ -20,11 +27,20 @@
 namespace wnb {
 using namespace tc;
 
-struct WgDev {
-  int T, kblocks_per_seq, total_kblocks;
+constexpr int WG_MAXJOBS = 6;
+struct WgJob {
+  CUtensorMap map_g, map_x, map_x2, map_dw;
   int m0, N, off;
   int nsrc, off2;        // optional second X tensor (same N): its dW block follows the first one's columns
+  int pair_begin, npairs;
+  int pad_[9];
 };
+struct WgDev {
+  int T, kblocks_per_seq, total_kblocks, njobs;
+  int pad_[12];
+  WgJob job[WG_MAXJOBS];
+};
+static_assert(sizeof(WgJob) % 64 == 0 && sizeof(WgDev) <= 4000, "kernel parameter layout");
 
 constexpr int WG_THREADS = 192;                  // TMA warp, MMA warp, 4 epilogue warps
 constexpr int WG_BOX = 64 * 128;                 // one {64 ch, 64 frames} box = 8 KB
@@ -45,8 +61,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t saddr, uint
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1)
-wgrad2_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_x,
-              const __grid_constant__ CUtensorMap map_x2, const __grid_constant__ CUtensorMap map_dw, const WgDev p) {
+wgrad2_kernel(const __grid_constant__ WgDev P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -59,12 +74,19 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  // this pair's contiguous range of (batch, 64-frame) blocks
-  const int per = (p.total_kblocks + npairs - 1) / npairs;
-  const int kb_begin = pair * per;
-  const int kb_end = (kb_begin + per) < p.total_kblocks ? (kb_begin + per) : p.total_kblocks;
-  const int nkb = kb_end > kb_begin ? kb_end - kb_begin : 0;
+  const int pair = blockIdx.x >> 1;
+  int ji = 0;
+  for (int j = 1; j < P.njobs; ++j)
+    if (pair >= P.job[j].pair_begin) ji = j;
+  const WgJob& p = P.job[ji];
+  const CUtensorMap& map_g = p.map_g;
+  const CUtensorMap& map_x = p.map_x;
+  const CUtensorMap& map_x2 = p.map_x2;
+  const CUtensorMap& map_dw = p.map_dw;
+  // this pair's (batch, 64-frame) blocks: kb_begin, kb_begin + npairs, ... (strided: all pairs of all jobs move through
+  // the frames together)
+  const int kb_begin = pair - p.pair_begin, kb_step = p.npairs;
+  const int nkb = kb_begin < P.total_kblocks ? (P.total_kblocks - kb_begin + kb_step - 1) / kb_step : 0;
   const int nhalf = p.N / 2;                                  // X channels held by this CTA
   const int xboxes = nhalf / 64;                              // boxes per X tensor per CTA
   const uint32_t stage_bytes = (uint32_t)(2 * WG_BOX + p.nsrc * xboxes * WG_BOX);
@@ -94,9 +116,9 @@ wgrad2_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        const int b = kb / p.kblocks_per_seq;
-        const int t0 = (kb - b * p.kblocks_per_seq) * 64;
+      for (int kb = kb_begin; kb < P.total_kblocks; kb += kb_step) {
+        const int b = kb / P.kblocks_per_seq;
+        const int t0 = (kb - b * P.kblocks_per_seq) * 64;
         mbar_wait(empty_bar(stage), phase ^ 1);
         const uint32_t sa = smem_base + stage * WG_STAGE;
         if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * stage_bytes);
@@ -221,36 +243,78 @@ static int wg_map_dw(CUtensorMap* m, const void* ptr, int rows, int N) {
 
 using namespace wnb;
 
-extern "C" int wnb200_wgrad2_tc(int B, int T_, int Cg, int m0, int N, int nsrc, const int32_t* off /*host*/,
-                                const void* g_nlc, const void* x_nlc, const void* x2_nlc, float* dw, void* stream) {
-  WNB_CHECK_ARG(N == 128 || N == 256, "wgrad_tc: N=%d must be 128 or 256", N);
-  WNB_CHECK_ARG(nsrc == 1 || nsrc == 2, "wgrad_tc: nsrc=%d must be 1 or 2", nsrc);
-  WNB_CHECK_ARG(m0 >= 0 && m0 < Cg && Cg % 8 == 0, "wgrad_tc: row offset %d outside the %d channels of g", m0, Cg);
-  // rows beyond Cg are zero-filled by TMA (their dW rows receive zeros)
+static int wg_launch(int B, int T_, int njobs, const wnb200_wgrad_job_t* jobs, void* stream) {
+  WNB_CHECK_ARG(njobs >= 1 && njobs <= WG_MAXJOBS, "wgrad_jobs_tc: %d jobs (1..%d per launch)", njobs, WG_MAXJOBS);
+  WNB_CHECK_ARG(jobs != nullptr, "wgrad_jobs_tc: null job list");
   if (B == 0 || T_ == 0) return 0;
-  WNB_CHECK_ARG(g_nlc && x_nlc && dw && off && (nsrc == 1 || x2_nlc), "wgrad_tc: null pointer");
-  WgDev p;
-  p.T = T_;
-  p.kblocks_per_seq = ceil_div(T_, 64);
-  p.total_kblocks = p.kblocks_per_seq * B;
-  p.m0 = m0; p.N = N; p.off = off[0];
-  p.nsrc = nsrc; p.off2 = nsrc > 1 ? off[1] : 0;
-  CUtensorMap mg, mx, mx2, mdw;
-  int rc;
-  if ((rc = wg_map_nlc64(&mg, g_nlc, B, T_, Cg))) return rc;
-  if ((rc = wg_map_nlc64(&mx, x_nlc, B, T_, N))) return rc;
-  mx2 = mx;
-  if (nsrc > 1 && (rc = wg_map_nlc64(&mx2, x2_nlc, B, T_, N))) return rc;
-  if ((rc = wg_map_dw(&mdw, dw, 256, nsrc * N))) return rc;
-  WNB_SET_SMEM_ATTR(WG_SMEM, wgrad2_kernel);
+  WgDev P;
+  memset(&P, 0, sizeof(P));
+  P.T = T_;
+  P.kblocks_per_seq = ceil_div(T_, 64);
+  P.total_kblocks = P.kblocks_per_seq * B;
+  P.njobs = njobs;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int pairs = sms / 2;
-  if (p.total_kblocks < pairs) pairs = p.total_kblocks;
-  wgrad2_kernel<<<2 * pairs, WG_THREADS, WG_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(mg, mx, mx2, mdw, p);
+  if ((long long)P.total_kblocks * njobs < pairs) pairs = P.total_kblocks * njobs;
+  if (pairs < njobs) pairs = njobs;
+  int wsum = 0;
+  for (int j = 0; j < njobs; ++j) {
+    const wnb200_wgrad_job_t& a = jobs[j];
+    WNB_CHECK_ARG(a.N == 128 || a.N == 256, "wgrad_tc: N=%d must be 128 or 256", a.N);
+    WNB_CHECK_ARG(a.nsrc == 1 || a.nsrc == 2, "wgrad_tc: nsrc=%d must be 1 or 2", a.nsrc);
+    WNB_CHECK_ARG(a.m0 >= 0 && a.m0 < a.Cg && a.Cg % 8 == 0, "wgrad_tc: row offset %d outside the %d channels of g", a.m0, a.Cg);
+    WNB_CHECK_ARG(a.g && a.x && a.dw && (a.nsrc == 1 || a.x2), "wgrad_tc: null pointer");
+    wsum += a.nsrc;
+  }
+  // pairs per job in proportion to the MMA work (one 256 x N product per source and 64 frames); the remainder goes to the
+  // first jobs
+  int given = 0;
+  for (int j = 0; j < njobs; ++j) {
+    int n = pairs * jobs[j].nsrc / wsum;
+    if (n < 1) n = 1;
+    P.job[j].npairs = n;
+    given += n;
+  }
+  for (int j = 0; given < pairs; j = (j + 1) % njobs) { ++P.job[j].npairs; ++given; }
+  for (int j = njobs - 1; given > pairs; j = (j + njobs - 1) % njobs)
+    if (P.job[j].npairs > 1) { --P.job[j].npairs; --given; }
+  int begin = 0;
+  for (int j = 0; j < njobs; ++j) {
+    const wnb200_wgrad_job_t& a = jobs[j];
+    WgJob& q = P.job[j];
+    q.pair_begin = begin;
+    begin += q.npairs;
+    q.m0 = a.m0; q.N = a.N; q.off = a.off[0];
+    q.nsrc = a.nsrc; q.off2 = a.nsrc > 1 ? a.off[1] : 0;
+    int rc;
+    // rows beyond Cg are zero-filled by TMA (their dW rows receive zeros)
+    if ((rc = wg_map_nlc64(&q.map_g, a.g, B, T_, a.Cg))) return rc;
+    if ((rc = wg_map_nlc64(&q.map_x, a.x, B, T_, a.N))) return rc;
+    q.map_x2 = q.map_x;
+    if (a.nsrc > 1 && (rc = wg_map_nlc64(&q.map_x2, a.x2, B, T_, a.N))) return rc;
+    if ((rc = wg_map_dw(&q.map_dw, a.dw, 256, a.nsrc * a.N))) return rc;
+  }
+  WNB_SET_SMEM_ATTR(WG_SMEM, wgrad2_kernel);
+  wgrad2_kernel<<<2 * begin, WG_THREADS, WG_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(P);
   WNB_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int wnb200_wgrad_jobs_tc(int B, int T_, int njobs, const wnb200_wgrad_job_t* jobs, void* stream) {
+  return wg_launch(B, T_, njobs, jobs, stream);
+}
+
+extern "C" int wnb200_wgrad2_tc(int B, int T_, int Cg, int m0, int N, int nsrc, const int32_t* off /*host*/,
+                                const void* g_nlc, const void* x_nlc, const void* x2_nlc, float* dw, void* stream) {
+  WNB_CHECK_ARG(off != nullptr, "wgrad_tc: null pointer");
+  wnb200_wgrad_job_t a;
+  memset(&a, 0, sizeof(a));
+  a.g = g_nlc; a.Cg = Cg; a.m0 = m0; a.x = x_nlc; a.x2 = x2_nlc; a.N = N; a.nsrc = nsrc;
+  a.off[0] = off[0]; a.off[1] = nsrc > 1 ? off[1] : 0;
+  a.dw = dw;
+  return wg_launch(B, T_, 1, &a, stream);
 }
 
 extern "C" int wnb200_wgrad_tc(int B, int T_, int Cg, int m0, int N, int off, const void* g_nlc, const void* x_nlc,

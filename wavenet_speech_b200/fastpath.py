@@ -424,6 +424,31 @@ def wgrad2(g_nlc, xs, offs, m0=0, dw=None):
     return dw
 
 
+WGRAD_MAXJOBS = 6
+
+
+def wgrad_jobs(jobs):
+    """jobs: list of (g_nlc, m0, xs, offs, dw) -- wgrad2's arguments -- over the SAME [B, T]: one launch for up to
+    WGRAD_MAXJOBS of them (wnb200_wgrad_jobs_tc: the jobs sweep the frames together, shared operands come from L2)."""
+    B, T = jobs[0][0].shape[:2]
+    for i0 in range(0, len(jobs), WGRAD_MAXJOBS):
+        part = jobs[i0:i0 + WGRAD_MAXJOBS]
+        arr = (_lib.WgradJob * len(part))()
+        for a, (g, m0, xs, offs, dw) in zip(arr, part):
+            assert g.shape[:2] == (B, T) and len(xs) in (1, 2) and all(x.shape == xs[0].shape and x.shape[:2] == (B, T) for x in xs)
+            a.g, a.Cg, a.m0 = g.data_ptr(), g.shape[2], int(m0)
+            a.x, a.x2 = xs[0].data_ptr(), (xs[1].data_ptr() if len(xs) > 1 else None)
+            a.N, a.nsrc = xs[0].shape[2], len(xs)
+            a.off[0], a.off[1] = int(offs[0]), (int(offs[1]) if len(xs) > 1 else 0)
+            assert dw.dtype == torch.float32 and dw.numel() >= 256 * len(xs) * xs[0].shape[2]
+            a.dw = dw.data_ptr()
+        _lib.current_tag = "wgrad"
+        try:
+            _lib.call("wnb200_wgrad_jobs_tc", B, T, len(part), ctypes.cast(arr, ctypes.c_void_p), ops._stream())
+        finally:
+            _lib.current_tag = None
+
+
 def leaky_to_bf16(x):
     y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     _lib.call("wnb200_leaky_to_bf16", x.numel(), ops._p(x), ops._p(y), ops._stream())

@@ -119,6 +119,32 @@ def wgrad_multi(g, rows, srcs):
     return [o[0] if len(o) == 1 else torch.cat(o, 0) for o in outs]
 
 
+def wgrad_group(reqs):
+    """reqs: list of (g, rows, srcs, dw_into) with wgrad_multi's meaning, all over the same frames: every 256-row x
+    (one or two sources) product of every request goes into as few launches as possible (FP.wgrad_jobs), so that the
+    operands the requests share -- x, the gate, the gradients -- are read from HBM once.  dw_into (optional, one source,
+    rows == 256): a zeroed fp32 [256, N] tensor that receives the product in place.  Returns wgrad_multi's lists."""
+    jobs, outs = [], []
+    for g, rows, srcs, dw_into in reqs:
+        N = srcs[0][0].shape[2]
+        o = [[] for _ in srcs]
+        for m0 in range(0, rows, 256):
+            nr = min(256, rows - m0)
+            for i in range(0, len(srcs), 2):
+                pair = srcs[i:i + 2]
+                if dw_into is not None:
+                    assert len(srcs) == 1 and rows == 256
+                    dw = dw_into
+                else:
+                    dw = _zeros(256 * len(pair) * N, g.device).view(256, len(pair) * N)
+                jobs.append((g, m0, [q[0] for q in pair], [q[1] for q in pair], dw))
+                for q in range(len(pair)):
+                    o[i + q].append(dw[:nr, q * N:(q + 1) * N])
+        outs.append(o)
+    FP.wgrad_jobs(jobs)
+    return [[p[0] if len(p) == 1 else torch.cat(p, 0) for p in o] for o in outs]
+
+
 def wgrad_rows(g, x, off, rows, N):
     return wgrad_multi(g, rows, [(x, off)])[0]
 
@@ -222,18 +248,23 @@ def stack_backward(stack, saved, dskips, need_dx0):
                 dx = FP.dense(dab, neg, pb["wdx_taps"], zb, C, colsum=dx_cs)
             else:
                 dx = FP.dense(dab, neg, pb["wdx"], zb, C, x2=dres, offsets2=[0], colsum=dx_cs)
-        dwab = wgrad_multi(dab, 2 * C, [(x, offs[j]) for j in range(k)])            # k x [2C, C]
+        # all weight gradients of the block in one launch: k x [2C, C] for the taps, [gate | x] for the two 1x1s on the
+        # residual path, and M[l] (in place when it is one 256-row tile)
+        reqs = [(dab, 2 * C, [(x, offs[j]) for j in range(k)], None)]
+        if dres is not None:
+            reqs.append((dres, C, [(act, 0), (x, 0)], None))
+        reqs.append((dskips, C, [(act, 0)], M_all[l] if C == 256 else None))
+        got = wgrad_group(reqs)
+        dwab = got[0]
         dwt = torch.stack([d[:C] for d in dwab], 2)
         dws = torch.stack([d[C:] for d in dwab], 2)
         dwres = dwproj = dbres = None
         if dres is not None:
-            dwres, dwproj = wgrad_multi(dres, C, [(act, 0), (x, 0)])
+            dwres, dwproj = got[1]
             dwres = dwres.unsqueeze(2)
             dbres = dres_cs
-        if C == 256:
-            FP.wgrad2(dskips, [act], [0], 0, dw=M_all[l])      # written in place (one 256-row tile)
-        else:
-            M_all[l].copy_(wgrad_rows(dskips, act, 0, C, C))
+        if C != 256:
+            M_all[l].copy_(got[-1][0])
         grads[l] = [dwt, dbab[:C], dws, dbab[C:], dwres, dbres, None, None, dwproj, dbres, None, csk_rows[l]]
         saved[l] = None                                     # free this layer's activations
         dres, dres_cs = dx, dx_cs
