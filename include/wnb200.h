@@ -280,6 +280,11 @@ typedef struct {
   const void* gb_sg;      /* ... sigmoid (both NLC bf16 [B,T,N], 16-byte aligned), y is NLC bf16 [B,T,2N]:
                              y[..,0:N] = d * sg * (1 - th^2), y[..,N:2N] = d * th * sg * (1 - sg), th = gate / sg;
                              colsum is then fp32 [2N].  Replaces wnb200_gate_bwd_nlc_from_gate + one HBM round trip. */
+  const float* pos_w;     /* mode 0, optional: after bias / LeakyReLU, y[b,t,c] += hardtanh(pos_w[c] * (pos_t0 + t) + pos_b[c])
+                             -- RawCTCNet(positions=True) position mixing (raw_ctcnet.py:131-135) fused into the feature
+                             layer's 1x1; fp32 [N] each */
+  const float* pos_b;
+  int32_t pos_t0;         /* global frame index of t = 0 (a time shard of a longer read) */
 } wnb200_dense_t;
 int wnb200_dense_fwd_tc(const wnb200_dense_t* args /*host*/, void* stream);
 

@@ -310,3 +310,39 @@ def test_fp16_range_guard_falls_back_to_bf16_format():
                 b.residual_proj.weight.copy_(w)
             assert torch.equal(net(x), y_ok)               # new weight version: precise again
             assert FP.stream_saturated(net) is False
+
+
+@pytest.mark.parametrize("C,mode", [(128, "precise"), (256, "precise"), (128, "fast")])
+def test_raw_ctcnet_positions_on_the_tensor_core_path(C, mode):
+    """RawCTCNet(positions=True) (raw_ctcnet.py:131-135): the position term hardtanh(w t + b) is added in the epilogue
+    of the feature layer's 1x1 contraction, so the net stays on the tensor-core path (round 1 sent it to the generic
+    kernels).  Against the oracle, and -- with a time offset t0 (a shard of a longer read) -- against the generic path."""
+    torch.manual_seed(31 + C)
+    layers = [(C, C, 2, d) for d in (1, 2, 4)]
+    net = W.RawCTCNet(C, 3, 5, layers, C, positions=True, softmax=False)
+    with torch.no_grad():                          # make the term vary over the read instead of saturating at t = 1
+        net.positions_conv1x1[0].weight.mul_(1e-3).add_(torch.randn(C, 1, 1) * 2e-3)
+        net.positions_conv1x1[0].bias.add_(torch.randn(C) * 0.3)
+    sd = {k: r16(v) for k, v in net.state_dict().items()}
+    from wavenet_speech_b200.utils import signal_gen as SG
+    x = r16(torch.from_numpy(SG.raw_batch(2, 700, seed=5)))
+    ref = O.raw_ctcnet_forward(sd, x, layers, positions=True, softmax=False)
+    ref_nopos = O.raw_ctcnet_forward(sd, x, layers, positions=False, softmax=False)
+    assert G.rel_linf(ref_nopos, ref) > 0.05       # the term matters in this test
+    net = net.cuda().bfloat16().eval()
+    xg = x.cuda().bfloat16()
+    with FP.tc_precision(mode), torch.no_grad():
+        net(xg)                                    # (weight packs are built on the first call)
+        n0 = W._lib.launch_count
+        y = net(xg).float().cpu()
+        assert W._lib.launch_count - n0 <= 12      # featuriser, 1x1, 4 blocks, skip contraction, 2 head launches
+        assert G.rel_linf(y, ref) <= TOL, G.rel_linf(y, ref)
+        y_t0 = net(xg, t0=1234).float().cpu()
+    # the generic path with the same offset (fp32 FFMA kernels on the bf16-rounded parameters)
+    net32 = W.RawCTCNet(C, 3, 5, layers, C, positions=True, softmax=False)
+    net32.load_state_dict(sd)
+    net32 = net32.cuda().eval()
+    with torch.no_grad():
+        g_t0 = net32(x.cuda(), t0=1234).float().cpu()
+    assert G.rel_linf(y_t0, g_t0) <= TOL, G.rel_linf(y_t0, g_t0)
+    assert G.rel_linf(y_t0, y) > 1e-3

@@ -65,7 +65,8 @@ class Dense(_Sized):
                 ("t_off2", ctypes.c_int32 * 3), ("x", c_void_p), ("w", c_void_p),
                 ("bias", c_void_p), ("y", c_void_p), ("x2", c_void_p), ("colsum", c_void_p),
                 ("act_fmt", ctypes.c_int32), ("nlayers", ctypes.c_int32), ("y_lo", c_void_p),
-                ("gb_gate", c_void_p), ("gb_sg", c_void_p)]
+                ("gb_gate", c_void_p), ("gb_sg", c_void_p), ("pos_w", c_void_p), ("pos_b", c_void_p),
+                ("pos_t0", ctypes.c_int32)]
 
 
 class WgradJob(ctypes.Structure):

@@ -44,6 +44,9 @@ struct DenseDev {
   int f16;          // operands (and NLC output) are fp16 instead of bf16 (WNB200_ACT_F16X2)
   int split;        // NLC mode, fp16: the output leaves as an fp16 (hi, lo) pair (map_y, map_ylo)
   int nlayers;      // > 0: x is a stack [nlayers][B][T][Cin] and K runs over (layer, channel): y = sum_l W_l x_l (+ bias)
+  const float* pos_w;    // NLC mode, optional: y += hardtanh(pos_w[c] * (pos_t0 + t) + pos_b[c]) after bias / LeakyReLU
+  const float* pos_b;    // (RawCTCNet position mixing, raw_ctcnet.py:131-135)
+  int pos_t0;
   const bf16* gb_gate;   // gate-backward epilogue (training, NLC mode, bf16): acc is d(gate); with the forward's gate and
   const bf16* gb_sg;     // sigmoid (NLC [B,T,N]) y[.., 0:N] = d(tanh pre-act), y[.., N:2N] = d(sigmoid pre-act); colsum [2N]
 };
@@ -214,8 +217,10 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       mbar_wait(acc_full(r), (uint32_t)(use & 1));
       tc_fence_after();
 
+      const float pos_t = (float)(p.pos_t0 + t0 + row);       // this thread's frame, as the reference's float arange
+      auto pos_term = [&](int ch) { return fminf(1.f, fmaxf(-1.f, fmaf(__ldg(p.pos_w + ch), pos_t, __ldg(p.pos_b + ch)))); };
       if (p.mode == 0) {
-        // -------- (+bias, LeakyReLU) -> bf16 NLC, 64 channels per TMA store --------
+        // -------- (+bias, LeakyReLU [, + position term]) -> bf16 NLC, 64 channels per TMA store --------
         for (int c = 0; c < p.N / 64; ++c, ++nchunk) {
           const int col = c * 64 + h * 32;
           float a[32];
@@ -315,6 +320,7 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
             for (int i = 0; i < 32; i += 2) {
               float v0 = a[i] + bv[i], v1 = a[i + 1] + bv[i + 1];
               if (p.leaky) { v0 = leaky(v0); v1 = leaky(v1); }
+              if (p.pos_w) { v0 += pos_term(col + i); v1 += pos_term(col + i + 1); }
               split_f16x2(v0, v1, pk[i >> 1], pl[i >> 1]);
             }
             if (issuer) bulk_wait_read0();
@@ -340,6 +346,7 @@ dense2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
           for (int i = 0; i < 32; i += 2) {
             float v0 = a[i] + bv[i], v1 = a[i + 1] + bv[i + 1];
             if (p.leaky) { v0 = leaky(v0); v1 = leaky(v1); }
+            if (p.pos_w) { v0 += pos_term(col + i); v1 += pos_term(col + i + 1); }
             pk[i >> 1] = pack_act2(p.f16 != 0, v0, v1);
           }
           const uint32_t boff = (nchunk & 1u) * DN_ABYTES;
@@ -897,6 +904,9 @@ extern "C" int wnb200_dense_fwd_tc(const wnb200_dense_t* a, void* stream) {
                 "dense_fwd_tc: the gate-backward epilogue is an NLC, bf16, linear one");
   WNB_CHECK_ARG(!a->gb_gate || ((reinterpret_cast<uintptr_t>(a->gb_gate) | reinterpret_cast<uintptr_t>(a->gb_sg)) & 15) == 0,
                 "dense_fwd_tc: gb_gate / gb_sg must be 16-byte aligned");
+  WNB_CHECK_ARG((a->pos_w == nullptr) == (a->pos_b == nullptr), "dense_fwd_tc: pos_w and pos_b come together");
+  WNB_CHECK_ARG(!a->pos_w || (a->mode == 0 && !a->gb_gate), "dense_fwd_tc: the position term belongs to the NLC mode");
+  p.pos_w = a->pos_w; p.pos_b = a->pos_b; p.pos_t0 = a->pos_t0;
   p.gb_gate = reinterpret_cast<const bf16*>(a->gb_gate);
   p.gb_sg = reinterpret_cast<const bf16*>(a->gb_sg);
   const int esize = a->out_f32 ? 4 : 2;

@@ -338,13 +338,14 @@ def resblock(x_nlc, pk, res, skips, skips_init, dbg=None, variant=None, save=Non
 
 
 def dense(x_nlc, offsets, w, bias, N, mode=0, leaky=0, out=None, n_out=0, softmax=0, x2=None, offsets2=(), colsum=None,
-          fmt=0, split=False, nlayers=0, gate_bwd=None):
+          fmt=0, split=False, nlayers=0, gate_bwd=None, positions=None):
     """CTA-pair dense contraction.  mode 0 -> NLC bf16 [B,T,N]; mode 1 -> NCL `out` [B,n_out,T].
     Optional second source x2 [B,T,Cin2] with its own taps: its columns follow x's in `w`.
     colsum (mode 0): fp32 [N] tensor that the column sums of the output are ADDED to.
     nlayers: x_nlc is a stack [L, B, T, Cin] and w is [N, L*Cin]: y = epi(sum_l W_l x_l + bias), one contraction.
     gate_bwd = (gate, sigmoid) NLC bf16 [B,T,N]: the result is d(gate) and the epilogue applies the gate's backward:
-    returns NLC bf16 [B,T,2N] = [d tanh-pre-activation | d sigmoid-pre-activation]; colsum is then fp32 [2N]."""
+    returns NLC bf16 [B,T,2N] = [d tanh-pre-activation | d sigmoid-pre-activation]; colsum is then fp32 [2N].
+    positions = (w fp32 [N], b fp32 [N], t0): y += hardtanh(w * (t0 + t) + b) after the LeakyReLU (raw_ctcnet.py:131-135)."""
     if nlayers:
         assert x_nlc.dim() == 4 and x_nlc.shape[0] == nlayers and len(offsets) == 1 and x2 is None
         _L, B, T, Cin = x_nlc.shape
@@ -369,6 +370,10 @@ def dense(x_nlc, offsets, w, bias, N, mode=0, leaky=0, out=None, n_out=0, softma
             out_lo = torch.empty_like(out)
             a.y_lo = out_lo.data_ptr()
     a.act_fmt = fmt
+    if positions is not None:
+        pw, pb, pt0 = positions
+        assert pw.dtype == torch.float32 and pb.dtype == torch.float32 and pw.numel() == N and pb.numel() == N and mode == 0
+        a.pos_w, a.pos_b, a.pos_t0 = pw.data_ptr(), pb.data_ptr(), int(pt0)
     a.nlayers = int(nlayers)
     a.out_f32 = 1 if out.dtype == torch.float32 else 0
     a.x, a.w, a.bias, a.y = x_nlc.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr()
@@ -712,7 +717,7 @@ def _stack_packs(model, precise=False):
 
 
 @range_guard
-def try_raw_ctcnet_forward(model, seq):
+def try_raw_ctcnet_forward(model, seq, t0=0):
     """RawCTCNet.forward (reference raw_ctcnet.py:117-153) on the tensor-core path, or None if not eligible."""
     if not tc_dtype_ok(seq) or not seq.is_cuda or seq.dim() != 3 or seq.shape[1] != 1:
         return None
@@ -720,7 +725,7 @@ def try_raw_ctcnet_forward(model, seq):
     if not _no_graph(model, seq):
         from . import training
         return training.raw_ctcnet_forward_train(model, seq) if training.raw_ctcnet_train_eligible(model, seq) else None
-    if not (F == C and model.out_dim == C and C in (128, 256) and not model.positions
+    if not (F == C and model.out_dim == C and C in (128, 256)
             and _stack_ok(C, model.layers) and model.input_kernel_size <= 3 and model.feature_kwidth * F <= 8192
             and seq.shape[0] > 0 and seq.shape[2] > 0):
         return None
@@ -731,8 +736,12 @@ def try_raw_ctcnet_forward(model, seq):
 
     def build():
         f0, f2 = model.feature_layer[0], model.feature_layer[2]
+        pos = None
+        if model.positions:                       # position mixing rides in the epilogue of the feature layer's 1x1
+            pc = model.positions_conv1x1[0]
+            pos = (pc.weight.detach().float().reshape(-1).contiguous(), pc.bias.detach().float().contiguous())
         return {"f0w": f0.weight.detach().float()[:, 0, :].contiguous(), "f0b": f0.bias.detach().float().contiguous(),
-                "f2w": cast(f2.weight.detach().float()[:, :, 0]), "f2b": f2.bias.detach().float().contiguous(),
+                "f2w": cast(f2.weight.detach().float()[:, :, 0]), "f2b": f2.bias.detach().float().contiguous(), "pos": pos,
                 "blocks": _stack_packs(model, prec), "head": pack_head(model.output_block, C, prec)}
 
     pk = _with_skip(_cached(model, "raw_ctcnet_p" if prec else "raw_ctcnet", build))
@@ -744,10 +753,11 @@ def try_raw_ctcnet_forward(model, seq):
     _lib.call("wnb200_featurize_nlc", ops._dt(seq), B, T, F, fk, ops._p(seq), ops._p(pk["f0w"]), ops._p(pk["f0b"]),
               fmt, ops._p(h), ops._stream())
     h_lo = None
+    pos = None if pk["pos"] is None else (pk["pos"][0], pk["pos"][1], int(t0))
     if prec:
-        h, h_lo = dense(h, [0], pk["f2w"], pk["f2b"], F, leaky=1, fmt=fmt, split=True)
+        h, h_lo = dense(h, [0], pk["f2w"], pk["f2b"], F, leaky=1, fmt=fmt, split=True, positions=pos)
     else:
-        h = dense(h, [0], pk["f2w"], pk["f2b"], F, leaky=1)
+        h = dense(h, [0], pk["f2w"], pk["f2b"], F, leaky=1, positions=pos)
     _, skips_act = run_blocks(h, None, None, pk["blocks"], None, True, True, h_lo=h_lo, skip=pk["skip"])
     return run_head(skips_act, pk["head"], seq.dtype, model.softmax)
 

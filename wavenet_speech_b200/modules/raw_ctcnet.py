@@ -81,11 +81,10 @@ class RawCTCNet(nn.Module):
     def forward(self, seq, t0=0):
         """seq: (batch, 1, T) -> (batch, num_labels, T + feature_kwidth - 1).  `t0` (extension, default 0)
         is the global frame index of seq[..., 0] for position mixing on a time shard."""
-        if t0 == 0:
-            from .. import fastpath
-            y = fastpath.try_raw_ctcnet_forward(self, seq)
-            if y is not None:
-                return y
+        from .. import fastpath
+        y = fastpath.try_raw_ctcnet_forward(self, seq, t0)
+        if y is not None:
+            return y
         out = self.featurize(seq)
         if self.positions:
             pc = self.positions_conv1x1[0]
