@@ -751,6 +751,241 @@ argmax_reg(int C, int Tn, int tiles_per_read, int ntiles, const T* x, long long*
   });
 }
 
+// ------------------------------------------------------------------------------------------ register tiles, unaligned rows
+// Rows whose length is not a multiple of 16 bytes (the train step's T - 1 = 16383 frames, legacy_code/train.py:30) start
+// at a different 2-byte phase in every channel, so no 16-byte load lines up with a frame boundary.  The loads stay
+// ALIGNED instead and the frames shift: channel c's row starts at element e_c = (b C + c) Tn; a thread loads the aligned
+// vector that contains its frames, and position i of vector v holds frame 8v + i - (e_c + t0) mod V of the tile.  That
+// shift is the same for channels 8 apart (8 Tn is a multiple of V), so a thread's channels g, g+32, ... share it, and so
+// do the four channel groups of a WARP when they are w, w+8, w+16, w+24 -- the in-register reduction over channels and
+// the two shuffle steps work unchanged; only the cross-warp step indexes shared memory by frame.  A tile owns 7 vectors
+// of frames (56 in bf16) and loads 8 per channel (12.5 % more L2 -> SM traffic, the same HBM traffic).
+template <typename T, int KC>
+struct RegTileU {
+  static constexpr int V = 16 / sizeof(T);
+  static constexpr int TT = 8 * V;               // positions loaded per channel (and the shared-memory stride)
+  static constexpr int TV = 7 * V;               // frames a tile owns
+  uint4 raw[KC];
+  bool cok[KC];
+  int g, v, shift;
+  long long voff;                                // element offset of this thread's vector of channel g
+  __device__ __forceinline__ void load(const T* x, long long total, int b, int C, int Tn, int t0, uint32_t fill) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    g = warp + 8 * (lane >> 3);
+    v = lane & 7;
+    const long long e = ((long long)b * C + g) * Tn + t0;
+    shift = (int)(e & (V - 1));
+    voff = e - shift + v * V;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const int c = g + 32 * k;
+      cok[k] = c < C;
+      const long long o = voff + (long long)32 * k * Tn;
+      raw[k] = make_uint4(fill, fill, fill, fill);
+      if (cok[k] && o + V <= total) raw[k] = __ldg(reinterpret_cast<const uint4*>(x + o));
+      else if (cok[k]) {                          // the last vector of the tensor: element by element
+        T* e1 = reinterpret_cast<T*>(&raw[k]);
+        for (int i = 0; i < V; ++i)
+          if (o + i < total) e1[i] = x[o + i];
+      }
+    }
+  }
+  // frame (within the tile) of position i, or -1 when it belongs to a neighbouring tile / lies past the row
+  __device__ __forceinline__ void slots(int (&sl)[V], int Tn, int t0) const {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int j = v * V + i - shift;
+      sl[i] = (j >= 0 && j < TV && t0 + j < Tn) ? j : -1;
+    }
+  }
+  __device__ __forceinline__ float get(int k, int i) const { return to_f32<T>(reinterpret_cast<const T*>(&raw[k])[i]); }
+};
+
+template <typename T, int KC>
+__device__ __forceinline__ void tile_max_u(const RegTileU<T, KC>& r, float (&m)[RegTileU<T, KC>::V]) {
+  constexpr int V = RegTileU<T, KC>::V;
+#pragma unroll
+  for (int i = 0; i < V; ++i) m[i] = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < KC; ++k)
+#pragma unroll
+    for (int i = 0; i < V; ++i) m[i] = fmaxf(m[i], r.get(k, i));        // channels past C hold the -inf fill
+}
+
+template <int V, bool MAXOP>
+__device__ __forceinline__ void frames_combine_u(float (&p)[V], const int (&sl)[V], float* red, float* fin) {
+  constexpr int TT = 8 * V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      const float q = __shfl_xor_sync(0xffffffffu, p[i], o);
+      p[i] = MAXOP ? fmaxf(p[i], q) : p[i] + q;
+    }
+    if (lane < 8 && sl[i] >= 0) red[warp * TT + sl[i]] = p[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 7 * V) {                     // every warp has written every owned frame (shift < V)
+    float a = red[threadIdx.x];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      const float q = red[w * TT + threadIdx.x];
+      a = MAXOP ? fmaxf(a, q) : a + q;
+    }
+    fin[threadIdx.x] = a;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < V; ++i) p[i] = sl[i] >= 0 ? fin[sl[i]] : (MAXOP ? 0.f : 1.f);
+}
+
+template <typename T, int KC>
+__device__ __forceinline__ void softmax_stats_u(const RegTileU<T, KC>& r, const int (&sl)[RegTileU<T, KC>::V],
+                                                float (&m)[RegTileU<T, KC>::V], float (&s)[RegTileU<T, KC>::V],
+                                                float* red, float* fin) {
+  constexpr int V = RegTileU<T, KC>::V;
+  tile_max_u(r, m);
+  frames_combine_u<V, true>(m, sl, red, fin);
+  float ml[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { s[i] = 0.f; ml[i] = ExpSub<T>::scale(m[i]); }
+#pragma unroll
+  for (int k = 0; k < KC; ++k)
+#pragma unroll
+    for (int i = 0; i < V; ++i) s[i] += ExpSub<T>::eval(r.get(k, i), ml[i]);
+  frames_combine_u<V, false>(s, sl, red + 8 * 8 * V, fin + 8 * V);
+}
+
+template <typename T, int KC>
+__global__ void __launch_bounds__(CT_THREADS, 2)
+xent_fwd_regu(int C, int Tn, int tiles_per_read, int ntiles, long long total, const T* x, const long long* target,
+              float* loss_bt, float* lse_out) {
+  using RT = RegTileU<T, KC>;
+  constexpr int V = RT::V, TT = RT::TT, TV = RT::TV;
+  __shared__ float red[16 * TT], fin[2 * TT];
+  const int tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  const int b = tile / tiles_per_read, t0 = (tile - b * tiles_per_read) * TV;
+  RT r;
+  r.load(x, total, b, C, Tn, t0, NegInf<T>::bits);
+  // the target's logit comes straight from global memory (the line is in L1 / L2: this CTA loads it)
+  float xt = 0.f;
+  const int tf = t0 + (int)threadIdx.x;
+  if (threadIdx.x < TV && tf < Tn) {
+    long long tg = target[(long long)b * Tn + tf];
+    tg = tg < 0 ? 0 : (tg >= C ? C - 1 : tg);
+    xt = to_f32<T>(__ldg(x + ((long long)b * C + tg) * Tn + tf));
+  }
+  int sl[V];
+  r.slots(sl, Tn, t0);
+  float m[V], sum[V];
+  softmax_stats_u<T, KC>(r, sl, m, sum, red, fin);
+  if (threadIdx.x < TV && tf < Tn) {              // one thread per owned frame: fin = (max | sum) per frame
+    const float lse = fin[threadIdx.x] + logf(fin[8 * V + threadIdx.x]);
+    const long long col = (long long)b * Tn + tf;
+    loss_bt[col] = lse - xt;
+    lse_out[col] = lse;
+  }
+}
+
+template <typename T, int KC>
+__global__ void __launch_bounds__(CT_THREADS, 2)
+xent_bwd_regu(int C, int Tn, int tiles_per_read, int ntiles, long long total, const T* x, const long long* target,
+              const float* lse, const float* gscale, T* dx) {
+  using RT = RegTileU<T, KC>;
+  constexpr int V = RT::V, TV = RT::TV;
+  const int tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  const int b = tile / tiles_per_read, t0 = (tile - b * tiles_per_read) * TV;
+  RT r;
+  r.load(x, total, b, C, Tn, t0, 0u);
+  int sl[V];
+  r.slots(sl, Tn, t0);
+  float l[V];
+  int tg[V];
+  bool any = false, all = true;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    l[i] = 0.f;
+    tg[i] = -1;
+    if (sl[i] >= 0) {
+      const long long col = (long long)b * Tn + t0 + sl[i];
+      l[i] = lse[col];
+      const long long tv = target[col];
+      tg[i] = (int)(tv < 0 ? 0 : (tv >= C ? C - 1 : tv));       // clamped like the forward
+      any = true;
+    } else {
+      all = false;
+    }
+  }
+  if (!any) return;
+  const float gs = *gscale;
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    if (!r.cok[k]) continue;
+    const int c = r.g + 32 * k;
+    uint4 val;
+    T* o = reinterpret_cast<T*>(&val);
+#pragma unroll
+    for (int i = 0; i < V; ++i) o[i] = from_f32<T>((exp_t<T>(r.get(k, i) - l[i]) - (c == tg[i] ? 1.f : 0.f)) * gs);
+    T* dst = dx + r.voff + (long long)32 * k * Tn;
+    if (all) {
+      *reinterpret_cast<uint4*>(dst) = val;       // dx has x's layout and alignment
+    } else {                                      // a vector that straddles a tile or row boundary: its own frames only
+#pragma unroll
+      for (int i = 0; i < V; ++i)
+        if (sl[i] >= 0) dst[i] = o[i];
+    }
+  }
+}
+
+template <typename T, int KC>
+__global__ void __launch_bounds__(CT_THREADS, 2)
+argmax_regu(int C, int Tn, int tiles_per_read, int ntiles, long long total, const T* x, long long* out) {
+  using RT = RegTileU<T, KC>;
+  constexpr int V = RT::V, TT = RT::TT, TV = RT::TV;
+  __shared__ float redv[8 * TT];
+  __shared__ int redc[8 * TT];
+  const int tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  const int b = tile / tiles_per_read, t0 = (tile - b * tiles_per_read) * TV;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  RT r;
+  r.load(x, total, b, C, Tn, t0, NegInf<T>::bits);
+  int sl[V];
+  r.slots(sl, Tn, t0);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    float m = r.cok[0] ? r.get(0, i) : -INFINITY;
+    int a = r.cok[0] ? r.g : C;                     // ascending channels within a thread: strict > keeps the lowest
+#pragma unroll
+    for (int k = 1; k < KC; ++k) {
+      const float val = r.get(k, i);
+      if (r.cok[k] && val > m) { m = val; a = r.g + 32 * k; }
+    }
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+      const int a2 = __shfl_xor_sync(0xffffffffu, a, o);
+      if (a2 < C && (a >= C || m2 > m || (m2 == m && a2 < a))) { m = m2; a = a2; }
+    }
+    if (lane < 8 && sl[i] >= 0) { redv[warp * TT + sl[i]] = m; redc[warp * TT + sl[i]] = a; }
+  }
+  __syncthreads();
+  if (threadIdx.x < TV && t0 + threadIdx.x < Tn) {
+    float M = redv[threadIdx.x];
+    int A = redc[threadIdx.x];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) {
+      const float val = redv[q * TT + threadIdx.x];
+      const int a = redc[q * TT + threadIdx.x];
+      if (a < C && (A >= C || val > M || (val == M && a < A))) { M = val; A = a; }
+    }
+    out[(long long)b * Tn + t0 + threadIdx.x] = A;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 // largest TT in {256 .. 8} such that ntiles tiles of [C x (TT + pad)] elements + scratch fit in `budget` bytes
 static bool pick_geom(int C, int Tn, int esize, int ntiles, TileGeom* g, size_t* smem) {
@@ -847,6 +1082,37 @@ static inline int rt_persistent_grid(long long ntiles) { return (int)ntiles; }
     }                                                                                                      \
   } while (0)
 
+// register tiles on rows that are NOT 16-byte multiples (aligned loads, shifted frames: RegTileU)
+#define RT_TRY_U(KERNEL, P0, P1, ...)                                                                      \
+  do {                                                                                                     \
+    const int esize_ = dtype == WNB200_F32 ? 4 : 2;                                                        \
+    const int TV_ = 7 * (16 / esize_);                                                                     \
+    const long long ntiles_ = (long long)B * ((T_ + TV_ - 1) / TV_);                                       \
+    auto al_ = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };    \
+    if (C <= 256 && (dtype == WNB200_F32 || dtype == WNB200_BF16) && al_(P0) && al_(P1) &&                 \
+        ((long long)T_ * esize_) % 16 != 0 && ntiles_ < (1LL << 31)) {                                     \
+      const int tiles_ = (T_ + TV_ - 1) / TV_;                                                             \
+      const unsigned grid_ = (unsigned)ntiles_;                                                            \
+      const int nt_ = (int)ntiles_;                                                                        \
+      const long long total_ = (long long)B * C * T_;                                                      \
+      cudaStream_t st_ = (cudaStream_t)stream;                                                             \
+      const int kc_ = C <= 64 ? 2 : (C <= 128 ? 4 : 8);                                                    \
+      if (dtype == WNB200_F32) {                                                                           \
+        using T = float;                                                                                   \
+        if (kc_ == 2) KERNEL<T, 2><<<grid_, CT_THREADS, 0, st_>>>(C, T_, tiles_, nt_, total_, __VA_ARGS__);  \
+        else if (kc_ == 4) KERNEL<T, 4><<<grid_, CT_THREADS, 0, st_>>>(C, T_, tiles_, nt_, total_, __VA_ARGS__); \
+        else KERNEL<T, 8><<<grid_, CT_THREADS, 0, st_>>>(C, T_, tiles_, nt_, total_, __VA_ARGS__);           \
+      } else {                                                                                             \
+        using T = bf16;                                                                                    \
+        if (kc_ == 2) KERNEL<T, 2><<<grid_, CT_THREADS, 0, st_>>>(C, T_, tiles_, nt_, total_, __VA_ARGS__);  \
+        else if (kc_ == 4) KERNEL<T, 4><<<grid_, CT_THREADS, 0, st_>>>(C, T_, tiles_, nt_, total_, __VA_ARGS__); \
+        else KERNEL<T, 8><<<grid_, CT_THREADS, 0, st_>>>(C, T_, tiles_, nt_, total_, __VA_ARGS__);           \
+      }                                                                                                    \
+      WNB_LAUNCH_OK();                                                                                     \
+      return 0;                                                                                            \
+    }                                                                                                      \
+  } while (0)
+
 #define CT_LAUNCH(KERNEL, NTILES, P0, P1, P2, FALLBACK, ...)                                               \
   do {                                                                                                     \
     const int esize = dtype == WNB200_F32 ? 4 : 2;                                                         \
@@ -894,6 +1160,7 @@ extern "C" int wnb200_xent_fwd(int dtype, int B, int C, int T_, const void* logi
   WNB_CHECK_ARG(logits && target && loss_bt && lse, "xent_fwd: null pointer");
   if ((long long)B * T_ == 0) return 0;
   RT_TRY_P(xent_fwd_reg, logits, nullptr, (const T*)logits, (const long long*)target, loss_bt, lse);
+  RT_TRY_U(xent_fwd_regu, logits, nullptr, (const T*)logits, (const long long*)target, loss_bt, lse);
   CT_LAUNCH(xent_fwd_tile, 1, logits, nullptr, nullptr,
             wnb200_xent_fwd_col(dtype, B, C, T_, logits, target, loss_bt, lse, stream), (const T*)logits,
             (const long long*)target, loss_bt, lse);
@@ -904,6 +1171,7 @@ extern "C" int wnb200_xent_bwd(int dtype, int B, int C, int T_, const void* logi
   WNB_CHECK_ARG(logits && target && lse && gscale && dlogits, "xent_bwd: null pointer");
   if ((long long)B * T_ == 0) return 0;
   RT_TRY(xent_bwd_reg, logits, dlogits, (const T*)logits, (const long long*)target, lse, gscale, (T*)dlogits);
+  RT_TRY_U(xent_bwd_regu, logits, dlogits, (const T*)logits, (const long long*)target, lse, gscale, (T*)dlogits);
   CT_LAUNCH(xent_bwd_tile, 1, logits, dlogits, nullptr,
             wnb200_xent_bwd_col(dtype, B, C, T_, logits, target, lse, gscale, dlogits, stream), (const T*)logits,
             (const long long*)target, lse, gscale, (T*)dlogits);
@@ -932,6 +1200,7 @@ extern "C" int wnb200_argmax_channels(int dtype, int B, int C, int T_, const voi
   WNB_CHECK_ARG(x && out && C >= 1, "argmax_channels: bad args");
   if ((long long)B * T_ == 0) return 0;
   RT_TRY_P(argmax_reg, x, nullptr, (const T*)x, (long long*)out);
+  RT_TRY_U(argmax_regu, x, nullptr, (const T*)x, (long long*)out);
   CT_LAUNCH(argmax_tile, 1, x, nullptr, nullptr, wnb200_argmax_channels_col(dtype, B, C, T_, x, out, stream),
             (const T*)x, (long long*)out);
 }
