@@ -751,6 +751,58 @@ argmax_reg(int C, int Tn, int tiles_per_read, int ntiles, const T* x, long long*
   });
 }
 
+// Wide variant for bf16 and C <= 256: [C channels x 128 frames] per CTA, thread (g = tid / 16, v = tid % 16) keeps vector
+// v of channels g, g+16, ... (16 loads in flight per thread).  A channel row is 2 T bytes from the next one, so a tile
+// touches C different DRAM pages; 256 bytes per visit instead of 128.
+template <int KC>
+__global__ void __launch_bounds__(CT_THREADS, 2)
+argmax_reg_wide(int C, int Tn, int tiles_per_read, int ntiles, const __nv_bfloat16* x, long long* out) {
+  constexpr int V = 8, TT = 128;
+  __shared__ float redv[8 * TT];
+  __shared__ int redc[8 * TT];
+  const int tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  const int b = tile / tiles_per_read, t0 = (tile - b * tiles_per_read) * TT;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = threadIdx.x >> 4, v = threadIdx.x & 15;
+  const int t = t0 + v * V;
+  const bool tok = t + V <= Tn;
+  const __nv_bfloat16* xb = x + (long long)b * C * Tn;
+  uint4 raw[KC];
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const int c = g + 16 * k;
+    raw[k] = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);
+    if (c < C && tok) raw[k] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)c * Tn + t));
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    float m = -INFINITY;
+    int a = C;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const float val = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(&raw[k])[i]);
+      if (g + 16 * k < C && (a >= C || val > m)) { m = val; a = g + 16 * k; }
+    }
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, 16);
+    const int a2 = __shfl_xor_sync(0xffffffffu, a, 16);
+    if (a2 < C && (a >= C || m2 > m || (m2 == m && a2 < a))) { m = m2; a = a2; }
+    if (lane < 16) { redv[warp * TT + v * V + i] = m; redc[warp * TT + v * V + i] = a; }
+  }
+  __syncthreads();
+  if (threadIdx.x < TT && t0 + threadIdx.x < Tn) {
+    float M = redv[threadIdx.x];
+    int A = redc[threadIdx.x];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) {
+      const float val = redv[q * TT + threadIdx.x];
+      const int a = redc[q * TT + threadIdx.x];
+      if (a < C && (A >= C || val > M || (val == M && a < A))) { M = val; A = a; }
+    }
+    out[(long long)b * Tn + t0 + threadIdx.x] = A;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ register tiles, unaligned rows
 // Rows whose length is not a multiple of 16 bytes (the train step's T - 1 = 16383 frames, legacy_code/train.py:30) start
 // at a different 2-byte phase in every channel, so no 16-byte load lines up with a frame boundary.  The loads stay
@@ -1199,6 +1251,14 @@ extern "C" int wnb200_layernorm_bwd(int dtype, int B, int C, int T_, const void*
 extern "C" int wnb200_argmax_channels(int dtype, int B, int C, int T_, const void* x, int64_t* out, void* stream) {
   WNB_CHECK_ARG(x && out && C >= 1, "argmax_channels: bad args");
   if ((long long)B * T_ == 0) return 0;
+  if (dtype == WNB200_BF16 && C > 128 && C <= 256 && vec_ok(x, nullptr, nullptr, T_, 2) && T_ >= 1024 &&
+      (long long)B * ((T_ + 127) / 128) < (1LL << 31)) {
+    const int tiles = (T_ + 127) / 128;
+    argmax_reg_wide<16><<<(unsigned)((long long)B * tiles), CT_THREADS, 0, (cudaStream_t)stream>>>(
+        C, T_, tiles, B * tiles, (const bf16*)x, (long long*)out);
+    WNB_LAUNCH_OK();
+    return 0;
+  }
   RT_TRY_P(argmax_reg, x, nullptr, (const T*)x, (long long*)out);
   RT_TRY_U(argmax_regu, x, nullptr, (const T*)x, (long long*)out);
   CT_LAUNCH(argmax_tile, 1, x, nullptr, nullptr, wnb200_argmax_channels_col(dtype, B, C, T_, x, out, stream),
