@@ -50,6 +50,14 @@ extern "C" {
 #define WNB200_EPI_LEAKY 1 /* y = LeakyReLU_0.01(acc + bias)   (wavenet.py:67-71)         */
 #define WNB200_EPI_GATE 2  /* y = tanh(acc_t + b_t) * sigmoid(acc_s + b_s) (block.py:185) */
 
+#define WNB200_EPI_MU 3    /* y = g1 * tanh(g2 * h + g3 * u), g_i = sigmoid(acc_i + b_i), u = tanh(acc_4 + b_4)
+                              (MultiplicativeUnit, block.py:213-220); wnb200_taps_fwd_ex only                       */
+
+#define WNB200_PRE_NONE 0   /* source used as stored                                                               */
+#define WNB200_PRE_LEAKY 1  /* LeakyReLU(0.01) applied as the source is loaded (wavenet.py:67-71)                  */
+#define WNB200_PRE_LNRELU 2 /* ReLU(LayerNorm(source)) applied as it is loaded (ByteNet blocks, block.py:103-110,
+                               150-160); needs the source's wnb200_ln_t; wnb200_taps_fwd_ex / _wgrad_ex only        */
+
 #define WNB200_MAX_SRC 4
 
 /* One (input tensor, weight slab, time offset) term of a tap-sum contraction. */
@@ -61,8 +69,37 @@ typedef struct {
   int32_t C;            /* channels contracted                                            */
   int32_t T_src;        /* valid time extent of x; reads outside [0, T_src) give 0        */
   int32_t t_off;        /* output frame t reads x[.., t + t_off]                          */
-  int32_t pre_act;      /* 1: LeakyReLU(0.01) applied to x as it is loaded, 0: none        */
+  int32_t pre_act;      /* WNB200_PRE_*                                                   */
 } wnb200_src_t;
+
+/* LayerNorm (layernorm.py:25-28) of a source, for WNB200_PRE_LNRELU: per-frame statistics written by wnb200_ln_stats
+ * and the module's gamma / beta. */
+typedef struct {
+  const float* stats; /* [B, T_src, 2] = (mean over channels, 1 / (unbiased std + eps)) */
+  const float* gamma; /* [C] */
+  const float* beta;  /* [C] */
+} wnb200_ln_t;
+
+/* Arguments of wnb200_taps_fwd_ex: wnb200_taps_fwd's plus the ByteNet fusions. */
+typedef struct {
+  uint32_t struct_size; /* = sizeof(wnb200_taps_t) */
+  int32_t dtype, B, T_out, M, nsrc;
+  int32_t epilogue;     /* WNB200_EPI_* */
+  int32_t accumulate;
+  const wnb200_src_t* srcs; /* host, nsrc entries */
+  const wnb200_ln_t* ln;    /* host, nsrc entries (read for sources with WNB200_PRE_LNRELU), or NULL */
+  const float* bias;
+  void* out;
+  void* th;
+  void* sg;
+  const void* residual; /* [B, M, T_out], added to the result after the epilogue (`seq + stack(seq)`, block.py:119,166);
+                           NULL: none; not with EPI_GATE */
+  const void* mu_h;     /* EPI_MU: h [B, M, T_out].  Weight rows / bias are packed per 32 channels as
+                           rows [0, 64): channel r / 4 of the group, unit r % 4 in the order (gate1, gate2, gate3, update),
+                           rows [64, 128): channel 16 + (r - 64) / 4 likewise: 4 * ceil(M / 32) * 32 rows */
+  int32_t mu_h_ln;      /* EPI_MU: 1 = mu_h is source 0's raw tensor and its LayerNorm + ReLU is applied on the fly */
+  int32_t reserved0;
+} wnb200_taps_t;
 
 const char* wnb200_last_error(void);
 int wnb200_version(void);
@@ -84,10 +121,16 @@ int wnb200_taps_fwd(int dtype, int B, int T_out, int M, int nsrc, const wnb200_s
                     const float* bias, int epilogue, int accumulate, void* out, void* th, void* sg,
                     void* stream);
 
+int wnb200_taps_fwd_ex(const wnb200_taps_t* args /*host*/, void* stream);
+
 /* dW[m, c] += sum_{b,t} dout[b, m, t] * pre(x[b, c, t + t_off]) ; dout is contiguous [B, M, T_out].
  * Weight gradient of every conv / linear above (autograd of conv_ops.py:43, block.py:73-78). */
 int wnb200_taps_wgrad(int dtype, int B, int T_out, int M, const wnb200_src_t* src /*host, w unused*/,
                       const void* dout, float* dw, void* stream);
+
+/* The same with a wnb200_ln_t for a source with WNB200_PRE_LNRELU (ln may be NULL otherwise). */
+int wnb200_taps_wgrad_ex(int dtype, int B, int T_out, int M, const wnb200_src_t* src /*host, w unused*/,
+                         const wnb200_ln_t* ln /*host*/, const void* dout, float* dw, void* stream);
 
 /* out[c] += sum_{b,t} a[b,c,t] * (b_or_null ? b[b,c,t] : 1)   (bias / gamma / beta gradients) */
 int wnb200_channel_reduce(int dtype, int B, int C, int T, const void* a, const void* b_or_null,
@@ -474,6 +517,31 @@ int wnb200_ncl_to_nlc_bf16_strided(int dtype, int B, int C, int T, int64_t sb, i
 int wnb200_ncl_to_nlc_act(int dtype, int act_fmt, int B, int C, int T, int64_t sb, int64_t sc, const void* x, void* y,
                           void* stream);
 int wnb200_nlc_to_ncl(int out_dtype, int src_is_f32, int B, int C, int T, const void* x, void* y, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ByteNet residual blocks (block.py:86-173) and the frame-at-a-time LinearConv1d (linear_conv_ops.py:39-68).
+ * ln_stats:    stats[b, t] = (mean_c x[b, c, t], 1 / (unbiased std_c + eps))   (layernorm.py:25-28); x contiguous [B, C, T].
+ *              A contraction reads the normalised, rectified tensor through WNB200_PRE_LNRELU without it ever being stored.
+ * ln_relu_fwd: y = ReLU(gamma * (x - mean) * r + beta) stored (training keeps it for the MultiplicativeUnit's backward).
+ * ln_relu_bwd: dy = gradient w.r.t. that y -> dx (may be NULL), dgamma / dbeta += (fp32 [C], may be NULL).
+ * ------------------------------------------------------------------------------------------ */
+int wnb200_ln_stats(int dtype, int B, int C, int T, const void* x, float eps, float* stats, void* stream);
+int wnb200_ln_relu_fwd(int dtype, int B, int C, int T, const void* x, const float* stats, const float* gamma,
+                       const float* beta, void* y, void* stream);
+int wnb200_ln_relu_bwd(int dtype, int B, int C, int T, const void* x, const float* stats, const float* gamma,
+                       const float* beta, float eps, const void* dy, void* dx, float* dgamma, float* dbeta, void* stream);
+
+/* LinearConv1d.linear (linear_conv_ops.py:39-68): y[n, m] = bias[m] + sum_{c, j} w[m, c, j] * frame[n, c, j * dilation],
+ * frame [N, Cin, rf] with rf = k + (dilation - 1) * (k - 1), w [Cout, Cin, k], y [N, Cout]; k <= 32. */
+int wnb200_linear_frame(int dtype, int N, int Cin, int Cout, int k, int dilation, const void* w, const float* bias,
+                        const void* frame, void* y, void* stream);
+/* The same frame evaluated incrementally: the caller hands over frame number `step` (x [N, Cin]) and a history ring
+ * hist [rf, N, Cin] (zero before step 0, owned by the caller, rf = (k - 1) * dilation + 1); the call computes
+ * y[n, :] from x and the k - 1 earlier frames the kernel's taps address, and files x in the ring.  A decoder that
+ * emits one frame per step (bytenet_decoder.py:146-186 re-evaluates its whole receptive field per step) does O(k)
+ * instead of O(rf) work per layer and step. */
+int wnb200_linear_step(int dtype, int N, int Cin, int Cout, int k, int dilation, int64_t step, const void* w,
+                       const float* bias, const void* x, void* hist, void* y, void* stream);
 
 #ifdef __cplusplus
 }

@@ -250,6 +250,41 @@ def multiplicative_unit(sd, prefix, h, d):
     return g1.mul(torch.tanh(g2.mul(h) + g3.mul(u)))
 
 
+def residual_relu_block(sd, prefix, x, d):
+    """modules/block.py:130-173 (ResidualReLUBlock.forward): x + [LN, ReLU, 1x1 (C -> C/2), LN, ReLU, causal conv
+    (k, d), LN, ReLU, 1x1 (C/2 -> C)](x).  `stack.{i}` are the reference's nn.Sequential indices."""
+    s = prefix + "stack."
+    h = torch.relu(layernorm(x, sd[s + "0.gamma"], sd[s + "0.beta"]))
+    h = F.conv1d(h, sd[s + "2.weight"], sd[s + "2.bias"])
+    h = torch.relu(layernorm(h, sd[s + "3.gamma"], sd[s + "3.beta"]))
+    h = causal_conv1d(h, sd[s + "5.conv1d.weight"], sd[s + "5.conv1d.bias"], d)
+    h = torch.relu(layernorm(h, sd[s + "6.gamma"], sd[s + "6.beta"]))
+    h = F.conv1d(h, sd[s + "8.weight"], sd[s + "8.bias"])
+    return x + h
+
+
+def residual_mu_block(sd, prefix, x, d):
+    """modules/block.py:86-126 (ResidualMUBlock.forward): x + [LN, ReLU, 1x1 (C -> C/2), LN, ReLU, MU(k, d), MU(1),
+    1x1 (C/2 -> C)](x)."""
+    s = prefix + "stack."
+    h = torch.relu(layernorm(x, sd[s + "0.gamma"], sd[s + "0.beta"]))
+    h = F.conv1d(h, sd[s + "2.weight"], sd[s + "2.bias"])
+    h = torch.relu(layernorm(h, sd[s + "3.gamma"], sd[s + "3.beta"]))
+    h = multiplicative_unit(sd, s + "5.", h, d)
+    h = multiplicative_unit(sd, s + "6.", h, 1)
+    h = F.conv1d(h, sd[s + "7.weight"], sd[s + "7.bias"])
+    return x + h
+
+
+def linear_conv1d_stream(seq, w, b, d):
+    """LinearConv1d.linear (modules/linear_conv_ops.py:39-68) on every causal window of `seq` (zeros before the
+    first frame): the frame-at-a-time evaluation a decoder asks for.  -> (batch, c_out, T)."""
+    k = w.shape[2]
+    rf = k + (d - 1) * (k - 1)
+    padded = torch.cat([seq.new_zeros(seq.shape[0], seq.shape[1], rf - 1), seq], 2)
+    return torch.stack([linear_conv1d_linear(padded[:, :, t:t + rf], w, b, d) for t in range(seq.shape[2])], 2)
+
+
 # ----------------------------------------------------------------------------
 # losses / decode (legacy_code/train.py, modules/sequence_decoders.py)
 # ----------------------------------------------------------------------------

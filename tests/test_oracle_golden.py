@@ -91,6 +91,34 @@ def test_layernorm_linearconv_mu():
     _exact(O.multiplicative_unit(g["sd"], "", g["inp"]["x"], g["meta"]["d"]), g["out"]["y"])
 
 
+@pytest.mark.parametrize("name", [n for n in G.names() if n.startswith("bytenet_")])
+def test_bytenet_blocks_and_their_gradients(name):
+    """ResidualReLUBlock / ResidualMUBlock (block.py:86-173): outputs AND the gradients torch autograd wrote through the
+    reference module, reproduced by autograd through the oracle."""
+    g = G.load(name)
+    fn = O.residual_mu_block if "_mu_" in name else O.residual_relu_block
+    sd = {k: v.clone().requires_grad_(True) for k, v in g["sd"].items()}
+    x = g["inp"]["x"].clone().requires_grad_(True)
+    y = fn(sd, "", x, g["meta"]["d"])
+    _exact(y.detach(), g["out"]["y"])
+    (y * g["inp"]["probe"]).sum().backward()
+    assert torch.allclose(x.grad, g["out"]["grad_x"], rtol=1e-4, atol=1e-6)
+    for k, v in sd.items():
+        ref = g["out"]["grad/" + k]
+        assert torch.allclose(v.grad, ref, rtol=1e-4, atol=1e-5 * float(ref.abs().max()) + 1e-7), k
+
+
+@pytest.mark.parametrize("name", [n for n in G.names() if n.startswith("linearconv_stream")])
+def test_linearconv_stream(name):
+    g = G.load(name)
+    y = O.linear_conv1d_stream(g["inp"]["seq"], g["sd"]["weight"], g["sd"]["bias"], g["meta"]["d"])
+    _exact(y, g["out"]["y"])
+    # frame-at-a-time evaluation == the causal convolution (conv_ops.py:39-44) of the whole sequence
+    # (another summation order: held to fp32 round-off, not bit for bit)
+    yc = O.causal_conv1d(g["inp"]["seq"], g["sd"]["weight"], g["sd"]["bias"], g["meta"]["d"])
+    assert torch.allclose(yc, g["out"]["y"], rtol=1e-5, atol=1e-6), float((yc - g["out"]["y"]).abs().max())
+
+
 def test_ctc_known_answers():
     # reference tests/test_classifier.py:53-59 -> 2.4628 ; ipynbs/CTC Overfit.ipynb cell 27 -> 1.4519
     acts = torch.tensor([[[.1, .6, .1, .1, .1]], [[.1, .1, .6, .1, .1]]])

@@ -31,6 +31,20 @@ class Src(ctypes.Structure):
                 ("pre_act", ctypes.c_int32)]
 
 
+class Ln(ctypes.Structure):
+    """Mirror of wnb200_ln_t."""
+    _fields_ = [("stats", c_void_p), ("gamma", c_void_p), ("beta", c_void_p)]
+
+
+class Taps(_Sized):
+    """Mirror of wnb200_taps_t."""
+    _fields_ = [("struct_size", ctypes.c_uint32), ("dtype", ctypes.c_int32), ("B", ctypes.c_int32),
+                ("T_out", ctypes.c_int32), ("M", ctypes.c_int32), ("nsrc", ctypes.c_int32),
+                ("epilogue", ctypes.c_int32), ("accumulate", ctypes.c_int32), ("srcs", ctypes.POINTER(Src)),
+                ("ln", ctypes.POINTER(Ln)), ("bias", c_void_p), ("out", c_void_p), ("th", c_void_p), ("sg", c_void_p),
+                ("residual", c_void_p), ("mu_h", c_void_p), ("mu_h_ln", ctypes.c_int32), ("reserved0", ctypes.c_int32)]
+
+
 class Chain(_Sized):
     """Mirror of wnb200_chain_t."""
     _fields_ = [("struct_size", ctypes.c_uint32),
@@ -97,6 +111,16 @@ SIGNATURES = {
     "wnb200_check_device": [],
     "wnb200_taps_fwd": [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(Src), c_void_p, c_int, c_int,
                         c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_taps_fwd_ex": [ctypes.POINTER(Taps), c_void_p],
+    "wnb200_taps_wgrad_ex": [c_int, c_int, c_int, c_int, ctypes.POINTER(Src), ctypes.POINTER(Ln), c_void_p, c_void_p,
+                             c_void_p],
+    "wnb200_ln_stats": [c_int, c_int, c_int, c_int, c_void_p, ctypes.c_float, c_void_p, c_void_p],
+    "wnb200_ln_relu_fwd": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_ln_relu_bwd": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_float, c_void_p,
+                           c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_linear_frame": [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "wnb200_linear_step": [c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                           c_void_p, c_void_p],
     "wnb200_taps_wgrad": [c_int, c_int, c_int, c_int, ctypes.POINTER(Src), c_void_p, c_void_p, c_void_p],
     "wnb200_channel_reduce": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_gate_bwd": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],

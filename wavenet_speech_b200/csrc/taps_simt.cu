@@ -12,6 +12,8 @@
 // register micro-tiles, register-prefetch double buffering through shared memory.
 // Zero padding of the reference (conv1d padding at the true sequence ends) = the bounds check
 // on t + off_s; the columns the reference computes and slices away are never computed.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace wnb {
@@ -23,6 +25,10 @@ struct SrcDev {
   const void* w;
   long long bs, cs;
   int C, T_src, t_off, pre_act;
+  // pre_act == WNB200_PRE_LNRELU: relu(gamma[c] * (x - mean[b,t]) * r[b,t] + beta[c]) as the source is loaded
+  const float* ln_stats;   // [B, T_src, 2] = (mean, 1 / (std + eps))
+  const float* ln_gamma;   // [C]
+  const float* ln_beta;    // [C]
 };
 
 struct TapsParams {
@@ -33,7 +39,39 @@ struct TapsParams {
   void* out;
   void* th;
   void* sg;
+  const void* residual;    // [B, M, T_out] added to the result (ByteNet blocks' `seq + stack(seq)`), or null
+  const void* mu_h;        // EPI_MU: h of g1 * tanh(g2 * h + g3 * u), [B, M, T_out]
+  int mu_h_ln;             // EPI_MU: mu_h is source 0's raw tensor, its LayerNorm + ReLU is applied on the fly
 };
+
+// the transform a source undergoes on its way into the contraction
+__device__ __forceinline__ float pre_transform(const SrcDev& S, float v, int b, int c, int t) {
+  if (S.pre_act == WNB200_PRE_LEAKY) return leaky(v);
+  if (S.pre_act == WNB200_PRE_LNRELU) {
+    const float2 st = *reinterpret_cast<const float2*>(S.ln_stats + ((long long)b * S.T_src + t) * 2);
+    return fmaxf(S.ln_gamma[c] * (v - st.x) * st.y + S.ln_beta[c], 0.f);
+  }
+  return v;
+}
+
+template <typename T>
+__device__ __forceinline__ void add_row4(const T* base, long long idx, int t, int T_out, float v[4], bool vec_ok) {
+  if (t >= T_out) return;
+  const T* p = base + idx;
+  if (vec_ok && t + 3 < T_out) {
+    if constexpr (sizeof(T) == 4) {
+      const float4 r = *reinterpret_cast<const float4*>(p);
+      v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] += to_f32<T>(p[i]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (t + i < T_out) v[i] += to_f32<T>(p[i]);
+  }
+}
 
 template <typename T>
 __device__ __forceinline__ void store_row4(T* base, long long idx, int t, int T_out, const float v[4],
@@ -112,7 +150,7 @@ __global__ void __launch_bounds__(NT, 2) taps_fwd_kernel(const TapsParams p) {
       float v = 0.f;
       if (c < S.C && t >= 0 && t < S.T_src) {
         v = to_f32<T>(x[t]);
-        if (S.pre_act) v = leaky(v);
+        if (S.pre_act) v = pre_transform(S, v, b, c, t);
       }
       rb[i] = v;
     }
@@ -184,6 +222,42 @@ __global__ void __launch_bounds__(NT, 2) taps_fwd_kernel(const TapsParams p) {
         if (sg) store_row4<T>(sg, rowbase + t, t, p.T_out, vs, false, vec_ok);
       }
     }
+  } else if constexpr (EPI == WNB200_EPI_MU) {
+    // MultiplicativeUnit (block.py:213-220): a 128-row tile holds 32 channels x (gate1, gate2, gate3, update); a thread's
+    // rows [ty*4, ty*4+4) are the four pre-activations of channel ty, rows [64+ty*4, ..+4) those of channel 16+ty
+    const T* hsrc = reinterpret_cast<const T*>(p.mu_h);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int ch = blockIdx.y * 32 + half * 16 + ty;
+      if (ch >= p.M) continue;
+      const int r0 = row0 + half * 64 + ty * 4;
+      float bi[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) bi[q] = p.bias ? p.bias[r0 + q] : 0.f;
+      const long long rowbase = ((long long)b * p.M + ch) * p.T_out;
+      const SrcDev& S0 = p.src[0];
+      const T* hrow = p.mu_h_ln ? hsrc + (long long)b * S0.bs + (long long)ch * S0.cs : hsrc + rowbase;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int t = t0 + h * 64 + tx * 4;
+        float vo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          vo[j] = 0.f;
+          if (t + j < p.T_out) {
+            float hv = to_f32<T>(hrow[t + j]);
+            if (p.mu_h_ln) hv = pre_transform(S0, hv, b, ch, t + j);
+            const float g1 = sigmoid_precise(acc[half * 4 + 0][h * 4 + j] + bi[0]);
+            const float g2 = sigmoid_precise(acc[half * 4 + 1][h * 4 + j] + bi[1]);
+            const float g3 = sigmoid_precise(acc[half * 4 + 2][h * 4 + j] + bi[2]);
+            const float u = tanhf(acc[half * 4 + 3][h * 4 + j] + bi[3]);
+            vo[j] = g1 * tanhf(g2 * hv + g3 * u);
+          }
+        }
+        if (p.residual) add_row4<T>(reinterpret_cast<const T*>(p.residual), rowbase + t, t, p.T_out, vo, vec_ok);
+        store_row4<T>(out, rowbase + t, t, p.T_out, vo, p.accumulate != 0, vec_ok);
+      }
+    }
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -201,6 +275,7 @@ __global__ void __launch_bounds__(NT, 2) taps_fwd_kernel(const TapsParams p) {
           if (EPI == WNB200_EPI_LEAKY) v = leaky(v);
           vo[j] = v;
         }
+        if (p.residual) add_row4<T>(reinterpret_cast<const T*>(p.residual), rowbase + t, t, p.T_out, vo, vec_ok);
         store_row4<T>(out, rowbase + t, t, p.T_out, vo, p.accumulate != 0, vec_ok);
       }
     }
@@ -253,7 +328,7 @@ __global__ void __launch_bounds__(256) taps_wgrad_kernel(const WgradParams p) {
         const int tsrc = t + p.src.t_off;
         if (c_ok && tsrc >= 0 && tsrc < p.src.T_src) {
           xv = to_f32<T>(x[tsrc]);
-          if (p.src.pre_act) xv = leaky(xv);
+          if (p.src.pre_act) xv = pre_transform(p.src, xv, b, c0 + l_row, tsrc);
         }
       }
       Ds[l_t + i][l_row] = dv;
@@ -310,9 +385,15 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(int B, int C, int T
   }
 }
 
-static int fill_src(SrcDev& d, const wnb200_src_t& s) {
+static int fill_src(SrcDev& d, const wnb200_src_t& s, const wnb200_ln_t* ln) {
   d.x = s.x; d.w = s.w; d.bs = s.batch_stride; d.cs = s.chan_stride;
   d.C = s.C; d.T_src = s.T_src; d.t_off = s.t_off; d.pre_act = s.pre_act;
+  d.ln_stats = d.ln_gamma = d.ln_beta = nullptr;
+  WNB_CHECK_ARG(s.pre_act >= WNB200_PRE_NONE && s.pre_act <= WNB200_PRE_LNRELU, "taps: bad pre_act %d", s.pre_act);
+  if (s.pre_act == WNB200_PRE_LNRELU) {
+    WNB_CHECK_ARG(ln && ln->stats && ln->gamma && ln->beta, "taps: a source with PRE_LNRELU needs its wnb200_ln_t");
+    d.ln_stats = ln->stats; d.ln_gamma = ln->gamma; d.ln_beta = ln->beta;
+  }
   return 0;
 }
 
@@ -323,6 +404,7 @@ static int launch_taps(const TapsParams& p, int epilogue, cudaStream_t st) {
     case WNB200_EPI_NONE: taps_fwd_kernel<T, WNB200_EPI_NONE><<<grid, NT, 0, st>>>(p); break;
     case WNB200_EPI_LEAKY: taps_fwd_kernel<T, WNB200_EPI_LEAKY><<<grid, NT, 0, st>>>(p); break;
     case WNB200_EPI_GATE: taps_fwd_kernel<T, WNB200_EPI_GATE><<<grid, NT, 0, st>>>(p); break;
+    case WNB200_EPI_MU: taps_fwd_kernel<T, WNB200_EPI_MU><<<grid, NT, 0, st>>>(p); break;
     default: set_error("taps_fwd: bad epilogue %d", epilogue); return 1;
   }
   WNB_LAUNCH_OK();
@@ -333,35 +415,57 @@ static int launch_taps(const TapsParams& p, int epilogue, cudaStream_t st) {
 
 using namespace wnb;
 
-extern "C" int wnb200_taps_fwd(int dtype, int B, int T_out, int M, int nsrc, const wnb200_src_t* srcs,
-                               const float* bias, int epilogue, int accumulate, void* out, void* th,
-                               void* sg, void* stream) {
+extern "C" int wnb200_taps_fwd_ex(const wnb200_taps_t* a, void* stream) {
+  WNB_CHECK_ARG(a != nullptr, "taps_fwd_ex: null args");
+  WNB_CHECK_STRUCT(a, wnb200_taps_t, "taps_fwd_ex");
+  const int dtype = a->dtype, B = a->B, T_out = a->T_out, M = a->M, nsrc = a->nsrc, epilogue = a->epilogue;
   WNB_CHECK_ARG(dtype == WNB200_F32 || dtype == WNB200_BF16, "taps_fwd: bad dtype %d", dtype);
   WNB_CHECK_ARG(nsrc >= 1 && nsrc <= WNB200_MAX_SRC, "taps_fwd: nsrc %d out of range", nsrc);
   WNB_CHECK_ARG(B >= 0 && T_out >= 0 && M >= 1, "taps_fwd: bad shape B=%d T=%d M=%d", B, T_out, M);
   if (B == 0 || T_out == 0) return 0;
-  WNB_CHECK_ARG(out != nullptr && srcs != nullptr, "taps_fwd: null pointer");
+  WNB_CHECK_ARG(a->out != nullptr && a->srcs != nullptr, "taps_fwd: null pointer");
   WNB_CHECK_ARG(B <= 65535, "taps_fwd: batch %d > 65535", B);
   TapsParams p;
   p.B = B; p.T_out = T_out; p.M = M; p.nsrc = nsrc;
-  p.rows = (epilogue == WNB200_EPI_GATE) ? 2 * ceil_div(M, 64) * 64 : M;
+  p.rows = (epilogue == WNB200_EPI_GATE) ? 2 * ceil_div(M, 64) * 64
+         : (epilogue == WNB200_EPI_MU) ? 4 * ceil_div(M, 32) * 32 : M;
   for (int s = 0; s < nsrc; ++s) {
-    WNB_CHECK_ARG(srcs[s].x && srcs[s].w && srcs[s].C >= 1, "taps_fwd: source %d invalid", s);
-    fill_src(p.src[s], srcs[s]);
+    WNB_CHECK_ARG(a->srcs[s].x && a->srcs[s].w && a->srcs[s].C >= 1, "taps_fwd: source %d invalid", s);
+    if (fill_src(p.src[s], a->srcs[s], a->ln ? a->ln + s : nullptr)) return 1;
   }
-  p.bias = bias; p.accumulate = accumulate; p.out = out; p.th = th; p.sg = sg;
+  p.bias = a->bias; p.accumulate = a->accumulate; p.out = a->out; p.th = a->th; p.sg = a->sg;
+  p.residual = a->residual; p.mu_h = a->mu_h; p.mu_h_ln = a->mu_h_ln;
+  if (epilogue == WNB200_EPI_MU) {
+    WNB_CHECK_ARG(a->mu_h != nullptr, "taps_fwd: EPI_MU needs mu_h");
+    WNB_CHECK_ARG(!a->mu_h_ln || (a->srcs[0].pre_act == WNB200_PRE_LNRELU && a->srcs[0].C == M &&
+                                  a->srcs[0].T_src == T_out && a->mu_h == a->srcs[0].x),
+                  "taps_fwd: mu_h_ln wants mu_h == source 0 (C == M, T_src == T_out) with PRE_LNRELU");
+  }
+  WNB_CHECK_ARG(!(a->residual && epilogue == WNB200_EPI_GATE), "taps_fwd: residual is not available with EPI_GATE");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return dtype == WNB200_F32 ? launch_taps<float>(p, epilogue, st) : launch_taps<__nv_bfloat16>(p, epilogue, st);
 }
 
-extern "C" int wnb200_taps_wgrad(int dtype, int B, int T_out, int M, const wnb200_src_t* src, const void* dout,
-                                 float* dw, void* stream) {
+extern "C" int wnb200_taps_fwd(int dtype, int B, int T_out, int M, int nsrc, const wnb200_src_t* srcs,
+                               const float* bias, int epilogue, int accumulate, void* out, void* th,
+                               void* sg, void* stream) {
+  wnb200_taps_t a;
+  memset(&a, 0, sizeof(a));
+  a.struct_size = sizeof(a);
+  a.dtype = dtype; a.B = B; a.T_out = T_out; a.M = M; a.nsrc = nsrc; a.epilogue = epilogue; a.accumulate = accumulate;
+  a.srcs = srcs; a.bias = bias; a.out = out; a.th = th; a.sg = sg;
+  WNB_CHECK_ARG(epilogue != WNB200_EPI_MU, "taps_fwd: EPI_MU goes through wnb200_taps_fwd_ex");
+  return wnb200_taps_fwd_ex(&a, stream);
+}
+
+extern "C" int wnb200_taps_wgrad_ex(int dtype, int B, int T_out, int M, const wnb200_src_t* src, const wnb200_ln_t* ln,
+                                    const void* dout, float* dw, void* stream) {
   WNB_CHECK_ARG(dtype == WNB200_F32 || dtype == WNB200_BF16, "taps_wgrad: bad dtype %d", dtype);
   if (B == 0 || T_out == 0) return 0;
   WNB_CHECK_ARG(src && src->x && dout && dw, "taps_wgrad: null pointer");
   WgradParams p;
   p.B = B; p.T_out = T_out; p.M = M; p.nchunk = ceil_div(T_out, WG_CHUNK);
-  fill_src(p.src, *src);
+  if (fill_src(p.src, *src, ln)) return 1;
   p.dout = dout; p.dw = dw;
   WNB_CHECK_ARG((long long)B * p.nchunk <= 65535, "taps_wgrad: too many splits");
   dim3 grid(ceil_div(src->C, 64), ceil_div(M, 64), B * p.nchunk);
@@ -370,6 +474,11 @@ extern "C" int wnb200_taps_wgrad(int dtype, int B, int T_out, int M, const wnb20
   else taps_wgrad_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);
   WNB_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int wnb200_taps_wgrad(int dtype, int B, int T_out, int M, const wnb200_src_t* src, const void* dout,
+                                 float* dw, void* stream) {
+  return wnb200_taps_wgrad_ex(dtype, B, T_out, M, src, nullptr, dout, dw, stream);
 }
 
 extern "C" int wnb200_channel_reduce(int dtype, int B, int C, int T, const void* a, const void* b_or_null,

@@ -7,7 +7,7 @@ Offsets follow the reference exactly: see `tap_offsets`.
 import torch
 
 from . import ops
-from .ops import EPI_GATE, EPI_LEAKY, EPI_NONE, Term
+from .ops import EPI_GATE, EPI_LEAKY, EPI_MU, EPI_NONE, PRE_LNRELU, Term
 
 
 # --------------------------------------------------------------------------- offsets
@@ -473,10 +473,157 @@ class _MUGate(torch.autograd.Function):
 def multiplicative_unit(h, convs, offsets):
     """MultiplicativeUnit.forward: ONE tap-sum launch for the four causal convolutions (their filters stacked on
     the output-channel axis) + one gate launch.  convs = (gate1, gate2, gate3, update) nn.Conv1d holders."""
+    if len(offsets) <= ops.MAX_SRC and not needs_grad(h, *[q for c in convs for q in (c.weight, c.bias)]):
+        return multiplicative_unit_fused(h, convs, offsets)       # inference: the gate is the contraction's epilogue
     w = torch.cat([c.weight for c in convs], 0)
     b = torch.cat([c.bias for c in convs], 0)
     pre = conv_taps(h, w, b, offsets)
     return _MUGate.apply(pre, h)
+
+
+# --------------------------------------------------------------------------- ByteNet blocks (block.py:86-173)
+def _flat32(p):
+    return _cached_layout([p], "flat32", torch.float32, lambda: p.detach().float().reshape(-1).contiguous())
+
+
+class _FusedConv(torch.autograd.Function):
+    """out = bias + sum_j W[:, :, j] @ pre(x)[.., t + off_j]  (+ residual), with pre = ReLU(LayerNorm(.)) applied AS THE
+    OPERAND IS LOADED when gamma / beta are given: the normalised tensor of the reference's
+    [LayerNorm, ReLU, conv] triples (block.py:103-105, 108-110, 150-160) is never stored.  Launches: statistics +
+    contraction; backward: transposed contraction, LayerNorm+ReLU backward (dx, dgamma, dbeta in one pass), weight
+    gradients with the same on-the-fly operand."""
+
+    @staticmethod
+    def forward(ctx, cfg, x, gamma, beta, weight, bias, residual):
+        x = x.contiguous()
+        dtype = x.dtype
+        M = weight.shape[0]
+        T = x.shape[2]
+        offs = cfg["offsets"]
+        ln = None
+        if gamma is not None:
+            ln = (ops.ln_stats(x, cfg["eps"]), _flat32(gamma), _flat32(beta))
+        slabs = _slabs(weight, dtype)
+        pre = PRE_LNRELU if ln is not None else 0
+        terms = [Term(x, slabs[j], off, pre, ln) for j, off in enumerate(offs)]
+        res = None if residual is None else residual.contiguous()
+        out = ops.taps_fwd(terms, _f32(bias), M, T, residual=res)
+        ctx.cfg = cfg
+        ctx.bias_dtype = None if bias is None else bias.dtype
+        ctx.save_for_backward(x, weight, gamma, beta, None if ln is None else ln[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        cfg = ctx.cfg
+        x, weight, gamma, beta, stats = ctx.saved_tensors
+        offs = cfg["offsets"]
+        dout = dout.contiguous()
+        dtype = dout.dtype
+        M, T = dout.shape[1], dout.shape[2]
+        C = x.shape[1]
+        ln = None
+        if gamma is not None:
+            ln = (stats, _flat32(gamma), _flat32(beta))
+        need = ctx.needs_input_grad          # (cfg, x, gamma, beta, weight, bias, residual)
+        dx = dgamma = dbeta = dw = db = None
+        if need[1] or need[2] or need[3]:
+            wt = _slabs_t(weight, dtype)
+            dh = ops.taps_fwd([Term(dout, wt[j], -off) for j, off in enumerate(offs)], None, C, T)
+            if ln is None:
+                dx = dh
+            else:
+                dx, dg, dbt = ops.ln_relu_bwd(x, ln[0], ln[1], ln[2], cfg["eps"], dh, want_dx=need[1])
+                dgamma = dg.view(gamma.shape).to(gamma.dtype)
+                dbeta = dbt.view(gamma.shape).to(gamma.dtype)
+        if need[4]:
+            k = len(offs)
+            dwk = torch.zeros((k, M, C), dtype=torch.float32, device=dout.device)
+            for j, off in enumerate(offs):
+                ops.taps_wgrad(x, off, PRE_LNRELU if ln is not None else 0, dout, dwk[j], ln=ln)
+            dw = dwk.permute(1, 2, 0)
+            if weight.dim() == 2:
+                dw = dw[:, :, 0]
+            dw = dw.to(weight.dtype)
+        if ctx.bias_dtype is not None and need[5]:
+            db = ops.channel_reduce(dout).to(ctx.bias_dtype)
+        return None, dx, dgamma, dbeta, dw, db, (dout if need[6] else None)
+
+
+def fused_conv(x, weight, bias, offsets, ln=None, residual=None):
+    """conv over `offsets` of ReLU(LayerNorm(x)) (ln = the LayerNorm module) or of x, plus an optional residual."""
+    gamma = beta = None
+    cfg = {"offsets": [int(o) for o in offsets], "eps": 0.0}
+    if ln is not None:
+        if ln.dim != 1:
+            raise NotImplementedError("LayerNorm kernel normalises dim=1 of a (B, C, T) tensor")
+        gamma, beta = ln.gamma, ln.beta
+        cfg["eps"] = float(ln.eps)
+    return _FusedConv.apply(cfg, x, gamma, beta, weight, bias, residual)
+
+
+class _LNReLU(torch.autograd.Function):
+    """ReLU(LayerNorm(x)) stored (one statistics + one apply launch); the training form of the MU block keeps it for the
+    MultiplicativeUnit's backward."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        x = x.contiguous()
+        g, b = _flat32(gamma), _flat32(beta)
+        stats = ops.ln_stats(x, eps)
+        ctx.eps = eps
+        ctx.save_for_backward(x, stats, gamma, beta)
+        return ops.ln_relu_fwd(x, stats, g, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stats, gamma, beta = ctx.saved_tensors
+        dx, dg, db = ops.ln_relu_bwd(x, stats, _flat32(gamma), _flat32(beta), ctx.eps, dy)
+        return dx, dg.view(gamma.shape).to(gamma.dtype), db.view(gamma.shape).to(gamma.dtype), None
+
+
+def ln_relu(x, ln):
+    if ln.dim != 1:
+        raise NotImplementedError("LayerNorm kernel normalises dim=1 of a (B, C, T) tensor")
+    return _LNReLU.apply(x, ln.gamma, ln.beta, float(ln.eps))
+
+
+def _pack_mu(convs, dtype):
+    """The four convolutions of a MultiplicativeUnit in EPI_MU's row order (wnb200.h): per 32 channels, rows [0, 64) =
+    channels 0..15 x (gate1, gate2, gate3, update), rows [64, 128) = channels 16..31 likewise.  -> ([k, rows, C], [rows])"""
+    ws = [c.weight for c in convs]
+    bs = [c.bias for c in convs]
+
+    def build():
+        M, C, k = ws[0].shape
+        nt = (M + 31) // 32
+        r = torch.arange(nt * 128, device=ws[0].device)
+        tile, rr = r // 128, r % 128
+        ch = tile * 32 + torch.where(rr < 64, rr // 4, 16 + (rr - 64) // 4)
+        unit = rr % 4
+        ok = ch < M
+        src = torch.where(ok, unit * M + ch, torch.full_like(ch, 4 * M))       # row 4M = the zero row
+        w = torch.cat([w_.detach().to(dtype) for w_ in ws] + [ws[0].new_zeros((1, C, k), dtype=dtype)], 0)
+        b = torch.cat([b_.detach().float() for b_ in bs] + [bs[0].new_zeros(1, dtype=torch.float32)], 0)
+        return w[src].permute(2, 0, 1).contiguous(), b[src].contiguous()
+    return _cached_layout(ws + bs, "mu", dtype, build)
+
+
+def multiplicative_unit_fused(h, convs, offsets, ln=None, residual=None):
+    """MultiplicativeUnit.forward in ONE launch (no autograd): the four convolutions' contraction with the gate
+    g1 * tanh(g2 * h + g3 * tanh(u)) as its epilogue.  ln = a LayerNorm module: h is ReLU(LayerNorm(h)) formed on the
+    fly, for the operand AND for the gate's h."""
+    h = h.contiguous()
+    wk, bk = _pack_mu(convs, h.dtype)
+    lnp = None
+    if ln is not None:
+        lnp = (ops.ln_stats(h, float(ln.eps)), _flat32(ln.gamma), _flat32(ln.beta))
+    terms = [Term(h, wk[j], off, PRE_LNRELU if lnp is not None else 0, lnp) for j, off in enumerate(offsets)]
+    return ops.taps_fwd(terms, bk, h.shape[1], h.shape[2], EPI_MU, mu_h=h, mu_h_ln=lnp is not None, residual=residual)
+
+
+def needs_grad(*tensors):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
 
 class _Positions(torch.autograd.Function):

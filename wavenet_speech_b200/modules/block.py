@@ -66,11 +66,14 @@ class MultiplicativeUnit(nn.Module):
         self.receptive_field = max(self.gate1.receptive_field, self.gate2.receptive_field,
                                    self.gate3.receptive_field, self.update.receptive_field)
 
+    @property
+    def convs(self):
+        return (self.gate1.conv1d, self.gate2.conv1d, self.gate3.conv1d, self.update.conv1d)
+
     @device_guard
     def forward(self, h):
-        # one contraction launch for the four convolutions + one fused gate launch (forward and backward)
-        return WF.multiplicative_unit(h, (self.gate1.conv1d, self.gate2.conv1d, self.gate3.conv1d, self.update.conv1d),
-                                      self.gate1.offsets)
+        # inference: ONE launch (the gate is the contraction's epilogue); with gradients: contraction + gate kernel
+        return WF.multiplicative_unit(h, self.convs, self.gate1.offsets)
 
     def init(self):
         for p in self.parameters():
@@ -81,9 +84,8 @@ class MultiplicativeUnit(nn.Module):
 
 
 class _ByteNetBlock(nn.Module):
-    @device_guard
-    def forward(self, seq):
-        return seq + self.stack(seq)
+    """`seq + stack(seq)` (block.py:117-119, 164-166).  `stack` is the reference's nn.Sequential (same indices, same
+    state_dict keys); forward walks it in fused steps instead of calling it module by module."""
 
     def init(self):
         for p in self.parameters():
@@ -120,6 +122,33 @@ class ResidualMUBlock(_ByteNetBlock):
             _Conv1x1(half, nchannels, 1))
         self.receptive_field = self.stack[5].receptive_field
 
+    @device_guard
+    def forward(self, seq):
+        """Three (statistics, contraction) pairs: each LayerNorm + ReLU is applied as the following convolution loads
+        its operand, the last contraction's store adds `seq`."""
+        st = self.stack
+        seq = seq.contiguous()
+        h = WF.fused_conv(seq, st[2].weight, st[2].bias, [0], ln=st[0])
+        h = WF.fused_conv(h, st[5].conv1d.weight, st[5].conv1d.bias, st[5].offsets, ln=st[3])
+        return WF.fused_conv(h, st[8].weight, st[8].bias, [0], ln=st[6], residual=seq)
+
+    @device_guard
+    def forward(self, seq):
+        """Inference, 6 launches and no normalised tensor in HBM: statistics; 1x1 reading ReLU(LN(seq)) on the fly;
+        statistics; MU(k, d) = ONE contraction whose operand and whose gate's h are ReLU(LN(.)) formed on the fly and
+        whose epilogue is the gate; MU(1) likewise; 1x1 whose store adds `seq`.  With gradients the two units run as
+        contraction + gate kernel on a stored h (their backward needs both)."""
+        st = self.stack
+        seq = seq.contiguous()
+        z = WF.fused_conv(seq, st[2].weight, st[2].bias, [0], ln=st[0])
+        mu1, mu2 = st[5], st[6]
+        if WF.needs_grad(seq, *self.parameters()) or len(mu1.gate1.offsets) > WF.ops.MAX_SRC:
+            h = mu2(mu1(WF.ln_relu(z, st[3])))
+        else:
+            h = WF.multiplicative_unit_fused(z, mu1.convs, mu1.gate1.offsets, ln=st[3])
+            h = WF.multiplicative_unit_fused(h, mu2.convs, mu2.gate1.offsets)
+        return WF.fused_conv(h, st[7].weight, st[7].bias, [0], residual=seq)
+
 
 class ResidualReLUBlock(_ByteNetBlock):
     """ByteNet residual ReLU block (reference block.py:130-173)."""
@@ -133,3 +162,13 @@ class ResidualReLUBlock(_ByteNetBlock):
             CausalConv1d(half, half, kernel_width=k_width, dilation=dilation), LayerNorm(half), _ReLU(),
             _Conv1x1(half, nchannels, 1))
         self.receptive_field = self.stack[5].receptive_field
+
+    @device_guard
+    def forward(self, seq):
+        """Three (statistics, contraction) pairs: each LayerNorm + ReLU is applied as the following convolution loads
+        its operand, the last contraction's store adds `seq`."""
+        st = self.stack
+        seq = seq.contiguous()
+        h = WF.fused_conv(seq, st[2].weight, st[2].bias, [0], ln=st[0])
+        h = WF.fused_conv(h, st[5].conv1d.weight, st[5].conv1d.bias, st[5].offsets, ln=st[3])
+        return WF.fused_conv(h, st[8].weight, st[8].bias, [0], ln=st[6], residual=seq)

@@ -9,7 +9,8 @@ import torch
 
 from . import _lib
 
-EPI_NONE, EPI_LEAKY, EPI_GATE = 0, 1, 2
+EPI_NONE, EPI_LEAKY, EPI_GATE, EPI_MU = 0, 1, 2, 3
+PRE_NONE, PRE_LEAKY, PRE_LNRELU = 0, 1, 2
 MAX_SRC = 4
 _DT = {torch.float32: 0, torch.bfloat16: 1}
 
@@ -66,11 +67,22 @@ def time_major(x):
 
 
 class Term(object):
-    """One (x, weight-slab, offset) term.  x: [B, C, T_src] with stride(2)==1; w: [rows, C] contiguous."""
-    __slots__ = ("x", "w", "t_off", "pre_act")
+    """One (x, weight-slab, offset) term.  x: [B, C, T_src] with stride(2)==1; w: [rows, C] contiguous.
+    pre_act == PRE_LNRELU: `ln` = (stats [B, T_src, 2], gamma [C], beta [C]) fp32, the source is read as
+    ReLU(LayerNorm(x)) without that tensor being stored."""
+    __slots__ = ("x", "w", "t_off", "pre_act", "ln")
 
-    def __init__(self, x, w, t_off=0, pre_act=0):
-        self.x, self.w, self.t_off, self.pre_act = x, w, int(t_off), int(pre_act)
+    def __init__(self, x, w, t_off=0, pre_act=0, ln=None):
+        self.x, self.w, self.t_off, self.pre_act, self.ln = x, w, int(t_off), int(pre_act), ln
+        assert (self.pre_act == PRE_LNRELU) == (ln is not None)
+
+
+def _fill_ln(dst, term):
+    stats, gamma, beta = term.ln
+    assert stats.dtype == gamma.dtype == beta.dtype == torch.float32
+    assert stats.is_contiguous() and gamma.is_contiguous() and beta.is_contiguous()
+    assert stats.shape == (term.x.shape[0], term.x.shape[2], 2) and gamma.numel() == term.x.shape[1]
+    dst.stats, dst.gamma, dst.beta = stats.data_ptr(), gamma.data_ptr(), beta.data_ptr()
 
 
 def _fill(src, term):
@@ -85,8 +97,10 @@ def _fill(src, term):
     src.pre_act = term.pre_act
 
 
-def taps_fwd(terms, bias, M, T_out, epilogue=EPI_NONE, out=None, accumulate=False, want_gate_parts=False):
-    """out[b,m,t] (+)= epi(bias[m] + sum_terms w @ pre(x[.., t+off])).  Returns out (and th, sg)."""
+def taps_fwd(terms, bias, M, T_out, epilogue=EPI_NONE, out=None, accumulate=False, want_gate_parts=False,
+             residual=None, mu_h=None, mu_h_ln=False):
+    """out[b,m,t] (+)= epi(bias[m] + sum_terms w @ pre(x[.., t+off])) [+ residual].  Returns out (and th, sg).
+    epilogue == EPI_MU: `mu_h` is the h of the MultiplicativeUnit's gate (the weights' rows in the MU packing)."""
     x0 = terms[0].x
     _need_cuda(x0)
     check_device()
@@ -111,13 +125,39 @@ def taps_fwd(terms, bias, M, T_out, epilogue=EPI_NONE, out=None, accumulate=Fals
     if len(chunks) > 1:
         assert epilogue in (EPI_NONE, EPI_LEAKY) and not (late_leaky and accumulate), \
             "more than %d terms: the gate epilogue is applied by the caller (functional._ResBlock)" % MAX_SRC
+    extended = residual is not None or epilogue == EPI_MU or any(tm.ln is not None for tm in terms)
+    if residual is not None:
+        assert residual.shape == out.shape and residual.dtype == out.dtype and residual.is_contiguous()
+        assert epilogue != EPI_GATE and not late_leaky
+    if epilogue == EPI_MU:
+        assert len(chunks) == 1 and mu_h is not None and mu_h.dtype == x0.dtype
+        assert mu_h is terms[0].x if mu_h_ln else (mu_h.shape == out.shape and mu_h.is_contiguous())
     for ci, chunk in enumerate(chunks):
         arr = (_lib.Src * len(chunk))()
         for i, tm in enumerate(chunk):
             _fill(arr[i], tm)
-        _lib.call("wnb200_taps_fwd", dt, B, T_out, M, len(chunk), arr, _p(bias if ci == 0 else None),
-                  EPI_NONE if late_leaky else epilogue, 1 if (accumulate or ci > 0) else 0, _p(out), _p(th), _p(sg),
-                  _stream())
+        if not extended:
+            _lib.call("wnb200_taps_fwd", dt, B, T_out, M, len(chunk), arr, _p(bias if ci == 0 else None),
+                      EPI_NONE if late_leaky else epilogue, 1 if (accumulate or ci > 0) else 0, _p(out), _p(th), _p(sg),
+                      _stream())
+            continue
+        lns = (_lib.Ln * len(chunk))()
+        for i, tm in enumerate(chunk):
+            if tm.ln is not None:
+                _fill_ln(lns[i], tm)
+        a = _lib.Taps()
+        a.dtype, a.B, a.T_out, a.M, a.nsrc = dt, B, T_out, M, len(chunk)
+        a.epilogue = EPI_NONE if late_leaky else epilogue
+        a.accumulate = 1 if (accumulate or ci > 0) else 0
+        a.srcs, a.ln = arr, lns
+        a.bias = 0 if (bias is None or ci > 0) else bias.data_ptr()
+        a.out = out.data_ptr()
+        a.th = 0 if th is None else th.data_ptr()
+        a.sg = 0 if sg is None else sg.data_ptr()
+        a.residual = residual.data_ptr() if (residual is not None and ci == len(chunks) - 1) else 0
+        a.mu_h = 0 if mu_h is None else mu_h.data_ptr()
+        a.mu_h_ln = 1 if mu_h_ln else 0
+        _lib.call("wnb200_taps_fwd_ex", ctypes.byref(a), _stream())
     if late_leaky:       # x * (x > 0 ? 1 : 0.01), in place, with the LeakyReLU-backward kernel applied to (x, x)
         _lib.call("wnb200_leaky_bwd", dt, out.numel(), _p(out), _p(out), _p(out), _stream())
     if want_gate_parts:
@@ -125,16 +165,84 @@ def taps_fwd(terms, bias, M, T_out, epilogue=EPI_NONE, out=None, accumulate=Fals
     return out
 
 
-def taps_wgrad(x, t_off, pre_act, dout, dw):
+def taps_wgrad(x, t_off, pre_act, dout, dw, ln=None):
     """dw[m,c] += sum_{b,t} dout[b,m,t] * pre(x[b,c,t+t_off]); dw fp32 [M, C]."""
     _need_cuda(x, dout, dw)
     assert dout.is_contiguous() and dw.dtype == torch.float32 and dw.is_contiguous()
     assert x.stride(2) == 1 and x.dtype == dout.dtype
     B, M, T_out = dout.shape
     src = _lib.Src()
-    _fill(src, Term(x, None, t_off, pre_act))
-    _lib.call("wnb200_taps_wgrad", _dt(x), B, T_out, M, ctypes.byref(src), _p(dout), _p(dw), _stream())
+    tm = Term(x, None, t_off, pre_act, ln)
+    _fill(src, tm)
+    if ln is None:
+        _lib.call("wnb200_taps_wgrad", _dt(x), B, T_out, M, ctypes.byref(src), _p(dout), _p(dw), _stream())
+    else:
+        lnc = _lib.Ln()
+        _fill_ln(lnc, tm)
+        _lib.call("wnb200_taps_wgrad_ex", _dt(x), B, T_out, M, ctypes.byref(src), ctypes.byref(lnc), _p(dout), _p(dw),
+                  _stream())
     return dw
+
+
+def ln_stats(x, eps):
+    """(mean over channels, 1 / (unbiased std + eps)) per frame of a contiguous (B, C, T) tensor -> fp32 (B, T, 2)."""
+    _need_cuda(x)
+    check_device()
+    assert x.is_contiguous() and x.dim() == 3
+    B, C, T = x.shape
+    stats = torch.empty((B, T, 2), dtype=torch.float32, device=x.device)
+    _lib.call("wnb200_ln_stats", _dt(x), B, C, T, _p(x), float(eps), _p(stats), _stream())
+    return stats
+
+
+def ln_relu_fwd(x, stats, gamma, beta):
+    B, C, T = x.shape
+    y = torch.empty_like(x)
+    _lib.call("wnb200_ln_relu_fwd", _dt(x), B, C, T, _p(x), _p(stats), _p(gamma), _p(beta), _p(y), _stream())
+    return y
+
+
+def ln_relu_bwd(x, stats, gamma, beta, eps, dy, want_dx=True):
+    """Backward of ReLU(LayerNorm(x)) -> (dx or None, dgamma fp32 [C], dbeta fp32 [C])."""
+    B, C, T = x.shape
+    dy = dy.contiguous()
+    assert dy.dtype == x.dtype and dy.shape == x.shape
+    dx = torch.empty_like(x) if want_dx else None
+    dgamma = torch.zeros(C, dtype=torch.float32, device=x.device)
+    dbeta = torch.zeros(C, dtype=torch.float32, device=x.device)
+    _lib.call("wnb200_ln_relu_bwd", _dt(x), B, C, T, _p(x), _p(stats), _p(gamma), _p(beta), float(eps), _p(dy), _p(dx),
+              _p(dgamma), _p(dbeta), _stream())
+    return dx, dgamma, dbeta
+
+
+def linear_frame(frame, weight, bias, dilation):
+    """LinearConv1d.linear: frame (N, Cin, rf), weight (Cout, Cin, k) -> (N, Cout)."""
+    _need_cuda(frame, weight)
+    check_device()
+    frame = frame.contiguous()
+    N, Cin, rf = frame.shape
+    Cout, _, k = weight.shape
+    assert weight.is_contiguous() and weight.dtype == frame.dtype and rf == k + (dilation - 1) * (k - 1)
+    y = torch.empty((N, Cout), dtype=frame.dtype, device=frame.device)
+    _lib.call("wnb200_linear_frame", _dt(frame), N, Cin, Cout, k, int(dilation), _p(weight), _p(bias), _p(frame), _p(y),
+              _stream())
+    return y
+
+
+def linear_step(x, weight, bias, dilation, step, hist, out=None):
+    """One frame of the incremental evaluation: x (N, Cin) is frame number `step`; hist (rf, N, Cin) is the ring the
+    call reads the earlier taps from and files x into.  -> (N, Cout)."""
+    _need_cuda(x, weight)
+    check_device()
+    N, Cin = x.shape
+    Cout, _, k = weight.shape
+    assert x.is_contiguous() and weight.is_contiguous() and weight.dtype == x.dtype
+    if k > 1:
+        assert hist.shape == ((k - 1) * dilation + 1, N, Cin) and hist.is_contiguous() and hist.dtype == x.dtype
+    y = out if out is not None else torch.empty((N, Cout), dtype=x.dtype, device=x.device)
+    _lib.call("wnb200_linear_step", _dt(x), N, Cin, Cout, k, int(dilation), int(step), _p(weight), _p(bias), _p(x),
+              _p(hist), _p(y), _stream())
+    return y
 
 
 def channel_reduce(a, b=None, out=None):
