@@ -25,6 +25,14 @@ def _err(a, ref):
     return G.rel_linf(a.detach().float().cpu(), ref)
 
 
+def _grad_err(a, ref, scale):
+    """|a - ref| over max(|ref|, 1e-3 * the largest gradient of the module): a gradient that is a cancellation to round-off
+    (the c4 fixtures normalise over TWO channels, where LayerNorm's output is +-0.707 whatever the input and nothing flows
+    back through it) is compared on the scale of the gradients that are not."""
+    a, ref = a.detach().double().cpu().flatten(), ref.double().flatten()
+    return float((a - ref).abs().max() / max(float(ref.abs().max()), 1e-3 * scale, 1e-30))
+
+
 @pytest.mark.parametrize("name", [n for n in G.names() if n.startswith("bytenet_")])
 def test_blocks_against_reference_fixtures(name):
     """Inference (fused: LayerNorm + ReLU on the operand load, MU gate and residual add in the epilogues) and training
@@ -41,11 +49,12 @@ def test_blocks_against_reference_fixtures(name):
     y = net(xg)
     assert _err(y, g["out"]["y"]) <= FP32_TOL
     (y * g["inp"]["probe"].cuda()).sum().backward()
-    assert _err(xg.grad, g["out"]["grad_x"]) <= GRAD_TOL, ("dx", _err(xg.grad, g["out"]["grad_x"]))
+    scale = max(float(v.abs().max()) for k, v in g["out"].items() if k.startswith("grad"))
+    assert _grad_err(xg.grad, g["out"]["grad_x"], scale) <= GRAD_TOL, ("dx", _grad_err(xg.grad, g["out"]["grad_x"], scale))
     for n, p in net.named_parameters():
         ref = g["out"]["grad/" + n]
         assert p.grad is not None, n
-        assert _err(p.grad, ref) <= GRAD_TOL, (n, _err(p.grad, ref))
+        assert _grad_err(p.grad, ref, scale) <= GRAD_TOL, (n, _grad_err(p.grad, ref, scale))
 
 
 @pytest.mark.parametrize("kind,nch,k,d,B,T", [("relu", 256, 3, 4, 3, 1003), ("mu", 256, 3, 4, 3, 1003),
@@ -78,9 +87,10 @@ def test_blocks_against_the_oracle(kind, nch, k, d, B, T):
     y = net(xg)
     assert _err(y, ref.detach()) <= FP32_TOL
     (y * probe.cuda()).sum().backward()
-    assert _err(xg.grad, xr.grad) <= GRAD_TOL, ("dx", _err(xg.grad, xr.grad))
+    scale = max([float(v.grad.abs().max()) for v in sd.values()] + [float(xr.grad.abs().max())])
+    assert _grad_err(xg.grad, xr.grad, scale) <= GRAD_TOL, ("dx", _grad_err(xg.grad, xr.grad, scale))
     for n, p in net.named_parameters():
-        assert _err(p.grad, sd[n].grad) <= GRAD_TOL, (n, _err(p.grad, sd[n].grad))
+        assert _grad_err(p.grad, sd[n].grad, scale) <= GRAD_TOL, (n, _grad_err(p.grad, sd[n].grad, scale))
 
 
 def test_inference_launch_counts():
