@@ -239,3 +239,80 @@ if "longread" in which:    # config 5: 1M-sample read, time-sharded in 8 shards 
                       "per_shard_ms_max": max(ms_shards), "projected_8gpu_samples_per_s": T / (max(ms_shards) * 1e-3),
                       "sharded_equals_full_bitwise": same,
                       "max_abs_diff": float((y.float() - full.float()).abs().max())}))
+
+
+if "bytenet" in which:     # ByteNet residual blocks (block.py:86-173) and the frame-at-a-time LinearConv1d
+    import torch.nn.functional as F
+    sys.path.insert(0, ROOT)
+    from oracle import wavenet_oracle as O          # stock-torch comparator on the same GPU (the reference's op sequence)
+    C, k, d = int(opts.get("C", 512)), 3, 4
+    B, T = int(opts.get("B", 16)), int(opts.get("T", 8192))
+    for kind, cls, fn in (("relu", W.ResidualReLUBlock, O.residual_relu_block), ("mu", W.ResidualMUBlock, O.residual_mu_block)):
+        for dtype in (torch.float32, torch.bfloat16):
+            torch.manual_seed(0)
+            net = cls(C, k, d)
+            net.init()
+            net = net.cuda().to(dtype)
+            sd = {kk: v.detach() for kk, v in net.state_dict().items()}
+            x = torch.randn(B, C, T, device="cuda", dtype=dtype)
+            with torch.no_grad():
+                ms = timed(lambda: net(x), 10)
+                ms_stock = timed(lambda: fn(sd, "", x, d), 5)
+                y, yr = net(x), fn(sd, "", x, d)
+                ms_strict = None
+                if dtype == torch.float32:      # stock torch defaults to TF32 convolutions: time it at fp32 accuracy too
+                    tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+                    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+                    ms_strict = timed(lambda: fn(sd, "", x, d), 5)
+                    ys = fn(sd, "", x, d)
+                    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
+            h = C // 2
+            # FLOP as written: 1x1 down + (relu: k-tap conv | mu: 4 k-tap + 4 1-tap convs) + 1x1 up, per frame
+            mac = C * h + h * C + (k * h * h if kind == "relu" else 4 * k * h * h + 4 * h * h)
+            xg = x.clone().requires_grad_(True)
+            def step():
+                for p in net.parameters():
+                    p.grad = None
+                net(xg).sum().backward()
+            ms_tr = timed(step, 5)
+            es = x.element_size()
+            print(json.dumps({"what": "bytenet_block", "kind": kind, "dtype": str(dtype).split(".")[1], "C": C, "k": k, "d": d,
+                              "B": B, "T": T, "fwd_ms": round(ms, 3), "fwd_samples_per_s": round(B * T / ms * 1e3),
+                              "fwd_tflops": round(2 * mac * B * T / ms / 1e9, 1),
+                              "min_bytes_gbps": round(2 * B * C * T * es / ms / 1e6, 1),
+                              "stock_torch_gpu_fwd_ms": round(ms_stock, 3), "speedup_vs_stock": round(ms_stock / ms, 2),
+                              "fwd_bwd_ms": round(ms_tr, 3),
+                              "max_abs_diff_vs_stock": float((y.float() - yr.float()).abs().max()),
+                              "stock_torch_gpu_strict_fp32_fwd_ms": None if ms_strict is None else round(ms_strict, 3),
+                              "max_abs_diff_vs_strict_fp32_stock": None if ms_strict is None else
+                              float((y.float() - ys.float()).abs().max())}))
+    # incremental decoding: one frame per step through a LinearConv1d
+    for (cin, cout, kk, dd, N) in ((512, 512, 3, 4, 16), (1024, 1024, 5, 16, 8)):
+        conv = W.LinearConv1d(cin, cout, kk, dilation=dd).cuda()
+        rf = conv.receptive_field
+        st = conv.stream(N)
+        xt = torch.randn(N, cin, device="cuda")
+        frame = torch.randn(N, cin, rf, device="cuda")
+        with torch.no_grad():
+            us_push = timed(lambda: st.push(xt), 200, warmup=20) * 1e3
+            us_lin = timed(lambda: conv.linear(frame), 200, warmup=20) * 1e3
+            us_stock = timed(lambda: F.linear(frame[:, :, conv._ker_ixs].reshape(N, cin * kk),
+                                              conv.weight.view(cout, cin * kk), conv.bias), 200, warmup=20) * 1e3
+            g = torch.cuda.CUDAGraph()
+            xs = xt.clone()
+            yb = torch.empty(N, cout, device="cuda")
+            from wavenet_speech_b200 import ops as _ops
+            hist = torch.zeros(rf, N, cin, device="cuda")
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                _ops.linear_step(xs, conv.weight, conv.bias, dd, 0, hist, out=yb)
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g, stream=s):
+                    for i in range(rf):          # one ring revolution: the slot addresses repeat with period rf
+                        _ops.linear_step(xs, conv.weight, conv.bias, dd, i, hist, out=yb)
+            us_graph = timed(lambda: g.replay(), 20, warmup=3) * 1e3 / rf
+        wbytes = cout * cin * kk * 4
+        print(json.dumps({"what": "linearconv_step", "cin": cin, "cout": cout, "k": kk, "d": dd, "rf": rf, "N": N,
+                          "push_us": round(us_push, 2), "push_graph_us": round(us_graph, 2),
+                          "weight_gbps_in_graph": round(wbytes / us_graph / 1e3, 1),
+                          "linear_us": round(us_lin, 2), "stock_torch_linear_us": round(us_stock, 2)}))

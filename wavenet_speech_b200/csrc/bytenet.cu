@@ -236,14 +236,17 @@ struct LinParams {
 
 template <typename T>
 __global__ void __launch_bounds__(256) linear_frame_kernel(const LinParams p) {
-  extern __shared__ float xin[];                 // [nb][K], K = Cin * k
+  extern __shared__ __align__(16) float xin[];   // [nb][K], K = Cin * k, W's column order (c major, tap minor)
   const int K = p.Cin * p.k;
   const int n0 = blockIdx.y * LS_NB;
   const int nb = min(LS_NB, p.N - n0);
-  for (int i = threadIdx.x; i < nb * K; i += blockDim.x) {
-    const int n = i / K, e = i - n * K;
-    const int c = e / p.k, j = e - c * p.k;
-    xin[i] = to_f32<T>(reinterpret_cast<const T*>(p.tap[j])[(long long)(n0 + n) * p.sn + (long long)c * p.sc]);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // gather: one (batch item, tap) pair per warp pass, lanes along the channels (contiguous in the history ring)
+  for (int pair = warp; pair < nb * p.k; pair += 8) {
+    const int n = pair / p.k, j = pair - n * p.k;
+    const T* src = reinterpret_cast<const T*>(p.tap[j]) + (long long)(n0 + n) * p.sn;
+    float* dst = xin + n * K + j;
+    for (int c = lane; c < p.Cin; c += 32) dst[c * p.k] = to_f32<T>(src[(long long)c * p.sc]);
   }
   if (p.ring_slot && blockIdx.x == 0 && blockIdx.y == 0) {
     // the slot written here is not among the taps of this step (ring length = receptive field)
@@ -252,21 +255,45 @@ __global__ void __launch_bounds__(256) linear_frame_kernel(const LinParams p) {
     for (int i = threadIdx.x; i < p.N * p.Cin; i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const T* w = reinterpret_cast<const T*>(p.w);
   T* y = reinterpret_cast<T*>(p.y);
   const int m_begin = blockIdx.x * p.rows_per_cta;
   const int m_end = min(p.Cout, m_begin + p.rows_per_cta);
+  const bool vec = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0;
   for (int m = m_begin + warp; m < m_end; m += 8) {
     float acc[LS_NB];
 #pragma unroll
     for (int n = 0; n < LS_NB; ++n) acc[n] = 0.f;
     const T* wr = w + (long long)m * K;
-    for (int e = lane; e < K; e += 32) {
-      const float wv = to_f32<T>(wr[e]);
+    if (vec) {
+      // 4 weights per lane and step (16-byte loads when fp32), four steps in flight
+#pragma unroll 4
+      for (int e = lane * 4; e < K; e += 128) {
+        float wv[4];
+        if constexpr (sizeof(T) == 4) {
+          const float4 q = *reinterpret_cast<const float4*>(wr + e);
+          wv[0] = q.x; wv[1] = q.y; wv[2] = q.z; wv[3] = q.w;
+        } else {
+          const uint2 q = *reinterpret_cast<const uint2*>(wr + e);
+          const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&q.x);
+          const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&q.y);
+          wv[0] = __low2float(a); wv[1] = __high2float(a); wv[2] = __low2float(b); wv[3] = __high2float(b);
+        }
 #pragma unroll
-      for (int n = 0; n < LS_NB; ++n)
-        if (n < nb) acc[n] = fmaf(wv, xin[n * K + e], acc[n]);
+        for (int n = 0; n < LS_NB; ++n) {
+          if (n < nb) {
+            const float4 xv = *reinterpret_cast<const float4*>(xin + n * K + e);
+            acc[n] = fmaf(wv[0], xv.x, fmaf(wv[1], xv.y, fmaf(wv[2], xv.z, fmaf(wv[3], xv.w, acc[n]))));
+          }
+        }
+      }
+    } else {
+      for (int e = lane; e < K; e += 32) {
+        const float wv = to_f32<T>(wr[e]);
+#pragma unroll
+        for (int n = 0; n < LS_NB; ++n)
+          if (n < nb) acc[n] = fmaf(wv, xin[n * K + e], acc[n]);
+      }
     }
 #pragma unroll
     for (int n = 0; n < LS_NB; ++n) {
@@ -284,9 +311,8 @@ static int launch_linear(LinParams& p, cudaStream_t st) {
   const size_t smem = (size_t)LS_NB * K * sizeof(float);
   WNB_CHECK_ARG(smem <= 200 * 1024, "linear: Cin * k = %d does not fit the shared staging (<= 6400)", K);
   if (smem > 48 * 1024) WNB_SET_SMEM_ATTR((int)smem, linear_frame_kernel<T>);
-  // enough CTAs to spread W over the SMs, at least 8 rows (one per warp) each
-  int ctas = ceil_div(p.Cout, 8);
-  if (ctas > 148) ctas = 148;
+  // W spread over every SM: a CTA takes ceil(Cout / 148) rows (one per warp, up to 8 at a time)
+  int ctas = p.Cout < 148 ? p.Cout : 148;
   p.rows_per_cta = ceil_div(p.Cout, ctas);
   dim3 grid(ceil_div(p.Cout, p.rows_per_cta), ceil_div(p.N, LS_NB));
   linear_frame_kernel<T><<<grid, 256, smem, st>>>(p);

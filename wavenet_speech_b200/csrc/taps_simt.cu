@@ -112,7 +112,7 @@ __device__ __forceinline__ void store_row4(T* base, long long idx, int t, int T_
   }
 }
 
-template <typename T, int EPI>
+template <typename T, int EPI, bool LN>
 __global__ void __launch_bounds__(NT, 2) taps_fwd_kernel(const TapsParams p) {
   __shared__ __align__(16) float As[2][BK][BM + 4];
   __shared__ __align__(16) float Bs[2][BK][BN + 4];
@@ -131,34 +131,82 @@ __global__ void __launch_bounds__(NT, 2) taps_fwd_kernel(const TapsParams p) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-  float ra[4], rb[4];
+  // Register prefetch: the loads of slab i+1 are ISSUED before the FFMA loop of slab i and CONSUMED (converted,
+  // transformed, written to shared memory) after it.  Nothing between the issue and the loop may read the loaded
+  // registers -- round 2's profile (profiles/r2_ncu_full_taps_*.csv) showed the kernel at 38 % of the FFMA pipe with
+  // its largest stall on the LeakyReLU compare that used to sit right behind the load.
+  T rat[4], rbt[4];
+  unsigned rb_ok = 0;
+  int ld_s = 0, ld_c = 0;
+  float2 lst[4];          // LN only: (mean, 1/(std+eps)) of the four frames
+  float lg = 0.f, lb = 0.f;
 
   auto load_regs = [&](int s, int k0) {
     const SrcDev& S = p.src[s];
     const int grow = row0 + a_row;
-    const T* w = reinterpret_cast<const T*>(S.w);
+    const T* w = reinterpret_cast<const T*>(S.w) + (long long)grow * S.C + k0 + a_k;
+    const bool row_ok = grow < p.rows;
+    if (row_ok && (S.C & 3) == 0 && k0 + a_k + 3 < S.C) {
+      if constexpr (sizeof(T) == 4) {
+        const float4 q = *reinterpret_cast<const float4*>(w);
+        rat[0] = q.x; rat[1] = q.y; rat[2] = q.z; rat[3] = q.w;
+      } else {
+        const uint2 q = *reinterpret_cast<const uint2*>(w);
+        *reinterpret_cast<uint2*>(&rat[0]) = q;
+      }
+    } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = k0 + a_k + i;
-      ra[i] = (grow < p.rows && k < S.C) ? to_f32<T>(w[(long long)grow * S.C + k]) : 0.f;
+      for (int i = 0; i < 4; ++i) {
+        rat[i] = from_f32<T>(0.f);
+        if (row_ok && k0 + a_k + i < S.C) rat[i] = w[i];
+      }
     }
     const int c = k0 + b_k;
-    const T* x = reinterpret_cast<const T*>(S.x) + (long long)b * S.bs + (long long)c * S.cs;
+    const int ts = t0 + b_t + S.t_off;
+    const T* x = reinterpret_cast<const T*>(S.x) + (long long)b * S.bs + (long long)c * S.cs + ts;
+    ld_s = s; ld_c = c;
+    rb_ok = 0;
+    if (c < S.C) {
+      if (ts >= 0 && ts + 3 < S.T_src && ((reinterpret_cast<uintptr_t>(x) & (4 * sizeof(T) - 1)) == 0)) {
+        rb_ok = 15u;
+        if constexpr (sizeof(T) == 4) {
+          const float4 q = *reinterpret_cast<const float4*>(x);
+          rbt[0] = q.x; rbt[1] = q.y; rbt[2] = q.z; rbt[3] = q.w;
+        } else {
+          *reinterpret_cast<uint2*>(&rbt[0]) = *reinterpret_cast<const uint2*>(x);
+        }
+      } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int t = t0 + b_t + i + S.t_off;
-      float v = 0.f;
-      if (c < S.C && t >= 0 && t < S.T_src) {
-        v = to_f32<T>(x[t]);
-        if (S.pre_act) v = pre_transform(S, v, b, c, t);
+        for (int i = 0; i < 4; ++i) {
+          rbt[i] = from_f32<T>(0.f);
+          if (ts + i >= 0 && ts + i < S.T_src) { rbt[i] = x[i]; rb_ok |= 1u << i; }
+        }
       }
-      rb[i] = v;
+      if constexpr (LN) {
+        if (S.pre_act == WNB200_PRE_LNRELU) {
+          lg = S.ln_gamma[c]; lb = S.ln_beta[c];
+          const float2* stp = reinterpret_cast<const float2*>(S.ln_stats) + (long long)b * S.T_src + ts;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) lst[i] = (rb_ok >> i & 1u) ? stp[i] : make_float2(0.f, 0.f);
+        }
+      }
     }
   };
   auto store_smem = [&](int buf) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) As[buf][a_k + i][a_row] = ra[i];
-    *reinterpret_cast<float4*>(&Bs[buf][b_k][b_t]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+    for (int i = 0; i < 4; ++i) As[buf][a_k + i][a_row] = to_f32<T>(rat[i]);
+    const int pre = p.src[ld_s].pre_act;
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float q = (rb_ok >> i & 1u) ? to_f32<T>(rbt[i]) : 0.f;
+      if (pre == WNB200_PRE_LEAKY) q = leaky(q);
+      if constexpr (LN) {
+        if (pre == WNB200_PRE_LNRELU) q = (rb_ok >> i & 1u) ? fmaxf(lg * (q - lst[i].x) * lst[i].y + lb, 0.f) : 0.f;
+      }
+      v[i] = q;
+    }
+    *reinterpret_cast<float4*>(&Bs[buf][b_k][b_t]) = make_float4(v[0], v[1], v[2], v[3]);
   };
 
   int niter = 0;
@@ -400,11 +448,23 @@ static int fill_src(SrcDev& d, const wnb200_src_t& s, const wnb200_ln_t* ln) {
 template <typename T>
 static int launch_taps(const TapsParams& p, int epilogue, cudaStream_t st) {
   dim3 grid(ceil_div(p.T_out, BN), ceil_div(p.rows, BM), p.B);
+  bool ln = false;
+  for (int s = 0; s < p.nsrc; ++s) ln = ln || p.src[s].pre_act == WNB200_PRE_LNRELU;
+  if (ln && epilogue != WNB200_EPI_NONE && epilogue != WNB200_EPI_MU) {
+    set_error("taps_fwd: PRE_LNRELU sources go with EPI_NONE or EPI_MU");
+    return 1;
+  }
   switch (epilogue) {
-    case WNB200_EPI_NONE: taps_fwd_kernel<T, WNB200_EPI_NONE><<<grid, NT, 0, st>>>(p); break;
-    case WNB200_EPI_LEAKY: taps_fwd_kernel<T, WNB200_EPI_LEAKY><<<grid, NT, 0, st>>>(p); break;
-    case WNB200_EPI_GATE: taps_fwd_kernel<T, WNB200_EPI_GATE><<<grid, NT, 0, st>>>(p); break;
-    case WNB200_EPI_MU: taps_fwd_kernel<T, WNB200_EPI_MU><<<grid, NT, 0, st>>>(p); break;
+    case WNB200_EPI_NONE:
+      if (ln) taps_fwd_kernel<T, WNB200_EPI_NONE, true><<<grid, NT, 0, st>>>(p);
+      else taps_fwd_kernel<T, WNB200_EPI_NONE, false><<<grid, NT, 0, st>>>(p);
+      break;
+    case WNB200_EPI_LEAKY: taps_fwd_kernel<T, WNB200_EPI_LEAKY, false><<<grid, NT, 0, st>>>(p); break;
+    case WNB200_EPI_GATE: taps_fwd_kernel<T, WNB200_EPI_GATE, false><<<grid, NT, 0, st>>>(p); break;
+    case WNB200_EPI_MU:
+      if (ln) taps_fwd_kernel<T, WNB200_EPI_MU, true><<<grid, NT, 0, st>>>(p);
+      else taps_fwd_kernel<T, WNB200_EPI_MU, false><<<grid, NT, 0, st>>>(p);
+      break;
     default: set_error("taps_fwd: bad epilogue %d", epilogue); return 1;
   }
   WNB_LAUNCH_OK();
