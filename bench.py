@@ -162,7 +162,7 @@ def cpu_baseline(w, target_s=12.0, threads=None):
 def train_step_measure(w, rank, world, dist, max_over_ranks, barrier, steps=5, warmup=2):
     """The metric's "fwd+bwd" half: BASELINE configs[2], the WaveNet-CTC train step (legacy_code/train.py:24-61) on
     the same WaveNet plus the ecoli classifier, batch-sharded (weak scaling), bf16 tensor-core kernels with fp32
-    master weights, fused Adam, gradient all-reduce when N > 1.  Inputs resident on the device."""
+    master weights, Adam (wavenet_speech_b200.optim.Adam: torch.optim.Adam's update in one launch), gradient all-reduce when N > 1.  Inputs resident on the device."""
     import wavenet_speech_b200 as W
     from wavenet_speech_b200 import train as TRN
     from wavenet_speech_b200.utils import signal_gen as S
@@ -171,7 +171,7 @@ def train_step_measure(w, rank, world, dist, max_over_ranks, barrier, steps=5, w
     wn = W.WaveNet(w["in_dim"], w["entry_k"], [(C, C, 2, d) for d in w["dil"]], C, softmax=False).cuda()
     cn = W.WaveNetClassifier(C, 5, [(C, C, 2, d) for d in [1, 2, 4, 8, 16] * 3], C, pool_kernel_size=3,
                              softmax=False).cuda()
-    opt = torch.optim.Adam(list(wn.parameters()) + list(cn.parameters()), lr=1e-5, fused=True)
+    opt = W.optim.Adam(list(wn.parameters()) + list(cn.parameters()), lr=1e-5)    # torch.optim.Adam's rule, one launch
     B, T = w["batch"], w["T"]
     nb = min(B, 8)
     lev, labels = S.quantized_batch(nb, T, num_levels=w["in_dim"], seed=77 + rank, with_labels=True)

@@ -543,6 +543,26 @@ int wnb200_linear_frame(int dtype, int N, int Cin, int Cout, int k, int dilation
 int wnb200_linear_step(int dtype, int N, int Cin, int Cout, int k, int dilation, int64_t step, const void* w,
                        const float* bias, const void* x, void* hist, void* y, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Adam over every parameter tensor in ONE launch (legacy_code/train.py:55 `opt.step()`; torch.optim.Adam semantics
+ * without amsgrad: g += wd * p; m = b1 m + (1 - b1) g; v = b2 v + (1 - b2) g^2;
+ * p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)), fp32 state, fp32 or bf16 parameters / gradients.
+ * items (DEVICE array): one entry per tensor; chunks (DEVICE array of nchunks (item, first element) int32 pairs):
+ * tensor i contributes ceil(numel_i / wnb200_adam_chunk_elems()) consecutive chunks.  step counts from 1.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  void* param;       /* fp32 or bf16 [numel] */
+  const void* grad;  /* same dtype as param */
+  float* exp_avg;    /* fp32 [numel] */
+  float* exp_avg_sq; /* fp32 [numel] */
+  int64_t numel;
+  int32_t is_bf16;
+  int32_t reserved0;
+} wnb200_adam_item_t;
+int wnb200_adam_chunk_elems(void);
+int wnb200_adam_step(int nchunks, const wnb200_adam_item_t* items /*device*/, const int32_t* chunks /*device*/, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -105,7 +105,10 @@ if "train_tc" in which:    # config 3 on the tensor-core path: bf16 operands, fp
     dil = [1, 2, 4, 8, 16, 32, 64, 128, 256, 512] * 2
     wn = W.WaveNet(256, 2, [(256, 256, 2, d) for d in dil], 256, softmax=False).cuda()
     cn = W.WaveNetClassifier(256, 5, [(256, 256, 2, d) for d in ECOLI], 256, pool_kernel_size=3, softmax=False).cuda()
-    opt = torch.optim.Adam(list(wn.parameters()) + list(cn.parameters()), lr=1e-5, fused=True)
+    if opts.get("opt", "ours") == "torch":
+        opt = torch.optim.Adam(list(wn.parameters()) + list(cn.parameters()), lr=1e-5, fused=True)
+    else:
+        opt = W.optim.Adam(list(wn.parameters()) + list(cn.parameters()), lr=1e-5)
     B, T = int(opts.get("B", 32)), int(opts.get("T", 16384))
     lev, labels = SG.quantized_batch(min(B, 8), T, seed=5, with_labels=True)
     rep = (B + 7) // 8

@@ -112,7 +112,7 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
     pairs = {"wnb200_src_t": _lib.Src, "wnb200_chain_t": _lib.Chain, "wnb200_resblock_t": _lib.ResBlock,
              "wnb200_dense_t": _lib.Dense, "wnb200_ln_t": _lib.Ln, "wnb200_taps_t": _lib.Taps,
              "wnb200_pack_block_t": _lib.PackBlock, "wnb200_pack_head_t": _lib.PackHead,
-             "wnb200_wgrad_job_t": _lib.WgradJob}
+             "wnb200_wgrad_job_t": _lib.WgradJob, "wnb200_adam_item_t": _lib.AdamItem}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "wnb200.h"', 'int main(void) {']
     for cname, cls in pairs.items():
         lines.append('  printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))

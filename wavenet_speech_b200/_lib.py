@@ -89,6 +89,12 @@ class WgradJob(ctypes.Structure):
                 ("N", ctypes.c_int32), ("nsrc", ctypes.c_int32), ("off", ctypes.c_int32 * 2), ("dw", c_void_p)]
 
 
+class AdamItem(ctypes.Structure):
+    """Mirror of wnb200_adam_item_t."""
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
+                ("numel", c_int64), ("is_bf16", ctypes.c_int32), ("reserved0", ctypes.c_int32)]
+
+
 class PackBlock(_Sized):
     """Mirror of wnb200_pack_block_t."""
     _fields_ = [("struct_size", ctypes.c_uint32), ("C", ctypes.c_int32), ("k", ctypes.c_int32),
@@ -121,6 +127,9 @@ SIGNATURES = {
     "wnb200_linear_frame": [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_linear_step": [c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_void_p, c_void_p],
+    "wnb200_adam_chunk_elems": [],
+    "wnb200_adam_step": [c_int, c_void_p, c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                         ctypes.c_float, c_int64, c_void_p],
     "wnb200_taps_wgrad": [c_int, c_int, c_int, c_int, ctypes.POINTER(Src), c_void_p, c_void_p, c_void_p],
     "wnb200_channel_reduce": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_gate_bwd": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
@@ -219,7 +228,7 @@ def load():
 # kernel launches issued per C-ABI call (for bench.py's `gpu_launches` claim)
 _LAUNCHES_PER_CALL = {"wnb200_sum_f32": 2, "wnb200_last_error": 0, "wnb200_version": 0, "wnb200_check_device": 0,
                       "wnb200_tc_pack_bytes": 0, "wnb200_ctc_workspace_bytes": 0, "wnb200_ctc_fwd": 2,
-                      "wnb200_workspace_bytes": 0}
+                      "wnb200_workspace_bytes": 0, "wnb200_adam_chunk_elems": 0}
 launch_count = 0
 _event_log = None     # list of (name, start_event, end_event) while kernel timing is on
 current_tag = None    # optional label (e.g. "resblock") attached to timed calls by the caller
