@@ -1,5 +1,7 @@
 """wavenet_speech_b200.optim.Adam (one launch over every parameter tensor) against torch.optim.Adam, the optimizer the
 reference trains with (legacy_code/train.py:112-114, 55)."""
+import copy
+
 import pytest
 import torch
 
@@ -59,7 +61,7 @@ def test_state_dict_round_trip_with_torch():
         for a, b in zip(ps, pr):
             a.copy_(b)
     o = W.optim.Adam(ps, lr=1e-2)
-    o.load_state_dict(t.state_dict())
+    o.load_state_dict(copy.deepcopy(t.state_dict()))      # (load_state_dict keeps the tensors it is handed)
     for step in range(3, 6):
         torch.manual_seed(step)
         for a, b in zip(ps, pr):
@@ -70,7 +72,7 @@ def test_state_dict_round_trip_with_torch():
     for a, b in zip(ps, pr):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
     t2 = torch.optim.Adam(pr, lr=1e-2)
-    t2.load_state_dict(o.state_dict())
+    t2.load_state_dict(copy.deepcopy(o.state_dict()))
     assert float(t2.state[pr[0]]["step"]) == 6.0
     for step in range(6, 8):
         torch.manual_seed(step)
