@@ -543,6 +543,19 @@ int wnb200_linear_frame(int dtype, int N, int Cin, int Cout, int k, int dilation
 int wnb200_linear_step(int dtype, int N, int Cin, int Cout, int k, int dilation, int64_t step, const void* w,
                        const float* bias, const void* x, void* hist, void* y, void* stream);
 
+/* Tensor-core form of the ByteNet blocks (bf16 inference; contractions = wnb200_dense_fwd_tc on NLC activations):
+ * lnrelu_rows:          y[r, :] = ReLU(LayerNorm(x[r, :])) for NLC rows (r = frame), bf16 in / out, C % 8 == 0, C <= 1024.
+ * mu_gate_rows:         out = g1 * tanh(g2 * h + g3 * tanh(u)) with the pre-activation of unit u (gate1, gate2, gate3,
+ *                       update) at pre_u + r * pre_pitch + c (four tensors or four column blocks of one).
+ * nlc_parts_to_ncl_add: out[b, p * Cp + c, t] = residual[b, p * Cp + c, t] + parts[p][b, t, c]: back to NCL with the block's
+ *                       `seq +` (block.py:119,166); parts = host array of nparts <= 4 device pointers. */
+int wnb200_lnrelu_rows(int64_t rows, int C, const void* x, const float* gamma, const float* beta, float eps, void* y,
+                       void* stream);
+int wnb200_mu_gate_rows(int64_t rows, int C, const void* pre0, const void* pre1, const void* pre2, const void* pre3,
+                        int64_t pre_pitch, const void* h, void* out, void* stream);
+int wnb200_nlc_parts_to_ncl_add(int B, int C, int T, int nparts, int Cp, const void* const* parts /*host*/,
+                                const void* residual, void* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Adam over every parameter tensor in ONE launch (legacy_code/train.py:55 `opt.step()`; torch.optim.Adam semantics
  * without amsgrad: g += wd * p; m = b1 m + (1 - b1) g; v = b2 v + (1 - b2) g^2;

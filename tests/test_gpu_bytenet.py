@@ -217,3 +217,51 @@ def test_stream_matches_the_causal_convolution(cin, cout, k, d, N, T, dtype):
         with torch.no_grad():
             yl = conv.linear(sq[:, :, T - rf:].contiguous())
         assert _err(yl, ref[:, :, -1]) <= tol
+
+
+@pytest.mark.parametrize("kind,nch,k,d,B,T", [("relu", 512, 3, 4, 2, 1003), ("mu", 512, 3, 4, 2, 1003),
+                                               ("relu", 384, 2, 16, 3, 512), ("mu", 384, 2, 5, 1, 777),
+                                               ("relu", 256, 1, 1, 2, 300), ("mu", 128, 3, 2, 4, 64),
+                                               ("mu", 256, 2, 512, 1, 2048)])
+def test_tensor_core_form(kind, nch, k, d, B, T):
+    """bf16 inference on the tcgen05 form (bytenet_tc.py): against the fp32 oracle on the same bf16-rounded weights and
+    input (<= 2e-2), and against the generic CUDA-core kernels on the same tensors; the launches are dense2 contractions."""
+    from wavenet_speech_b200 import bytenet_tc
+    torch.manual_seed(2000 + nch + T + k)
+    cls = W.ResidualMUBlock if kind == "mu" else W.ResidualReLUBlock
+    fn = O.residual_mu_block if kind == "mu" else O.residual_relu_block
+    net = cls(nch, k, d)
+    net.init()
+    with torch.no_grad():
+        for n, p in net.named_parameters():
+            if n.endswith("gamma") or n.endswith("beta"):
+                p.add_(torch.randn_like(p) * 0.2)
+    sd = {kk: v.detach().to(torch.bfloat16).float() for kk, v in net.state_dict().items()}
+    x = torch.randn(B, nch, T).to(torch.bfloat16)
+    ref = fn(sd, "", x.float(), d)
+    net = net.cuda().to(torch.bfloat16)
+    xg = x.cuda()
+    assert bytenet_tc.eligible(net, xg)
+    log = []
+    orig = _lib.call
+
+    def spy(name, *a):
+        log.append(name)
+        return orig(name, *a)
+    _lib.call = spy
+    try:
+        with torch.no_grad():
+            y = net(xg)
+    finally:
+        _lib.call = orig
+    assert "wnb200_dense_fwd_tc" in log and "wnb200_taps_fwd_ex" not in log and "wnb200_taps_fwd" not in log, log
+    assert y.dtype == torch.bfloat16 and tuple(y.shape) == tuple(ref.shape)
+    assert _err(y, ref) <= 2e-2, (kind, nch, _err(y, ref))
+    bytenet_tc.ENABLED = False
+    try:
+        with torch.no_grad():
+            y_gen = net(xg)
+    finally:
+        bytenet_tc.ENABLED = True
+    assert _err(y, y_gen.float().cpu()) <= 2e-2, _err(y, y_gen.float().cpu())
+    assert not bytenet_tc.eligible(net, xg.float()) and not bytenet_tc.eligible(net, xg.clone().requires_grad_(True))

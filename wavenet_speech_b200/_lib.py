@@ -127,6 +127,10 @@ SIGNATURES = {
     "wnb200_linear_frame": [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "wnb200_linear_step": [c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_void_p, c_void_p],
+    "wnb200_lnrelu_rows": [c_int64, c_int, c_void_p, c_void_p, c_void_p, ctypes.c_float, c_void_p, c_void_p],
+    "wnb200_mu_gate_rows": [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
+    "wnb200_nlc_parts_to_ncl_add": [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p), c_void_p, c_void_p,
+                                    c_void_p],
     "wnb200_adam_chunk_elems": [],
     "wnb200_adam_step": [c_int, c_void_p, c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                          ctypes.c_float, c_int64, c_void_p],

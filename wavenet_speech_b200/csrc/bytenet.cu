@@ -320,6 +320,165 @@ static int launch_linear(LinParams& p, cudaStream_t st) {
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------ tensor-core form (NLC rows)
+// On the tcgen05 path (bf16 inference, bytenet_tc.py) activations are NLC: a frame's channels are contiguous, LayerNorm
+// is a row reduction.  One warp per frame row, the row in registers (C <= 1024: 4 x 16-byte vectors per lane), two
+// passes (mean, then the unbiased variance about it), ReLU, one 16-byte store per vector.
+constexpr int LR_MAXV = 4;
+
+__global__ void __launch_bounds__(256) lnrelu_rows_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float eps, __nv_bfloat16* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = C >> 3;                       // 16-byte vectors per row
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
+  uint4 raw[LR_MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LR_MAXV; ++i) {
+    const int v = lane + 32 * i;
+    raw[i] = make_uint4(0, 0, 0, 0);
+    if (v < nvec) {
+      raw[i] = xr[v];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s += __low2float(h[q]) + __high2float(h[q]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < LR_MAXV; ++i) {
+    if (lane + 32 * i < nvec) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float a = __low2float(h[q]) - mean, b = __high2float(h[q]) - mean;
+        var += a * a + b * b;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float r = 1.f / (sqrtf(var / (float)(C - 1)) + eps);
+  uint4* yr = reinterpret_cast<uint4*>(y + row * C);
+#pragma unroll
+  for (int i = 0; i < LR_MAXV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8), g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(beta + v * 8), b1 = *reinterpret_cast<const float4*>(beta + v * 8 + 4);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      uint4 o;
+      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float a = fmaxf(gg[2 * q] * (__low2float(h[q]) - mean) * r + bb[2 * q], 0.f);
+        const float b = fmaxf(gg[2 * q + 1] * (__high2float(h[q]) - mean) * r + bb[2 * q + 1], 0.f);
+        oh[q] = __floats2bfloat162_rn(a, b);
+      }
+      yr[v] = o;
+    }
+  }
+}
+
+// MultiplicativeUnit gate on NLC rows: pre-activations of unit u at pre[u] + row * pitch + c (four tensors, or four
+// column blocks of one), h and out [rows, C].  8 channels per thread, 16-byte accesses.
+struct MuRows {
+  const __nv_bfloat16* pre[4];
+  long long pitch;
+};
+
+__global__ void __launch_bounds__(256) mu_gate_rows_kernel(long long rows, int C, const MuRows m,
+                                                           const __nv_bfloat16* __restrict__ h,
+                                                           __nv_bfloat16* __restrict__ out) {
+  const int nvec = C >> 3;
+  const long long total = rows * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / nvec;
+    const int c = (int)(i - row * nvec) * 8;
+    uint4 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) p[u] = *reinterpret_cast<const uint4*>(m.pre[u] + row * m.pitch + c);
+    const uint4 hv = *reinterpret_cast<const uint4*>(h + row * C + c);
+    uint4 o;
+    __nv_bfloat16* oe = reinterpret_cast<__nv_bfloat16*>(&o);
+    const __nv_bfloat16* he = reinterpret_cast<const __nv_bfloat16*>(&hv);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float g1 = sigmoid_precise(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(&p[0])[q]));
+      const float g2 = sigmoid_precise(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(&p[1])[q]));
+      const float g3 = sigmoid_precise(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(&p[2])[q]));
+      const float u = tanhf(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(&p[3])[q]));
+      oe[q] = __float2bfloat16_rn(g1 * tanhf(g2 * __bfloat162float(he[q]) + g3 * u));
+    }
+    *reinterpret_cast<uint4*>(out + row * C + c) = o;
+  }
+}
+
+// out[b, p * Cp + c, t] = residual[b, p * Cp + c, t] + part_p[b, t, c]: the block's last 1x1 leaves the tensor-core
+// path as up to 4 NLC column blocks (N <= 256 per contraction); this is the layout change back to NCL with the
+// `seq +` of block.py:119,166 riding on it.  64 x 64 tiles through shared memory, 16-byte accesses on both sides.
+struct PartsArgs {
+  const __nv_bfloat16* part[4];
+  int nparts, Cp;
+};
+
+__global__ void __launch_bounds__(256) nlc_parts_to_ncl_add_kernel(int C, int Tn, const PartsArgs a,
+                                                                   const __nv_bfloat16* __restrict__ residual,
+                                                                   __nv_bfloat16* __restrict__ out) {
+  __shared__ uint32_t tile[64][33];               // [frame][channel pair], odd pitch: conflict-free writes, 2-way reads
+  const int b = blockIdx.z, c0 = blockIdx.y * 64, t0 = blockIdx.x * 64;
+  const int part = c0 / a.Cp, cp0 = c0 - part * a.Cp;
+  const __nv_bfloat16* src = a.part[part] + ((long long)b * Tn) * a.Cp + cp0;
+  for (int i = threadIdx.x; i < 64 * 8; i += 256) {       // a frame's 64 channels = 8 vectors of 16 bytes
+    const int f = i >> 3, v = i & 7;
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (t0 + f < Tn) q = *reinterpret_cast<const uint4*>(src + (long long)(t0 + f) * a.Cp + v * 8);
+    tile[f][v * 4 + 0] = q.x; tile[f][v * 4 + 1] = q.y; tile[f][v * 4 + 2] = q.z; tile[f][v * 4 + 3] = q.w;
+  }
+  __syncthreads();
+  const bool vec = (Tn & 7) == 0;
+  {
+    const int cp = threadIdx.x >> 3, fv = (threadIdx.x & 7) * 8;     // channel pair, first of 8 frames
+    if (t0 + fv < Tn) {
+      uint32_t w[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) w[q] = tile[fv + q][cp];
+#pragma unroll
+      for (int hch = 0; hch < 2; ++hch) {
+        const long long o = ((long long)b * C + c0 + 2 * cp + hch) * Tn + t0 + fv;
+        float v8[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const __nv_bfloat162 pr = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
+          v8[q] = hch ? __high2float(pr) : __low2float(pr);
+        }
+        if (vec) {
+          const uint4 rq = *reinterpret_cast<const uint4*>(residual + o);
+          const __nv_bfloat162* re = reinterpret_cast<const __nv_bfloat162*>(&rq);
+          uint4 ov;
+          __nv_bfloat162* oe = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            oe[q] = __floats2bfloat162_rn(__low2float(re[q]) + v8[2 * q], __high2float(re[q]) + v8[2 * q + 1]);
+          *reinterpret_cast<uint4*>(out + o) = ov;
+        } else {
+          for (int q = 0; q < 8 && t0 + fv + q < Tn; ++q)
+            out[o + q] = __float2bfloat16_rn(__bfloat162float(residual[o + q]) + v8[q]);
+        }
+      }
+    }
+  }
+}
+
 }  // namespace wnb
 
 using namespace wnb;
@@ -424,4 +583,52 @@ extern "C" int wnb200_linear_step(int dtype, int N, int Cin, int Cout, int k, in
   }
   cudaStream_t st = (cudaStream_t)stream;
   BN_DISPATCH(dtype, "linear_step", return launch_linear<T>(p, st));
+}
+
+extern "C" int wnb200_lnrelu_rows(int64_t rows, int C, const void* x, const float* gamma, const float* beta, float eps,
+                                  void* y, void* stream) {
+  if (rows == 0) return 0;
+  WNB_CHECK_ARG(x && gamma && beta && y, "lnrelu_rows: null pointer");
+  WNB_CHECK_ARG(C >= 8 && C % 8 == 0 && C <= 256 * LR_MAXV, "lnrelu_rows: C=%d must be a multiple of 8 <= %d", C, 256 * LR_MAXV);
+  WNB_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) |
+                  reinterpret_cast<uintptr_t>(beta)) & 15) == 0, "lnrelu_rows: pointers must be 16-byte aligned");
+  const long long ctas = (rows + 7) / 8;
+  WNB_CHECK_ARG(ctas < (1ll << 31), "lnrelu_rows: too many rows");
+  lnrelu_rows_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(rows, C, (const bf16*)x, gamma, beta, eps, (bf16*)y);
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_mu_gate_rows(int64_t rows, int C, const void* pre0, const void* pre1, const void* pre2,
+                                   const void* pre3, int64_t pre_pitch, const void* h, void* out, void* stream) {
+  if (rows == 0) return 0;
+  WNB_CHECK_ARG(pre0 && pre1 && pre2 && pre3 && h && out, "mu_gate_rows: null pointer");
+  WNB_CHECK_ARG(C >= 8 && C % 8 == 0 && pre_pitch >= C && pre_pitch % 8 == 0, "mu_gate_rows: C=%d pitch=%lld", C,
+                (long long)pre_pitch);
+  MuRows m;
+  m.pre[0] = (const bf16*)pre0; m.pre[1] = (const bf16*)pre1; m.pre[2] = (const bf16*)pre2; m.pre[3] = (const bf16*)pre3;
+  m.pitch = pre_pitch;
+  const long long total = rows * (C / 8);
+  long long g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  mu_gate_rows_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(rows, C, m, (const bf16*)h, (bf16*)out);
+  WNB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int wnb200_nlc_parts_to_ncl_add(int B, int C, int T_, int nparts, int Cp, const void* const* parts,
+                                           const void* residual, void* out, void* stream) {
+  if (B == 0 || T_ == 0) return 0;
+  WNB_CHECK_ARG(parts && residual && out, "nlc_parts_to_ncl_add: null pointer");
+  WNB_CHECK_ARG(nparts >= 1 && nparts <= 4 && Cp % 64 == 0 && nparts * Cp == C, "nlc_parts_to_ncl_add: C=%d = %d x %d?", C,
+                nparts, Cp);
+  WNB_CHECK_ARG(B <= 65535, "nlc_parts_to_ncl_add: batch too large");
+  PartsArgs a;
+  a.nparts = nparts; a.Cp = Cp;
+  for (int i = 0; i < 4; ++i) a.part[i] = i < nparts ? (const bf16*)parts[i] : nullptr;
+  for (int i = 0; i < nparts; ++i) WNB_CHECK_ARG(parts[i] != nullptr, "nlc_parts_to_ncl_add: part %d is null", i);
+  dim3 grid(ceil_div(T_, 64), C / 64, B);
+  nlc_parts_to_ncl_add_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(C, T_, a, (const bf16*)residual, (bf16*)out);
+  WNB_LAUNCH_OK();
+  return 0;
 }

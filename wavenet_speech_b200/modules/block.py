@@ -126,6 +126,9 @@ class ResidualMUBlock(_ByteNetBlock):
     def forward(self, seq):
         """Three (statistics, contraction) pairs: each LayerNorm + ReLU is applied as the following convolution loads
         its operand, the last contraction's store adds `seq`."""
+        from .. import bytenet_tc
+        if bytenet_tc.eligible(self, seq):        # bf16 inference: the tcgen05 form (NLC, dense2 contractions)
+            return bytenet_tc.relu_block_forward(self, seq)
         st = self.stack
         seq = seq.contiguous()
         h = WF.fused_conv(seq, st[2].weight, st[2].bias, [0], ln=st[0])
@@ -138,6 +141,9 @@ class ResidualMUBlock(_ByteNetBlock):
         statistics; MU(k, d) = ONE contraction whose operand and whose gate's h are ReLU(LN(.)) formed on the fly and
         whose epilogue is the gate; MU(1) likewise; 1x1 whose store adds `seq`.  With gradients the two units run as
         contraction + gate kernel on a stored h (their backward needs both)."""
+        from .. import bytenet_tc
+        if bytenet_tc.eligible(self, seq):        # bf16 inference: the tcgen05 form (NLC, dense2 contractions)
+            return bytenet_tc.mu_block_forward(self, seq)
         st = self.stack
         seq = seq.contiguous()
         z = WF.fused_conv(seq, st[2].weight, st[2].bias, [0], ln=st[0])
@@ -167,6 +173,9 @@ class ResidualReLUBlock(_ByteNetBlock):
     def forward(self, seq):
         """Three (statistics, contraction) pairs: each LayerNorm + ReLU is applied as the following convolution loads
         its operand, the last contraction's store adds `seq`."""
+        from .. import bytenet_tc
+        if bytenet_tc.eligible(self, seq):        # bf16 inference: the tcgen05 form (NLC, dense2 contractions)
+            return bytenet_tc.relu_block_forward(self, seq)
         st = self.stack
         seq = seq.contiguous()
         h = WF.fused_conv(seq, st[2].weight, st[2].bias, [0], ln=st[0])
