@@ -277,7 +277,8 @@ typedef struct {
   void* skips_act;        /* optional (last layer of an inference stack, res = NULL): NLC bf16 [B,T,C] that receives
                              LeakyReLU(skips + contribution) (wavenet.py:100-103); `skips` is then read, not updated */
   const void* x_lo;       /* F16X2: lo half of the input stream, NLC fp16 [B,T,C]; NULL = the input is exactly x */
-  void* res_lo;           /* F16X2: lo half of the output stream (required when res != NULL) */
+  void* res_lo;           /* F16X2: lo half of the output stream; NULL with gate_out: the output stream carries its hi half
+                             only (the last blocks of a deep stack, whose rounding is hardly amplified any more) */
   void* gate_out;         /* optional: NLC [B,T,C] in act_fmt that receives the gate tanh(.)*sigmoid(.).  When
                              given, the call does NOT touch `skips` (may be NULL): the skip sum of the whole stack,
                              sum_l (Wbn_l Wskip_l) gate_l + biases, is left to ONE wnb200_dense_fwd_tc call with

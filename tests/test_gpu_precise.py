@@ -346,3 +346,34 @@ def test_raw_ctcnet_positions_on_the_tensor_core_path(C, mode):
         g_t0 = net32(x.cuda(), t0=1234).float().cpu()
     assert G.rel_linf(y_t0, g_t0) <= TOL, G.rel_linf(y_t0, g_t0)
     assert G.rel_linf(y_t0, y) > 1e-3
+
+
+def test_hi_only_tail_of_a_stack():
+    """The block kernel accepts `res` without `res_lo` (the stream's hi half only); fastpath.HI_ONLY_TAIL hands the last
+    blocks of a stack over that way.  8 blocks with the last 4 hi-only: still within the tolerance, different bits from
+    the all-pair run (the knob did something), and the default (0) is bit-identical to itself."""
+    torch.manual_seed(5)
+    C = 256
+    layers = [(C, C, 2, d) for d in [1, 2, 4, 8, 16, 32, 64, 128]]
+    net = W.WaveNet(C, 2, layers, C, softmax=False)
+    sd = {k: r16(v) for k, v in net.state_dict().items()}
+    lev = torch.randint(0, C, (2, 700))
+    x = torch.zeros(2, C, 700).scatter_(1, lev.unsqueeze(1), 1.0)
+    ref = O.wavenet_forward(sd, x, layers, softmax=False)
+    net = net.cuda().bfloat16().eval()
+    xg = x.cuda().bfloat16()
+    assert FP.HI_ONLY_TAIL == 0
+    with torch.no_grad():
+        y0 = net(xg)
+        try:
+            FP.HI_ONLY_TAIL = 4
+            y4 = net(xg)
+            FP.HI_ONLY_TAIL = 100                    # more than the stack has: every block hi-only
+            y_all = net(xg)
+        finally:
+            FP.HI_ONLY_TAIL = 0
+        y0b = net(xg)
+    assert torch.equal(y0, y0b)
+    e0, e4, ea = (G.rel_linf(t.float().cpu(), ref) for t in (y0, y4, y_all))
+    assert e0 <= TOL and e4 <= TOL and ea <= TOL, (e0, e4, ea)
+    assert not torch.equal(y0, y_all)

@@ -37,7 +37,7 @@ struct Res3Dev {
   int ntaps, t_off[3];
   const float* bias1;   // [2C] packed like W1 rows (pre-scaled in the fp16 format)
   const float* bias2;   // [>= C] bres + bproj
-  int write_res, has_lo;
+  int write_res, has_lo, write_lo;   // write_lo: the fp16 format's output carries its lo half (else hi only)
   int* sat_flag;        // optional: set to 1 when a stream value left the fp16 range (the hi half saturated)
   bf16* sg_out;         // SAVE (training, bf16 format): NLC [B,T,C] that receives sigmoid(.) -- backward's second factor
 };
@@ -399,7 +399,9 @@ resblock3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           mbar_arrive_cluster(r_e2a);
         }
         uint32_t pk[16];
-        if constexpr (PREC) {
+        bool pair_out = false;
+        if constexpr (PREC) pair_out = p.write_lo != 0;
+        if (pair_out) {
           uint32_t pl[16];
           uint32_t sat = 0;
 #pragma unroll
@@ -428,8 +430,19 @@ resblock3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             bulk_commit();
           }
         } else {
+          if constexpr (PREC) {                   // fp16 format, hi half only (the tail of a deep stack, fastpath.py)
+            uint32_t sat = 0;
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) pk[i >> 1] = pack_bf16x2(a[i] + bv[i], a[i + 1] + bv[i + 1]);
+            for (int i = 0; i < 32; i += 2) {
+              pk[i >> 1] = pack_f16x2_sat(a[i] + bv[i], a[i + 1] + bv[i + 1]);
+              const uint32_t m = pk[i >> 1] & 0x7fff7fffu;
+              sat |= (uint32_t)((m & 0xffffu) == 0x7bffu) | (uint32_t)((m >> 16) == 0x7bffu);
+            }
+            if (sat && p.sat_flag) atomicOr(p.sat_flag, 1);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) pk[i >> 1] = pack_bf16x2(a[i] + bv[i], a[i + 1] + bv[i + 1]);
+          }
           const uint32_t boff = (nchunk & 1u) * R3_ABYTES;
           // at most the latest group may still be reading: that is either the other buffer's chunk or the gate store
           if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -483,7 +496,7 @@ int resblock3_launch(const wnb200_resblock_t* a, void* stream) {
                 "resblock_fwd_tc: with gate_out the gate IS the saved activation; only save_sg may accompany it");
   WNB_CHECK_ARG(!a->save_sg || !prec, "resblock_fwd_tc: save_sg (training) belongs to the bf16 format");
   WNB_CHECK_ARG(prec || (!a->x_lo && !a->res_lo), "resblock_fwd_tc: x_lo / res_lo belong to the fp16 (hi, lo) format");
-  WNB_CHECK_ARG(!prec || !a->res || a->res_lo, "resblock_fwd_tc: the fp16 (hi, lo) format writes res AND res_lo");
+  // (fp16 format: res without res_lo = the output stream carries its hi half only)
   Res3Dev p;
   memset(&p, 0, sizeof(p));
   p.B = a->B; p.T = a->T;
@@ -494,6 +507,7 @@ int resblock3_launch(const wnb200_resblock_t* a, void* stream) {
   p.bias1 = a->bias1; p.bias2 = a->bias2;
   p.write_res = a->res != nullptr;
   p.has_lo = prec && a->x_lo != nullptr;
+  p.write_lo = prec && a->res != nullptr && a->res_lo != nullptr;
   p.sat_flag = prec ? reinterpret_cast<int*>(a->sat_flag) : nullptr;
   p.sg_out = reinterpret_cast<bf16*>(a->save_sg);
   CUtensorMap mx, mw1, mw2, mres, mgate, mxlo, mreslo;
@@ -505,7 +519,7 @@ int resblock3_launch(const wnb200_resblock_t* a, void* stream) {
   mres = mx; mxlo = mx; mreslo = mx;
   if (a->res && (rc = rb_map_nlc(&mres, a->res, a->B, a->T, C, 2))) return rc;
   if (p.has_lo && (rc = rb_map_nlc(&mxlo, a->x_lo, a->B, a->T, C, 2))) return rc;
-  if (prec && a->res && (rc = rb_map_nlc(&mreslo, a->res_lo, a->B, a->T, C, 2))) return rc;
+  if (p.write_lo && (rc = rb_map_nlc(&mreslo, a->res_lo, a->B, a->T, C, 2))) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (prec)
     return C == 256 ? launch_resblock3<256, true, false>(mx, mw1, mw2, mres, mgate, mxlo, mreslo, p, st)

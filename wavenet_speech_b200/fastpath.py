@@ -18,6 +18,7 @@ the K-major bf16 matrices the kernels stream by TMA (see wnb200.h, wnb200_chain_
   conv1x1_skip's output) and saves one of the block's five contractions.
 """
 import ctypes
+import os
 
 import torch
 
@@ -536,6 +537,15 @@ def _gate_stack_budget(dev):
     return min(GATE_STACK_BUDGET, free // 2)
 
 
+# Precise format: how many of the LAST blocks of a stack carry the stream as its fp16 hi half only (the kernel accepts
+# `res` without `res_lo`).  Dropping the lo half saves a seventh K slab and 2 x B*T*C*2 bytes of traffic per launch
+# (0.065 ms of 0.47 per config-2 layer).  Measured at 20 WaveNet / 16 RawCTCNet blocks
+# (profiles/r2_parity_hi_only_tail.jsonl, tests/tools/parity_hi_only_tail.py): worst output error 9.0e-3 with the pair
+# everywhere, 1.1e-2 with 6 hi-only blocks, 1.3e-2 with 10, 1.6e-2 with all of them (forward 10.9 -> 10.6 -> 9.7 ms): the
+# margin to the 2e-2 contract goes faster than the milliseconds, so the default keeps the pair in every block.
+HI_ONLY_TAIL = int(os.environ.get("WNB200_HI_ONLY_TAIL", "0"))
+
+
 def run_blocks_deferred(h, packs, skip, h_lo=None):
     """Residual stack with the skip sum deferred (resblock3_kernel + one `nlayers` contraction): returns the head's
     input LeakyReLU(skip sum) as an NLC tensor in the packs' format.  The running sum never exists in HBM.
@@ -553,19 +563,23 @@ def run_blocks_deferred(h, packs, skip, h_lo=None):
     prec = packs[0].get("fmt", 0) == _lib.ACT_F16X2
     gates = torch.empty((L, B, T, C), dtype=h.dtype, device=h.device)
     buf = [h, torch.empty_like(h)]
-    lo = [h_lo, torch.empty_like(h)] if prec else [None, None]
+    lo = [h_lo, None]                              # [the input's lo half or None, a spare buffer]
     sat = None
     if prec and _sat_ctx is not None:
         sat = _sat_ctx["flag"]
         _sat_ctx["ran"] = True
+    n_pair = max(0, L - 1 - HI_ONLY_TAIL)          # blocks 0 .. n_pair-1 hand a (hi, lo) pair to their successor
     for l, pk in enumerate(packs):
         last = l == L - 1
+        out_lo = prec and not last and l < n_pair
+        if out_lo and lo[1] is None:
+            lo[1] = torch.empty_like(h)
         resblock(buf[0], pk, None if last else buf[1], None, False, x_lo=lo[0],
-                 res_lo=None if (last or not prec) else lo[1], gate_out=gates[l], sat_flag=sat)
+                 res_lo=lo[1] if out_lo else None, gate_out=gates[l], sat_flag=sat)
         if not last:
             buf = [buf[1], buf[0]]
             if prec:
-                lo = [lo[1], lo[0] if lo[0] is not None else torch.empty_like(h)]
+                lo = [lo[1], lo[0]] if out_lo else [None, lo[1] if lo[1] is not None else lo[0]]
     wcat, bsum = skip
     return dense(gates, [0], wcat, bsum, C, leaky=1, fmt=packs[0].get("fmt", 0), nlayers=L)
 
