@@ -232,7 +232,8 @@ class _ResBlock(torch.autograd.Function):
             else:
                 act, th, sg = ops.taps_fwd(gterms, bg, M, T, EPI_GATE), None, None
         wres2, wproj2, wskip2 = _slabs(wres, dtype)[0], _slabs(wproj, dtype)[0], _slabs(wskip, dtype)[0]
-        b_res = _f32(bres) + _f32(bproj)
+        b_res = _cached_layout([bres, bproj], "bias_sum", torch.float32,
+                               lambda: (bres.detach().float() + bproj.detach().float()).contiguous())
         res = ops.taps_fwd([Term(act, wres2), Term(x, wproj2)], b_res, M, T)
         skip = ops.taps_fwd([Term(act, wskip2)], _f32(bskip), M, T)
         ctx.offsets = list(offsets)
