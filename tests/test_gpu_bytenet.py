@@ -268,3 +268,41 @@ def test_tensor_core_form(kind, nch, k, d, B, T):
     with torch.no_grad():
         assert not bytenet_tc.eligible(net, xg.float())          # fp32 keeps the fp32-accurate kernels
     assert not bytenet_tc.eligible(net, xg)                      # gradients requested: generic kernels (they have a backward)
+
+
+def test_randomised_small_shapes_and_edges():
+    """Random small configurations (odd channel counts around the tile sizes, T down to 1 and below the dilation, kernel
+    widths 1..6 incl. chained tap launches): forward without gradients (fused epilogues) and with (contraction + gate
+    kernels) against the oracle; empty batch."""
+    import random
+    rng = random.Random(1234)
+    for it in range(14):
+        kind = rng.choice(["relu", "mu"])
+        nch = 2 * rng.choice([2, 3, 5, 8, 17, 31, 33, 48, 65])
+        k = rng.choice([1, 2, 2, 3, 4, 6]) if kind == "relu" else rng.choice([1, 2, 3, 4])
+        d = rng.choice([1, 2, 3, 7, 16])
+        B = rng.choice([1, 2, 3])
+        T = rng.choice([1, 2, 3, 5, 17, 64, 129, 200])
+        torch.manual_seed(it)
+        cls = W.ResidualMUBlock if kind == "mu" else W.ResidualReLUBlock
+        fn = O.residual_mu_block if kind == "mu" else O.residual_relu_block
+        net = cls(nch, k, d)
+        net.init()
+        sd = {kk: v.detach().clone() for kk, v in net.state_dict().items()}
+        x = torch.randn(B, nch, T)
+        ref = fn(sd, "", x, d)
+        net = net.cuda()
+        with torch.no_grad():
+            y1 = net(x.cuda())
+        y2 = net(x.cuda().requires_grad_(True))
+        assert tuple(y1.shape) == tuple(ref.shape)
+        assert _err(y1, ref) <= FP32_TOL and _err(y2, ref) <= FP32_TOL, (kind, nch, k, d, B, T, _err(y1, ref), _err(y2, ref))
+    net = W.ResidualReLUBlock(8, 2, 2).cuda()
+    with torch.no_grad():
+        assert tuple(net(torch.zeros(0, 8, 16, device="cuda")).shape) == (0, 8, 16)
+    net = W.ResidualMUBlock(8, 2, 2).cuda()
+    with torch.no_grad():
+        assert tuple(net(torch.zeros(0, 8, 16, device="cuda")).shape) == (0, 8, 16)
+    conv = W.LinearConv1d(4, 6, 3, dilation=2).cuda()
+    with torch.no_grad():
+        assert tuple(conv.linear(torch.zeros(0, 4, conv.receptive_field, device="cuda")).shape) == (0, 6)
