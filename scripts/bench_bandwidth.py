@@ -85,3 +85,27 @@ report("featurize_nlc (B1: Conv1d(1,F,3) + LeakyReLU -> NLC bf16)", Bf * Tf * 2 
 logits = torch.randn(1024, 5, 4002, device="cuda", dtype=bf)
 report("ctc_greedy_decode (argmax + collapse + pack)", logits.numel() * 2 + 1024 * 4002 * 2,
        lambda: ops.ctc_greedy_decode(logits), note="1024 reads x 4002 frames x 5 classes; one CTA per read")
+
+# ---- ByteNet pieces: LayerNorm + ReLU on NLC rows (tensor-core form), the MU gate on rows, the way back to
+# NCL with the residual add; the NCL statistics / apply / backward kernels of the generic form
+import ctypes
+from wavenet_speech_b200 import functional as WF
+g32 = torch.ones(C, device="cuda") + 0.1 * torch.randn(C, device="cuda")
+b32 = 0.1 * torch.randn(C, device="cuda")
+y_nlc = torch.empty_like(x_nlc)
+report("lnrelu_rows NLC bf16: LayerNorm + ReLU over contiguous channels (B4, tensor-core form)", 4 * n,
+       lambda: _lib.call("wnb200_lnrelu_rows", B * T, C, ops._p(x_nlc), ops._p(g32), ops._p(b32), 1e-6, ops._p(y_nlc),
+                         ops._stream()))
+pre4 = torch.randn(B, T, 4 * C, device="cuda", dtype=bf)
+report("mu_gate_rows NLC bf16: g1 tanh(g2 h + g3 tanh(u))", 2 * n * 6,
+       lambda: _lib.call("wnb200_mu_gate_rows", B * T, C, *[ctypes.c_void_p(pre4.data_ptr() + 2 * C * u) for u in range(4)],
+                         4 * C, ops._p(x_nlc), ops._p(y_nlc), ops._stream()))
+out_ncl = torch.empty_like(x_ncl)
+parts = (ctypes.c_void_p * 1)(x_nlc.data_ptr())
+report("nlc_parts_to_ncl_add: NLC -> NCL + residual", 6 * n,
+       lambda: _lib.call("wnb200_nlc_parts_to_ncl_add", B, C, T, 1, C, parts, ops._p(x_ncl), ops._p(out_ncl), ops._stream()))
+report("ln_stats NCL bf16: per-frame mean / 1/(std+eps)", 2 * n + 8 * B * T, lambda: ops.ln_stats(x_ncl, 1e-6))
+st = ops.ln_stats(x_ncl, 1e-6)
+report("ln_relu_fwd NCL bf16 (given the statistics)", 4 * n + 8 * B * T, lambda: ops.ln_relu_fwd(x_ncl, st, g32, b32))
+dy = torch.randn_like(x_ncl)
+report("ln_relu_bwd NCL bf16: dx, dgamma, dbeta", 6 * n + 8 * B * T, lambda: ops.ln_relu_bwd(x_ncl, st, g32, b32, 1e-6, dy))

@@ -327,67 +327,88 @@ static int launch_linear(LinParams& p, cudaStream_t st) {
 // passes (mean, then the unbiased variance about it), ReLU, one 16-byte store per vector.
 constexpr int LR_MAXV = 4;
 
+// VPR = 16-byte vectors per lane and row (C <= 256 * VPR); a warp works on 4 / VPR rows at once so that every lane
+// always has 4 loads in flight (a single 512-byte row per warp left the kernel at 0.39 of the copy peak).
+template <int VPR>
 __global__ void __launch_bounds__(256) lnrelu_rows_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           float eps, __nv_bfloat16* __restrict__ y) {
+  constexpr int RPW = LR_MAXV / VPR;             // rows per warp pass
   const int lane = threadIdx.x & 31;
-  const long long row = blockIdx.x * 8ll + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const long long row0 = (blockIdx.x * 8ll + (threadIdx.x >> 5)) * RPW;
+  if (row0 >= rows) return;
   const int nvec = C >> 3;                       // 16-byte vectors per row
-  const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
   uint4 raw[LR_MAXV];
-  float s = 0.f;
+  float s[RPW], var[RPW];
 #pragma unroll
-  for (int i = 0; i < LR_MAXV; ++i) {
-    const int v = lane + 32 * i;
-    raw[i] = make_uint4(0, 0, 0, 0);
-    if (v < nvec) {
-      raw[i] = xr[v];
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+  for (int r = 0; r < RPW; ++r) {
+    s[r] = 0.f;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) s += __low2float(h[q]) + __high2float(h[q]);
+    for (int j = 0; j < VPR; ++j) {
+      const int v = lane + 32 * j;
+      const int i = r * VPR + j;
+      raw[i] = make_uint4(0, 0, 0, 0);
+      if (v < nvec && row0 + r < rows) raw[i] = reinterpret_cast<const uint4*>(x + (row0 + r) * C)[v];
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / (float)C;
-  float var = 0.f;
+  for (int r = 0; r < RPW; ++r) {
 #pragma unroll
-  for (int i = 0; i < LR_MAXV; ++i) {
-    if (lane + 32 * i < nvec) {
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+    for (int j = 0; j < VPR; ++j) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[r * VPR + j]);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float a = __low2float(h[q]) - mean, b = __high2float(h[q]) - mean;
-        var += a * a + b * b;
+      for (int q = 0; q < 4; ++q) s[r] += __low2float(h[q]) + __high2float(h[q]);      // vectors past the row hold zeros
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+    s[r] /= (float)C;
+    var[r] = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPR; ++j) {
+      if (lane + 32 * j < nvec) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[r * VPR + j]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float a = __low2float(h[q]) - s[r], b = __high2float(h[q]) - s[r];
+          var[r] += a * a + b * b;
+        }
       }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) var[r] += __shfl_xor_sync(0xffffffffu, var[r], o);
+    var[r] = 1.f / (sqrtf(var[r] / (float)(C - 1)) + eps);          // unbiased std, eps on the std (layernorm.py:27)
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-  const float r = 1.f / (sqrtf(var / (float)(C - 1)) + eps);
-  uint4* yr = reinterpret_cast<uint4*>(y + row * C);
+  for (int j = 0; j < VPR; ++j) {
+    const int v = lane + 32 * j;
+    if (v >= nvec) continue;
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8), g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + v * 8), b1 = *reinterpret_cast<const float4*>(beta + v * 8 + 4);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-  for (int i = 0; i < LR_MAXV; ++i) {
-    const int v = lane + 32 * i;
-    if (v < nvec) {
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
-      const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8), g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
-      const float4 b0 = *reinterpret_cast<const float4*>(beta + v * 8), b1 = *reinterpret_cast<const float4*>(beta + v * 8 + 4);
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    for (int r = 0; r < RPW; ++r) {
+      if (row0 + r >= rows) continue;
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[r * VPR + j]);
       uint4 o;
       __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float a = fmaxf(gg[2 * q] * (__low2float(h[q]) - mean) * r + bb[2 * q], 0.f);
-        const float b = fmaxf(gg[2 * q + 1] * (__high2float(h[q]) - mean) * r + bb[2 * q + 1], 0.f);
+        const float a = fmaxf(gg[2 * q] * (__low2float(h[q]) - s[r]) * var[r] + bb[2 * q], 0.f);
+        const float b = fmaxf(gg[2 * q + 1] * (__high2float(h[q]) - s[r]) * var[r] + bb[2 * q + 1], 0.f);
         oh[q] = __floats2bfloat162_rn(a, b);
       }
-      yr[v] = o;
+      reinterpret_cast<uint4*>(y + (row0 + r) * C)[v] = o;
     }
   }
 }
+
+__device__ __forceinline__ float bn_tanh_approx(float v) {
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float bn_sigmoid_approx(float v) { return fmaf(bn_tanh_approx(0.5f * v), 0.5f, 0.5f); }
 
 // MultiplicativeUnit gate on NLC rows: pre-activations of unit u at pre[u] + row * pitch + c (four tensors, or four
 // column blocks of one), h and out [rows, C].  8 channels per thread, 16-byte accesses.
@@ -413,11 +434,12 @@ __global__ void __launch_bounds__(256) mu_gate_rows_kernel(long long rows, int C
     const __nv_bfloat16* he = reinterpret_cast<const __nv_bfloat16*>(&hv);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const float g1 = sigmoid_precise(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(&p[0])[q]));
-      const float g2 = sigmoid_precise(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(&p[1])[q]));
-      const float g3 = sigmoid_precise(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(&p[2])[q]));
-      const float u = tanhf(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(&p[3])[q]));
-      oe[q] = __float2bfloat16_rn(g1 * tanhf(g2 * __bfloat162float(he[q]) + g3 * u));
+      // bf16 in / out: the MUFU approximations (5e-4 absolute) are below the output's rounding (4e-3 relative)
+      const float g1 = bn_sigmoid_approx(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(&p[0])[q]));
+      const float g2 = bn_sigmoid_approx(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(&p[1])[q]));
+      const float g3 = bn_sigmoid_approx(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(&p[2])[q]));
+      const float u = bn_tanh_approx(__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(&p[3])[q]));
+      oe[q] = __float2bfloat16_rn(g1 * bn_tanh_approx(g2 * __bfloat162float(he[q]) + g3 * u));
     }
     *reinterpret_cast<uint4*>(out + row * C + c) = o;
   }
@@ -462,21 +484,112 @@ __global__ void __launch_bounds__(256) nlc_parts_to_ncl_add_kernel(int C, int Tn
           v8[q] = hch ? __high2float(pr) : __low2float(pr);
         }
         if (vec) {
-          const uint4 rq = *reinterpret_cast<const uint4*>(residual + o);
+          uint4 rq = make_uint4(0, 0, 0, 0);
+          if (residual) rq = *reinterpret_cast<const uint4*>(residual + o);
           const __nv_bfloat162* re = reinterpret_cast<const __nv_bfloat162*>(&rq);
           uint4 ov;
           __nv_bfloat162* oe = reinterpret_cast<__nv_bfloat162*>(&ov);
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            oe[q] = __floats2bfloat162_rn(__low2float(re[q]) + v8[2 * q], __high2float(re[q]) + v8[2 * q + 1]);
+            oe[q] = residual ? __floats2bfloat162_rn(__low2float(re[q]) + v8[2 * q], __high2float(re[q]) + v8[2 * q + 1])
+                             : __floats2bfloat162_rn(v8[2 * q], v8[2 * q + 1]);    // pure layout change (keeps -0)
           *reinterpret_cast<uint4*>(out + o) = ov;
         } else {
           for (int q = 0; q < 8 && t0 + fv + q < Tn; ++q)
-            out[o + q] = __float2bfloat16_rn(__bfloat162float(residual[o + q]) + v8[q]);
+            out[o + q] = __float2bfloat16_rn(residual ? __bfloat162float(residual[o + q]) + v8[q] : v8[q]);
         }
       }
     }
   }
+}
+
+
+// AvgPool1d(P) fused with NCL -> NLC (classifier.py:53,102 feeding the tensor-core stack), bf16 rows that start 16-byte
+// aligned: a thread pools 8 output frames of TWO adjacent channels from P 16-byte vectors per row (eight lanes cover
+// 128 P contiguous bytes of a row), the (c, c+1) words cross the [64][33] tile and leave as 16-byte vectors of 8 channels.
+template <int P>
+__global__ void __launch_bounds__(256) avgpool_ncl_to_nlc_v3_kernel(int C, int Tn, int To, bool f16,
+                                                                    const __nv_bfloat16* __restrict__ x,
+                                                                    __nv_bfloat16* __restrict__ y) {
+  __shared__ uint32_t tile[64][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 64, t0 = blockIdx.x * 64;       // t0: pooled frames
+  const int cp = threadIdx.x >> 3, fv = (threadIdx.x & 7) * 8;
+  const float inv = 1.f / (float)P;
+  float pooled[2][8];
+#pragma unroll
+  for (int hch = 0; hch < 2; ++hch) {
+    const __nv_bfloat16* row = x + ((long long)b * C + c0 + 2 * cp + hch) * Tn + (long long)(t0 + fv) * P;
+    float v[8 * P];
+    if ((long long)(t0 + fv + 8) * P <= Tn) {
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(row) + j);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          v[8 * j + 2 * k] = __uint_as_float(w[k] << 16);
+          v[8 * j + 2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8 * P; ++i) v[i] = ((long long)(t0 + fv) * P + i < Tn) ? __bfloat162float(row[i]) : 0.f;
+    }
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < P; ++k) a += v[f * P + k];
+      pooled[hch][f] = a * inv;
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < 8; ++f) {
+    uint32_t w;
+    if (f16) {
+      const __half2 h2 = __floats2half2_rn(pooled[0][f], pooled[1][f]);
+      w = *reinterpret_cast<const uint32_t*>(&h2);
+    } else {
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(pooled[0][f], pooled[1][f]);
+      w = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+    tile[fv + f][cp] = w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = threadIdx.x; i < 64 * 8; i += 256) {
+    const int f = i >> 3, vv = i & 7;
+    if (t0 + f < To) {
+      const uint4 o = make_uint4(tile[f][4 * vv], tile[f][4 * vv + 1], tile[f][4 * vv + 2], tile[f][4 * vv + 3]);
+      *reinterpret_cast<uint4*>(y + ((long long)b * To + t0 + f) * C + c0 + 8 * vv) = o;
+    }
+  }
+}
+
+// host side of the two fast paths that other translation units route to (dense_tc.cu, chain_tc.cu)
+int avgpool_ncl_to_nlc_v3_launch(int B, int C, int T_, int pool, bool f16, const void* x, void* y, cudaStream_t st) {
+  const int To = T_ / pool;
+  dim3 grid(ceil_div(To, 64), C / 64, B);
+  const __nv_bfloat16* xs = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* ys = reinterpret_cast<__nv_bfloat16*>(y);
+  switch (pool) {
+    case 1: avgpool_ncl_to_nlc_v3_kernel<1><<<grid, 256, 0, st>>>(C, T_, To, f16, xs, ys); break;
+    case 2: avgpool_ncl_to_nlc_v3_kernel<2><<<grid, 256, 0, st>>>(C, T_, To, f16, xs, ys); break;
+    case 3: avgpool_ncl_to_nlc_v3_kernel<3><<<grid, 256, 0, st>>>(C, T_, To, f16, xs, ys); break;
+    case 4: avgpool_ncl_to_nlc_v3_kernel<4><<<grid, 256, 0, st>>>(C, T_, To, f16, xs, ys); break;
+    default: return -1;
+  }
+  return 0;
+}
+
+int nlc_to_ncl_bf16_fast_launch(int B, int C, int T_, const void* x, void* y, cudaStream_t st) {
+  PartsArgs a;
+  a.nparts = 1; a.Cp = C;
+  a.part[0] = reinterpret_cast<const __nv_bfloat16*>(x);
+  a.part[1] = a.part[2] = a.part[3] = nullptr;
+  dim3 grid(ceil_div(T_, 64), C / 64, B);
+  nlc_parts_to_ncl_add_kernel<<<grid, 256, 0, st>>>(C, T_, a, nullptr, reinterpret_cast<__nv_bfloat16*>(y));
+  return 0;
 }
 
 }  // namespace wnb
@@ -592,9 +705,13 @@ extern "C" int wnb200_lnrelu_rows(int64_t rows, int C, const void* x, const floa
   WNB_CHECK_ARG(C >= 8 && C % 8 == 0 && C <= 256 * LR_MAXV, "lnrelu_rows: C=%d must be a multiple of 8 <= %d", C, 256 * LR_MAXV);
   WNB_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) |
                   reinterpret_cast<uintptr_t>(beta)) & 15) == 0, "lnrelu_rows: pointers must be 16-byte aligned");
-  const long long ctas = (rows + 7) / 8;
+  const int vpr = C <= 256 ? 1 : (C <= 512 ? 2 : 4);
+  const long long ctas = (rows + 8 * (LR_MAXV / vpr) - 1) / (8 * (LR_MAXV / vpr));
   WNB_CHECK_ARG(ctas < (1ll << 31), "lnrelu_rows: too many rows");
-  lnrelu_rows_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(rows, C, (const bf16*)x, gamma, beta, eps, (bf16*)y);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vpr == 1) lnrelu_rows_kernel<1><<<(unsigned)ctas, 256, 0, st>>>(rows, C, (const bf16*)x, gamma, beta, eps, (bf16*)y);
+  else if (vpr == 2) lnrelu_rows_kernel<2><<<(unsigned)ctas, 256, 0, st>>>(rows, C, (const bf16*)x, gamma, beta, eps, (bf16*)y);
+  else lnrelu_rows_kernel<4><<<(unsigned)ctas, 256, 0, st>>>(rows, C, (const bf16*)x, gamma, beta, eps, (bf16*)y);
   WNB_LAUNCH_OK();
   return 0;
 }
@@ -619,7 +736,7 @@ extern "C" int wnb200_mu_gate_rows(int64_t rows, int C, const void* pre0, const 
 extern "C" int wnb200_nlc_parts_to_ncl_add(int B, int C, int T_, int nparts, int Cp, const void* const* parts,
                                            const void* residual, void* out, void* stream) {
   if (B == 0 || T_ == 0) return 0;
-  WNB_CHECK_ARG(parts && residual && out, "nlc_parts_to_ncl_add: null pointer");
+  WNB_CHECK_ARG(parts && out, "nlc_parts_to_ncl_add: null pointer");      // residual == NULL: layout change only
   WNB_CHECK_ARG(nparts >= 1 && nparts <= 4 && Cp % 64 == 0 && nparts * Cp == C, "nlc_parts_to_ncl_add: C=%d = %d x %d?", C,
                 nparts, Cp);
   WNB_CHECK_ARG(B <= 65535, "nlc_parts_to_ncl_add: batch too large");

@@ -591,12 +591,21 @@ __global__ void __launch_bounds__(256) nlc_to_ncl_kernel(int C, int Tn, const TI
 }
 }  // namespace wnb
 
+namespace wnb { int nlc_to_ncl_bf16_fast_launch(int B, int C, int T_, const void* x, void* y, cudaStream_t st); }
+
 extern "C" int wnb200_nlc_to_ncl(int out_dtype, int src_is_f32, int B, int C, int T_, const void* x, void* y,
                                  void* stream) {
   WNB_CHECK_ARG(x && y, "nlc_to_ncl: null pointer");
   if (B == 0 || C == 0 || T_ == 0) return 0;
   dim3 grid(ceil_div(T_, 64), ceil_div(C, 64), B), block(256);
   cudaStream_t st = (cudaStream_t)stream;
+  if (!src_is_f32 && out_dtype == WNB200_BF16 && C % 64 == 0 && B <= 65535 &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    // bf16 -> bf16: the word-tile kernel of bytenet.cu (two channels per word, 16-byte accesses on both sides)
+    nlc_to_ncl_bf16_fast_launch(B, C, T_, x, y, st);
+    WNB_LAUNCH_OK();
+    return 0;
+  }
   if (src_is_f32) {
     if (out_dtype == WNB200_F32) nlc_to_ncl_kernel<float, float><<<grid, block, 0, st>>>(C, T_, (const float*)x, (float*)y);
     else nlc_to_ncl_kernel<float, bf16><<<grid, block, 0, st>>>(C, T_, (const float*)x, (bf16*)y);
