@@ -335,9 +335,11 @@ __global__ void __launch_bounds__(256) lnrelu_rows_kernel(long long rows, int C,
                                                           float eps, __nv_bfloat16* __restrict__ y) {
   constexpr int RPW = LR_MAXV / VPR;             // rows per warp pass
   const int lane = threadIdx.x & 31;
+  const int nvec = C >> 3;                       // 16-byte vectors per row
+  // (one pass per warp, many short CTAs: a grid-stride loop over the row groups measured 0.52 of the copy peak against
+  // 0.72 -- the next group's loads do not start before this group's stores have been issued)
   const long long row0 = (blockIdx.x * 8ll + (threadIdx.x >> 5)) * RPW;
   if (row0 >= rows) return;
-  const int nvec = C >> 3;                       // 16-byte vectors per row
   uint4 raw[LR_MAXV];
   float s[RPW], var[RPW];
 #pragma unroll

@@ -200,6 +200,52 @@ __global__ void avgpool_fwd_kernel(long long rows, int Tn, int To, int pool, con
   }
 }
 
+// input rows 16-byte aligned: a thread pools V outputs (one 16-byte vector when the pooled rows are aligned too, element
+// stores otherwise -- T / pool is rarely a multiple of 8) from P 16-byte vectors of input
+template <typename T, int P>
+__global__ void __launch_bounds__(256) avgpool_fwd_vec_kernel(long long rows, int Tn, int To, bool out_vec,
+                                                              const T* __restrict__ x, T* __restrict__ y) {
+  constexpr int V = 16 / (int)sizeof(T);
+  const int nv = (To + V - 1) / V;
+  const long long n = rows * nv;
+  const float inv = 1.f / (float)P;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nv;
+    const int j = (int)(i - r * nv);
+    const T* xr = x + r * Tn + (long long)j * V * P;
+    float v[V * P];
+    if ((j + 1) * V * P <= Tn) {
+#pragma unroll
+      for (int q = 0; q < P; ++q) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr) + q);
+        const T* e = reinterpret_cast<const T*>(&u);
+#pragma unroll
+        for (int k = 0; k < V; ++k) v[q * V + k] = to_f32<T>(e[k]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < V * P; ++k) v[k] = (j * V * P + k < Tn) ? to_f32<T>(xr[k]) : 0.f;
+    }
+    uint4 o;
+    T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+    for (int f = 0; f < V; ++f) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < P; ++k) s += v[f * P + k];
+      oe[f] = from_f32<T>(s * inv);
+    }
+    T* yr = y + r * To + (long long)j * V;
+    if (out_vec && (j + 1) * V <= To) {
+      *reinterpret_cast<uint4*>(yr) = o;
+    } else {
+#pragma unroll
+      for (int f = 0; f < V; ++f)
+        if (j * V + f < To) yr[f] = oe[f];
+    }
+  }
+}
+
 template <typename T>
 __global__ void avgpool_bwd_kernel(long long rows, int Tn, int To, int pool, const T* dy, T* dx) {
   const long long n = rows * Tn;
@@ -673,6 +719,20 @@ extern "C" int wnb200_avgpool_fwd(int dtype, int B, int C, int T_, int pool, con
   const long long n = (long long)B * C * To;
   if (n == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    const int V = dtype == WNB200_F32 ? 4 : 8;
+    if (pool <= 4 && T_ % V == 0 && To > 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+      const long long nv = (long long)B * C * ((To + V - 1) / V);
+      const bool out_vec = To % V == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+#define AP_VEC(TT, PP) avgpool_fwd_vec_kernel<TT, PP><<<grid_for(nv), 256, 0, st>>>((long long)B * C, T_, To, out_vec, (const TT*)x, (TT*)y)
+#define AP_POOL(TT) switch (pool) { case 1: AP_VEC(TT, 1); break; case 2: AP_VEC(TT, 2); break; case 3: AP_VEC(TT, 3); break; default: AP_VEC(TT, 4); break; }
+      if (dtype == WNB200_F32) { AP_POOL(float) } else if (dtype == WNB200_BF16) { AP_POOL(bf16) } else { set_error("avgpool_fwd: bad dtype %d", dtype); return 1; }
+#undef AP_POOL
+#undef AP_VEC
+      WNB_LAUNCH_OK();
+      return 0;
+    }
+  }
   DISPATCH(dtype, "avgpool_fwd", (avgpool_fwd_kernel<T><<<grid_for(n), 256, 0, st>>>((long long)B * C, T_, To, pool,
                                                                                     (const T*)x, (T*)y)));
   WNB_LAUNCH_OK();
