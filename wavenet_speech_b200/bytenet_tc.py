@@ -5,7 +5,7 @@ tensor-core path -- every convolution is `wnb200_dense_fwd_tc` (CTA-pair tcgen05
 = the causal padding), LayerNorm + ReLU is a row kernel over a frame's contiguous channels, the MultiplicativeUnit's gate
 an elementwise row kernel, and the way back to NCL carries the block's `seq +`.  Products of bf16 operands are exact in
 the fp32 accumulator, so this is the arithmetic of the generic kernels on bf16 storage up to the bf16 rounding of the
-normalised operand (held to <= 2e-2 against the fp32 oracle on the same bf16-rounded weights, tests/test_gpu_bytenet.py).
+normalised operand (held to <= 2e-2 against an fp32 evaluation of the same bf16-rounded weights, tests/test_gpu_bytenet.py).
 Anything else (fp32, gradients, other shapes) stays on the generic kernels (functional.fused_conv)."""
 import ctypes
 
