@@ -580,7 +580,7 @@ softmax_fwd_reg(int C, int Tn, int tiles_per_read, int ntiles, const T* x, T* y,
 }
 
 template <typename T, int KC>
-__global__ void __launch_bounds__(CT_THREADS, 2)
+__global__ void __launch_bounds__(CT_THREADS, 4)
 xent_fwd_reg(int C, int Tn, int tiles_per_read, int ntiles, const T* x, const long long* target, float* loss_bt,
              float* lse_out) {
   using RT = RegTile<T, KC>;
@@ -614,19 +614,14 @@ xent_fwd_reg(int C, int Tn, int tiles_per_read, int ntiles, const T* x, const lo
 
 // LayerNorm over channels (layernorm.py:25-28: unbiased std, eps added to the std), register tile
 template <typename T, int KC>
-__global__ void __launch_bounds__(CT_THREADS, 2)
+__global__ void __launch_bounds__(CT_THREADS, 3)
 layernorm_fwd_reg(int C, int Tn, int tiles_per_read, int ntiles, const T* x, const float* gamma, const float* beta,
                   float eps, T* y, float* stats) {
   using RT = RegTile<T, KC>;
   constexpr int V = RT::V, TT = RT::TT;
   __shared__ float red[16 * TT], fin[2 * TT];
-  float gm[KC], bt[KC];
-#pragma unroll
-  for (int k = 0; k < KC; ++k) {
-    const int c = (threadIdx.x >> 3) + 32 * k;
-    gm[k] = c < C ? gamma[c] : 0.f;
-    bt[k] = c < C ? beta[c] : 0.f;
-  }
+  // (gamma / beta are read where they are used: a CTA normalises ONE tile, keeping 2 KC of them in registers from the
+  // start only cost occupancy -- 128 registers with spills, 2 CTAs per SM)
   const float invC = 1.f / (float)C, invC1 = 1.f / (float)(C - 1);
   reg_tiles<T, KC>(C, Tn, tiles_per_read, ntiles, x, 0u, [&](const RT& r, int b, int t0) {
     const long long rb = (long long)b * C * Tn;
@@ -667,7 +662,9 @@ layernorm_fwd_reg(int C, int Tn, int tiles_per_read, int ntiles, const T* x, con
       uint4 val;
       T* o = reinterpret_cast<T*>(&val);
 #pragma unroll
-      for (int i = 0; i < V; ++i) o[i] = from_f32<T>(gm[k] * (r.get(k, i) - mean[i]) * rr[i] + bt[k]);
+      const float gk = __ldg(gamma + r.g + 32 * k), bk = __ldg(beta + r.g + 32 * k);
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = from_f32<T>(gk * (r.get(k, i) - mean[i]) * rr[i] + bk);
       *reinterpret_cast<uint4*>(y + rb + (long long)(r.g + 32 * k) * Tn + t0 + r.v * V) = val;
     }
   });
