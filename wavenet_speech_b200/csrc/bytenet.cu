@@ -328,7 +328,8 @@ static int launch_linear(LinParams& p, cudaStream_t st) {
 constexpr int LR_MAXV = 4;
 
 // VPR = 16-byte vectors per lane and row (C <= 256 * VPR); a warp works on 4 / VPR rows at once so that every lane
-// always has 4 loads in flight (a single 512-byte row per warp left the kernel at 0.39 of the copy peak).
+// always has 4 loads in flight (a single 512-byte row per warp left the kernel at 0.39 of the copy peak; 8 loads per lane
+// cost the occupancy they were meant to use: 110-128 registers, 0.53).
 template <int VPR>
 __global__ void __launch_bounds__(256) lnrelu_rows_kernel(long long rows, int C, const __nv_bfloat16* __restrict__ x,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
