@@ -657,6 +657,14 @@ def main():
             "tflops_as_written": 4 * C * C * L * samples / (sk_ms * 1e-3) / 1e12,
             "tflops_executed": 2 * C * C * L * samples / (sk_ms * 1e-3) / 1e12,
             "what": "sum_l (Wbn_l Wskip_l) gate_l over K = layers x channels, accumulated in TMEM (wavenet.py:97-100)"}
+        # the residual stack as a whole (SURVEY 8d's 16 C^2 FLOP per frame and layer as written = the block launches plus
+        # the skip contraction), over the summed launch times of one pass
+        stack_ms = (float(sum(per[dom])) + float(sum(per[sk]))) / float(n_pass)
+        stack_tf = 16 * C * C * L * samples / (stack_ms * 1e-3) / 1e12
+        roofline["stack"] = {"ms_per_step": stack_ms, "tflops_as_written": stack_tf,
+                             "frac": stack_tf / peaks["bf16_tflops_sustained"],
+                             "what": "all block launches + the skip contraction of one forward against 16 C^2 FLOP per frame "
+                                     "and layer as written (block.py:54-82 + wavenet.py:100)"}
 
     input_mb = x_dev.numel() * x_dev.element_size() / 1e6
     fwd_bwd = None
