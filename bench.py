@@ -75,6 +75,12 @@ class ClockSampler(object):
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            # nvidia-smi's start-up (NVML attach) can stall the driver for tens of milliseconds: wait for its first sample
+            # so that this happens before the warm-up, never inside the timed region (measured: a 20-step region that
+            # caught it read 36-38 M samples/s instead of 46 M)
+            t_end = time.time() + 3.0
+            while not self.lines and time.time() < t_end:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
@@ -416,6 +422,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the fwd+bwd (config 3 train step) measurement")
     ap.add_argument("--e2e-chunks", type=int, default=2)
+    ap.add_argument("--no-e2e-graph", action="store_true",
+                    help="e2e: issue every chunk's ~25 launches from Python instead of replaying one CUDA graph per chunk")
     ap.add_argument("--precision", default="precise", choices=["precise", "fast"],
                     help="tensor-core activation format: precise = fp16 operands + fp16 (hi, lo) residual stream + exact "
                          "gate (meets 2e-2 at 20 blocks); fast = bf16 stream + tanh.approx (round-1 format)")
@@ -515,11 +523,19 @@ def main():
             from wavenet_speech_b200.pipeline import HostPipeline
             y_host = torch.empty(y.shape, dtype=y.dtype).pin_memory()
             del y
-            pipe = HostPipeline(net, chunks=args.e2e_chunks)     # public API: pinned host in -> pinned host out
+            pipe = HostPipeline(net, chunks=args.e2e_chunks, graph=not args.no_e2e_graph)   # public API: pinned host in -> pinned host out
             y_hosts = [y_host, torch.empty_like(y_host).pin_memory()]
+            # warm-up = the timed loop's own pattern (back-to-back submits): the caching allocator must have seen the
+            # overlap of step k's copy-out with step k+1's kernels, or it grows its pool with (synchronising) cudaMalloc
+            # calls INSIDE the timed region -- measured: e2e 21-28 M samples/s on the runs where that happened, 43-45 M
+            # otherwise, same binary, same box
             for k in range(2):
                 pipe(x_host, y_hosts[k])
+            for k in range(max(3, args.warmup) + 2):
+                pipe.submit(x_host, y_hosts[k & 1])
+            pipe.wait()
             barrier()
+            n_malloc0 = torch.cuda.memory_stats().get("num_device_alloc", 0)
             t0 = time.perf_counter()
             e0.record()
             for k in range(args.steps):                          # every step: H2D of its input, kernels, D2H of its
@@ -533,8 +549,9 @@ def main():
                    "h2d_bytes_per_step": x_host.numel() * x_host.element_size(),
                    "d2h_bytes_per_step": y_host.numel() * y_host.element_size(),
                    "ms_per_step": ms_e2e / args.steps,
-                   "api": "wavenet_speech_b200.pipeline.HostPipeline(model, chunks=%d).submit(x_pinned, y_pinned) per step, "
-                          ".wait() once at the end" % args.e2e_chunks}
+                   "cuda_mallocs_in_timed_region": torch.cuda.memory_stats().get("num_device_alloc", 0) - n_malloc0,
+                   "api": "wavenet_speech_b200.pipeline.HostPipeline(model, chunks=%d, graph=%s).submit(x_pinned, y_pinned) per "
+                          "step, .wait() once at the end" % (args.e2e_chunks, not args.no_e2e_graph)}
 
         # ---- what the HOST can deliver: every rank moves the step's bytes in and out (same pinned buffers, same two
         # copy streams) with no kernels at all.  e2e cannot be faster than this; at N = 8 it is the limiter.
@@ -572,10 +589,14 @@ def main():
         if not args.no_e2e and args.dtype == "bf16" and w["in_dim"] == w["C"] and w["C"] in (128, 256):
             from wavenet_speech_b200.pipeline import HostPipeline
             lev_host = x_host.float().argmax(1).to(torch.uint8).pin_memory()
-            pipe2 = HostPipeline(net, chunks=args.e2e_chunks, fn=net.forward_levels)
+            pipe2 = HostPipeline(net, chunks=args.e2e_chunks, fn=net.forward_levels, graph=not args.no_e2e_graph)
             for k in range(2):
                 pipe2(lev_host, y_hosts[k])
+            for k in range(max(3, args.warmup) + 2):
+                pipe2.submit(lev_host, y_hosts[k & 1])
+            pipe2.wait()
             barrier()
+            n_malloc0 = torch.cuda.memory_stats().get("num_device_alloc", 0)
             t0 = time.perf_counter()
             e0.record()
             for k in range(args.steps):
@@ -586,6 +607,7 @@ def main():
             wall_ms = (time.perf_counter() - t0) * 1e3
             ms_l = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
             e2e_levels = {"value": samples * world * args.steps / (ms_l * 1e-3), "unit": UNIT,
+                          "cuda_mallocs_in_timed_region": torch.cuda.memory_stats().get("num_device_alloc", 0) - n_malloc0,
                           "h2d_bytes_per_step": lev_host.numel(), "d2h_bytes_per_step": y_host.numel() * y_host.element_size(),
                           "ms_per_step": ms_l / args.steps,
                           "api": "HostPipeline(model, chunks=%d, fn=model.forward_levels).submit(levels_u8_pinned, y_pinned)"

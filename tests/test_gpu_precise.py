@@ -217,6 +217,38 @@ def test_host_pipeline_back_to_back_submits():
             assert torch.equal(o, d), chunks
 
 
+def test_host_pipeline_graph_replay():
+    """HostPipeline(graph=True): the chunk forward replayed as one CUDA graph per staging slot.  Different batches back
+    to back (the graph's output buffer is reused: a replay waits for the previous copy-out), ragged last chunk (runs
+    eagerly), levels in (forward_levels under capture): bit-identical to the direct calls."""
+    from wavenet_speech_b200.pipeline import HostPipeline
+    torch.manual_seed(6)
+    C = 128
+    layers = [(C, C, 2, d) for d in (1, 2, 4, 8, 16, 32)]
+    net = W.WaveNet(C, 2, layers, C, softmax=True).cuda().bfloat16().eval()
+    xs = [torch.randn(8, C, 3000).bfloat16().pin_memory() for _ in range(4)]
+    with torch.no_grad():
+        direct = [net(x.cuda()).cpu() for x in xs]
+    for chunks in (1, 2, 4, 3):                     # 3: chunks of 2, 3, 3 reads -> the first one is ragged
+        pipe = HostPipeline(net, chunks=chunks, graph=True)
+        outs = [pipe.submit(x) for x in xs]
+        pipe.wait()
+        for o, d in zip(outs, direct):
+            assert torch.equal(o, d), chunks
+        outs = [pipe.submit(x) for x in reversed(xs)]            # the captured graphs again, other data
+        pipe.wait()
+        for o, d in zip(outs, reversed(direct)):
+            assert torch.equal(o, d), chunks
+    levs = [torch.randint(0, C, (8, 3000), dtype=torch.uint8).pin_memory() for _ in range(3)]
+    with torch.no_grad():
+        direct = [net.forward_levels(l.cuda()).cpu() for l in levs]
+    pipe = HostPipeline(net, chunks=2, fn=net.forward_levels, graph=True)
+    outs = [pipe.submit(l) for l in levs]
+    pipe.wait()
+    for o, d in zip(outs, direct):
+        assert torch.equal(o, d)
+
+
 @pytest.mark.parametrize("fmt", ["fast", "precise"])
 @pytest.mark.parametrize("L,B,T,C", [(3, 2, 300, 256), (5, 1, 130, 128), (20, 1, 257, 256)])
 def test_stack_wide_skip_contraction(fmt, L, B, T, C):

@@ -13,8 +13,13 @@ class HostPipeline(object):
     """`fn` (default: the model itself) is what runs on each device chunk; `HostPipeline(net, fn=net.forward_levels)`
     streams (B, T) uint8 / integer level tensors instead of (B, 256, T) one-hot tensors: 1/512 of the bytes."""
 
-    def __init__(self, model, chunks=4, device=None, fn=None):
+    def __init__(self, model, chunks=4, device=None, fn=None, graph=False):
+        """graph=True: the forward of a (full-size) chunk is captured once per staging slot as a CUDA graph and replayed --
+        one launch per chunk instead of ~25 Python-issued ones, so the host is far ahead of the GPU from the first step
+        after a synchronisation (a 20-step timed region no longer depends on the host thread never being descheduled)."""
         self.model = model if fn is None else fn
+        self.graph = bool(graph)
+        self._graphs = {}          # staging slot -> (GraphedForward on that slot's buffer, event: its output was copied out)
         self.chunks = int(chunks)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.s_in = torch.cuda.Stream(self.device)
@@ -30,6 +35,7 @@ class HostPipeline(object):
         if self._bufs is None or self._bufs[0] != key:
             xs = [torch.empty(x_shape, dtype=x_dtype, device=self.device) for _ in range(min(n, 2))]
             self._bufs = (key, xs)
+            self._graphs = {}                    # graphs were captured on the old buffers
             # fresh blocks come from the compute stream's pool: whatever used that memory before is ordered on the
             # compute stream, so the copy stream waits for this point before its first write
             ev = torch.cuda.Event()
@@ -72,7 +78,18 @@ class HostPipeline(object):
                 xd.copy_(x_host[s:e], non_blocking=True)
                 in_done[i].record(self.s_in)
             cur.wait_event(in_done[i])
-            y = self.model(xd)
+            graphed = self.graph and (e - s) == per
+            if graphed:
+                g = self._graphs.get(slot)
+                if g is None:                    # first use of this slot: warm up + capture on the slot's own buffer
+                    g = [GraphedForward(self.model, xbuf[slot], static_input=True), None]
+                    self._graphs[slot] = g
+                if g[1] is not None:
+                    cur.wait_event(g[1])         # the graph's output buffer: its previous content has been copied out
+                g[0].graph.replay()
+                y = g[0].y
+            else:
+                y = self.model(xd)
             comp_done[i].record(cur)
             buf_free[slot] = comp_done[i]
             if y_host is None:
@@ -80,7 +97,11 @@ class HostPipeline(object):
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(comp_done[i])
                 y_host[s:e].copy_(y, non_blocking=True)
-                y.record_stream(self.s_out)
+                if graphed:
+                    g[1] = torch.cuda.Event()
+                    g[1].record(self.s_out)
+                else:
+                    y.record_stream(self.s_out)
             outs.append(y)
         return y_host
 
@@ -93,10 +114,12 @@ class GraphedForward(object):
     time point at the graph's private buffers.  `g(x)` copies x into the static input, replays, and returns the static
     output tensor (valid until the next call)."""
 
-    def __init__(self, model, example, warmup=2):
+    def __init__(self, model, example, warmup=2, static_input=False):
+        """static_input=True: `example` itself is the graph's input buffer (the caller refills it and calls
+        `self.graph.replay()`; the result is `self.y`)."""
         assert example.is_cuda, "GraphedForward needs a CUDA example input"
         self.model = model
-        self.x = example.detach().clone()
+        self.x = example if static_input else example.detach().clone()
         side = torch.cuda.Stream(example.device)
         side.wait_stream(torch.cuda.current_stream(example.device))
         with torch.cuda.stream(side), torch.no_grad():
