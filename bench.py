@@ -439,6 +439,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the fwd+bwd (config 3 train step) measurement")
     ap.add_argument("--e2e-chunks", type=int, default=2)
+    ap.add_argument("--no-graph", action="store_true",
+                    help="device-resident timing: issue the forward's launches from Python instead of one graph replay per step")
     ap.add_argument("--no-e2e-graph", action="store_true",
                     help="e2e: issue every chunk's ~25 launches from Python instead of replaying one CUDA graph per chunk")
     ap.add_argument("--precision", default="precise", choices=["precise", "fast"],
@@ -499,24 +501,50 @@ def main():
     # ---- device-resident timing ----------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
+    def graphed(tag):
+        """The forward as ONE CUDA-graph replay per step (pipeline.GraphedForward, captured on x_dev itself): a 20-step
+        region that starts from an empty launch queue otherwise depends on the Python thread issuing ~25 launches per
+        step without ever losing 50 ms (torchrun, 2 ranks: 74 M samples/s read where 93 M is the rate).  Same kernels,
+        same order; --no-graph issues them from Python."""
+        if args.no_graph:
+            return None
+        try:
+            from wavenet_speech_b200.pipeline import GraphedForward
+            return GraphedForward(net, x_dev, static_input=True)
+        except Exception as e:                                   # (a path that cannot be captured: time it eagerly)
+            sys.stderr.write("bench: %s forward not captured (%s); eager launches\n" % (tag, e))
+            return None
+
     with torch.no_grad():
         for _ in range(args.warmup):
             y = net(x_dev)
-        barrier()
+        torch.cuda.synchronize()
         l0 = _lib.launch_count
+        y = net(x_dev)
+        launches_per_forward = _lib.launch_count - l0            # our kernels in one forward (eager count)
+        gf = graphed("timed")
+        if gf is not None:
+            for _ in range(2):
+                gf.graph.replay()
+            y = gf.y
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         with quiet_gc():
             w0 = time.time()
             e0.record()
             for _ in range(args.steps):
-                y = net(x_dev)
+                if gf is not None:
+                    gf.graph.replay()
+                else:
+                    y = net(x_dev)
             e1.record()
             barrier()
         sampler.mark(w0, time.time())
         ms = max_over_ranks(e0.elapsed_time(e1))
-        launches = _lib.launch_count - l0
+        launches = launches_per_forward * args.steps             # executed inside the timed region (in the graph or not)
         clocks = sampler.stop()
+        launch_mode = "cuda graph replay (pipeline.GraphedForward), 1 launch per step" if gf is not None else "eager"
 
         # ---- the other activation format on the same input, same steps (reported under config) -----------
         other = "fast" if args.precision == "precise" else "precise"
@@ -525,13 +553,20 @@ def main():
             with W.tc_precision(other):
                 for _ in range(2):
                     net(x_dev)
+                gfo = graphed("other-format")
+                if gfo is not None:
+                    gfo.graph.replay()
                 barrier()
                 with quiet_gc():
                     e0.record()
                     for _ in range(args.steps):
-                        net(x_dev)
+                        if gfo is not None:
+                            gfo.graph.replay()
+                        else:
+                            net(x_dev)
                     e1.record()
                     barrier()
+                del gfo
             ms_o = max_over_ranks(e0.elapsed_time(e1))
             other_fmt = {"precision": other, "value": samples * world * args.steps / (ms_o * 1e-3), "unit": UNIT,
                          "ms_per_step": ms_o / args.steps}
@@ -741,6 +776,7 @@ def main():
                    "layers": len(w["dil"]), "softmax": True, "sharding": "batch x%d" % world,
                    "l2": "input %.0f MB and every inter-layer tensor exceed the 126 MB L2" % input_mb,
                    "flop_per_sample": flops_per_timestep(w),
+                   "launch": launch_mode,
                    "precision": ("precise: bf16 in/out, fp16 tensor-core operands, residual stream as an fp16 (hi, lo) pair, "
                                  "fp32 accumulation (<= 2e-2 at 20 blocks, tests/test_gpu_precise.py)") if precise else
                                 "fast: bf16 operands and residual stream, tanh.approx gate",
