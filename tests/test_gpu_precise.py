@@ -239,6 +239,20 @@ def test_host_pipeline_graph_replay():
         pipe.wait()
         for o, d in zip(outs, reversed(direct)):
             assert torch.equal(o, d), chunks
+    # new weights / another activation format after the capture: the pipeline captures again
+    pipe = HostPipeline(net, chunks=2, graph=True)
+    y_a = pipe(xs[0]).clone()
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(1.01)
+        direct_b = net(xs[0].cuda()).cpu()
+    y_b = pipe(xs[0]).clone()
+    assert torch.equal(y_b, direct_b) and not torch.equal(y_a, y_b)
+    with FP.tc_precision("fast"), torch.no_grad():
+        direct_c = net(xs[0].cuda()).cpu()
+        y_c = pipe(xs[0]).clone()
+    assert torch.equal(y_c, direct_c)
+    assert torch.equal(pipe(xs[0]), direct_b)
     levs = [torch.randint(0, C, (8, 3000), dtype=torch.uint8).pin_memory() for _ in range(3)]
     with torch.no_grad():
         direct = [net.forward_levels(l.cuda()).cpu() for l in levs]

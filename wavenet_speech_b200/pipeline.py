@@ -20,6 +20,8 @@ class HostPipeline(object):
         self.model = model if fn is None else fn
         self.graph = bool(graph)
         self._graphs = {}          # staging slot -> (GraphedForward on that slot's buffer, event: its output was copied out)
+        self._graph_key = None     # what the captured graphs depend on besides the buffers: weights, activation format
+        self._module = model if isinstance(model, torch.nn.Module) else getattr(self.model, "__self__", None)
         self.chunks = int(chunks)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.s_in = torch.cuda.Stream(self.device)
@@ -43,6 +45,14 @@ class HostPipeline(object):
             self._buf_free = [ev, ev]
         return self._bufs[1]
 
+    def _capture_key(self):
+        """A captured graph holds the weight packs and the activation format of its capture: new weights (optimiser
+        step, load_state_dict) or another `tc_precision` / `reduced_precision` setting mean a new capture."""
+        from . import fastpath
+        mod = self._module
+        wkey = None if not isinstance(mod, torch.nn.Module) else tuple((p.data_ptr(), p._version) for p in mod.parameters())
+        return (wkey, fastpath._PRECISE, fastpath._REDUCED, fastpath.HI_ONLY_TAIL)
+
     def __call__(self, x_host, y_host=None):
         """x_host: pinned CPU tensor (B, C, T).  Returns y_host (pinned CPU tensor), valid when the call returns
         (it synchronises on the last copy-out)."""
@@ -65,6 +75,10 @@ class HostPipeline(object):
         per = max(e - s for s, e in bounds)
         xbuf = self._buffers(n, (per,) + tuple(x_host.shape[1:]), x_host.dtype)
         cur = torch.cuda.current_stream(self.device)
+        if self.graph:
+            key = self._capture_key()
+            if key != self._graph_key:
+                self._graphs, self._graph_key = {}, key
         in_done = [torch.cuda.Event() for _ in range(n)]
         comp_done = [torch.cuda.Event() for _ in range(n)]
         buf_free = self._buf_free
