@@ -49,6 +49,10 @@ x_f32 = torch.randn(B, T, C, device="cuda", dtype=f32)
 d2, d3 = torch.randn_like(x_nlc), torch.randn_like(x_nlc)
 tgt = torch.randint(0, C, (B, T), device="cuda")
 
+# what a READ-ONLY pass reaches on this GPU with stock kernels (the copy peak counts a read and a write stream): torch's own
+# linear sum and its channel reduction over the same NCL tensor
+report("reference: torch.sum over 268 MB bf16 (read-only, linear)", 2 * n, lambda: x_ncl.sum())
+report("reference: torch.amax over the channels of the NCL tensor (read-only)", 2 * n, lambda: x_ncl.amax(1))
 report("ncl_to_nlc_bf16 (input layout change)", 4 * n, lambda: FP.ncl_to_nlc_bf16(x_ncl))
 report("nlc_to_ncl (output layout change)", 4 * n, lambda: FP.nlc_to_ncl(x_nlc, bf))
 report("leaky_to_bf16 (fp32 skip sum -> head input)", 6 * n, lambda: FP.leaky_to_bf16(x_f32))

@@ -10,6 +10,8 @@
 // channel count too large for an 8-frame tile falls back to the per-column kernels in elementwise.cu.
 #include <float.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace wnb {
@@ -432,6 +434,14 @@ struct RegTile {
     }
   }
   __device__ __forceinline__ float get(int k, int i) const { return to_f32<T>(reinterpret_cast<const T*>(&raw[k])[i]); }
+  // Between two passes over the tile: makes the packed registers opaque to the compiler, so that it re-unpacks them in
+  // the next pass instead of carrying 8 KC fp32 copies across (bf16 softmax: 128 registers and two CTAs per SM with the
+  // copies, three CTAs without -- these kernels are latency-bound on their loads at 16 warps per SM).
+  __device__ __forceinline__ void repack() const {
+    uint4* q = const_cast<uint4*>(raw);
+#pragma unroll
+    for (int k = 0; k < KC; ++k) asm volatile("" : "+r"(q[k].x), "+r"(q[k].y), "+r"(q[k].z), "+r"(q[k].w));
+  }
 };
 
 // One tile per CTA: tile = blockIdx.x.  (A persistent variant -- 2 CTAs per SM walking tiles with the next tile's
@@ -540,6 +550,7 @@ __device__ __forceinline__ void softmax_stats(const RegTile<T, KC>& r, float (&m
   constexpr int V = RegTile<T, KC>::V;
   tile_max(r, m);
   frames_combine<V, true>(m, red, fin, r.v);
+  r.repack();
   float ml[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) { s[i] = 0.f; ml[i] = ExpSub<T>::scale(m[i]); }
@@ -551,7 +562,7 @@ __device__ __forceinline__ void softmax_stats(const RegTile<T, KC>& r, float (&m
 }
 
 template <typename T, int KC>
-__global__ void __launch_bounds__(CT_THREADS, 2)
+__global__ void __launch_bounds__(CT_THREADS, 4)
 softmax_fwd_reg(int C, int Tn, int tiles_per_read, int ntiles, const T* x, T* y, int log_mode) {
   using RT = RegTile<T, KC>;
   constexpr int V = RT::V, TT = RT::TT;
@@ -561,6 +572,7 @@ softmax_fwd_reg(int C, int Tn, int tiles_per_read, int ntiles, const T* x, T* y,
     float m[V], sum[V];
     softmax_stats<T, KC>(r, m, sum, red, fin);
     if (!r.tok) return;
+    r.repack();
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       sum[i] = log_mode ? m[i] + logf(sum[i]) : 1.f / sum[i];
@@ -614,7 +626,7 @@ xent_fwd_reg(int C, int Tn, int tiles_per_read, int ntiles, const T* x, const lo
 
 // LayerNorm over channels (layernorm.py:25-28: unbiased std, eps added to the std), register tile
 template <typename T, int KC>
-__global__ void __launch_bounds__(CT_THREADS, 3)
+__global__ void __launch_bounds__(CT_THREADS, 4)
 layernorm_fwd_reg(int C, int Tn, int tiles_per_read, int ntiles, const T* x, const float* gamma, const float* beta,
                   float eps, T* y, float* stats) {
   using RT = RegTile<T, KC>;
@@ -633,6 +645,7 @@ layernorm_fwd_reg(int C, int Tn, int tiles_per_read, int ntiles, const T* x, con
 #pragma unroll
       for (int i = 0; i < V; ++i) mean[i] += r.get(k, i);            // channels >= C were filled with zeros
     frames_combine<V, false>(mean, red, fin, r.v);
+    r.repack();
 #pragma unroll
     for (int i = 0; i < V; ++i) { mean[i] *= invC; rr[i] = 0.f; }
 #pragma unroll
@@ -646,6 +659,7 @@ layernorm_fwd_reg(int C, int Tn, int tiles_per_read, int ntiles, const T* x, con
     }
     frames_combine<V, false>(rr, red + 8 * 8 * V, fin + 8 * V, r.v);
     if (!r.tok) return;
+    r.repack();
 #pragma unroll
     for (int i = 0; i < V; ++i) rr[i] = 1.f / (sqrtf(rr[i] * invC1) + eps);
     if (stats && r.g == 0) {
@@ -704,7 +718,7 @@ xent_bwd_reg(int C, int Tn, int tiles_per_read, const T* x, const long long* tar
 }
 
 template <typename T, int KC>
-__global__ void __launch_bounds__(CT_THREADS, 2)
+__global__ void __launch_bounds__(CT_THREADS, 4)
 argmax_reg(int C, int Tn, int tiles_per_read, int ntiles, const T* x, long long* out) {
   using RT = RegTile<T, KC>;
   constexpr int V = RT::V, TT = RT::TT;
@@ -1248,7 +1262,9 @@ extern "C" int wnb200_layernorm_bwd(int dtype, int B, int C, int T_, const void*
 extern "C" int wnb200_argmax_channels(int dtype, int B, int C, int T_, const void* x, int64_t* out, void* stream) {
   WNB_CHECK_ARG(x && out && C >= 1, "argmax_channels: bad args");
   if ((long long)B * T_ == 0) return 0;
-  if (dtype == WNB200_BF16 && C > 128 && C <= 256 && vec_ok(x, nullptr, nullptr, T_, 2) && T_ >= 1024 &&
+  // A/B switch: the 64-frame register tile at four CTAs per SM measured 0.53 of the copy peak, the wide tile 0.60
+  static const bool use_wide = getenv("WNB200_ARGMAX_NARROW") == nullptr;
+  if (use_wide && dtype == WNB200_BF16 && C > 128 && C <= 256 && vec_ok(x, nullptr, nullptr, T_, 2) && T_ >= 1024 &&
       (long long)B * ((T_ + 127) / 128) < (1LL << 31)) {
     const int tiles = (T_ + 127) / 128;
     argmax_reg_wide<16><<<(unsigned)((long long)B * tiles), CT_THREADS, 0, (cudaStream_t)stream>>>(
