@@ -685,7 +685,7 @@ layernorm_fwd_reg(int C, int Tn, int tiles_per_read, int ntiles, const T* x, con
 }
 
 template <typename T, int KC>
-__global__ void __launch_bounds__(CT_THREADS)
+__global__ void __launch_bounds__(CT_THREADS, 3)
 xent_bwd_reg(int C, int Tn, int tiles_per_read, const T* x, const long long* target, const float* lse,
              const float* gscale, T* dx) {
   using RT = RegTile<T, KC>;
@@ -862,6 +862,11 @@ struct RegTileU {
     }
   }
   __device__ __forceinline__ float get(int k, int i) const { return to_f32<T>(reinterpret_cast<const T*>(&raw[k])[i]); }
+  __device__ __forceinline__ void repack() const {        // see RegTile::repack
+    uint4* q = const_cast<uint4*>(raw);
+#pragma unroll
+    for (int k = 0; k < KC; ++k) asm volatile("" : "+r"(q[k].x), "+r"(q[k].y), "+r"(q[k].z), "+r"(q[k].w));
+  }
 };
 
 template <typename T, int KC>
@@ -910,6 +915,7 @@ __device__ __forceinline__ void softmax_stats_u(const RegTileU<T, KC>& r, const 
   constexpr int V = RegTileU<T, KC>::V;
   tile_max_u(r, m);
   frames_combine_u<V, true>(m, sl, red, fin);
+  r.repack();
   float ml[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) { s[i] = 0.f; ml[i] = ExpSub<T>::scale(m[i]); }
@@ -921,7 +927,7 @@ __device__ __forceinline__ void softmax_stats_u(const RegTileU<T, KC>& r, const 
 }
 
 template <typename T, int KC>
-__global__ void __launch_bounds__(CT_THREADS, 2)
+__global__ void __launch_bounds__(CT_THREADS, 4)
 xent_fwd_regu(int C, int Tn, int tiles_per_read, int ntiles, long long total, const T* x, const long long* target,
               float* loss_bt, float* lse_out) {
   using RT = RegTileU<T, KC>;
@@ -953,7 +959,7 @@ xent_fwd_regu(int C, int Tn, int tiles_per_read, int ntiles, long long total, co
 }
 
 template <typename T, int KC>
-__global__ void __launch_bounds__(CT_THREADS, 2)
+__global__ void __launch_bounds__(CT_THREADS, 3)
 xent_bwd_regu(int C, int Tn, int tiles_per_read, int ntiles, long long total, const T* x, const long long* target,
               const float* lse, const float* gscale, T* dx) {
   using RT = RegTileU<T, KC>;
@@ -1004,7 +1010,7 @@ xent_bwd_regu(int C, int Tn, int tiles_per_read, int ntiles, long long total, co
 }
 
 template <typename T, int KC>
-__global__ void __launch_bounds__(CT_THREADS, 2)
+__global__ void __launch_bounds__(CT_THREADS, 4)
 argmax_regu(int C, int Tn, int tiles_per_read, int ntiles, long long total, const T* x, long long* out) {
   using RT = RegTileU<T, KC>;
   constexpr int V = RT::V, TT = RT::TT, TV = RT::TV;
